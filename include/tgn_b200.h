@@ -1,0 +1,321 @@
+/*
+ * tgn_b200.h -- C-ABI of the B200 (sm_100a) TGN hot path.
+ *
+ * This is the drop-in boundary for the per-batch hot path of
+ * cseduashraful/tgb-tgn-dgl (sampler -> message aggregation -> GRU memory
+ * update -> temporal-attention embedding).  The reference has no FFI of its own
+ * (it is pure Python over torch / torch_scatter / torch_geometric / TGL's
+ * sampler_core); each entry point below names the reference call it replaces
+ * as file:line relative to the reference tree.  INTEGRATION.md shows the ctypes
+ * stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - every function returns int32_t: 0 = TGN_OK, -1 = TGN_EINVAL,
+ *     -2 = TGN_ECUDA; tgn_last_error() returns a thread-local message.
+ *   - all data pointers are DEVICE pointers owned by the caller; nothing is
+ *     allocated and the host is never synchronised inside a call.
+ *   - variable-length outputs are written into caller-sized buffers and their
+ *     element count is left in a device int32_t.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous and
+ *     may be captured into CUDA graphs.
+ *   - "count_dev" arguments (nullable) let a size be read from device memory:
+ *     when non-NULL the accompanying host count is the upper bound used for
+ *     the launch geometry and the kernel clamps to *count_dev.
+ *   - workspaces (`ws`) are caller-owned scratch; required sizes come from the
+ *     matching *_ws_bytes() helper.
+ */
+#ifndef TGN_B200_H_
+#define TGN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGN_OK 0
+#define TGN_EINVAL (-1)
+#define TGN_ECUDA (-2)
+
+#define TGN_ABI_VERSION 1
+
+/* aggregation modes (modules/msg_agg.py:15 LastAggregator, :24 MeanAggregator) */
+#define TGN_AGG_LAST 0
+#define TGN_AGG_MEAN 1
+/* t-CSR sampling strategies (config/TGN.yml:5 `strategy`) */
+#define TGN_SAMPLE_RECENT 0
+#define TGN_SAMPLE_UNIFORM 1
+/* memory updater cells (modules/memory_module.py:71-74) */
+#define TGN_CELL_GRU 0
+#define TGN_CELL_RNN 1
+
+int32_t tgn_abi_version(void);
+const char* tgn_last_error(void);
+
+/* ------------------------------------------------------------------------- *
+ * Sorted-unique + relabel by bitmap ranking.
+ * Replaces torch.cat([...]).unique() + `_assoc[n_id] = arange` at
+ * neighbor_loader.py:46-47, memory_module.py:129,153, epoch_utils.py:215.
+ * The bitmap is two-level (bit per node, bit per 1024-node group); it must be
+ * all-zero before the first mark and is left all-zero by tgn_unique_rank.
+ * ------------------------------------------------------------------------- */
+int64_t tgn_bitmap_bytes(int64_t num_nodes);
+int32_t tgn_unique_mark(const int64_t* ids, int32_t count, const int32_t* count_dev,
+                        int64_t num_nodes, void* bitmap, void* stream);
+/* out_ids[0..*out_count) ascending; assoc[id] = rank (assoc nullable). */
+int32_t tgn_unique_rank(void* bitmap, int64_t num_nodes, int64_t* out_ids, int32_t out_cap,
+                        int64_t* assoc, int32_t* out_count, void* stream);
+/* out[i] = assoc[ids[i]]   (neighbor_loader.py:48) */
+int32_t tgn_relabel(const int64_t* ids, int32_t count, const int32_t* count_dev,
+                    const int64_t* assoc, int64_t* out, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * LastNeighborLoader ring (neighbor_loader.py:15-109).
+ * State: neighbors int64 [N,K], e_id int64 [N,K] (-1 = empty), t float [N,K].
+ * ------------------------------------------------------------------------- */
+int64_t tgn_nbr_lookup_ws_bytes(int32_t num_roots, int32_t size_k);
+/* neighbor_loader.py:27-42: gather the K slots of every root, drop e_id < 0,
+ * keep root-order x slot-order.  Writes GLOBAL ids; root_off[r] = first edge of
+ * root r (root_off has num_roots+1 entries); *out_count = #edges.  When bitmap
+ * is non-NULL every emitted neighbour is also marked in it (for the union at
+ * neighbor_loader.py:46). */
+int32_t tgn_nbr_lookup(const int64_t* n_id, int32_t num_roots, const int32_t* num_roots_dev,
+                       int32_t size_k, int64_t num_nodes, const int64_t* neighbors,
+                       const int64_t* e_id, const float* t, int64_t* out_nbr,
+                       int64_t* out_centre, int64_t* out_eid, float* out_t, int32_t* root_off,
+                       int32_t* out_count, void* bitmap, void* ws, void* stream);
+/* neighbor_loader.py:52-104: append B events in both directions and keep the K
+ * largest e_id (and, independently, the K largest t) per touched node.  e_id of
+ * event i is cur_e_id + i; if cur_e_id_dev != NULL the base is read from it and
+ * the kernel advances it by B.  2*B <= TGN_SORT_MAX. */
+int32_t tgn_nbr_insert(const int64_t* src, const int64_t* dst, const float* t, int32_t batch,
+                       int64_t cur_e_id, int64_t* cur_e_id_dev, int32_t size_k,
+                       int64_t num_nodes, int64_t* neighbors, int64_t* e_id, float* t_state,
+                       void* stream);
+#define TGN_SORT_MAX 8192
+
+/* ------------------------------------------------------------------------- *
+ * TGL sampler_core.ParallelSampler over t-CSR (README.md:1-5; t-CSR file keys
+ * indptr/indices/ts/eid at utils.py:73; parameters config/TGN.yml:1-9).
+ * For every root (n, t): candidates are the row entries with
+ *   t_lo <= ts < t_hi,  t_hi = t + offset,  t_lo = (duration > 0 ? t_hi - duration : -inf)
+ * recent : the last min(k, #cand) of them, most recent first
+ * uniform: all of them if #cand <= k, else k draws with replacement
+ *          (Philox-4x32-10 keyed by seed, counter = (root index, draw)).
+ * Outputs are compact and ordered by root: nbr/eid/ts/dts[*out_count],
+ * col = root index, root_off[num_roots+1].
+ * ------------------------------------------------------------------------- */
+int64_t tgn_tcsr_sample_ws_bytes(int32_t num_roots);
+int32_t tgn_tcsr_sample(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
+                        const float* ts, int32_t num_nodes, const int32_t* root_nodes,
+                        const float* root_ts, int32_t num_roots, int32_t k, int32_t strategy,
+                        float offset, float duration, uint64_t seed, int32_t* out_nbr,
+                        int32_t* out_col, int32_t* out_eid, float* out_ts, float* out_dts,
+                        int32_t* root_off, int32_t* out_count, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Message aggregators on materialised messages.
+ * tgn_agg_last  = LastAggregator.forward   (modules/msg_agg.py:15-21):
+ *   argmax[s] = first i with index[i]==s and maximal t[i]  (M if none)
+ *   out[s,:]  = msg[argmax[s],:] or 0.
+ * tgn_agg_mean  = MeanAggregator.forward   (modules/msg_agg.py:24-26).
+ * t is int64 (t_is_float=0) or float32 (t_is_float=1).
+ * ws: 16*S bytes (last) / 4*S bytes (mean).
+ * ------------------------------------------------------------------------- */
+int32_t tgn_agg_last(const float* msg, const int64_t* index, const void* t, int32_t t_is_float,
+                     int32_t num_msgs, int32_t dim_size, int32_t width, float* out,
+                     int64_t* argmax, void* ws, void* stream);
+int32_t tgn_agg_mean(const float* msg, const int64_t* index, int32_t num_msgs,
+                     int32_t dim_size, int32_t width, float* out, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Tensorised per-node message store (replaces the Python dict at
+ * modules/memory_module.py:140-145,180-191).  Events are appended to a log;
+ * per node and per direction the store keeps the run of its events of the
+ * LAST batch it appeared in (start,count into a sorted permutation log) and
+ * the first-wins latest event of that run.
+ * ------------------------------------------------------------------------- */
+typedef struct tgn_msgstore {
+  int64_t num_nodes;
+  int64_t capacity;   /* log capacity in events */
+  int32_t raw_dim;    /* D_e */
+  int32_t t_is_float; /* dtype of ev_t: 0 int64, 1 float32 */
+  int64_t* ev_src;    /* [capacity] */
+  int64_t* ev_dst;    /* [capacity] */
+  void* ev_t;         /* [capacity] int64 or float32 */
+  float* ev_msg;      /* [capacity, raw_dim] */
+  int32_t* s_perm;    /* [capacity] log ids sorted by (src, position) per batch */
+  int32_t* d_perm;    /* [capacity] same, by dst */
+  int32_t* s_start;   /* [N] offset into s_perm */
+  int32_t* s_cnt;     /* [N] */
+  int32_t* s_last;    /* [N] log id of latest (first-wins) event, -1 if none */
+  int32_t* d_start;
+  int32_t* d_cnt;
+  int32_t* d_last;
+} tgn_msgstore;
+
+/* memory_module.py:133-134 (_update_msg_store for both directions).
+ * Appends the batch at log position `base` (host value, or read from
+ * base_dev which is then advanced by batch).  batch <= TGN_SORT_MAX. */
+int32_t tgn_msgstore_update(const tgn_msgstore* st, const int64_t* src, const int64_t* dst,
+                            const void* t, const float* raw_msg, int32_t batch, int64_t base,
+                            int64_t* base_dev, void* stream);
+/* memory_module.py:140-145 (_reset_message_store) */
+int32_t tgn_msgstore_reset(const tgn_msgstore* st, void* stream);
+
+/* Materialise the messages of nodes n_id exactly as _compute_msg does
+ * (memory_module.py:193-207) for direction dir (0 = s-store, 1 = d-store):
+ * first a counting pass, then the fill (stored tuples in store order: for the
+ * d-store the stored "src" is the event's dst).  The module-level API feeds
+ * these to the user's message module; the fused path below never materialises
+ * messages. */
+int32_t tgn_msgstore_count(const tgn_msgstore* st, const int64_t* n_id, int32_t num, int32_t dir,
+                           int32_t* offsets /* [num+1] exclusive */, void* ws, void* stream);
+int64_t tgn_msgstore_count_ws_bytes(int32_t num);
+int32_t tgn_msgstore_gather(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                            int32_t dir, const int32_t* offsets, int64_t* out_src /* [M] */,
+                            int64_t* out_dst, void* out_t /* [M] dtype of ev_t */,
+                            float* out_raw /* [M,raw_dim] */, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused message build (gather + IdentityMessage concat + TimeEncoder + Last /
+ * Mean aggregation) for nodes n_id -- memory_module.py:152-169,176 with
+ * msg_func.py:17-18 and the TimeEncoder contract (cos(w*dt+b)).
+ *   x[s,:]        = aggregated message [mem[n], mem[other], raw, cos(w*(t-lu[n])+b)]
+ *                   (zero row if the node has no stored event)
+ *   lu_out[s]     = max stored t (0 if none), in the dtype of the stored t
+ *   sel_ev[s]     = chosen log id (last mode) or -1
+ *   sel_dt[s]     = t - last_update[n] of the chosen event (for backward)
+ * ------------------------------------------------------------------------- */
+int32_t tgn_msg_build(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                      const int32_t* num_dev, int32_t agg_mode, const float* memory,
+                      const int64_t* last_update, int32_t memory_dim, const float* time_w,
+                      const float* time_b, int32_t time_dim, float* x,
+                      void* lu_out /* [num] dtype of ev_t */, int32_t* sel_ev, float* sel_dt,
+                      void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Dense fp32 building block: C[M,N] (=|+=) A[M,K] * B^T|B (+ bias).
+ * a_rows (nullable) gathers rows of A:  A_m = A_base[a_rows[m], :].
+ * trans_a: A stored [K,M]; trans_b: B stored [K,N] (else [N,K]).
+ * split_k > 1 accumulates atomically into C (C must be initialised).
+ * m_dev / k_dev (nullable) read the row count / reduction length from device.
+ * Used for the GRU gate GEMMs (torch.nn.GRUCell at memory_module.py:72,172),
+ * the TransformerConv projections (emb_module.py:21-23,29) and the decoder
+ * (decoder.py:24-27) and for their gradients.
+ * ------------------------------------------------------------------------- */
+int32_t tgn_sgemm(const float* a, const int64_t* a_rows, const float* b, const float* bias,
+                  float* c, int32_t m, const int32_t* m_dev, int32_t n, int32_t k,
+                  const int32_t* k_dev, int32_t lda, int32_t ldb, int32_t ldc, int32_t trans_a,
+                  int32_t trans_b, int32_t accumulate, int32_t split_k, void* stream);
+
+/* GRUCell / RNNCell gate math (torch.nn.GRUCell semantics, gate order r,z,n):
+ *   gi = x W_ih^T + b_ih [S,3D], gh = h W_hh^T + b_hh [S,3D]  (from tgn_sgemm)
+ *   r = sig(gi_r+gh_r), z = sig(gi_z+gh_z), n = tanh(gi_n + r*gh_n)
+ *   out = (1-z)*n + z*h ;  h = memory[h_rows[s]] (h_rows nullable -> h[s])
+ * gates (nullable) receives r,z,n,gh_n [S,4D] for the backward pass. */
+int32_t tgn_gru_gates_fwd(const float* gi, const float* gh, const float* h,
+                          const int64_t* h_rows, int32_t num, const int32_t* num_dev,
+                          int32_t dim, float* out, float* gates, void* stream);
+/* d_gi [S,3D], d_gh [S,3D] (and optional d_h [S,D]) from d_out. */
+int32_t tgn_gru_gates_bwd(const float* d_out, const float* gates, const float* h,
+                          const int64_t* h_rows, int32_t num, const int32_t* num_dev,
+                          int32_t dim, float* d_gi, float* d_gh, float* d_h, void* stream);
+int32_t tgn_rnn_gates_fwd(const float* gi, const float* gh, int32_t num, int32_t dim, float* out,
+                          void* stream);
+
+/* In-place state write (memory_module.py:147-150):
+ *   memory[n_id[s],:] = new_mem[src_rows ? src_rows[s] : s, :]; last_update likewise
+ * (new_lu is int64 or float32; float values are truncated like tensor.long()) */
+int32_t tgn_memory_scatter(const int64_t* n_id, int32_t num, const int32_t* num_dev,
+                           const float* new_mem, const void* new_lu, int32_t lu_is_float,
+                           const int64_t* src_rows, int32_t dim, float* memory,
+                           int64_t* last_update, void* stream);
+
+/* out[s,:] = table[rows[s],:]  (memory[n_id], memory_module.py:172) */
+int32_t tgn_gather_rows(const float* table, const int64_t* rows, int32_t num,
+                        const int32_t* num_dev, int32_t dim, float* out, void* stream);
+/* out[c] (+)= sum_r x[r,c]  -- bias gradients */
+int32_t tgn_colsum(const float* x, int32_t rows, const int32_t* rows_dev, int32_t cols, int32_t ld,
+                   float* out, int32_t accumulate, void* stream);
+/* TimeEncoder backward: accumulates d_w, d_b (+=) from grad[num, dim] of cos(w*t+b);
+ * rows with row_mask[i] < 0 (nullable) are skipped. */
+int32_t tgn_time_encode_bwd(const float* t, const int32_t* row_mask, int32_t num,
+                            const int32_t* num_dev, const float* w, const float* b, int32_t dim,
+                            const float* grad, int32_t ld_grad, float* d_w, float* d_b,
+                            void* stream);
+/* torch.optim.Adam step (pyg_model_utils.py:38-43 getOptimizer) over a flat
+ * parameter buffer; *step_dev (float) is the step counter, advanced by 1. */
+int32_t tgn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                      int64_t count, float lr, float beta1, float beta2, float eps,
+                      float* step_dev, void* stream);
+
+/* TimeEncoder forward: out[i,c] = cos(w[c]*t[i] + b[c]) (contract from
+ * memory_module.py:203, emb_module.py:27; DGL twin model_utils.py:223-237) */
+int32_t tgn_time_encode(const float* t, int32_t num, const float* w, const float* b,
+                        int32_t dim, float* out, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused temporal attention (GraphAttentionEmbedding.forward emb_module.py:25-29
+ * + torch_geometric TransformerConv(heads=H, concat=True, root_weight=True,
+ * edge_dim=time_dim+raw_dim, beta=False)).
+ *   proj   [Nb, 4*H*C]  = x * [Wq;Wk;Wv;Wskip]^T + bias   (from tgn_sgemm)
+ *   per edge e (j -> i): rel_t = last_update[j] - t[e]  (int64 or float32 each,
+ *     torch type promotion: int-int exact then float, otherwise float32);
+ *     ea = [cos(w*rel_t+b), msg_e];  ee = We * ea   [H*C]
+ *     a  = <q_i, k_j + ee> / sqrt(C) per head; alpha = softmax over edges of i
+ *     out_i = sum alpha * (v_j + ee) + skip_i
+ * Edges must be grouped by centre: centre c owns edges [row_ptr[c], row_ptr[c+1])
+ * listed in edge_perm (nullable = identity); centre_ids[c] (nullable = c) is the
+ * row of x/out it refers to.  msg rows come from msg[msg_rows ? msg_rows[e] : e].
+ * Rows of `out` that are not centres must be pre-filled with skip by the
+ * caller (tgn_attn_fill_skip).  alpha_out (nullable) [E,H] is kept for backward.
+ * dropout on alpha uses Philox(seed) keyed by (edge, head); p = 0 disables.
+ * ------------------------------------------------------------------------- */
+int32_t tgn_attn_fwd(const float* proj, const void* last_update_local, int32_t lu_is_float,
+                     const int64_t* nbr_local, const void* t_edge, int32_t t_is_float,
+                     const float* msg, const int64_t* msg_rows, const int32_t* row_ptr,
+                     const int32_t* edge_perm, const int64_t* centre_ids, int32_t num_centres, const int32_t* num_centres_dev, int32_t heads,
+                     int32_t head_dim, int32_t raw_dim, int32_t time_dim, const float* w_edge,
+                     const float* time_w, const float* time_b, float dropout_p, uint64_t seed,
+                     float* out, float* alpha_out, float* ee_out, void* stream);
+/* out[r,:] = proj[r, 3*H*C : 4*H*C]  for all Nb rows */
+int32_t tgn_attn_fill_skip(const float* proj, int32_t num_rows, const int32_t* num_rows_dev,
+                           int32_t hc, float* out, void* stream);
+
+/* Backward of tgn_attn_fwd.  tgn_attn_bwd_init writes d_proj = [0,0,0,d_out]
+ * (skip block) for every row; tgn_attn_bwd then adds the q/k/v blocks and
+ * writes d_ee [E,H*C] (gradient of W_edge*edge_attr).  tgn_attn_edge_attr
+ * re-materialises edge_attr [E,time_dim+raw_dim] and rel_t [E] for the W_edge
+ * and TimeEncoder gradients (rows >= *num_edges_dev are zero-filled). */
+int32_t tgn_attn_bwd_init(const float* d_out, int32_t num_rows, const int32_t* num_rows_dev,
+                          int32_t hc, float* d_proj, void* stream);
+int32_t tgn_attn_bwd(const float* proj, const int64_t* nbr_local, const int32_t* row_ptr,
+                     const int32_t* edge_perm, const int64_t* centre_ids, int32_t num_centres,
+                     const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
+                     const float* alpha, const float* ee, const float* d_out, float dropout_p,
+                     uint64_t seed, float* d_proj, float* d_ee, void* stream);
+int32_t tgn_attn_edge_attr(const void* last_update_local, int32_t lu_is_float,
+                           const int64_t* nbr_local, const void* t_edge, int32_t t_is_float,
+                           const float* msg, const int64_t* msg_rows, int32_t num_edges,
+                           const int32_t* num_edges_dev, int32_t raw_dim, int32_t time_dim,
+                           const float* time_w, const float* time_b, float* edge_attr,
+                           float* rel_t, void* stream);
+
+/* LinkPredictor forward (decoder.py:24-27) on gathered rows:
+ *   h = relu(Ws z[a] + bs + Wd z[b] + bd); score = wf . h + bf  (logit; sigmoid optional)
+ * hs/hd [Nb,C] are the per-node projections (tgn_sgemm); a/b are row ids. */
+int32_t tgn_link_score(const float* hs, const float* hd, const int64_t* a_rows,
+                       const int64_t* b_rows, int32_t num, int32_t dim, const float* w_final,
+                       const float* b_final, int32_t apply_sigmoid, float* out, void* stream);
+
+/* TGB MRR (epoch_utils.py:108-113; tgb Evaluator): per positive
+ *   rank = 1 + 0.5*(#{neg > pos} + #{neg >= pos}); rr = 1/rank */
+int32_t tgn_mrr(const float* pos, const float* neg, int32_t num_pos, int32_t num_neg,
+                float* rr_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGN_B200_H_ */

@@ -1,0 +1,218 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference files from
+/root/reference (this container only -- the GPU box has no reference tree, so
+the vectors are committed).
+
+  python tests/golden/make_golden.py
+
+What runs from the reference itself:
+  neighbor_loader.LastNeighborLoader            (imports as-is)
+  modules.msg_agg.{LastAggregator,MeanAggregator}
+  modules.msg_func.IdentityMessage
+  modules.memory_module.TGNMemory
+  modules.emb_module.GraphAttentionEmbedding
+  modules.decoder.LinkPredictor
+The last five import torch_geometric / torch_scatter / modules.time_enc, none of
+which exists here; they are satisfied with stand-in modules that re-export
+oracle/thirdparty.py (restated third-party arithmetic -- "parity unpinned" for
+that layer, see its header).  Everything the reference itself implements on top
+(message store, train/eval ordering, flush on eval, time deltas, concat order,
+edge_attr order, ...) is exercised from its own source.
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, REPO)
+
+from oracle import thirdparty as tp  # noqa: E402
+
+
+def install_stubs():
+    tg = types.ModuleType("torch_geometric")
+    tg_nn = types.ModuleType("torch_geometric.nn")
+    tg_inits = types.ModuleType("torch_geometric.nn.inits")
+    tg_utils = types.ModuleType("torch_geometric.utils")
+    ts = types.ModuleType("torch_scatter")
+    tg_nn.TransformerConv = tp.TransformerConv
+    tg_inits.zeros = tp.zeros
+    tg_utils.scatter = tp.scatter
+    ts.scatter_max = tp.scatter_max
+    tg.nn, tg.utils, tg_nn.inits = tg_nn, tg_utils, tg_inits
+    sys.modules.update({"torch_geometric": tg, "torch_geometric.nn": tg_nn,
+                        "torch_geometric.nn.inits": tg_inits, "torch_geometric.utils": tg_utils,
+                        "torch_scatter": ts})
+    sys.path.insert(0, REF)
+    te = types.ModuleType("modules.time_enc")   # file absent from the reference tree
+    te.TimeEncoder = tp.TimeEncoder
+    import modules  # the reference's package
+    sys.modules["modules.time_enc"] = te
+    modules.time_enc = te
+
+
+def sd_np(module, prefix):
+    return {f"{prefix}.{k}": v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def gen_neighbor_loader(path):
+    import contextlib
+    import io
+    from neighbor_loader import LastNeighborLoader
+    rng = np.random.default_rng(0)
+    out = {}
+    case = 0
+    for (N, K, B, steps, bip) in [(50, 4, 8, 12, True), (200, 10, 40, 10, True), (30, 3, 6, 15, False),
+                                  (64, 20, 16, 6, False)]:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ld = LastNeighborLoader(N, K, device="cpu")
+        tcur = 0.0
+        for s in range(steps):
+            # keep every node's multiplicity per batch <= K so the reference's
+            # unstable sort cannot change the result (see oracle header)
+            while True:
+                if bip:
+                    src = rng.integers(0, N // 2, B); dst = rng.integers(N // 2, N, B)
+                else:
+                    src = rng.integers(0, N, B); dst = rng.integers(0, N, B)
+                cnt = np.bincount(np.concatenate([src, dst]), minlength=N)
+                if cnt.max() <= K:
+                    break
+            t = np.sort(rng.integers(0, 50, B) + tcur).astype(np.float32); tcur = float(t[-1])
+            roots = np.unique(np.concatenate([src, dst, rng.integers(0, N, B)]))
+            n_id, ei, e_id, tt = ld(torch.from_numpy(roots))
+            pre = f"c{case}_s{s}_"
+            out[pre + "roots"] = roots
+            out[pre + "n_id"] = n_id.numpy(); out[pre + "edge_index"] = ei.numpy()
+            out[pre + "e_id"] = e_id.numpy(); out[pre + "t"] = tt.numpy()
+            out[pre + "src"] = src; out[pre + "dst"] = dst; out[pre + "tin"] = t
+            ld.insert(torch.from_numpy(src), torch.from_numpy(dst), torch.from_numpy(t))
+            # state after the insert; slots with e_id < 0 hold uninitialised neighbours in the
+            # reference (torch.empty) -> mask them
+            eid_state = ld.e_id.numpy().copy()
+            nb_state = np.where(eid_state >= 0, ld.neighbors.numpy(), 0)
+            out[pre + "state_e"] = eid_state; out[pre + "state_n"] = nb_state
+            out[pre + "state_t"] = ld.t.numpy().copy()
+        out[f"c{case}_meta"] = np.array([N, K, B, steps])
+        case += 1
+    out["num_cases"] = np.array(case)
+    np.savez_compressed(path, **out)
+
+
+def gen_aggregators(path):
+    from modules.msg_agg import LastAggregator, MeanAggregator
+    rng = np.random.default_rng(1)
+    out = {}
+    for i, (M, S, W, tmax, dt) in enumerate([(40, 12, 8, 5, "i64"), (300, 50, 472, 1000, "i64"),
+                                              (64, 70, 5, 3, "f32"), (0, 4, 6, 1, "i64")]):
+        msg = rng.standard_normal((M, W)).astype(np.float32)
+        index = rng.integers(0, S, M).astype(np.int64)
+        if i == 1:
+            index = np.sort(index)
+        t = rng.integers(0, tmax, M)
+        t = t.astype(np.int64) if dt == "i64" else t.astype(np.float32)
+        tm, ti, tt = torch.from_numpy(msg), torch.from_numpy(index), torch.from_numpy(t)
+        out[f"a{i}_msg"], out[f"a{i}_index"], out[f"a{i}_t"] = msg, index, t
+        out[f"a{i}_S"] = np.array(S)
+        out[f"a{i}_last"] = LastAggregator()(tm, ti, tt, S).numpy()
+        out[f"a{i}_mean"] = MeanAggregator()(tm, ti, tt, S).numpy()
+    out["num_cases"] = np.array(4)
+    np.savez_compressed(path, **out)
+
+
+def gen_memory(path):
+    from modules.memory_module import TGNMemory
+    from modules.msg_agg import LastAggregator, MeanAggregator
+    from modules.msg_func import IdentityMessage
+    out = {}
+    case = 0
+    for (N, De, D, B, steps, aggr, tdt) in [(40, 6, 8, 10, 6, "last", "i64"), (60, 4, 12, 16, 5, "mean", "i64"),
+                                            (300, 172, 100, 40, 5, "last", "i64")]:
+        # NB: float timestamps cannot be pinned -- the reference itself raises at
+        # memory_module.py:150 ("Index put requires the source and destination dtypes match")
+        torch.manual_seed(10 + case)
+        rng = np.random.default_rng(20 + case)
+        mem = TGNMemory(N, De, D, D, IdentityMessage(De, D, D),
+                        LastAggregator() if aggr == "last" else MeanAggregator())
+        # small time weights keep cos() well-conditioned (wiki-scale deltas are exercised on the GPU side)
+        with torch.no_grad():
+            mem.time_enc.lin.weight.mul_(0.05)
+        out.update(sd_np(mem, f"m{case}_sd"))
+        mem.train()
+        tcur = 0
+        for s in range(steps):
+            src = rng.integers(0, N // 2, B).astype(np.int64); dst = rng.integers(N // 2, N, B).astype(np.int64)
+            # distinct timestamps inside a batch (see the oracle header on sort stability)
+            t = np.sort(rng.choice(np.arange(tcur + 1, tcur + 200), B, replace=False)); tcur = int(t[-1])
+            t = t.astype(np.int64) if tdt == "i64" else t.astype(np.float32)
+            raw = rng.standard_normal((B, De)).astype(np.float32)
+            q = np.unique(np.concatenate([src, dst, rng.integers(0, N, 6)])).astype(np.int64)
+            if s == steps - 2:
+                mem.eval()       # exercises the flush (memory_module.py:209-215) and eval ordering
+            z, lu = mem(torch.from_numpy(q))
+            pre = f"m{case}_s{s}_"
+            out[pre + "q"], out[pre + "z"], out[pre + "lu"] = q, z.detach().numpy(), lu.detach().numpy()
+            out[pre + "src"], out[pre + "dst"], out[pre + "t"], out[pre + "raw"] = src, dst, t, raw
+            out[pre + "training"] = np.array(int(mem.training))
+            mem.update_state(torch.from_numpy(src), torch.from_numpy(dst), torch.from_numpy(t),
+                             torch.from_numpy(raw))
+            mem.detach()
+            out[pre + "memory"] = mem.memory.detach().numpy().copy()
+            out[pre + "last_update"] = mem.last_update.numpy().copy()
+        out[f"m{case}_meta"] = np.array([N, De, D, B, steps, 0 if aggr == "last" else 1, 0 if tdt == "i64" else 1])
+        case += 1
+    out["num_cases"] = np.array(case)
+    np.savez_compressed(path, **out)
+
+
+def gen_embedding(path):
+    from modules.emb_module import GraphAttentionEmbedding
+    from modules.decoder import LinkPredictor
+    out = {}
+    for case, (Nb, E, D, De, ludt) in enumerate([(30, 80, 8, 6, "i64"), (50, 0, 12, 4, "i64"),
+                                                 (40, 150, 100, 172, "f32")]):
+        torch.manual_seed(30 + case)
+        rng = np.random.default_rng(40 + case)
+        te = tp.TimeEncoder(D)
+        with torch.no_grad():
+            te.lin.weight.mul_(0.05)
+        gnn = GraphAttentionEmbedding(D, D, De, te).eval()
+        lp = LinkPredictor(D)
+        x = rng.standard_normal((Nb, D)).astype(np.float32)
+        lu = rng.integers(0, 500, Nb)
+        lu = lu.astype(np.int64) if ludt == "i64" else lu.astype(np.float32)
+        # edges grouped by centre the way the neighbour loader emits them; some nodes get none
+        centres = np.sort(rng.integers(0, Nb // 2, E)).astype(np.int64)
+        nbrs = rng.integers(0, Nb, E).astype(np.int64)
+        t = rng.integers(0, 500, E).astype(np.float32)
+        msg = rng.standard_normal((E, De)).astype(np.float32)
+        ei = torch.from_numpy(np.stack([nbrs, centres]))
+        z = gnn(torch.from_numpy(x), torch.from_numpy(lu), ei, torch.from_numpy(t), torch.from_numpy(msg))
+        a = rng.integers(0, Nb, 20).astype(np.int64); b = rng.integers(0, Nb, 20).astype(np.int64)
+        prob = lp(z[torch.from_numpy(a)], z[torch.from_numpy(b)])
+        pre = f"e{case}_"
+        out.update(sd_np(gnn, pre + "gnn")); out.update(sd_np(lp, pre + "lp"))
+        out[pre + "x"], out[pre + "lu"], out[pre + "edge_index"] = x, lu, ei.numpy()
+        out[pre + "t"], out[pre + "msg"], out[pre + "z"] = t, msg, z.detach().numpy()
+        out[pre + "a"], out[pre + "b"], out[pre + "prob"] = a, b, prob.detach().numpy()
+        out[pre + "meta"] = np.array([Nb, E, D, De])
+    out["num_cases"] = np.array(3)
+    np.savez_compressed(path, **out)
+
+
+if __name__ == "__main__":
+    if not os.path.isdir(REF):
+        sys.exit("reference tree not present: golden vectors can only be regenerated where /root/reference exists")
+    install_stubs()
+    gen_neighbor_loader(os.path.join(HERE, "neighbor_loader.npz"))
+    gen_aggregators(os.path.join(HERE, "aggregators.npz"))
+    gen_memory(os.path.join(HERE, "memory.npz"))
+    gen_embedding(os.path.join(HERE, "embedding.npz"))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

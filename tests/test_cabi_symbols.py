@@ -1,0 +1,64 @@
+"""CPU checks of the drop-in boundary: the shared library loads, exports every
+symbol include/tgn_b200.h declares, and argument validation answers without a GPU."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+from tgn_b200 import _cabi
+
+
+def test_header_declares_the_hot_path():
+    syms = _cabi.declared_symbols()
+    for must in ["tgn_nbr_lookup", "tgn_nbr_insert", "tgn_tcsr_sample", "tgn_agg_last", "tgn_agg_mean",
+                 "tgn_msgstore_update", "tgn_msg_build", "tgn_sgemm", "tgn_gru_gates_fwd",
+                 "tgn_gru_gates_bwd", "tgn_attn_fwd", "tgn_attn_bwd", "tgn_unique_rank", "tgn_mrr"]:
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_cabi.LIB_PATH), "libtgn_b200.so not built (run __graft_entry__.build())"
+    out = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [s for s in _cabi.declared_symbols() if s not in exported]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    extra = [s for s in exported if s.startswith("tgn_") and s not in _cabi.declared_symbols()]
+    assert not extra, f"exported but not declared: {extra}"
+
+
+def test_library_loads_and_reports_version():
+    lib = _cabi.lib()
+    assert lib.tgn_abi_version() == 1
+    assert lib.tgn_bitmap_bytes(9227) == (10 * 32 + 1) * 4   # 10 groups of 1024 nodes + 1 summary word
+    assert lib.tgn_nbr_lookup_ws_bytes(600, 10) == (3 + 1) * 8
+
+
+def test_argument_validation_needs_no_gpu():
+    lib = _cabi.lib()
+    rc = lib.tgn_nbr_insert(None, None, None, 5000, 0, None, 10, 100, None, None, None, None)
+    assert rc == _cabi.TGN_EINVAL and b"TGN_SORT_MAX" in lib.tgn_last_error()
+    rc = lib.tgn_nbr_lookup(None, 4, None, 0, 10, None, None, None, None, None, None, None, None, None,
+                            None, None, None)
+    assert rc == _cabi.TGN_EINVAL and b"size_k" in lib.tgn_last_error()
+    with pytest.raises(_cabi.TgnError):
+        _cabi.check(lib.tgn_tcsr_sample(None, None, None, None, 10, None, None, 4, 10, 7, 0.0, 0.0, 0,
+                                        None, None, None, None, None, None, None, None, None))
+
+
+def test_msgstore_struct_matches_header():
+    src = open(_cabi.HEADER).read()
+    body = src[src.index("typedef struct tgn_msgstore {"):src.index("} tgn_msgstore;")]
+    import re
+    names = re.findall(r"(\w+);", _cabi._strip_comments(body))
+    assert names == [f[0] for f in _cabi.MsgStoreStruct._fields_]
+
+
+def test_product_modules_refuse_cpu():
+    import torch
+    from neighbor_loader import LastNeighborLoader
+    with pytest.raises(RuntimeError):
+        LastNeighborLoader(10, 2, device="cpu")
+    from tgn_b200 import ops
+    with pytest.raises(_cabi.TgnError):
+        ops.agg_last(torch.zeros(2, 2), torch.zeros(2, dtype=torch.long), torch.zeros(2, dtype=torch.long), 2)

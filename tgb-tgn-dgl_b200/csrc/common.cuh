@@ -1,0 +1,169 @@
+// Shared device/host helpers for the sm_100a TGN hot-path kernels.
+// Everything in csrc/ is written for B200 (sm_100a) only; there is no CPU or
+// multi-arch fallback.  Status/err conventions follow include/tgn_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define TGN_OK 0
+#define TGN_EINVAL (-1)
+#define TGN_ECUDA (-2)
+
+namespace tgn {
+
+// thread-local last-error text, read through tgn_last_error()
+char* err_buf();
+int set_err(int code, const char* fmt, ...);
+
+#define TGN_REQUIRE(cond, ...)                         \
+  do {                                                 \
+    if (!(cond)) return ::tgn::set_err(TGN_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+#define TGN_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (expr);                                                 \
+    if (e__ != cudaSuccess)                                                   \
+      return ::tgn::set_err(TGN_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, \
+                            #expr, cudaGetErrorString(e__));                  \
+  } while (0)
+
+#define TGN_LAUNCH_CHECK()                                                    \
+  do {                                                                        \
+    cudaError_t e__ = cudaPeekAtLastError();                                  \
+    if (e__ != cudaSuccess)                                                   \
+      return ::tgn::set_err(TGN_ECUDA, "%s:%d launch -> %s", __FILE__,       \
+                            __LINE__, cudaGetErrorString(e__));               \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Grid for a grid-stride elementwise kernel: whole multiples of the SM count.
+static inline int stride_grid(long long work_items, int block, int max_waves = 8) {
+  long long blocks = (work_items + block - 1) / block;
+  if (blocks < 1) blocks = 1;
+  long long cap = (long long)kNumSMs * max_waves;
+  if (blocks > cap) blocks = cap;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming 128-bit global accesses (read-once data: keep it out of L1)
+__device__ __forceinline__ int4 ld_stream_v4(const void* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_v4(void* p, int4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
+// A device-side element count: either a host constant or a value another
+// kernel left in device memory (so a captured CUDA graph can be replayed with
+// data-dependent sizes and no host sync).
+struct DevCount {
+  const int32_t* dev;  // nullable
+  int32_t host;        // used when dev == nullptr; otherwise the upper bound
+  __device__ __forceinline__ int get() const {
+    if (dev == nullptr) return host;
+    int v = *dev;
+    return v < host ? v : host;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Single-pass chained scan across CTAs ("decoupled look-back").
+// ws[0] is the tile ticket, ws[1..] one status word per tile:
+//   bits 63..62: 0 = empty, 1 = tile aggregate, 2 = inclusive prefix
+//   bits 61..0 : value
+// The workspace must be zero when the kernel starts (the host wrapper issues a
+// cudaMemsetAsync in front of the launch).  Tiles are numbered by ticket so a
+// tile only ever waits for tiles that are already running.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int lookback_take_tile(unsigned long long* ws) {
+  __shared__ int s_tile;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(ws, 1ull);
+  __syncthreads();
+  return s_tile;
+}
+
+// Called by ONE thread of the CTA.  Returns the exclusive prefix of this tile.
+__device__ __forceinline__ long long lookback_prefix(unsigned long long* ws, int tile,
+                                                     long long tile_sum) {
+  volatile unsigned long long* st = ws + 1;
+  const unsigned long long kAgg = 1ull << 62, kInc = 2ull << 62, kMask = (1ull << 62) - 1;
+  if (tile == 0) {
+    st[0] = kInc | (unsigned long long)tile_sum;
+    return 0;
+  }
+  st[tile] = kAgg | (unsigned long long)tile_sum;
+  long long prefix = 0;
+  for (int p = tile - 1; p >= 0; --p) {
+    unsigned long long v;
+    do {
+      v = st[p];
+    } while ((v >> 62) == 0);
+    prefix += (long long)(v & kMask);
+    if ((v >> 62) == 2) break;
+  }
+  st[tile] = kInc | (unsigned long long)(prefix + tile_sum);
+  return prefix;
+}
+
+// Philox-4x32-10 counter-based RNG (Salmon et al. 2011) -- used for uniform
+// neighbour draws and attention dropout so results do not depend on the
+// launch geometry.
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ Philox(uint64_t seed)
+      : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+  __device__ __forceinline__ uint4 operator()(uint64_t ctr_lo, uint64_t ctr_hi) const {
+    uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32);
+    uint32_t c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+
+}  // namespace tgn

@@ -1,0 +1,433 @@
+// Tensorised TGN message store + fused message build.
+//
+// The reference keeps, per node, a Python dict entry holding the node's events
+// of the last batch it appeared in (modules/memory_module.py:140-145,180-191),
+// once keyed by source (msg_s_store) and once by destination (msg_d_store).
+// Here the events of every update_state() call are appended to a device log
+// (ev_src/ev_dst/ev_t/ev_msg); the batch is sorted by (node, position) in
+// shared memory and every touched node records
+//     start,count : its run inside the sorted permutation log (s_perm/d_perm)
+//     last        : the log id of its latest event, first-wins on equal t
+// which is exactly the information _compute_msg + LastAggregator/MeanAggregator
+// consume.  Entries are overwritten per batch like the dict entries are.
+//
+// Ordering note: the reference orders a node's events by torch.sort (unstable
+// for small CPU tensors).  The store fixes the order to batch position
+// (stable); this only matters for equal timestamps inside one node's run.
+#include "../../include/tgn_b200.h"
+#include "common.cuh"
+
+namespace tgn {
+
+__device__ __forceinline__ void block_bitonic_sort64(unsigned long long* s, int P) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = s[i], b = s[ixj];
+          bool asc = (i & k) == 0;
+          if ((a > b) == asc) {
+            s[i] = b;
+            s[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <typename T>
+__device__ void store_direction(const int64_t* __restrict__ key_nodes, const T* __restrict__ t,
+                                int B, int P, int64_t base, int64_t num_nodes,
+                                unsigned long long* s_key, int32_t* __restrict__ perm,
+                                int32_t* __restrict__ start, int32_t* __restrict__ cnt,
+                                int32_t* __restrict__ last) {
+  for (int j = threadIdx.x; j < P; j += blockDim.x)
+    s_key[j] = j < B ? (((unsigned long long)key_nodes[j] << 16) | (unsigned)j) : ~0ull;
+  __syncthreads();
+  block_bitonic_sort64(s_key, P);
+  for (int q = threadIdx.x; q < B; q += blockDim.x) {
+    const unsigned long long key = s_key[q];
+    const int64_t node = (int64_t)(key >> 16);
+    perm[base + q] = (int32_t)(base + (int)(key & 0xffffu));
+    const bool run_end = (q == B - 1) || ((int64_t)(s_key[q + 1] >> 16) != node);
+    if (!run_end || node < 0 || node >= num_nodes) continue;
+    // walk the run backwards: first-wins maximum of t
+    int qs = q;
+    int best = (int)(key & 0xffffu);
+    T best_t = t[best];
+    while (qs > 0 && (int64_t)(s_key[qs - 1] >> 16) == node) {
+      --qs;
+      const int j = (int)(s_key[qs] & 0xffffu);
+      const T tj = t[j];
+      if (tj >= best_t) {  // earlier position wins ties
+        best_t = tj;
+        best = j;
+      }
+    }
+    start[node] = (int32_t)(base + qs);
+    cnt[node] = q - qs + 1;
+    last[node] = (int32_t)(base + best);
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024, 1)
+    msgstore_update_kernel(tgn_msgstore st, const int64_t* __restrict__ src,
+                           const int64_t* __restrict__ dst, const T* __restrict__ t,
+                           const float* __restrict__ raw, int B, int P, int64_t base_host,
+                           int64_t* __restrict__ base_dev) {
+  extern __shared__ unsigned long long s_key[];
+  const int64_t base = base_dev ? *base_dev : base_host;
+  if (base + B > st.capacity) return;  // caller sizes the log; never write out of bounds
+  T* ev_t = reinterpret_cast<T*>(st.ev_t);
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    st.ev_src[base + i] = src[i];
+    st.ev_dst[base + i] = dst[i];
+    ev_t[base + i] = t[i];
+  }
+  const long long nraw = (long long)B * st.raw_dim;
+  float* dm = st.ev_msg + base * st.raw_dim;
+  for (long long i = threadIdx.x; i < nraw; i += blockDim.x) dm[i] = raw[i];
+  store_direction<T>(src, t, B, P, base, st.num_nodes, s_key, st.s_perm, st.s_start, st.s_cnt,
+                     st.s_last);
+  store_direction<T>(dst, t, B, P, base, st.num_nodes, s_key, st.d_perm, st.d_start, st.d_cnt,
+                     st.d_last);
+  if (base_dev && threadIdx.x == 0) *base_dev = base + B;
+}
+
+__global__ void msgstore_reset_kernel(tgn_msgstore st) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < st.num_nodes;
+       n += (int64_t)gridDim.x * blockDim.x) {
+    st.s_cnt[n] = 0;
+    st.d_cnt[n] = 0;
+    st.s_last[n] = -1;
+    st.d_last[n] = -1;
+    st.s_start[n] = 0;
+    st.d_start[n] = 0;
+  }
+}
+
+// exclusive scan of cnt[n_id[i]] with the chained-scan workspace (tile = 1024)
+__global__ void __launch_bounds__(1024)
+    msgstore_count_kernel(const int32_t* __restrict__ cnt, const int64_t* __restrict__ n_id,
+                          int num, int64_t num_nodes, int32_t* __restrict__ offsets,
+                          unsigned long long* __restrict__ ws) {
+  __shared__ int s_warp[32];
+  __shared__ long long s_prefix;
+  const int ntiles = (num + 1023) / 1024;
+  const int tile = lookback_take_tile(ws);
+  if (tile >= ntiles) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int i = tile * 1024 + tid;
+  int c = 0;
+  if (i < num) {
+    const int64_t n = n_id[i];
+    if (n >= 0 && n < num_nodes) c = cnt[n];
+  }
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  int wbase = 0, total = 0;
+  for (int w = 0; w < 32; ++w) {
+    if (w < wid) wbase += s_warp[w];
+    total += s_warp[w];
+  }
+  if (tid == 0) {
+    long long pre = lookback_prefix(ws, tile, total);
+    s_prefix = pre;
+    if (tile == ntiles - 1) offsets[num] = (int32_t)(pre + total);
+  }
+  __syncthreads();
+  if (i < num) offsets[i] = (int32_t)(s_prefix + wbase + incl - c);
+}
+
+// one warp per node: copy the node's stored tuples in store order
+template <typename T>
+__global__ void msgstore_gather_kernel(tgn_msgstore st, const int64_t* __restrict__ n_id, int num,
+                                       int dir, const int32_t* __restrict__ offsets,
+                                       int64_t* __restrict__ out_src,
+                                       int64_t* __restrict__ out_dst, T* __restrict__ out_t,
+                                       float* __restrict__ out_raw) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const T* ev_t = reinterpret_cast<const T*>(st.ev_t);
+  for (int s = blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < num;
+       s += gridDim.x * warps_per_block) {
+    const int64_t n = n_id[s];
+    if (n < 0 || n >= st.num_nodes) continue;
+    const int c = dir == 0 ? st.s_cnt[n] : st.d_cnt[n];
+    const int b = dir == 0 ? st.s_start[n] : st.d_start[n];
+    const int32_t* perm = dir == 0 ? st.s_perm : st.d_perm;
+    const int o = offsets[s];
+    for (int j = 0; j < c; ++j) {
+      const int e = perm[b + j];
+      if (lane == 0) {
+        // stored tuple is (src,dst) for the s-store and (dst,src) for the d-store
+        out_src[o + j] = dir == 0 ? st.ev_src[e] : st.ev_dst[e];
+        out_dst[o + j] = dir == 0 ? st.ev_dst[e] : st.ev_src[e];
+        out_t[o + j] = ev_t[e];
+      }
+      for (int c2 = lane; c2 < st.raw_dim; c2 += 32)
+        out_raw[(long long)(o + j) * st.raw_dim + c2] = st.ev_msg[(long long)e * st.raw_dim + c2];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Fused message build: one warp per node, lanes over the message columns.
+// x row layout = IdentityMessage (msg_func.py:17-18): [mem[n], mem[other], raw, t_enc]
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float rel_time(T t, int64_t lu);
+template <>
+__device__ __forceinline__ float rel_time<int64_t>(int64_t t, int64_t lu) {
+  return (float)(t - lu);  // int64 subtraction, then .to(float) (memory_module.py:202-203)
+}
+template <>
+__device__ __forceinline__ float rel_time<float>(float t, int64_t lu) {
+  return t - (float)lu;  // float32 - int64 promotes to float32
+}
+
+template <typename T>
+__global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_id, DevCount num,
+                                 int agg_mode, const float* __restrict__ memory,
+                                 const int64_t* __restrict__ last_update, int Dm,
+                                 const float* __restrict__ time_w,
+                                 const float* __restrict__ time_b, int Dt, float* __restrict__ x,
+                                 T* __restrict__ lu_out, int32_t* __restrict__ sel_ev,
+                                 float* __restrict__ sel_dt) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int S = num.get();
+  const int De = st.raw_dim;
+  const int W = 2 * Dm + De + Dt;
+  const T* ev_t = reinterpret_cast<const T*>(st.ev_t);
+  for (int s = blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < S;
+       s += gridDim.x * warps_per_block) {
+    const int64_t n = n_id[s];
+    float* xr = x + (long long)s * W;
+    const bool ok = n >= 0 && n < st.num_nodes;
+    const int sc = ok ? st.s_cnt[n] : 0, dc = ok ? st.d_cnt[n] : 0;
+    if (sc + dc == 0) {
+      for (int c = lane; c < W; c += 32) xr[c] = 0.f;
+      if (lane == 0) {
+        lu_out[s] = (T)0;
+        if (sel_ev) sel_ev[s] = -1;
+        if (sel_dt) sel_dt[s] = 0.f;
+      }
+      continue;
+    }
+    const int64_t lu = last_update[n];
+    const float* mn = memory + n * Dm;
+    if (agg_mode == TGN_AGG_LAST) {
+      const int es = sc > 0 ? st.s_last[n] : -1, ed = dc > 0 ? st.d_last[n] : -1;
+      T ts_ = es >= 0 ? ev_t[es] : (T)0, td_ = ed >= 0 ? ev_t[ed] : (T)0;
+      // messages of the s-store precede those of the d-store (memory_module.py:166-168):
+      // on equal t the s-store event wins
+      const bool pick_s = es >= 0 && (ed < 0 || ts_ >= td_);
+      const int e = pick_s ? es : ed;
+      const T te = pick_s ? ts_ : td_;
+      const int64_t other = pick_s ? st.ev_dst[e] : st.ev_src[e];
+      const float dt = rel_time<T>(te, lu);
+      const float* mo = memory + other * Dm;
+      const float* rw = st.ev_msg + (long long)e * De;
+      for (int c = lane; c < Dm; c += 32) {
+        xr[c] = mn[c];
+        xr[Dm + c] = mo[c];
+      }
+      for (int c = lane; c < De; c += 32) xr[2 * Dm + c] = rw[c];
+      for (int c = lane; c < Dt; c += 32)
+        xr[2 * Dm + De + c] = cosf(__fmaf_rn(dt, time_w[c], time_b[c]));
+      if (lane == 0) {
+        lu_out[s] = te;
+        if (sel_ev) sel_ev[s] = e;
+        if (sel_dt) sel_dt[s] = dt;
+      }
+    } else {
+      // mean over all stored messages, s-store first (order of msg_agg.py:26 input)
+      const float inv = 1.f / (float)(sc + dc);
+      T tmax = (T)0;
+      bool first = true;
+      for (int c0 = 0; c0 < W; c0 += 32) {
+        const int c = c0 + lane;
+        float acc = 0.f;
+        for (int dir = 0; dir < 2; ++dir) {
+          const int cnt = dir == 0 ? sc : dc;
+          const int b = dir == 0 ? st.s_start[n] : st.d_start[n];
+          const int32_t* perm = dir == 0 ? st.s_perm : st.d_perm;
+          for (int j = 0; j < cnt; ++j) {
+            const int e = perm[b + j];
+            const T te = ev_t[e];
+            if (c0 == 0) {
+              if (first || te > tmax) tmax = te;
+              first = false;
+            }
+            if (c < W) {
+              float v;
+              if (c < Dm) v = mn[c];
+              else if (c < 2 * Dm) {
+                const int64_t other = dir == 0 ? st.ev_dst[e] : st.ev_src[e];
+                v = memory[other * Dm + (c - Dm)];
+              } else if (c < 2 * Dm + De) v = st.ev_msg[(long long)e * De + (c - 2 * Dm)];
+              else {
+                const int cc = c - 2 * Dm - De;
+                v = cosf(__fmaf_rn(rel_time<T>(te, lu), time_w[cc], time_b[cc]));
+              }
+              acc += v;
+            }
+          }
+        }
+        if (c < W) xr[c] = acc * inv;
+      }
+      if (lane == 0) {
+        lu_out[s] = tmax;
+        if (sel_ev) sel_ev[s] = -1;
+        if (sel_dt) sel_dt[s] = 0.f;
+      }
+    }
+  }
+}
+
+}  // namespace tgn
+
+using namespace tgn;
+
+extern "C" {
+
+static int32_t check_store(const tgn_msgstore* st, const char* who) {
+  TGN_REQUIRE(st, "%s: store is NULL", who);
+  TGN_REQUIRE(st->num_nodes > 0 && st->capacity > 0 && st->raw_dim >= 0, "%s: bad store sizes",
+              who);
+  TGN_REQUIRE(st->capacity < (1ll << 31), "%s: log capacity must fit int32", who);
+  TGN_REQUIRE(st->ev_src && st->ev_dst && st->ev_t && (st->ev_msg || st->raw_dim == 0) &&
+                  st->s_perm && st->d_perm && st->s_start && st->s_cnt && st->s_last &&
+                  st->d_start && st->d_cnt && st->d_last,
+              "%s: store has NULL arrays", who);
+  return TGN_OK;
+}
+
+int32_t tgn_msgstore_update(const tgn_msgstore* st, const int64_t* src, const int64_t* dst,
+                            const void* t, const float* raw_msg, int32_t batch, int64_t base,
+                            int64_t* base_dev, void* stream) {
+  int32_t rc = check_store(st, "msgstore_update");
+  if (rc) return rc;
+  TGN_REQUIRE(batch >= 0 && batch <= TGN_SORT_MAX, "msgstore_update: batch %d exceeds %d", batch,
+              TGN_SORT_MAX);
+  if (batch == 0) return TGN_OK;
+  TGN_REQUIRE(src && dst && t && (raw_msg || st->raw_dim == 0), "msgstore_update: NULL input");
+  TGN_REQUIRE(base_dev || (base >= 0 && base + batch <= st->capacity),
+              "msgstore_update: log overflow (base %lld + %d > capacity %lld)", (long long)base,
+              batch, (long long)st->capacity);
+  int P = 2;
+  while (P < batch) P <<= 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TGN_CUDA(cudaFuncSetAttribute(msgstore_update_kernel<int64_t>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TGN_SORT_MAX * 8));
+    TGN_CUDA(cudaFuncSetAttribute(msgstore_update_kernel<float>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TGN_SORT_MAX * 8));
+    attr_set = true;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (st->t_is_float)
+    msgstore_update_kernel<float><<<1, 1024, (size_t)P * 8, s>>>(
+        *st, src, dst, (const float*)t, raw_msg, batch, P, base, base_dev);
+  else
+    msgstore_update_kernel<int64_t><<<1, 1024, (size_t)P * 8, s>>>(
+        *st, src, dst, (const int64_t*)t, raw_msg, batch, P, base, base_dev);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_msgstore_reset(const tgn_msgstore* st, void* stream) {
+  int32_t rc = check_store(st, "msgstore_reset");
+  if (rc) return rc;
+  msgstore_reset_kernel<<<stride_grid(st->num_nodes, 256), 256, 0, (cudaStream_t)stream>>>(*st);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int64_t tgn_msgstore_count_ws_bytes(int32_t num) {
+  if (num < 0) return 0;
+  int ntiles = num > 0 ? (num + 1023) / 1024 : 1;
+  return (int64_t)(ntiles + 1) * 8;
+}
+
+int32_t tgn_msgstore_count(const tgn_msgstore* st, const int64_t* n_id, int32_t num, int32_t dir,
+                           int32_t* offsets, void* ws, void* stream) {
+  int32_t rc = check_store(st, "msgstore_count");
+  if (rc) return rc;
+  TGN_REQUIRE(num >= 0 && offsets && ws && (dir == 0 || dir == 1), "msgstore_count: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (num == 0) {
+    TGN_CUDA(cudaMemsetAsync(offsets, 0, 4, s));
+    return TGN_OK;
+  }
+  TGN_REQUIRE(n_id, "msgstore_count: n_id is NULL");
+  const int ntiles = (num + 1023) / 1024;
+  TGN_CUDA(cudaMemsetAsync(ws, 0, (size_t)(ntiles + 1) * 8, s));
+  msgstore_count_kernel<<<ntiles, 1024, 0, s>>>(dir == 0 ? st->s_cnt : st->d_cnt, n_id, num,
+                                                st->num_nodes, offsets,
+                                                (unsigned long long*)ws);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_msgstore_gather(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                            int32_t dir, const int32_t* offsets, int64_t* out_src,
+                            int64_t* out_dst, void* out_t, float* out_raw, void* stream) {
+  int32_t rc = check_store(st, "msgstore_gather");
+  if (rc) return rc;
+  TGN_REQUIRE(num >= 0 && (dir == 0 || dir == 1), "msgstore_gather: bad arguments");
+  if (num == 0) return TGN_OK;
+  TGN_REQUIRE(n_id && offsets && out_src && out_dst && out_t && (out_raw || st->raw_dim == 0),
+              "msgstore_gather: NULL pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = stride_grid((long long)num * 32, 256);
+  if (st->t_is_float)
+    msgstore_gather_kernel<float><<<grid, 256, 0, s>>>(*st, n_id, num, dir, offsets, out_src,
+                                                       out_dst, (float*)out_t, out_raw);
+  else
+    msgstore_gather_kernel<int64_t><<<grid, 256, 0, s>>>(*st, n_id, num, dir, offsets, out_src,
+                                                         out_dst, (int64_t*)out_t, out_raw);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_msg_build(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                      const int32_t* num_dev, int32_t agg_mode, const float* memory,
+                      const int64_t* last_update, int32_t memory_dim, const float* time_w,
+                      const float* time_b, int32_t time_dim, float* x, void* lu_out,
+                      int32_t* sel_ev, float* sel_dt, void* stream) {
+  int32_t rc = check_store(st, "msg_build");
+  if (rc) return rc;
+  TGN_REQUIRE(num >= 0 && memory_dim >= 1 && time_dim >= 0, "msg_build: bad sizes");
+  TGN_REQUIRE(agg_mode == TGN_AGG_LAST || agg_mode == TGN_AGG_MEAN, "msg_build: bad agg_mode");
+  if (num == 0) return TGN_OK;
+  TGN_REQUIRE(n_id && memory && last_update && x && lu_out && (time_dim == 0 || (time_w && time_b)),
+              "msg_build: NULL pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  DevCount c{num_dev, num};
+  const int grid = stride_grid((long long)num * 32, 256);
+  if (st->t_is_float)
+    msg_build_kernel<float><<<grid, 256, 0, s>>>(*st, n_id, c, agg_mode, memory, last_update,
+                                                 memory_dim, time_w, time_b, time_dim, x,
+                                                 (float*)lu_out, sel_ev, sel_dt);
+  else
+    msg_build_kernel<int64_t><<<grid, 256, 0, s>>>(*st, n_id, c, agg_mode, memory, last_update,
+                                                   memory_dim, time_w, time_b, time_dim, x,
+                                                   (int64_t*)lu_out, sel_ev, sel_dt);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+}  // extern "C"

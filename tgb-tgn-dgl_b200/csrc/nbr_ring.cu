@@ -1,0 +1,277 @@
+// LastNeighborLoader ring on the GPU (reference neighbor_loader.py:15-109).
+//
+// State (caller-owned, same layout and dtypes as the reference's tensors):
+//   neighbors int64 [N,K], e_id int64 [N,K] (-1 = empty slot), t float [N,K]
+//
+// lookup : one pass over the K slots of every root.  The (root, slot) pairs of
+//          a tile are flattened over the CTA so every lane carries a pair and
+//          the loads of one row are contiguous; valid pairs are compacted in
+//          (root order x slot order) with warp ballots + a chained scan across
+//          CTAs, so the kernel reads every slot exactly once and writes every
+//          output exactly once.
+// insert : single CTA; the 2B (node, position) keys are sorted in shared
+//          memory (bitonic, stable because the position is part of the key),
+//          the thread at the end of each node run merges the last <=K new
+//          events with the node's old row.
+#include "../../include/tgn_b200.h"
+#include "common.cuh"
+
+namespace tgn {
+
+constexpr int kLookupThreads = 256;
+constexpr int kLookupPairsPerThread = 8;
+constexpr int kLookupTilePairs = kLookupThreads * kLookupPairsPerThread;  // 2048
+constexpr int kMaxK = 64;
+
+__global__ void __launch_bounds__(kLookupThreads)
+    nbr_lookup_kernel(const int64_t* __restrict__ n_id, DevCount roots, int K, int tile_roots,
+                      int64_t num_nodes, const int64_t* __restrict__ nbrs,
+                      const int64_t* __restrict__ eids, const float* __restrict__ ts,
+                      int64_t* __restrict__ out_nbr, int64_t* __restrict__ out_ctr,
+                      int64_t* __restrict__ out_eid, float* __restrict__ out_t,
+                      int32_t* __restrict__ root_off, int32_t* __restrict__ out_count,
+                      uint32_t* __restrict__ l0, uint32_t* __restrict__ l1,
+                      unsigned long long* __restrict__ ws) {
+  __shared__ int s_warp_tot[kLookupThreads / 32];
+  __shared__ long long s_tile_prefix;
+  const int R = roots.get();
+  const int ntiles = (R + tile_roots - 1) / tile_roots;
+  const int tile = lookback_take_tile(ws);
+  if (tile >= (ntiles > 0 ? ntiles : 1)) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int r0 = tile * tile_roots;
+  const int nr = min(tile_roots, R - r0);
+  const int npairs = nr > 0 ? nr * K : 0;
+
+  int64_t v_e[kLookupPairsPerThread], v_n[kLookupPairsPerThread], v_c[kLookupPairsPerThread];
+  float v_t[kLookupPairsPerThread];
+  unsigned ball[kLookupPairsPerThread];
+  int wtot = 0;
+#pragma unroll
+  for (int j = 0; j < kLookupPairsPerThread; ++j) {
+    const int p = wid * (32 * kLookupPairsPerThread) + j * 32 + lane;
+    bool valid = false;
+    v_e[j] = -1;
+    if (p < npairs) {
+      const int r = p / K, slot = p - r * K;
+      const int64_t c = n_id[r0 + r];
+      v_c[j] = c;
+      if (c >= 0 && c < num_nodes) {
+        const int64_t at = c * K + slot;
+        v_e[j] = eids[at];
+        v_n[j] = nbrs[at];
+        v_t[j] = ts[at];
+        valid = v_e[j] >= 0;
+      }
+    }
+    ball[j] = __ballot_sync(0xffffffffu, valid);
+    wtot += __popc(ball[j]);
+  }
+  if (lane == 0) s_warp_tot[wid] = wtot;
+  __syncthreads();
+  if (tid == 0) {
+    long long tot = 0;
+#pragma unroll
+    for (int w = 0; w < kLookupThreads / 32; ++w) tot += s_warp_tot[w];
+    long long pre = lookback_prefix(ws, tile, tot);
+    s_tile_prefix = pre;
+    if (tile == (ntiles > 0 ? ntiles : 1) - 1) {
+      root_off[R] = (int32_t)(pre + tot);
+      *out_count = (int32_t)(pre + tot);
+    }
+  }
+  __syncthreads();
+  long long base = s_tile_prefix;
+  for (int w = 0; w < wid; ++w) base += s_warp_tot[w];
+#pragma unroll
+  for (int j = 0; j < kLookupPairsPerThread; ++j) {
+    const int p = wid * (32 * kLookupPairsPerThread) + j * 32 + lane;
+    const long long pos = base + __popc(ball[j] & lanemask_lt());
+    if (p < npairs) {
+      const int r = p / K, slot = p - r * K;
+      if (slot == 0) root_off[r0 + r] = (int32_t)pos;
+      if ((ball[j] >> lane) & 1u) {
+        out_nbr[pos] = v_n[j];
+        out_ctr[pos] = v_c[j];
+        out_eid[pos] = v_e[j];
+        out_t[pos] = v_t[j];
+        if (l0) {
+          const int64_t id = v_n[j];
+          if (id >= 0 && id < num_nodes) {
+            uint32_t old = atomicOr(&l0[id >> 5], 1u << (id & 31));
+            if (old == 0) {
+              int64_t g = id >> 10;
+              atomicOr(&l1[g >> 5], 1u << (g & 31));
+            }
+          }
+        }
+      }
+    }
+    base += __popc(ball[j]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// insert
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void block_bitonic_sort(unsigned long long* s, int P) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = s[i], b = s[ixj];
+          bool asc = (i & k) == 0;
+          if ((a > b) == asc) {
+            s[i] = b;
+            s[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+    nbr_insert_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                      const float* __restrict__ t, int B, int P, int64_t cur_host,
+                      int64_t* __restrict__ cur_dev, int K, int64_t num_nodes,
+                      int64_t* __restrict__ nbrs, int64_t* __restrict__ eids,
+                      float* __restrict__ ts) {
+  extern __shared__ unsigned long long s_key[];
+  const int n = 2 * B;
+  const int64_t cur = cur_dev ? *cur_dev : cur_host;
+  // nodes = cat[dst, src] (neighbor_loader.py:58): entry j < B is centred on dst[j]
+  for (int j = threadIdx.x; j < P; j += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (j < n) {
+      int64_t node = j < B ? dst[j] : src[j - B];
+      key = ((unsigned long long)node << 16) | (unsigned)j;
+    }
+    s_key[j] = key;
+  }
+  __syncthreads();
+  block_bitonic_sort(s_key, P);
+  for (int q = threadIdx.x; q < n; q += blockDim.x) {
+    const unsigned long long key = s_key[q];
+    const int64_t node = (int64_t)(key >> 16);
+    const bool run_end = (q == n - 1) || ((int64_t)(s_key[q + 1] >> 16) != node);
+    if (!run_end || node < 0 || node >= num_nodes) continue;
+    // candidates: old row (K) + the last <=K entries of the run
+    int64_t ce[2 * kMaxK], cn[2 * kMaxK];
+    float ct[2 * kMaxK];
+    int m = 0;
+    for (int s = 0; s < K; ++s) {
+      ce[m] = eids[node * K + s];
+      cn[m] = nbrs[node * K + s];
+      ct[m] = ts[node * K + s];
+      ++m;
+    }
+    int taken = 0;
+    for (int i = 0; i < K && q - i >= 0; ++i) {
+      const unsigned long long kq = s_key[q - i];
+      if ((int64_t)(kq >> 16) != node) break;
+      const int j = (int)(kq & 0xffffu);
+      const int ev = j < B ? j : j - B;
+      ce[m] = cur + ev;
+      cn[m] = j < B ? src[ev] : dst[ev];
+      ct[m] = t[ev];
+      ++m;
+      ++taken;
+    }
+    // the dense [n,K] block of the reference is padded with -1 (neighbor_loader.py:77-82)
+    const int n_fill = K - taken;
+    // top-K of e_id, descending (neighbor_loader.py:99) -- selection sort on the prefix
+    for (int a = 0; a < K; ++a) {
+      int best = a;
+      for (int b = a + 1; b < m; ++b)
+        if (ce[b] > ce[best]) best = b;
+      int64_t te = ce[a]; ce[a] = ce[best]; ce[best] = te;
+      int64_t tn = cn[a]; cn[a] = cn[best]; cn[best] = tn;
+      // t is ranked independently below, keep ct aligned with its own values only
+    }
+    // top-K of t, descending, independent of e_id (neighbor_loader.py:100)
+    float tt[3 * kMaxK];
+    for (int a = 0; a < m; ++a) tt[a] = ct[a];
+    int mt = m;
+    for (int a = 0; a < n_fill; ++a) tt[mt++] = -1.0f;
+    for (int a = 0; a < K; ++a) {
+      int best = a;
+      for (int b = a + 1; b < mt; ++b)
+        if (tt[b] > tt[best]) best = b;
+      float x = tt[a]; tt[a] = tt[best]; tt[best] = x;
+    }
+    for (int s = 0; s < K; ++s) {
+      eids[node * K + s] = ce[s];
+      nbrs[node * K + s] = cn[s];
+      ts[node * K + s] = tt[s];
+    }
+  }
+  __syncthreads();
+  if (cur_dev && threadIdx.x == 0) *cur_dev = cur + B;
+}
+
+}  // namespace tgn
+
+using namespace tgn;
+
+extern "C" {
+
+static inline int lookup_tile_roots(int K) { return kLookupTilePairs / K; }
+
+int64_t tgn_nbr_lookup_ws_bytes(int32_t num_roots, int32_t size_k) {
+  if (size_k < 1 || size_k > kMaxK || num_roots < 0) return 0;
+  int tr = lookup_tile_roots(size_k);
+  int ntiles = num_roots > 0 ? (num_roots + tr - 1) / tr : 1;
+  return (int64_t)(ntiles + 1) * 8;
+}
+
+int32_t tgn_nbr_lookup(const int64_t* n_id, int32_t num_roots, const int32_t* num_roots_dev,
+                       int32_t size_k, int64_t num_nodes, const int64_t* neighbors,
+                       const int64_t* e_id, const float* t, int64_t* out_nbr,
+                       int64_t* out_centre, int64_t* out_eid, float* out_t, int32_t* root_off,
+                       int32_t* out_count, void* bitmap, void* ws, void* stream) {
+  TGN_REQUIRE(size_k >= 1 && size_k <= kMaxK, "nbr_lookup: size_k must be in [1,%d]", kMaxK);
+  TGN_REQUIRE(num_roots >= 0 && num_nodes > 0, "nbr_lookup: bad sizes");
+  TGN_REQUIRE(neighbors && e_id && t && root_off && out_count && ws, "nbr_lookup: NULL pointer");
+  TGN_REQUIRE(num_roots == 0 || (n_id && out_nbr && out_centre && out_eid && out_t),
+              "nbr_lookup: NULL buffer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int tr = lookup_tile_roots(size_k);
+  const int ntiles = num_roots > 0 ? (num_roots + tr - 1) / tr : 1;
+  TGN_CUDA(cudaMemsetAsync(ws, 0, (size_t)(ntiles + 1) * 8, s));
+  uint32_t* l0 = (uint32_t*)bitmap;
+  uint32_t* l1 = l0 ? l0 + ((num_nodes + 1023) / 1024) * 32 : nullptr;
+  DevCount rc{num_roots_dev, num_roots};
+  nbr_lookup_kernel<<<ntiles, kLookupThreads, 0, s>>>(
+      n_id, rc, size_k, tr, num_nodes, neighbors, e_id, t, out_nbr, out_centre, out_eid, out_t,
+      root_off, out_count, l0, l1, (unsigned long long*)ws);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_nbr_insert(const int64_t* src, const int64_t* dst, const float* t, int32_t batch,
+                       int64_t cur_e_id, int64_t* cur_e_id_dev, int32_t size_k,
+                       int64_t num_nodes, int64_t* neighbors, int64_t* e_id, float* t_state,
+                       void* stream) {
+  TGN_REQUIRE(size_k >= 1 && size_k <= kMaxK, "nbr_insert: size_k must be in [1,%d]", kMaxK);
+  TGN_REQUIRE(batch >= 0 && 2 * (int64_t)batch <= TGN_SORT_MAX,
+              "nbr_insert: 2*batch=%lld exceeds TGN_SORT_MAX=%d", 2ll * batch, TGN_SORT_MAX);
+  if (batch == 0) return TGN_OK;
+  TGN_REQUIRE(src && dst && t && neighbors && e_id && t_state, "nbr_insert: NULL pointer");
+  int P = 2;
+  while (P < 2 * batch) P <<= 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TGN_CUDA(cudaFuncSetAttribute(nbr_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TGN_SORT_MAX * 8));
+    attr_set = true;
+  }
+  nbr_insert_kernel<<<1, 1024, (size_t)P * 8, (cudaStream_t)stream>>>(
+      src, dst, t, batch, P, cur_e_id, cur_e_id_dev, size_k, num_nodes, neighbors, e_id, t_state);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+}  // extern "C"

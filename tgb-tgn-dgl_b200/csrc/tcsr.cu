@@ -1,0 +1,169 @@
+// Temporal neighbour sampling over a t-CSR graph (TGL sampler_core semantics;
+// the reference names it at README.md:1-5, the t-CSR keys at utils.py:73 and
+// the parameters at config/TGN.yml:1-9 -- its C++ source is not part of the
+// reference tree, see SURVEY.md B1 for the restated algorithm).
+//
+// One CTA handles a tile of 256 roots:
+//   phase 1  one thread per root: binary search of the timestamp-sorted row for
+//            the candidate window [lo, hi)  (256 independent searches per CTA
+//            keep the memory system busy; a search is a dependent chain)
+//   phase 2  block scan of the per-root output counts + chained scan across
+//            CTAs -> exact output offsets, outputs stay ordered by root
+//   phase 3  the tile's outputs are flattened over the CTA: every lane emits
+//            one sampled neighbour (coalesced stores, near-contiguous loads
+//            because a root's most recent entries are adjacent in the row)
+#include "../../include/tgn_b200.h"
+#include "common.cuh"
+
+namespace tgn {
+
+constexpr int kTcsrTile = 256;
+
+__device__ __forceinline__ int lower_bound_f(const float* __restrict__ ts, int lo, int hi,
+                                             float key) {
+  // first index in [lo,hi) with ts[idx] >= key
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(ts + mid) < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kTcsrTile)
+    tcsr_sample_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                       const int32_t* __restrict__ eid, const float* __restrict__ ts,
+                       int num_nodes, const int32_t* __restrict__ root_nodes,
+                       const float* __restrict__ root_ts, int R, int k, int strategy,
+                       float offset, float duration, uint64_t seed,
+                       int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_col,
+                       int32_t* __restrict__ out_eid, float* __restrict__ out_ts,
+                       float* __restrict__ out_dts, int32_t* __restrict__ root_off,
+                       int32_t* __restrict__ out_count, unsigned long long* __restrict__ ws) {
+  __shared__ int s_lo[kTcsrTile], s_hi[kTcsrTile], s_pref[kTcsrTile + 1];
+  __shared__ float s_t[kTcsrTile];
+  __shared__ int s_warp[kTcsrTile / 32];
+  __shared__ long long s_tile_prefix;
+  const int ntiles = (R + kTcsrTile - 1) / kTcsrTile;
+  const int tile = lookback_take_tile(ws);
+  if (tile >= ntiles) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int gi = tile * kTcsrTile + tid;
+
+  // phase 1
+  int lo = 0, hi = 0;
+  float tr = 0.f;
+  if (gi < R) {
+    const int n = root_nodes[gi];
+    tr = root_ts[gi];
+    if (n >= 0 && n < num_nodes) {
+      const int rs = __ldg(indptr + n), re = __ldg(indptr + n + 1);
+      const float t_hi = tr + offset;
+      hi = lower_bound_f(ts, rs, re, t_hi);
+      lo = duration > 0.f ? lower_bound_f(ts, rs, hi, t_hi - duration) : rs;
+    }
+  }
+  const int cand = hi - lo;
+  const int cnt = cand < k ? cand : k;
+  s_lo[tid] = lo;
+  s_hi[tid] = hi;
+  s_t[tid] = tr;
+
+  // phase 2: block exclusive scan of cnt
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  int wbase = 0;
+  for (int w = 0; w < wid; ++w) wbase += s_warp[w];
+  s_pref[tid] = wbase + incl - cnt;
+  if (tid == kTcsrTile - 1) s_pref[kTcsrTile] = wbase + incl;
+  __syncthreads();
+  const int tile_total = s_pref[kTcsrTile];
+  if (tid == 0) {
+    long long pre = lookback_prefix(ws, tile, tile_total);
+    s_tile_prefix = pre;
+    if (tile == ntiles - 1) {
+      root_off[R] = (int32_t)(pre + tile_total);
+      *out_count = (int32_t)(pre + tile_total);
+    }
+  }
+  __syncthreads();
+  const long long base = s_tile_prefix;
+  if (gi < R) root_off[gi] = (int32_t)(base + s_pref[tid]);
+
+  // phase 3: flattened emit
+  Philox rng(seed);
+  for (int q = tid; q < tile_total; q += kTcsrTile) {
+    int a = 0, b = kTcsrTile;  // largest r with s_pref[r] <= q
+    while (b - a > 1) {
+      int mid = (a + b) >> 1;
+      if (s_pref[mid] <= q) a = mid;
+      else b = mid;
+    }
+    const int r = a, j = q - s_pref[r];
+    const int rlo = s_lo[r], rhi = s_hi[r];
+    const int rc = rhi - rlo;
+    int idx;
+    if (strategy == TGN_SAMPLE_RECENT || rc <= k) {
+      idx = rhi - 1 - j;
+    } else {
+      uint4 x = rng((uint64_t)(tile * kTcsrTile + r), (uint64_t)j);
+      idx = rlo + (int)(x.x % (uint32_t)rc);
+    }
+    const float tj = __ldg(ts + idx);
+    const long long o = base + q;
+    out_nbr[o] = __ldg(indices + idx);
+    out_eid[o] = __ldg(eid + idx);
+    out_ts[o] = tj;
+    out_dts[o] = s_t[r] - tj;
+    out_col[o] = tile * kTcsrTile + r;
+  }
+}
+
+}  // namespace tgn
+
+using namespace tgn;
+
+extern "C" {
+
+int64_t tgn_tcsr_sample_ws_bytes(int32_t num_roots) {
+  if (num_roots < 0) return 0;
+  int ntiles = num_roots > 0 ? (num_roots + kTcsrTile - 1) / kTcsrTile : 1;
+  return (int64_t)(ntiles + 1) * 8;
+}
+
+int32_t tgn_tcsr_sample(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
+                        const float* ts, int32_t num_nodes, const int32_t* root_nodes,
+                        const float* root_ts, int32_t num_roots, int32_t k, int32_t strategy,
+                        float offset, float duration, uint64_t seed, int32_t* out_nbr,
+                        int32_t* out_col, int32_t* out_eid, float* out_ts, float* out_dts,
+                        int32_t* root_off, int32_t* out_count, void* ws, void* stream) {
+  TGN_REQUIRE(num_roots >= 0 && num_nodes > 0 && k >= 1, "tcsr_sample: bad sizes");
+  TGN_REQUIRE(strategy == TGN_SAMPLE_RECENT || strategy == TGN_SAMPLE_UNIFORM,
+              "tcsr_sample: unknown strategy %d", strategy);
+  TGN_REQUIRE(indptr && indices && eid && ts && root_off && out_count && ws,
+              "tcsr_sample: NULL pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (num_roots == 0) {
+    TGN_CUDA(cudaMemsetAsync(root_off, 0, 4, s));
+    TGN_CUDA(cudaMemsetAsync(out_count, 0, 4, s));
+    return TGN_OK;
+  }
+  TGN_REQUIRE(root_nodes && root_ts && out_nbr && out_col && out_eid && out_ts && out_dts,
+              "tcsr_sample: NULL buffer");
+  const int ntiles = (num_roots + kTcsrTile - 1) / kTcsrTile;
+  TGN_CUDA(cudaMemsetAsync(ws, 0, (size_t)(ntiles + 1) * 8, s));
+  tcsr_sample_kernel<<<ntiles, kTcsrTile, 0, s>>>(
+      indptr, indices, eid, ts, num_nodes, root_nodes, root_ts, num_roots, k, strategy, offset,
+      duration, seed, out_nbr, out_col, out_eid, out_ts, out_dts, root_off, out_count,
+      (unsigned long long*)ws);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+}  // extern "C"

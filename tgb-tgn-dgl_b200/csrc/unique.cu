@@ -1,0 +1,179 @@
+// Sorted-unique + relabel by two-level bitmap ranking, and the library's error
+// plumbing.  Replaces torch.cat(...).unique() + `_assoc[n_id] = arange(...)`
+// (reference neighbor_loader.py:46-48, modules/memory_module.py:129,153).
+//
+// Layout of `bitmap` (uint32 words):
+//   L0: one bit per node, ceil(N/32) words, padded to a whole 32-word group
+//   L1: one bit per 32-word L0 group (= 1024 nodes)
+// Marking sets both levels; ranking walks only the groups whose L1 bit is set,
+// so its cost follows the number of touched groups, not N.
+#include <stdarg.h>
+
+#include "../../include/tgn_b200.h"
+#include "common.cuh"
+
+namespace tgn {
+static thread_local char g_err[512] = "";
+char* err_buf() { return g_err; }
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static inline int64_t l0_groups(int64_t n) { return (n + 1023) / 1024; }
+static inline int64_t l0_words(int64_t n) { return l0_groups(n) * 32; }
+static inline int64_t l1_words(int64_t n) { return (l0_groups(n) + 31) / 32; }
+
+__global__ void unique_mark_kernel(const int64_t* __restrict__ ids, DevCount cnt, int64_t n_nodes,
+                                   uint32_t* __restrict__ l0, uint32_t* __restrict__ l1) {
+  const int n = cnt.get();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int64_t id = ids[i];
+    if (id < 0 || id >= n_nodes) continue;  // out-of-range ids are ignored (caller validates)
+    uint32_t bit = 1u << (id & 31);
+    uint32_t old = atomicOr(&l0[id >> 5], bit);
+    if (old == 0) {
+      int64_t g = id >> 10;
+      atomicOr(&l1[g >> 5], 1u << (g & 31));
+    }
+  }
+}
+
+// One CTA of 1024 threads.  Thread t owns group (chunk*1024 + t): popcount of
+// its 32 words, block scan, then it emits its ids in ascending order and clears
+// the words it read (second read is an L1 hit).
+__global__ void __launch_bounds__(1024, 1)
+    unique_rank_kernel(uint32_t* __restrict__ l0, uint32_t* __restrict__ l1, int64_t n_groups,
+                       int64_t n_l1_words, int64_t* __restrict__ out_ids, int32_t out_cap,
+                       int64_t* __restrict__ assoc, int32_t* __restrict__ out_count) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base, s_total;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int64_t g0 = 0; g0 < n_groups; g0 += 1024) {
+    const int64_t g = g0 + tid;
+    int cnt = 0;
+    bool live = false;
+    if (g < n_groups) live = (l1[g >> 5] >> (g & 31)) & 1u;
+    uint4* p = reinterpret_cast<uint4*>(l0 + g * 32);
+    if (live) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint4 v = p[q];
+        cnt += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+      }
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int v = s_warp[lane];
+      int iv = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, iv, o);
+        if (lane >= o) iv += y;
+      }
+      s_warp[lane] = iv - v;  // exclusive warp offsets
+      if (lane == 31) s_total = iv;
+    }
+    __syncthreads();
+    int pos = s_base + s_warp[wid] + (incl - cnt);
+    if (live) {
+#pragma unroll 1
+      for (int q = 0; q < 8; ++q) {
+        uint4 v = p[q];
+        uint32_t ws4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          uint32_t bits = ws4[r];
+          while (bits) {
+            int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            int64_t id = (g << 10) + ((q * 4 + r) << 5) + b;
+            if (pos < out_cap) out_ids[pos] = id;
+            if (assoc) assoc[id] = pos;
+            ++pos;
+          }
+        }
+        p[q] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_base += s_total;
+    if (tid < 32) {
+      int64_t wi = (g0 >> 5) + tid;
+      if (wi < n_l1_words) l1[wi] = 0;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *out_count = s_base;
+}
+
+__global__ void relabel_kernel(const int64_t* __restrict__ ids, DevCount cnt,
+                               const int64_t* __restrict__ assoc, int64_t* __restrict__ out) {
+  const int n = cnt.get();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = assoc[ids[i]];
+}
+}  // namespace tgn
+
+using namespace tgn;
+
+extern "C" {
+
+int32_t tgn_abi_version(void) { return TGN_ABI_VERSION; }
+const char* tgn_last_error(void) { return tgn::err_buf(); }
+
+int64_t tgn_bitmap_bytes(int64_t num_nodes) {
+  if (num_nodes < 0) return 0;
+  return (l0_words(num_nodes) + l1_words(num_nodes)) * 4;
+}
+
+int32_t tgn_unique_mark(const int64_t* ids, int32_t count, const int32_t* count_dev,
+                        int64_t num_nodes, void* bitmap, void* stream) {
+  TGN_REQUIRE(count >= 0 && num_nodes > 0 && bitmap, "unique_mark: bad arguments");
+  if (count == 0) return TGN_OK;
+  TGN_REQUIRE(ids, "unique_mark: ids is NULL");
+  uint32_t* l0 = (uint32_t*)bitmap;
+  uint32_t* l1 = l0 + l0_words(num_nodes);
+  DevCount c{count_dev, count};
+  unique_mark_kernel<<<stride_grid(count, 256), 256, 0, (cudaStream_t)stream>>>(ids, c, num_nodes,
+                                                                                 l0, l1);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_unique_rank(void* bitmap, int64_t num_nodes, int64_t* out_ids, int32_t out_cap,
+                        int64_t* assoc, int32_t* out_count, void* stream) {
+  TGN_REQUIRE(bitmap && out_ids && out_count && num_nodes > 0 && out_cap >= 0,
+              "unique_rank: bad arguments");
+  uint32_t* l0 = (uint32_t*)bitmap;
+  uint32_t* l1 = l0 + l0_words(num_nodes);
+  unique_rank_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+      l0, l1, l0_groups(num_nodes), l1_words(num_nodes), out_ids, out_cap, assoc, out_count);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_relabel(const int64_t* ids, int32_t count, const int32_t* count_dev,
+                    const int64_t* assoc, int64_t* out, void* stream) {
+  TGN_REQUIRE(count >= 0, "relabel: negative count");
+  if (count == 0) return TGN_OK;
+  TGN_REQUIRE(ids && assoc && out, "relabel: NULL pointer");
+  DevCount c{count_dev, count};
+  relabel_kernel<<<stride_grid(count, 256), 256, 0, (cudaStream_t)stream>>>(ids, c, assoc, out);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,320 @@
+"""GPU parity tests of the individual kernels, through the C-ABI (ctypes), against
+the oracle and the committed golden vectors.  Bit-exact for ids / indices /
+argmax / last_update; 1e-5 for fp32 math."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tgn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda"
+
+
+def cu(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from tgn_b200 import ops as _ops
+    return _ops
+
+
+# ------------------------------------------------------------------ unique / relabel
+@pytest.mark.parametrize("N,count", [(10, 0), (10, 7), (1024, 300), (1025, 2000), (9227, 600),
+                                     (352637, 6600), (994790, 200200), (3_000_000, 50_000)])
+def test_unique_relabel(ops, N, count):
+    rng = np.random.default_rng(N + count)
+    ids = rng.integers(0, N, count).astype(np.int64)
+    if count:
+        ids[0], ids[-1] = 0, N - 1
+    assoc = torch.full((N,), -7, dtype=torch.int64, device=DEV)
+    parts = [cu(ids[: count // 2]), cu(ids[count // 2:])] if count else [cu(ids)]
+    out = ops.unique_relabel(parts, N, assoc)
+    ref = np.unique(ids)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    if count:
+        assert np.array_equal(assoc[cu(ref)].cpu().numpy(), np.arange(ref.size))
+    # the bitmap is left clean: a second call on other ids is unaffected
+    ids2 = rng.integers(0, N, 13).astype(np.int64)
+    assert np.array_equal(ops.unique_relabel([cu(ids2)], N).cpu().numpy(), np.unique(ids2))
+
+
+# ------------------------------------------------------------------ neighbour ring
+def test_ring_golden(ops):
+    from neighbor_loader import LastNeighborLoader
+    z = np.load(os.path.join(G, "neighbor_loader.npz"))
+    for c in range(int(z["num_cases"])):
+        N, K, B, steps = z[f"c{c}_meta"].tolist()
+        ld = LastNeighborLoader(N, K, device=DEV)
+        for s in range(steps):
+            p = f"c{c}_s{s}_"
+            n_id, ei, e_id, t = ld(cu(z[p + "roots"]))
+            assert np.array_equal(n_id.cpu().numpy(), z[p + "n_id"])
+            assert np.array_equal(ei.cpu().numpy(), z[p + "edge_index"])
+            assert np.array_equal(e_id.cpu().numpy(), z[p + "e_id"])
+            assert np.array_equal(t.cpu().numpy(), z[p + "t"])
+            assert np.array_equal(ld._assoc[n_id].cpu().numpy(), np.arange(n_id.numel()))
+            ld.insert(cu(z[p + "src"]), cu(z[p + "dst"]), cu(z[p + "tin"]))
+            e_state = ld.e_id.cpu().numpy()
+            assert np.array_equal(e_state, z[p + "state_e"])
+            assert np.array_equal(np.where(e_state >= 0, ld.neighbors.cpu().numpy(), 0), z[p + "state_n"])
+            assert np.array_equal(ld.t.cpu().numpy(), z[p + "state_t"])
+        assert ld.cur_e_id == B * steps
+
+
+@pytest.mark.parametrize("N,K,B,steps,bip", [(9227, 10, 200, 30, True), (500, 20, 600, 10, False),
+                                             (64, 3, 50, 12, False), (2000, 10, 2000, 4, True),
+                                             (300, 64, 100, 5, False)])
+def test_ring_vs_oracle_random(ops, N, K, B, steps, bip):
+    """wiki-like popularity (hubs get > K events per batch), self loops, non-bipartite."""
+    from neighbor_loader import LastNeighborLoader
+    rng = np.random.default_rng(N * K + B)
+    ld = LastNeighborLoader(N, K, device=DEV)
+    ring = orc.NeighborRing(N, K)
+    tcur = 0
+    for s in range(steps):
+        u = rng.random(B)
+        if bip:
+            src = (u ** 3 * (N // 2)).astype(np.int64); dst = N // 2 + (rng.random(B) ** 3 * (N - N // 2)).astype(np.int64)
+        else:
+            src = (u ** 2 * N).astype(np.int64); dst = (rng.random(B) ** 2 * N).astype(np.int64)
+        t = np.sort(rng.integers(0, 30, B) + tcur).astype(np.float32); tcur = int(t[-1])
+        roots = np.unique(np.concatenate([src, dst, rng.integers(0, N, B)]))
+        if s % 3 == 2:
+            roots = rng.permutation(roots)      # lookup order follows the caller's order
+        got = ld(cu(roots))
+        ref = ring.lookup(roots)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a.cpu().numpy(), b)
+        ld.insert(cu(src), cu(dst), cu(t))
+        ring.insert(src, dst, t)
+        e_state = ld.e_id.cpu().numpy()
+        assert np.array_equal(e_state, ring.e_id)
+        assert np.array_equal(np.where(e_state >= 0, ld.neighbors.cpu().numpy(), 0),
+                              np.where(ring.e_id >= 0, ring.neighbors, 0))
+        assert np.array_equal(ld.t.cpu().numpy(), ring.t)
+    ld.reset_state()
+    assert ld.cur_e_id == 0 and int((ld.e_id != -1).sum()) == 0
+    out = ld(cu(np.array([1, 2, 3])))
+    assert out[1].shape == (2, 0) and out[0].tolist() == [1, 2, 3]
+
+
+def test_ring_large_lookup_properties(ops):
+    """eval-sized lookup (200 x 1001 roots worth of nodes on the comment shape): size-independent
+    properties -- edge order follows roots, every emitted slot is valid, counts add up."""
+    N, K = 994790, 10
+    g = torch.Generator(device=DEV).manual_seed(0)
+    e_id = torch.randint(-1, 10_000_000, (N, K), device=DEV, generator=g)
+    e_id = torch.sort(e_id, dim=1, descending=True).values
+    nbrs = torch.randint(0, N, (N, K), device=DEV, generator=g)
+    t = torch.rand((N, K), device=DEV, generator=g)
+    roots = torch.unique(torch.randint(0, N, (200_200,), device=DEV, generator=g))
+    assoc = torch.zeros(N, dtype=torch.int64, device=DEV)
+    ids, ei, eo, to, off = ops.nbr_lookup(roots, nbrs, e_id, t, assoc)
+    valid = e_id[roots] >= 0
+    assert eo.numel() == int(valid.sum())
+    assert torch.equal(eo, e_id[roots][valid]) and torch.equal(to, t[roots][valid])
+    assert torch.equal(ids[ei[0]], nbrs[roots][valid])
+    assert torch.equal(ids[ei[1]], roots.view(-1, 1).expand(-1, K)[valid])
+    assert torch.equal(off[1:].long() - off[:-1].long(), valid.sum(1))
+    assert torch.equal(ids, torch.unique(torch.cat([roots, nbrs[roots][valid]])))
+
+
+# ------------------------------------------------------------------ t-CSR sampler
+def _graph(rng, N, E, tmax):
+    src = (rng.random(E) ** 2 * N).astype(np.int64); dst = rng.integers(0, N, E)
+    t = np.sort(rng.integers(0, tmax, E)).astype(np.float32)
+    return orc.build_tcsr(src, dst, t, N)
+
+
+@pytest.mark.parametrize("strategy", ["recent", "uniform"])
+@pytest.mark.parametrize("N,E,R,k,dur", [(50, 600, 300, 5, 0.0), (2000, 40000, 3000, 10, 0.0),
+                                         (2000, 40000, 1000, 20, 300.0), (10, 3, 40, 4, 0.0)])
+def test_tcsr_vs_oracle(ops, strategy, N, E, R, k, dur):
+    rng = np.random.default_rng(E + k)
+    indptr, indices, eid, ts = _graph(rng, N, E, 5000)
+    roots = rng.integers(0, N, R).astype(np.int32)
+    rts = rng.integers(0, 5200, R).astype(np.float32)
+    ref = orc.tcsr_sample_ref(indptr, indices, eid, ts, roots, rts, k, strategy, 0.0, dur, seed=11)
+    (n, c, e, t, d), off, cnt = ops.tcsr_sample(cu(indptr), cu(indices), cu(eid), cu(ts), cu(roots), cu(rts), k,
+                                                0 if strategy == "recent" else 1, 0.0, dur, 11)
+    m = int(cnt.item())
+    assert m == ref[0].size
+    for got, want in zip((n, c, e, t, d), ref[:5]):
+        assert np.array_equal(got[:m].cpu().numpy(), want)
+    assert np.array_equal(off.cpu().numpy(), ref[5])
+
+
+def test_tcsr_empty_and_ragged(ops):
+    indptr, indices, eid, ts = orc.build_tcsr([0, 0], [1, 1], [3.0, 3.0], 4)   # nodes 2,3 isolated; tie at t=3
+    (n, c, e, t, d), off, cnt = ops.tcsr_sample(cu(indptr), cu(indices), cu(eid), cu(ts),
+                                                cu(np.array([2, 0, 0, 1, 3], np.int32)),
+                                                cu(np.array([9, 3, 3.5, 100, 0], np.float32)), 3)
+    assert off.cpu().tolist() == [0, 0, 0, 2, 4, 4] and int(cnt) == 4    # ts < t is strict
+    assert e[:4].cpu().tolist() == [1, 0, 1, 0]
+    empty = ops.tcsr_sample(cu(indptr), cu(indices), cu(eid), cu(ts), cu(np.zeros(0, np.int32)),
+                            cu(np.zeros(0, np.float32)), 3)
+    assert int(empty[2]) == 0
+
+
+def test_tcsr_uniform_statistics(ops):
+    """one hub with 1000 earlier events, 20000 roots x k=20 draws: chi-square against uniform."""
+    E = 1000
+    indptr, indices, eid, ts = orc.build_tcsr(np.zeros(E, np.int64), np.arange(1, E + 1), np.arange(E), E + 1)
+    R, k = 20000, 20
+    (n, c, e, t, d), off, cnt = ops.tcsr_sample(cu(indptr), cu(indices), cu(eid), cu(ts),
+                                                cu(np.zeros(R, np.int32)), cu(np.full(R, 2000.0, np.float32)),
+                                                k, 1, 0.0, 0.0, 1234)
+    assert int(cnt) == R * k
+    hist = np.bincount(e.cpu().numpy(), minlength=E).astype(np.float64)
+    chi2 = ((hist - R * k / E) ** 2 / (R * k / E)).sum()
+    assert 800 < chi2 < 1250, chi2       # dof = 999, +-5.6 sigma
+
+
+def test_tcsr_large_properties(ops):
+    """review-sized graph: recent-k output is sorted by root, most-recent-first, strictly earlier."""
+    rng = np.random.default_rng(5)
+    N, E = 352637, 2_000_000
+    indptr, indices, eid, ts = _graph(rng, N, E, 100000)
+    R, k = 500_000, 10
+    roots = rng.integers(0, N, R).astype(np.int32); rts = rng.integers(0, 100000, R).astype(np.float32)
+    (n, c, e, t, d), off, cnt = ops.tcsr_sample(cu(indptr), cu(indices), cu(eid), cu(ts), cu(roots), cu(rts), k)
+    m = int(cnt)
+    c, t, d, off = c[:m].long(), t[:m], d[:m], off.long()
+    assert m == int(off[-1]) and bool((c[1:] >= c[:-1]).all())
+    rt = cu(rts)
+    assert bool((t < rt[c]).all()) and torch.equal(d, rt[c] - t)
+    same = c[1:] == c[:-1]
+    assert bool((t[1:][same] <= t[:-1][same]).all())
+    deg_before = torch.searchsorted(cu(ts), rt)   # not per-row; only check the count bound
+    assert bool(((off[1:] - off[:-1]) <= k).all())
+    # count = min(k, #earlier in row): recompute on the host for a sample of roots
+    for r in rng.integers(0, R, 200):
+        row = ts[indptr[roots[r]]:indptr[roots[r] + 1]]
+        assert int(off[r + 1] - off[r]) == min(k, int((row < rts[r]).sum()))
+
+
+# ------------------------------------------------------------------ aggregators
+def test_aggregators_golden_and_ties(ops):
+    z = np.load(os.path.join(G, "aggregators.npz"))
+    for i in range(int(z["num_cases"])):
+        msg, idx, t, S = cu(z[f"a{i}_msg"]), cu(z[f"a{i}_index"]), cu(z[f"a{i}_t"]), int(z[f"a{i}_S"])
+        out, arg = ops.agg_last(msg, idx, t, S)
+        assert np.array_equal(out.cpu().numpy(), z[f"a{i}_last"])
+        np.testing.assert_allclose(ops.agg_mean(msg, idx, S).cpu().numpy(), z[f"a{i}_mean"], rtol=1e-5, atol=1e-6)
+    rng = np.random.default_rng(3)
+    for M, S, W, dt in [(5000, 700, 472, np.int64), (10000, 50, 33, np.float32), (7, 3, 1, np.int64)]:
+        msg = rng.standard_normal((M, W)).astype(np.float32)
+        idx = rng.integers(0, S, M); t = rng.integers(-3, 4, M).astype(dt)   # heavy ties, negative t
+        ref = orc.LastAggregator()(torch.from_numpy(msg), torch.from_numpy(idx), torch.from_numpy(t), S)
+        _, ref_arg = orc.tp.scatter_max(torch.from_numpy(t), torch.from_numpy(idx), 0, S)
+        out, arg = ops.agg_last(cu(msg), cu(idx), cu(t), S)
+        assert np.array_equal(arg.cpu().numpy(), ref_arg.numpy())
+        assert np.array_equal(out.cpu().numpy(), ref.numpy())
+        refm = orc.MeanAggregator()(torch.from_numpy(msg), torch.from_numpy(idx), None, S)
+        np.testing.assert_allclose(ops.agg_mean(cu(msg), cu(idx), S).cpu().numpy(), refm.numpy(), rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------ dense
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+@pytest.mark.parametrize("m,n,k,split", [(1, 1, 1, 1), (65, 300, 472, 1), (600, 400, 100, 1), (300, 472, 4000, 8),
+                                         (129, 63, 17, 2)])
+def test_sgemm(ops, ta, tb, m, n, k, split):
+    g = torch.Generator(device="cpu").manual_seed(m * n + k)
+    A = torch.randn((k, m) if ta else (m, k), generator=g)
+    B = torch.randn((k, n) if tb else (n, k), generator=g)
+    bias = torch.randn(n, generator=g)
+    ref = (A.t() if ta else A).double() @ (B if tb else B.t()).double() + bias.double()
+    out = ops.sgemm(A.to(DEV), B.to(DEV), bias.to(DEV), m=m, n=n, k=k, lda=A.shape[1], ldb=B.shape[1],
+                    trans_a=ta, trans_b=tb, split_k=split)
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=2e-5, atol=2e-4 if k > 1000 else 2e-5)
+
+
+def test_sgemm_gather_and_device_counts(ops):
+    g = torch.Generator(device="cpu").manual_seed(0)
+    table = torch.randn(50, 24, generator=g); W = torch.randn(30, 24, generator=g)
+    rows = torch.randint(0, 50, (40,), generator=g)
+    cnt = torch.tensor([33], dtype=torch.int32, device=DEV)
+    out = torch.full((40, 30), 7.0, device=DEV)
+    ops.sgemm(table.to(DEV), W.to(DEV), m=40, n=30, k=24, lda=24, ldb=24, a_rows=rows.to(DEV), out=out, m_dev=cnt)
+    torch.testing.assert_close(out[:33].cpu(), table[rows[:33]] @ W.t(), rtol=1e-5, atol=1e-5)
+    assert bool((out[33:] == 7.0).all())
+    # reduction length from the device: C = A^T B over the first 33 rows only
+    A = torch.randn(40, 12, generator=g); B = torch.randn(40, 9, generator=g)
+    got = ops.sgemm(A.to(DEV), B.to(DEV), m=12, n=9, k=40, lda=12, ldb=9, trans_a=True, trans_b=True, k_dev=cnt)
+    torch.testing.assert_close(got.cpu(), A[:33].t() @ B[:33], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("S,Dx,D", [(1, 5, 3), (333, 472, 100), (4000, 274, 100)])
+def test_gru_cell_fwd_bwd(ops, S, Dx, D):
+    torch.manual_seed(S)
+    cell = torch.nn.GRUCell(Dx, D)
+    x = torch.randn(S, Dx, requires_grad=True); h = torch.randn(S, D, requires_grad=True)
+    ref = cell(x, h)
+    wgt = torch.randn(S, D)
+    (ref * wgt).sum().backward()
+    p = [q.detach().to(DEV).requires_grad_() for q in (cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh)]
+    xg = x.detach().to(DEV).requires_grad_(); hg = h.detach().to(DEV).requires_grad_()
+    out = ops.gru_cell(xg, hg, *p)
+    torch.testing.assert_close(out.cpu(), ref.detach(), rtol=1e-5, atol=1e-5)
+    (out * wgt.to(DEV)).sum().backward()
+    tol = dict(rtol=1e-4, atol=1e-4 * max(1.0, S / 300))
+    torch.testing.assert_close(xg.grad.cpu(), x.grad, **tol)
+    torch.testing.assert_close(hg.grad.cpu(), h.grad, **tol)
+    for a, b in zip(p, (cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh)):
+        torch.testing.assert_close(a.grad.cpu(), b.grad, **tol)
+
+
+def test_time_encode_fwd_bwd(ops):
+    torch.manual_seed(0)
+    te = orc.tp.TimeEncoder(100)
+    t = (torch.rand(777) * 2.6e6).float()        # wiki-scale deltas: full-range cosf, fma rounding
+    ref = te(t)
+    (ref * torch.linspace(-1, 1, 100)).sum().backward()
+    w = te.lin.weight.detach().view(-1).to(DEV).requires_grad_(); b = te.lin.bias.detach().to(DEV).requires_grad_()
+    out = ops.time_encode_autograd(t.to(DEV), w, b)
+    torch.testing.assert_close(out.cpu(), ref.detach(), rtol=0, atol=2e-6)
+    (out * torch.linspace(-1, 1, 100, device=DEV)).sum().backward()
+    torch.testing.assert_close(w.grad.cpu(), te.lin.weight.grad.view(-1), rtol=1e-4, atol=1.0)  # grads ~ 1e6-scale
+    torch.testing.assert_close(b.grad.cpu(), te.lin.bias.grad, rtol=1e-4, atol=1e-3)
+
+
+def test_link_score_and_mrr(ops):
+    torch.manual_seed(1)
+    lp = orc.LinkPredictor(100)
+    z = torch.randn(300, 100)
+    a = torch.randint(0, 300, (500,)); b = torch.randint(0, 300, (500,))
+    ref_logit = lp.logits(z[a], z[b]).view(-1).detach(); ref_prob = lp(z[a], z[b]).view(-1).detach()
+    zd = z.to(DEV)
+    hs = ops.sgemm(zd, lp.lin_src.weight.detach().to(DEV), lp.lin_src.bias.detach().to(DEV), m=300, n=100, k=100, lda=100, ldb=100)
+    hd = ops.sgemm(zd, lp.lin_dst.weight.detach().to(DEV), lp.lin_dst.bias.detach().to(DEV), m=300, n=100, k=100, lda=100, ldb=100)
+    wf = lp.lin_final.weight.detach().view(-1).to(DEV); bf = lp.lin_final.bias.detach().to(DEV)
+    torch.testing.assert_close(ops.link_score(hs, hd, a.to(DEV), b.to(DEV), wf, bf, False).cpu(), ref_logit, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(ops.link_score(hs, hd, a.to(DEV), b.to(DEV), wf, bf, True).cpu(), ref_prob, rtol=1e-5, atol=1e-5)
+    rng = np.random.default_rng(0)
+    pos = rng.random(200).astype(np.float32); neg = rng.random((200, 999)).astype(np.float32)
+    neg[:, :5] = pos[:, None]     # ties
+    np.testing.assert_allclose(ops.mrr(cu(pos), cu(neg)).cpu().numpy(), orc.mrr_ref(pos, neg), rtol=1e-6)
+
+
+def test_adam_matches_torch(ops):
+    torch.manual_seed(0)
+    p = torch.randn(1000, requires_grad=True)
+    opt = torch.optim.Adam([p], lr=1e-3)
+    pg = p.detach().clone().to(DEV); m = torch.zeros_like(pg); v = torch.zeros_like(pg)
+    step = torch.zeros(1, device=DEV)
+    for i in range(5):
+        g = torch.randn(1000)
+        p.grad = g.clone(); opt.step()
+        ops.adam_step(pg, g.to(DEV), m, v, step, 1e-3)
+    torch.testing.assert_close(pg.cpu(), p.detach(), rtol=1e-5, atol=1e-6)
+    assert float(step) == 5.0

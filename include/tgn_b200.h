@@ -63,9 +63,11 @@ const char* tgn_last_error(void);
 int64_t tgn_bitmap_bytes(int64_t num_nodes);
 int32_t tgn_unique_mark(const int64_t* ids, int32_t count, const int32_t* count_dev,
                         int64_t num_nodes, void* bitmap, void* stream);
-/* out_ids[0..*out_count) ascending; assoc[id] = rank (assoc nullable). */
+/* out_ids[0..*out_count) ascending; assoc[id] = rank (assoc nullable).  With
+ * keep_marks != 0 the bitmap is left as is (more ids can be marked and ranked
+ * again), otherwise it is cleared. */
 int32_t tgn_unique_rank(void* bitmap, int64_t num_nodes, int64_t* out_ids, int32_t out_cap,
-                        int64_t* assoc, int32_t* out_count, void* stream);
+                        int64_t* assoc, int32_t* out_count, int32_t keep_marks, void* stream);
 /* out[i] = assoc[ids[i]]   (neighbor_loader.py:48) */
 int32_t tgn_relabel(const int64_t* ids, int32_t count, const int32_t* count_dev,
                     const int64_t* assoc, int64_t* out, void* stream);
@@ -268,7 +270,10 @@ int32_t tgn_time_encode(const float* t, int32_t num, const float* w, const float
  *     out_i = sum alpha * (v_j + ee) + skip_i
  * Edges must be grouped by centre: centre c owns edges [row_ptr[c], row_ptr[c+1])
  * listed in edge_perm (nullable = identity); centre_ids[c] (nullable = c) is the
- * row of x/out it refers to.  msg rows come from msg[msg_rows ? msg_rows[e] : e].
+ * row of x/out it refers to.  The edge payload (msg row AND t_edge entry) of edge e is
+ * read at row msg_rows[e] when msg_rows is given (e.g. the event ids from the neighbour
+ * lookup, indexing the resident event arrays), else at row e.  The dropout seed is
+ * seed + *seed_dev (seed_dev nullable), so a replayed CUDA graph draws a fresh mask.
  * Rows of `out` that are not centres must be pre-filled with skip by the
  * caller (tgn_attn_fill_skip).  alpha_out (nullable) [E,H] is kept for backward.
  * dropout on alpha uses Philox(seed) keyed by (edge, head); p = 0 disables.
@@ -278,7 +283,7 @@ int32_t tgn_attn_fwd(const float* proj, const void* last_update_local, int32_t l
                      const float* msg, const int64_t* msg_rows, const int32_t* row_ptr,
                      const int32_t* edge_perm, const int64_t* centre_ids, int32_t num_centres, const int32_t* num_centres_dev, int32_t heads,
                      int32_t head_dim, int32_t raw_dim, int32_t time_dim, const float* w_edge,
-                     const float* time_w, const float* time_b, float dropout_p, uint64_t seed,
+                     const float* time_w, const float* time_b, float dropout_p, uint64_t seed, const int64_t* seed_dev,
                      float* out, float* alpha_out, float* ee_out, void* stream);
 /* out[r,:] = proj[r, 3*H*C : 4*H*C]  for all Nb rows */
 int32_t tgn_attn_fill_skip(const float* proj, int32_t num_rows, const int32_t* num_rows_dev,
@@ -295,13 +300,22 @@ int32_t tgn_attn_bwd(const float* proj, const int64_t* nbr_local, const int32_t*
                      const int32_t* edge_perm, const int64_t* centre_ids, int32_t num_centres,
                      const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
                      const float* alpha, const float* ee, const float* d_out, float dropout_p,
-                     uint64_t seed, float* d_proj, float* d_ee, void* stream);
+                     uint64_t seed, const int64_t* seed_dev, float* d_proj, float* d_ee, void* stream);
 int32_t tgn_attn_edge_attr(const void* last_update_local, int32_t lu_is_float,
                            const int64_t* nbr_local, const void* t_edge, int32_t t_is_float,
                            const float* msg, const int64_t* msg_rows, int32_t num_edges,
                            const int32_t* num_edges_dev, int32_t raw_dim, int32_t time_dim,
                            const float* time_w, const float* time_b, float* edge_attr,
                            float* rel_t, void* stream);
+
+/* Batch staging (replaces the host DataLoader walk, temporal_dataset.py:34-57 +
+ * epoch_utils.py:186-215): slices events [*pos_dev, *pos_dev + batch) of the
+ * resident event arrays into ids3 = [src|dst|neg] (int64 [3*batch]), t_i64, t_f32 and
+ * msg [batch, raw_dim], then advances *pos_dev by batch. */
+int32_t tgn_batch_load(const int64_t* src_all, const int64_t* dst_all, const int64_t* neg_all,
+                       const int64_t* t_all, const float* msg_all, int32_t raw_dim, int32_t batch,
+                       int64_t* pos_dev, int64_t* ids3, int64_t* t_i64, float* t_f32, float* msg,
+                       void* stream);
 
 /* LinkPredictor forward (decoder.py:24-27) on gathered rows:
  *   h = relu(Ws z[a] + bs + Wd z[b] + bd); score = wf . h + bf  (logit; sigmoid optional)

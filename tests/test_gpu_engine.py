@@ -1,0 +1,146 @@
+"""GPU: the fused training step (tgn_b200.engine.TGNEngine, eager and CUDA-graph
+replay) against the CPU oracle's training step on the same weights and events:
+loss per step, memory, last_update (bit-exact), neighbour ring (bit-exact), weights
+after Adam; and the evaluation step's MRR."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tgn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _setup(N, De, D, K, B, E, seed, use_graph, lr=1e-3):
+    from tgn_b200.engine import TGNEngine
+    from tgn_b200 import synth
+    rng = np.random.default_rng(seed)
+    ns = N // 2
+    src = np.floor(rng.random(E) ** 2 * ns).astype(np.int64)
+    dst = ns + np.floor(rng.random(E) ** 2 * (N - ns)).astype(np.int64)
+    t = np.sort(rng.integers(0, 40 * E, E)).astype(np.int64)
+    msg = rng.standard_normal((E, De)).astype(np.float32)
+    neg = synth.sample_negatives(dst, np.unique(dst), np.random.default_rng(seed + 1))
+    ref = orc.build_model(De, D, N, seed=seed)
+    with torch.no_grad():
+        ref["memory"].time_enc.lin.weight.mul_(0.002)   # keep cos() well-conditioned at these time deltas
+    ref["gnn"].conv.dropout = 0.0
+    for m in ref.values():
+        m.train()
+    eng = TGNEngine(N, De, D, K, B, device=DEV, lr=lr, dropout=0.0, use_graph=use_graph, log_capacity=E)
+    eng.load_state(ref["memory"].state_dict(), ref["gnn"].state_dict(), ref["link_pred"].state_dict())
+    ev = dict(src=torch.from_numpy(src), dst=torch.from_numpy(dst), t=torch.from_numpy(t),
+              msg=torch.from_numpy(msg), neg=torch.from_numpy(neg))
+    eng.set_events(**ev)
+    return ref, eng, ev
+
+
+def _oracle_grads(ref):
+    g = {k: v.grad for k, v in ref["memory"].named_parameters()}
+    gg = dict(ref["gnn"].named_parameters())
+    g["conv.w_node"] = torch.cat([gg[f"conv.lin_{n}.weight"].grad for n in ("query", "key", "value", "skip")])
+    g["conv.b_node"] = torch.cat([gg[f"conv.lin_{n}.bias"].grad for n in ("query", "key", "value", "skip")])
+    g["conv.lin_edge.weight"] = gg["conv.lin_edge.weight"].grad
+    g.update({k: v.grad for k, v in ref["link_pred"].named_parameters()})
+    return g
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_steps_match_oracle(use_graph):
+    """Every step: same loss and same gradients from the same weights and state.  Adam turns
+    rounding-level gradient noise on near-zero gradients into lr-sized weight differences, so
+    the oracle's post-step weights are copied into the engine after each step (Adam itself is
+    checked in test_adam_matches_torch and by the free-running test below)."""
+    N, De, D, K, B, steps = 400, 12, 32, 5, 50, 10
+    ref, eng, ev = _setup(N, De, D, K, B, B * steps, 7, use_graph)
+    loader = orc.TorchNeighborLoader(N, K)
+    opt = torch.optim.Adam(orc.model_parameters(ref), lr=1e-3)
+    strip = lambda sd: {k: v for k, v in sd.items() if k not in ("memory", "last_update", "_assoc")}
+    for s in range(steps):
+        sl = slice(s * B, (s + 1) * B)
+        loss = float(eng.train_step(from_device=True))
+        loss_ref = orc.train_step(ref, loader, opt, ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl],
+                                  ev["msg"][sl], ev["t"], ev["msg"], dropout=False)
+        assert abs(loss - loss_ref) < 1e-4 * max(1.0, abs(loss_ref)), (s, loss, loss_ref)
+        for k, g in _oracle_grads(ref).items():
+            torch.testing.assert_close(eng.p[k].grad.cpu(), g, rtol=2e-3, atol=2e-6, msg=lambda m: f"step {s} {k}: {m}")
+        torch.testing.assert_close(eng.memory.cpu(), ref["memory"].memory.detach(), rtol=1e-4, atol=1e-5)
+        assert torch.equal(eng.last_update.cpu(), ref["memory"].last_update)
+        eng.load_state(strip(ref["memory"].state_dict()), ref["gnn"].state_dict(), ref["link_pred"].state_dict())
+    assert torch.equal(eng.e_id.cpu(), loader.e_id)
+    valid = loader.e_id >= 0
+    assert torch.equal(eng.neighbors.cpu()[valid], loader.neighbors[valid])
+    assert torch.equal(eng.t_ring.cpu(), loader.t)
+
+
+def test_free_running_training_tracks_oracle():
+    """no weight syncing: 12 Adam steps stay close (loose tolerance, see above)."""
+    N, De, D, K, B, steps = 400, 12, 32, 5, 50, 12
+    ref, eng, ev = _setup(N, De, D, K, B, B * steps, 9, True)
+    loader = orc.TorchNeighborLoader(N, K)
+    opt = torch.optim.Adam(orc.model_parameters(ref), lr=1e-3)
+    for s in range(steps):
+        sl = slice(s * B, (s + 1) * B)
+        loss = float(eng.train_step(from_device=True))
+        loss_ref = orc.train_step(ref, loader, opt, ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl],
+                                  ev["msg"][sl], ev["t"], ev["msg"], dropout=False)
+        assert abs(loss - loss_ref) < 1e-2, (s, loss, loss_ref)
+    assert torch.equal(eng.last_update.cpu(), ref["memory"].last_update)
+    assert torch.equal(eng.e_id.cpu(), loader.e_id)
+    assert float(eng.adam_step_dev) == steps
+
+
+def test_host_staged_batches_equal_device_staged():
+    N, De, D, K, B, steps = 300, 8, 16, 4, 32, 8
+    _, eng_a, ev = _setup(N, De, D, K, B, B * steps, 11, True)
+    _, eng_b, _ = _setup(N, De, D, K, B, B * steps, 11, True)
+    pin = {k: v.pin_memory() for k, v in ev.items()}
+    for s in range(steps):
+        sl = slice(s * B, (s + 1) * B)
+        la = float(eng_a.train_step(from_device=True))
+        eng_b.stage_batch(pin["src"][sl], pin["dst"][sl], pin["neg"][sl], pin["t"][sl], pin["msg"][sl])
+        lb = float(eng_b.train_step(from_device=False))
+        assert abs(la - lb) < 1e-4, (s, la, lb)   # atomics in the gradient reductions: not bitwise
+    torch.testing.assert_close(eng_a.memory, eng_b.memory, rtol=1e-2, atol=1e-3)
+
+
+def test_eval_mrr_matches_oracle():
+    """train a few steps, switch to eval (flush), score one batch against Q negatives."""
+    from tgn_b200 import ops, synth
+    N, De, D, K, B, steps, Q = 300, 8, 16, 5, 40, 6, 20
+    ref, eng, ev = _setup(N, De, D, K, B, B * (steps + 2), 5, False)
+    loader = orc.TorchNeighborLoader(N, K)
+    opt = torch.optim.Adam(orc.model_parameters(ref), lr=1e-3)
+    for s in range(steps):
+        sl = slice(s * B, (s + 1) * B)
+        orc.train_step(ref, loader, opt, ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl], ev["msg"][sl],
+                       ev["t"], ev["msg"], dropout=False)
+        eng.train_step(from_device=True)
+    for m in ref.values():
+        m.eval()
+    eng.flush_to_eval()
+    torch.testing.assert_close(eng.memory.cpu(), ref["memory"].memory.detach(), rtol=1e-3, atol=1e-4)
+    assert torch.equal(eng.last_update.cpu(), ref["memory"].last_update)
+    for s in range(steps, steps + 2):
+        sl = slice(s * B, (s + 1) * B)
+        src, dst, t, msg = ev["src"][sl], ev["dst"][sl], ev["t"][sl], ev["msg"][sl]
+        neg = torch.from_numpy(synth.eval_negatives(src.numpy(), dst.numpy(), N, Q, seed=s, dst_lo=N // 2))
+        with torch.no_grad():
+            n_id = torch.cat([src, dst, neg.view(-1)]).unique()
+            n_id, ei, e_id, _ = loader(n_id)
+            z, lu = ref["memory"](n_id)
+            z = ref["gnn"](z, lu, ei, ev["t"][e_id], ev["msg"][e_id])
+            a = loader._assoc
+            pos_r = ref["link_pred"](z[a[src]], z[a[dst]]).view(-1)
+            neg_r = ref["link_pred"](z[a[src]].repeat_interleave(Q, 0), z[a[neg.view(-1)]]).view(B, Q)
+            ref["memory"].update_state(src, dst, t, msg)
+            loader.insert(src, dst, t.float())
+        pos_g, neg_g = eng.eval_scores(src, dst, neg, t, msg)
+        torch.testing.assert_close(pos_g.cpu(), pos_r, rtol=1e-3, atol=1e-5)
+        torch.testing.assert_close(neg_g.cpu(), neg_r, rtol=1e-3, atol=1e-5)
+        mrr_g = float(ops.mrr(pos_g, neg_g).mean())
+        mrr_r = float(orc.mrr_ref(pos_r.numpy(), neg_r.numpy()).mean())
+        assert abs(mrr_g - mrr_r) < 0.005
+    torch.testing.assert_close(eng.memory.cpu(), ref["memory"].memory.detach(), rtol=1e-3, atol=1e-4)
+    assert torch.equal(eng.last_update.cpu(), ref["memory"].last_update)

@@ -194,7 +194,6 @@ def test_tcsr_large_properties(ops):
     assert bool((t < rt[c]).all()) and torch.equal(d, rt[c] - t)
     same = c[1:] == c[:-1]
     assert bool((t[1:][same] <= t[:-1][same]).all())
-    deg_before = torch.searchsorted(cu(ts), rt)   # not per-row; only check the count bound
     assert bool(((off[1:] - off[:-1]) <= k).all())
     # count = min(k, #earlier in row): recompute on the host for a sample of roots
     for r in rng.integers(0, R, 200):
@@ -236,7 +235,8 @@ def test_sgemm(ops, ta, tb, m, n, k, split):
     ref = (A.t() if ta else A).double() @ (B if tb else B.t()).double() + bias.double()
     out = ops.sgemm(A.to(DEV), B.to(DEV), bias.to(DEV), m=m, n=n, k=k, lda=A.shape[1], ldb=B.shape[1],
                     trans_a=ta, trans_b=tb, split_k=split)
-    torch.testing.assert_close(out.cpu().double(), ref, rtol=2e-5, atol=2e-4 if k > 1000 else 2e-5)
+    # fp32 accumulation over k terms of N(0,1) products: error grows ~ sqrt(k) * eps * |sum|
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-5, atol=1e-5 * max(4.0, k ** 0.5))
 
 
 def test_sgemm_gather_and_device_counts(ops):

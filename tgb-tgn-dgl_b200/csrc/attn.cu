@@ -42,12 +42,14 @@ struct AttnArgs {
   const float* time_b;
   float dropout_p;
   uint64_t seed;
+  const int64_t* seed_dev;
   float* out;
   float* alpha_out;  // [E,H]  (softmax weights before dropout)
   float* ee_out;     // [E,H*C]
 };
 
-__device__ __forceinline__ float attn_rel_t(const AttnArgs& a, int64_t j, int e) {
+// e = payload row (msg_rows[edge] when given, else the edge position)
+__device__ __forceinline__ float attn_rel_t(const AttnArgs& a, int64_t j, long long e) {
   if (!a.lu_is_float && !a.t_is_float) {
     const int64_t d = reinterpret_cast<const int64_t*>(a.lu)[j] -
                       reinterpret_cast<const int64_t*>(a.t_edge)[e];
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_fwd_kernel(AttnArgs a
   const float inv_sqrt_c = rsqrtf((float)a.C);
   const int CH = (HC + 31) >> 5;
   const float keep = 1.f - a.dropout_p;
-  Philox rng(a.seed);
+  Philox rng(a.seed + (a.seed_dev ? (uint64_t)*a.seed_dev : 0ull));
 
   for (int ci = blockIdx.x * kAttnWarps + wid; ci < nC; ci += gridDim.x * kAttnWarps) {
     const int64_t row = a.centre_ids ? a.centre_ids[ci] : ci;
@@ -112,10 +114,10 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_fwd_kernel(AttnArgs a
 #pragma unroll
       for (int u = 0; u < kEB; ++u) {
         if (u < ne) {
-          const float rt = attn_rel_t(a, jn[u], eid[u]);
+          const long long mr = a.msg_rows ? a.msg_rows[eid[u]] : eid[u];
+          const float rt = attn_rel_t(a, jn[u], mr);
           for (int d = lane; d < a.Dt; d += 32)
             ea[d * kEB + u] = cosf(__fmaf_rn(rt, a.time_w[d], a.time_b[d]));
-          const long long mr = a.msg_rows ? a.msg_rows[eid[u]] : eid[u];
           const float* mp = a.msg + mr * a.De;
           for (int d = lane; d < a.De; d += 32) ea[(a.Dt + d) * kEB + u] = mp[d];
         } else {
@@ -248,8 +250,8 @@ int32_t tgn_attn_fwd(const float* proj, const void* last_update_local, int32_t l
                      const int32_t* edge_perm, const int64_t* centre_ids, int32_t num_centres,
                      const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
                      int32_t raw_dim, int32_t time_dim, const float* w_edge, const float* time_w,
-                     const float* time_b, float dropout_p, uint64_t seed, float* out,
-                     float* alpha_out, float* ee_out, void* stream) {
+                     const float* time_b, float dropout_p, uint64_t seed, const int64_t* seed_dev,
+                     float* out, float* alpha_out, float* ee_out, void* stream) {
   TGN_REQUIRE(num_centres >= 0 && heads >= 1 && heads <= kMaxHeads && head_dim >= 1,
               "attn_fwd: bad sizes (heads must be <= %d)", kMaxHeads);
   TGN_REQUIRE(heads * head_dim <= 32 * kMaxCH, "attn_fwd: heads*head_dim must be <= %d",
@@ -276,7 +278,7 @@ int32_t tgn_attn_fwd(const float* proj, const void* last_update_local, int32_t l
   a.row_ptr = row_ptr; a.edge_perm = edge_perm; a.centre_ids = centre_ids;
   a.centres = DevCount{num_centres_dev, num_centres};
   a.H = heads; a.C = head_dim; a.De = raw_dim; a.Dt = time_dim; a.w_edge = w_edge;
-  a.time_w = time_w; a.time_b = time_b; a.dropout_p = dropout_p; a.seed = seed; a.out = out;
+  a.time_w = time_w; a.time_b = time_b; a.dropout_p = dropout_p; a.seed = seed; a.seed_dev = seed_dev; a.out = out;
   a.alpha_out = alpha_out; a.ee_out = ee_out;
   int grid = ceil_div(num_centres, kAttnWarps);
   if (grid > kNumSMs) grid = kNumSMs;

@@ -34,6 +34,7 @@ struct AttnBwdArgs {
   const float* d_out;  // [Nb,HC]
   float dropout_p;
   uint64_t seed;
+  const int64_t* seed_dev;
   float* d_proj;  // [Nb,4HC]
   float* d_ee;    // [E,HC]
 };
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) attn_bwd_kernel(AttnBwdArgs a)
   const float inv_sqrt_c = rsqrtf((float)a.C);
   const int CH = (HC + 31) >> 5;
   const float keep = 1.f - a.dropout_p;
-  Philox rng(a.seed);
+  Philox rng(a.seed + (a.seed_dev ? (uint64_t)*a.seed_dev : 0ull));
   for (int ci = blockIdx.x * kBwdWarps + wid; ci < nC; ci += gridDim.x * kBwdWarps) {
     const int64_t row = a.centre_ids ? a.centre_ids[ci] : ci;
     const float* pr = a.proj + row * 4 * HC;
@@ -184,15 +185,16 @@ __global__ void attn_edge_attr_kernel(EdgeAttrArgs a) {
     }
     if (d < a.Dt) {
       const int64_t j = a.nbr[e];
+      const long long pr = a.msg_rows ? a.msg_rows[e] : e;
       float rt;
       if (!a.lu_is_float && !a.t_is_float) {
         rt = (float)(reinterpret_cast<const int64_t*>(a.lu)[j] -
-                     reinterpret_cast<const int64_t*>(a.t_edge)[e]);
+                     reinterpret_cast<const int64_t*>(a.t_edge)[pr]);
       } else {
         const float l = a.lu_is_float ? reinterpret_cast<const float*>(a.lu)[j]
                                       : (float)reinterpret_cast<const int64_t*>(a.lu)[j];
-        const float t = a.t_is_float ? reinterpret_cast<const float*>(a.t_edge)[e]
-                                     : (float)reinterpret_cast<const int64_t*>(a.t_edge)[e];
+        const float t = a.t_is_float ? reinterpret_cast<const float*>(a.t_edge)[pr]
+                                     : (float)reinterpret_cast<const int64_t*>(a.t_edge)[pr];
         rt = l - t;
       }
       a.ea[x] = cosf(__fmaf_rn(rt, a.time_w[d], a.time_b[d]));
@@ -226,7 +228,8 @@ int32_t tgn_attn_bwd(const float* proj, const int64_t* nbr_local, const int32_t*
                      const int32_t* edge_perm, const int64_t* centre_ids, int32_t num_centres,
                      const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
                      const float* alpha, const float* ee, const float* d_out, float dropout_p,
-                     uint64_t seed, float* d_proj, float* d_ee, void* stream) {
+                     uint64_t seed, const int64_t* seed_dev, float* d_proj, float* d_ee,
+                     void* stream) {
   TGN_REQUIRE(num_centres >= 0 && heads >= 1 && heads <= kBMaxHeads && head_dim >= 1 &&
                   heads * head_dim <= 32 * kBMaxCH,
               "attn_bwd: bad sizes");
@@ -237,7 +240,7 @@ int32_t tgn_attn_bwd(const float* proj, const int64_t* nbr_local, const int32_t*
   a.proj = proj; a.nbr = nbr_local; a.row_ptr = row_ptr; a.edge_perm = edge_perm;
   a.centre_ids = centre_ids; a.centres = DevCount{num_centres_dev, num_centres};
   a.H = heads; a.C = head_dim; a.alpha = alpha; a.ee = ee; a.d_out = d_out;
-  a.dropout_p = dropout_p; a.seed = seed; a.d_proj = d_proj; a.d_ee = d_ee;
+  a.dropout_p = dropout_p; a.seed = seed; a.seed_dev = seed_dev; a.d_proj = d_proj; a.d_ee = d_ee;
   int grid = ceil_div(num_centres, kBwdWarps);
   if (grid > kNumSMs * 4) grid = kNumSMs * 4;
   attn_bwd_kernel<<<grid, kBwdWarps * 32, 0, (cudaStream_t)stream>>>(a);

@@ -48,7 +48,8 @@ __global__ void unique_mark_kernel(const int64_t* __restrict__ ids, DevCount cnt
 __global__ void __launch_bounds__(1024, 1)
     unique_rank_kernel(uint32_t* __restrict__ l0, uint32_t* __restrict__ l1, int64_t n_groups,
                        int64_t n_l1_words, int64_t* __restrict__ out_ids, int32_t out_cap,
-                       int64_t* __restrict__ assoc, int32_t* __restrict__ out_count) {
+                       int64_t* __restrict__ assoc, int32_t* __restrict__ out_count,
+                       int keep_marks) {
   __shared__ int s_warp[32];
   __shared__ int s_base, s_total;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -105,14 +106,14 @@ __global__ void __launch_bounds__(1024, 1)
             ++pos;
           }
         }
-        p[q] = make_uint4(0, 0, 0, 0);
+        if (!keep_marks) p[q] = make_uint4(0, 0, 0, 0);
       }
     }
     __syncthreads();
     if (tid == 0) s_base += s_total;
     if (tid < 32) {
       int64_t wi = (g0 >> 5) + tid;
-      if (wi < n_l1_words) l1[wi] = 0;
+      if (wi < n_l1_words && !keep_marks) l1[wi] = 0;
     }
     __syncthreads();
   }
@@ -154,13 +155,14 @@ int32_t tgn_unique_mark(const int64_t* ids, int32_t count, const int32_t* count_
 }
 
 int32_t tgn_unique_rank(void* bitmap, int64_t num_nodes, int64_t* out_ids, int32_t out_cap,
-                        int64_t* assoc, int32_t* out_count, void* stream) {
+                        int64_t* assoc, int32_t* out_count, int32_t keep_marks, void* stream) {
   TGN_REQUIRE(bitmap && out_ids && out_count && num_nodes > 0 && out_cap >= 0,
               "unique_rank: bad arguments");
   uint32_t* l0 = (uint32_t*)bitmap;
   uint32_t* l1 = l0 + l0_words(num_nodes);
   unique_rank_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
-      l0, l1, l0_groups(num_nodes), l1_words(num_nodes), out_ids, out_cap, assoc, out_count);
+      l0, l1, l0_groups(num_nodes), l1_words(num_nodes), out_ids, out_cap, assoc, out_count,
+      keep_marks);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

@@ -65,9 +65,9 @@ def unique_mark(ids: Tensor, num_nodes: int, bitmap: Tensor, count_dev: Optional
 
 
 def unique_rank(num_nodes: int, bitmap: Tensor, out_ids: Tensor, assoc: Optional[Tensor],
-                out_count: Tensor):
+                out_count: Tensor, keep_marks: bool = False):
     check(_L().tgn_unique_rank(_p(bitmap), num_nodes, _p(out_ids), out_ids.numel(), _p(assoc),
-                               _p(out_count), _stream()))
+                               _p(out_count), int(keep_marks), _stream()))
 
 
 def unique_relabel(id_lists: Sequence[Tensor], num_nodes: int,
@@ -176,7 +176,8 @@ def tcsr_sample(indptr: Tensor, indices: Tensor, eid: Tensor, ts: Tensor, roots:
     cnt = torch.empty(1, dtype=torch.int32, device=dev)
     ws = torch.empty(max(_L().tgn_tcsr_sample_ws_bytes(R), 16) // 8, dtype=torch.int64, device=dev)
     check(_L().tgn_tcsr_sample(_p(indptr), _p(indices), _p(eid), _p(ts), indptr.numel() - 1,
-                               _p(roots), _p(root_ts), R, k, strategy, offset, duration, seed,
+                               _p(roots), _p(root_ts), R, k, strategy, offset, duration,
+                               int(seed) & 0xFFFFFFFFFFFFFFFF,
                                _p(o_n), _p(o_c), _p(o_e), _p(o_t), _p(o_d), _p(off), _p(cnt),
                                _p(ws), _stream()))
     return (o_n, o_c, o_e, o_t, o_d), off, cnt
@@ -291,9 +292,8 @@ class MsgStore:
         dst = _need(dst, torch.int64, "dst")
         raw = _need(raw_msg, torch.float32, "raw_msg") if self.raw_dim else None
         t = t.contiguous()
-        for lo in range(0, B, SORT_MAX):
-            if B > SORT_MAX:
-                raise _cabi.TgnError(f"update_state batch {B} exceeds TGN_SORT_MAX={SORT_MAX}")
+        if B > SORT_MAX:
+            raise _cabi.TgnError(f"update_state batch {B} exceeds TGN_SORT_MAX={SORT_MAX}")
         check(_L().tgn_msgstore_update(ctypes.byref(self.struct()), _p(src), _p(dst), _p(t), _p(raw),
                                        B, self.size, _p(base_dev), _stream()))
         self.size += B
@@ -597,8 +597,8 @@ class _AttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w_node, b_node, w_edge, time_w, time_b, lu, nbr, t_edge, msg, msg_rows,
                 row_ptr, edge_perm, centre_ids, heads, dropout_p, seed, counts):
-        # counts = (rows_dev, edges_dev, centres_dev) or None
-        rows_dev, edges_dev, centres_dev = counts if counts is not None else (None, None, None)
+        # counts = (rows_dev, edges_dev, centres_dev, seed_dev) or None
+        rows_dev, edges_dev, centres_dev, seed_dev = counts if counts is not None else (None,) * 4
         Nb, Din = x.shape
         HC = w_edge.shape[0]
         C = HC // heads
@@ -613,22 +613,23 @@ class _AttnFn(torch.autograd.Function):
         alpha = torch.empty((max(E, 1), heads), dtype=torch.float32, device=dev)
         ee = torch.empty((max(E, 1), HC), dtype=torch.float32, device=dev)
         lu_f, t_f = _t_flag(lu), _t_flag(t_edge)
-        if nC:
+        if nC and E:  # no edges: every row is its skip projection (already written)
             check(_L().tgn_attn_fwd(_p(proj), _p(lu), lu_f, _p(nbr), _p(t_edge), t_f, _p(msg),
                                     _p(msg_rows), _p(row_ptr), _p(edge_perm), _p(centre_ids), nC,
                                     _p(centres_dev), heads, C, De, Dt, _p(w_edge), _p(time_w),
-                                    _p(time_b), float(dropout_p), int(seed), _p(out), _p(alpha),
+                                    _p(time_b), float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(seed_dev), _p(out), _p(alpha),
                                     _p(ee), _stream()))
         ctx.save_for_backward(x, w_node, w_edge, time_w, time_b, lu, nbr, t_edge, msg, msg_rows,
                               row_ptr, edge_perm, centre_ids, proj, alpha, ee)
-        ctx.meta = (heads, C, De, Dt, float(dropout_p), int(seed), rows_dev, edges_dev, centres_dev)
+        ctx.meta = (heads, C, De, Dt, float(dropout_p), int(seed), rows_dev, edges_dev, centres_dev,
+                    seed_dev)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         (x, w_node, w_edge, time_w, time_b, lu, nbr, t_edge, msg, msg_rows, row_ptr, edge_perm,
          centre_ids, proj, alpha, ee) = ctx.saved_tensors
-        heads, C, De, Dt, p, seed, rows_dev, edges_dev, centres_dev = ctx.meta
+        heads, C, De, Dt, p, seed, rows_dev, edges_dev, centres_dev, seed_dev = ctx.meta
         Nb, Din = x.shape
         HC = heads * C
         E = nbr.numel()
@@ -644,7 +645,7 @@ class _AttnFn(torch.autograd.Function):
         d_tb = torch.zeros_like(time_b)
         if nC and E:
             check(_L().tgn_attn_bwd(_p(proj), _p(nbr), _p(row_ptr), _p(edge_perm), _p(centre_ids), nC,
-                                    _p(centres_dev), heads, C, _p(alpha), _p(ee), _p(d_out), p, seed,
+                                    _p(centres_dev), heads, C, _p(alpha), _p(ee), _p(d_out), p, seed & 0xFFFFFFFFFFFFFFFF, _p(seed_dev),
                                     _p(d_proj), _p(d_ee), _stream()))
             ea = torch.empty((E, De_in), dtype=torch.float32, device=dev)
             rel = torch.empty(E, dtype=torch.float32, device=dev)

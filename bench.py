@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Headline benchmark: train events/sec of the TGN step (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (B200 path)
+    python bench.py --impl reference --steps K --warmup W    # reference CPU path (oracle port)
+
+Workload at N=1 (BASELINE.json configs[1]): synthetic tgbl-review shape (352,637 nodes,
+D_e=1), batch 200, 10 most-recent neighbours, memory/time/embedding dim 100, Adam lr 1e-4,
+attention dropout 0.1.  One step = sample -> memory -> attention -> decode -> BCE ->
+backward -> Adam -> update_state -> insert on one batch.  The step starts from a mid-epoch
+state (neighbour rings filled by the first `--prefill` events) so that every root has its K
+neighbours, as in steady-state training.
+
+value  : events/s with the event arrays resident in HBM (CUDA-graph replay, CUDA events).
+e2e    : events/s through TGNEngine with HOST batches: per step two H2D copies from pinned
+         memory (ids+timestamps, messages) and a D2H read of the loss.
+N > 1  : the training step does not shard across batches (batch i+1 reads the memory batch i
+         wrote, memory_module.py:126-138): N independent replicas, weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, "tgb-tgn-dgl_b200")
+for _p in (REPO, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOAD = "tgbl-review"
+HIDDEN = 100
+LR = 1e-4
+
+
+def ring_after(src, dst, t, K, N):
+    """Neighbour ring (neighbors, e_id, t) after inserting events 0..len-1 in order -- the K
+    largest event ids per node (neighbor_loader.py:52-104), built vectorised on the host."""
+    E = src.size
+    nodes = np.concatenate([dst, src])
+    nbrs = np.concatenate([src, dst])
+    eid = np.concatenate([np.arange(E), np.arange(E)])
+    order = np.lexsort((-eid, nodes))
+    nodes, nbrs, eid = nodes[order], nbrs[order], eid[order]
+    start = np.flatnonzero(np.r_[True, nodes[1:] != nodes[:-1]])
+    rank = np.arange(nodes.size) - np.repeat(start, np.diff(np.r_[start, nodes.size]))
+    keep = rank < K
+    nb = np.zeros((N, K), np.int64)
+    ei = np.full((N, K), -1, np.int64)
+    tt = np.full((N, K), -1.0, np.float32)
+    nb[nodes[keep], rank[keep]] = nbrs[keep]
+    ei[nodes[keep], rank[keep]] = eid[keep]
+    tt[nodes[keep], rank[keep]] = t[eid[keep]].astype(np.float32)
+    return nb, ei, tt
+
+
+def init_state_dicts(raw_dim, hidden, num_nodes, seed):
+    """Random-init weights with the reference's initialisers (pyg_model_utils.getModel)."""
+    from modules.decoder import LinkPredictor
+    from modules.emb_module import GraphAttentionEmbedding
+    from modules.memory_module import TGNMemory
+    from modules.msg_agg import LastAggregator
+    from modules.msg_func import IdentityMessage
+    torch.manual_seed(seed)
+    mem = TGNMemory(1, raw_dim, hidden, hidden, IdentityMessage(raw_dim, hidden, hidden), LastAggregator())
+    gnn = GraphAttentionEmbedding(hidden, hidden, raw_dim, mem.time_enc)
+    lp = LinkPredictor(hidden)
+    strip = {k: v for k, v in mem.state_dict().items() if k not in ("memory", "last_update", "_assoc")}
+    return strip, gnn.state_dict(), lp.state_dict()
+
+
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def run_cpu_reference(data, steps, warmup, prefill, budget_s):
+    """The reference's CPU path for the same step: oracle port of modules/* + neighbor_loader
+    (Python-dict message store included -- that is the reference's algorithm), torch CPU with
+    all host threads.  Bounded by `budget_s` seconds of timed work."""
+    from oracle import tgn_oracle as orc
+    N, De, B, K = data["num_nodes"], data["raw_dim"], data["batch"], data["K"]
+    model = orc.build_model(De, HIDDEN, N, seed=1)
+    for m in model.values():
+        m.train()
+    loader = orc.TorchNeighborLoader(N, K)
+    nb, ei, tt = ring_after(data["src"][:prefill], data["dst"][:prefill], data["t"][:prefill], K, N)
+    loader.neighbors, loader.e_id, loader.t = torch.from_numpy(nb), torch.from_numpy(ei), torch.from_numpy(tt)
+    loader.cur_e_id = prefill
+    opt = torch.optim.Adam(orc.model_parameters(model), lr=LR)
+    ev = {k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")}
+    done, t_timed = 0, 0.0
+    for s in range(warmup + steps):
+        lo = prefill + s * B
+        sl = slice(lo, lo + B)
+        t0 = time.perf_counter()
+        orc.train_step(model, loader, opt, ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl], ev["msg"][sl],
+                       ev["t"], ev["msg"], dropout=True)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            t_timed += dt
+            done += 1
+            if t_timed > budget_s:
+                break
+    return done, t_timed
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--prefill", type=int, default=1_000_000)
+    ap.add_argument("--cpu-steps", type=int, default=60, help="bounded sample of the CPU baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K_steps, W = args.steps, max(args.warmup, 3)
+
+    from tgn_b200 import synth
+    cfg = synth.SHAPES[WORKLOAD]
+    B, K = cfg["B"], cfg["K"]
+    need = args.prefill + (2 * (W + K_steps) + 8) * B
+    config = {"workload": f"synthetic {WORKLOAD} shape: {cfg['N']} nodes, raw_dim {cfg['De']}, batch {B}, "
+                          f"{K} recent nbrs, dim {HIDDEN}, Adam lr {LR}, ring prefilled with {args.prefill} events",
+              "l2": "inputs differ every step (new batch, new ring/memory rows); weights (~1.2 MB) stay L2-resident by design",
+              "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (step does not shard across batches)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        data = synth.synth_events(WORKLOAD, seed=0, max_events=args.prefill + (W + K_steps + 2) * B)
+        torch.set_num_threads(os.cpu_count() or 1)
+        done, t_timed = run_cpu_reference(data, K_steps, W, args.prefill, budget_s=150.0)
+        val = done * B / t_timed
+        line = {"impl": "reference", "metric": "train events/sec (TGN step)", "value": val, "unit": "events/s",
+                "n_gpus": args.gpus, "steps": done, "warmup": W, "ms_per_step": 1e3 * t_timed / done,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "events/s", "cores": torch.get_num_threads(), "kind": "port",
+                                 "sample": f"{done} of {K_steps} requested steps (150 s budget), oracle port of the reference's torch-CPU path"},
+                "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the B200 path has no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from tgn_b200.engine import TGNEngine
+    data = synth.synth_events(WORKLOAD, seed=rank, max_events=need)
+    N, De = data["num_nodes"], data["raw_dim"]
+    eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.1, use_graph=True,
+                    log_capacity=data["src"].size, seed=1234 + rank)
+    eng.load_state(*init_state_dicts(De, HIDDEN, N, seed=1))
+    ev = {k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")}
+    eng.set_events(**ev)
+    ring = ring_after(data["src"][:args.prefill], data["dst"][:args.prefill], data["t"][:args.prefill], K, N)
+    eng.prefill(args.prefill, tuple(torch.from_numpy(a) for a in ring))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm
+    for _ in range(W):
+        eng.train_step(from_device=True)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K_steps):
+        eng.train_step(from_device=True)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    loss_dev = float(eng.loss)
+
+    # ---------------- end-to-end arm: host batches, H2D every step, loss read back every step
+    pos = eng.events_done
+    pack = torch.empty(((W + K_steps), 4 * B), dtype=torch.long).pin_memory()
+    msgs = torch.empty(((W + K_steps), B, max(De, 1)), dtype=torch.float32).pin_memory()
+    for s in range(W + K_steps):
+        sl = slice(pos + s * B, pos + (s + 1) * B)
+        pack[s] = torch.cat([ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl]])
+        msgs[s] = ev["msg"][sl]
+    for s in range(W):
+        eng.stage_packed(pack[s], msgs[s])
+        float(eng.train_step(from_device=False))
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for s in range(W, W + K_steps):
+        eng.stage_packed(pack[s], msgs[s])
+        loss_host = float(eng.train_step(from_device=False))
+    f1.record()
+    barrier()
+    clocks.stop_flag = True
+    ms_e2e = torch.tensor([f0.elapsed_time(f1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(ms), float(ms_e2e)
+
+    # ---------------- launches per step (counted once, outside the timed region)
+    from torch.profiler import ProfilerActivity, profile
+    eng_use_graph = eng.use_graph
+    eng.use_graph = False
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        eng.train_step(from_device=True)
+        torch.cuda.synchronize()
+    eng.use_graph = eng_use_graph
+    kern = [e for e in prof.events() if e.device_type is not None and "cuda" in str(e.device_type).lower()]
+    ours = [e for e in kern if "tgn::" in e.name]
+    per_kernel = {}
+    for e in kern:
+        key = e.name.split("(")[0][-60:]
+        per_kernel.setdefault(key, [0, 0.0])
+        per_kernel[key][0] += 1
+        per_kernel[key][1] += e.device_time
+    top = sorted(per_kernel.items(), key=lambda kv: -kv[1][1])[:6]
+
+    # ---------------- roofline of the dominant kernel: the GRU input-gate GEMM
+    roof = dominant_kernel_roofline(eng, dev)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        line = {"metric": "train events/sec (TGN step)", "value": world * K_steps * B / (ms / 1e3), "unit": "events/s",
+                "n_gpus": world, "steps": K_steps, "warmup": W, "ms_per_step": ms / K_steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "e2e": {"value": world * K_steps * B / (ms_e2e / 1e3), "unit": "events/s",
+                        "h2d_bytes_per_step": 4 * B * 8 + B * De * 4, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / K_steps},
+                "gpu_launches": len(ours) * K_steps,
+                "launches_per_step": {"tgn_kernels": len(ours), "all_kernels": len(kern)},
+                "top_kernels_eager_us": {k: [v[0], round(v[1], 1)] for k, v in top},
+                "clocks": clocks.summary(), "final_loss": {"device_arm": loss_dev, "e2e_arm": loss_host},
+                "roofline": roof_with_peak(roof, peaks)}
+        if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            cdata = synth.synth_events(WORKLOAD, seed=0, max_events=args.prefill + (args.cpu_steps + 8) * B)
+            done, t_cpu = run_cpu_reference(cdata, args.cpu_steps, 5, args.prefill, budget_s=40.0)
+            line["cpu_baseline"] = {"value": done * B / t_cpu, "unit": "events/s", "cores": torch.get_num_threads(),
+                                    "kind": "port", "ms_per_step": 1e3 * t_cpu / done,
+                                    "sample": f"{done} training steps of the same workload (same shape, batch, prefill) "
+                                              "on the host CPU, oracle port of the reference's torch-CPU path"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(eng, dev):
+    """Times the kernel that dominates the step -- the fp32 GRU input-gate GEMM
+    gi[S,300] = x[S,Dx] W_ih^T + b (tgn::sgemm_kernel) -- alone, on the step's own shapes,
+    with CUDA events on the launching stream.  Algorithmic work per launch:
+    2*S*Dx*3D flops; bytes S*Dx*4 + 3D*Dx*4 + S*3D*4."""
+    from tgn_b200 import ops
+    S = int(eng.Nb_dev.item())
+    Dx, D = eng.Dx, eng.D
+    x = torch.randn(max(S, 1), Dx, device=dev)
+    w, b = eng.p["memory_updater.weight_ih"].detach(), eng.p["memory_updater.bias_ih"].detach()
+    out = torch.empty(max(S, 1), 3 * D, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    times = []
+    for i in range(13):
+        flush.zero_()                      # evict L2 between timed launches
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.sgemm(x, w, b, m=S, n=3 * D, k=Dx, lda=Dx, ldb=Dx, out=out)
+        c.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(a.elapsed_time(c) * 1e-3)
+    t = float(np.mean(times))
+    flops = 2.0 * S * Dx * 3 * D
+    nbytes = 4.0 * (S * Dx + 3 * D * Dx + S * 3 * D)
+    return {"kernel": "tgn::sgemm_kernel<false,false> (GRU gate GEMM gi = x W_ih^T)", "rows": S, "seconds": t,
+            "flops": flops, "bytes": nbytes}
+
+
+def roof_with_peak(r, peaks):
+    peak = peaks.get("bf16_tflops", 1590.0)
+    ach = r["flops"] / r["seconds"] / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": None, "kernel": r["kernel"], "rows_per_launch": r["rows"], "us_per_launch": r["seconds"] * 1e6,
+            "algorithmic_flops_per_launch": r["flops"], "algorithmic_bytes_per_launch": r["bytes"],
+            "achieved_gbs": r["bytes"] / r["seconds"] / 1e9,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1590 (B200_PROFILING.md)",
+            "note": "fp32 CUDA-core GEMM measured against the bf16 tensor peak: the tcgen05 port of this kernel is the next optimisation"}
+
+
+if __name__ == "__main__":
+    main()

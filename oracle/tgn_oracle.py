@@ -419,4 +419,4 @@ def train_step(model, loader: TorchNeighborLoader, optimizer, src, dst, neg, t, 
     loss.backward()
     optimizer.step()
     memory.detach()
-    return float(loss)
+    return float(loss.detach())

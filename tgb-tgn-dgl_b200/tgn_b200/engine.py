@@ -101,8 +101,9 @@ class TGNEngine:
         Nb = min(self.N, R + E)
         i64 = dict(dtype=torch.long, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
-        self.in_ids3 = torch.zeros(3 * B, **i64)
-        self.in_t_i64 = torch.zeros(B, **i64)
+        self.in_i64 = torch.zeros(4 * B, **i64)          # [src | dst | neg | t]: one H2D copy per step
+        self.in_ids3 = self.in_i64[:3 * B]
+        self.in_t_i64 = self.in_i64[3 * B:]
         self.in_t_f32 = torch.zeros(B, device=dev)
         self.in_msg = torch.zeros((B, max(self.De, 1)), device=dev)
         self.roots = torch.zeros(R, **i64)
@@ -183,6 +184,28 @@ class TGNEngine:
         check(_L().tgn_batch_load(_p(ev["src"]), _p(ev["dst"]), _p(ev["neg"]), _p(ev["t"]), _p(ev["msg"]),
                                   self.De, self.B, _p(self.pos_dev), _p(self.in_ids3), _p(self.in_t_i64),
                                   _p(self.in_t_f32), _p(self.in_msg), _stream()))
+
+    def stage_packed(self, ids_t: Tensor, msg: Tensor):
+        """End-to-end staging: `ids_t` = pinned host int64 [4B] = [src|dst|neg|t], `msg` pinned
+        host float32 [B, De]; two H2D copies, the float timestamps are derived on the device."""
+        self.in_i64.copy_(ids_t, non_blocking=True)
+        if self.De:
+            self.in_msg.copy_(msg, non_blocking=True)
+        self.in_t_f32.copy_(self.in_t_i64)
+
+    def prefill(self, count: int, ring_state=None):
+        """Start from a mid-epoch state: the first `count` events of set_events() are taken as
+        already seen.  ring_state = (neighbors, e_id, t) host/device tensors of the ring after
+        those events (bench.py builds them vectorised); the cursors move to `count`."""
+        if ring_state is not None:
+            self.neighbors.copy_(ring_state[0])
+            self.e_id.copy_(ring_state[1])
+            self.t_ring.copy_(ring_state[2])
+        self.cur_e_id_dev.fill_(count)
+        self.log_base_dev.fill_(count)
+        self.pos_dev.fill_(count)
+        self.events_done = count
+        self.store.size = count
 
     def stage_batch(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor):
         """Copies one batch (host or device tensors) into the static step buffers."""

@@ -212,6 +212,15 @@ int32_t tgn_sgemm(const float* a, const int64_t* a_rows, const float* b, const f
                   const int32_t* k_dev, int32_t lda, int32_t ldb, int32_t ldc, int32_t trans_a,
                   int32_t trans_b, int32_t accumulate, int32_t split_k, void* stream);
 
+/* Same contract as tgn_sgemm on the tcgen05 tensor cores (kind::tf32, fp32
+ * accumulate in TMEM).  precision = 1: operands rounded to tf32 (~1e-3 relative);
+ * precision = 3: 3xTF32 error-compensated split, fp32-level accuracy (~1e-6). */
+int32_t tgn_tc_gemm(const float* a, const int64_t* a_rows, const float* b, const float* bias,
+                    float* c, int32_t m, const int32_t* m_dev, int32_t n, int32_t k,
+                    const int32_t* k_dev, int32_t lda, int32_t ldb, int32_t ldc, int32_t trans_a,
+                    int32_t trans_b, int32_t accumulate, int32_t split_k, int32_t precision,
+                    void* stream);
+
 /* GRUCell / RNNCell gate math (torch.nn.GRUCell semantics, gate order r,z,n):
  *   gi = x W_ih^T + b_ih [S,3D], gh = h W_hh^T + b_hh [S,3D]  (from tgn_sgemm)
  *   r = sig(gi_r+gh_r), z = sig(gi_z+gh_z), n = tanh(gi_n + r*gh_n)

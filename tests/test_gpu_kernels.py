@@ -223,34 +223,43 @@ def test_aggregators_golden_and_ties(ops):
 
 
 # ------------------------------------------------------------------ dense
+@pytest.mark.parametrize("prec", [0, 3, 1])
 @pytest.mark.parametrize("ta", [False, True])
 @pytest.mark.parametrize("tb", [False, True])
 @pytest.mark.parametrize("m,n,k,split", [(1, 1, 1, 1), (65, 300, 472, 1), (600, 400, 100, 1), (300, 472, 4000, 8),
-                                         (129, 63, 17, 2)])
-def test_sgemm(ops, ta, tb, m, n, k, split):
+                                         (129, 63, 17, 2), (5023, 300, 472, 1)])
+def test_sgemm(ops, prec, ta, tb, m, n, k, split):
+    """prec 0: fp32 CUDA cores; 3: tcgen05 3xTF32 (same tolerance); 1: tcgen05 tf32 (2e-2 bar)."""
     g = torch.Generator(device="cpu").manual_seed(m * n + k)
     A = torch.randn((k, m) if ta else (m, k), generator=g)
     B = torch.randn((k, n) if tb else (n, k), generator=g)
     bias = torch.randn(n, generator=g)
     ref = (A.t() if ta else A).double() @ (B if tb else B.t()).double() + bias.double()
     out = ops.sgemm(A.to(DEV), B.to(DEV), bias.to(DEV), m=m, n=n, k=k, lda=A.shape[1], ldb=B.shape[1],
-                    trans_a=ta, trans_b=tb, split_k=split)
+                    trans_a=ta, trans_b=tb, split_k=split, prec=prec)
+    if prec == 1:
+        scale = float(ref.abs().max())
+        torch.testing.assert_close(out.cpu().double(), ref, rtol=2e-2, atol=2e-3 * max(scale, 1.0))
+        return
     # fp32 accumulation over k terms of N(0,1) products: error grows ~ sqrt(k) * eps * |sum|
     torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-5, atol=1e-5 * max(4.0, k ** 0.5))
 
 
-def test_sgemm_gather_and_device_counts(ops):
+@pytest.mark.parametrize("prec", [0, 3])
+def test_sgemm_gather_and_device_counts(ops, prec):
     g = torch.Generator(device="cpu").manual_seed(0)
     table = torch.randn(50, 24, generator=g); W = torch.randn(30, 24, generator=g)
     rows = torch.randint(0, 50, (40,), generator=g)
     cnt = torch.tensor([33], dtype=torch.int32, device=DEV)
     out = torch.full((40, 30), 7.0, device=DEV)
-    ops.sgemm(table.to(DEV), W.to(DEV), m=40, n=30, k=24, lda=24, ldb=24, a_rows=rows.to(DEV), out=out, m_dev=cnt)
+    ops.sgemm(table.to(DEV), W.to(DEV), m=40, n=30, k=24, lda=24, ldb=24, a_rows=rows.to(DEV), out=out, m_dev=cnt,
+              prec=prec)
     torch.testing.assert_close(out[:33].cpu(), table[rows[:33]] @ W.t(), rtol=1e-5, atol=1e-5)
     assert bool((out[33:] == 7.0).all())
     # reduction length from the device: C = A^T B over the first 33 rows only
     A = torch.randn(40, 12, generator=g); B = torch.randn(40, 9, generator=g)
-    got = ops.sgemm(A.to(DEV), B.to(DEV), m=12, n=9, k=40, lda=12, ldb=9, trans_a=True, trans_b=True, k_dev=cnt)
+    got = ops.sgemm(A.to(DEV), B.to(DEV), m=12, n=9, k=40, lda=12, ldb=9, trans_a=True, trans_b=True, k_dev=cnt,
+                    prec=prec)
     torch.testing.assert_close(got.cpu(), A[:33].t() @ B[:33], rtol=1e-5, atol=1e-5)
 
 

@@ -340,21 +340,41 @@ class MsgStore:
 # ---------------------------------------------------------------------------
 # dense
 # ---------------------------------------------------------------------------
+# GEMM engine of the dense path: 0 = fp32 FMA on CUDA cores (tgn_sgemm, the 1e-5 parity path),
+# 1 = tcgen05 kind::tf32 (fastest, ~1e-3), 3 = tcgen05 3xTF32 (tensor cores, fp32-level accuracy).
+GEMM_PRECISION = 3
+
+
+def set_gemm_precision(mode: int) -> int:
+    global GEMM_PRECISION
+    if mode not in (0, 1, 3):
+        raise ValueError("gemm precision must be 0 (fp32 CUDA cores), 1 (tf32) or 3 (3xtf32)")
+    old, GEMM_PRECISION = GEMM_PRECISION, mode
+    return old
+
+
 def sgemm(a: Tensor, b: Tensor, bias: Optional[Tensor] = None, *, m: int, n: int, k: int,
           lda: int, ldb: int, trans_a: bool = False, trans_b: bool = False,
           out: Optional[Tensor] = None, ldc: Optional[int] = None, accumulate: bool = False,
           split_k: int = 1, a_rows: Optional[Tensor] = None, m_dev: Optional[Tensor] = None,
-          k_dev: Optional[Tensor] = None, a_off: int = 0, b_off: int = 0) -> Tensor:
-    """C[m,n] (=|+=) op(A) op(B) (+bias) on the fp32 CUDA-core path.
+          k_dev: Optional[Tensor] = None, a_off: int = 0, b_off: int = 0,
+          prec: Optional[int] = None) -> Tensor:
+    """C[m,n] (=|+=) op(A) op(B) (+bias); engine chosen by `prec` / GEMM_PRECISION.
     a_off / b_off are element offsets into a / b (for column slices)."""
+    prec = GEMM_PRECISION if prec is None else prec
     if out is None:
         out = torch.empty((m, n), dtype=torch.float32, device=a.device)
         if split_k > 1:
             out.zero_()
     ldc = ldc if ldc is not None else out.stride(0)
-    check(_L().tgn_sgemm(a.data_ptr() + 4 * a_off, _p(a_rows), b.data_ptr() + 4 * b_off, _p(bias),
-                         _p(out), m, _p(m_dev), n, k, _p(k_dev), lda, ldb, ldc, int(trans_a),
-                         int(trans_b), int(accumulate), split_k, _stream()))
+    if prec == 0:
+        check(_L().tgn_sgemm(a.data_ptr() + 4 * a_off, _p(a_rows), b.data_ptr() + 4 * b_off, _p(bias),
+                             _p(out), m, _p(m_dev), n, k, _p(k_dev), lda, ldb, ldc, int(trans_a),
+                             int(trans_b), int(accumulate), split_k, _stream()))
+    else:
+        check(_L().tgn_tc_gemm(a.data_ptr() + 4 * a_off, _p(a_rows), b.data_ptr() + 4 * b_off, _p(bias),
+                               _p(out), m, _p(m_dev), n, k, _p(k_dev), lda, ldb, ldc, int(trans_a),
+                               int(trans_b), int(accumulate), split_k, prec, _stream()))
     return out
 
 

@@ -49,11 +49,11 @@ def test_memory_golden(force_unfused):
                 mem.eval()
             with torch.no_grad():
                 zz, lu = mem(cu(z[p + "q"]))
-            torch.testing.assert_close(zz.cpu(), torch.from_numpy(z[p + "z"]), rtol=1e-5, atol=2e-6)
+            torch.testing.assert_close(zz.cpu(), torch.from_numpy(z[p + "z"]), rtol=1e-5, atol=5e-6)
             assert np.array_equal(lu.cpu().numpy(), z[p + "lu"])            # bit-exact last_update
             mem.update_state(cu(z[p + "src"]), cu(z[p + "dst"]), cu(z[p + "t"]), cu(z[p + "raw"]))
             mem.detach()
-            torch.testing.assert_close(mem.memory.cpu(), torch.from_numpy(z[p + "memory"]), rtol=1e-5, atol=2e-6)
+            torch.testing.assert_close(mem.memory.cpu(), torch.from_numpy(z[p + "memory"]), rtol=1e-5, atol=5e-6)
             assert np.array_equal(mem.last_update.cpu().numpy(), z[p + "last_update"])
 
 

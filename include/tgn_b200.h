@@ -221,6 +221,29 @@ int32_t tgn_tc_gemm(const float* a, const int64_t* a_rows, const float* b, const
                     int32_t trans_b, int32_t accumulate, int32_t split_k, int32_t precision,
                     void* stream);
 
+/* Batched TMA + tcgen05 GEMM launch: up to 4 independent problems of the tgn_tc_gemm
+ * contract in ONE kernel (one CTA per 128x128 tile of any of them) -- e.g. the two GRU
+ * gate GEMMs, or a weight gradient together with the matching input gradient.
+ * Operands must be 16-byte aligned with lda/ldb multiples of 4 (TMA); no row gather.
+ * mode: 0 store, 1 C += , 2 atomic C += (required for split_k > 1; C initialised by caller).
+ * With k_dev the reduction stops at *k_dev exactly (the tail of the last k-block is
+ * masked in shared memory); with m_dev rows >= *m_dev of C are left untouched. */
+typedef struct tgn_gemm_desc {
+  const float* a;
+  const float* b;
+  const float* bias; /* nullable, [n] */
+  float* c;
+  const int32_t* m_dev; /* nullable */
+  const int32_t* k_dev; /* nullable */
+  int32_t m, n, k;
+  int32_t lda, ldb, ldc;
+  int32_t trans_a, trans_b;
+  int32_t mode;
+  int32_t split_k;
+} tgn_gemm_desc;
+int32_t tgn_gemm_batch(const tgn_gemm_desc* problems, int32_t count, int32_t precision,
+                       void* stream);
+
 /* GRUCell / RNNCell gate math (torch.nn.GRUCell semantics, gate order r,z,n):
  *   gi = x W_ih^T + b_ih [S,3D], gh = h W_hh^T + b_hh [S,3D]  (from tgn_sgemm)
  *   r = sig(gi_r+gh_r), z = sig(gi_z+gh_z), n = tanh(gi_n + r*gh_n)

@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(TcArgs g) {
   }
 }
 
+bool gemm_tma_ok(const float* a, const float* b, int lda, int ldb);  // gemm_tma.cu
 }  // namespace tgn
 
 using namespace tgn;
@@ -343,6 +344,16 @@ int32_t tgn_tc_gemm(const float* a, const int64_t* a_rows, const float* b, const
   if (m == 0 || n == 0) return TGN_OK;
   TGN_REQUIRE(a && b && c, "tc_gemm: NULL pointer");
   TGN_REQUIRE(!(trans_a && a_rows), "tc_gemm: row gather needs a row-major A");
+  if (!a_rows && gemm_tma_ok(a, b, lda, ldb)) {
+    // aligned, ungathered operands: the TMA-fed kernel (gemm_tma.cu)
+    tgn_gemm_desc d;
+    d.a = a; d.b = b; d.bias = bias; d.c = c; d.m_dev = m_dev; d.k_dev = k_dev;
+    d.m = m; d.n = n; d.k = k; d.lda = lda; d.ldb = ldb; d.ldc = ldc;
+    d.trans_a = trans_a; d.trans_b = trans_b;
+    d.mode = split_k > 1 ? 2 : (accumulate ? 1 : 0);
+    d.split_k = split_k;
+    return tgn_gemm_batch(&d, 1, precision, stream);
+  }
   const size_t smem = (size_t)kStages * kStageFloats * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {

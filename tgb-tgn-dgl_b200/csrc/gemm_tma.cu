@@ -1,0 +1,487 @@
+// TMA-fed tcgen05 GEMM (the dense engine of the training step):
+//     C[M,N] (=|+=|atomic+=) op(A)[M,K] * op(B)[K,N] (+ bias), fp32 in, fp32 accumulate in TMEM
+// for the GRU gate GEMMs (torch.nn.GRUCell at reference modules/memory_module.py:72,172),
+// the TransformerConv projections (modules/emb_module.py:21-23,29), the decoder
+// (modules/decoder.py:24-27) and all of their gradients.  Up to kMaxProb independent
+// problems share one launch (one CTA per 128x128 output tile of any of them).
+//
+// Warp roles (192 threads, one CTA per SM):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes straight into SWIZZLE_128B
+//               shared-memory tiles, completion on a per-stage mbarrier (tx bytes).  Rows /
+//               columns outside the tensor are zero-filled by the TMA unit, so no operand
+//               needs padding.  K-major operands (row-major [MN,K]) take one [128 x 32]
+//               box; MN-major operands (row-major [K,MN], i.e. the "transposed" operands of
+//               the gradient GEMMs) take four [32 k x 32 mn] boxes and are consumed by the
+//               tensor core through MN-major descriptors -- nothing is transposed in software
+//   warp 1      MMA issuer: one lane issues tcgen05.mma.kind::tf32 (M=128, N=128, K=8) from
+//               shared-memory descriptors into a 128-column TMEM accumulator, and releases a
+//               stage with tcgen05.commit
+//   warps 2-5   precision 3 ("3xTF32"): split every landed tile in place into hi = tf32(x)
+//               and lo = x - hi (fp32-exact), so that D += a_hi b_hi + a_hi b_lo + a_lo b_hi
+//               holds fp32-level accuracy (~1e-6); then the epilogue: tcgen05.ld of the
+//               accumulator (warp w owns TMEM lanes 32*(w%4)..), bias, 128-bit stores /
+//               vector reductions (split-K)
+//   precision 1: operands go to the tensor core as they land (tf32 mantissa), no split pass.
+#include <cuda.h>
+
+#include "../../include/tgn_b200.h"
+#include "common.cuh"
+
+namespace tgn {
+
+constexpr int GM = 128, GN = 128, GK = 32;    // GK floats = 128 bytes = one swizzle span
+constexpr int kGTileBytes = GM * GK * 4;      // 16 KB per operand tile
+constexpr int kGStageBytes = 4 * kGTileBytes; // A_hi, A_lo, B_hi, B_lo
+constexpr int kGStages = 3;
+constexpr int kGThreads = 192;
+constexpr int kMaxProb = 4;
+
+struct GemmProb {
+  float* c;
+  const float* bias;
+  const int32_t* m_dev;  // nullable: live row count of C / op(A)
+  const int32_t* k_dev;  // nullable: live reduction length
+  int m, n, k;           // host sizes (= tensor-map extents)
+  int ldc;
+  int a_mn, b_mn;  // operand is MN-major (stored [K, MN])
+  int split_k;
+  int mode;        // 0 store, 1 accumulate, 2 atomic add
+  int tiles_m, tiles_n;
+  int tile_begin;  // first linear CTA index of this problem
+};
+
+struct GemmParams {
+  GemmProb p[kMaxProb];
+  int nprob;
+  int prec;
+};
+
+struct alignas(64) GemmMaps {
+  CUtensorMap a[kMaxProb];
+  CUtensorMap b[kMaxProb];
+};
+
+__device__ __forceinline__ uint32_t g_smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void g_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void g_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  const uint32_t a = g_smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void g_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(g_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void g_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void g_tma_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                         int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(g_smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// shared-memory matrix descriptors.
+//   K-major : SWIZZLE_128B (16-byte chunks); 8-row x 128-byte atoms 1024 bytes apart (SBO)
+//   MN-major: tf32 operands only exist in the SWIZZLE_128B_BASE32B layout (32-byte chunks
+//             XOR k-row % 4): atoms are [4 k-rows x 32 mn]; next 4 k-rows at SBO = 512,
+//             next 32 mn at LBO = 4096 (one TMA box of 32 k-rows)
+__device__ __forceinline__ uint64_t g_desc(uint32_t saddr, bool mn_major) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(mn_major ? (4096 >> 4) : 1) << 16;
+  d |= (uint64_t)(mn_major ? (512 >> 4) : (1024 >> 4)) << 32;
+  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+  d |= (uint64_t)(mn_major ? 1 : 2) << 61; // SWIZZLE_128B_BASE32B : SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint32_t g_idesc(bool a_mn, bool b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;   // D = f32
+  d |= 2u << 7;   // A = tf32
+  d |= 2u << 10;  // B = tf32
+  d |= (a_mn ? 1u : 0u) << 15;
+  d |= (b_mn ? 1u : 0u) << 16;
+  d |= (uint32_t)(GN >> 3) << 17;
+  d |= (uint32_t)(GM >> 4) << 24;
+  return d;
+}
+__device__ __forceinline__ void g_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                      uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void g_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   g_smem_u32(bar))
+               : "memory");
+}
+
+// x -> (tf32(x) rounded to nearest, x - tf32(x)); element-wise, so the swizzle is irrelevant
+__device__ __forceinline__ void g_split4(float4& v, float4& lo) {
+  float* x = reinterpret_cast<float*>(&v);
+  float* l = reinterpret_cast<float*>(&lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float h = __uint_as_float((__float_as_uint(x[i]) + 0x1000u) & 0xFFFFE000u);
+    l[i] = x[i] - h;
+    x[i] = h;
+  }
+}
+
+// zero the elements of float4 number `idx` of a [128 x 32] SWIZZLE_128B tile whose k index
+// (within the k-block) is >= klive.  K-major: 8 float4 per row, k-chunk = position ^ (row & 7);
+// MN-major: four [32 k x 32 mn] boxes of 256 float4, the row inside a box is the k index.
+__device__ __forceinline__ void g_mask4(float4& v, int idx, bool mn_major, int klive) {
+  if (mn_major) {
+    if (((idx & 255) >> 3) >= klive) v = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    const int r = idx >> 3, kc = ((idx & 7) ^ (r & 7)) << 2;
+    if (kc + 0 >= klive) v.x = 0.f;
+    if (kc + 1 >= klive) v.y = 0.f;
+    if (kc + 2 >= klive) v.z = 0.f;
+    if (kc + 3 >= klive) v.w = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kGThreads, 1)
+    tgemm_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmParams prm) {
+  extern __shared__ __align__(1024) uint8_t g_smem[];
+  __shared__ __align__(8) uint64_t s_full[kGStages], s_conv[kGStages], s_empty[kGStages], s_acc;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- which problem / tile / K-split is this CTA
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxProb; ++i)
+    if (i < prm.nprob && (int)blockIdx.x >= prm.p[i].tile_begin) pi = i;
+  const GemmProb& P = prm.p[pi];
+  int local = blockIdx.x - P.tile_begin;
+  const int tn = local % P.tiles_n;
+  local /= P.tiles_n;
+  const int tm = local % P.tiles_m;
+  const int split = local / P.tiles_m;
+  const int M = P.m_dev ? min(*P.m_dev, P.m) : P.m;
+  const int K = P.k_dev ? min(*P.k_dev, P.k) : P.k;
+  const int m0 = tm * GM, n0 = tn * GN;
+  if (m0 >= M) return;
+  const int kchunk = ((K + P.split_k - 1) / P.split_k + GK - 1) / GK * GK;
+  const int kbeg = split * kchunk;
+  const int kend = min(K, kbeg + kchunk);
+  const int nk = kend > kbeg ? (kend - kbeg + GK - 1) / GK : 0;
+  if (nk == 0 && P.mode != 0) return;  // nothing to add
+  const bool split3 = prm.prec == 3;
+  // a live reduction length that ends inside the last 32-wide k-block (and inside the tensor,
+  // where the TMA unit does not zero-fill) is cut off by zeroing the tail of that block
+  const bool tail_mask = nk > 0 && kend < P.k && ((kend - kbeg) & (GK - 1)) != 0;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g_smem) + 1023) &
+                                             ~(uintptr_t)1023);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < kGStages; ++i) {
+      g_mbar_init(&s_full[i], 1);
+      g_mbar_init(&s_conv[i], 128);
+      g_mbar_init(&s_empty[i], 1);
+    }
+    g_mbar_init(&s_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     g_smem_u32(&s_tmem)),
+                 "r"(GN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const CUtensorMap* ma = &maps.a[pi];
+      const CUtensorMap* mb = &maps.b[pi];
+      asm volatile("prefetch.tensormap [%0];" ::"l"(ma) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(mb) : "memory");
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % kGStages;
+        if (kb >= kGStages) g_mbar_wait(&s_empty[s], ((kb / kGStages) - 1) & 1);
+        const uint32_t st = g_smem_u32(smem + (size_t)s * kGStageBytes);
+        const int k0 = kbeg + kb * GK;
+        g_mbar_expect_tx(&s_full[s], 2 * kGTileBytes);
+        if (!P.a_mn) {
+          g_tma_2d(st, ma, &s_full[s], k0, m0);
+        } else {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) g_tma_2d(st + b * 4096, ma, &s_full[s], m0 + 32 * b, k0);
+        }
+        if (!P.b_mn) {
+          g_tma_2d(st + 2 * kGTileBytes, mb, &s_full[s], k0, n0);
+        } else {
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            g_tma_2d(st + 2 * kGTileBytes + b * 4096, mb, &s_full[s], n0 + 32 * b, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = g_idesc(P.a_mn != 0, P.b_mn != 0);
+    const uint32_t a_step = P.a_mn ? 1024u : 32u, b_step = P.b_mn ? 1024u : 32u;
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % kGStages;
+      const bool conv = split3 || (tail_mask && kb == nk - 1);
+      g_mbar_wait(conv ? &s_conv[s] : &s_full[s], (kb / kGStages) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t a_hi = g_smem_u32(smem + (size_t)s * kGStageBytes);
+        const uint32_t a_lo = a_hi + kGTileBytes, b_hi = a_hi + 2 * kGTileBytes,
+                       b_lo = a_hi + 3 * kGTileBytes;
+#pragma unroll
+        for (int kk = 0; kk < GK / 8; ++kk) {  // one MMA consumes K = 8 tf32
+          const uint64_t dah = g_desc(a_hi + kk * a_step, P.a_mn != 0);
+          const uint64_t dbh = g_desc(b_hi + kk * b_step, P.b_mn != 0);
+          g_mma(tmem, dah, dbh, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+          if (split3) {
+            const uint64_t dal = g_desc(a_lo + kk * a_step, P.a_mn != 0);
+            const uint64_t dbl = g_desc(b_lo + kk * b_step, P.b_mn != 0);
+            g_mma(tmem, dah, dbl, idesc, 1u);
+            g_mma(tmem, dal, dbh, idesc, 1u);
+          }
+        }
+        g_commit(&s_empty[s]);
+        if (kb == nk - 1) g_commit(&s_acc);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== split pass (3xTF32) + epilogue: warps 2..5 =====
+    const int et = tid - 64;  // 0..127
+    if (split3 || tail_mask) {
+      for (int kb = split3 ? 0 : nk - 1; kb < nk; ++kb) {
+        const int s = kb % kGStages;
+        g_mbar_wait(&s_full[s], (kb / kGStages) & 1);
+        float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * kGStageBytes);
+        float4* a_lo = a_hi + kGTileBytes / 16;
+        float4* b_hi = a_hi + 2 * (kGTileBytes / 16);
+        float4* b_lo = a_hi + 3 * (kGTileBytes / 16);
+        const int klive = (tail_mask && kb == nk - 1) ? kend - (kbeg + kb * GK) : GK;
+#pragma unroll
+        for (int i = 0; i < kGTileBytes / 16 / 128; ++i) {
+          const int idx = i * 128 + et;
+          float4 va = a_hi[idx], la, vb = b_hi[idx], lb;
+          if (klive < GK) {
+            g_mask4(va, idx, P.a_mn != 0, klive);
+            g_mask4(vb, idx, P.b_mn != 0, klive);
+          }
+          if (split3) {
+            g_split4(va, la);
+            g_split4(vb, lb);
+            a_lo[idx] = la;
+            b_lo[idx] = lb;
+          }
+          a_hi[idx] = va;
+          b_hi[idx] = vb;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic -> async proxy
+        g_mbar_arrive(&s_conv[s]);
+      }
+    }
+    if (nk > 0) {
+      g_mbar_wait(&s_acc, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const int q = warp & 3;  // TMEM lane group this warp may read
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < M;
+    float* crow = P.c + (long long)row * P.ldc;
+    const bool vec_ok = (P.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.c) & 15) == 0);
+#pragma unroll 1
+    for (int cc = 0; cc < GN; cc += 32) {
+      const int c0 = n0 + cc;
+      if (c0 >= P.n) break;  // warp-uniform
+      uint32_t v[32];
+      if (nk > 0) {
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cc;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+              "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
+              "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+              "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (!row_ok) continue;
+      const bool full = c0 + 32 <= P.n;
+      const bool add_bias = P.bias != nullptr && split == 0;
+      if (full && vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          if (add_bias) {
+            const float4 b4 = *reinterpret_cast<const float4*>(P.bias + c0 + j);
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+          }
+          float4* dst = reinterpret_cast<float4*>(crow + c0 + j);
+          if (P.mode == 2) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x),
+                         "f"(o.y), "f"(o.z), "f"(o.w)
+                         : "memory");
+          } else if (P.mode == 1) {
+            const float4 old = *dst;
+            *dst = make_float4(old.x + o.x, old.y + o.y, old.z + o.z, old.w + o.w);
+          } else {
+            *dst = o;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = c0 + j;
+          if (n < P.n) {
+            float x = __uint_as_float(v[j]);
+            if (add_bias) x += P.bias[n];
+            if (P.mode == 2) atomicAdd(crow + n, x);
+            else if (P.mode == 1) crow[n] += x;
+            else crow[n] = x;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(GN));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// row-major fp32 matrix [rows, cols] with leading dimension ld -> 2-D tensor map whose
+// inner dimension is the column index; box = box_cols x box_rows, SWIZZLE_128B
+static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols,
+                    long long ld, int box_cols, int box_rows, bool mn_major) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_err(TGN_ECUDA, "gemm: cuTensorMapEncodeTiled is not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(TGN_ECUDA, "gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return TGN_OK;
+}
+
+bool gemm_tma_ok(const float* a, const float* b, int lda, int ldb) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0 &&
+         (lda & 3) == 0 && (ldb & 3) == 0;
+}
+
+}  // namespace tgn
+
+using namespace tgn;
+
+extern "C" {
+
+int32_t tgn_gemm_batch(const tgn_gemm_desc* d, int32_t count, int32_t precision, void* stream) {
+  TGN_REQUIRE(d && count >= 1 && count <= kMaxProb, "gemm_batch: 1..%d problems per launch", kMaxProb);
+  TGN_REQUIRE(precision == 1 || precision == 3, "gemm_batch: precision must be 1 (tf32) or 3 (3xtf32)");
+  GemmMaps maps;
+  GemmParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.prec = precision;
+  int tiles = 0, np = 0;
+  for (int i = 0; i < count; ++i) {
+    const tgn_gemm_desc& g = d[i];
+    TGN_REQUIRE(g.m >= 0 && g.n >= 0 && g.k >= 0 && g.split_k >= 1, "gemm_batch[%d]: bad sizes", i);
+    TGN_REQUIRE(g.mode >= 0 && g.mode <= 2, "gemm_batch[%d]: mode must be 0, 1 or 2", i);
+    TGN_REQUIRE(g.split_k == 1 || g.mode == 2, "gemm_batch[%d]: split_k > 1 needs mode 2 (atomic)", i);
+    if (g.m == 0 || g.n == 0) continue;
+    TGN_REQUIRE(g.a && g.b && g.c, "gemm_batch[%d]: NULL pointer", i);
+    TGN_REQUIRE(gemm_tma_ok(g.a, g.b, g.lda, g.ldb),
+                "gemm_batch[%d]: operands must be 16-byte aligned with lda, ldb multiples of 4", i);
+    GemmProb& P = prm.p[np];
+    P.c = g.c; P.bias = g.bias; P.m_dev = g.m_dev; P.k_dev = g.k_dev;
+    P.m = g.m; P.n = g.n; P.k = g.k; P.ldc = g.ldc;
+    P.a_mn = g.trans_a ? 1 : 0; P.b_mn = g.trans_b ? 1 : 0;
+    P.split_k = g.split_k; P.mode = g.mode;
+    P.tiles_m = ceil_div(g.m, GM); P.tiles_n = ceil_div(g.n, GN);
+    P.tile_begin = tiles;
+    tiles += P.tiles_m * P.tiles_n * g.split_k;
+    int rc;
+    // op(A)(m,k): !trans_a -> a[m*lda+k]; trans_a -> a[k*lda+m]
+    if (!g.trans_a) rc = make_map(&maps.a[np], g.a, g.m, g.k, g.lda, GK, GM, false);
+    else rc = make_map(&maps.a[np], g.a, g.k, g.m, g.lda, 32, GK, true);
+    if (rc != TGN_OK) return rc;
+    // op(B)(k,n): !trans_b -> b[n*ldb+k]; trans_b -> b[k*ldb+n]
+    if (!g.trans_b) rc = make_map(&maps.b[np], g.b, g.n, g.k, g.ldb, GK, GN, false);
+    else rc = make_map(&maps.b[np], g.b, g.k, g.n, g.ldb, 32, GK, true);
+    if (rc != TGN_OK) return rc;
+    ++np;
+  }
+  if (np == 0) return TGN_OK;
+  prm.nprob = np;
+  const size_t smem = (size_t)kGStages * kGStageBytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TGN_CUDA(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  tgemm_kernel<<<tiles, kGThreads, smem, (cudaStream_t)stream>>>(maps, prm);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+}  // extern "C"

@@ -26,12 +26,19 @@ for name, m, n, k, ta, tb, split in shapes:
     out = torch.zeros(m, n, device=dev)
     res = []
     for prec in (0, 1, 3):
+        run = lambda: ops.sgemm(A, B, m=m, n=n, k=k, lda=A.shape[1], ldb=B.shape[1], trans_a=ta, trans_b=tb,
+                                out=out, split_k=split, prec=prec)
         for _ in range(3):
-            ops.sgemm(A, B, m=m, n=n, k=k, lda=A.shape[1], ldb=B.shape[1], trans_a=ta, trans_b=tb, out=out, split_k=split, prec=prec)
+            run()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()          # graph replay: device time without the Python launch cost
+        with torch.cuda.graph(g):
+            for _ in range(20):
+                run()
+        g.replay(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(20):
-            ops.sgemm(A, B, m=m, n=n, k=k, lda=A.shape[1], ldb=B.shape[1], trans_a=ta, trans_b=tb, out=out, split_k=split, prec=prec)
+        g.replay()
         e1.record(); torch.cuda.synchronize()
         res.append(e0.elapsed_time(e1) / 20 * 1e3)
     fl = 2.0 * m * n * k

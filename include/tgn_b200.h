@@ -197,6 +197,15 @@ int32_t tgn_msg_build(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
                       void* lu_out /* [num] dtype of ev_t */, int32_t* sel_ev, float* sel_dt,
                       void* stream);
 
+/* tgn_msg_build with a caller-chosen row stride ldx >= message width (padding columns are
+ * zeroed; a stride that is a multiple of 4 makes x a TMA operand) and, when h_out is given,
+ * the gather h_out[s,:] = memory[n_id[s],:] (memory_module.py:172) in the same pass. */
+int32_t tgn_msg_build_ld(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                         const int32_t* num_dev, int32_t agg_mode, const float* memory,
+                         const int64_t* last_update, int32_t memory_dim, const float* time_w,
+                         const float* time_b, int32_t time_dim, float* x, int32_t ldx, float* h_out,
+                         void* lu_out, int32_t* sel_ev, float* sel_dt, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Dense fp32 building block: C[M,N] (=|+=) A[M,K] * B^T|B (+ bias).
  * a_rows (nullable) gathers rows of A:  A_m = A_base[a_rows[m], :].
@@ -339,6 +348,57 @@ int32_t tgn_attn_edge_attr(const void* last_update_local, int32_t lu_is_float,
                            const int32_t* num_edges_dev, int32_t raw_dim, int32_t time_dim,
                            const float* time_w, const float* time_b, float* edge_attr,
                            float* rel_t, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Pieces of the captured training step that run between the GEMMs.
+ * ------------------------------------------------------------------------- */
+/* oa = assoc[a], ob = assoc[b], oc = assoc[c] in one launch (neighbor_loader.py:48,
+ * epoch_utils.py:99,262) */
+int32_t tgn_relabel3(const int64_t* a, int32_t na, const int32_t* na_dev, int64_t* oa,
+                     const int64_t* b, int32_t nb, const int32_t* nb_dev, int64_t* ob,
+                     const int64_t* c, int32_t nc, const int32_t* nc_dev, int64_t* oc,
+                     const int64_t* assoc, void* stream);
+/* edge_attr[e, 0:ld] = [cos(w*rel_t+b) (time_dim), msg (raw_dim), 0...] with
+ * rel_t = last_update[nbr[e]] - t_edge[msg_rows[e]] (emb_module.py:26-28), int64 times;
+ * sin_out [E,time_dim] (nullable) keeps sin(w*rel_t+b) for tgn_time_bwd_sin. */
+int32_t tgn_edge_attr_ld(const int64_t* last_update_local, const int64_t* nbr_local,
+                         const int64_t* t_edge, const float* msg, const int64_t* msg_rows,
+                         int32_t num_edges, const int32_t* num_edges_dev, int32_t raw_dim,
+                         int32_t time_dim, const float* time_w, const float* time_b, int32_t ld,
+                         float* edge_attr, float* sin_out, float* rel_t, void* stream);
+/* TimeEncoder gradient from stored sines: d_w[c] += sum_i grad[i,c] * -sin[i,c] * t[i],
+ * d_b[c] += sum_i grad[i,c] * -sin[i,c]; rows with row_mask[i] < 0 are skipped. */
+int32_t tgn_time_bwd_sin(const float* t, const int32_t* row_mask, int32_t num, const int32_t* num_dev,
+                         const float* sin_vals, int32_t dim, const float* grad, int32_t ld_grad,
+                         float* d_w, float* d_b, void* stream);
+/* TransformerConv core with the edge projection ee = W_edge*edge_attr [E,H*C] precomputed
+ * (by tgn_gemm_batch): scores, softmax over each centre's edges [row_ptr[c], row_ptr[c+1]),
+ * dropout, aggregation, + skip.  Writes out[centre_ids[c], :] and alpha [E,H]. */
+int32_t tgn_attn_core_fwd(const float* proj, const int64_t* nbr_local, const int32_t* row_ptr,
+                          const int64_t* centre_ids, int32_t num_centres,
+                          const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
+                          const float* ee, float dropout_p, uint64_t seed, const int64_t* seed_dev,
+                          float* out, float* alpha, void* stream);
+/* Backward: zero-fills d_proj [num_rows, 4*H*C], then writes the q and skip blocks of the
+ * centre rows, atomically adds the k / v blocks of the neighbour rows and writes d_ee [E,H*C].
+ * d_out is read at the centre rows only. */
+int32_t tgn_attn_core_bwd(const float* proj, const int64_t* nbr_local, const int32_t* row_ptr,
+                          const int64_t* centre_ids, int32_t num_centres,
+                          const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
+                          const float* ee, const float* alpha, const float* d_out, float dropout_p,
+                          uint64_t seed, const int64_t* seed_dev, int32_t num_rows, float* d_proj,
+                          float* d_ee, void* stream);
+/* LinkPredictor tail + BCE-with-logits loss and gradient (decoder.py:24-27, pyg-mem-tgn.py:51).
+ * hs [B,D] = lin_src(z_src), hd [2B,D] = lin_dst([z_dst; z_neg]).  Accumulates (+=) loss
+ * (mean over positives + mean over negatives), d_w_final, d_b_final, d_b_src, d_b_dst;
+ * writes logits [2B] (nullable), dh [2B,D] (gradient of hd) and dhs [B,D] (gradient of hs). */
+int32_t tgn_dec_loss(const float* hs, const float* hd, const float* w_final, const float* b_final,
+                     int32_t batch, int32_t dim, float* loss, float* logits, float* dh, float* dhs,
+                     float* d_w_final, float* d_b_final, float* d_b_src, float* d_b_dst,
+                     void* stream);
+/* dst[rows[i], :] += src[i, :] (atomic) */
+int32_t tgn_scatter_add_rows(const float* src, const int64_t* rows, int32_t num,
+                             const int32_t* num_dev, int32_t dim, float* dst, void* stream);
 
 /* Batch staging (replaces the host DataLoader walk, temporal_dataset.py:34-57 +
  * epoch_utils.py:186-215): slices events [*pos_dev, *pos_dev + batch) of the

@@ -203,8 +203,8 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
                                  const int64_t* __restrict__ last_update, int Dm,
                                  const float* __restrict__ time_w,
                                  const float* __restrict__ time_b, int Dt, float* __restrict__ x,
-                                 T* __restrict__ lu_out, int32_t* __restrict__ sel_ev,
-                                 float* __restrict__ sel_dt) {
+                                 int ldx, float* __restrict__ h_out, T* __restrict__ lu_out,
+                                 int32_t* __restrict__ sel_ev, float* __restrict__ sel_dt) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int S = num.get();
@@ -214,9 +214,12 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
   for (int s = blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < S;
        s += gridDim.x * warps_per_block) {
     const int64_t n = n_id[s];
-    float* xr = x + (long long)s * W;
+    float* xr = x + (long long)s * ldx;
     const bool ok = n >= 0 && n < st.num_nodes;
     const int sc = ok ? st.s_cnt[n] : 0, dc = ok ? st.d_cnt[n] : 0;
+    for (int c = W + lane; c < ldx; c += 32) xr[c] = 0.f;  // row padding (TMA-aligned stride)
+    if (h_out)
+      for (int c = lane; c < Dm; c += 32) h_out[(long long)s * Dm + c] = ok ? memory[n * Dm + c] : 0.f;
     if (sc + dc == 0) {
       for (int c = lane; c < W; c += 32) xr[c] = 0.f;
       if (lane == 0) {
@@ -403,15 +406,16 @@ int32_t tgn_msgstore_gather(const tgn_msgstore* st, const int64_t* n_id, int32_t
   return TGN_OK;
 }
 
-int32_t tgn_msg_build(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
-                      const int32_t* num_dev, int32_t agg_mode, const float* memory,
-                      const int64_t* last_update, int32_t memory_dim, const float* time_w,
-                      const float* time_b, int32_t time_dim, float* x, void* lu_out,
-                      int32_t* sel_ev, float* sel_dt, void* stream) {
+int32_t tgn_msg_build_ld(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                         const int32_t* num_dev, int32_t agg_mode, const float* memory,
+                         const int64_t* last_update, int32_t memory_dim, const float* time_w,
+                         const float* time_b, int32_t time_dim, float* x, int32_t ldx, float* h_out,
+                         void* lu_out, int32_t* sel_ev, float* sel_dt, void* stream) {
   int32_t rc = check_store(st, "msg_build");
   if (rc) return rc;
   TGN_REQUIRE(num >= 0 && memory_dim >= 1 && time_dim >= 0, "msg_build: bad sizes");
   TGN_REQUIRE(agg_mode == TGN_AGG_LAST || agg_mode == TGN_AGG_MEAN, "msg_build: bad agg_mode");
+  TGN_REQUIRE(ldx >= 2 * memory_dim + st->raw_dim + time_dim, "msg_build: ldx smaller than the message width");
   if (num == 0) return TGN_OK;
   TGN_REQUIRE(n_id && memory && last_update && x && lu_out && (time_dim == 0 || (time_w && time_b)),
               "msg_build: NULL pointer");
@@ -420,14 +424,25 @@ int32_t tgn_msg_build(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
   const int grid = stride_grid((long long)num * 32, 256);
   if (st->t_is_float)
     msg_build_kernel<float><<<grid, 256, 0, s>>>(*st, n_id, c, agg_mode, memory, last_update,
-                                                 memory_dim, time_w, time_b, time_dim, x,
+                                                 memory_dim, time_w, time_b, time_dim, x, ldx, h_out,
                                                  (float*)lu_out, sel_ev, sel_dt);
   else
     msg_build_kernel<int64_t><<<grid, 256, 0, s>>>(*st, n_id, c, agg_mode, memory, last_update,
-                                                   memory_dim, time_w, time_b, time_dim, x,
-                                                   (int64_t*)lu_out, sel_ev, sel_dt);
+                                                   memory_dim, time_w, time_b, time_dim, x, ldx,
+                                                   h_out, (int64_t*)lu_out, sel_ev, sel_dt);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
+}
+
+int32_t tgn_msg_build(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                      const int32_t* num_dev, int32_t agg_mode, const float* memory,
+                      const int64_t* last_update, int32_t memory_dim, const float* time_w,
+                      const float* time_b, int32_t time_dim, float* x, void* lu_out,
+                      int32_t* sel_ev, float* sel_dt, void* stream) {
+  TGN_REQUIRE(st, "msg_build: store is NULL");
+  return tgn_msg_build_ld(st, n_id, num, num_dev, agg_mode, memory, last_update, memory_dim, time_w,
+                          time_b, time_dim, x, 2 * memory_dim + st->raw_dim + time_dim, nullptr,
+                          lu_out, sel_ev, sel_dt, stream);
 }
 
 }  // extern "C"

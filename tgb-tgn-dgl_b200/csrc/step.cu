@@ -1,0 +1,550 @@
+// Kernels of the captured training step that sit between the tensor-core GEMMs
+// (engine.py drives them; every size that depends on the batch is read from device memory):
+//
+//   tgn_relabel3          the three `_assoc[...]` gathers of one step in one launch
+//                         (neighbor_loader.py:48, epoch_utils.py:99,262)
+//   tgn_edge_attr_ld      edge_attr = [cos(w*rel_t+b), msg] with a TMA-aligned row stride
+//                         (modules/emb_module.py:26-28), plus sin(w*rel_t+b) for the backward
+//   tgn_attn_core_fwd/bwd TransformerConv softmax / aggregation over each centre's edges with the
+//                         edge projection ee = W_edge * edge_attr taken from the GEMM
+//                         (modules/emb_module.py:29)
+//   tgn_dec_loss          LinkPredictor tail + BCE-with-logits loss and its gradient
+//                         (modules/decoder.py:24-27, pyg-mem-tgn.py:51, epoch_utils.py:305-310)
+//   tgn_scatter_add_rows  dst[rows[i],:] += src[i,:]
+//   tgn_time_bwd_sin      TimeEncoder gradient from stored sines
+#include "../../include/tgn_b200.h"
+#include "common.cuh"
+
+namespace tgn {
+
+__global__ void relabel3_kernel(const int64_t* __restrict__ a, DevCount na, int64_t* __restrict__ oa,
+                                const int64_t* __restrict__ b, DevCount nb, int64_t* __restrict__ ob,
+                                const int64_t* __restrict__ c, DevCount nc, int64_t* __restrict__ oc,
+                                const int64_t* __restrict__ assoc) {
+  const int ca = na.get(), cb = nb.get(), cc = nc.get();
+  const int total = ca + cb + cc;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < ca) oa[i] = assoc[a[i]];
+    else if (i < ca + cb) ob[i - ca] = assoc[b[i - ca]];
+    else oc[i - ca - cb] = assoc[c[i - ca - cb]];
+  }
+}
+
+struct EdgeAttr2Args {
+  const int64_t* lu;      // last_update of the local rows (int64)
+  const int64_t* nbr;     // local row of each edge's neighbour
+  const int64_t* t_edge;  // event timestamps (int64), indexed by msg_rows[e]
+  const float* msg;       // event messages [*, De], indexed by msg_rows[e]
+  const int64_t* msg_rows;
+  DevCount edges;
+  int De, Dt, ld;
+  const float* time_w;
+  const float* time_b;
+  float* ea;     // [E, ld]
+  float* sn;     // [E, Dt] sin(w*rel+b) (nullable)
+  float* rel;    // [E]
+};
+
+__global__ void edge_attr_ld_kernel(EdgeAttr2Args a) {
+  const int E = a.edges.get();
+  const long long total = (long long)E * a.ld;
+  for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total;
+       x += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(x / a.ld), d = (int)(x - (long long)e * a.ld);
+    const long long mr = a.msg_rows ? a.msg_rows[e] : e;
+    if (d < a.Dt) {
+      const float rt = (float)(a.lu[a.nbr[e]] - a.t_edge[mr]);
+      float sv, cv;
+      sincosf(__fmaf_rn(rt, a.time_w[d], a.time_b[d]), &sv, &cv);
+      a.ea[x] = cv;
+      if (a.sn) a.sn[(long long)e * a.Dt + d] = sv;
+      if (d == 0 && a.rel) a.rel[e] = rt;
+    } else if (d < a.Dt + a.De) {
+      a.ea[x] = a.msg[mr * a.De + (d - a.Dt)];
+    } else {
+      a.ea[x] = 0.f;
+    }
+  }
+}
+
+// d_w[c] += sum_i g[i,c] * (-sin_i,c) * t[i];  d_b[c] += sum_i g[i,c] * (-sin_i,c)
+// rows with mask[i] < 0 are skipped (zero-message rows carry no time encoding).
+__global__ void time_bwd_sin_kernel(const float* __restrict__ t, const int32_t* __restrict__ mask,
+                                    DevCount num, const float* __restrict__ sn, int D,
+                                    const float* __restrict__ g, int ldg, float* __restrict__ d_w,
+                                    float* __restrict__ d_b) {
+  __shared__ float s_w[8][33], s_b[8][33];
+  const int R = num.get();
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  const int rows_per_cta = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
+  float aw = 0.f, ab = 0.f;
+  if (c < D) {
+    for (int r = r0 + ry; r < r1; r += 8) {
+      if (mask && mask[r] < 0) continue;
+      const float ds = -sn[(long long)r * D + c] * g[(long long)r * ldg + c];
+      aw = fmaf(ds, t[r], aw);
+      ab += ds;
+    }
+  }
+  s_w[ry][threadIdx.x & 31] = aw;
+  s_b[ry][threadIdx.x & 31] = ab;
+  __syncthreads();
+  if (ry == 0 && c < D) {
+    float vw = 0.f, vb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      vw += s_w[i][threadIdx.x & 31];
+      vb += s_b[i][threadIdx.x & 31];
+    }
+    atomicAdd(&d_w[c], vw);
+    atomicAdd(&d_b[c], vb);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// attention core: one warp per centre, lanes own channels (lane, lane+32, ...)
+// ------------------------------------------------------------------------------------------
+constexpr int kCoreWarps = 4;
+constexpr int kCMaxCH = 8;     // H*C <= 256
+constexpr int kCMaxHeads = 8;
+
+struct AttnCoreArgs {
+  const float* proj;  // [Nb, 4HC] = q | k | v | skip
+  const int64_t* nbr;
+  const int32_t* row_ptr;
+  const int64_t* centre_ids;
+  DevCount centres;
+  int H, C;
+  const float* ee;  // [E, HC]
+  float dropout_p;
+  uint64_t seed;
+  const int64_t* seed_dev;
+  float* out;       // fwd: [Nb, HC] rows of centres written
+  float* alpha;     // [E, H]
+  const float* d_out;
+  float* d_proj;    // bwd: [Nb, 4HC], zero on entry
+  float* d_ee;      // bwd: [E, HC]
+};
+
+__global__ void __launch_bounds__(kCoreWarps * 32) attn_core_fwd_kernel(AttnCoreArgs a) {
+  const int HC = a.H * a.C;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nC = a.centres.get();
+  const float inv_sqrt_c = rsqrtf((float)a.C);
+  const int CH = (HC + 31) >> 5;
+  const float keep = 1.f - a.dropout_p;
+  Philox rng(a.seed + (a.seed_dev ? (uint64_t)*a.seed_dev : 0ull));
+  for (int ci = blockIdx.x * kCoreWarps + wid; ci < nC; ci += gridDim.x * kCoreWarps) {
+    const int64_t row = a.centre_ids ? a.centre_ids[ci] : ci;
+    const float* pr = a.proj + row * 4 * HC;
+    float q[kCMaxCH], acc[kCMaxCH];
+    int head[kCMaxCH];
+#pragma unroll
+    for (int i = 0; i < kCMaxCH; ++i) {
+      const int c = lane + 32 * i;
+      const bool ok = i < CH && c < HC;
+      q[i] = ok ? pr[c] : 0.f;
+      acc[i] = 0.f;
+      head[i] = ok ? c / a.C : -1;
+    }
+    float mrun[kCMaxHeads], lrun[kCMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kCMaxHeads; ++h) {
+      mrun[h] = -INFINITY;
+      lrun[h] = 0.f;
+    }
+    const int e0 = a.row_ptr[ci], e1 = a.row_ptr[ci + 1];
+    for (int e = e0; e < e1; ++e) {
+      const int64_t j = a.nbr[e];
+      const float* pj = a.proj + j * 4 * HC;
+      const float* pe = a.ee + (long long)e * HC;
+      float vv[kCMaxCH], part[kCMaxHeads];
+#pragma unroll
+      for (int h = 0; h < kCMaxHeads; ++h) part[h] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kCMaxCH; ++i) {
+        const int c = lane + 32 * i;
+        const bool ok = i < CH && c < HC;
+        const float eev = ok ? pe[c] : 0.f;
+        const float kv = ok ? pj[HC + c] + eev : 0.f;
+        vv[i] = ok ? pj[2 * HC + c] + eev : 0.f;
+#pragma unroll
+        for (int h = 0; h < kCMaxHeads; ++h)
+          if (head[i] == h) part[h] = fmaf(q[i], kv, part[h]);
+      }
+      float pw[kCMaxHeads], sc[kCMaxHeads];
+#pragma unroll
+      for (int h = 0; h < kCMaxHeads; ++h) {
+        pw[h] = 0.f;
+        sc[h] = 1.f;
+        if (h < a.H) {
+          const float s = warp_sum(part[h]) * inv_sqrt_c;
+          const float mnew = fmaxf(mrun[h], s);
+          sc[h] = expf(mrun[h] - mnew);  // 0 on the first edge
+          float p = expf(s - mnew);
+          lrun[h] = lrun[h] * sc[h] + p;
+          mrun[h] = mnew;
+          if (lane == 0) a.alpha[(long long)e * a.H + h] = s;
+          if (a.dropout_p > 0.f) {
+            const uint4 r = rng((uint64_t)e, (uint64_t)h);
+            const float uni = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+            p = uni < keep ? p / keep : 0.f;
+          }
+          pw[h] = p;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kCMaxCH; ++i)
+#pragma unroll
+        for (int h = 0; h < kCMaxHeads; ++h)
+          if (head[i] == h) acc[i] = acc[i] * sc[h] + pw[h] * vv[i];
+    }
+    float* po = a.out + row * HC;
+#pragma unroll
+    for (int i = 0; i < kCMaxCH; ++i) {
+      const int c = lane + 32 * i;
+      if (i < CH && c < HC) {
+        float l = 1.f;
+#pragma unroll
+        for (int h = 0; h < kCMaxHeads; ++h)
+          if (head[i] == h) l = lrun[h];
+        po[c] = ((e1 > e0) ? acc[i] / l : 0.f) + pr[3 * HC + c];
+      }
+    }
+    __syncwarp();
+    for (int idx = lane; idx < (e1 - e0) * a.H; idx += 32) {  // raw scores -> softmax weights
+      const int h = idx % a.H;
+      float m = 0.f, l = 1.f;
+#pragma unroll
+      for (int hh = 0; hh < kCMaxHeads; ++hh)
+        if (hh == h) {
+          m = mrun[hh];
+          l = lrun[hh];
+        }
+      float* pa = a.alpha + (long long)e0 * a.H + idx;
+      *pa = expf(*pa - m) / l;
+    }
+  }
+}
+
+// out_i = sum_e a~_e (v_j + ee_e) + skip_i,  a~ = dropout(alpha), alpha = softmax_e(s_e),
+// s_e = <q_i, k_j + ee_e>/sqrt(C).  Two passes over the centre's edges (the second one
+// recomputes the dot products); neighbour rows of d_proj receive atomic adds.
+__global__ void __launch_bounds__(kCoreWarps * 32) attn_core_bwd_kernel(AttnCoreArgs a) {
+  const int HC = a.H * a.C;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nC = a.centres.get();
+  const float inv_sqrt_c = rsqrtf((float)a.C);
+  const int CH = (HC + 31) >> 5;
+  const float keep = 1.f - a.dropout_p;
+  Philox rng(a.seed + (a.seed_dev ? (uint64_t)*a.seed_dev : 0ull));
+  for (int ci = blockIdx.x * kCoreWarps + wid; ci < nC; ci += gridDim.x * kCoreWarps) {
+    const int64_t row = a.centre_ids ? a.centre_ids[ci] : ci;
+    const float* pr = a.proj + row * 4 * HC;
+    const float* go = a.d_out + row * HC;
+    float q[kCMaxCH], g[kCMaxCH], dq[kCMaxCH];
+    int head[kCMaxCH];
+#pragma unroll
+    for (int i = 0; i < kCMaxCH; ++i) {
+      const int c = lane + 32 * i;
+      const bool ok = i < CH && c < HC;
+      q[i] = ok ? pr[c] : 0.f;
+      g[i] = ok ? go[c] : 0.f;
+      dq[i] = 0.f;
+      head[i] = ok ? c / a.C : -1;
+    }
+    const int e0 = a.row_ptr[ci], e1 = a.row_ptr[ci + 1];
+    float dot[kCMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kCMaxHeads; ++h) dot[h] = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int e = e0; e < e1; ++e) {
+        const int64_t j = a.nbr[e];
+        const float* pj = a.proj + j * 4 * HC;
+        const float* pe = a.ee + (long long)e * HC;
+        float kk[kCMaxCH], part[kCMaxHeads];
+#pragma unroll
+        for (int h = 0; h < kCMaxHeads; ++h) part[h] = 0.f;
+#pragma unroll
+        for (int i = 0; i < kCMaxCH; ++i) {
+          const int c = lane + 32 * i;
+          const bool ok = i < CH && c < HC;
+          const float eev = ok ? pe[c] : 0.f;
+          kk[i] = ok ? pj[HC + c] + eev : 0.f;
+          const float vv = ok ? pj[2 * HC + c] + eev : 0.f;
+#pragma unroll
+          for (int h = 0; h < kCMaxHeads; ++h)
+            if (head[i] == h) part[h] = fmaf(g[i], vv, part[h]);
+        }
+        float al[kCMaxHeads], dal[kCMaxHeads], mk[kCMaxHeads];
+#pragma unroll
+        for (int h = 0; h < kCMaxHeads; ++h) {
+          al[h] = 0.f;
+          dal[h] = 0.f;
+          mk[h] = 1.f;
+          if (h < a.H) {
+            al[h] = a.alpha[(long long)e * a.H + h];
+            if (a.dropout_p > 0.f) {
+              const uint4 r = rng((uint64_t)e, (uint64_t)h);
+              const float uni = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+              mk[h] = uni < keep ? 1.f / keep : 0.f;
+            }
+            dal[h] = warp_sum(part[h]) * mk[h];
+          }
+        }
+        if (pass == 0) {
+#pragma unroll
+          for (int h = 0; h < kCMaxHeads; ++h) dot[h] = fmaf(al[h], dal[h], dot[h]);
+          continue;
+        }
+        float* dpj = a.d_proj + j * 4 * HC;
+        float* dpe = a.d_ee + (long long)e * HC;
+#pragma unroll
+        for (int i = 0; i < kCMaxCH; ++i) {
+          const int c = lane + 32 * i;
+          if (!(i < CH && c < HC)) continue;
+          float dsh = 0.f, at = 0.f;
+#pragma unroll
+          for (int h = 0; h < kCMaxHeads; ++h)
+            if (head[i] == h) {
+              dsh = al[h] * (dal[h] - dot[h]) * inv_sqrt_c;
+              at = al[h] * mk[h];
+            }
+          dq[i] = fmaf(dsh, kk[i], dq[i]);
+          const float dk = dsh * q[i];
+          const float dv = at * g[i];
+          atomicAdd(dpj + HC + c, dk);
+          atomicAdd(dpj + 2 * HC + c, dv);
+          dpe[c] = dk + dv;
+        }
+      }
+    }
+    float* dpr = a.d_proj + row * 4 * HC;
+#pragma unroll
+    for (int i = 0; i < kCMaxCH; ++i) {
+      const int c = lane + 32 * i;
+      if (i < CH && c < HC) {
+        dpr[c] = dq[i];          // centres are unique: plain stores for the q and skip blocks
+        dpr[3 * HC + c] = g[i];  // (a centre that is also a neighbour only gets k/v atomics)
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// decoder tail + loss.  Event i (< B) owns the positive pair (src_i, dst_i) = row i of hd and
+// the negative pair (src_i, neg_i) = row B+i of hd; both share hs row i.
+//   h = relu(hs + hd), logit = wf.h + bf, loss = mean softplus(-pos) + mean softplus(neg)
+// One warp per event; CTA-level reduction of the parameter gradients, then atomics.
+// ------------------------------------------------------------------------------------------
+constexpr int kDecWarps = 8;
+
+__global__ void __launch_bounds__(kDecWarps * 32)
+    dec_loss_kernel(const float* __restrict__ hs, const float* __restrict__ hd,
+                    const float* __restrict__ wf, const float* __restrict__ bf, int B, int D,
+                    float* __restrict__ loss, float* __restrict__ logits, float* __restrict__ dh,
+                    float* __restrict__ dhs, float* __restrict__ d_wf, float* __restrict__ d_bf,
+                    float* __restrict__ d_bs, float* __restrict__ d_bd) {
+  extern __shared__ float s_red[];  // [3][D] : d_wf, d_bs, d_bd partials
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  const float invB = 1.f / (float)B;
+  float loss_acc = 0.f, dbf_acc = 0.f;
+  for (int i = blockIdx.x * kDecWarps + wid; i < B; i += gridDim.x * kDecWarps) {
+    float dl[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const float* ph = hd + (long long)(s * B + i) * D;
+      float acc = 0.f;
+      for (int c = lane; c < D; c += 32)
+        acc = fmaf(fmaxf(hs[(long long)i * D + c] + ph[c], 0.f), wf[c], acc);
+      const float logit = warp_sum(acc) + bf[0];
+      // softplus(x) = max(x,0) + log1p(exp(-|x|)), x = -logit for positives
+      const float x = s == 0 ? -logit : logit;
+      loss_acc += (fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)))) * invB;
+      const float sg = 1.f / (1.f + expf(-logit));
+      dl[s] = (sg - (s == 0 ? 1.f : 0.f)) * invB;
+      dbf_acc += dl[s];
+      if (logits && lane == 0) logits[s * B + i] = logit;
+    }
+    for (int c = lane; c < D; c += 32) {
+      const float a = hs[(long long)i * D + c];
+      const float h0 = fmaxf(a + hd[(long long)i * D + c], 0.f);
+      const float h1 = fmaxf(a + hd[(long long)(B + i) * D + c], 0.f);
+      const float w = wf[c];
+      const float g0 = h0 > 0.f ? dl[0] * w : 0.f;
+      const float g1 = h1 > 0.f ? dl[1] * w : 0.f;
+      dh[(long long)i * D + c] = g0;
+      dh[(long long)(B + i) * D + c] = g1;
+      dhs[(long long)i * D + c] = g0 + g1;
+      atomicAdd(&s_red[c], dl[0] * h0 + dl[1] * h1);
+      atomicAdd(&s_red[D + c], g0 + g1);
+      atomicAdd(&s_red[2 * D + c], g0 + g1);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    if (s_red[c] != 0.f) atomicAdd(&d_wf[c], s_red[c]);
+    if (s_red[D + c] != 0.f) atomicAdd(&d_bs[c], s_red[D + c]);
+    if (s_red[2 * D + c] != 0.f) atomicAdd(&d_bd[c], s_red[2 * D + c]);
+  }
+  if (lane == 0) {  // every lane of a warp holds the same loss_acc / dbf_acc
+    if (loss_acc != 0.f) atomicAdd(loss, loss_acc);
+    if (dbf_acc != 0.f) atomicAdd(d_bf, dbf_acc);
+  }
+}
+
+__global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ rows,
+                                        DevCount num, int D, float* __restrict__ dst) {
+  const int n = num.get();
+  const long long total = (long long)n * D;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / D), c = (int)(e - (long long)i * D);
+    atomicAdd(&dst[rows[i] * D + c], src[e]);
+  }
+}
+
+}  // namespace tgn
+
+using namespace tgn;
+
+extern "C" {
+
+int32_t tgn_relabel3(const int64_t* a, int32_t na, const int32_t* na_dev, int64_t* oa,
+                     const int64_t* b, int32_t nb, const int32_t* nb_dev, int64_t* ob,
+                     const int64_t* c, int32_t nc, const int32_t* nc_dev, int64_t* oc,
+                     const int64_t* assoc, void* stream) {
+  TGN_REQUIRE(na >= 0 && nb >= 0 && nc >= 0, "relabel3: negative count");
+  if (na + nb + nc == 0) return TGN_OK;
+  TGN_REQUIRE(assoc && (na == 0 || (a && oa)) && (nb == 0 || (b && ob)) && (nc == 0 || (c && oc)),
+              "relabel3: NULL pointer");
+  relabel3_kernel<<<stride_grid((long long)na + nb + nc, 256), 256, 0, (cudaStream_t)stream>>>(
+      a, DevCount{na_dev, na}, oa, b, DevCount{nb_dev, nb}, ob, c, DevCount{nc_dev, nc}, oc, assoc);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_edge_attr_ld(const int64_t* last_update_local, const int64_t* nbr_local,
+                         const int64_t* t_edge, const float* msg, const int64_t* msg_rows,
+                         int32_t num_edges, const int32_t* num_edges_dev, int32_t raw_dim,
+                         int32_t time_dim, const float* time_w, const float* time_b, int32_t ld,
+                         float* edge_attr, float* sin_out, float* rel_t, void* stream) {
+  TGN_REQUIRE(num_edges >= 0 && raw_dim >= 0 && time_dim >= 0 && ld >= raw_dim + time_dim && ld >= 1,
+              "edge_attr_ld: bad sizes");
+  if (num_edges == 0) return TGN_OK;
+  TGN_REQUIRE(last_update_local && nbr_local && t_edge && (msg || raw_dim == 0) && edge_attr &&
+                  (time_dim == 0 || (time_w && time_b)),
+              "edge_attr_ld: NULL pointer");
+  EdgeAttr2Args a;
+  a.lu = last_update_local; a.nbr = nbr_local; a.t_edge = t_edge; a.msg = msg; a.msg_rows = msg_rows;
+  a.edges = DevCount{num_edges_dev, num_edges}; a.De = raw_dim; a.Dt = time_dim; a.ld = ld;
+  a.time_w = time_w; a.time_b = time_b; a.ea = edge_attr; a.sn = sin_out; a.rel = rel_t;
+  edge_attr_ld_kernel<<<stride_grid((long long)num_edges * ld, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_time_bwd_sin(const float* t, const int32_t* row_mask, int32_t num, const int32_t* num_dev,
+                         const float* sin_vals, int32_t dim, const float* grad, int32_t ld_grad,
+                         float* d_w, float* d_b, void* stream) {
+  TGN_REQUIRE(num >= 0 && dim >= 1 && ld_grad >= dim, "time_bwd_sin: bad sizes");
+  if (num == 0) return TGN_OK;
+  TGN_REQUIRE(t && sin_vals && grad && d_w && d_b, "time_bwd_sin: NULL pointer");
+  int gy = ceil_div(num, 128);
+  if (gy > 64) gy = 64;
+  time_bwd_sin_kernel<<<dim3(ceil_div(dim, 32), gy), 256, 0, (cudaStream_t)stream>>>(
+      t, row_mask, DevCount{num_dev, num}, sin_vals, dim, grad, ld_grad, d_w, d_b);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+static int32_t core_args(AttnCoreArgs& a, const float* proj, const int64_t* nbr_local,
+                         const int32_t* row_ptr, const int64_t* centre_ids, int32_t num_centres,
+                         const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
+                         const float* ee, float dropout_p, uint64_t seed, const int64_t* seed_dev) {
+  TGN_REQUIRE(num_centres >= 0 && heads >= 1 && heads <= kCMaxHeads && head_dim >= 1 &&
+                  heads * head_dim <= 32 * kCMaxCH,
+              "attn_core: bad sizes (heads <= %d, heads*head_dim <= %d)", kCMaxHeads, 32 * kCMaxCH);
+  TGN_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attn_core: dropout_p must be in [0,1)");
+  TGN_REQUIRE(proj && nbr_local && row_ptr && ee, "attn_core: NULL pointer");
+  a.proj = proj; a.nbr = nbr_local; a.row_ptr = row_ptr; a.centre_ids = centre_ids;
+  a.centres = DevCount{num_centres_dev, num_centres}; a.H = heads; a.C = head_dim; a.ee = ee;
+  a.dropout_p = dropout_p; a.seed = seed; a.seed_dev = seed_dev;
+  a.out = nullptr; a.alpha = nullptr; a.d_out = nullptr; a.d_proj = nullptr; a.d_ee = nullptr;
+  return TGN_OK;
+}
+
+int32_t tgn_attn_core_fwd(const float* proj, const int64_t* nbr_local, const int32_t* row_ptr,
+                          const int64_t* centre_ids, int32_t num_centres,
+                          const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
+                          const float* ee, float dropout_p, uint64_t seed, const int64_t* seed_dev,
+                          float* out, float* alpha, void* stream) {
+  if (num_centres == 0) return TGN_OK;
+  AttnCoreArgs a;
+  int32_t rc = core_args(a, proj, nbr_local, row_ptr, centre_ids, num_centres, num_centres_dev, heads,
+                         head_dim, ee, dropout_p, seed, seed_dev);
+  if (rc) return rc;
+  TGN_REQUIRE(out && alpha, "attn_core_fwd: NULL output");
+  a.out = out; a.alpha = alpha;
+  attn_core_fwd_kernel<<<ceil_div(num_centres, kCoreWarps), kCoreWarps * 32, 0, (cudaStream_t)stream>>>(a);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_attn_core_bwd(const float* proj, const int64_t* nbr_local, const int32_t* row_ptr,
+                          const int64_t* centre_ids, int32_t num_centres,
+                          const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
+                          const float* ee, const float* alpha, const float* d_out, float dropout_p,
+                          uint64_t seed, const int64_t* seed_dev, int32_t num_rows, float* d_proj,
+                          float* d_ee, void* stream) {
+  TGN_REQUIRE(num_rows >= 0, "attn_core_bwd: bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (num_rows > 0) {
+    TGN_REQUIRE(d_proj, "attn_core_bwd: d_proj is NULL");
+    TGN_CUDA(cudaMemsetAsync(d_proj, 0, (size_t)num_rows * 4 * heads * head_dim * sizeof(float), s));
+  }
+  if (num_centres == 0) return TGN_OK;
+  AttnCoreArgs a;
+  int32_t rc = core_args(a, proj, nbr_local, row_ptr, centre_ids, num_centres, num_centres_dev, heads,
+                         head_dim, ee, dropout_p, seed, seed_dev);
+  if (rc) return rc;
+  TGN_REQUIRE(alpha && d_out && d_proj && d_ee, "attn_core_bwd: NULL pointer");
+  a.alpha = const_cast<float*>(alpha); a.d_out = d_out; a.d_proj = d_proj; a.d_ee = d_ee;
+  attn_core_bwd_kernel<<<ceil_div(num_centres, kCoreWarps), kCoreWarps * 32, 0, s>>>(a);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_dec_loss(const float* hs, const float* hd, const float* w_final, const float* b_final,
+                     int32_t batch, int32_t dim, float* loss, float* logits, float* dh, float* dhs,
+                     float* d_w_final, float* d_b_final, float* d_b_src, float* d_b_dst,
+                     void* stream) {
+  TGN_REQUIRE(batch >= 1 && dim >= 1, "dec_loss: bad sizes");
+  TGN_REQUIRE(hs && hd && w_final && b_final && loss && dh && dhs && d_w_final && d_b_final &&
+                  d_b_src && d_b_dst,
+              "dec_loss: NULL pointer");
+  int grid = ceil_div(batch, kDecWarps);
+  if (grid > kNumSMs) grid = kNumSMs;
+  dec_loss_kernel<<<grid, kDecWarps * 32, (size_t)3 * dim * sizeof(float), (cudaStream_t)stream>>>(
+      hs, hd, w_final, b_final, batch, dim, loss, logits, dh, dhs, d_w_final, d_b_final, d_b_src,
+      d_b_dst);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_scatter_add_rows(const float* src, const int64_t* rows, int32_t num,
+                             const int32_t* num_dev, int32_t dim, float* dst, void* stream) {
+  TGN_REQUIRE(num >= 0 && dim >= 1, "scatter_add_rows: bad sizes");
+  if (num == 0) return TGN_OK;
+  TGN_REQUIRE(src && rows && dst, "scatter_add_rows: NULL pointer");
+  scatter_add_rows_kernel<<<stride_grid((long long)num * dim, 256), 256, 0, (cudaStream_t)stream>>>(
+      src, rows, DevCount{num_dev, num}, dim, dst);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+}  // extern "C"

@@ -49,6 +49,19 @@ class MsgStoreStruct(ctypes.Structure):
     ]
 
 
+class GemmDesc(ctypes.Structure):
+    """Mirror of `struct tgn_gemm_desc` (field order must match the header)."""
+
+    _fields_ = [
+        ("a", ctypes.c_void_p), ("b", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("c", ctypes.c_void_p),
+        ("m_dev", ctypes.c_void_p), ("k_dev", ctypes.c_void_p),
+        ("m", ctypes.c_int32), ("n", ctypes.c_int32), ("k", ctypes.c_int32),
+        ("lda", ctypes.c_int32), ("ldb", ctypes.c_int32), ("ldc", ctypes.c_int32),
+        ("trans_a", ctypes.c_int32), ("trans_b", ctypes.c_int32),
+        ("mode", ctypes.c_int32), ("split_k", ctypes.c_int32),
+    ]
+
+
 _SCALARS = {
     "int32_t": ctypes.c_int32,
     "int64_t": ctypes.c_int64,

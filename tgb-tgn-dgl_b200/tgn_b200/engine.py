@@ -3,25 +3,30 @@
 One step = the per-batch flow the reference's four hot-path pieces serve
 (pyg_epoch_utils.py:106-137 commented flow == PyG/TGB tgn.py):
 
-    roots = unique(src, dst, neg)            -> bitmap ranking           (unique.cu)
-    neighbour lookup of the roots            -> ring kernel              (nbr_ring.cu)
-    n_id = unique(roots + neighbours), relabel
-    z, last_update = memory(n_id)            -> fused store gather + concat + time-enc
-                                                + Last aggregation + GRU (msgstore.cu, dense.cu)
-    z = gnn(z, last_update, edges, t, msg)   -> fused time-enc + attention (attn.cu)
-    pos/neg logits, BCE loss, backward, Adam
-    memory.update_state(src, dst, t, msg)    -> scatter of the rows just computed + store update
-    neighbor_loader.insert(src, dst, t)      -> ring insert
+    roots = unique(src, dst, neg)            -> bitmap ranking                 (unique.cu)
+    neighbour lookup of the roots            -> ring kernel                    (nbr_ring.cu)
+    n_id = unique(roots + neighbours), relabel                                 (step.cu)
+    z, last_update = memory(n_id)            -> store gather + concat + time-enc + Last
+                                                aggregation (msgstore.cu), gate GEMMs on
+                                                tcgen05 (gemm_tma.cu), gate math (dense.cu)
+    z = gnn(z, last_update, edges, t, msg)   -> projection / edge GEMMs + softmax core (step.cu)
+    pos/neg logits, BCE loss                 -> decoder GEMMs + loss kernel     (step.cu)
+    backward                                 -> hand-derived, same kernels; every weight
+                                                gradient is a split-K GEMM accumulating
+                                                straight into the flat gradient buffer
+    Adam                                     -> one launch over the flat buffers (dense.cu)
+    memory.update_state / loader.insert      -> on a forked stream, overlapping the backward
 
-All buffers are sized by upper bounds (3B roots, 3B*K edges, ...) and the true
-counts stay in device memory, so the step has no host synchronisation and is
-captured once into a CUDA graph; a replay needs no host work besides the launch.
-State and weights use the reference's names so that state_dicts move freely
-between this engine, the drop-in modules and the CPU oracle.
+No autograd, no allocation and no host synchronisation inside a step: all buffers are
+sized by upper bounds (3B roots, 3B*K edges, ...), the true counts stay in device memory,
+and the whole step is captured once into a CUDA graph.  State and weights use the
+reference's names so that state_dicts move freely between this engine, the drop-in
+modules and the CPU oracle.
 """
 from __future__ import annotations
 
 import ctypes
+from types import SimpleNamespace
 from typing import Dict, Optional
 
 import torch
@@ -35,44 +40,68 @@ _p = ops._p
 _stream = ops._stream
 
 
+def _up4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
 class TGNEngine:
     def __init__(self, num_nodes: int, raw_dim: int, hidden: int, size_k: int, batch_size: int,
                  device="cuda", lr: float = 1e-4, heads: int = 2, dropout: float = 0.1,
-                 log_capacity: int = 1 << 20, seed: int = 0, use_graph: bool = True):
+                 log_capacity: int = 1 << 20, seed: int = 0, use_graph: bool = True,
+                 precision: int = 3):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("TGNEngine runs on CUDA only (no CPU fallback)")
+        if hidden % 4 or hidden % heads:
+            raise ValueError("hidden must be a multiple of 4 (TMA row alignment) and of heads")
+        if precision not in (1, 3):
+            raise ValueError("precision: 1 = tf32 tensor cores, 3 = 3xTF32 (fp32-level accuracy)")
         self.dev, self.N, self.De, self.D, self.K, self.B = dev, num_nodes, raw_dim, hidden, size_k, batch_size
         self.H, self.C = heads, hidden // heads
         self.HC = self.H * self.C
         self.Dt = hidden
-        self.Dx = 2 * hidden + raw_dim + hidden
-        self.lr, self.dropout, self.seed, self.use_graph = lr, dropout, seed, use_graph
-        D, De, Dt, Dx, HC = self.D, self.De, self.Dt, self.Dx, self.HC
-        # ---- parameters: one flat buffer (one Adam launch, one grad memset)
-        shapes = [("time_enc.lin.weight", (Dt, 1)), ("time_enc.lin.bias", (Dt,)),
-                  ("memory_updater.weight_ih", (3 * D, Dx)), ("memory_updater.weight_hh", (3 * D, D)),
-                  ("memory_updater.bias_ih", (3 * D,)), ("memory_updater.bias_hh", (3 * D,)),
-                  ("conv.w_node", (4 * HC, D)), ("conv.b_node", (4 * HC,)),
-                  ("conv.lin_edge.weight", (HC, Dt + De)),
-                  ("lin_src.weight", (D, D)), ("lin_src.bias", (D,)),
-                  ("lin_dst.weight", (D, D)), ("lin_dst.bias", (D,)),
-                  ("lin_final.weight", (1, D)), ("lin_final.bias", (1,))]
-        total = sum(int(torch.Size(s).numel()) for _, s in shapes)
-        self.flat = torch.zeros(total, device=dev)
-        self.flat_grad = torch.zeros(total, device=dev)
-        self.exp_avg = torch.zeros(total, device=dev)
-        self.exp_avg_sq = torch.zeros(total, device=dev)
+        self.Dx = 2 * hidden + raw_dim + hidden          # IdentityMessage width (msg_func.py:15)
+        self.ldx = _up4(self.Dx)                          # TMA-aligned row strides
+        self.Din = self.Dt + raw_dim                      # edge_attr width (emb_module.py:28)
+        self.lde = _up4(self.Din)
+        self.lr, self.dropout, self.seed, self.use_graph, self.prec = lr, dropout, seed, use_graph, precision
+        D, Dt, HC = self.D, self.Dt, self.HC
+        # ---- parameters: one flat buffer (one Adam launch, one memset for all gradients).
+        # (name, logical shape, leading dimension): padded columns stay zero for ever -- their
+        # gradients are exact zeros, so Adam never moves them
+        table = [("time_enc.lin.weight", (Dt, 1), 1), ("time_enc.lin.bias", (Dt,), None),
+                 ("memory_updater.weight_ih", (3 * D, self.Dx), self.ldx),
+                 ("memory_updater.weight_hh", (3 * D, D), D),
+                 ("memory_updater.bias_ih", (3 * D,), None), ("memory_updater.bias_hh", (3 * D,), None),
+                 ("conv.w_node", (4 * HC, D), D), ("conv.b_node", (4 * HC,), None),
+                 ("conv.lin_edge.weight", (HC, self.Din), self.lde),
+                 ("lin_src.weight", (D, D), D), ("lin_src.bias", (D,), None),
+                 ("lin_dst.weight", (D, D), D), ("lin_dst.bias", (D,), None),
+                 ("lin_final.weight", (1, D), D), ("lin_final.bias", (1,), None)]
+        self.off: Dict[str, int] = {}
+        self.ld: Dict[str, int] = {}
+        o = 0
+        for name, shp, ld in table:
+            self.off[name] = o
+            self.ld[name] = ld if ld is not None else shp[0]
+            o += _up4(shp[0] * ld if ld is not None else shp[0])
+        self.n_param = o
+        # gradients, the loss scalar and the embedding-gradient rows share one zero-filled blob
+        R, E, Nb = self._bounds(batch_size)
+        self.zero_blob = torch.zeros(o + 4 + Nb * HC, device=dev)
+        self.flat = torch.zeros(o, device=dev)
+        self.flat_grad = self.zero_blob[:o]
+        self.loss_acc = self.zero_blob[o:o + 1]
+        self.d_emb = self.zero_blob[o + 4:].view(Nb, HC)
+        self.exp_avg = torch.zeros(o, device=dev)
+        self.exp_avg_sq = torch.zeros(o, device=dev)
         self.adam_step_dev = torch.zeros(1, device=dev)
         self.p: Dict[str, Tensor] = {}
-        o = 0
-        for name, shp in shapes:
-            n = int(torch.Size(shp).numel())
-            v = self.flat[o:o + n].view(shp)
+        for name, shp, ld in table:
+            v = self._view(self.flat, name, shp)
             v.requires_grad_()
-            v.grad = self.flat_grad[o:o + n].view(shp)
+            v.grad = self._view(self.flat_grad, name, shp)
             self.p[name] = v
-            o += n
         # ---- state
         self.memory = torch.zeros((num_nodes, D), device=dev)
         self.last_update = torch.zeros(num_nodes, dtype=torch.long, device=dev)
@@ -85,43 +114,64 @@ class TGNEngine:
         self.cur_e_id_dev = torch.zeros(1, dtype=torch.long, device=dev)   # ring event counter
         self.log_base_dev = torch.zeros(1, dtype=torch.long, device=dev)   # store log position
         self.pos_dev = torch.zeros(1, dtype=torch.long, device=dev)        # dataset cursor
-        self.step_dev = torch.zeros(1, dtype=torch.long, device=dev)       # dropout stream (advanced after backward)
+        self.step_dev = torch.zeros(1, dtype=torch.long, device=dev)       # dropout stream
         self.events_done = 0
         self.events = None
-        self._alloc_step_buffers(batch_size)
-        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
-        self.training = True
-        self.launches_per_step = None
-
-    # ------------------------------------------------------------------ buffers
-    def _alloc_step_buffers(self, B: int):
-        dev, K = self.dev, self.K
-        R = 3 * B
-        E = R * K
-        Nb = min(self.N, R + E)
-        i64 = dict(dtype=torch.long, device=dev)
-        i32 = dict(dtype=torch.int32, device=dev)
-        self.in_i64 = torch.zeros(4 * B, **i64)          # [src | dst | neg | t]: one H2D copy per step
-        self.in_ids3 = self.in_i64[:3 * B]
-        self.in_t_i64 = self.in_i64[3 * B:]
-        self.in_t_f32 = torch.zeros(B, device=dev)
-        self.in_msg = torch.zeros((B, max(self.De, 1)), device=dev)
-        self.roots = torch.zeros(R, **i64)
-        self.R_dev = torch.zeros(1, **i32)
-        self.nbr_g = torch.zeros(E, **i64)
-        self.ctr_g = torch.zeros(E, **i64)
-        self.eid = torch.zeros(E, **i64)
-        self.t_e = torch.zeros(E, device=dev)
-        self.root_off = torch.zeros(R + 1, **i32)
-        self.E_dev = torch.zeros(1, **i32)
-        self.lookup_ws = torch.zeros(max(_L().tgn_nbr_lookup_ws_bytes(R, K), 16) // 8, **i64)
-        self.n_id = torch.zeros(Nb, **i64)
-        self.Nb_dev = torch.zeros(1, **i32)
-        self.nbr_l = torch.zeros(E, **i64)
-        self.ctr_l = torch.zeros(R, **i64)
-        self.ids3_l = torch.zeros(3 * B, **i64)
+        self.side = torch.cuda.Stream(device=dev)
+        self.w = self._alloc_work(R, E, Nb, batch_size)
+        self.in_i64 = torch.zeros(4 * batch_size, dtype=torch.long, device=dev)  # [src|dst|neg|t]
+        self.in_ids3 = self.in_i64[:3 * batch_size]
+        self.in_t_i64 = self.in_i64[3 * batch_size:]
+        self.in_t_f32 = torch.zeros(batch_size, device=dev)
+        self.in_msg = torch.zeros((batch_size, max(raw_dim, 1)), device=dev)
         self.loss = torch.zeros((), device=dev)
         self.bounds = (R, E, Nb)
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.training = True
+
+    # ------------------------------------------------------------------ layout helpers
+    def _bounds(self, B: int, roots: Optional[int] = None):
+        R = 3 * B if roots is None else roots
+        E = R * self.K
+        return R, E, min(self.N, R + E)
+
+    def _view(self, flat: Tensor, name: str, shp) -> Tensor:
+        o, ld = self.off[name], self.ld[name]
+        if len(shp) == 1:
+            return flat[o:o + shp[0]]
+        return flat[o:o + shp[0] * ld].view(shp[0], ld)[:, :shp[1]]
+
+    def _g(self, name: str) -> int:
+        """element offset of a parameter's gradient inside flat_grad (== offset inside flat)"""
+        return self.off[name]
+
+    def _alloc_work(self, R: int, E: int, Nb: int, B: int, train: bool = True) -> SimpleNamespace:
+        dev, D, HC, H = self.dev, self.D, self.HC, self.H
+        f = lambda *s: torch.zeros(s, device=dev)
+        i64 = lambda *s: torch.zeros(s, dtype=torch.long, device=dev)
+        i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)
+        w = SimpleNamespace(R=R, E=E, Nb=Nb, B=B)
+        w.roots, w.R_dev = i64(R), i32(1)
+        w.nbr_g, w.ctr_g, w.eid, w.t_e = i64(E), i64(E), i64(E), f(E)
+        w.root_off, w.E_dev = i32(R + 1), i32(1)
+        w.lookup_ws = i64(max(_L().tgn_nbr_lookup_ws_bytes(R, self.K), 16) // 8)
+        w.n_id, w.Nb_dev = i64(Nb), i32(1)
+        w.nbr_l, w.ctr_l = i64(E), i64(R)
+        # memory forward
+        w.x, w.h = f(Nb, self.ldx), f(Nb, D)
+        w.lu, w.sel_ev, w.sel_dt = i64(Nb), i32(Nb), f(Nb)
+        w.gi, w.gh, w.z, w.gates = f(Nb, 3 * D), f(Nb, 3 * D), f(Nb, D), f(Nb, 4 * D)
+        # attention
+        w.proj = f(Nb, 4 * HC)
+        w.ea, w.sn_e, w.rel = f(E, self.lde), f(E, max(self.Dt, 1)), f(E)
+        w.ee, w.alpha, w.emb = f(E, HC), f(E, H), f(Nb, HC)
+        if train:
+            w.ids_l = i64(3 * B)
+            w.zcat, w.hcat, w.dhcat, w.dzcat = f(3 * B, D), f(3 * B, D), f(3 * B, D), f(3 * B, D)
+            w.logits = f(2 * B)
+            w.d_proj, w.d_ee, w.d_eat = f(Nb, 4 * HC), f(E, HC), f(E, max(self.Dt, 1))
+            w.d_z, w.d_gi, w.d_gh, w.d_x = f(Nb, D), f(Nb, 3 * D), f(Nb, 3 * D), f(Nb, self.ldx)
+        return w
 
     # ------------------------------------------------------------------ weights / state exchange
     def load_state(self, memory_sd: Dict[str, Tensor], gnn_sd: Dict[str, Tensor], lp_sd: Dict[str, Tensor]):
@@ -142,17 +192,17 @@ class TGNEngine:
 
     def export_state(self):
         HC = self.HC
-        mem = {k: self.p[k].detach().clone() for k in ("time_enc.lin.weight", "time_enc.lin.bias",
-               "memory_updater.weight_ih", "memory_updater.weight_hh", "memory_updater.bias_ih",
-               "memory_updater.bias_hh")}
+        c = lambda k: self.p[k].detach().clone().contiguous()
+        mem = {k: c(k) for k in ("time_enc.lin.weight", "time_enc.lin.bias", "memory_updater.weight_ih",
+                                 "memory_updater.weight_hh", "memory_updater.bias_ih", "memory_updater.bias_hh")}
         mem.update(memory=self.memory.clone(), last_update=self.last_update.clone(), _assoc=self.assoc.clone())
         gnn = {"time_enc.lin.weight": mem["time_enc.lin.weight"], "time_enc.lin.bias": mem["time_enc.lin.bias"],
-               "conv.lin_edge.weight": self.p["conv.lin_edge.weight"].detach().clone()}
+               "conv.lin_edge.weight": c("conv.lin_edge.weight")}
         for i, n in enumerate(("query", "key", "value", "skip")):
             gnn[f"conv.lin_{n}.weight"] = self.p["conv.w_node"].detach()[i * HC:(i + 1) * HC].clone()
             gnn[f"conv.lin_{n}.bias"] = self.p["conv.b_node"].detach()[i * HC:(i + 1) * HC].clone()
-        lp = {k: self.p[k].detach().clone() for k in ("lin_src.weight", "lin_src.bias", "lin_dst.weight",
-              "lin_dst.bias", "lin_final.weight", "lin_final.bias")}
+        lp = {k: c(k) for k in ("lin_src.weight", "lin_src.bias", "lin_dst.weight", "lin_dst.bias",
+                                "lin_final.weight", "lin_final.bias")}
         return mem, gnn, lp
 
     def reset_state(self):
@@ -218,56 +268,58 @@ class TGNEngine:
         if self.De:
             self.in_msg.copy_(msg, non_blocking=True)
 
-    # ------------------------------------------------------------------ the step
-    def _sample(self):
+    # ------------------------------------------------------------------ pieces of the step
+    def _sample(self, w, ids: Tensor, ids_l: Tensor):
         """roots -> neighbour lookup -> union -> relabel; everything bound-sized, counts on device."""
-        B, N, K = self.B, self.N, self.K
-        R, E, Nb = self.bounds
+        N, K = self.N, self.K
         L, s = _L(), _stream()
-        check(L.tgn_unique_mark(_p(self.in_ids3), 3 * B, None, N, _p(self.bitmap), s))
-        check(L.tgn_unique_rank(_p(self.bitmap), N, _p(self.roots), R, None, _p(self.R_dev), 1, s))
-        check(L.tgn_nbr_lookup(_p(self.roots), R, _p(self.R_dev), K, N, _p(self.neighbors), _p(self.e_id),
-                               _p(self.t_ring), _p(self.nbr_g), _p(self.ctr_g), _p(self.eid), _p(self.t_e),
-                               _p(self.root_off), _p(self.E_dev), _p(self.bitmap), _p(self.lookup_ws), s))
-        check(L.tgn_unique_rank(_p(self.bitmap), N, _p(self.n_id), Nb, _p(self.assoc), _p(self.Nb_dev), 0, s))
-        check(L.tgn_relabel(_p(self.nbr_g), E, _p(self.E_dev), _p(self.assoc), _p(self.nbr_l), s))
-        check(L.tgn_relabel(_p(self.roots), R, _p(self.R_dev), _p(self.assoc), _p(self.ctr_l), s))
-        check(L.tgn_relabel(_p(self.in_ids3), 3 * B, None, _p(self.assoc), _p(self.ids3_l), s))
+        check(L.tgn_unique_mark(_p(ids), ids.numel(), None, N, _p(self.bitmap), s))
+        check(L.tgn_unique_rank(_p(self.bitmap), N, _p(w.roots), w.R, None, _p(w.R_dev), 1, s))
+        check(L.tgn_nbr_lookup(_p(w.roots), w.R, _p(w.R_dev), K, N, _p(self.neighbors), _p(self.e_id),
+                               _p(self.t_ring), _p(w.nbr_g), _p(w.ctr_g), _p(w.eid), _p(w.t_e),
+                               _p(w.root_off), _p(w.E_dev), _p(self.bitmap), _p(w.lookup_ws), s))
+        check(L.tgn_unique_rank(_p(self.bitmap), N, _p(w.n_id), w.Nb, _p(self.assoc), _p(w.Nb_dev), 0, s))
+        check(L.tgn_relabel3(_p(w.nbr_g), w.E, _p(w.E_dev), _p(w.nbr_l), _p(w.roots), w.R, _p(w.R_dev),
+                             _p(w.ctr_l), _p(ids), ids.numel(), None, _p(ids_l), _p(self.assoc), s))
 
-    def _embed(self, train: bool):
-        p = self.p
+    def _memory_fwd(self, w, n_id: Tensor, S: int, S_dev: Optional[Tensor]):
+        """TGNMemory._get_updated_memory (memory_module.py:152-178): w.z [S,D], w.lu [S]."""
+        p, D, L, s = self.p, self.D, _L(), _stream()
+        check(L.tgn_msg_build_ld(ctypes.byref(self.store.struct()), _p(n_id), S, _p(S_dev), ops.AGG_LAST,
+                                 _p(self.memory), _p(self.last_update), D, _p(p["time_enc.lin.weight"]),
+                                 _p(p["time_enc.lin.bias"]), self.Dt, _p(w.x), self.ldx, _p(w.h), _p(w.lu),
+                                 _p(w.sel_ev), _p(w.sel_dt), s))
+        ops.gemm_batch([
+            ops.gemm_desc(w.x, self.flat, w.gi, m=S, n=3 * D, k=self.Dx, lda=self.ldx, ldb=self.ldx, ldc=3 * D,
+                          b_off=self.off["memory_updater.weight_ih"], bias=p["memory_updater.bias_ih"], m_dev=S_dev),
+            ops.gemm_desc(w.h, self.flat, w.gh, m=S, n=3 * D, k=D, lda=D, ldb=D, ldc=3 * D,
+                          b_off=self.off["memory_updater.weight_hh"], bias=p["memory_updater.bias_hh"], m_dev=S_dev),
+        ], self.prec)
+        check(L.tgn_gru_gates_fwd(_p(w.gi), _p(w.gh), _p(w.h), None, S, _p(S_dev), D, _p(w.z), _p(w.gates), s))
+
+    def _attention_fwd(self, w, z: Tensor, lu: Tensor, train: bool):
+        """GraphAttentionEmbedding.forward (emb_module.py:25-29) for the centres (= roots)."""
+        p, D, HC, L, s = self.p, self.D, self.HC, _L(), _stream()
         ev = self.events
-        if train:
-            z, lu = ops.memory_update(p["time_enc.lin.weight"].view(-1), p["time_enc.lin.bias"],
-                                      p["memory_updater.weight_ih"], p["memory_updater.weight_hh"],
-                                      p["memory_updater.bias_ih"], p["memory_updater.bias_hh"], self.store,
-                                      self.n_id, self.memory, self.last_update, ops.AGG_LAST, self.Nb_dev)
-        else:
-            z = ops.gather_rows(self.memory, self.n_id, self.Nb_dev)
-            lu = torch.empty_like(self.n_id)
-            check(_L().tgn_relabel(_p(self.n_id), self.n_id.numel(), _p(self.Nb_dev), _p(self.last_update),
-                                   _p(lu), _stream()))
-        emb = ops.temporal_attention(
-            z, p["conv.w_node"], p["conv.b_node"], p["conv.lin_edge.weight"],
-            p["time_enc.lin.weight"].view(-1), p["time_enc.lin.bias"], lu, self.nbr_l, ev["t"], ev["msg"],
-            self.root_off, heads=self.H, msg_rows=self.eid, centre_ids=self.ctr_l,
-            dropout_p=self.dropout if train else 0.0, seed=self.seed,
-            counts=(self.Nb_dev, self.E_dev, self.R_dev, self.step_dev))
-        return z, lu, emb
+        ops.gemm_batch([ops.gemm_desc(z, self.flat, w.proj, m=w.Nb, n=4 * HC, k=D, lda=D, ldb=D, ldc=4 * HC,
+                                      b_off=self.off["conv.w_node"], bias=p["conv.b_node"], m_dev=w.Nb_dev)], self.prec)
+        check(L.tgn_edge_attr_ld(_p(lu), _p(w.nbr_l), _p(ev["t"]), _p(ev["msg"]) if self.De else None, _p(w.eid),
+                                 w.E, _p(w.E_dev), self.De, self.Dt, _p(p["time_enc.lin.weight"]),
+                                 _p(p["time_enc.lin.bias"]), self.lde, _p(w.ea), _p(w.sn_e) if train else None,
+                                 _p(w.rel), s))
+        ops.gemm_batch([ops.gemm_desc(w.ea, self.flat, w.ee, m=w.E, n=HC, k=self.Din, lda=self.lde, ldb=self.lde,
+                                      ldc=HC, b_off=self.off["conv.lin_edge.weight"], m_dev=w.E_dev)], self.prec)
+        check(L.tgn_attn_core_fwd(_p(w.proj), _p(w.nbr_l), _p(w.root_off), _p(w.ctr_l), w.R, _p(w.R_dev),
+                                  self.H, self.C, _p(w.ee), self.dropout if train else 0.0, self.seed,
+                                  _p(self.step_dev), _p(w.emb), _p(w.alpha), s))
 
-    def _logits(self, emb: Tensor):
-        p, B = self.p, self.B
-        a = ops.linear(emb.index_select(0, self.ids3_l[:B]), p["lin_src.weight"], p["lin_src.bias"])
-        b = ops.linear(emb.index_select(0, self.ids3_l[B:]), p["lin_dst.weight"], p["lin_dst.bias"])
-        h = (a.repeat(2, 1) + b).relu()
-        return ops.linear(h, p["lin_final.weight"], p["lin_final.bias"]).view(2, B)
-
-    def _update_state(self, z: Tensor, lu: Tensor):
+    def _update_state(self, w):
+        """memory.update_state + neighbor_loader.insert (memory_module.py:126-138, epoch_utils.py:300).
+        Train ordering: memory rows first (they are the rows the forward just produced: same
+        store, same weights), then the store, then the ring."""
         B = self.B
-        # memory[n] = z[assoc[n]] for n in (src, dst): the rows _update_memory would recompute
-        # (memory_module.py:147-150) are the rows the forward just produced (same store, same weights)
-        ops.memory_scatter(self.in_ids3[:2 * B], z.detach(), lu, self.memory, self.last_update,
-                           src_rows=self.ids3_l[:2 * B])
+        ops.memory_scatter(self.in_ids3[:2 * B], w.z, w.lu, self.memory, self.last_update,
+                           src_rows=w.ids_l[:2 * B])
         self.store.update(self.in_ids3[:B], self.in_ids3[B:2 * B], self.in_t_i64, self.in_msg,
                           base_dev=self.log_base_dev)
         check(_L().tgn_nbr_insert(_p(self.in_ids3), self.in_ids3[B:].data_ptr(), _p(self.in_t_f32), B, 0,
@@ -275,15 +327,90 @@ class TGNEngine:
                                   _p(self.t_ring), _stream()))
 
     def _train_body(self):
-        self.flat_grad.zero_()
-        self._sample()
-        z, lu, emb = self._embed(True)
-        logits = self._logits(emb)
-        loss = torch.nn.functional.softplus(-logits[0]).mean() + torch.nn.functional.softplus(logits[1]).mean()
-        self._update_state(z, lu)
-        loss.backward()
+        w, p, B, D, HC, L = self.w, self.p, self.B, self.D, self.HC, _L()
+        off, fg, fl = self.off, self.flat_grad, self.flat
+        main = torch.cuda.current_stream()
+        self.zero_blob.zero_()
+        self._sample(w, self.in_ids3, w.ids_l)
+        self._memory_fwd(w, w.n_id, w.Nb, w.Nb_dev)
+        # ---- state update on a forked stream: it only needs z / last_update of the forward
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self._update_state(w)
+        self._attention_fwd(w, w.z, w.lu, True)
+        s = _stream()
+        # ---- decoder + loss (decoder.py:24-27; BCEWithLogits, pyg-mem-tgn.py:51)
+        check(L.tgn_gather_rows(_p(w.emb), _p(w.ids_l), 3 * B, None, HC, _p(w.zcat), s))
+        ops.gemm_batch([
+            ops.gemm_desc(w.zcat, fl, w.hcat, m=B, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_src.weight"],
+                          bias=p["lin_src.bias"]),
+            ops.gemm_desc(w.zcat, fl, w.hcat, m=2 * B, n=D, k=D, lda=D, ldb=D, ldc=D, a_off=B * D, c_off=B * D,
+                          b_off=off["lin_dst.weight"], bias=p["lin_dst.bias"]),
+        ], self.prec)
+        gptr = lambda name: fg.data_ptr() + 4 * off[name]
+        check(L.tgn_dec_loss(_p(w.hcat), w.hcat.data_ptr() + 4 * B * D, _p(p["lin_final.weight"]),
+                             _p(p["lin_final.bias"]), B, D, _p(self.loss_acc), _p(w.logits),
+                             w.dhcat.data_ptr() + 4 * B * D, _p(w.dhcat), gptr("lin_final.weight"),
+                             gptr("lin_final.bias"), gptr("lin_src.bias"), gptr("lin_dst.bias"), s))
+        ops.gemm_batch([
+            # dW_src += dhs^T z_src ; dW_dst += dh^T [z_dst; z_neg]
+            ops.gemm_desc(w.dhcat, w.zcat, fg, m=D, n=D, k=B, lda=D, ldb=D, ldc=D, trans_a=True, trans_b=True,
+                          mode=1, c_off=off["lin_src.weight"]),
+            ops.gemm_desc(w.dhcat, w.zcat, fg, m=D, n=D, k=2 * B, lda=D, ldb=D, ldc=D, trans_a=True, trans_b=True,
+                          mode=1, a_off=B * D, b_off=B * D, c_off=off["lin_dst.weight"]),
+            # d z_src = dhs W_src ; d [z_dst; z_neg] = dh W_dst
+            ops.gemm_desc(w.dhcat, fl, w.dzcat, m=B, n=D, k=D, lda=D, ldb=D, ldc=D, trans_b=True,
+                          b_off=off["lin_src.weight"]),
+            ops.gemm_desc(w.dhcat, fl, w.dzcat, m=2 * B, n=D, k=D, lda=D, ldb=D, ldc=D, trans_b=True,
+                          a_off=B * D, c_off=B * D, b_off=off["lin_dst.weight"]),
+        ], self.prec)
+        check(L.tgn_scatter_add_rows(_p(w.dzcat), _p(w.ids_l), 3 * B, None, HC, _p(self.d_emb), s))
+        # ---- attention backward
+        check(L.tgn_attn_core_bwd(_p(w.proj), _p(w.nbr_l), _p(w.root_off), _p(w.ctr_l), w.R, _p(w.R_dev),
+                                  self.H, self.C, _p(w.ee), _p(w.alpha), _p(self.d_emb), self.dropout, self.seed,
+                                  _p(self.step_dev), w.Nb, _p(w.d_proj), _p(w.d_ee), s))
+        split_e = max(1, min(16, w.E // 512))
+        split_n = max(1, min(16, w.Nb // 512))
+        g = [  # dW_edge += d_ee^T edge_attr ; dW_node += d_proj^T z ; d z = d_proj W_node
+            ops.gemm_desc(w.d_ee, w.ea, fg, m=HC, n=self.Din, k=w.E, lda=HC, ldb=self.lde, ldc=self.lde,
+                          trans_a=True, trans_b=True, mode=2, split_k=split_e, k_dev=w.E_dev,
+                          c_off=off["conv.lin_edge.weight"]),
+            ops.gemm_desc(w.d_proj, w.z, fg, m=4 * HC, n=D, k=w.Nb, lda=4 * HC, ldb=D, ldc=D, trans_a=True,
+                          trans_b=True, mode=2, split_k=split_n, k_dev=w.Nb_dev, c_off=off["conv.w_node"]),
+            ops.gemm_desc(w.d_proj, fl, w.d_z, m=w.Nb, n=D, k=4 * HC, lda=4 * HC, ldb=D, ldc=D, trans_b=True,
+                          b_off=off["conv.w_node"], m_dev=w.Nb_dev),
+        ]
+        if self.Dt:  # d edge_attr[:, :Dt] = d_ee W_edge[:, :Dt]  (time-encoder gradient)
+            g.append(ops.gemm_desc(w.d_ee, fl, w.d_eat, m=w.E, n=self.Dt, k=HC, lda=HC, ldb=self.lde, ldc=self.Dt,
+                                   trans_b=True, b_off=off["conv.lin_edge.weight"], m_dev=w.E_dev))
+        ops.gemm_batch(g, self.prec)
+        ops.colsum(w.d_proj, w.Nb, 4 * HC, 4 * HC, p["conv.b_node"].grad, True, rows_dev=w.Nb_dev)
+        if self.Dt:
+            check(L.tgn_time_bwd_sin(_p(w.rel), None, w.E, _p(w.E_dev), _p(w.sn_e), self.Dt, _p(w.d_eat), self.Dt,
+                                     gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), s))
+        # ---- GRU backward (torch.nn.GRUCell, memory_module.py:72,172)
+        check(L.tgn_gru_gates_bwd(_p(w.d_z), _p(w.gates), _p(w.h), None, w.Nb, _p(w.Nb_dev), D, _p(w.d_gi),
+                                  _p(w.d_gh), None, s))
+        ops.gemm_batch([
+            ops.gemm_desc(w.d_gi, w.x, fg, m=3 * D, n=self.Dx, k=w.Nb, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
+                          trans_a=True, trans_b=True, mode=2, split_k=split_n, k_dev=w.Nb_dev,
+                          c_off=off["memory_updater.weight_ih"]),
+            ops.gemm_desc(w.d_gh, w.h, fg, m=3 * D, n=D, k=w.Nb, lda=3 * D, ldb=D, ldc=D, trans_a=True,
+                          trans_b=True, mode=2, split_k=split_n, k_dev=w.Nb_dev,
+                          c_off=off["memory_updater.weight_hh"]),
+            # d x = d_gi W_ih (only its time-encoding columns are consumed)
+            ops.gemm_desc(w.d_gi, fl, w.d_x, m=w.Nb, n=self.Dx, k=3 * D, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
+                          trans_b=True, b_off=off["memory_updater.weight_ih"], m_dev=w.Nb_dev),
+        ], self.prec)
+        ops.colsum(w.d_gi, w.Nb, 3 * D, 3 * D, p["memory_updater.bias_ih"].grad, True, rows_dev=w.Nb_dev)
+        ops.colsum(w.d_gh, w.Nb, 3 * D, 3 * D, p["memory_updater.bias_hh"].grad, True, rows_dev=w.Nb_dev)
+        if self.Dt:
+            check(L.tgn_time_encode_bwd(_p(w.sel_dt), _p(w.sel_ev), w.Nb, _p(w.Nb_dev), _p(p["time_enc.lin.weight"]),
+                                        _p(p["time_enc.lin.bias"]), self.Dt, w.d_x.data_ptr() + 4 * (2 * D + self.De),
+                                        self.ldx, gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), s))
+        self.loss.copy_(self.loss_acc[0])
+        main.wait_stream(self.side)
         ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.adam_step_dev, self.lr)
-        self.loss.copy_(loss.detach())
         self.step_dev.add_(1)
 
     def _run(self, key: tuple, body):
@@ -292,7 +419,7 @@ class TGNEngine:
             return
         g = self._graphs.get(key)
         if g is None:
-            # warm-up already happened: the first calls of every configuration run eagerly
+            # warm-up: the first calls of every configuration run eagerly
             cnt = self._graphs.get(("warm",) + key, 0)
             if cnt < 3:
                 self._graphs[("warm",) + key] = cnt + 1
@@ -307,7 +434,7 @@ class TGNEngine:
 
     def train_step(self, from_device: bool = True):
         """One training batch.  from_device=True: slice the next batch out of the resident event
-        arrays (set_events); False: the caller staged it with stage_batch()."""
+        arrays (set_events); False: the caller staged it with stage_batch() / stage_packed()."""
         if from_device:
             self._run(("train", True), lambda: (self.stage_batch_from_device(), self._train_body()))
         else:
@@ -322,26 +449,29 @@ class TGNEngine:
         """test() body for one batch (epoch_utils.py:28-157): scores of the positives and of
         the [B,Q] negatives, then eval-mode update_state (store first, then memory) and insert.
         Returns (pos[B], neg[B,Q]) probabilities."""
-        dev, N = self.dev, self.N
+        dev, N, D, HC, L = self.dev, self.N, self.D, self.HC, _L()
         src, dst, neg = src.to(dev, torch.long), dst.to(dev, torch.long), neg.to(dev, torch.long)
         t_i = t.to(dev, torch.long)
         B, Q = neg.shape
-        n_in = torch.cat([src, dst, neg.reshape(-1)])
-        roots = ops.unique_relabel([n_in], N)
-        ids, edge_index, e_id, _, root_off = ops.nbr_lookup(roots, self.neighbors, self.e_id, self.t_ring, self.assoc)
-        p, ev = self.p, self.events
-        z = ops.gather_rows(self.memory, ids)
-        lu = self.last_update[ids]
-        ctr_l = ops.relabel(roots, self.assoc)
-        emb = ops.temporal_attention(z, p["conv.w_node"], p["conv.b_node"], p["conv.lin_edge.weight"],
-                                     p["time_enc.lin.weight"].view(-1), p["time_enc.lin.bias"], lu,
-                                     edge_index[0].contiguous(), ev["t"], ev["msg"], root_off, heads=self.H,
-                                     msg_rows=e_id, centre_ids=ctr_l)
-        Nb, D = emb.shape
-        hs = ops.sgemm(emb, p["lin_src.weight"], p["lin_src.bias"], m=Nb, n=D, k=D, lda=D, ldb=D)
-        hd = ops.sgemm(emb, p["lin_dst.weight"], p["lin_dst.bias"], m=Nb, n=D, k=D, lda=D, ldb=D)
-        sl, dl, nl = self.assoc[src], self.assoc[dst], self.assoc[neg.reshape(-1)]
-        wf, bf = p["lin_final.weight"].view(-1), p["lin_final.bias"]
+        ids = torch.cat([src, dst, neg.reshape(-1)]).contiguous()
+        R, E, Nb = self._bounds(B, roots=min(N, ids.numel()))
+        w = self._alloc_work(R, E, Nb, B, train=False)
+        ids_l = torch.empty_like(ids)
+        self._sample(w, ids, ids_l)
+        s = _stream()
+        check(L.tgn_gather_rows(_p(self.memory), _p(w.n_id), w.Nb, _p(w.Nb_dev), D, _p(w.z), s))
+        check(L.tgn_relabel(_p(w.n_id), w.Nb, _p(w.Nb_dev), _p(self.last_update), _p(w.lu), s))
+        self._attention_fwd(w, w.z, w.lu, False)
+        hs, hd = torch.empty((Nb, D), device=dev), torch.empty((Nb, D), device=dev)
+        p, off = self.p, self.off
+        ops.gemm_batch([
+            ops.gemm_desc(w.emb, self.flat, hs, m=Nb, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_src.weight"],
+                          bias=p["lin_src.bias"], m_dev=w.Nb_dev),
+            ops.gemm_desc(w.emb, self.flat, hd, m=Nb, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_dst.weight"],
+                          bias=p["lin_dst.bias"], m_dev=w.Nb_dev),
+        ], self.prec)
+        sl, dl, nl = ids_l[:B], ids_l[B:2 * B], ids_l[2 * B:]
+        wf, bf = p["lin_final.weight"].reshape(-1), p["lin_final.bias"]
         pos = ops.link_score(hs, hd, sl, dl, wf, bf, True)
         negs = ops.link_score(hs, hd, sl.repeat_interleave(Q), nl, wf, bf, True).view(B, Q)
         # eval ordering of update_state: store first, then memory (memory_module.py:135-138)
@@ -349,11 +479,10 @@ class TGNEngine:
         self.log_base_dev += B
         self.events_done += B
         n_upd = ops.unique_relabel([src, dst], N)
-        m_new, lu_new = ops.memory_update(p["time_enc.lin.weight"].view(-1), p["time_enc.lin.bias"],
-                                          p["memory_updater.weight_ih"], p["memory_updater.weight_hh"],
-                                          p["memory_updater.bias_ih"], p["memory_updater.bias_hh"], self.store,
-                                          n_upd, self.memory, self.last_update, ops.AGG_LAST, None)
-        ops.memory_scatter(n_upd, m_new, lu_new, self.memory, self.last_update)
+        S = n_upd.numel()
+        wm = self._alloc_work(1, 1, S, 1, train=False)
+        self._memory_fwd(wm, n_upd, S, None)
+        ops.memory_scatter(n_upd, wm.z, wm.lu, self.memory, self.last_update)
         ops.nbr_insert(src, dst, t_i.to(torch.float32), 0, self.neighbors, self.e_id, self.t_ring,
                        cur_e_id_dev=self.cur_e_id_dev)
         return pos, negs
@@ -362,17 +491,16 @@ class TGNEngine:
     def flush_to_eval(self):
         """TGNMemory.train(False) (memory_module.py:209-215): every node goes through the updater
         with its stored messages, then the store is cleared."""
-        p = self.p
         new_mem = torch.empty_like(self.memory)
         new_lu = torch.empty_like(self.last_update)
-        for lo in range(0, self.N, 1 << 16):
-            ids = torch.arange(lo, min(self.N, lo + (1 << 16)), device=self.dev)
-            m, lu = ops.memory_update(p["time_enc.lin.weight"].view(-1), p["time_enc.lin.bias"],
-                                      p["memory_updater.weight_ih"], p["memory_updater.weight_hh"],
-                                      p["memory_updater.bias_ih"], p["memory_updater.bias_hh"], self.store,
-                                      ids, self.memory, self.last_update, ops.AGG_LAST, None)
-            new_mem[lo:lo + ids.numel()] = m
-            new_lu[lo:lo + ids.numel()] = lu
+        chunk = 1 << 16
+        wm = self._alloc_work(1, 1, min(self.N, chunk), 1, train=False)
+        for lo in range(0, self.N, chunk):
+            ids = torch.arange(lo, min(self.N, lo + chunk), device=self.dev)
+            n = ids.numel()
+            self._memory_fwd(wm, ids, n, None)
+            new_mem[lo:lo + n] = wm.z[:n]
+            new_lu[lo:lo + n] = wm.lu[:n]
         self.memory.copy_(new_mem)
         self.last_update.copy_(new_lu)
         self.store.reset()

@@ -378,6 +378,29 @@ def sgemm(a: Tensor, b: Tensor, bias: Optional[Tensor] = None, *, m: int, n: int
     return out
 
 
+def gemm_desc(a, b, c, *, m: int, n: int, k: int, lda: int, ldb: int, ldc: int, bias=None,
+              trans_a: bool = False, trans_b: bool = False, mode: int = 0, split_k: int = 1,
+              m_dev=None, k_dev=None, a_off: int = 0, b_off: int = 0, c_off: int = 0) -> _cabi.GemmDesc:
+    """One problem of a tgn_gemm_batch launch: C[m,n] (=, +=, atomic +=) op(A) op(B) (+bias).
+    mode 0 store / 1 accumulate / 2 atomic (needed for split_k > 1).  *_off are element offsets."""
+    d = _cabi.GemmDesc()
+    d.a, d.b, d.c = a.data_ptr() + 4 * a_off, b.data_ptr() + 4 * b_off, c.data_ptr() + 4 * c_off
+    d.bias = _p(bias)
+    d.m_dev, d.k_dev = _p(m_dev), _p(k_dev)
+    d.m, d.n, d.k, d.lda, d.ldb, d.ldc = m, n, k, lda, ldb, ldc
+    d.trans_a, d.trans_b, d.mode, d.split_k = int(trans_a), int(trans_b), mode, split_k
+    return d
+
+
+def gemm_batch(descs: Sequence[_cabi.GemmDesc], prec: Optional[int] = None):
+    """Up to 4 GEMMs in one TMA + tcgen05 launch (tgn_gemm_batch)."""
+    prec = GEMM_PRECISION if prec is None else prec
+    if prec not in (1, 3):
+        raise _cabi.TgnError("gemm_batch runs on the tensor cores: precision must be 1 (tf32) or 3 (3xtf32)")
+    arr = (_cabi.GemmDesc * len(descs))(*descs)
+    check(_L().tgn_gemm_batch(ctypes.byref(arr), len(descs), prec, _stream()))
+
+
 def gather_rows(table: Tensor, rows: Tensor, num_dev: Optional[Tensor] = None) -> Tensor:
     rows = _need(rows, torch.int64, "rows")
     out = torch.empty((rows.numel(), table.shape[1]), dtype=torch.float32, device=table.device)

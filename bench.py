@@ -144,6 +144,8 @@ def main():
     ap.add_argument("--prefill", type=int, default=1_000_000)
     ap.add_argument("--cpu-steps", type=int, default=60, help="bounded sample of the CPU baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", type=int, default=3, choices=[1, 3],
+                    help="tensor-core GEMM mode: 3 = 3xTF32 (fp32-level accuracy), 1 = single-pass tf32")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -188,7 +190,7 @@ def main():
     data = synth.synth_events(WORKLOAD, seed=rank, max_events=need)
     N, De = data["num_nodes"], data["raw_dim"]
     eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.1, use_graph=True,
-                    log_capacity=data["src"].size, seed=1234 + rank)
+                    log_capacity=data["src"].size, seed=1234 + rank, precision=args.precision)
     eng.load_state(*init_state_dicts(De, HIDDEN, N, seed=1))
     ev = {k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")}
     eng.set_events(**ev)
@@ -299,7 +301,7 @@ def dominant_kernel_roofline(eng, dev):
     with CUDA events on the launching stream.  Algorithmic work per launch:
     2*S*Dx*3D flops; bytes S*Dx*4 + 3D*Dx*4 + S*3D*4."""
     from tgn_b200 import ops
-    S = int(eng.Nb_dev.item())
+    S = int(eng.w.Nb_dev.item())
     Dx, D = eng.Dx, eng.D
     x = torch.randn(max(S, 1), Dx, device=dev)
     w, b = eng.p["memory_updater.weight_ih"].detach(), eng.p["memory_updater.bias_ih"].detach()

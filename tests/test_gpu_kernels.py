@@ -263,6 +263,35 @@ def test_sgemm_gather_and_device_counts(ops, prec):
     torch.testing.assert_close(got.cpu(), A[:33].t() @ B[:33], rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("prec", [3, 1])
+@pytest.mark.parametrize("m,n,k,ta,tb,split,live", [(300, 472, 5000, True, True, 8, 4321), (400, 100, 5000, True, True, 8, 4999),
+                                                   (100, 104, 6000, True, True, 11, 5555), (260, 100, 400, False, True, 1, 333),
+                                                   (200, 64, 96, False, False, 1, 70)])
+def test_tma_gemm_device_reduction_length(ops, prec, m, n, k, ta, tb, split, live):
+    """TMA path: the reduction stops at *k_dev exactly (tail of the last k-block masked in shared
+    memory) in both precisions; rows past the live length hold garbage that must not leak in."""
+    g = torch.Generator(device="cpu").manual_seed(k + live)
+    A = torch.randn((k, m) if ta else (m, k), generator=g)
+    B = torch.randn((k, n) if tb else (n, k), generator=g)
+    Am, Bm = A.clone(), B.clone()
+    if ta: A[live:] = 1e30
+    else: A[:, live:] = 1e30
+    if tb: B[live:] = -1e30
+    else: B[:, live:] = -1e30
+    for X in (Am, Bm):
+        pass
+    ref = ((Am[:live].t() if ta else Am[:, :live]).double() @ (Bm[:live] if tb else Bm[:, :live].t()).double())
+    kdev = torch.tensor([live], dtype=torch.int32, device=DEV)
+    out = torch.zeros(m, n, device=DEV)
+    ops.sgemm(A.to(DEV), B.to(DEV), m=m, n=n, k=k, lda=A.shape[1], ldb=B.shape[1], trans_a=ta, trans_b=tb, out=out,
+              split_k=split, k_dev=kdev, prec=prec)
+    scale = float(ref.abs().max())
+    if prec == 1:
+        torch.testing.assert_close(out.cpu().double(), ref, rtol=2e-2, atol=2e-3 * scale)
+    else:
+        torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-5, atol=1e-5 * max(4.0, live ** 0.5) * 2)
+
+
 @pytest.mark.parametrize("S,Dx,D", [(1, 5, 3), (333, 472, 100), (4000, 274, 100)])
 def test_gru_cell_fwd_bwd(ops, S, Dx, D):
     torch.manual_seed(S)

@@ -253,8 +253,9 @@ __global__ void __launch_bounds__(kGThreads, 1)
     const uint32_t a_step = P.a_mn ? 1024u : 32u, b_step = P.b_mn ? 1024u : 32u;
     for (int kb = 0; kb < nk; ++kb) {
       const int s = kb % kGStages;
-      const bool conv = split3 || (tail_mask && kb == nk - 1);
-      g_mbar_wait(conv ? &s_conv[s] : &s_full[s], (kb / kGStages) & 1);
+      // with a split or mask pass in this CTA the issuer follows warps 2-5 through every
+      // phase (a barrier may only be waited on phase by phase)
+      g_mbar_wait((split3 || tail_mask) ? &s_conv[s] : &s_full[s], (kb / kGStages) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         const uint32_t a_hi = g_smem_u32(smem + (size_t)s * kGStageBytes);
@@ -281,9 +282,13 @@ __global__ void __launch_bounds__(kGThreads, 1)
     // ===== split pass (3xTF32) + epilogue: warps 2..5 =====
     const int et = tid - 64;  // 0..127
     if (split3 || tail_mask) {
-      for (int kb = split3 ? 0 : nk - 1; kb < nk; ++kb) {
+      for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % kGStages;
         g_mbar_wait(&s_full[s], (kb / kGStages) & 1);
+        if (!split3 && kb != nk - 1) {  // tf32 mode: only the masked last block is touched
+          g_mbar_arrive(&s_conv[s]);
+          continue;
+        }
         float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * kGStageBytes);
         float4* a_lo = a_hi + kGTileBytes / 16;
         float4* b_hi = a_hi + 2 * (kGTileBytes / 16);

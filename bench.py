@@ -142,7 +142,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--prefill", type=int, default=1_000_000)
-    ap.add_argument("--cpu-steps", type=int, default=60, help="bounded sample of the CPU baseline leg")
+    ap.add_argument("--cpu-steps", type=int, default=400, help="bounded sample of the CPU baseline leg")
+    ap.add_argument("--no-kernel-rooflines", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=int, default=3, choices=[1, 3],
                     help="tensor-core GEMM mode: 3 = 3xTF32 (fp32-level accuracy), 1 = single-pass tf32")
@@ -250,8 +251,8 @@ def main():
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         eng.train_step(from_device=True)
         torch.cuda.synchronize()
-    eng.use_graph = eng_use_graph
-    kern = [e for e in prof.events() if e.device_type is not None and "cuda" in str(e.device_type).lower()]
+    kern = [e for e in prof.events() if e.device_type is not None and "cuda" in str(e.device_type).lower()
+            and "memset" not in e.name.lower() and "memcpy" not in e.name.lower()]
     ours = [e for e in kern if "tgn::" in e.name]
     per_kernel = {}
     for e in kern:
@@ -261,8 +262,9 @@ def main():
         per_kernel[key][1] += e.device_time
     top = sorted(per_kernel.items(), key=lambda kv: -kv[1][1])[:6]
 
-    # ---------------- roofline of the dominant kernel: the GRU input-gate GEMM
+    # ---------------- roofline of the dominant kernel, timed inside (eager) steps
     roof = dominant_kernel_roofline(eng, dev)
+    eng.use_graph = eng_use_graph
 
     if rank == 0:
         peaks = {}
@@ -272,7 +274,8 @@ def main():
             pass
         line = {"metric": "train events/sec (TGN step)", "value": world * K_steps * B / (ms / 1e3), "unit": "events/s",
                 "n_gpus": world, "steps": K_steps, "warmup": W, "ms_per_step": ms / K_steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32x3 (fp32-accurate split, fp32 accumulate)" if args.precision == 3 else "tf32",
                 "data": "synthetic", "config": config,
                 "e2e": {"value": world * K_steps * B / (ms_e2e / 1e3), "unit": "events/s",
                         "h2d_bytes_per_step": 4 * B * 8 + B * De * 4, "d2h_bytes_per_step": 4,
@@ -282,46 +285,42 @@ def main():
                 "top_kernels_eager_us": {k: [v[0], round(v[1], 1)] for k, v in top},
                 "clocks": clocks.summary(), "final_loss": {"device_arm": loss_dev, "e2e_arm": loss_host},
                 "roofline": roof_with_peak(roof, peaks)}
+        if world == 1 and not args.no_kernel_rooflines:
+            line["kernel_rooflines"] = kernel_rooflines(dev, peaks)
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
             cdata = synth.synth_events(WORKLOAD, seed=0, max_events=args.prefill + (args.cpu_steps + 8) * B)
-            done, t_cpu = run_cpu_reference(cdata, args.cpu_steps, 5, args.prefill, budget_s=40.0)
+            done, t_cpu = run_cpu_reference(cdata, args.cpu_steps, 5, args.prefill, budget_s=25.0)
             line["cpu_baseline"] = {"value": done * B / t_cpu, "unit": "events/s", "cores": torch.get_num_threads(),
                                     "kind": "port", "ms_per_step": 1e3 * t_cpu / done,
-                                    "sample": f"{done} training steps of the same workload (same shape, batch, prefill) "
-                                              "on the host CPU, oracle port of the reference's torch-CPU path"}
+                                    "sample": f"{done} training steps ({done * B} events) of the same workload (same "
+                                              "shape, batch, prefill) on the host CPU: oracle port of the reference's "
+                                              "torch-CPU path incl. its Python-dict message store"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 def dominant_kernel_roofline(eng, dev):
-    """Times the kernel that dominates the step -- the fp32 GRU input-gate GEMM
-    gi[S,300] = x[S,Dx] W_ih^T + b (tgn::sgemm_kernel) -- alone, on the step's own shapes,
-    with CUDA events on the launching stream.  Algorithmic work per launch:
-    2*S*Dx*3D flops; bytes S*Dx*4 + 3D*Dx*4 + S*3D*4."""
-    from tgn_b200 import ops
+    """The kernel with the largest share of the step is tgn::tgemm_kernel (TMA + tcgen05 GEMM,
+    ~30% over its 7 launches); its heaviest launch is the GRU gate GEMM pair
+    gi[S,3D] = x[S,Dx] W_ih^T + b, gh[S,3D] = h[S,D] W_hh^T + b (one launch).  It is timed
+    INSIDE eager training steps with CUDA events on the launching stream (engine probe), so the
+    operands are as warm/cold as in the real step.  Algorithmic work per launch:
+    2*S*(Dx+D)*3D flops; bytes S*(Dx+D)*4 + 3D*(Dx+D)*4 + 2*S*3D*4."""
+    eng.probe = {}
+    for _ in range(24):
+        eng.train_step(from_device=True)
+    torch.cuda.synchronize()
+    ev = eng.probe["gru_gate_gemm"][4:]
+    eng.probe = None
+    t = float(np.mean([a.elapsed_time(b) for a, b in ev])) * 1e-3
     S = int(eng.w.Nb_dev.item())
     Dx, D = eng.Dx, eng.D
-    x = torch.randn(max(S, 1), Dx, device=dev)
-    w, b = eng.p["memory_updater.weight_ih"].detach(), eng.p["memory_updater.bias_ih"].detach()
-    out = torch.empty(max(S, 1), 3 * D, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    times = []
-    for i in range(13):
-        flush.zero_()                      # evict L2 between timed launches
-        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        ops.sgemm(x, w, b, m=S, n=3 * D, k=Dx, lda=Dx, ldb=Dx, out=out)
-        c.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            times.append(a.elapsed_time(c) * 1e-3)
-    t = float(np.mean(times))
-    flops = 2.0 * S * Dx * 3 * D
-    nbytes = 4.0 * (S * Dx + 3 * D * Dx + S * 3 * D)
-    return {"kernel": "tgn::sgemm_kernel<false,false> (GRU gate GEMM gi = x W_ih^T)", "rows": S, "seconds": t,
-            "flops": flops, "bytes": nbytes}
+    flops = 2.0 * S * (Dx + D) * 3 * D
+    nbytes = 4.0 * (S * (Dx + D) + 3 * D * (Dx + D) + 2 * S * 3 * D)
+    return {"kernel": "tgn::tgemm_kernel (GRU gate GEMMs gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh, one launch)",
+            "rows": S, "seconds": t, "flops": flops, "bytes": nbytes, "launches_timed": len(ev), "prec": eng.prec}
 
 
 def roof_with_peak(r, peaks):
@@ -329,10 +328,95 @@ def roof_with_peak(r, peaks):
     ach = r["flops"] / r["seconds"] / 1e12
     return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "traffic": None, "kernel": r["kernel"], "rows_per_launch": r["rows"], "us_per_launch": r["seconds"] * 1e6,
+            "launches_timed": r["launches_timed"],
             "algorithmic_flops_per_launch": r["flops"], "algorithmic_bytes_per_launch": r["bytes"],
             "achieved_gbs": r["bytes"] / r["seconds"] / 1e9,
-            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1590 (B200_PROFILING.md)",
-            "note": "fp32 CUDA-core GEMM measured against the bf16 tensor peak: the tcgen05 port of this kernel is the next optimisation"}
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS bf16)" if "bf16_tflops" in peaks
+                           else "fallback 1590 (B200_PROFILING.md)",
+            "note": "algorithmic flops (one product per multiply-add); the kernel computes in tf32 (dense tf32 peak is "
+                    "half the bf16 figure used as denominator)" + (", and issues 3 tensor-core products per algorithmic "
+                    "one (3xTF32 split for fp32-level accuracy)" if r["prec"] == 3 else "") +
+                    "; at ~5k rows per launch the launch is latency-bound, see kernel_rooflines for the same kernels "
+                    "on large launches"}
+
+
+def _time_launch(fn, reps=8, flush=None):
+    ts = []
+    for i in range(reps + 2):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ts.append(a.elapsed_time(b) * 1e-3)
+    return float(np.median(ts))
+
+
+def kernel_rooflines(dev, peaks):
+    """Large-launch roofline points of the hot-path kernels (the per-step launches at B=200 are
+    latency-bound): algorithmic bytes / CUDA-event time, L2 flushed between launches."""
+    from tgn_b200 import ops
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    tf = peaks.get("bf16_tflops", 1590.0)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    out = []
+    g = torch.Generator(device="cpu").manual_seed(0)
+    # ---- t-CSR most-recent-k sampler: 2M roots over a 40M-entry graph (deg ~ 113), k = 10
+    N, deg = 352_637, 113
+    indptr = (torch.arange(N + 1, dtype=torch.int64) * deg).to(torch.int32).to(dev)
+    nnz = N * deg
+    ts = torch.arange(deg, dtype=torch.float32).repeat(N).to(dev)
+    indices = torch.randint(0, N, (nnz,), generator=g, dtype=torch.int32).to(dev)
+    eid = torch.arange(nnz, dtype=torch.int32, device=dev)
+    R, k = 2_000_000, 10
+    roots = torch.randint(0, N, (R,), generator=g, dtype=torch.int32).to(dev)
+    rts = (torch.rand(R, generator=g) * deg + 12).to(dev)
+    t = _time_launch(lambda: ops.tcsr_sample(indptr, indices, eid, ts, roots, rts, k), flush=flush)
+    nbytes = R * (8 + 4 * 7 + k * 12 + k * 20 + 8)   # indptr pair, ~log2(deg) probes, k entries in, k rows out, root
+    out.append({"kernel": "tgn::tcsr_sample_kernel (recent-10, 2M roots, deg 113)", "bound": "hbm",
+                "achieved": nbytes / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": nbytes / t / 1e9 / hbm,
+                "sampled_nbrs_per_s": R * k / t, "us": t * 1e6})
+    del indices, eid, ts, indptr
+    # ---- neighbour-ring lookup: 1M roots, K = 10
+    K = 10
+    nb = torch.randint(0, N, (N, K), generator=g).to(dev)
+    ei = torch.randint(0, 1 << 30, (N, K), generator=g).to(dev)
+    tt = torch.rand(N, K, generator=g).to(dev)
+    R2 = 1_000_000
+    r2 = torch.randint(0, N, (R2,), generator=g).to(dev)
+    t = _time_launch(lambda: ops.nbr_lookup_raw(r2, nb, ei, tt, None), flush=flush)
+    nbytes = R2 * (8 + K * 20 + K * 28)
+    out.append({"kernel": "tgn::nbr_lookup_kernel (1M roots, K=10)", "bound": "hbm", "achieved": nbytes / t / 1e9,
+                "peak": hbm, "unit": "GB/s", "frac": nbytes / t / 1e9 / hbm, "sampled_nbrs_per_s": R2 * K / t,
+                "us": t * 1e6})
+    del nb, ei, tt
+    # ---- aggregators on materialised messages: M = 1M messages of width 472 into S = 250k segments
+    M, S, W = 1_000_000, 250_000, 472
+    msg = torch.randn(M, W, device=dev)
+    idx = torch.randint(0, S, (M,), generator=g).to(dev)
+    tm = torch.randint(0, 1000, (M,), generator=g).to(dev)
+    t = _time_launch(lambda: ops.agg_last(msg, idx, tm, S), flush=flush)
+    nbytes = M * 16 + S * 8 + S * 2 * W * 4
+    out.append({"kernel": "tgn::agg_last (1M msgs x 472 -> 250k segments)", "bound": "hbm", "achieved": nbytes / t / 1e9,
+                "peak": hbm, "unit": "GB/s", "frac": nbytes / t / 1e9 / hbm, "us": t * 1e6})
+    t = _time_launch(lambda: ops.agg_mean(msg, idx, S), flush=flush)
+    nbytes = M * W * 4 + M * 8 + S * W * 4
+    out.append({"kernel": "tgn::agg_mean (1M msgs x 472 -> 250k segments)", "bound": "hbm", "achieved": nbytes / t / 1e9,
+                "peak": hbm, "unit": "GB/s", "frac": nbytes / t / 1e9 / hbm, "us": t * 1e6})
+    del msg, idx, tm
+    # ---- the GEMM kernel on a large launch: GRU gate GEMM for 262,144 rows
+    Sg, Dx, D = 262_144, 472, 100
+    x = torch.randn(Sg, Dx, device=dev); wih = torch.randn(3 * D, Dx, device=dev); o = torch.empty(Sg, 3 * D, device=dev)
+    for prec in (3, 1):
+        t = _time_launch(lambda: ops.sgemm(x, wih, m=Sg, n=3 * D, k=Dx, lda=Dx, ldb=Dx, out=o, prec=prec), flush=flush)
+        fl = 2.0 * Sg * Dx * 3 * D
+        out.append({"kernel": f"tgn::tgemm_kernel (x W_ih^T, 262144 rows, {'3xTF32' if prec == 3 else 'tf32'})",
+                    "bound": "tensor", "achieved": fl / t / 1e12, "peak": tf, "unit": "TFLOP/s",
+                    "frac": fl / t / 1e12 / tf, "achieved_gbs": 4.0 * (Sg * Dx + Sg * 3 * D) / t / 1e9, "us": t * 1e6})
+    return out
 
 
 if __name__ == "__main__":

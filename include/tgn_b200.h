@@ -123,8 +123,9 @@ int32_t tgn_tcsr_sample(const int32_t* indptr, const int32_t* indices, const int
  *   out[s,:]  = msg[argmax[s],:] or 0.
  * tgn_agg_mean  = MeanAggregator.forward   (modules/msg_agg.py:24-26).
  * t is int64 (t_is_float=0) or float32 (t_is_float=1).
- * ws: 16*S bytes (last) / 4*S bytes (mean).
+ * ws: 16*S bytes (last) / tgn_agg_mean_ws_bytes(M, S) bytes (mean).
  * ------------------------------------------------------------------------- */
+int64_t tgn_agg_mean_ws_bytes(int32_t num_msgs, int32_t dim_size);
 int32_t tgn_agg_last(const float* msg, const int64_t* index, const void* t, int32_t t_is_float,
                      int32_t num_msgs, int32_t dim_size, int32_t width, float* out,
                      int64_t* argmax, void* ws, void* stream);
@@ -199,12 +200,14 @@ int32_t tgn_msg_build(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
 
 /* tgn_msg_build with a caller-chosen row stride ldx >= message width (padding columns are
  * zeroed; a stride that is a multiple of 4 makes x a TMA operand) and, when h_out is given,
- * the gather h_out[s,:] = memory[n_id[s],:] (memory_module.py:172) in the same pass. */
+ * the gather h_out[s,:] = memory[n_id[s],:] (memory_module.py:172) in the same pass;
+ * sin_out [S,time_dim] (nullable, last aggregator) keeps sin(w*dt+b) of the chosen event for
+ * tgn_time_bwd_sin. */
 int32_t tgn_msg_build_ld(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
                          const int32_t* num_dev, int32_t agg_mode, const float* memory,
                          const int64_t* last_update, int32_t memory_dim, const float* time_w,
                          const float* time_b, int32_t time_dim, float* x, int32_t ldx, float* h_out,
-                         void* lu_out, int32_t* sel_ev, float* sel_dt, void* stream);
+                         float* sin_out, void* lu_out, int32_t* sel_ev, float* sel_dt, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Dense fp32 building block: C[M,N] (=|+=) A[M,K] * B^T|B (+ bias).

@@ -11,7 +11,9 @@
 // produces) are combined with a segmented shuffle scan first, so a run issues a
 // single atomic.
 // MeanAggregator.forward (msg_agg.py:24-26) = scatter(..., reduce="mean"):
-// sum / max(count, 1); empty segments stay 0.
+// sum / max(count, 1); empty segments stay 0.  No float atomics: message ids are counting-sorted
+// by segment (integer atomics + a chained scan), then one warp per segment streams its rows
+// with 128-bit loads, so the message matrix is read exactly once and the sum is reproducible.
 #include "../../include/tgn_b200.h"
 #include "common.cuh"
 
@@ -105,34 +107,143 @@ __global__ void agg_last_gather4_kernel(const float4* __restrict__ msg,
   }
 }
 
-__global__ void agg_mean_zero_kernel(float* out, float* cnt, int S, int W) {
-  const long long total = (long long)S * W;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x)
-    out[e] = 0.f;
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x)
-    cnt[s] = 0.f;
-}
-__global__ void agg_mean_add_kernel(const float* __restrict__ msg,
-                                    const int64_t* __restrict__ index, int M, int S, int W,
-                                    float* __restrict__ out, float* __restrict__ cnt) {
-  const long long total = (long long)M * W;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(e / W), c = (int)(e - (long long)i * W);
+// ---- segmented mean without float atomics: counting sort of the message ids by segment
+// (integer atomics only), then one warp per segment streams its rows with 128-bit loads.
+//   ws = int32 off[S+1] | int32 cur[S] | int32 perm[M]
+__global__ void agg_mean_count_kernel(const int64_t* __restrict__ index, int M, int S,
+                                      int32_t* __restrict__ cnt) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
     const int64_t s = index[i];
-    if (s < 0 || s >= S) continue;
-    atomicAdd(&out[s * W + c], msg[e]);
-    if (c == 0) atomicAdd(&cnt[s], 1.f);
+    if (s >= 0 && s < S) atomicAdd(&cnt[s], 1);
   }
 }
-__global__ void agg_mean_div_kernel(float* __restrict__ out, const float* __restrict__ cnt, int S,
-                                    int W) {
-  const long long total = (long long)S * W;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const int s = (int)(e / W);
-    out[e] = out[e] / fmaxf(cnt[s], 1.f);
+
+constexpr int kScanTile = 2048;  // 256 threads x 8 segments
+
+// exclusive scan of cnt[0..S) in place (cnt becomes off), off[S] = total, cur[s] = off[s]
+__global__ void __launch_bounds__(256)
+    agg_mean_scan_kernel(int32_t* __restrict__ off, int32_t* __restrict__ cur, int S,
+                         unsigned long long* __restrict__ ws) {
+  __shared__ int s_warp[8];
+  __shared__ long long s_prefix;
+  const int tile = lookback_take_tile(ws);
+  const int ntiles = (S + kScanTile - 1) / kScanTile;
+  if (tile >= ntiles) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int base = tile * kScanTile + tid * 8;
+  int v[8], sum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] = base + j < S ? off[base + j] : 0;
+    sum += v[j];
+  }
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  int wbase = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    if (w < wid) wbase += s_warp[w];
+    tot += s_warp[w];
+  }
+  if (tid == 0) {
+    const long long pre = lookback_prefix(ws, tile, tot);
+    s_prefix = pre;
+    if (tile == ntiles - 1) off[S] = (int32_t)(pre + tot);
+  }
+  __syncthreads();
+  int run = (int)s_prefix + wbase + incl - sum;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (base + j < S) {
+      off[base + j] = run;
+      cur[base + j] = run;
+    }
+    run += v[j];
+  }
+}
+
+__global__ void agg_mean_fill_kernel(const int64_t* __restrict__ index, int M, int S,
+                                     int32_t* __restrict__ cur, int32_t* __restrict__ perm) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+    const int64_t s = index[i];
+    if (s >= 0 && s < S) perm[atomicAdd(&cur[s], 1)] = i;
+  }
+}
+
+// One warp per segment.  Segments of <= 32 messages are put back into message order with a
+// warp bitonic sort first, so the summation order (and the result) is reproducible.
+template <bool kVec>
+__global__ void __launch_bounds__(256)
+    agg_mean_reduce_kernel(const float* __restrict__ msg, const int32_t* __restrict__ off,
+                           const int32_t* __restrict__ perm, int S, int W,
+                           float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < S; s += gridDim.x * wpb) {
+    const int b = off[s], n = off[s + 1] - b;
+    const float inv = 1.f / (float)(n > 1 ? n : 1);
+    int mine = (n <= 32 && lane < n) ? perm[b + lane] : 0x7fffffff;
+    if (n > 1 && n <= 32) {
+#pragma unroll
+      for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          const int other = __shfl_xor_sync(0xffffffffu, mine, j);
+          const bool up = ((lane & k) == 0) == ((lane & j) == 0);
+          mine = up ? min(mine, other) : max(mine, other);
+        }
+    }
+    if (kVec) {
+      const int W4 = W >> 2;
+      const float4* m4 = reinterpret_cast<const float4*>(msg);
+      float4* o4 = reinterpret_cast<float4*>(out) + (long long)s * W4;
+      for (int c0 = 0; c0 < W4; c0 += 128) {  // 4 float4 per lane per pass
+        float4 acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < n; ++j) {
+          const int i = n <= 32 ? __shfl_sync(0xffffffffu, mine, j) : perm[b + j];
+          const float4* row = m4 + (long long)i * W4;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u * 32 + lane;
+            if (c < W4) {
+              const float4 v = row[c];
+              acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * 32 + lane;
+          if (c < W4) o4[c] = make_float4(acc[u].x * inv, acc[u].y * inv, acc[u].z * inv, acc[u].w * inv);
+        }
+      }
+    } else {
+      for (int c0 = 0; c0 < W; c0 += 128) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < n; ++j) {
+          const int i = n <= 32 ? __shfl_sync(0xffffffffu, mine, j) : perm[b + j];
+          const float* row = msg + (long long)i * W;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u * 32 + lane;
+            if (c < W) acc[u] += row[c];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * 32 + lane;
+          if (c < W) out[(long long)s * W + c] = acc[u] * inv;
+        }
+      }
+    }
   }
 }
 
@@ -180,6 +291,15 @@ int32_t tgn_agg_last(const float* msg, const int64_t* index, const void* t, int3
   return TGN_OK;
 }
 
+int64_t tgn_agg_mean_ws_bytes(int32_t num_msgs, int32_t dim_size) {
+  if (num_msgs < 0 || dim_size < 0) return 0;
+  const int ntiles = (dim_size + kScanTile - 1) / kScanTile;
+  // off[S+1] | cur[S] | perm[M] (int32), then the scan's ticket + tile states (8-byte aligned)
+  int64_t words = 2ll * dim_size + 1 + num_msgs;
+  words = (words + 1) & ~1ll;
+  return words * 4 + (int64_t)(ntiles + 1) * 8;
+}
+
 int32_t tgn_agg_mean(const float* msg, const int64_t* index, int32_t num_msgs,
                      int32_t dim_size, int32_t width, float* out, void* ws, void* stream) {
   TGN_REQUIRE(num_msgs >= 0 && dim_size >= 0 && width >= 1, "agg_mean: bad sizes");
@@ -187,18 +307,30 @@ int32_t tgn_agg_mean(const float* msg, const int64_t* index, int32_t num_msgs,
   TGN_REQUIRE(out && ws, "agg_mean: NULL output/workspace");
   TGN_REQUIRE(num_msgs == 0 || (msg && index), "agg_mean: NULL input");
   cudaStream_t s = (cudaStream_t)stream;
-  float* cnt = (float*)ws;
-  const long long tot_out = (long long)dim_size * width;
-  agg_mean_zero_kernel<<<stride_grid(tot_out, 256), 256, 0, s>>>(out, cnt, dim_size, width);
-  TGN_LAUNCH_CHECK();
-  if (num_msgs > 0) {
-    const long long tot_in = (long long)num_msgs * width;
-    agg_mean_add_kernel<<<stride_grid(tot_in, 256), 256, 0, s>>>(msg, index, num_msgs, dim_size,
-                                                                 width, out, cnt);
-    TGN_LAUNCH_CHECK();
-    agg_mean_div_kernel<<<stride_grid(tot_out, 256), 256, 0, s>>>(out, cnt, dim_size, width);
+  const int S = dim_size, M = num_msgs;
+  int32_t* off = (int32_t*)ws;
+  int32_t* cur = off + S + 1;
+  int32_t* perm = cur + S;
+  int64_t words = (2ll * S + 1 + M + 1) & ~1ll;
+  unsigned long long* scan_ws = (unsigned long long*)((int32_t*)ws + words);
+  const int ntiles = (S + kScanTile - 1) / kScanTile;
+  TGN_CUDA(cudaMemsetAsync(off, 0, (size_t)(S + 1) * 4, s));
+  TGN_CUDA(cudaMemsetAsync(scan_ws, 0, (size_t)(ntiles + 1) * 8, s));
+  if (M > 0) {
+    agg_mean_count_kernel<<<stride_grid(M, 256), 256, 0, s>>>(index, M, S, off);
     TGN_LAUNCH_CHECK();
   }
+  agg_mean_scan_kernel<<<ntiles, 256, 0, s>>>(off, cur, S, scan_ws);
+  TGN_LAUNCH_CHECK();
+  if (M > 0) {
+    agg_mean_fill_kernel<<<stride_grid(M, 256), 256, 0, s>>>(index, M, S, cur, perm);
+    TGN_LAUNCH_CHECK();
+  }
+  const bool vec = (width % 4 == 0) && (((uintptr_t)msg | (uintptr_t)out) % 16 == 0);
+  const int grid = stride_grid((long long)S * 32, 256, 16);
+  if (vec) agg_mean_reduce_kernel<true><<<grid, 256, 0, s>>>(msg, off, perm, S, width, out);
+  else agg_mean_reduce_kernel<false><<<grid, 256, 0, s>>>(msg, off, perm, S, width, out);
+  TGN_LAUNCH_CHECK();
   return TGN_OK;
 }
 

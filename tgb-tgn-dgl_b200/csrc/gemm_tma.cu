@@ -5,7 +5,7 @@
 // (modules/decoder.py:24-27) and all of their gradients.  Up to kMaxProb independent
 // problems share one launch (one CTA per 128x128 output tile of any of them).
 //
-// Warp roles (192 threads, one CTA per SM):
+// Warp roles (320 threads, one CTA per SM):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes straight into SWIZZLE_128B
 //               shared-memory tiles, completion on a per-stage mbarrier (tx bytes).  Rows /
 //               columns outside the tensor are zero-filled by the TMA unit, so no operand
@@ -16,10 +16,10 @@
 //   warp 1      MMA issuer: one lane issues tcgen05.mma.kind::tf32 (M=128, N=128, K=8) from
 //               shared-memory descriptors into a 128-column TMEM accumulator, and releases a
 //               stage with tcgen05.commit
-//   warps 2-5   precision 3 ("3xTF32"): split every landed tile in place into hi = tf32(x)
+//   warps 2-9   precision 3 ("3xTF32"): split every landed tile in place into hi = tf32(x)
 //               and lo = x - hi (fp32-exact), so that D += a_hi b_hi + a_hi b_lo + a_lo b_hi
 //               holds fp32-level accuracy (~1e-6); then the epilogue: tcgen05.ld of the
-//               accumulator (warp w owns TMEM lanes 32*(w%4)..), bias, 128-bit stores /
+//               accumulator (warp w owns TMEM lanes 32*(w%4).. and one column half), bias, 128-bit stores /
 //               vector reductions (split-K)
 //   precision 1: operands go to the tensor core as they land (tf32 mantissa), no split pass.
 #include <cuda.h>
@@ -33,7 +33,8 @@ constexpr int GM = 128, GN = 128, GK = 32;    // GK floats = 128 bytes = one swi
 constexpr int kGTileBytes = GM * GK * 4;      // 16 KB per operand tile
 constexpr int kGStageBytes = 4 * kGTileBytes; // A_hi, A_lo, B_hi, B_lo
 constexpr int kGStages = 3;
-constexpr int kGThreads = 192;
+constexpr int kGThreads = 320;   // TMA warp, MMA warp, 8 split/epilogue warps
+constexpr int kGConv = 256;      // threads of the split/epilogue warps
 constexpr int kMaxProb = 4;
 
 struct GemmProb {
@@ -149,6 +150,19 @@ __device__ __forceinline__ void g_split4(float4& v, float4& lo) {
   }
 }
 
+__device__ __forceinline__ float4 g_lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void g_sts4(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
 // zero the elements of float4 number `idx` of a [128 x 32] SWIZZLE_128B tile whose k index
 // (within the k-block) is >= klive.  K-major: 8 float4 per row, k-chunk = position ^ (row & 7);
 // MN-major: four [32 k x 32 mn] boxes of 256 float4, the row inside a box is the k index.
@@ -202,7 +216,7 @@ __global__ void __launch_bounds__(kGThreads, 1)
 #pragma unroll
     for (int i = 0; i < kGStages; ++i) {
       g_mbar_init(&s_full[i], 1);
-      g_mbar_init(&s_conv[i], 128);
+      g_mbar_init(&s_conv[i], kGConv);
       g_mbar_init(&s_empty[i], 1);
     }
     g_mbar_init(&s_acc, 1);
@@ -279,8 +293,8 @@ __global__ void __launch_bounds__(kGThreads, 1)
       __syncwarp();
     }
   } else {
-    // ===== split pass (3xTF32) + epilogue: warps 2..5 =====
-    const int et = tid - 64;  // 0..127
+    // ===== split pass (3xTF32) + epilogue: warps 2..9 =====
+    const int et = tid - 64;  // 0..255
     if (split3 || tail_mask) {
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % kGStages;
@@ -289,27 +303,32 @@ __global__ void __launch_bounds__(kGThreads, 1)
           g_mbar_arrive(&s_conv[s]);
           continue;
         }
-        float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * kGStageBytes);
-        float4* a_lo = a_hi + kGTileBytes / 16;
-        float4* b_hi = a_hi + 2 * (kGTileBytes / 16);
-        float4* b_lo = a_hi + 3 * (kGTileBytes / 16);
+        const uint32_t a_hi = g_smem_u32(smem + (size_t)s * kGStageBytes);
         const int klive = (tail_mask && kb == nk - 1) ? kend - (kbeg + kb * GK) : GK;
+        float4 va[4], vb[4];
 #pragma unroll
-        for (int i = 0; i < kGTileBytes / 16 / 128; ++i) {
-          const int idx = i * 128 + et;
-          float4 va = a_hi[idx], la, vb = b_hi[idx], lb;
+        for (int i = 0; i < 4; ++i) {  // all loads first: 8 x 128-bit shared loads in flight
+          const uint32_t o = (uint32_t)(i * kGConv + et) * 16u;
+          va[i] = g_lds4(a_hi + o);
+          vb[i] = g_lds4(a_hi + 2 * kGTileBytes + o);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = i * kGConv + et;
+          const uint32_t o = (uint32_t)idx * 16u;
+          float4 la, lb;
           if (klive < GK) {
-            g_mask4(va, idx, P.a_mn != 0, klive);
-            g_mask4(vb, idx, P.b_mn != 0, klive);
+            g_mask4(va[i], idx, P.a_mn != 0, klive);
+            g_mask4(vb[i], idx, P.b_mn != 0, klive);
           }
           if (split3) {
-            g_split4(va, la);
-            g_split4(vb, lb);
-            a_lo[idx] = la;
-            b_lo[idx] = lb;
+            g_split4(va[i], la);
+            g_split4(vb[i], lb);
+            g_sts4(a_hi + kGTileBytes + o, la);
+            g_sts4(a_hi + 3 * kGTileBytes + o, lb);
           }
-          a_hi[idx] = va;
-          b_hi[idx] = vb;
+          g_sts4(a_hi + o, va[i]);
+          g_sts4(a_hi + 2 * kGTileBytes + o, vb[i]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic -> async proxy
         g_mbar_arrive(&s_conv[s]);
@@ -319,13 +338,14 @@ __global__ void __launch_bounds__(kGThreads, 1)
       g_mbar_wait(&s_acc, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    const int q = warp & 3;  // TMEM lane group this warp may read
+    const int q = warp & 3;             // TMEM lane group this warp may read
+    const int chalf = warp >= 6 ? 64 : 0;  // warps 2-5: columns 0..63, warps 6-9: 64..127
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < M;
     float* crow = P.c + (long long)row * P.ldc;
     const bool vec_ok = (P.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.c) & 15) == 0);
 #pragma unroll 1
-    for (int cc = 0; cc < GN; cc += 32) {
+    for (int cc = chalf; cc < chalf + 64; cc += 32) {
       const int c0 = n0 + cc;
       if (c0 >= P.n) break;  // warp-uniform
       uint32_t v[32];

@@ -203,8 +203,9 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
                                  const int64_t* __restrict__ last_update, int Dm,
                                  const float* __restrict__ time_w,
                                  const float* __restrict__ time_b, int Dt, float* __restrict__ x,
-                                 int ldx, float* __restrict__ h_out, T* __restrict__ lu_out,
-                                 int32_t* __restrict__ sel_ev, float* __restrict__ sel_dt) {
+                                 int ldx, float* __restrict__ h_out, float* __restrict__ sin_out,
+                                 T* __restrict__ lu_out, int32_t* __restrict__ sel_ev,
+                                 float* __restrict__ sel_dt) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int S = num.get();
@@ -248,8 +249,12 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
         xr[Dm + c] = mo[c];
       }
       for (int c = lane; c < De; c += 32) xr[2 * Dm + c] = rw[c];
-      for (int c = lane; c < Dt; c += 32)
-        xr[2 * Dm + De + c] = cosf(__fmaf_rn(dt, time_w[c], time_b[c]));
+      for (int c = lane; c < Dt; c += 32) {
+        float sv, cv;
+        sincosf(__fmaf_rn(dt, time_w[c], time_b[c]), &sv, &cv);
+        xr[2 * Dm + De + c] = cv;
+        if (sin_out) sin_out[(long long)s * Dt + c] = sv;  // for tgn_time_bwd_sin
+      }
       if (lane == 0) {
         lu_out[s] = te;
         if (sel_ev) sel_ev[s] = e;
@@ -410,12 +415,13 @@ int32_t tgn_msg_build_ld(const tgn_msgstore* st, const int64_t* n_id, int32_t nu
                          const int32_t* num_dev, int32_t agg_mode, const float* memory,
                          const int64_t* last_update, int32_t memory_dim, const float* time_w,
                          const float* time_b, int32_t time_dim, float* x, int32_t ldx, float* h_out,
-                         void* lu_out, int32_t* sel_ev, float* sel_dt, void* stream) {
+                         float* sin_out, void* lu_out, int32_t* sel_ev, float* sel_dt, void* stream) {
   int32_t rc = check_store(st, "msg_build");
   if (rc) return rc;
   TGN_REQUIRE(num >= 0 && memory_dim >= 1 && time_dim >= 0, "msg_build: bad sizes");
   TGN_REQUIRE(agg_mode == TGN_AGG_LAST || agg_mode == TGN_AGG_MEAN, "msg_build: bad agg_mode");
   TGN_REQUIRE(ldx >= 2 * memory_dim + st->raw_dim + time_dim, "msg_build: ldx smaller than the message width");
+  TGN_REQUIRE(!sin_out || agg_mode == TGN_AGG_LAST, "msg_build: sin_out needs the last aggregator");
   if (num == 0) return TGN_OK;
   TGN_REQUIRE(n_id && memory && last_update && x && lu_out && (time_dim == 0 || (time_w && time_b)),
               "msg_build: NULL pointer");
@@ -425,11 +431,11 @@ int32_t tgn_msg_build_ld(const tgn_msgstore* st, const int64_t* n_id, int32_t nu
   if (st->t_is_float)
     msg_build_kernel<float><<<grid, 256, 0, s>>>(*st, n_id, c, agg_mode, memory, last_update,
                                                  memory_dim, time_w, time_b, time_dim, x, ldx, h_out,
-                                                 (float*)lu_out, sel_ev, sel_dt);
+                                                 sin_out, (float*)lu_out, sel_ev, sel_dt);
   else
     msg_build_kernel<int64_t><<<grid, 256, 0, s>>>(*st, n_id, c, agg_mode, memory, last_update,
                                                    memory_dim, time_w, time_b, time_dim, x, ldx,
-                                                   h_out, (int64_t*)lu_out, sel_ev, sel_dt);
+                                                   h_out, sin_out, (int64_t*)lu_out, sel_ev, sel_dt);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }
@@ -442,7 +448,7 @@ int32_t tgn_msg_build(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
   TGN_REQUIRE(st, "msg_build: store is NULL");
   return tgn_msg_build_ld(st, n_id, num, num_dev, agg_mode, memory, last_update, memory_dim, time_w,
                           time_b, time_dim, x, 2 * memory_dim + st->raw_dim + time_dim, nullptr,
-                          lu_out, sel_ev, sel_dt, stream);
+                          nullptr, lu_out, sel_ev, sel_dt, stream);
 }
 
 }  // extern "C"

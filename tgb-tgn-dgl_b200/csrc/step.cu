@@ -128,207 +128,277 @@ struct AttnCoreArgs {
   float* d_ee;      // bwd: [E, HC]
 };
 
+// Channel ownership: lane l holds the float4 chunks f = l and l + 32 (channels 4f..4f+3), so a
+// projection / edge row is fetched with one or two 128-bit loads per lane and the k / v
+// gradients leave as 128-bit vector reductions.  Edges are handled four at a time with all
+// row loads issued before the first use.
+constexpr int kEG = 4;  // edges per group
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+// hm[i][h] = 1 if channel c0+i belongs to head h: per-head sums / picks become plain FMAs
+template <int H>
+struct HeadMask {
+  float m[4][H];
+  __device__ __forceinline__ void init(int c0, int C, bool on) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int h = 0; h < H; ++h) m[i][h] = (on && (c0 + i) / C == h) ? 1.f : 0.f;
+  }
+  // part[h] += sum_i x_i * y_i over the channels of head h
+  __device__ __forceinline__ void dot(float4 x, float4 y, float* part) const {
+    const float pr[4] = {x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int h = 0; h < H; ++h) part[h] = fmaf(pr[i], m[i][h], part[h]);
+  }
+  // per-channel value of a per-head quantity
+  __device__ __forceinline__ float4 pick(const float* v) const {
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int h = 0; h < H; ++h) o[i] = fmaf(v[h], m[i][h], o[i]);
+    return make_float4(o[0], o[1], o[2], o[3]);
+  }
+};
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+template <int H>
 __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_fwd_kernel(AttnCoreArgs a) {
-  const int HC = a.H * a.C;
+  const int HC = a.H * a.C, C = a.C;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nC = a.centres.get();
-  const float inv_sqrt_c = rsqrtf((float)a.C);
-  const int CH = (HC + 31) >> 5;
+  const float inv_sqrt_c = rsqrtf((float)C);
   const float keep = 1.f - a.dropout_p;
+  const int c0[2] = {4 * lane, 4 * (lane + 32)};
+  const bool ok[2] = {c0[0] < HC, c0[1] < HC};
+  HeadMask<H> hm[2];
+  hm[0].init(c0[0], C, ok[0]);
+  hm[1].init(c0[1], C, ok[1]);
   Philox rng(a.seed + (a.seed_dev ? (uint64_t)*a.seed_dev : 0ull));
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int ci = blockIdx.x * kCoreWarps + wid; ci < nC; ci += gridDim.x * kCoreWarps) {
     const int64_t row = a.centre_ids ? a.centre_ids[ci] : ci;
     const float* pr = a.proj + row * 4 * HC;
-    float q[kCMaxCH], acc[kCMaxCH];
-    int head[kCMaxCH];
+    float4 q[2];
 #pragma unroll
-    for (int i = 0; i < kCMaxCH; ++i) {
-      const int c = lane + 32 * i;
-      const bool ok = i < CH && c < HC;
-      q[i] = ok ? pr[c] : 0.f;
-      acc[i] = 0.f;
-      head[i] = ok ? c / a.C : -1;
-    }
-    float mrun[kCMaxHeads], lrun[kCMaxHeads];
+    for (int u = 0; u < 2; ++u) q[u] = ok[u] ? ld4(pr + c0[u]) : z4;
+    const int e0 = a.row_ptr[ci], e1 = a.row_ptr[ci + 1];
+    float mrun[H], lrun[H];
 #pragma unroll
-    for (int h = 0; h < kCMaxHeads; ++h) {
+    for (int h = 0; h < H; ++h) {
       mrun[h] = -INFINITY;
       lrun[h] = 0.f;
     }
-    const int e0 = a.row_ptr[ci], e1 = a.row_ptr[ci + 1];
-    for (int e = e0; e < e1; ++e) {
-      const int64_t j = a.nbr[e];
-      const float* pj = a.proj + j * 4 * HC;
-      const float* pe = a.ee + (long long)e * HC;
-      float vv[kCMaxCH], part[kCMaxHeads];
+    // ---- pass 1: raw scores -> alpha buffer, running max / normaliser
+    for (int eb = e0; eb < e1; eb += kEG) {
+      float4 kk[kEG][2], ee[kEG][2];
 #pragma unroll
-      for (int h = 0; h < kCMaxHeads; ++h) part[h] = 0.f;
+      for (int g = 0; g < kEG; ++g) {
+        const int e = eb + g;
+        const bool live = e < e1;
+        const int64_t j = live ? a.nbr[e] : 0;
 #pragma unroll
-      for (int i = 0; i < kCMaxCH; ++i) {
-        const int c = lane + 32 * i;
-        const bool ok = i < CH && c < HC;
-        const float eev = ok ? pe[c] : 0.f;
-        const float kv = ok ? pj[HC + c] + eev : 0.f;
-        vv[i] = ok ? pj[2 * HC + c] + eev : 0.f;
-#pragma unroll
-        for (int h = 0; h < kCMaxHeads; ++h)
-          if (head[i] == h) part[h] = fmaf(q[i], kv, part[h]);
-      }
-      float pw[kCMaxHeads], sc[kCMaxHeads];
-#pragma unroll
-      for (int h = 0; h < kCMaxHeads; ++h) {
-        pw[h] = 0.f;
-        sc[h] = 1.f;
-        if (h < a.H) {
-          const float s = warp_sum(part[h]) * inv_sqrt_c;
-          const float mnew = fmaxf(mrun[h], s);
-          sc[h] = expf(mrun[h] - mnew);  // 0 on the first edge
-          float p = expf(s - mnew);
-          lrun[h] = lrun[h] * sc[h] + p;
-          mrun[h] = mnew;
-          if (lane == 0) a.alpha[(long long)e * a.H + h] = s;
-          if (a.dropout_p > 0.f) {
-            const uint4 r = rng((uint64_t)e, (uint64_t)h);
-            const float uni = (float)(r.x >> 8) * (1.0f / 16777216.0f);
-            p = uni < keep ? p / keep : 0.f;
-          }
-          pw[h] = p;
+        for (int u = 0; u < 2; ++u) {
+          const bool on = live && ok[u];
+          kk[g][u] = on ? ld4(a.proj + j * 4 * HC + HC + c0[u]) : z4;
+          ee[g][u] = on ? ld4(a.ee + (long long)e * HC + c0[u]) : z4;
         }
       }
 #pragma unroll
-      for (int i = 0; i < kCMaxCH; ++i)
+      for (int g = 0; g < kEG; ++g) {
+        const int e = eb + g;
+        if (e >= e1) break;  // warp-uniform
+        float part[H];
 #pragma unroll
-        for (int h = 0; h < kCMaxHeads; ++h)
-          if (head[i] == h) acc[i] = acc[i] * sc[h] + pw[h] * vv[i];
-    }
-    float* po = a.out + row * HC;
+        for (int h = 0; h < H; ++h) part[h] = 0.f;
 #pragma unroll
-    for (int i = 0; i < kCMaxCH; ++i) {
-      const int c = lane + 32 * i;
-      if (i < CH && c < HC) {
-        float l = 1.f;
+        for (int u = 0; u < 2; ++u) hm[u].dot(q[u], f4_add(kk[g][u], ee[g][u]), part);
 #pragma unroll
-        for (int h = 0; h < kCMaxHeads; ++h)
-          if (head[i] == h) l = lrun[h];
-        po[c] = ((e1 > e0) ? acc[i] / l : 0.f) + pr[3 * HC + c];
+        for (int h = 0; h < H; ++h) {
+          if (h < H) {
+            const float sc = warp_sum(part[h]) * inv_sqrt_c;
+            const float mnew = fmaxf(mrun[h], sc);
+            lrun[h] = lrun[h] * expf(mrun[h] - mnew) + expf(sc - mnew);
+            mrun[h] = mnew;
+            if (lane == 0) a.alpha[(long long)e * H + h] = sc;
+          }
+        }
       }
     }
     __syncwarp();
-    for (int idx = lane; idx < (e1 - e0) * a.H; idx += 32) {  // raw scores -> softmax weights
-      const int h = idx % a.H;
-      float m = 0.f, l = 1.f;
+    // ---- pass 2: softmax weights (kept for the backward), dropout, aggregation
+    float4 acc[2] = {z4, z4};
+    for (int eb = e0; eb < e1; eb += kEG) {
+      float4 vv[kEG][2];
+      float al[kEG][H];
 #pragma unroll
-      for (int hh = 0; hh < kCMaxHeads; ++hh)
-        if (hh == h) {
-          m = mrun[hh];
-          l = lrun[hh];
+      for (int g = 0; g < kEG; ++g) {
+        const int e = eb + g;
+        const bool live = e < e1;
+        const int64_t j = live ? a.nbr[e] : 0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const bool on = live && ok[u];
+          vv[g][u] = on ? f4_add(ld4(a.proj + j * 4 * HC + 2 * HC + c0[u]), ld4(a.ee + (long long)e * HC + c0[u])) : z4;
         }
-      float* pa = a.alpha + (long long)e0 * a.H + idx;
-      *pa = expf(*pa - m) / l;
+#pragma unroll
+        for (int h = 0; h < H; ++h) al[g][h] = (live && h < H) ? a.alpha[(long long)e * H + h] : 0.f;
+      }
+      __syncwarp();  // every lane has read the raw scores before lane 0 overwrites them
+#pragma unroll
+      for (int g = 0; g < kEG; ++g) {
+        const int e = eb + g;
+        if (e >= e1) break;
+        float pw[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          pw[h] = 0.f;
+          if (h < H) {
+            float p = expf(al[g][h] - mrun[h]) / lrun[h];
+            if (lane == 0) a.alpha[(long long)e * H + h] = p;
+            if (a.dropout_p > 0.f) {
+              const uint4 r = rng((uint64_t)e, (uint64_t)h);
+              const float uni = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+              p = uni < keep ? p / keep : 0.f;
+            }
+            pw[h] = p;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float4 w4 = hm[u].pick(pw);
+          acc[u].x = fmaf(w4.x, vv[g][u].x, acc[u].x);
+          acc[u].y = fmaf(w4.y, vv[g][u].y, acc[u].y);
+          acc[u].z = fmaf(w4.z, vv[g][u].z, acc[u].z);
+          acc[u].w = fmaf(w4.w, vv[g][u].w, acc[u].w);
+        }
+      }
     }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (ok[u]) *reinterpret_cast<float4*>(a.out + row * HC + c0[u]) = f4_add(acc[u], ld4(pr + 3 * HC + c0[u]));
   }
 }
 
 // out_i = sum_e a~_e (v_j + ee_e) + skip_i,  a~ = dropout(alpha), alpha = softmax_e(s_e),
-// s_e = <q_i, k_j + ee_e>/sqrt(C).  Two passes over the centre's edges (the second one
-// recomputes the dot products); neighbour rows of d_proj receive atomic adds.
+// s_e = <q_i, k_j + ee_e>/sqrt(C).  Pass A: dot_h = sum_e alpha_e d alpha_e; pass B recomputes
+// d alpha and emits the gradients; neighbour rows of d_proj receive vector reductions.
+template <int H>
 __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_bwd_kernel(AttnCoreArgs a) {
-  const int HC = a.H * a.C;
+  const int HC = a.H * a.C, C = a.C;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nC = a.centres.get();
-  const float inv_sqrt_c = rsqrtf((float)a.C);
-  const int CH = (HC + 31) >> 5;
+  const float inv_sqrt_c = rsqrtf((float)C);
   const float keep = 1.f - a.dropout_p;
+  const int c0[2] = {4 * lane, 4 * (lane + 32)};
+  const bool ok[2] = {c0[0] < HC, c0[1] < HC};
+  HeadMask<H> hm[2];
+  hm[0].init(c0[0], C, ok[0]);
+  hm[1].init(c0[1], C, ok[1]);
   Philox rng(a.seed + (a.seed_dev ? (uint64_t)*a.seed_dev : 0ull));
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int ci = blockIdx.x * kCoreWarps + wid; ci < nC; ci += gridDim.x * kCoreWarps) {
     const int64_t row = a.centre_ids ? a.centre_ids[ci] : ci;
     const float* pr = a.proj + row * 4 * HC;
-    const float* go = a.d_out + row * HC;
-    float q[kCMaxCH], g[kCMaxCH], dq[kCMaxCH];
-    int head[kCMaxCH];
+    float4 q[2], g4[2], dq[2] = {z4, z4};
 #pragma unroll
-    for (int i = 0; i < kCMaxCH; ++i) {
-      const int c = lane + 32 * i;
-      const bool ok = i < CH && c < HC;
-      q[i] = ok ? pr[c] : 0.f;
-      g[i] = ok ? go[c] : 0.f;
-      dq[i] = 0.f;
-      head[i] = ok ? c / a.C : -1;
+    for (int u = 0; u < 2; ++u) {
+      q[u] = ok[u] ? ld4(pr + c0[u]) : z4;
+      g4[u] = ok[u] ? ld4(a.d_out + row * HC + c0[u]) : z4;
     }
     const int e0 = a.row_ptr[ci], e1 = a.row_ptr[ci + 1];
-    float dot[kCMaxHeads];
+    float dot[H];
 #pragma unroll
-    for (int h = 0; h < kCMaxHeads; ++h) dot[h] = 0.f;
+    for (int h = 0; h < H; ++h) dot[h] = 0.f;
     for (int pass = 0; pass < 2; ++pass) {
-      for (int e = e0; e < e1; ++e) {
-        const int64_t j = a.nbr[e];
-        const float* pj = a.proj + j * 4 * HC;
-        const float* pe = a.ee + (long long)e * HC;
-        float kk[kCMaxCH], part[kCMaxHeads];
+      for (int eb = e0; eb < e1; eb += kEG) {
+        float4 kk[kEG][2], vv[kEG][2];
+        float al[kEG][H];
+        int64_t jn[kEG];
 #pragma unroll
-        for (int h = 0; h < kCMaxHeads; ++h) part[h] = 0.f;
+        for (int g = 0; g < kEG; ++g) {
+          const int e = eb + g;
+          const bool live = e < e1;
+          jn[g] = live ? a.nbr[e] : 0;
 #pragma unroll
-        for (int i = 0; i < kCMaxCH; ++i) {
-          const int c = lane + 32 * i;
-          const bool ok = i < CH && c < HC;
-          const float eev = ok ? pe[c] : 0.f;
-          kk[i] = ok ? pj[HC + c] + eev : 0.f;
-          const float vv = ok ? pj[2 * HC + c] + eev : 0.f;
-#pragma unroll
-          for (int h = 0; h < kCMaxHeads; ++h)
-            if (head[i] == h) part[h] = fmaf(g[i], vv, part[h]);
-        }
-        float al[kCMaxHeads], dal[kCMaxHeads], mk[kCMaxHeads];
-#pragma unroll
-        for (int h = 0; h < kCMaxHeads; ++h) {
-          al[h] = 0.f;
-          dal[h] = 0.f;
-          mk[h] = 1.f;
-          if (h < a.H) {
-            al[h] = a.alpha[(long long)e * a.H + h];
-            if (a.dropout_p > 0.f) {
-              const uint4 r = rng((uint64_t)e, (uint64_t)h);
-              const float uni = (float)(r.x >> 8) * (1.0f / 16777216.0f);
-              mk[h] = uni < keep ? 1.f / keep : 0.f;
-            }
-            dal[h] = warp_sum(part[h]) * mk[h];
+          for (int u = 0; u < 2; ++u) {
+            const bool on = live && ok[u];
+            const float4 eev = on ? ld4(a.ee + (long long)e * HC + c0[u]) : z4;
+            vv[g][u] = on ? f4_add(ld4(a.proj + jn[g] * 4 * HC + 2 * HC + c0[u]), eev) : z4;
+            kk[g][u] = (on && pass == 1) ? f4_add(ld4(a.proj + jn[g] * 4 * HC + HC + c0[u]), eev) : z4;
           }
+#pragma unroll
+          for (int h = 0; h < H; ++h) al[g][h] = (live && h < H) ? a.alpha[(long long)e * H + h] : 0.f;
         }
-        if (pass == 0) {
 #pragma unroll
-          for (int h = 0; h < kCMaxHeads; ++h) dot[h] = fmaf(al[h], dal[h], dot[h]);
-          continue;
-        }
-        float* dpj = a.d_proj + j * 4 * HC;
-        float* dpe = a.d_ee + (long long)e * HC;
+        for (int g = 0; g < kEG; ++g) {
+          const int e = eb + g;
+          if (e >= e1) break;
+          float part[H], dal[H], mk[H];
 #pragma unroll
-        for (int i = 0; i < kCMaxCH; ++i) {
-          const int c = lane + 32 * i;
-          if (!(i < CH && c < HC)) continue;
-          float dsh = 0.f, at = 0.f;
+          for (int h = 0; h < H; ++h) part[h] = 0.f;
 #pragma unroll
-          for (int h = 0; h < kCMaxHeads; ++h)
-            if (head[i] == h) {
-              dsh = al[h] * (dal[h] - dot[h]) * inv_sqrt_c;
-              at = al[h] * mk[h];
+          for (int u = 0; u < 2; ++u) hm[u].dot(g4[u], vv[g][u], part);
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            mk[h] = 1.f;
+            dal[h] = 0.f;
+            if (h < H) {
+              if (a.dropout_p > 0.f) {
+                const uint4 r = rng((uint64_t)e, (uint64_t)h);
+                const float uni = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+                mk[h] = uni < keep ? 1.f / keep : 0.f;
+              }
+              dal[h] = warp_sum(part[h]) * mk[h];
             }
-          dq[i] = fmaf(dsh, kk[i], dq[i]);
-          const float dk = dsh * q[i];
-          const float dv = at * g[i];
-          atomicAdd(dpj + HC + c, dk);
-          atomicAdd(dpj + 2 * HC + c, dv);
-          dpe[c] = dk + dv;
+          }
+          if (pass == 0) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) dot[h] = fmaf(al[g][h], dal[h], dot[h]);
+            continue;
+          }
+          float ds[H], at[H];
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            ds[h] = al[g][h] * (dal[h] - dot[h]) * inv_sqrt_c;
+            at[h] = al[g][h] * mk[h];
+          }
+          float* dpj = a.d_proj + jn[g] * 4 * HC;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (!ok[u]) continue;
+            const float4 d4 = hm[u].pick(ds), a4 = hm[u].pick(at);
+            dq[u].x = fmaf(d4.x, kk[g][u].x, dq[u].x);
+            dq[u].y = fmaf(d4.y, kk[g][u].y, dq[u].y);
+            dq[u].z = fmaf(d4.z, kk[g][u].z, dq[u].z);
+            dq[u].w = fmaf(d4.w, kk[g][u].w, dq[u].w);
+            const float4 dk = make_float4(d4.x * q[u].x, d4.y * q[u].y, d4.z * q[u].z, d4.w * q[u].w);
+            const float4 dv = make_float4(a4.x * g4[u].x, a4.y * g4[u].y, a4.z * g4[u].z, a4.w * g4[u].w);
+            red_add_v4(dpj + HC + c0[u], dk);
+            red_add_v4(dpj + 2 * HC + c0[u], dv);
+            *reinterpret_cast<float4*>(a.d_ee + (long long)e * HC + c0[u]) = f4_add(dk, dv);
+          }
         }
       }
     }
     float* dpr = a.d_proj + row * 4 * HC;
 #pragma unroll
-    for (int i = 0; i < kCMaxCH; ++i) {
-      const int c = lane + 32 * i;
-      if (i < CH && c < HC) {
-        dpr[c] = dq[i];          // centres are unique: plain stores for the q and skip blocks
-        dpr[3 * HC + c] = g[i];  // (a centre that is also a neighbour only gets k/v atomics)
-      }
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      // centres are unique: plain stores for the q and skip blocks (a centre that is also a
+      // neighbour only ever receives k / v reductions)
+      *reinterpret_cast<float4*>(dpr + c0[u]) = dq[u];
+      *reinterpret_cast<float4*>(dpr + 3 * HC + c0[u]) = g4[u];
     }
   }
 }
@@ -467,8 +537,10 @@ static int32_t core_args(AttnCoreArgs& a, const float* proj, const int64_t* nbr_
                          const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
                          const float* ee, float dropout_p, uint64_t seed, const int64_t* seed_dev) {
   TGN_REQUIRE(num_centres >= 0 && heads >= 1 && heads <= kCMaxHeads && head_dim >= 1 &&
-                  heads * head_dim <= 32 * kCMaxCH,
-              "attn_core: bad sizes (heads <= %d, heads*head_dim <= %d)", kCMaxHeads, 32 * kCMaxCH);
+                  heads * head_dim <= 32 * kCMaxCH && (heads * head_dim) % 4 == 0,
+              "attn_core: bad sizes (heads <= %d, heads*head_dim <= %d and a multiple of 4)",
+              kCMaxHeads, 32 * kCMaxCH);
+  TGN_REQUIRE(heads == 1 || heads == 2 || heads == 4 || heads == 8, "attn_core: heads must be 1, 2, 4 or 8");
   TGN_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attn_core: dropout_p must be in [0,1)");
   TGN_REQUIRE(proj && nbr_local && row_ptr && ee, "attn_core: NULL pointer");
   a.proj = proj; a.nbr = nbr_local; a.row_ptr = row_ptr; a.centre_ids = centre_ids;
@@ -490,7 +562,14 @@ int32_t tgn_attn_core_fwd(const float* proj, const int64_t* nbr_local, const int
   if (rc) return rc;
   TGN_REQUIRE(out && alpha, "attn_core_fwd: NULL output");
   a.out = out; a.alpha = alpha;
-  attn_core_fwd_kernel<<<ceil_div(num_centres, kCoreWarps), kCoreWarps * 32, 0, (cudaStream_t)stream>>>(a);
+  const int grid = ceil_div(num_centres, kCoreWarps);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (heads) {
+    case 1: attn_core_fwd_kernel<1><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
+    case 2: attn_core_fwd_kernel<2><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
+    case 4: attn_core_fwd_kernel<4><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
+    default: attn_core_fwd_kernel<8><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
+  }
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }
@@ -514,7 +593,13 @@ int32_t tgn_attn_core_bwd(const float* proj, const int64_t* nbr_local, const int
   if (rc) return rc;
   TGN_REQUIRE(alpha && d_out && d_proj && d_ee, "attn_core_bwd: NULL pointer");
   a.alpha = const_cast<float*>(alpha); a.d_out = d_out; a.d_proj = d_proj; a.d_ee = d_ee;
-  attn_core_bwd_kernel<<<ceil_div(num_centres, kCoreWarps), kCoreWarps * 32, 0, s>>>(a);
+  const int grid = ceil_div(num_centres, kCoreWarps);
+  switch (heads) {
+    case 1: attn_core_bwd_kernel<1><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
+    case 2: attn_core_bwd_kernel<2><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
+    case 4: attn_core_bwd_kernel<4><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
+    default: attn_core_bwd_kernel<8><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
+  }
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

@@ -42,15 +42,20 @@ __global__ void unique_mark_kernel(const int64_t* __restrict__ ids, DevCount cnt
   }
 }
 
-// One CTA of 1024 threads.  Thread t owns group (chunk*1024 + t): popcount of
-// its 32 words, block scan, then it emits its ids in ascending order and clears
-// the words it read (second read is an L1 hit).
+// One CTA of 1024 threads, 1024 groups (= 2^20 nodes) per round.
+//   phase 1  thread t counts the set bits of group t (only if its L1 bit is set), block scan
+//            of the counts -> first output position of every group
+//   phase 2  one warp per live group, lane = word of the group: warp prefix over the word
+//            popcounts, every lane emits the ids of its own word in ascending order -- ids come
+//            out globally sorted and the emission runs 32 lanes wide even when one hub group
+//            holds most of the batch
 __global__ void __launch_bounds__(1024, 1)
     unique_rank_kernel(uint32_t* __restrict__ l0, uint32_t* __restrict__ l1, int64_t n_groups,
                        int64_t n_l1_words, int64_t* __restrict__ out_ids, int32_t out_cap,
                        int64_t* __restrict__ assoc, int32_t* __restrict__ out_count,
                        int keep_marks) {
   __shared__ int s_warp[32];
+  __shared__ int s_off[1024];
   __shared__ int s_base, s_total;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) s_base = 0;
@@ -58,13 +63,11 @@ __global__ void __launch_bounds__(1024, 1)
   for (int64_t g0 = 0; g0 < n_groups; g0 += 1024) {
     const int64_t g = g0 + tid;
     int cnt = 0;
-    bool live = false;
-    if (g < n_groups) live = (l1[g >> 5] >> (g & 31)) & 1u;
-    uint4* p = reinterpret_cast<uint4*>(l0 + g * 32);
-    if (live) {
+    if (g < n_groups && ((l1[g >> 5] >> (g & 31)) & 1u)) {
+      const uint4* p = reinterpret_cast<const uint4*>(l0 + g * 32);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        uint4 v = p[q];
+        const uint4 v = p[q];
         cnt += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
       }
     }
@@ -88,26 +91,32 @@ __global__ void __launch_bounds__(1024, 1)
       if (lane == 31) s_total = iv;
     }
     __syncthreads();
-    int pos = s_base + s_warp[wid] + (incl - cnt);
-    if (live) {
-#pragma unroll 1
-      for (int q = 0; q < 8; ++q) {
-        uint4 v = p[q];
-        uint32_t ws4[4] = {v.x, v.y, v.z, v.w};
+    // exclusive offset of the group, or -1 for an empty group
+    s_off[tid] = cnt > 0 ? s_base + s_warp[wid] + (incl - cnt) : -1;
+    __syncthreads();
+    for (int gl = wid; gl < 1024 && g0 + gl < n_groups; gl += 32) {
+      const int gbase = s_off[gl];
+      if (gbase < 0) continue;  // warp-uniform
+      uint32_t* wp = l0 + (g0 + gl) * 32 + lane;
+      uint32_t bits = *wp;
+      const int c = __popc(bits);
+      int pre = c;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          uint32_t bits = ws4[r];
-          while (bits) {
-            int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            int64_t id = (g << 10) + ((q * 4 + r) << 5) + b;
-            if (pos < out_cap) out_ids[pos] = id;
-            if (assoc) assoc[id] = pos;
-            ++pos;
-          }
-        }
-        if (!keep_marks) p[q] = make_uint4(0, 0, 0, 0);
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += y;
       }
+      int pos = gbase + pre - c;
+      const int64_t id0 = ((g0 + gl) << 10) + (lane << 5);
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int64_t id = id0 + b;
+        if (pos < out_cap) out_ids[pos] = id;
+        if (assoc) assoc[id] = pos;
+        ++pos;
+      }
+      if (!keep_marks && c) *wp = 0u;
     }
     __syncthreads();
     if (tid == 0) s_base += s_total;

@@ -128,6 +128,7 @@ class TGNEngine:
         self.bounds = (R, E, Nb)
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.training = True
+        self.probe = None   # bench.py: {"name": [(start_event, stop_event), ...]} filled in eager steps
 
     # ------------------------------------------------------------------ layout helpers
     def _bounds(self, B: int, roots: Optional[int] = None):
@@ -160,6 +161,7 @@ class TGNEngine:
         # memory forward
         w.x, w.h = f(Nb, self.ldx), f(Nb, D)
         w.lu, w.sel_ev, w.sel_dt = i64(Nb), i32(Nb), f(Nb)
+        w.sn_m = f(Nb, max(self.Dt, 1)) if train else None
         w.gi, w.gh, w.z, w.gates = f(Nb, 3 * D), f(Nb, 3 * D), f(Nb, D), f(Nb, 4 * D)
         # attention
         w.proj = f(Nb, 4 * HC)
@@ -269,6 +271,18 @@ class TGNEngine:
             self.in_msg.copy_(msg, non_blocking=True)
 
     # ------------------------------------------------------------------ pieces of the step
+    def _timed(self, name: str, fn):
+        """Runs fn(); with self.probe set (eager steps only) brackets it with CUDA events on the
+        launching stream so bench.py can read the in-step duration of one launch."""
+        if self.probe is None:
+            fn()
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.probe.setdefault(name, []).append((e0, e1))
+
     def _sample(self, w, ids: Tensor, ids_l: Tensor):
         """roots -> neighbour lookup -> union -> relabel; everything bound-sized, counts on device."""
         N, K = self.N, self.K
@@ -287,14 +301,14 @@ class TGNEngine:
         p, D, L, s = self.p, self.D, _L(), _stream()
         check(L.tgn_msg_build_ld(ctypes.byref(self.store.struct()), _p(n_id), S, _p(S_dev), ops.AGG_LAST,
                                  _p(self.memory), _p(self.last_update), D, _p(p["time_enc.lin.weight"]),
-                                 _p(p["time_enc.lin.bias"]), self.Dt, _p(w.x), self.ldx, _p(w.h), _p(w.lu),
+                                 _p(p["time_enc.lin.bias"]), self.Dt, _p(w.x), self.ldx, _p(w.h), _p(w.sn_m), _p(w.lu),
                                  _p(w.sel_ev), _p(w.sel_dt), s))
-        ops.gemm_batch([
+        self._timed("gru_gate_gemm", lambda: ops.gemm_batch([
             ops.gemm_desc(w.x, self.flat, w.gi, m=S, n=3 * D, k=self.Dx, lda=self.ldx, ldb=self.ldx, ldc=3 * D,
                           b_off=self.off["memory_updater.weight_ih"], bias=p["memory_updater.bias_ih"], m_dev=S_dev),
             ops.gemm_desc(w.h, self.flat, w.gh, m=S, n=3 * D, k=D, lda=D, ldb=D, ldc=3 * D,
                           b_off=self.off["memory_updater.weight_hh"], bias=p["memory_updater.bias_hh"], m_dev=S_dev),
-        ], self.prec)
+        ], self.prec))
         check(L.tgn_gru_gates_fwd(_p(w.gi), _p(w.gh), _p(w.h), None, S, _p(S_dev), D, _p(w.z), _p(w.gates), s))
 
     def _attention_fwd(self, w, z: Tensor, lu: Tensor, train: bool):
@@ -405,9 +419,9 @@ class TGNEngine:
         ops.colsum(w.d_gi, w.Nb, 3 * D, 3 * D, p["memory_updater.bias_ih"].grad, True, rows_dev=w.Nb_dev)
         ops.colsum(w.d_gh, w.Nb, 3 * D, 3 * D, p["memory_updater.bias_hh"].grad, True, rows_dev=w.Nb_dev)
         if self.Dt:
-            check(L.tgn_time_encode_bwd(_p(w.sel_dt), _p(w.sel_ev), w.Nb, _p(w.Nb_dev), _p(p["time_enc.lin.weight"]),
-                                        _p(p["time_enc.lin.bias"]), self.Dt, w.d_x.data_ptr() + 4 * (2 * D + self.De),
-                                        self.ldx, gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), s))
+            check(L.tgn_time_bwd_sin(_p(w.sel_dt), _p(w.sel_ev), w.Nb, _p(w.Nb_dev), _p(w.sn_m), self.Dt,
+                                     w.d_x.data_ptr() + 4 * (2 * D + self.De), self.ldx,
+                                     gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), s))
         self.loss.copy_(self.loss_acc[0])
         main.wait_stream(self.side)
         ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.adam_step_dev, self.lr)

@@ -212,7 +212,7 @@ def agg_mean(msg: Tensor, index: Tensor, dim_size: int) -> Tensor:
     index = _need(index, torch.int64, "index")
     M, W = msg.shape
     out = torch.empty((dim_size, W), dtype=torch.float32, device=msg.device)
-    ws = torch.empty(max(dim_size, 1), dtype=torch.float32, device=msg.device)
+    ws = torch.empty(max(_L().tgn_agg_mean_ws_bytes(M, dim_size), 16) // 8, dtype=torch.int64, device=msg.device)
     check(_L().tgn_agg_mean(_p(msg), _p(index), M, dim_size, W, _p(out), _p(ws), _stream()))
     return out
 

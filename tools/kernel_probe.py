@@ -1,0 +1,43 @@
+"""Launches one hot-path kernel on a large input a few times (for ncu captures / quick timing).
+usage: python tools/kernel_probe.py {gemm3|gemm1|tcsr|lookup|agg_last|agg_mean}"""
+import os, sys
+import torch
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "tgb-tgn-dgl_b200"))
+from tgn_b200 import ops
+
+which = sys.argv[1]
+dev = "cuda"
+g = torch.Generator(device="cpu").manual_seed(0)
+N = 352_637
+if which in ("gemm3", "gemm1"):
+    S, Dx, D = 65_536, 472, 100
+    x = torch.randn(S, Dx, device=dev); w = torch.randn(3 * D, Dx, device=dev); o = torch.empty(S, 3 * D, device=dev)
+    fn = lambda: ops.sgemm(x, w, m=S, n=3 * D, k=Dx, lda=Dx, ldb=Dx, out=o, prec=3 if which == "gemm3" else 1)
+elif which == "tcsr":
+    deg = 113
+    indptr = (torch.arange(N + 1, dtype=torch.int64) * deg).to(torch.int32).to(dev)
+    ts = torch.arange(deg, dtype=torch.float32).repeat(N).to(dev)
+    indices = torch.randint(0, N, (N * deg,), generator=g, dtype=torch.int32).to(dev)
+    eid = torch.arange(N * deg, dtype=torch.int32, device=dev)
+    R = 2_000_000
+    roots = torch.randint(0, N, (R,), generator=g, dtype=torch.int32).to(dev)
+    rts = (torch.rand(R, generator=g) * deg + 12).to(dev)
+    fn = lambda: ops.tcsr_sample(indptr, indices, eid, ts, roots, rts, 10)
+elif which == "lookup":
+    K = 10
+    nb = torch.randint(0, N, (N, K), generator=g).to(dev); ei = torch.randint(0, 1 << 30, (N, K), generator=g).to(dev)
+    tt = torch.rand(N, K, generator=g).to(dev)
+    r2 = torch.randint(0, N, (1_000_000,), generator=g).to(dev)
+    fn = lambda: ops.nbr_lookup_raw(r2, nb, ei, tt, None)
+else:
+    M, S, W = 1_000_000, 250_000, 472
+    msg = torch.randn(M, W, device=dev); idx = torch.randint(0, S, (M,), generator=g).to(dev)
+    tm = torch.randint(0, 1000, (M,), generator=g).to(dev)
+    fn = (lambda: ops.agg_last(msg, idx, tm, S)) if which == "agg_last" else (lambda: ops.agg_mean(msg, idx, S))
+for _ in range(3):
+    fn()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+print(which, f"{e0.elapsed_time(e1) * 1e3:.1f} us")

@@ -31,8 +31,11 @@ namespace tgn {
 
 constexpr int GM = 128, GN = 128, GK = 32;    // GK floats = 128 bytes = one swizzle span
 constexpr int kGTileBytes = GM * GK * 4;      // 16 KB per operand tile
-constexpr int kGStageBytes = 4 * kGTileBytes; // A_hi, A_lo, B_hi, B_lo
-constexpr int kGStages = 3;
+// stage layout: A_hi | B_hi | A_lo | B_lo.  3xTF32 uses all four tiles (64 KB, 3 stages);
+// plain tf32 only the first two (32 KB), which doubles the ring depth in the same memory
+constexpr int kGStageBytes3 = 4 * kGTileBytes, kGStages3 = 3;
+constexpr int kGStageBytes1 = 2 * kGTileBytes, kGStages1 = 6;
+constexpr int kGMaxStages = 6;
 constexpr int kGThreads = 320;   // TMA warp, MMA warp, 8 split/epilogue warps
 constexpr int kGConv = 256;      // threads of the split/epilogue warps
 constexpr int kMaxProb = 4;
@@ -144,7 +147,7 @@ __device__ __forceinline__ void g_split4(float4& v, float4& lo) {
   float* l = reinterpret_cast<float*>(&lo);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float h = __uint_as_float((__float_as_uint(x[i]) + 0x1000u) & 0xFFFFE000u);
+    const float h = __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
     l[i] = x[i] - h;
     x[i] = h;
   }
@@ -181,7 +184,7 @@ __device__ __forceinline__ void g_mask4(float4& v, int idx, bool mn_major, int k
 __global__ void __launch_bounds__(kGThreads, 1)
     tgemm_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmParams prm) {
   extern __shared__ __align__(1024) uint8_t g_smem[];
-  __shared__ __align__(8) uint64_t s_full[kGStages], s_conv[kGStages], s_empty[kGStages], s_acc;
+  __shared__ __align__(8) uint64_t s_full[kGMaxStages], s_conv[kGMaxStages], s_empty[kGMaxStages], s_acc;
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -206,6 +209,8 @@ __global__ void __launch_bounds__(kGThreads, 1)
   const int nk = kend > kbeg ? (kend - kbeg + GK - 1) / GK : 0;
   if (nk == 0 && P.mode != 0) return;  // nothing to add
   const bool split3 = prm.prec == 3;
+  const int kGStages = split3 ? kGStages3 : kGStages1;
+  const int kGStageBytes = split3 ? kGStageBytes3 : kGStageBytes1;
   // a live reduction length that ends inside the last 32-wide k-block (and inside the tensor,
   // where the TMA unit does not zero-fill) is cut off by zeroing the tail of that block
   const bool tail_mask = nk > 0 && kend < P.k && ((kend - kbeg) & (GK - 1)) != 0;
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(kGThreads, 1)
                                              ~(uintptr_t)1023);
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < kGStages; ++i) {
+    for (int i = 0; i < kGMaxStages; ++i) {
       g_mbar_init(&s_full[i], 1);
       g_mbar_init(&s_conv[i], kGConv);
       g_mbar_init(&s_empty[i], 1);
@@ -253,11 +258,11 @@ __global__ void __launch_bounds__(kGThreads, 1)
           for (int b = 0; b < 4; ++b) g_tma_2d(st + b * 4096, ma, &s_full[s], m0 + 32 * b, k0);
         }
         if (!P.b_mn) {
-          g_tma_2d(st + 2 * kGTileBytes, mb, &s_full[s], k0, n0);
+          g_tma_2d(st + kGTileBytes, mb, &s_full[s], k0, n0);
         } else {
 #pragma unroll
           for (int b = 0; b < 4; ++b)
-            g_tma_2d(st + 2 * kGTileBytes + b * 4096, mb, &s_full[s], n0 + 32 * b, k0);
+            g_tma_2d(st + kGTileBytes + b * 4096, mb, &s_full[s], n0 + 32 * b, k0);
         }
       }
     }
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(kGThreads, 1)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         const uint32_t a_hi = g_smem_u32(smem + (size_t)s * kGStageBytes);
-        const uint32_t a_lo = a_hi + kGTileBytes, b_hi = a_hi + 2 * kGTileBytes,
+        const uint32_t b_hi = a_hi + kGTileBytes, a_lo = a_hi + 2 * kGTileBytes,
                        b_lo = a_hi + 3 * kGTileBytes;
 #pragma unroll
         for (int kk = 0; kk < GK / 8; ++kk) {  // one MMA consumes K = 8 tf32
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(kGThreads, 1)
         for (int i = 0; i < 4; ++i) {  // all loads first: 8 x 128-bit shared loads in flight
           const uint32_t o = (uint32_t)(i * kGConv + et) * 16u;
           va[i] = g_lds4(a_hi + o);
-          vb[i] = g_lds4(a_hi + 2 * kGTileBytes + o);
+          vb[i] = g_lds4(a_hi + kGTileBytes + o);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -324,11 +329,13 @@ __global__ void __launch_bounds__(kGThreads, 1)
           if (split3) {
             g_split4(va[i], la);
             g_split4(vb[i], lb);
-            g_sts4(a_hi + kGTileBytes + o, la);
+            g_sts4(a_hi + 2 * kGTileBytes + o, la);
             g_sts4(a_hi + 3 * kGTileBytes + o, lb);
           }
-          g_sts4(a_hi + o, va[i]);
-          g_sts4(a_hi + 2 * kGTileBytes + o, vb[i]);
+          if (klive < GK) {  // masked tail: the raw tile itself changes
+            g_sts4(a_hi + o, va[i]);
+            g_sts4(a_hi + kGTileBytes + o, vb[i]);
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic -> async proxy
         g_mbar_arrive(&s_conv[s]);
@@ -498,7 +505,7 @@ int32_t tgn_gemm_batch(const tgn_gemm_desc* d, int32_t count, int32_t precision,
   }
   if (np == 0) return TGN_OK;
   prm.nprob = np;
-  const size_t smem = (size_t)kGStages * kGStageBytes + 1024;
+  const size_t smem = (size_t)kGStages3 * kGStageBytes3 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     TGN_CUDA(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

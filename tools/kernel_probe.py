@@ -10,10 +10,12 @@ which = sys.argv[1]
 dev = "cuda"
 g = torch.Generator(device="cpu").manual_seed(0)
 N = 352_637
-if which in ("gemm3", "gemm1"):
-    S, Dx, D = 65_536, 472, 100
-    x = torch.randn(S, Dx, device=dev); w = torch.randn(3 * D, Dx, device=dev); o = torch.empty(S, 3 * D, device=dev)
-    fn = lambda: ops.sgemm(x, w, m=S, n=3 * D, k=Dx, lda=Dx, ldb=Dx, out=o, prec=3 if which == "gemm3" else 1)
+if which.startswith("gemm"):
+    # gemm3 / gemm1 [ _ld480 : rows padded to a multiple of 128 bytes ] [ _small : 5,023 rows as in the step ]
+    S, Dx, D = (5_023 if "small" in which else 65_536), 472, 100
+    ld = 480 if "ld480" in which else Dx
+    x = torch.randn(S, ld, device=dev); w = torch.randn(3 * D, ld, device=dev); o = torch.empty(S, 3 * D, device=dev)
+    fn = lambda: ops.sgemm(x, w, m=S, n=3 * D, k=Dx, lda=ld, ldb=ld, out=o, prec=3 if which.startswith("gemm3") else 1)
 elif which == "tcsr":
     deg = 113
     indptr = (torch.arange(N + 1, dtype=torch.int64) * deg).to(torch.int32).to(dev)
@@ -38,6 +40,11 @@ else:
 for _ in range(3):
     fn()
 torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    for _ in range(10):
+        fn()
+g.replay(); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-print(which, f"{e0.elapsed_time(e1) * 1e3:.1f} us")
+e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+print(which, f"{e0.elapsed_time(e1) * 1e2:.1f} us per launch (graph of 10)")

@@ -144,6 +144,8 @@ def main():
     ap.add_argument("--prefill", type=int, default=1_000_000)
     ap.add_argument("--cpu-steps", type=int, default=400, help="bounded sample of the CPU baseline leg")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
+    ap.add_argument("--no-eval-dp", action="store_true")
+    ap.add_argument("--eval-batches", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=int, default=3, choices=[1, 3],
                     help="tensor-core GEMM mode: 3 = 3xTF32 (fp32-level accuracy), 1 = single-pass tf32")
@@ -266,6 +268,10 @@ def main():
     roof = dominant_kernel_roofline(eng, dev)
     eng.use_graph = eng_use_graph
 
+    eval_dp = None
+    if not args.no_eval_dp:
+        eval_dp = bench_eval_dp(dev, rank, world, args.eval_batches, args.precision)
+
     if rank == 0:
         peaks = {}
         try:
@@ -285,6 +291,8 @@ def main():
                 "top_kernels_eager_us": {k: [v[0], round(v[1], 1)] for k, v in top},
                 "clocks": clocks.summary(), "final_loss": {"device_arm": loss_dev, "e2e_arm": loss_host},
                 "roofline": roof_with_peak(roof, peaks)}
+        if eval_dp is not None:
+            line["eval_dp"] = eval_dp
         if world == 1 and not args.no_kernel_rooflines:
             line["kernel_rooflines"] = kernel_rooflines(dev, peaks)
         if world == 1 and not args.no_cpu_baseline:
@@ -299,6 +307,55 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_eval_dp(dev, rank, world, n_batches, precision):
+    """TGB evaluation with the negatives scored data-parallel (BASELINE.json configs[4]): synthetic
+    tgbl-flight shape (18,143 nodes, D_e=16), 200 positives x 999 negatives per batch, negative
+    columns sharded round-robin over the ranks, one all-reduce of the 2*B rank counts per batch
+    (tgn_b200/dist_eval.py).  Model replicas are identical on every rank (same seeds), so the MRR
+    printed here is the same number for every --gpus N."""
+    import torch.distributed as dist
+    from tgn_b200 import dist_eval, synth
+    from tgn_b200.engine import TGNEngine
+    cfg = synth.SHAPES["tgbl-flight"]
+    B, K, Q, prefill = cfg["B"], cfg["K"], 999, 300_000
+    warm = 3
+    data = synth.synth_events("tgbl-flight", seed=0, max_events=prefill + (n_batches + warm + 1) * B)
+    N, De = data["num_nodes"], data["raw_dim"]
+    eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.1, use_graph=False,
+                    log_capacity=data["src"].size, seed=7, precision=precision)
+    eng.load_state(*init_state_dicts(De, HIDDEN, N, seed=1))
+    ev = {k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")}
+    eng.set_events(**ev)
+    ring = ring_after(data["src"][:prefill], data["dst"][:prefill], data["t"][:prefill], K, N)
+    eng.prefill(prefill, tuple(torch.from_numpy(a) for a in ring))
+    batches = []
+    for b in range(n_batches + warm):
+        sl = slice(prefill + b * B, prefill + (b + 1) * B)
+        neg = torch.from_numpy(synth.eval_negatives(data["src"][sl], data["dst"][sl], N, Q, seed=1000 + b))
+        batches.append(tuple(x.to(dev) for x in (ev["src"][sl], ev["dst"][sl], neg, ev["t"][sl], ev["msg"][sl])))
+    dist_eval.evaluate_dp(eng, batches[:warm], rank, world)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    mrr = dist_eval.evaluate_dp(eng, batches[warm:], rank, world)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    return {"metric": "TGB eval scored candidate edges/sec (999 negatives/positive, negatives data-parallel)",
+            "value": n_batches * B * (1 + Q) / (ms / 1e3), "unit": "edges/s", "n_gpus": world,
+            "ms_per_batch": ms / n_batches, "batches": n_batches, "mrr": mrr, "scaling": "strong",
+            "workload": f"synthetic tgbl-flight shape: {N} nodes, raw_dim {De}, batch {B}, {Q} negatives, "
+                        f"ring prefilled with {prefill} events",
+            "collective": "one all-reduce(sum) of 2*B int32 rank counts per batch" if world > 1 else "none"}
 
 
 def dominant_kernel_roofline(eng, dev):

@@ -399,6 +399,16 @@ int32_t tgn_dec_loss(const float* hs, const float* hd, const float* w_final, con
                      int32_t batch, int32_t dim, float* loss, float* logits, float* dh, float* dhs,
                      float* d_w_final, float* d_b_final, float* d_b_src, float* d_b_dst,
                      void* stream);
+/* TGB evaluation scoring (epoch_utils.py:99-113, decoder.py:24-27): for positive i the score of
+ * (src_rows[i], dst_rows[i]) and of its num_neg negatives (src_rows[i], neg_rows[i,q]) as sigmoid
+ * outputs; gt_out[i] = #{neg > pos}, ge_out[i] = #{neg >= pos} (the two counts of the TGB MRR
+ * rank = 1 + (gt + ge)/2, additive over shards of the negatives, so data-parallel evaluation
+ * all-reduces 2 integers per positive).  neg_out [num_pos, num_neg] is optional. */
+int32_t tgn_score_negs(const float* hs, const float* hd, const int64_t* src_rows,
+                       const int64_t* dst_rows, const int64_t* neg_rows, int32_t num_pos,
+                       int32_t num_neg, int32_t dim, const float* w_final, const float* b_final,
+                       float* pos_out, float* neg_out, int32_t* gt_out, int32_t* ge_out,
+                       void* stream);
 /* dst[rows[i], :] += src[i, :] (atomic) */
 int32_t tgn_scatter_add_rows(const float* src, const int64_t* rows, int32_t num,
                              const int32_t* num_dev, int32_t dim, float* dst, void* stream);

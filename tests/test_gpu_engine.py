@@ -144,3 +144,32 @@ def test_eval_mrr_matches_oracle():
         assert abs(mrr_g - mrr_r) < 0.005
     torch.testing.assert_close(eng.memory.cpu(), ref["memory"].memory.detach(), rtol=1e-3, atol=1e-4)
     assert torch.equal(eng.last_update.cpu(), ref["memory"].last_update)
+
+
+def test_eval_counts_are_additive_over_negative_shards():
+    """data-parallel evaluation: the TGB rank counts of column shards of the negatives sum to the
+    counts of the full matrix (bit-exact), the state after the batch does not depend on the shard,
+    and the MRR equals the one from the materialised scores."""
+    from tgn_b200 import dist_eval, ops, synth
+    N, De, D, K, B, steps, Q = 300, 8, 16, 5, 40, 6, 37
+    engs = []
+    for _ in range(3):   # identical replicas; the eval path has no atomics, so they stay bit-identical
+        _, eng, ev = _setup(N, De, D, K, B, B * steps, 21, False)
+        eng.flush_to_eval()
+        engs.append(eng)
+    for s in range(steps):
+        sl = slice(s * B, (s + 1) * B)
+        src, dst, t, msg = ev["src"][sl], ev["dst"][sl], ev["t"][sl], ev["msg"][sl]
+        neg = torch.from_numpy(synth.eval_negatives(src.numpy(), dst.numpy(), N, Q, seed=s, dst_lo=N // 2))
+        pos, negs, gt, ge = engs[0].eval_batch(src, dst, neg, t, msg)
+        parts = [engs[1 + r].eval_batch(src, dst, dist_eval.shard_columns(neg, r, 2), t, msg, want_neg_scores=False)
+                 for r in range(2)]
+        assert torch.equal(gt, parts[0][2] + parts[1][2]) and torch.equal(ge, parts[0][3] + parts[1][3])
+        torch.testing.assert_close(pos, parts[0][0], rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(pos, parts[1][0], rtol=1e-6, atol=1e-7)
+        rr = dist_eval.reciprocal_ranks(gt, ge)
+        assert torch.equal(rr, ops.mrr(pos, negs))
+        for e in engs[1:]:
+            assert torch.equal(e.memory, engs[0].memory) and torch.equal(e.last_update, engs[0].last_update)
+            assert torch.equal(e.e_id, engs[0].e_id)
+    assert int(engs[0].e_id.ge(0).sum()) > 0 and float(engs[0].memory.abs().sum()) > 0

@@ -467,6 +467,68 @@ __global__ void __launch_bounds__(kDecWarps * 32)
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// TGB evaluation: score one positive and its Q negatives and count how many negatives beat it.
+// One CTA per positive; hs[src] is staged once in shared memory, every warp then streams
+// negatives (lanes over channels).  Scores are sigmoid outputs compared in fp32, exactly what
+// the reference hands to the TGB evaluator (decoder.py:27, epoch_utils.py:99-113).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    score_negs_kernel(const float* __restrict__ hs, const float* __restrict__ hd,
+                      const int64_t* __restrict__ src_rows, const int64_t* __restrict__ dst_rows,
+                      const int64_t* __restrict__ neg_rows, int B, int Q, int D,
+                      const float* __restrict__ wf, const float* __restrict__ bf,
+                      float* __restrict__ pos_out, float* __restrict__ neg_out,
+                      int32_t* __restrict__ gt_out, int32_t* __restrict__ ge_out) {
+  extern __shared__ float s_a[];  // [D] hs row of the source, [D] w_final
+  __shared__ float s_pos;
+  __shared__ int s_gt, s_ge;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = blockIdx.x; i < B; i += gridDim.x) {
+    __syncthreads();
+    const float* pa = hs + src_rows[i] * D;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      s_a[c] = pa[c];
+      s_a[D + c] = wf[c];
+    }
+    if (threadIdx.x == 0) s_gt = s_ge = 0;
+    __syncthreads();
+    if (wid == 0) {
+      const float* pb = hd + dst_rows[i] * D;
+      float acc = 0.f;
+      for (int c = lane; c < D; c += 32) acc = fmaf(fmaxf(s_a[c] + pb[c], 0.f), s_a[D + c], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const float p = 1.f / (1.f + expf(-(acc + bf[0])));
+        s_pos = p;
+        pos_out[i] = p;
+      }
+    }
+    __syncthreads();
+    const float p = s_pos;
+    int gt = 0, ge = 0;
+    for (int q = wid; q < Q; q += nw) {
+      const float* pb = hd + neg_rows[(long long)i * Q + q] * D;
+      float acc = 0.f;
+      for (int c = lane; c < D; c += 32) acc = fmaf(fmaxf(s_a[c] + pb[c], 0.f), s_a[D + c], acc);
+      acc = warp_sum(acc);
+      const float v = 1.f / (1.f + expf(-(acc + bf[0])));
+      gt += v > p;
+      ge += v >= p;
+      if (neg_out && lane == 0) neg_out[(long long)i * Q + q] = v;
+    }
+    if (lane == 0) {
+      atomicAdd(&s_gt, gt);
+      atomicAdd(&s_ge, ge);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      gt_out[i] = s_gt;
+      ge_out[i] = s_ge;
+    }
+  }
+}
+
 __global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ rows,
                                         DevCount num, int D, float* __restrict__ dst) {
   const int n = num.get();
@@ -617,6 +679,24 @@ int32_t tgn_dec_loss(const float* hs, const float* hd, const float* w_final, con
   dec_loss_kernel<<<grid, kDecWarps * 32, (size_t)3 * dim * sizeof(float), (cudaStream_t)stream>>>(
       hs, hd, w_final, b_final, batch, dim, loss, logits, dh, dhs, d_w_final, d_b_final, d_b_src,
       d_b_dst);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_score_negs(const float* hs, const float* hd, const int64_t* src_rows,
+                       const int64_t* dst_rows, const int64_t* neg_rows, int32_t num_pos,
+                       int32_t num_neg, int32_t dim, const float* w_final, const float* b_final,
+                       float* pos_out, float* neg_out, int32_t* gt_out, int32_t* ge_out,
+                       void* stream) {
+  TGN_REQUIRE(num_pos >= 0 && num_neg >= 0 && dim >= 1, "score_negs: bad sizes");
+  if (num_pos == 0) return TGN_OK;
+  TGN_REQUIRE(hs && hd && src_rows && dst_rows && (neg_rows || num_neg == 0) && w_final &&
+                  b_final && pos_out && gt_out && ge_out,
+              "score_negs: NULL pointer");
+  int grid = num_pos < 8 * kNumSMs ? num_pos : 8 * kNumSMs;
+  score_negs_kernel<<<grid, 256, (size_t)2 * dim * sizeof(float), (cudaStream_t)stream>>>(
+      hs, hd, src_rows, dst_rows, neg_rows, num_pos, num_neg, dim, w_final, b_final, pos_out,
+      neg_out, gt_out, ge_out);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

@@ -458,47 +458,67 @@ class TGNEngine:
         return self.loss
 
     # ------------------------------------------------------------------ evaluation
+    def _eval_work(self, R, E, Nb, B):
+        key = (R, E, Nb)
+        if getattr(self, "_ew_key", None) != key:
+            self._ew, self._ew_key = self._alloc_work(R, E, Nb, B, train=False), key
+            self._ew.hs = torch.empty((Nb, self.D), device=self.dev)
+            self._ew.hd = torch.empty((Nb, self.D), device=self.dev)
+        return self._ew
+
     @torch.no_grad()
-    def eval_scores(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor):
-        """test() body for one batch (epoch_utils.py:28-157): scores of the positives and of
-        the [B,Q] negatives, then eval-mode update_state (store first, then memory) and insert.
-        Returns (pos[B], neg[B,Q]) probabilities."""
+    def eval_batch(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor,
+                   want_neg_scores: bool = True):
+        """test() body for one batch (epoch_utils.py:28-157): embeddings of the batch's nodes,
+        scores of the positives and of the [B,Q] negatives, then eval-mode update_state (store
+        first, then memory) and insert.  Returns (pos[B], neg[B,Q] or None, gt[B], ge[B]) with
+        gt/ge = number of negatives scoring above / not below the positive (TGB MRR counts).
+        `neg` may be any column shard of the full negative matrix (data-parallel evaluation):
+        the state update does not depend on it."""
         dev, N, D, HC, L = self.dev, self.N, self.D, self.HC, _L()
         src, dst, neg = src.to(dev, torch.long), dst.to(dev, torch.long), neg.to(dev, torch.long)
         t_i = t.to(dev, torch.long)
         B, Q = neg.shape
         ids = torch.cat([src, dst, neg.reshape(-1)]).contiguous()
         R, E, Nb = self._bounds(B, roots=min(N, ids.numel()))
-        w = self._alloc_work(R, E, Nb, B, train=False)
+        w = self._eval_work(R, E, Nb, B)
         ids_l = torch.empty_like(ids)
         self._sample(w, ids, ids_l)
         s = _stream()
         check(L.tgn_gather_rows(_p(self.memory), _p(w.n_id), w.Nb, _p(w.Nb_dev), D, _p(w.z), s))
         check(L.tgn_relabel(_p(w.n_id), w.Nb, _p(w.Nb_dev), _p(self.last_update), _p(w.lu), s))
         self._attention_fwd(w, w.z, w.lu, False)
-        hs, hd = torch.empty((Nb, D), device=dev), torch.empty((Nb, D), device=dev)
         p, off = self.p, self.off
         ops.gemm_batch([
-            ops.gemm_desc(w.emb, self.flat, hs, m=Nb, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_src.weight"],
+            ops.gemm_desc(w.emb, self.flat, w.hs, m=Nb, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_src.weight"],
                           bias=p["lin_src.bias"], m_dev=w.Nb_dev),
-            ops.gemm_desc(w.emb, self.flat, hd, m=Nb, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_dst.weight"],
+            ops.gemm_desc(w.emb, self.flat, w.hd, m=Nb, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_dst.weight"],
                           bias=p["lin_dst.bias"], m_dev=w.Nb_dev),
         ], self.prec)
-        sl, dl, nl = ids_l[:B], ids_l[B:2 * B], ids_l[2 * B:]
-        wf, bf = p["lin_final.weight"].reshape(-1), p["lin_final.bias"]
-        pos = ops.link_score(hs, hd, sl, dl, wf, bf, True)
-        negs = ops.link_score(hs, hd, sl.repeat_interleave(Q), nl, wf, bf, True).view(B, Q)
+        pos = torch.empty(B, device=dev)
+        negs = torch.empty((B, Q), device=dev) if want_neg_scores else None
+        gt = torch.empty(B, dtype=torch.int32, device=dev)
+        ge = torch.empty(B, dtype=torch.int32, device=dev)
+        check(L.tgn_score_negs(_p(w.hs), _p(w.hd), _p(ids_l), ids_l.data_ptr() + 8 * B, ids_l.data_ptr() + 16 * B,
+                               B, Q, D, _p(p["lin_final.weight"]), _p(p["lin_final.bias"]), _p(pos), _p(negs),
+                               _p(gt), _p(ge), s))
         # eval ordering of update_state: store first, then memory (memory_module.py:135-138)
         self.store.update(src, dst, t_i, msg.to(dev, torch.float32))
         self.log_base_dev += B
         self.events_done += B
         n_upd = ops.unique_relabel([src, dst], N)
         S = n_upd.numel()
-        wm = self._alloc_work(1, 1, S, 1, train=False)
-        self._memory_fwd(wm, n_upd, S, None)
-        ops.memory_scatter(n_upd, wm.z, wm.lu, self.memory, self.last_update)
+        if getattr(self, "_mw_cap", 0) < S:
+            self._mw, self._mw_cap = self._alloc_work(1, 1, max(S, 2 * B), 1, train=False), max(S, 2 * B)
+        self._memory_fwd(self._mw, n_upd, S, None)
+        ops.memory_scatter(n_upd, self._mw.z, self._mw.lu, self.memory, self.last_update)
         ops.nbr_insert(src, dst, t_i.to(torch.float32), 0, self.neighbors, self.e_id, self.t_ring,
                        cur_e_id_dev=self.cur_e_id_dev)
+        return pos, negs, gt, ge
+
+    def eval_scores(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor):
+        """(pos[B], neg[B,Q]) probabilities of one evaluation batch (see eval_batch)."""
+        pos, negs, _, _ = self.eval_batch(src, dst, neg, t, msg, True)
         return pos, negs
 
     @torch.no_grad()

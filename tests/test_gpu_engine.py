@@ -74,6 +74,25 @@ def test_train_steps_match_oracle(use_graph):
     assert torch.equal(eng.t_ring.cpu(), loader.t)
 
 
+def test_gemm_decoder_path_matches_oracle():
+    """the decoder on batched GEMMs (used when the weights do not fit the fused kernel's shared memory)"""
+    N, De, D, K, B, steps = 400, 12, 32, 5, 50, 4
+    ref, eng, ev = _setup(N, De, D, K, B, B * steps, 13, False)
+    eng.fused_decoder = False
+    loader = orc.TorchNeighborLoader(N, K)
+    opt = torch.optim.Adam(orc.model_parameters(ref), lr=1e-3)
+    strip = lambda sd: {k: v for k, v in sd.items() if k not in ("memory", "last_update", "_assoc")}
+    for s in range(steps):
+        sl = slice(s * B, (s + 1) * B)
+        loss = float(eng.train_step(from_device=True))
+        loss_ref = orc.train_step(ref, loader, opt, ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl],
+                                  ev["msg"][sl], ev["t"], ev["msg"], dropout=False)
+        assert abs(loss - loss_ref) < 1e-4 * max(1.0, abs(loss_ref)), (s, loss, loss_ref)
+        for k, g in _oracle_grads(ref).items():
+            torch.testing.assert_close(eng.p[k].grad.cpu(), g, rtol=2e-3, atol=2e-6, msg=lambda m: f"step {s} {k}: {m}")
+        eng.load_state(strip(ref["memory"].state_dict()), ref["gnn"].state_dict(), ref["link_pred"].state_dict())
+
+
 def test_free_running_training_tracks_oracle():
     """no weight syncing: 12 Adam steps stay close (loose tolerance, see above)."""
     N, De, D, K, B, steps = 400, 12, 32, 5, 50, 12

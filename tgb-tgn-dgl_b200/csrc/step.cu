@@ -468,6 +468,186 @@ __global__ void __launch_bounds__(kDecWarps * 32)
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused decoder forward + backward for the training step (decoder.py:24-27 + BCE-with-logits):
+// per event i the pairs (src_i,dst_i) and (src_i,neg_i)
+//   hs = Ws z_src + bs, hp = Wd z_dst + bd, hn = Wd z_neg + bd, h0 = relu(hs+hp), h1 = relu(hs+hn)
+//   logit = wf.h + bf, loss = mean softplus(-logit0) + mean softplus(logit1)
+// and, with d loss/d logit in hand, every gradient of the decoder: d z rows (atomics into the
+// embedding-gradient rows), dWs, dWd (outer products accumulated in shared memory, flushed once
+// per CTA as vector reductions), the biases and wf/bf.  Both 100x100 weights and both
+// accumulators live in shared memory (row stride D+1: conflict-free for row- and column-wise
+// walks); a CTA walks its events one after the other, thread c owns channel c.
+// Exact fp32 FMA arithmetic -- replaces 2 gathers, 6 GEMMs, the loss kernel and a scatter.
+// ------------------------------------------------------------------------------------------
+constexpr int kDecThreads = 512;  // thread (c, q): channel c = tid & 127, reduction quarter q = tid >> 7
+constexpr int kDecQ = kDecThreads / 128;
+
+__global__ void __launch_bounds__(kDecThreads)
+    dec_fused_kernel(const float* __restrict__ emb, const int64_t* __restrict__ ids_l, int B, int D,
+                     const float* __restrict__ Ws, const float* __restrict__ bs,
+                     const float* __restrict__ Wd, const float* __restrict__ bd,
+                     const float* __restrict__ wf, const float* __restrict__ bf,
+                     float* __restrict__ loss, float* __restrict__ logits, float* __restrict__ d_emb,
+                     float* __restrict__ dWs, float* __restrict__ dbs, float* __restrict__ dWd,
+                     float* __restrict__ dbd, float* __restrict__ dwf, float* __restrict__ dbf) {
+  extern __shared__ float sm[];
+  const int ld = D + 1;
+  float* sWs = sm;
+  float* sWd = sWs + D * ld;
+  float* sAs = sWd + D * ld;   // dWs accumulator
+  float* sAd = sAs + D * ld;   // dWd accumulator
+  float* sz = sAd + D * ld;    // [3][D] z_src, z_dst, z_neg
+  float* sg = sz + 3 * D;      // [3][D] dhs, g0, g1
+  __shared__ float s_p[3][kDecQ][128];  // partial sums of the quarters
+  __shared__ float s_h[2][128];
+  __shared__ float s_part[2][4];
+  __shared__ float s_logit[2];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int c = tid & 127, q = tid >> 7;
+  const int per = (D + kDecQ - 1) / kDecQ;
+  const int k0 = q * per, k1 = min(D, k0 + per);
+  for (int i = tid; i < D * D; i += kDecThreads) {
+    const int r = i / D, k = i - r * D;
+    sWs[r * ld + k] = Ws[i];
+    sWd[r * ld + k] = Wd[i];
+    sAs[r * ld + k] = 0.f;
+    sAd[r * ld + k] = 0.f;
+  }
+  const float invB = 1.f / (float)B;
+  const float bfv = bf[0];
+  float loss_acc = 0.f, dbf_acc = 0.f;
+  for (int ev = blockIdx.x; ev < B; ev += gridDim.x) {
+    const int64_t rs = ids_l[ev], rd = ids_l[B + ev], rn = ids_l[2 * B + ev];
+    __syncthreads();  // weights staged / previous event fully consumed
+    for (int k = tid; k < D; k += kDecThreads) {
+      sz[k] = emb[rs * D + k];
+      sz[D + k] = emb[rd * D + k];
+      sz[2 * D + k] = emb[rn * D + k];
+    }
+    __syncthreads();
+    // ---- forward partials: output channel c, inputs [k0, k1)
+    {
+      float hs = 0.f, hp = 0.f, hn = 0.f;
+      if (c < D) {
+        const float* ws = sWs + c * ld;
+        const float* wd = sWd + c * ld;
+#pragma unroll 5
+        for (int k = k0; k < k1; ++k) {
+          hs = fmaf(ws[k], sz[k], hs);
+          const float w = wd[k];
+          hp = fmaf(w, sz[D + k], hp);
+          hn = fmaf(w, sz[2 * D + k], hn);
+        }
+      }
+      s_p[0][q][c] = hs;
+      s_p[1][q][c] = hp;
+      s_p[2][q][c] = hn;
+    }
+    __syncthreads();
+    if (q == 0) {
+      float p0 = 0.f, p1 = 0.f;
+      if (c < D) {
+        float hs = bs[c], hp = bd[c], hn = hp;
+#pragma unroll
+        for (int j = 0; j < kDecQ; ++j) {
+          hs += s_p[0][j][c];
+          hp += s_p[1][j][c];
+          hn += s_p[2][j][c];
+        }
+        const float h0 = fmaxf(hs + hp, 0.f), h1 = fmaxf(hs + hn, 0.f);
+        s_h[0][c] = h0;
+        s_h[1][c] = h1;
+        p0 = wf[c] * h0;
+        p1 = wf[c] * h1;
+      }
+      p0 = warp_sum(p0);
+      p1 = warp_sum(p1);
+      if (lane == 0) {
+        s_part[0][tid >> 5] = p0;
+        s_part[1][tid >> 5] = p1;
+      }
+    }
+    __syncthreads();
+    if (tid < 2) {
+      const float v = bfv + s_part[tid][0] + s_part[tid][1] + s_part[tid][2] + s_part[tid][3];
+      s_logit[tid] = v;
+      if (logits) logits[tid * B + ev] = v;
+    }
+    __syncthreads();
+    const float l0 = s_logit[0], l1 = s_logit[1];
+    const float dl0 = (1.f / (1.f + expf(-l0)) - 1.f) * invB;
+    const float dl1 = (1.f / (1.f + expf(-l1))) * invB;
+    if (tid == 0) {
+      // softplus(x) = max(x,0) + log1p(exp(-|x|)); x = -logit for the positive pair
+      loss_acc += (fmaxf(-l0, 0.f) + log1pf(expf(-fabsf(l0))) + fmaxf(l1, 0.f) + log1pf(expf(-fabsf(l1)))) * invB;
+      dbf_acc += dl0 + dl1;
+    }
+    // ---- backward through the final layer / relu; weight-gradient rows over [k0, k1)
+    if (c < D) {
+      const float h0 = s_h[0][c], h1 = s_h[1][c];
+      const float w = wf[c];
+      const float g0 = h0 > 0.f ? dl0 * w : 0.f, g1 = h1 > 0.f ? dl1 * w : 0.f;
+      const float gs = g0 + g1;
+      if (q == 0) {
+        atomicAdd(&dwf[c], dl0 * h0 + dl1 * h1);
+        atomicAdd(&dbs[c], gs);
+        atomicAdd(&dbd[c], gs);
+        sg[c] = gs;
+        sg[D + c] = g0;
+        sg[2 * D + c] = g1;
+      }
+      float* as = sAs + c * ld;
+      float* ad = sAd + c * ld;
+#pragma unroll 5
+      for (int k = k0; k < k1; ++k) {
+        as[k] = fmaf(gs, sz[k], as[k]);
+        ad[k] = fmaf(g0, sz[D + k], fmaf(g1, sz[2 * D + k], ad[k]));
+      }
+    }
+    __syncthreads();
+    // ---- input gradients: input channel c, outputs [k0, k1) (column walks of the weights)
+    {
+      float ds = 0.f, dd = 0.f, dn = 0.f;
+      if (c < D) {
+#pragma unroll 5
+        for (int r = k0; r < k1; ++r) {
+          ds = fmaf(sWs[r * ld + c], sg[r], ds);
+          const float w = sWd[r * ld + c];
+          dd = fmaf(w, sg[D + r], dd);
+          dn = fmaf(w, sg[2 * D + r], dn);
+        }
+      }
+      s_p[0][q][c] = ds;
+      s_p[1][q][c] = dd;
+      s_p[2][q][c] = dn;
+    }
+    __syncthreads();
+    if (tid < 3 * 128) {  // three gradient rows, one per 128-thread group
+      const int which = tid >> 7;
+      if (c < D) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < kDecQ; ++j) v += s_p[which][j][c];
+        const int64_t row = which == 0 ? rs : (which == 1 ? rd : rn);
+        atomicAdd(&d_emb[row * D + c], v);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- flush the weight-gradient accumulators
+  for (int i = tid; i < D * D; i += kDecThreads) {
+    const int r = i / D, k = i - r * D;
+    const float a = sAs[r * ld + k], b = sAd[r * ld + k];
+    if (a != 0.f) atomicAdd(&dWs[i], a);
+    if (b != 0.f) atomicAdd(&dWd[i], b);
+  }
+  if (tid == 0) {
+    if (loss_acc != 0.f) atomicAdd(loss, loss_acc);
+    if (dbf_acc != 0.f) atomicAdd(dbf, dbf_acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // TGB evaluation: score one positive and its Q negatives and count how many negatives beat it.
 // One CTA per positive; hs[src] is staged once in shared memory, every warp then streams
 // negatives (lanes over channels).  Scores are sigmoid outputs compared in fp32, exactly what
@@ -679,6 +859,36 @@ int32_t tgn_dec_loss(const float* hs, const float* hd, const float* w_final, con
   dec_loss_kernel<<<grid, kDecWarps * 32, (size_t)3 * dim * sizeof(float), (cudaStream_t)stream>>>(
       hs, hd, w_final, b_final, batch, dim, loss, logits, dh, dhs, d_w_final, d_b_final, d_b_src,
       d_b_dst);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int64_t tgn_dec_fused_smem_bytes(int32_t dim) {
+  return ((int64_t)4 * dim * (dim + 1) + 6 * dim) * (int64_t)sizeof(float);
+}
+
+int32_t tgn_dec_fused(const float* emb, const int64_t* ids_local, int32_t batch, int32_t dim,
+                      const float* w_src, const float* b_src, const float* w_dst, const float* b_dst,
+                      const float* w_final, const float* b_final, float* loss, float* logits,
+                      float* d_emb, float* d_w_src, float* d_b_src, float* d_w_dst, float* d_b_dst,
+                      float* d_w_final, float* d_b_final, void* stream) {
+  TGN_REQUIRE(batch >= 1 && dim >= 1, "dec_fused: bad sizes");
+  const int64_t smem = tgn_dec_fused_smem_bytes(dim);
+  TGN_REQUIRE(smem <= 215 * 1024 && dim <= 128,
+              "dec_fused: dim %d does not fit shared memory (use the GEMM path)", dim);
+  TGN_REQUIRE(emb && ids_local && w_src && b_src && w_dst && b_dst && w_final && b_final && loss &&
+                  d_emb && d_w_src && d_b_src && d_w_dst && d_b_dst && d_w_final && d_b_final,
+              "dec_fused: NULL pointer");
+  static int64_t attr_smem = 0;
+  if (smem > attr_smem) {
+    TGN_CUDA(cudaFuncSetAttribute(dec_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  int grid = ceil_div(batch, 2);  // ~2 events per CTA: balances the event walk against the flush
+  if (grid > kNumSMs) grid = kNumSMs;
+  dec_fused_kernel<<<grid, kDecThreads, (size_t)smem, (cudaStream_t)stream>>>(
+      emb, ids_local, batch, dim, w_src, b_src, w_dst, b_dst, w_final, b_final, loss, logits, d_emb,
+      d_w_src, d_b_src, d_w_dst, d_b_dst, d_w_final, d_b_final);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

@@ -128,6 +128,7 @@ class TGNEngine:
         self.bounds = (R, E, Nb)
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.training = True
+        self.fused_decoder = _L().tgn_dec_fused_smem_bytes(hidden) <= 215 * 1024 and hidden <= 128
         self.probe = None   # bench.py: {"name": [(start_event, stop_event), ...]} filled in eager steps
 
     # ------------------------------------------------------------------ layout helpers
@@ -340,20 +341,12 @@ class TGNEngine:
                                   _p(self.cur_e_id_dev), self.K, self.N, _p(self.neighbors), _p(self.e_id),
                                   _p(self.t_ring), _stream()))
 
-    def _train_body(self):
-        w, p, B, D, HC, L = self.w, self.p, self.B, self.D, self.HC, _L()
+    def _decoder_gemm_path(self, w, s):
+        """Decoder forward/backward on the batched GEMM for hidden sizes whose weights do not fit
+        the fused kernel's shared memory."""
+        p, B, D, HC, L = self.p, self.B, self.D, self.HC, _L()
         off, fg, fl = self.off, self.flat_grad, self.flat
-        main = torch.cuda.current_stream()
-        self.zero_blob.zero_()
-        self._sample(w, self.in_ids3, w.ids_l)
-        self._memory_fwd(w, w.n_id, w.Nb, w.Nb_dev)
-        # ---- state update on a forked stream: it only needs z / last_update of the forward
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):
-            self._update_state(w)
-        self._attention_fwd(w, w.z, w.lu, True)
-        s = _stream()
-        # ---- decoder + loss (decoder.py:24-27; BCEWithLogits, pyg-mem-tgn.py:51)
+        gptr = lambda name: fg.data_ptr() + 4 * off[name]
         check(L.tgn_gather_rows(_p(w.emb), _p(w.ids_l), 3 * B, None, HC, _p(w.zcat), s))
         ops.gemm_batch([
             ops.gemm_desc(w.zcat, fl, w.hcat, m=B, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_src.weight"],
@@ -361,7 +354,6 @@ class TGNEngine:
             ops.gemm_desc(w.zcat, fl, w.hcat, m=2 * B, n=D, k=D, lda=D, ldb=D, ldc=D, a_off=B * D, c_off=B * D,
                           b_off=off["lin_dst.weight"], bias=p["lin_dst.bias"]),
         ], self.prec)
-        gptr = lambda name: fg.data_ptr() + 4 * off[name]
         check(L.tgn_dec_loss(_p(w.hcat), w.hcat.data_ptr() + 4 * B * D, _p(p["lin_final.weight"]),
                              _p(p["lin_final.bias"]), B, D, _p(self.loss_acc), _p(w.logits),
                              w.dhcat.data_ptr() + 4 * B * D, _p(w.dhcat), gptr("lin_final.weight"),
@@ -379,6 +371,30 @@ class TGNEngine:
                           a_off=B * D, c_off=B * D, b_off=off["lin_dst.weight"]),
         ], self.prec)
         check(L.tgn_scatter_add_rows(_p(w.dzcat), _p(w.ids_l), 3 * B, None, HC, _p(self.d_emb), s))
+
+    def _train_body(self):
+        w, p, B, D, HC, L = self.w, self.p, self.B, self.D, self.HC, _L()
+        off, fg, fl = self.off, self.flat_grad, self.flat
+        main = torch.cuda.current_stream()
+        self.zero_blob.zero_()
+        self._sample(w, self.in_ids3, w.ids_l)
+        self._memory_fwd(w, w.n_id, w.Nb, w.Nb_dev)
+        # ---- state update on a forked stream: it only needs z / last_update of the forward
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self._update_state(w)
+        self._attention_fwd(w, w.z, w.lu, True)
+        s = _stream()
+        # ---- decoder + loss + decoder backward (decoder.py:24-27; BCEWithLogits, pyg-mem-tgn.py:51)
+        gptr = lambda name: fg.data_ptr() + 4 * off[name]
+        if self.fused_decoder:
+            check(L.tgn_dec_fused(_p(w.emb), _p(w.ids_l), B, D, _p(p["lin_src.weight"]), _p(p["lin_src.bias"]),
+                                  _p(p["lin_dst.weight"]), _p(p["lin_dst.bias"]), _p(p["lin_final.weight"]),
+                                  _p(p["lin_final.bias"]), _p(self.loss_acc), _p(w.logits), _p(self.d_emb),
+                                  gptr("lin_src.weight"), gptr("lin_src.bias"), gptr("lin_dst.weight"),
+                                  gptr("lin_dst.bias"), gptr("lin_final.weight"), gptr("lin_final.bias"), s))
+        else:
+            self._decoder_gemm_path(w, s)
         # ---- attention backward
         check(L.tgn_attn_core_bwd(_p(w.proj), _p(w.nbr_l), _p(w.root_off), _p(w.ctr_l), w.R, _p(w.R_dev),
                                   self.H, self.C, _p(w.ee), _p(w.alpha), _p(self.d_emb), self.dropout, self.seed,

@@ -68,6 +68,10 @@ int32_t tgn_unique_mark(const int64_t* ids, int32_t count, const int32_t* count_
  * again), otherwise it is cleared. */
 int32_t tgn_unique_rank(void* bitmap, int64_t num_nodes, int64_t* out_ids, int32_t out_cap,
                         int64_t* assoc, int32_t* out_count, int32_t keep_marks, void* stream);
+/* tgn_unique_mark(ids) + tgn_unique_rank in one single-CTA launch (small id lists) */
+int32_t tgn_unique_mark_rank(const int64_t* ids, int32_t count, void* bitmap, int64_t num_nodes,
+                             int64_t* out_ids, int32_t out_cap, int64_t* assoc, int32_t* out_count,
+                             int32_t keep_marks, void* stream);
 /* out[i] = assoc[ids[i]]   (neighbor_loader.py:48) */
 int32_t tgn_relabel(const int64_t* ids, int32_t count, const int32_t* count_dev,
                     const int64_t* assoc, int64_t* out, void* stream);
@@ -268,6 +272,11 @@ int32_t tgn_gru_gates_fwd(const float* gi, const float* gh, const float* h,
 int32_t tgn_gru_gates_bwd(const float* d_out, const float* gates, const float* h,
                           const int64_t* h_rows, int32_t num, const int32_t* num_dev,
                           int32_t dim, float* d_gi, float* d_gh, float* d_h, void* stream);
+/* tgn_gru_gates_bwd (h given by row) that also accumulates (+=) the bias gradients
+ * d_b_ih[3D] = column sums of d_gi, d_b_hh[3D] = column sums of d_gh. */
+int32_t tgn_gru_gates_bwd_bias(const float* d_out, const float* gates, const float* h, int32_t num,
+                               const int32_t* num_dev, int32_t dim, float* d_gi, float* d_gh,
+                               float* d_b_ih, float* d_b_hh, void* stream);
 int32_t tgn_rnn_gates_fwd(const float* gi, const float* gh, int32_t num, int32_t dim, float* out,
                           void* stream);
 
@@ -296,6 +305,12 @@ int32_t tgn_time_encode_bwd(const float* t, const int32_t* row_mask, int32_t num
 int32_t tgn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                       int64_t count, float lr, float beta1, float beta2, float eps,
                       float* step_dev, void* stream);
+
+/* tgn_adam_step followed by the end-of-step scalars in one extra launch: *step_counter += 1
+ * (nullable; keys the dropout stream) and *loss_out = *loss_acc (nullable). */
+int32_t tgn_adam_finish(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                        int64_t count, float lr, float beta1, float beta2, float eps, float* step_dev,
+                        int64_t* step_counter, const float* loss_acc, float* loss_out, void* stream);
 
 /* TimeEncoder forward: out[i,c] = cos(w[c]*t[i] + b[c]) (contract from
  * memory_module.py:203, emb_module.py:27; DGL twin model_utils.py:223-237) */

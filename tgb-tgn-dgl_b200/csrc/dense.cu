@@ -358,6 +358,57 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 __global__ void adam_bump_kernel(float* step_dev) { *step_dev += 1.f; }
+// end-of-step scalars in one launch: Adam step count, the step counter that keys dropout, loss
+__global__ void step_finish_kernel(float* adam_step, int64_t* step_ctr, const float* loss_acc,
+                                   float* loss_out) {
+  *adam_step += 1.f;
+  if (step_ctr) *step_ctr += 1;
+  if (loss_acc && loss_out) *loss_out = *loss_acc;
+}
+
+// gru_gates_bwd with the two bias gradients (column sums of d_gi / d_gh) folded in: one CTA
+// per row chunk, thread j owns column j of every gate block, partial sums leave as atomics.
+__global__ void __launch_bounds__(128)
+    gru_gates_bwd_bias_kernel(const float* __restrict__ d_out, const float* __restrict__ gates,
+                              const float* __restrict__ h, DevCount num, int D,
+                              float* __restrict__ d_gi, float* __restrict__ d_gh,
+                              float* __restrict__ d_b_ih, float* __restrict__ d_b_hh) {
+  const int S = num.get();
+  const int rows_per = (S + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per, r1 = min(S, r0 + rows_per);
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    float sr = 0.f, sz = 0.f, sn = 0.f, shn = 0.f;
+    for (int s = r0; s < r1; ++s) {
+      const float* g = gates + (long long)s * 4 * D;
+      const float r = g[j], z = g[D + j], n = g[2 * D + j], ghn = g[3 * D + j];
+      const float hv = h[(long long)s * D + j];
+      const float go = d_out[(long long)s * D + j];
+      const float dn_pre = go * (1.f - z) * (1.f - n * n);
+      const float dr_pre = dn_pre * ghn * r * (1.f - r);
+      const float dz_pre = go * (hv - n) * z * (1.f - z);
+      float* dgi = d_gi + (long long)s * 3 * D;
+      float* dgh = d_gh + (long long)s * 3 * D;
+      dgi[j] = dr_pre;
+      dgi[D + j] = dz_pre;
+      dgi[2 * D + j] = dn_pre;
+      dgh[j] = dr_pre;
+      dgh[D + j] = dz_pre;
+      dgh[2 * D + j] = dn_pre * r;
+      sr += dr_pre;
+      sz += dz_pre;
+      sn += dn_pre;
+      shn += dn_pre * r;
+    }
+    if (r1 > r0) {
+      atomicAdd(&d_b_ih[j], sr);
+      atomicAdd(&d_b_ih[D + j], sz);
+      atomicAdd(&d_b_ih[2 * D + j], sn);
+      atomicAdd(&d_b_hh[j], sr);
+      atomicAdd(&d_b_hh[D + j], sz);
+      atomicAdd(&d_b_hh[2 * D + j], shn);
+    }
+  }
+}
 
 }  // namespace tgn
 
@@ -410,6 +461,20 @@ int32_t tgn_gru_gates_bwd(const float* d_out, const float* gates, const float* h
   DevCount c{num_dev, num};
   gru_gates_bwd_kernel<<<stride_grid((long long)num * dim, 256), 256, 0, (cudaStream_t)stream>>>(
       d_out, gates, h, h_rows, c, num, dim, d_gi, d_gh, d_h);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_gru_gates_bwd_bias(const float* d_out, const float* gates, const float* h, int32_t num,
+                               const int32_t* num_dev, int32_t dim, float* d_gi, float* d_gh,
+                               float* d_b_ih, float* d_b_hh, void* stream) {
+  TGN_REQUIRE(num >= 0 && dim >= 1, "gru_gates_bwd_bias: bad sizes");
+  if (num == 0) return TGN_OK;
+  TGN_REQUIRE(d_out && gates && h && d_gi && d_gh && d_b_ih && d_b_hh, "gru_gates_bwd_bias: NULL pointer");
+  int grid = ceil_div(num, 16);
+  if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+  gru_gates_bwd_bias_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+      d_out, gates, h, DevCount{num_dev, num}, dim, d_gi, d_gh, d_b_ih, d_b_hh);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }
@@ -539,6 +604,22 @@ int32_t tgn_adam_step(float* params, const float* grads, float* exp_avg, float* 
     TGN_LAUNCH_CHECK();
   }
   adam_bump_kernel<<<1, 1, 0, s>>>(step_dev);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_adam_finish(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                        int64_t count, float lr, float beta1, float beta2, float eps, float* step_dev,
+                        int64_t* step_counter, const float* loss_acc, float* loss_out, void* stream) {
+  TGN_REQUIRE(count >= 0 && step_dev, "adam_finish: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (count > 0) {
+    TGN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "adam_finish: NULL pointer");
+    adam_kernel<<<stride_grid(count, 256), 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, count,
+                                                        lr, beta1, beta2, eps, step_dev);
+    TGN_LAUNCH_CHECK();
+  }
+  step_finish_kernel<<<1, 1, 0, s>>>(step_dev, step_counter, loss_acc, loss_out);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

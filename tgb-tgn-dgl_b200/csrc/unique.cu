@@ -53,12 +53,25 @@ __global__ void __launch_bounds__(1024, 1)
     unique_rank_kernel(uint32_t* __restrict__ l0, uint32_t* __restrict__ l1, int64_t n_groups,
                        int64_t n_l1_words, int64_t* __restrict__ out_ids, int32_t out_cap,
                        int64_t* __restrict__ assoc, int32_t* __restrict__ out_count,
-                       int keep_marks) {
+                       int keep_marks, const int64_t* __restrict__ mark_ids, int mark_count,
+                       int64_t n_nodes) {
   __shared__ int s_warp[32];
   __shared__ int s_off[1024];
   __shared__ int s_base, s_total;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) s_base = 0;
+  // optional marking pass (the unique_mark launch folded in: this kernel is a single CTA, so a
+  // block barrier orders the bitmap writes before the ranking reads)
+  for (int i = tid; i < mark_count; i += 1024) {
+    const int64_t id = mark_ids[i];
+    if (id < 0 || id >= n_nodes) continue;
+    const uint32_t old = atomicOr(&l0[id >> 5], 1u << (id & 31));
+    if (old == 0) {
+      const int64_t g = id >> 10;
+      atomicOr(&l1[g >> 5], 1u << (g & 31));
+    }
+  }
+  __threadfence_block();
   __syncthreads();
   for (int64_t g0 = 0; g0 < n_groups; g0 += 1024) {
     const int64_t g = g0 + tid;
@@ -171,7 +184,22 @@ int32_t tgn_unique_rank(void* bitmap, int64_t num_nodes, int64_t* out_ids, int32
   uint32_t* l1 = l0 + l0_words(num_nodes);
   unique_rank_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
       l0, l1, l0_groups(num_nodes), l1_words(num_nodes), out_ids, out_cap, assoc, out_count,
-      keep_marks);
+      keep_marks, nullptr, 0, num_nodes);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_unique_mark_rank(const int64_t* ids, int32_t count, void* bitmap, int64_t num_nodes,
+                             int64_t* out_ids, int32_t out_cap, int64_t* assoc, int32_t* out_count,
+                             int32_t keep_marks, void* stream) {
+  TGN_REQUIRE(bitmap && out_ids && out_count && num_nodes > 0 && out_cap >= 0 && count >= 0 &&
+                  (ids || count == 0),
+              "unique_mark_rank: bad arguments");
+  uint32_t* l0 = (uint32_t*)bitmap;
+  uint32_t* l1 = l0 + l0_words(num_nodes);
+  unique_rank_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+      l0, l1, l0_groups(num_nodes), l1_words(num_nodes), out_ids, out_cap, assoc, out_count,
+      keep_marks, ids, count, num_nodes);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

@@ -288,8 +288,12 @@ class TGNEngine:
         """roots -> neighbour lookup -> union -> relabel; everything bound-sized, counts on device."""
         N, K = self.N, self.K
         L, s = _L(), _stream()
-        check(L.tgn_unique_mark(_p(ids), ids.numel(), None, N, _p(self.bitmap), s))
-        check(L.tgn_unique_rank(_p(self.bitmap), N, _p(w.roots), w.R, None, _p(w.R_dev), 1, s))
+        if ids.numel() <= 8192:   # small id list: marking folded into the single-CTA ranking launch
+            check(L.tgn_unique_mark_rank(_p(ids), ids.numel(), _p(self.bitmap), N, _p(w.roots), w.R, None,
+                                         _p(w.R_dev), 1, s))
+        else:
+            check(L.tgn_unique_mark(_p(ids), ids.numel(), None, N, _p(self.bitmap), s))
+            check(L.tgn_unique_rank(_p(self.bitmap), N, _p(w.roots), w.R, None, _p(w.R_dev), 1, s))
         check(L.tgn_nbr_lookup(_p(w.roots), w.R, _p(w.R_dev), K, N, _p(self.neighbors), _p(self.e_id),
                                _p(self.t_ring), _p(w.nbr_g), _p(w.ctr_g), _p(w.eid), _p(w.t_e),
                                _p(w.root_off), _p(w.E_dev), _p(self.bitmap), _p(w.lookup_ws), s))
@@ -419,8 +423,8 @@ class TGNEngine:
             check(L.tgn_time_bwd_sin(_p(w.rel), None, w.E, _p(w.E_dev), _p(w.sn_e), self.Dt, _p(w.d_eat), self.Dt,
                                      gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), s))
         # ---- GRU backward (torch.nn.GRUCell, memory_module.py:72,172)
-        check(L.tgn_gru_gates_bwd(_p(w.d_z), _p(w.gates), _p(w.h), None, w.Nb, _p(w.Nb_dev), D, _p(w.d_gi),
-                                  _p(w.d_gh), None, s))
+        check(L.tgn_gru_gates_bwd_bias(_p(w.d_z), _p(w.gates), _p(w.h), w.Nb, _p(w.Nb_dev), D, _p(w.d_gi),
+                                       _p(w.d_gh), gptr("memory_updater.bias_ih"), gptr("memory_updater.bias_hh"), s))
         ops.gemm_batch([
             ops.gemm_desc(w.d_gi, w.x, fg, m=3 * D, n=self.Dx, k=w.Nb, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
                           trans_a=True, trans_b=True, mode=2, split_k=split_n, k_dev=w.Nb_dev,
@@ -432,16 +436,14 @@ class TGNEngine:
             ops.gemm_desc(w.d_gi, fl, w.d_x, m=w.Nb, n=self.Dx, k=3 * D, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
                           trans_b=True, b_off=off["memory_updater.weight_ih"], m_dev=w.Nb_dev),
         ], self.prec)
-        ops.colsum(w.d_gi, w.Nb, 3 * D, 3 * D, p["memory_updater.bias_ih"].grad, True, rows_dev=w.Nb_dev)
-        ops.colsum(w.d_gh, w.Nb, 3 * D, 3 * D, p["memory_updater.bias_hh"].grad, True, rows_dev=w.Nb_dev)
         if self.Dt:
             check(L.tgn_time_bwd_sin(_p(w.sel_dt), _p(w.sel_ev), w.Nb, _p(w.Nb_dev), _p(w.sn_m), self.Dt,
                                      w.d_x.data_ptr() + 4 * (2 * D + self.De), self.ldx,
                                      gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), s))
-        self.loss.copy_(self.loss_acc[0])
         main.wait_stream(self.side)
-        ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.adam_step_dev, self.lr)
-        self.step_dev.add_(1)
+        check(L.tgn_adam_finish(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
+                                self.n_param, self.lr, 0.9, 0.999, 1e-8, _p(self.adam_step_dev), _p(self.step_dev),
+                                _p(self.loss_acc), _p(self.loss), _stream()))
 
     def _run(self, key: tuple, body):
         if not self.use_graph:

@@ -52,6 +52,11 @@ extern "C" {
 
 int32_t tgn_abi_version(void);
 const char* tgn_last_error(void);
+/* Programmatic dependent launch: kernels are launched with the programmatic-stream-serialization
+ * attribute so that the launch latency and prologue of each kernel overlap the tail of its
+ * predecessor on the stream (every kernel begins with griddepcontrol.wait, so results do not
+ * change).  Enabled by default; returns the previous setting. */
+int32_t tgn_set_pdl(int32_t enabled);
 
 /* ------------------------------------------------------------------------- *
  * Sorted-unique + relabel by bitmap ranking.

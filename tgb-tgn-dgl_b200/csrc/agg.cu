@@ -35,6 +35,8 @@ __device__ __forceinline__ unsigned long long load_enc(const void* t, int i) {
 
 __global__ void agg_last_init_kernel(unsigned long long* tmax, unsigned long long* arg, int S,
                                      unsigned long long sentinel) {
+  pdl_wait();
+  pdl_launch();
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
     tmax[s] = 0ull;
     arg[s] = sentinel;
@@ -44,6 +46,8 @@ __global__ void agg_last_init_kernel(unsigned long long* tmax, unsigned long lon
 template <bool kFloat>
 __global__ void agg_last_max_kernel(const int64_t* __restrict__ index, const void* __restrict__ t,
                                     int M, int S, unsigned long long* __restrict__ tmax) {
+  pdl_wait();
+  pdl_launch();
   const int lane = threadIdx.x & 31;
   const int total = (M + 31) & ~31;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -70,6 +74,8 @@ template <bool kFloat>
 __global__ void agg_last_arg_kernel(const int64_t* __restrict__ index, const void* __restrict__ t,
                                     int M, int S, const unsigned long long* __restrict__ tmax,
                                     unsigned long long* __restrict__ arg) {
+  pdl_wait();
+  pdl_launch();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
     int64_t idx = index[i];
     if (idx < 0 || idx >= S) continue;
@@ -81,6 +87,8 @@ __global__ void agg_last_gather_kernel(const float* __restrict__ msg,
                                        const unsigned long long* __restrict__ arg, int M, int S,
                                        int W, float* __restrict__ out,
                                        int64_t* __restrict__ argmax) {
+  pdl_wait();
+  pdl_launch();
   const long long total = (long long)S * W;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -95,6 +103,8 @@ __global__ void agg_last_gather4_kernel(const float4* __restrict__ msg,
                                         const unsigned long long* __restrict__ arg, int M, int S,
                                         int W4, float4* __restrict__ out,
                                         int64_t* __restrict__ argmax) {
+  pdl_wait();
+  pdl_launch();
   const long long total = (long long)S * W4;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -112,6 +122,8 @@ __global__ void agg_last_gather4_kernel(const float4* __restrict__ msg,
 //   ws = int32 off[S+1] | int32 cur[S] | int32 perm[M]
 __global__ void agg_mean_count_kernel(const int64_t* __restrict__ index, int M, int S,
                                       int32_t* __restrict__ cnt) {
+  pdl_wait();
+  pdl_launch();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
     const int64_t s = index[i];
     if (s >= 0 && s < S) atomicAdd(&cnt[s], 1);
@@ -124,6 +136,8 @@ constexpr int kScanTile = 2048;  // 256 threads x 8 segments
 __global__ void __launch_bounds__(256)
     agg_mean_scan_kernel(int32_t* __restrict__ off, int32_t* __restrict__ cur, int S,
                          unsigned long long* __restrict__ ws) {
+  pdl_wait();
+  pdl_launch();
   __shared__ int s_warp[8];
   __shared__ long long s_prefix;
   const int tile = lookback_take_tile(ws);
@@ -170,6 +184,8 @@ __global__ void __launch_bounds__(256)
 
 __global__ void agg_mean_fill_kernel(const int64_t* __restrict__ index, int M, int S,
                                      int32_t* __restrict__ cur, int32_t* __restrict__ perm) {
+  pdl_wait();
+  pdl_launch();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
     const int64_t s = index[i];
     if (s >= 0 && s < S) perm[atomicAdd(&cur[s], 1)] = i;
@@ -183,6 +199,8 @@ __global__ void __launch_bounds__(256)
     agg_mean_reduce_kernel(const float* __restrict__ msg, const int32_t* __restrict__ off,
                            const int32_t* __restrict__ perm, int S, int W,
                            float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < S; s += gridDim.x * wpb) {
@@ -263,28 +281,28 @@ int32_t tgn_agg_last(const float* msg, const int64_t* index, const void* t, int3
   cudaStream_t s = (cudaStream_t)stream;
   unsigned long long* tmax = (unsigned long long*)ws;
   unsigned long long* arg = tmax + dim_size;
-  agg_last_init_kernel<<<stride_grid(dim_size, 256), 256, 0, s>>>(tmax, arg, dim_size,
+  launch_k(agg_last_init_kernel, dim3(stride_grid(dim_size, 256)), dim3(256), 0, s, tmax, arg, dim_size,
                                                                   (unsigned long long)num_msgs);
   TGN_LAUNCH_CHECK();
   if (num_msgs > 0) {
     const int g = stride_grid(num_msgs, 256);
     if (t_is_float) {
-      agg_last_max_kernel<true><<<g, 256, 0, s>>>(index, t, num_msgs, dim_size, tmax);
-      agg_last_arg_kernel<true><<<g, 256, 0, s>>>(index, t, num_msgs, dim_size, tmax, arg);
+      launch_k(agg_last_max_kernel<true>, dim3(g), dim3(256), 0, s, index, t, num_msgs, dim_size, tmax);
+      launch_k(agg_last_arg_kernel<true>, dim3(g), dim3(256), 0, s, index, t, num_msgs, dim_size, tmax, arg);
     } else {
-      agg_last_max_kernel<false><<<g, 256, 0, s>>>(index, t, num_msgs, dim_size, tmax);
-      agg_last_arg_kernel<false><<<g, 256, 0, s>>>(index, t, num_msgs, dim_size, tmax, arg);
+      launch_k(agg_last_max_kernel<false>, dim3(g), dim3(256), 0, s, index, t, num_msgs, dim_size, tmax);
+      launch_k(agg_last_arg_kernel<false>, dim3(g), dim3(256), 0, s, index, t, num_msgs, dim_size, tmax, arg);
     }
     TGN_LAUNCH_CHECK();
   }
   const bool vec = (width % 4 == 0) && (((uintptr_t)msg | (uintptr_t)out) % 16 == 0);
   if (vec) {
     const long long total = (long long)dim_size * (width / 4);
-    agg_last_gather4_kernel<<<stride_grid(total, 256), 256, 0, s>>>(
+    launch_k(agg_last_gather4_kernel, dim3(stride_grid(total, 256)), dim3(256), 0, s, 
         (const float4*)msg, arg, num_msgs, dim_size, width / 4, (float4*)out, argmax);
   } else {
     const long long total = (long long)dim_size * width;
-    agg_last_gather_kernel<<<stride_grid(total, 256), 256, 0, s>>>(msg, arg, num_msgs, dim_size,
+    launch_k(agg_last_gather_kernel, dim3(stride_grid(total, 256)), dim3(256), 0, s, msg, arg, num_msgs, dim_size,
                                                                    width, out, argmax);
   }
   TGN_LAUNCH_CHECK();
@@ -317,19 +335,19 @@ int32_t tgn_agg_mean(const float* msg, const int64_t* index, int32_t num_msgs,
   TGN_CUDA(cudaMemsetAsync(off, 0, (size_t)(S + 1) * 4, s));
   TGN_CUDA(cudaMemsetAsync(scan_ws, 0, (size_t)(ntiles + 1) * 8, s));
   if (M > 0) {
-    agg_mean_count_kernel<<<stride_grid(M, 256), 256, 0, s>>>(index, M, S, off);
+    launch_k(agg_mean_count_kernel, dim3(stride_grid(M, 256)), dim3(256), 0, s, index, M, S, off);
     TGN_LAUNCH_CHECK();
   }
-  agg_mean_scan_kernel<<<ntiles, 256, 0, s>>>(off, cur, S, scan_ws);
+  launch_k(agg_mean_scan_kernel, dim3(ntiles), dim3(256), 0, s, off, cur, S, scan_ws);
   TGN_LAUNCH_CHECK();
   if (M > 0) {
-    agg_mean_fill_kernel<<<stride_grid(M, 256), 256, 0, s>>>(index, M, S, cur, perm);
+    launch_k(agg_mean_fill_kernel, dim3(stride_grid(M, 256)), dim3(256), 0, s, index, M, S, cur, perm);
     TGN_LAUNCH_CHECK();
   }
   const bool vec = (width % 4 == 0) && (((uintptr_t)msg | (uintptr_t)out) % 16 == 0);
   const int grid = stride_grid((long long)S * 32, 256, 16);
-  if (vec) agg_mean_reduce_kernel<true><<<grid, 256, 0, s>>>(msg, off, perm, S, width, out);
-  else agg_mean_reduce_kernel<false><<<grid, 256, 0, s>>>(msg, off, perm, S, width, out);
+  if (vec) launch_k(agg_mean_reduce_kernel<true>, dim3(grid), dim3(256), 0, s, msg, off, perm, S, width, out);
+  else launch_k(agg_mean_reduce_kernel<false>, dim3(grid), dim3(256), 0, s, msg, off, perm, S, width, out);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

@@ -63,6 +63,8 @@ __device__ __forceinline__ float attn_rel_t(const AttnArgs& a, int64_t j, long l
 }
 
 __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_fwd_kernel(AttnArgs a) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float smem[];
   const int HC = a.H * a.C;
   const int Din = a.Dt + a.De;
@@ -229,6 +231,8 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_fwd_kernel(AttnArgs a
 
 __global__ void attn_fill_skip_kernel(const float* __restrict__ proj, DevCount rows, int HC,
                                       float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   const int n = rows.get();
   const long long total = (long long)n * HC;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -282,7 +286,7 @@ int32_t tgn_attn_fwd(const float* proj, const void* last_update_local, int32_t l
   a.alpha_out = alpha_out; a.ee_out = ee_out;
   int grid = ceil_div(num_centres, kAttnWarps);
   if (grid > kNumSMs) grid = kNumSMs;
-  attn_fwd_kernel<<<grid, kAttnWarps * 32, smem, (cudaStream_t)stream>>>(a);
+  launch_k(attn_fwd_kernel, dim3(grid), dim3(kAttnWarps * 32), smem, (cudaStream_t)stream, a);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }
@@ -293,8 +297,7 @@ int32_t tgn_attn_fill_skip(const float* proj, int32_t num_rows, const int32_t* n
   if (num_rows == 0) return TGN_OK;
   TGN_REQUIRE(proj && out, "attn_fill_skip: NULL pointer");
   DevCount c{num_rows_dev, num_rows};
-  attn_fill_skip_kernel<<<stride_grid((long long)num_rows * hc, 256), 256, 0,
-                          (cudaStream_t)stream>>>(proj, c, hc, out);
+  launch_k(attn_fill_skip_kernel, dim3(stride_grid((long long)num_rows * hc, 256)), dim3(256), 0, (cudaStream_t)stream, proj, c, hc, out);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

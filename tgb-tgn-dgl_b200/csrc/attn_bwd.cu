@@ -40,6 +40,8 @@ struct AttnBwdArgs {
 };
 
 __global__ void __launch_bounds__(kBwdWarps * 32) attn_bwd_kernel(AttnBwdArgs a) {
+  pdl_wait();
+  pdl_launch();
   const int HC = a.H * a.C;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nC = a.centres.get();
@@ -145,6 +147,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32) attn_bwd_kernel(AttnBwdArgs a)
 // d_proj[r] = [0, 0, 0, d_out[r]] for r < rows, all-zero rows up to `bound`
 __global__ void attn_bwd_init_kernel(const float* __restrict__ d_out, DevCount rows, int bound,
                                      int HC, float* __restrict__ d_proj) {
+  pdl_wait();
+  pdl_launch();
   const int n = rows.get();
   const long long total = (long long)bound * 4 * HC;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -172,6 +176,8 @@ struct EdgeAttrArgs {
 };
 
 __global__ void attn_edge_attr_kernel(EdgeAttrArgs a) {
+  pdl_wait();
+  pdl_launch();
   const int E = a.edges.get();
   const int Din = a.Dt + a.De;
   const long long total = (long long)a.bound * Din;
@@ -218,8 +224,7 @@ int32_t tgn_attn_bwd_init(const float* d_out, int32_t num_rows, const int32_t* n
   if (num_rows == 0) return TGN_OK;
   TGN_REQUIRE(d_out && d_proj, "attn_bwd_init: NULL pointer");
   DevCount c{num_rows_dev, num_rows};
-  attn_bwd_init_kernel<<<stride_grid((long long)num_rows * 4 * hc, 256), 256, 0,
-                         (cudaStream_t)stream>>>(d_out, c, num_rows, hc, d_proj);
+  launch_k(attn_bwd_init_kernel, dim3(stride_grid((long long)num_rows * 4 * hc, 256)), dim3(256), 0, (cudaStream_t)stream, d_out, c, num_rows, hc, d_proj);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }
@@ -243,7 +248,7 @@ int32_t tgn_attn_bwd(const float* proj, const int64_t* nbr_local, const int32_t*
   a.dropout_p = dropout_p; a.seed = seed; a.seed_dev = seed_dev; a.d_proj = d_proj; a.d_ee = d_ee;
   int grid = ceil_div(num_centres, kBwdWarps);
   if (grid > kNumSMs * 4) grid = kNumSMs * 4;
-  attn_bwd_kernel<<<grid, kBwdWarps * 32, 0, (cudaStream_t)stream>>>(a);
+  launch_k(attn_bwd_kernel, dim3(grid), dim3(kBwdWarps * 32), 0, (cudaStream_t)stream, a);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }
@@ -265,8 +270,7 @@ int32_t tgn_attn_edge_attr(const void* last_update_local, int32_t lu_is_float,
   a.t_is_float = t_is_float; a.msg = msg; a.msg_rows = msg_rows;
   a.edges = DevCount{num_edges_dev, num_edges}; a.bound = num_edges; a.De = raw_dim;
   a.Dt = time_dim; a.time_w = time_w; a.time_b = time_b; a.ea = edge_attr; a.rel = rel_t;
-  attn_edge_attr_kernel<<<stride_grid((long long)num_edges * (raw_dim + time_dim), 256), 256, 0,
-                          (cudaStream_t)stream>>>(a);
+  launch_k(attn_edge_attr_kernel, dim3(stride_grid((long long)num_edges * (raw_dim + time_dim), 256)), dim3(256), 0, (cudaStream_t)stream, a);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

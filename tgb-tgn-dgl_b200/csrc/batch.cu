@@ -22,6 +22,8 @@ __global__ void batch_load_kernel(const int64_t* __restrict__ src_all,
                                   const int64_t* __restrict__ pos_dev, int64_t* __restrict__ ids3,
                                   int64_t* __restrict__ t_i64, float* __restrict__ t_f32,
                                   float* __restrict__ msg) {
+  pdl_wait();
+  pdl_launch();
   const int64_t pos = *pos_dev;
   const long long total = (long long)B * (De > 3 ? De : 3);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -38,7 +40,9 @@ __global__ void batch_load_kernel(const int64_t* __restrict__ src_all,
   }
 }
 
-__global__ void advance_kernel(int64_t* p, int64_t by) { *p += by; }
+__global__ void advance_kernel(int64_t* p, int64_t by) {
+  pdl_wait();
+  pdl_launch(); *p += by; }
 
 }  // namespace tgn
 
@@ -56,11 +60,11 @@ int32_t tgn_batch_load(const int64_t* src_all, const int64_t* dst_all, const int
               "batch_load: NULL pointer");
   cudaStream_t s = (cudaStream_t)stream;
   const long long total = (long long)batch * (raw_dim > 3 ? raw_dim : 3);
-  batch_load_kernel<<<stride_grid(total, 256), 256, 0, s>>>(src_all, dst_all, neg_all, t_all,
+  launch_k(batch_load_kernel, dim3(stride_grid(total, 256)), dim3(256), 0, s, src_all, dst_all, neg_all, t_all,
                                                             msg_all, raw_dim, batch, pos_dev, ids3,
                                                             t_i64, t_f32, msg);
   TGN_LAUNCH_CHECK();
-  advance_kernel<<<1, 1, 0, s>>>(pos_dev, batch);
+  launch_k(advance_kernel, dim3(1), dim3(1), 0, s, pos_dev, batch);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

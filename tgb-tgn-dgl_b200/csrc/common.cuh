@@ -52,6 +52,36 @@ static inline int stride_grid(long long work_items, int block, int max_waves = 8
 }
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the library starts with
+// pdl_wait() -- it blocks until the preceding kernel of the stream has completed and its
+// writes are visible -- followed by pdl_launch(), which lets the NEXT kernel of the stream
+// become resident early (its CTAs then sit in their own pdl_wait).  Launching through
+// launch_k() sets the programmatic-stream-serialization attribute, so the launch latency and
+// the prologue of kernel N+1 overlap the tail of kernel N (also inside captured CUDA graphs,
+// where the edge becomes a programmatic dependency).  tgn_set_pdl(0) turns the attribute off;
+// the two instructions are no-ops for a kernel launched without it.
+// ---------------------------------------------------------------------------
+int& pdl_flag();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_flag() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

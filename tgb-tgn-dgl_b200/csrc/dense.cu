@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(256)
                  const float* __restrict__ b, const float* __restrict__ bias,
                  float* __restrict__ c, DevCount mcnt, int N, DevCount kcnt, int lda, int ldb,
                  int ldc, int accumulate, int split_k) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int M = mcnt.get(), K = kcnt.get();
@@ -124,6 +126,8 @@ __global__ void gru_gates_fwd_kernel(const float* __restrict__ gi, const float* 
                                      const float* __restrict__ h,
                                      const int64_t* __restrict__ h_rows, DevCount num, int D,
                                      float* __restrict__ out, float* __restrict__ gates) {
+  pdl_wait();
+  pdl_launch();
   const int S = num.get();
   const long long total = (long long)S * D;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -155,6 +159,8 @@ __global__ void gru_gates_bwd_kernel(const float* __restrict__ d_out,
                                      const int64_t* __restrict__ h_rows, DevCount num, int bound,
                                      int D, float* __restrict__ d_gi, float* __restrict__ d_gh,
                                      float* __restrict__ d_h) {
+  pdl_wait();
+  pdl_launch();
   const int S = num.get();
   const long long total = (long long)bound * D;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -190,6 +196,8 @@ __global__ void gru_gates_bwd_kernel(const float* __restrict__ d_out,
 
 __global__ void rnn_gates_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
                                      long long total, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x)
     out[e] = tanhf(gi[e] + gh[e]);
@@ -202,6 +210,8 @@ __global__ void memory_scatter_kernel(const int64_t* __restrict__ n_id, DevCount
                                       const int64_t* __restrict__ src_rows, int D,
                                       float* __restrict__ memory,
                                       int64_t* __restrict__ last_update) {
+  pdl_wait();
+  pdl_launch();
   const int S = num.get();
   const long long total = (long long)S * D;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -217,6 +227,8 @@ __global__ void memory_scatter_kernel(const int64_t* __restrict__ n_id, DevCount
 __global__ void time_encode_kernel(const float* __restrict__ t, int num,
                                    const float* __restrict__ w, const float* __restrict__ b, int D,
                                    float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   const long long total = (long long)num * D;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -230,6 +242,8 @@ __global__ void link_score_kernel(const float* __restrict__ hs, const float* __r
                                   const int64_t* __restrict__ b_rows, int num, int D,
                                   const float* __restrict__ wf, const float* __restrict__ bf,
                                   int apply_sigmoid, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < num; i += gridDim.x * wpb) {
@@ -247,6 +261,8 @@ __global__ void link_score_kernel(const float* __restrict__ hs, const float* __r
 
 __global__ void mrr_kernel(const float* __restrict__ pos, const float* __restrict__ neg, int P,
                            int Q, float* __restrict__ rr) {
+  pdl_wait();
+  pdl_launch();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < P; i += gridDim.x * wpb) {
@@ -267,6 +283,8 @@ __global__ void mrr_kernel(const float* __restrict__ pos, const float* __restric
 __global__ void gather_rows_kernel(const float* __restrict__ table,
                                    const int64_t* __restrict__ rows, DevCount num, int D,
                                    float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   const int S = num.get();
   const long long total = (long long)S * D;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -279,6 +297,8 @@ __global__ void gather_rows_kernel(const float* __restrict__ table,
 // out[c] (+)= sum over rows of x[r, c]; one CTA per 32-column strip x row chunk
 __global__ void colsum_kernel(const float* __restrict__ x, DevCount rows, int cols, int ld,
                               float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float s_part[8][33];
   const int R = rows.get();
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -305,6 +325,8 @@ __global__ void time_encode_bwd_kernel(const float* __restrict__ t, const int32_
                                        const float* __restrict__ b, int D,
                                        const float* __restrict__ g, int ldg,
                                        float* __restrict__ d_w, float* __restrict__ d_b) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float s_w[8][33], s_b[8][33];
   const int R = num.get();
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -342,6 +364,8 @@ __global__ void time_encode_bwd_kernel(const float* __restrict__ t, const int32_
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                             float* __restrict__ m, float* __restrict__ v, long long n, float lr,
                             float b1, float b2, float eps, const float* __restrict__ step_dev) {
+  pdl_wait();
+  pdl_launch();
   const float step = *step_dev + 1.f;
   const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
   const float step_size = lr / bc1;
@@ -357,10 +381,14 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
     p[i] -= step_size * (mi / denom);
   }
 }
-__global__ void adam_bump_kernel(float* step_dev) { *step_dev += 1.f; }
+__global__ void adam_bump_kernel(float* step_dev) {
+  pdl_wait();
+  pdl_launch(); *step_dev += 1.f; }
 // end-of-step scalars in one launch: Adam step count, the step counter that keys dropout, loss
 __global__ void step_finish_kernel(float* adam_step, int64_t* step_ctr, const float* loss_acc,
                                    float* loss_out) {
+  pdl_wait();
+  pdl_launch();
   *adam_step += 1.f;
   if (step_ctr) *step_ctr += 1;
   if (loss_acc && loss_out) *loss_out = *loss_acc;
@@ -373,6 +401,8 @@ __global__ void __launch_bounds__(128)
                               const float* __restrict__ h, DevCount num, int D,
                               float* __restrict__ d_gi, float* __restrict__ d_gh,
                               float* __restrict__ d_b_ih, float* __restrict__ d_b_hh) {
+  pdl_wait();
+  pdl_launch();
   const int S = num.get();
   const int rows_per = (S + gridDim.x - 1) / gridDim.x;
   const int r0 = blockIdx.x * rows_per, r1 = min(S, r0 + rows_per);
@@ -428,7 +458,7 @@ int32_t tgn_sgemm(const float* a, const int64_t* a_rows, const float* b, const f
   DevCount mc{m_dev, m}, kc{k_dev, k};
   cudaStream_t s = (cudaStream_t)stream;
 #define LAUNCH(TA, TB)                                                                      \
-  sgemm_kernel<TA, TB><<<grid, 256, 0, s>>>(a, a_rows, b, bias, c, mc, n, kc, lda, ldb, ldc, \
+  launch_k(sgemm_kernel<TA, TB>, dim3(grid), dim3(256), 0, s, a, a_rows, b, bias, c, mc, n, kc, lda, ldb, ldc, \
                                             accumulate, split_k)
   if (!trans_a && !trans_b) LAUNCH(false, false);
   else if (!trans_a && trans_b) LAUNCH(false, true);
@@ -446,7 +476,7 @@ int32_t tgn_gru_gates_fwd(const float* gi, const float* gh, const float* h,
   if (num == 0) return TGN_OK;
   TGN_REQUIRE(gi && gh && h && out, "gru_gates_fwd: NULL pointer");
   DevCount c{num_dev, num};
-  gru_gates_fwd_kernel<<<stride_grid((long long)num * dim, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(gru_gates_fwd_kernel, dim3(stride_grid((long long)num * dim, 256)), dim3(256), 0, (cudaStream_t)stream, 
       gi, gh, h, h_rows, c, dim, out, gates);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -459,7 +489,7 @@ int32_t tgn_gru_gates_bwd(const float* d_out, const float* gates, const float* h
   if (num == 0) return TGN_OK;
   TGN_REQUIRE(d_out && gates && h && d_gi && d_gh, "gru_gates_bwd: NULL pointer");
   DevCount c{num_dev, num};
-  gru_gates_bwd_kernel<<<stride_grid((long long)num * dim, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(gru_gates_bwd_kernel, dim3(stride_grid((long long)num * dim, 256)), dim3(256), 0, (cudaStream_t)stream, 
       d_out, gates, h, h_rows, c, num, dim, d_gi, d_gh, d_h);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -473,7 +503,7 @@ int32_t tgn_gru_gates_bwd_bias(const float* d_out, const float* gates, const flo
   TGN_REQUIRE(d_out && gates && h && d_gi && d_gh && d_b_ih && d_b_hh, "gru_gates_bwd_bias: NULL pointer");
   int grid = ceil_div(num, 16);
   if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
-  gru_gates_bwd_bias_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+  launch_k(gru_gates_bwd_bias_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, 
       d_out, gates, h, DevCount{num_dev, num}, dim, d_gi, d_gh, d_b_ih, d_b_hh);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -485,7 +515,7 @@ int32_t tgn_rnn_gates_fwd(const float* gi, const float* gh, int32_t num, int32_t
   if (num == 0) return TGN_OK;
   TGN_REQUIRE(gi && gh && out, "rnn_gates_fwd: NULL pointer");
   const long long total = (long long)num * dim;
-  rnn_gates_fwd_kernel<<<stride_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(gi, gh, total,
+  launch_k(rnn_gates_fwd_kernel, dim3(stride_grid(total, 256)), dim3(256), 0, (cudaStream_t)stream, gi, gh, total,
                                                                                    out);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -503,10 +533,10 @@ int32_t tgn_memory_scatter(const int64_t* n_id, int32_t num, const int32_t* num_
   const int grid = stride_grid((long long)num * dim, 256);
   cudaStream_t s = (cudaStream_t)stream;
   if (lu_is_float)
-    memory_scatter_kernel<float><<<grid, 256, 0, s>>>(n_id, c, new_mem, (const float*)new_lu,
+    launch_k(memory_scatter_kernel<float>, dim3(grid), dim3(256), 0, s, n_id, c, new_mem, (const float*)new_lu,
                                                       src_rows, dim, memory, last_update);
   else
-    memory_scatter_kernel<int64_t><<<grid, 256, 0, s>>>(n_id, c, new_mem, (const int64_t*)new_lu,
+    launch_k(memory_scatter_kernel<int64_t>, dim3(grid), dim3(256), 0, s, n_id, c, new_mem, (const int64_t*)new_lu,
                                                         src_rows, dim, memory, last_update);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -517,7 +547,7 @@ int32_t tgn_time_encode(const float* t, int32_t num, const float* w, const float
   TGN_REQUIRE(num >= 0 && dim >= 1, "time_encode: bad sizes");
   if (num == 0) return TGN_OK;
   TGN_REQUIRE(t && w && b && out, "time_encode: NULL pointer");
-  time_encode_kernel<<<stride_grid((long long)num * dim, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(time_encode_kernel, dim3(stride_grid((long long)num * dim, 256)), dim3(256), 0, (cudaStream_t)stream, 
       t, num, w, b, dim, out);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -530,7 +560,7 @@ int32_t tgn_link_score(const float* hs, const float* hd, const int64_t* a_rows,
   if (num == 0) return TGN_OK;
   TGN_REQUIRE(hs && hd && a_rows && b_rows && w_final && b_final && out,
               "link_score: NULL pointer");
-  link_score_kernel<<<stride_grid((long long)num * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(link_score_kernel, dim3(stride_grid((long long)num * 32, 256)), dim3(256), 0, (cudaStream_t)stream, 
       hs, hd, a_rows, b_rows, num, dim, w_final, b_final, apply_sigmoid, out);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -541,7 +571,7 @@ int32_t tgn_mrr(const float* pos, const float* neg, int32_t num_pos, int32_t num
   TGN_REQUIRE(num_pos >= 0 && num_neg >= 0, "mrr: bad sizes");
   if (num_pos == 0) return TGN_OK;
   TGN_REQUIRE(pos && rr_out && (neg || num_neg == 0), "mrr: NULL pointer");
-  mrr_kernel<<<stride_grid((long long)num_pos * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(mrr_kernel, dim3(stride_grid((long long)num_pos * 32, 256)), dim3(256), 0, (cudaStream_t)stream, 
       pos, neg, num_pos, num_neg, rr_out);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -553,7 +583,7 @@ int32_t tgn_gather_rows(const float* table, const int64_t* rows, int32_t num,
   if (num == 0) return TGN_OK;
   TGN_REQUIRE(table && rows && out, "gather_rows: NULL pointer");
   DevCount c{num_dev, num};
-  gather_rows_kernel<<<stride_grid((long long)num * dim, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(gather_rows_kernel, dim3(stride_grid((long long)num * dim, 256)), dim3(256), 0, (cudaStream_t)stream, 
       table, rows, c, dim, out);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -570,7 +600,7 @@ int32_t tgn_colsum(const float* x, int32_t rows, const int32_t* rows_dev, int32_
   DevCount c{rows_dev, rows};
   int gy = ceil_div(rows, 256);
   if (gy > 64) gy = 64;
-  colsum_kernel<<<dim3(ceil_div(cols, 32), gy), 256, 0, s>>>(x, c, cols, ld, out);
+  launch_k(colsum_kernel, dim3(dim3(ceil_div(cols, 32), gy)), dim3(256), 0, s, x, c, cols, ld, out);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }
@@ -585,7 +615,7 @@ int32_t tgn_time_encode_bwd(const float* t, const int32_t* row_mask, int32_t num
   DevCount c{num_dev, num};
   int gy = ceil_div(num, 256);
   if (gy > 64) gy = 64;
-  time_encode_bwd_kernel<<<dim3(ceil_div(dim, 32), gy), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(time_encode_bwd_kernel, dim3(dim3(ceil_div(dim, 32), gy)), dim3(256), 0, (cudaStream_t)stream, 
       t, row_mask, c, w, b, dim, grad, ld_grad, d_w, d_b);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -599,11 +629,11 @@ int32_t tgn_adam_step(float* params, const float* grads, float* exp_avg, float* 
   cudaStream_t s = (cudaStream_t)stream;
   if (count > 0) {
     TGN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "adam_step: NULL pointer");
-    adam_kernel<<<stride_grid(count, 256), 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, count,
+    launch_k(adam_kernel, dim3(stride_grid(count, 256)), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, count,
                                                         lr, beta1, beta2, eps, step_dev);
     TGN_LAUNCH_CHECK();
   }
-  adam_bump_kernel<<<1, 1, 0, s>>>(step_dev);
+  launch_k(adam_bump_kernel, dim3(1), dim3(1), 0, s, step_dev);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }
@@ -615,11 +645,11 @@ int32_t tgn_adam_finish(float* params, const float* grads, float* exp_avg, float
   cudaStream_t s = (cudaStream_t)stream;
   if (count > 0) {
     TGN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "adam_finish: NULL pointer");
-    adam_kernel<<<stride_grid(count, 256), 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, count,
+    launch_k(adam_kernel, dim3(stride_grid(count, 256)), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, count,
                                                         lr, beta1, beta2, eps, step_dev);
     TGN_LAUNCH_CHECK();
   }
-  step_finish_kernel<<<1, 1, 0, s>>>(step_dev, step_counter, loss_acc, loss_out);
+  launch_k(step_finish_kernel, dim3(1), dim3(1), 0, s, step_dev, step_counter, loss_acc, loss_out);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

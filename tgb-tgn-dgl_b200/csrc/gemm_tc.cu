@@ -191,6 +191,8 @@ __device__ __forceinline__ void store_tile(const TileRegs& r, float* hi, float* 
 
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(TcArgs g) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ __align__(1024) float smem[];
   __shared__ __align__(8) uint64_t s_bar[kStages];
   __shared__ uint32_t s_tmem;
@@ -372,10 +374,10 @@ int32_t tgn_tc_gemm(const float* a, const int64_t* a_rows, const float* b, const
   cudaStream_t s = (cudaStream_t)stream;
   // op(A)(m,k): !trans_a -> a[m*lda+k] (K-contiguous), trans_a -> a[k*lda+m]
   // op(B)(k,n): !trans_b -> b[n*ldb+k] (K-contiguous), trans_b -> b[k*ldb+n]
-  if (!trans_a && !trans_b) tc_gemm_kernel<false, false><<<grid, 256, smem, s>>>(g);
-  else if (!trans_a && trans_b) tc_gemm_kernel<false, true><<<grid, 256, smem, s>>>(g);
-  else if (trans_a && !trans_b) tc_gemm_kernel<true, false><<<grid, 256, smem, s>>>(g);
-  else tc_gemm_kernel<true, true><<<grid, 256, smem, s>>>(g);
+  if (!trans_a && !trans_b) launch_k(tc_gemm_kernel<false, false>, dim3(grid), dim3(256), smem, s, g);
+  else if (!trans_a && trans_b) launch_k(tc_gemm_kernel<false, true>, dim3(grid), dim3(256), smem, s, g);
+  else if (trans_a && !trans_b) launch_k(tc_gemm_kernel<true, false>, dim3(grid), dim3(256), smem, s, g);
+  else launch_k(tc_gemm_kernel<true, true>, dim3(grid), dim3(256), smem, s, g);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

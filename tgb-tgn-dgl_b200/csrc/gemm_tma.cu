@@ -183,6 +183,8 @@ __device__ __forceinline__ void g_mask4(float4& v, int idx, bool mn_major, int k
 
 __global__ void __launch_bounds__(kGThreads, 1)
     tgemm_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmParams prm) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ __align__(1024) uint8_t g_smem[];
   __shared__ __align__(8) uint64_t s_full[kGMaxStages], s_conv[kGMaxStages], s_empty[kGMaxStages], s_acc;
   __shared__ uint32_t s_tmem;
@@ -199,22 +201,13 @@ __global__ void __launch_bounds__(kGThreads, 1)
   local /= P.tiles_n;
   const int tm = local % P.tiles_m;
   const int split = local / P.tiles_m;
-  const int M = P.m_dev ? min(*P.m_dev, P.m) : P.m;
-  const int K = P.k_dev ? min(*P.k_dev, P.k) : P.k;
   const int m0 = tm * GM, n0 = tn * GN;
-  if (m0 >= M) return;
-  const int kchunk = ((K + P.split_k - 1) / P.split_k + GK - 1) / GK * GK;
-  const int kbeg = split * kchunk;
-  const int kend = min(K, kbeg + kchunk);
-  const int nk = kend > kbeg ? (kend - kbeg + GK - 1) / GK : 0;
-  if (nk == 0 && P.mode != 0) return;  // nothing to add
   const bool split3 = prm.prec == 3;
   const int kGStages = split3 ? kGStages3 : kGStages1;
   const int kGStageBytes = split3 ? kGStageBytes3 : kGStageBytes1;
-  // a live reduction length that ends inside the last 32-wide k-block (and inside the tensor,
-  // where the TMA unit does not zero-fill) is cut off by zeroing the tail of that block
-  const bool tail_mask = nk > 0 && kend < P.k && ((kend - kbeg) & (GK - 1)) != 0;
 
+  // ---- prologue: nothing here reads what the preceding kernel wrote, so under programmatic
+  // dependent launch it overlaps that kernel's tail
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g_smem) + 1023) &
                                              ~(uintptr_t)1023);
   if (tid == 0) {
@@ -226,6 +219,8 @@ __global__ void __launch_bounds__(kGThreads, 1)
     }
     g_mbar_init(&s_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[pi]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[pi]) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -238,13 +233,27 @@ __global__ void __launch_bounds__(kGThreads, 1)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
 
+  pdl_wait();     // operands / device counts of the preceding kernels are visible from here on
+  pdl_launch();
+  const int M = P.m_dev ? min(*P.m_dev, P.m) : P.m;
+  const int K = P.k_dev ? min(*P.k_dev, P.k) : P.k;
+  const int kchunk = ((K + P.split_k - 1) / P.split_k + GK - 1) / GK * GK;
+  const int kbeg = split * kchunk;
+  const int kend = min(K, kbeg + kchunk);
+  int nk = kend > kbeg ? (kend - kbeg + GK - 1) / GK : 0;
+  // dead tile (past the live rows, or an empty K split with nothing to add): no loads, no
+  // stores, straight to the teardown
+  const bool live = m0 < M && !(nk == 0 && P.mode != 0);
+  if (!live) nk = 0;
+  // a live reduction length that ends inside the last 32-wide k-block (and inside the tensor,
+  // where the TMA unit does not zero-fill) is cut off by zeroing the tail of that block
+  const bool tail_mask = nk > 0 && kend < P.k && ((kend - kbeg) & (GK - 1)) != 0;
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       const CUtensorMap* ma = &maps.a[pi];
       const CUtensorMap* mb = &maps.b[pi];
-      asm volatile("prefetch.tensormap [%0];" ::"l"(ma) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(mb) : "memory");
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % kGStages;
         if (kb >= kGStages) g_mbar_wait(&s_empty[s], ((kb / kGStages) - 1) & 1);
@@ -348,7 +357,7 @@ __global__ void __launch_bounds__(kGThreads, 1)
     const int q = warp & 3;             // TMEM lane group this warp may read
     const int chalf = warp >= 6 ? 64 : 0;  // warps 2-5: columns 0..63, warps 6-9: 64..127
     const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < M;
+    const bool row_ok = live && row < M;
     float* crow = P.c + (long long)row * P.ldc;
     const bool vec_ok = (P.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.c) & 15) == 0);
 #pragma unroll 1
@@ -511,7 +520,7 @@ int32_t tgn_gemm_batch(const tgn_gemm_desc* d, int32_t count, int32_t precision,
     TGN_CUDA(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  tgemm_kernel<<<tiles, kGThreads, smem, (cudaStream_t)stream>>>(maps, prm);
+  launch_k(tgemm_kernel, dim3(tiles), dim3(kGThreads), smem, (cudaStream_t)stream, maps, prm);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

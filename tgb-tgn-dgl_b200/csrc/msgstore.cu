@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(1024, 1)
                            const int64_t* __restrict__ dst, const T* __restrict__ t,
                            const float* __restrict__ raw, int B, int P, int64_t base_host,
                            int64_t* __restrict__ base_dev) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ unsigned long long s_key[];
   const int64_t base = base_dev ? *base_dev : base_host;
   if (base + B > st.capacity) return;  // caller sizes the log; never write out of bounds
@@ -100,6 +102,8 @@ __global__ void __launch_bounds__(1024, 1)
 }
 
 __global__ void msgstore_reset_kernel(tgn_msgstore st) {
+  pdl_wait();
+  pdl_launch();
   for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < st.num_nodes;
        n += (int64_t)gridDim.x * blockDim.x) {
     st.s_cnt[n] = 0;
@@ -116,6 +120,8 @@ __global__ void __launch_bounds__(1024)
     msgstore_count_kernel(const int32_t* __restrict__ cnt, const int64_t* __restrict__ n_id,
                           int num, int64_t num_nodes, int32_t* __restrict__ offsets,
                           unsigned long long* __restrict__ ws) {
+  pdl_wait();
+  pdl_launch();
   __shared__ int s_warp[32];
   __shared__ long long s_prefix;
   const int ntiles = (num + 1023) / 1024;
@@ -157,6 +163,8 @@ __global__ void msgstore_gather_kernel(tgn_msgstore st, const int64_t* __restric
                                        int64_t* __restrict__ out_src,
                                        int64_t* __restrict__ out_dst, T* __restrict__ out_t,
                                        float* __restrict__ out_raw) {
+  pdl_wait();
+  pdl_launch();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const T* ev_t = reinterpret_cast<const T*>(st.ev_t);
@@ -206,6 +214,8 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
                                  int ldx, float* __restrict__ h_out, float* __restrict__ sin_out,
                                  T* __restrict__ lu_out, int32_t* __restrict__ sel_ev,
                                  float* __restrict__ sel_dt) {
+  pdl_wait();
+  pdl_launch();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int S = num.get();
@@ -347,10 +357,10 @@ int32_t tgn_msgstore_update(const tgn_msgstore* st, const int64_t* src, const in
   }
   cudaStream_t s = (cudaStream_t)stream;
   if (st->t_is_float)
-    msgstore_update_kernel<float><<<1, 1024, (size_t)P * 8, s>>>(
+    launch_k(msgstore_update_kernel<float>, dim3(1), dim3(1024), (size_t)P * 8, s, 
         *st, src, dst, (const float*)t, raw_msg, batch, P, base, base_dev);
   else
-    msgstore_update_kernel<int64_t><<<1, 1024, (size_t)P * 8, s>>>(
+    launch_k(msgstore_update_kernel<int64_t>, dim3(1), dim3(1024), (size_t)P * 8, s, 
         *st, src, dst, (const int64_t*)t, raw_msg, batch, P, base, base_dev);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -359,7 +369,7 @@ int32_t tgn_msgstore_update(const tgn_msgstore* st, const int64_t* src, const in
 int32_t tgn_msgstore_reset(const tgn_msgstore* st, void* stream) {
   int32_t rc = check_store(st, "msgstore_reset");
   if (rc) return rc;
-  msgstore_reset_kernel<<<stride_grid(st->num_nodes, 256), 256, 0, (cudaStream_t)stream>>>(*st);
+  launch_k(msgstore_reset_kernel, dim3(stride_grid(st->num_nodes, 256)), dim3(256), 0, (cudaStream_t)stream, *st);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }
@@ -383,7 +393,7 @@ int32_t tgn_msgstore_count(const tgn_msgstore* st, const int64_t* n_id, int32_t 
   TGN_REQUIRE(n_id, "msgstore_count: n_id is NULL");
   const int ntiles = (num + 1023) / 1024;
   TGN_CUDA(cudaMemsetAsync(ws, 0, (size_t)(ntiles + 1) * 8, s));
-  msgstore_count_kernel<<<ntiles, 1024, 0, s>>>(dir == 0 ? st->s_cnt : st->d_cnt, n_id, num,
+  launch_k(msgstore_count_kernel, dim3(ntiles), dim3(1024), 0, s, dir == 0 ? st->s_cnt : st->d_cnt, n_id, num,
                                                 st->num_nodes, offsets,
                                                 (unsigned long long*)ws);
   TGN_LAUNCH_CHECK();
@@ -402,10 +412,10 @@ int32_t tgn_msgstore_gather(const tgn_msgstore* st, const int64_t* n_id, int32_t
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = stride_grid((long long)num * 32, 256);
   if (st->t_is_float)
-    msgstore_gather_kernel<float><<<grid, 256, 0, s>>>(*st, n_id, num, dir, offsets, out_src,
+    launch_k(msgstore_gather_kernel<float>, dim3(grid), dim3(256), 0, s, *st, n_id, num, dir, offsets, out_src,
                                                        out_dst, (float*)out_t, out_raw);
   else
-    msgstore_gather_kernel<int64_t><<<grid, 256, 0, s>>>(*st, n_id, num, dir, offsets, out_src,
+    launch_k(msgstore_gather_kernel<int64_t>, dim3(grid), dim3(256), 0, s, *st, n_id, num, dir, offsets, out_src,
                                                          out_dst, (int64_t*)out_t, out_raw);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -429,11 +439,11 @@ int32_t tgn_msg_build_ld(const tgn_msgstore* st, const int64_t* n_id, int32_t nu
   DevCount c{num_dev, num};
   const int grid = stride_grid((long long)num * 32, 256);
   if (st->t_is_float)
-    msg_build_kernel<float><<<grid, 256, 0, s>>>(*st, n_id, c, agg_mode, memory, last_update,
+    launch_k(msg_build_kernel<float>, dim3(grid), dim3(256), 0, s, *st, n_id, c, agg_mode, memory, last_update,
                                                  memory_dim, time_w, time_b, time_dim, x, ldx, h_out,
                                                  sin_out, (float*)lu_out, sel_ev, sel_dt);
   else
-    msg_build_kernel<int64_t><<<grid, 256, 0, s>>>(*st, n_id, c, agg_mode, memory, last_update,
+    launch_k(msg_build_kernel<int64_t>, dim3(grid), dim3(256), 0, s, *st, n_id, c, agg_mode, memory, last_update,
                                                    memory_dim, time_w, time_b, time_dim, x, ldx,
                                                    h_out, sin_out, (int64_t*)lu_out, sel_ev, sel_dt);
   TGN_LAUNCH_CHECK();

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(kLookupThreads)
                       int32_t* __restrict__ root_off, int32_t* __restrict__ out_count,
                       uint32_t* __restrict__ l0, uint32_t* __restrict__ l1,
                       unsigned long long* __restrict__ ws) {
+  pdl_wait();
+  pdl_launch();
   __shared__ int s_warp_tot[kLookupThreads / 32];
   __shared__ long long s_tile_prefix;
   const int R = roots.get();
@@ -139,6 +141,8 @@ __global__ void __launch_bounds__(1024, 1)
                       int64_t* __restrict__ cur_dev, int K, int64_t num_nodes,
                       int64_t* __restrict__ nbrs, int64_t* __restrict__ eids,
                       float* __restrict__ ts) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ unsigned long long s_key[];
   const int n = 2 * B;
   const int64_t cur = cur_dev ? *cur_dev : cur_host;
@@ -244,7 +248,7 @@ int32_t tgn_nbr_lookup(const int64_t* n_id, int32_t num_roots, const int32_t* nu
   uint32_t* l0 = (uint32_t*)bitmap;
   uint32_t* l1 = l0 ? l0 + ((num_nodes + 1023) / 1024) * 32 : nullptr;
   DevCount rc{num_roots_dev, num_roots};
-  nbr_lookup_kernel<<<ntiles, kLookupThreads, 0, s>>>(
+  launch_k(nbr_lookup_kernel, dim3(ntiles), dim3(kLookupThreads), 0, s, 
       n_id, rc, size_k, tr, num_nodes, neighbors, e_id, t, out_nbr, out_centre, out_eid, out_t,
       root_off, out_count, l0, l1, (unsigned long long*)ws);
   TGN_LAUNCH_CHECK();
@@ -268,7 +272,7 @@ int32_t tgn_nbr_insert(const int64_t* src, const int64_t* dst, const float* t, i
                                   TGN_SORT_MAX * 8));
     attr_set = true;
   }
-  nbr_insert_kernel<<<1, 1024, (size_t)P * 8, (cudaStream_t)stream>>>(
+  launch_k(nbr_insert_kernel, dim3(1), dim3(1024), (size_t)P * 8, (cudaStream_t)stream, 
       src, dst, t, batch, P, cur_e_id, cur_e_id_dev, size_k, num_nodes, neighbors, e_id, t_state);
   TGN_LAUNCH_CHECK();
   return TGN_OK;

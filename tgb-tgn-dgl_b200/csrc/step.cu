@@ -21,6 +21,8 @@ __global__ void relabel3_kernel(const int64_t* __restrict__ a, DevCount na, int6
                                 const int64_t* __restrict__ b, DevCount nb, int64_t* __restrict__ ob,
                                 const int64_t* __restrict__ c, DevCount nc, int64_t* __restrict__ oc,
                                 const int64_t* __restrict__ assoc) {
+  pdl_wait();
+  pdl_launch();
   const int ca = na.get(), cb = nb.get(), cc = nc.get();
   const int total = ca + cb + cc;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -46,6 +48,8 @@ struct EdgeAttr2Args {
 };
 
 __global__ void edge_attr_ld_kernel(EdgeAttr2Args a) {
+  pdl_wait();
+  pdl_launch();
   const int E = a.edges.get();
   const long long total = (long long)E * a.ld;
   for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total;
@@ -73,6 +77,8 @@ __global__ void time_bwd_sin_kernel(const float* __restrict__ t, const int32_t* 
                                     DevCount num, const float* __restrict__ sn, int D,
                                     const float* __restrict__ g, int ldg, float* __restrict__ d_w,
                                     float* __restrict__ d_b) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float s_w[8][33], s_b[8][33];
   const int R = num.get();
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -174,6 +180,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 
 template <int H>
 __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_fwd_kernel(AttnCoreArgs a) {
+  pdl_wait();
+  pdl_launch();
   const int HC = a.H * a.C, C = a.C;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nC = a.centres.get();
@@ -295,6 +303,8 @@ __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_fwd_kernel(AttnCore
 // d alpha and emits the gradients; neighbour rows of d_proj receive vector reductions.
 template <int H>
 __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_bwd_kernel(AttnCoreArgs a) {
+  pdl_wait();
+  pdl_launch();
   const int HC = a.H * a.C, C = a.C;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nC = a.centres.get();
@@ -417,6 +427,8 @@ __global__ void __launch_bounds__(kDecWarps * 32)
                     float* __restrict__ loss, float* __restrict__ logits, float* __restrict__ dh,
                     float* __restrict__ dhs, float* __restrict__ d_wf, float* __restrict__ d_bf,
                     float* __restrict__ d_bs, float* __restrict__ d_bd) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float s_red[];  // [3][D] : d_wf, d_bs, d_bd partials
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) s_red[i] = 0.f;
@@ -490,6 +502,8 @@ __global__ void __launch_bounds__(kDecThreads)
                      float* __restrict__ loss, float* __restrict__ logits, float* __restrict__ d_emb,
                      float* __restrict__ dWs, float* __restrict__ dbs, float* __restrict__ dWd,
                      float* __restrict__ dbd, float* __restrict__ dwf, float* __restrict__ dbf) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sm[];
   const int ld = D + 1;
   float* sWs = sm;
@@ -660,6 +674,8 @@ __global__ void __launch_bounds__(256)
                       const float* __restrict__ wf, const float* __restrict__ bf,
                       float* __restrict__ pos_out, float* __restrict__ neg_out,
                       int32_t* __restrict__ gt_out, int32_t* __restrict__ ge_out) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float s_a[];  // [D] hs row of the source, [D] w_final
   __shared__ float s_pos;
   __shared__ int s_gt, s_ge;
@@ -711,6 +727,8 @@ __global__ void __launch_bounds__(256)
 
 __global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ rows,
                                         DevCount num, int D, float* __restrict__ dst) {
+  pdl_wait();
+  pdl_launch();
   const int n = num.get();
   const long long total = (long long)n * D;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -734,7 +752,7 @@ int32_t tgn_relabel3(const int64_t* a, int32_t na, const int32_t* na_dev, int64_
   if (na + nb + nc == 0) return TGN_OK;
   TGN_REQUIRE(assoc && (na == 0 || (a && oa)) && (nb == 0 || (b && ob)) && (nc == 0 || (c && oc)),
               "relabel3: NULL pointer");
-  relabel3_kernel<<<stride_grid((long long)na + nb + nc, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(relabel3_kernel, dim3(stride_grid((long long)na + nb + nc, 256)), dim3(256), 0, (cudaStream_t)stream, 
       a, DevCount{na_dev, na}, oa, b, DevCount{nb_dev, nb}, ob, c, DevCount{nc_dev, nc}, oc, assoc);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -755,7 +773,7 @@ int32_t tgn_edge_attr_ld(const int64_t* last_update_local, const int64_t* nbr_lo
   a.lu = last_update_local; a.nbr = nbr_local; a.t_edge = t_edge; a.msg = msg; a.msg_rows = msg_rows;
   a.edges = DevCount{num_edges_dev, num_edges}; a.De = raw_dim; a.Dt = time_dim; a.ld = ld;
   a.time_w = time_w; a.time_b = time_b; a.ea = edge_attr; a.sn = sin_out; a.rel = rel_t;
-  edge_attr_ld_kernel<<<stride_grid((long long)num_edges * ld, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  launch_k(edge_attr_ld_kernel, dim3(stride_grid((long long)num_edges * ld, 256)), dim3(256), 0, (cudaStream_t)stream, a);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }
@@ -768,7 +786,7 @@ int32_t tgn_time_bwd_sin(const float* t, const int32_t* row_mask, int32_t num, c
   TGN_REQUIRE(t && sin_vals && grad && d_w && d_b, "time_bwd_sin: NULL pointer");
   int gy = ceil_div(num, 128);
   if (gy > 64) gy = 64;
-  time_bwd_sin_kernel<<<dim3(ceil_div(dim, 32), gy), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(time_bwd_sin_kernel, dim3(dim3(ceil_div(dim, 32), gy)), dim3(256), 0, (cudaStream_t)stream, 
       t, row_mask, DevCount{num_dev, num}, sin_vals, dim, grad, ld_grad, d_w, d_b);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -807,10 +825,10 @@ int32_t tgn_attn_core_fwd(const float* proj, const int64_t* nbr_local, const int
   const int grid = ceil_div(num_centres, kCoreWarps);
   cudaStream_t s = (cudaStream_t)stream;
   switch (heads) {
-    case 1: attn_core_fwd_kernel<1><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
-    case 2: attn_core_fwd_kernel<2><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
-    case 4: attn_core_fwd_kernel<4><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
-    default: attn_core_fwd_kernel<8><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
+    case 1: launch_k(attn_core_fwd_kernel<1>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+    case 2: launch_k(attn_core_fwd_kernel<2>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+    case 4: launch_k(attn_core_fwd_kernel<4>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+    default: launch_k(attn_core_fwd_kernel<8>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
   }
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -837,10 +855,10 @@ int32_t tgn_attn_core_bwd(const float* proj, const int64_t* nbr_local, const int
   a.alpha = const_cast<float*>(alpha); a.d_out = d_out; a.d_proj = d_proj; a.d_ee = d_ee;
   const int grid = ceil_div(num_centres, kCoreWarps);
   switch (heads) {
-    case 1: attn_core_bwd_kernel<1><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
-    case 2: attn_core_bwd_kernel<2><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
-    case 4: attn_core_bwd_kernel<4><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
-    default: attn_core_bwd_kernel<8><<<grid, kCoreWarps * 32, 0, s>>>(a); break;
+    case 1: launch_k(attn_core_bwd_kernel<1>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+    case 2: launch_k(attn_core_bwd_kernel<2>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+    case 4: launch_k(attn_core_bwd_kernel<4>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+    default: launch_k(attn_core_bwd_kernel<8>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
   }
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -856,7 +874,7 @@ int32_t tgn_dec_loss(const float* hs, const float* hd, const float* w_final, con
               "dec_loss: NULL pointer");
   int grid = ceil_div(batch, kDecWarps);
   if (grid > kNumSMs) grid = kNumSMs;
-  dec_loss_kernel<<<grid, kDecWarps * 32, (size_t)3 * dim * sizeof(float), (cudaStream_t)stream>>>(
+  launch_k(dec_loss_kernel, dim3(grid), dim3(kDecWarps * 32), (size_t)3 * dim * sizeof(float), (cudaStream_t)stream, 
       hs, hd, w_final, b_final, batch, dim, loss, logits, dh, dhs, d_w_final, d_b_final, d_b_src,
       d_b_dst);
   TGN_LAUNCH_CHECK();
@@ -886,7 +904,7 @@ int32_t tgn_dec_fused(const float* emb, const int64_t* ids_local, int32_t batch,
   }
   int grid = ceil_div(batch, 2);  // ~2 events per CTA: balances the event walk against the flush
   if (grid > kNumSMs) grid = kNumSMs;
-  dec_fused_kernel<<<grid, kDecThreads, (size_t)smem, (cudaStream_t)stream>>>(
+  launch_k(dec_fused_kernel, dim3(grid), dim3(kDecThreads), (size_t)smem, (cudaStream_t)stream, 
       emb, ids_local, batch, dim, w_src, b_src, w_dst, b_dst, w_final, b_final, loss, logits, d_emb,
       d_w_src, d_b_src, d_w_dst, d_b_dst, d_w_final, d_b_final);
   TGN_LAUNCH_CHECK();
@@ -904,7 +922,7 @@ int32_t tgn_score_negs(const float* hs, const float* hd, const int64_t* src_rows
                   b_final && pos_out && gt_out && ge_out,
               "score_negs: NULL pointer");
   int grid = num_pos < 8 * kNumSMs ? num_pos : 8 * kNumSMs;
-  score_negs_kernel<<<grid, 256, (size_t)2 * dim * sizeof(float), (cudaStream_t)stream>>>(
+  launch_k(score_negs_kernel, dim3(grid), dim3(256), (size_t)2 * dim * sizeof(float), (cudaStream_t)stream, 
       hs, hd, src_rows, dst_rows, neg_rows, num_pos, num_neg, dim, w_final, b_final, pos_out,
       neg_out, gt_out, ge_out);
   TGN_LAUNCH_CHECK();
@@ -916,7 +934,7 @@ int32_t tgn_scatter_add_rows(const float* src, const int64_t* rows, int32_t num,
   TGN_REQUIRE(num >= 0 && dim >= 1, "scatter_add_rows: bad sizes");
   if (num == 0) return TGN_OK;
   TGN_REQUIRE(src && rows && dst, "scatter_add_rows: NULL pointer");
-  scatter_add_rows_kernel<<<stride_grid((long long)num * dim, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(scatter_add_rows_kernel, dim3(stride_grid((long long)num * dim, 256)), dim3(256), 0, (cudaStream_t)stream, 
       src, rows, DevCount{num_dev, num}, dim, dst);
   TGN_LAUNCH_CHECK();
   return TGN_OK;

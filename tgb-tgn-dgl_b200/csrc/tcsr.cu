@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(kTcsrTile)
                        int32_t* __restrict__ out_eid, float* __restrict__ out_ts,
                        float* __restrict__ out_dts, int32_t* __restrict__ root_off,
                        int32_t* __restrict__ out_count, unsigned long long* __restrict__ ws) {
+  pdl_wait();
+  pdl_launch();
   __shared__ int s_lo[kTcsrTile], s_hi[kTcsrTile], s_pref[kTcsrTile + 1];
   __shared__ float s_t[kTcsrTile];
   __shared__ int s_warp[kTcsrTile / 32];
@@ -158,7 +160,7 @@ int32_t tgn_tcsr_sample(const int32_t* indptr, const int32_t* indices, const int
               "tcsr_sample: NULL buffer");
   const int ntiles = (num_roots + kTcsrTile - 1) / kTcsrTile;
   TGN_CUDA(cudaMemsetAsync(ws, 0, (size_t)(ntiles + 1) * 8, s));
-  tcsr_sample_kernel<<<ntiles, kTcsrTile, 0, s>>>(
+  launch_k(tcsr_sample_kernel, dim3(ntiles), dim3(kTcsrTile), 0, s, 
       indptr, indices, eid, ts, num_nodes, root_nodes, root_ts, num_roots, k, strategy, offset,
       duration, seed, out_nbr, out_col, out_eid, out_ts, out_dts, root_off, out_count,
       (unsigned long long*)ws);

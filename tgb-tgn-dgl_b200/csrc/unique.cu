@@ -23,12 +23,19 @@ int set_err(int code, const char* fmt, ...) {
   return code;
 }
 
+int& pdl_flag() {
+  static int flag = 1;
+  return flag;
+}
+
 static inline int64_t l0_groups(int64_t n) { return (n + 1023) / 1024; }
 static inline int64_t l0_words(int64_t n) { return l0_groups(n) * 32; }
 static inline int64_t l1_words(int64_t n) { return (l0_groups(n) + 31) / 32; }
 
 __global__ void unique_mark_kernel(const int64_t* __restrict__ ids, DevCount cnt, int64_t n_nodes,
                                    uint32_t* __restrict__ l0, uint32_t* __restrict__ l1) {
+  pdl_wait();
+  pdl_launch();
   const int n = cnt.get();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int64_t id = ids[i];
@@ -55,6 +62,8 @@ __global__ void __launch_bounds__(1024, 1)
                        int64_t* __restrict__ assoc, int32_t* __restrict__ out_count,
                        int keep_marks, const int64_t* __restrict__ mark_ids, int mark_count,
                        int64_t n_nodes) {
+  pdl_wait();
+  pdl_launch();
   __shared__ int s_warp[32];
   __shared__ int s_off[1024];
   __shared__ int s_base, s_total;
@@ -144,6 +153,8 @@ __global__ void __launch_bounds__(1024, 1)
 
 __global__ void relabel_kernel(const int64_t* __restrict__ ids, DevCount cnt,
                                const int64_t* __restrict__ assoc, int64_t* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   const int n = cnt.get();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     out[i] = assoc[ids[i]];
@@ -156,6 +167,11 @@ extern "C" {
 
 int32_t tgn_abi_version(void) { return TGN_ABI_VERSION; }
 const char* tgn_last_error(void) { return tgn::err_buf(); }
+int32_t tgn_set_pdl(int32_t enabled) {
+  const int old = tgn::pdl_flag();
+  tgn::pdl_flag() = enabled ? 1 : 0;
+  return old;
+}
 
 int64_t tgn_bitmap_bytes(int64_t num_nodes) {
   if (num_nodes < 0) return 0;
@@ -170,7 +186,7 @@ int32_t tgn_unique_mark(const int64_t* ids, int32_t count, const int32_t* count_
   uint32_t* l0 = (uint32_t*)bitmap;
   uint32_t* l1 = l0 + l0_words(num_nodes);
   DevCount c{count_dev, count};
-  unique_mark_kernel<<<stride_grid(count, 256), 256, 0, (cudaStream_t)stream>>>(ids, c, num_nodes,
+  launch_k(unique_mark_kernel, dim3(stride_grid(count, 256)), dim3(256), 0, (cudaStream_t)stream, ids, c, num_nodes,
                                                                                  l0, l1);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
@@ -182,7 +198,7 @@ int32_t tgn_unique_rank(void* bitmap, int64_t num_nodes, int64_t* out_ids, int32
               "unique_rank: bad arguments");
   uint32_t* l0 = (uint32_t*)bitmap;
   uint32_t* l1 = l0 + l0_words(num_nodes);
-  unique_rank_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+  launch_k(unique_rank_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, 
       l0, l1, l0_groups(num_nodes), l1_words(num_nodes), out_ids, out_cap, assoc, out_count,
       keep_marks, nullptr, 0, num_nodes);
   TGN_LAUNCH_CHECK();
@@ -197,7 +213,7 @@ int32_t tgn_unique_mark_rank(const int64_t* ids, int32_t count, void* bitmap, in
               "unique_mark_rank: bad arguments");
   uint32_t* l0 = (uint32_t*)bitmap;
   uint32_t* l1 = l0 + l0_words(num_nodes);
-  unique_rank_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+  launch_k(unique_rank_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, 
       l0, l1, l0_groups(num_nodes), l1_words(num_nodes), out_ids, out_cap, assoc, out_count,
       keep_marks, ids, count, num_nodes);
   TGN_LAUNCH_CHECK();
@@ -210,7 +226,7 @@ int32_t tgn_relabel(const int64_t* ids, int32_t count, const int32_t* count_dev,
   if (count == 0) return TGN_OK;
   TGN_REQUIRE(ids && assoc && out, "relabel: NULL pointer");
   DevCount c{count_dev, count};
-  relabel_kernel<<<stride_grid(count, 256), 256, 0, (cudaStream_t)stream>>>(ids, c, assoc, out);
+  launch_k(relabel_kernel, dim3(stride_grid(count, 256)), dim3(256), 0, (cudaStream_t)stream, ids, c, assoc, out);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

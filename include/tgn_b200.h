@@ -219,6 +219,31 @@ int32_t tgn_msg_build_ld(const tgn_msgstore* st, const int64_t* n_id, int32_t nu
                          float* sin_out, void* lu_out, int32_t* sel_ev, float* sel_dt, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Owner-partitioned node memory (multi-GPU; memory_module.py:80-83 state split by node id).
+ * Node n lives on rank n % world at local row n / world.  tgn_part_gather writes, for every row
+ * s of n_id (all `num` rows; rows >= *num_dev are zero-filled), the memory row / last_update of
+ * n_id[s] and the memory row of the other endpoint of the event Last aggregation picks for it --
+ * but only where THIS rank owns them, zeros elsewhere -- so that a sum over ranks (one
+ * all-reduce) assembles every row on every rank.  tgn_msg_build_gathered is tgn_msg_build_ld on
+ * those assembled rows; tgn_memory_scatter_owned is the owner-side tgn_memory_scatter.
+ * ------------------------------------------------------------------------- */
+int32_t tgn_part_gather(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                        const int32_t* num_dev, const float* memory_local,
+                        const int64_t* last_update_local, int32_t memory_dim, int32_t rank,
+                        int32_t world, float* rows_n, float* rows_other, int64_t* lu_out,
+                        int64_t* other_out, void* stream);
+int32_t tgn_msg_build_gathered(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                               const int32_t* num_dev, const float* rows_n, const float* rows_other,
+                               const int64_t* last_update_rows, int32_t memory_dim,
+                               const float* time_w, const float* time_b, int32_t time_dim, float* x,
+                               int32_t ldx, float* h_out, float* sin_out, void* lu_out,
+                               int32_t* sel_ev, float* sel_dt, void* stream);
+int32_t tgn_memory_scatter_owned(const int64_t* n_id, int32_t num, const int32_t* num_dev,
+                                 const float* new_mem, const void* new_lu, int32_t lu_is_float,
+                                 const int64_t* src_rows, int32_t dim, int32_t rank, int32_t world,
+                                 float* memory_local, int64_t* last_update_local, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Dense fp32 building block: C[M,N] (=|+=) A[M,K] * B^T|B (+ bias).
  * a_rows (nullable) gathers rows of A:  A_m = A_base[a_rows[m], :].
  * trans_a: A stored [K,M]; trans_b: B stored [K,N] (else [N,K]).

@@ -356,3 +356,74 @@ def test_adam_matches_torch(ops):
         ops.adam_step(pg, g.to(DEV), m, v, step, 1e-3)
     torch.testing.assert_close(pg.cpu(), p.detach(), rtol=1e-5, atol=1e-6)
     assert float(step) == 5.0
+
+
+# ------------------------------------------------------------------ owner-partitioned memory
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_partitioned_memory_rows_assemble_exactly(ops, world):
+    """Emulates `world` ranks on one GPU: each rank's tgn_part_gather contribution is summed (what
+    the NCCL all-reduce does) and fed to tgn_msg_build_gathered; the result must equal
+    tgn_msg_build_ld on the unpartitioned table bit for bit.  Same for the owner-side write-back."""
+    import ctypes
+    from tgn_b200 import _cabi
+    L = _cabi.lib()
+    p = lambda t: None if t is None else t.data_ptr()
+    N, De, D, Dt, B = 257, 5, 16, 12, 64
+    rng = np.random.default_rng(world)
+    store = ops.MsgStore(N, De, DEV, capacity=4 * B, t_dtype=torch.int64)
+    for b in range(3):   # three batches: later batches overwrite the per-node runs of earlier ones
+        src = torch.from_numpy(rng.integers(0, N // 2, B)).to(DEV)
+        dst = torch.from_numpy(rng.integers(N // 2, N, B)).to(DEV)
+        t = torch.from_numpy(np.sort(rng.integers(100 * b, 100 * b + 50, B))).to(DEV)
+        store.update(src, dst, t, torch.from_numpy(rng.standard_normal((B, De)).astype(np.float32)).to(DEV))
+    memory = torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32)).to(DEV)
+    last_update = torch.from_numpy(rng.integers(0, 90, N)).to(DEV)
+    tw = torch.from_numpy(rng.standard_normal(Dt).astype(np.float32) * 0.01).to(DEV)
+    tb = torch.from_numpy(rng.standard_normal(Dt).astype(np.float32)).to(DEV)
+    n_id = torch.from_numpy(np.unique(rng.integers(0, N, 150))).to(DEV)
+    S = n_id.numel()
+    cnt = torch.tensor([S - 7], dtype=torch.int32, device=DEV)      # live rows < bound
+    ldx = 2 * D + De + Dt + 3
+    st = ctypes.byref(store.struct())
+
+    def outputs():
+        return (torch.zeros(S, ldx, device=DEV), torch.zeros(S, D, device=DEV), torch.zeros(S, Dt, device=DEV),
+                torch.zeros(S, dtype=torch.long, device=DEV), torch.zeros(S, dtype=torch.int32, device=DEV),
+                torch.zeros(S, device=DEV))
+    ref = outputs()
+    _cabi.check(L.tgn_msg_build_ld(st, p(n_id), S, p(cnt), 0, p(memory), p(last_update), D, p(tw), p(tb), Dt,
+                                   p(ref[0]), ldx, p(ref[1]), p(ref[2]), p(ref[3]), p(ref[4]), p(ref[5]), 0))
+    g_sum = torch.zeros(2, S, D, device=DEV)
+    lu_sum = torch.zeros(S, dtype=torch.long, device=DEV)
+    Nloc = (N + world - 1) // world
+    for r in range(world):
+        mem_loc = torch.zeros(Nloc, D, device=DEV)
+        lu_loc = torch.zeros(Nloc, dtype=torch.long, device=DEV)
+        own = memory[r::world]
+        mem_loc[:own.shape[0]] = own
+        lu_loc[:own.shape[0]] = last_update[r::world]
+        g = torch.full((2, S, D), 7.0, device=DEV)
+        lu = torch.full((S,), 7, dtype=torch.long, device=DEV)
+        _cabi.check(L.tgn_part_gather(st, p(n_id), S, p(cnt), p(mem_loc), p(lu_loc), D, r, world, p(g),
+                                      g.data_ptr() + 4 * S * D, p(lu), None, 0))
+        g_sum += g
+        lu_sum += lu
+    got = outputs()
+    _cabi.check(L.tgn_msg_build_gathered(st, p(n_id), S, p(cnt), p(g_sum), g_sum.data_ptr() + 4 * S * D, p(lu_sum),
+                                         D, p(tw), p(tb), Dt, p(got[0]), ldx, p(got[1]), p(got[2]), p(got[3]),
+                                         p(got[4]), p(got[5]), 0))
+    live = S - 7
+    for a, b in zip(ref, got):
+        assert torch.equal(a[:live], b[:live])
+    # owner-side write-back == tgn_memory_scatter on the full table
+    new_mem = torch.from_numpy(rng.standard_normal((S, D)).astype(np.float32)).to(DEV)
+    new_lu = torch.from_numpy(rng.integers(0, 1000, S)).to(DEV)
+    full_m, full_l = memory.clone(), last_update.clone()
+    ops.memory_scatter(n_id, new_mem, new_lu, full_m, full_l)
+    for r in range(world):
+        own = memory[r::world]
+        mem_loc = torch.zeros(Nloc, D, device=DEV); lu_loc = torch.zeros(Nloc, dtype=torch.long, device=DEV)
+        mem_loc[:own.shape[0]] = own; lu_loc[:own.shape[0]] = last_update[r::world]
+        _cabi.check(L.tgn_memory_scatter_owned(p(n_id), S, None, p(new_mem), p(new_lu), 0, None, D, r, world,
+                                               p(mem_loc), p(lu_loc), 0))
+        assert torch.equal(mem_loc[:own.shape[0]], full_m[r::world]) and torch.equal(lu_loc[:own.shape[0]], full_l[r::world])

@@ -213,7 +213,9 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
                                  const float* __restrict__ time_b, int Dt, float* __restrict__ x,
                                  int ldx, float* __restrict__ h_out, float* __restrict__ sin_out,
                                  T* __restrict__ lu_out, int32_t* __restrict__ sel_ev,
-                                 float* __restrict__ sel_dt) {
+                                 float* __restrict__ sel_dt, const float* __restrict__ gath_n,
+                                 const float* __restrict__ gath_o,
+                                 const int64_t* __restrict__ gath_lu) {
   pdl_wait();
   pdl_launch();
   const int lane = threadIdx.x & 31;
@@ -229,8 +231,10 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
     const bool ok = n >= 0 && n < st.num_nodes;
     const int sc = ok ? st.s_cnt[n] : 0, dc = ok ? st.d_cnt[n] : 0;
     for (int c = W + lane; c < ldx; c += 32) xr[c] = 0.f;  // row padding (TMA-aligned stride)
+    // owner-partitioned memory: rows / last_update come pre-assembled per row s (partition.cu)
+    const float* mn_src = gath_n ? gath_n + (long long)s * Dm : memory + (ok ? n : 0) * Dm;
     if (h_out)
-      for (int c = lane; c < Dm; c += 32) h_out[(long long)s * Dm + c] = ok ? memory[n * Dm + c] : 0.f;
+      for (int c = lane; c < Dm; c += 32) h_out[(long long)s * Dm + c] = ok ? mn_src[c] : 0.f;
     if (sc + dc == 0) {
       for (int c = lane; c < W; c += 32) xr[c] = 0.f;
       if (lane == 0) {
@@ -240,8 +244,8 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
       }
       continue;
     }
-    const int64_t lu = last_update[n];
-    const float* mn = memory + n * Dm;
+    const int64_t lu = gath_lu ? gath_lu[s] : last_update[n];
+    const float* mn = mn_src;
     if (agg_mode == TGN_AGG_LAST) {
       const int es = sc > 0 ? st.s_last[n] : -1, ed = dc > 0 ? st.d_last[n] : -1;
       T ts_ = es >= 0 ? ev_t[es] : (T)0, td_ = ed >= 0 ? ev_t[ed] : (T)0;
@@ -252,7 +256,7 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
       const T te = pick_s ? ts_ : td_;
       const int64_t other = pick_s ? st.ev_dst[e] : st.ev_src[e];
       const float dt = rel_time<T>(te, lu);
-      const float* mo = memory + other * Dm;
+      const float* mo = gath_o ? gath_o + (long long)s * Dm : memory + other * Dm;
       const float* rw = st.ev_msg + (long long)e * De;
       for (int c = lane; c < Dm; c += 32) {
         xr[c] = mn[c];
@@ -421,11 +425,13 @@ int32_t tgn_msgstore_gather(const tgn_msgstore* st, const int64_t* n_id, int32_t
   return TGN_OK;
 }
 
-int32_t tgn_msg_build_ld(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
-                         const int32_t* num_dev, int32_t agg_mode, const float* memory,
-                         const int64_t* last_update, int32_t memory_dim, const float* time_w,
-                         const float* time_b, int32_t time_dim, float* x, int32_t ldx, float* h_out,
-                         float* sin_out, void* lu_out, int32_t* sel_ev, float* sel_dt, void* stream) {
+static int32_t msg_build_impl(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                              const int32_t* num_dev, int32_t agg_mode, const float* memory,
+                              const int64_t* last_update, int32_t memory_dim, const float* time_w,
+                              const float* time_b, int32_t time_dim, float* x, int32_t ldx,
+                              float* h_out, float* sin_out, void* lu_out, int32_t* sel_ev,
+                              float* sel_dt, const float* gath_n, const float* gath_o,
+                              const int64_t* gath_lu, void* stream) {
   int32_t rc = check_store(st, "msg_build");
   if (rc) return rc;
   TGN_REQUIRE(num >= 0 && memory_dim >= 1 && time_dim >= 0, "msg_build: bad sizes");
@@ -441,13 +447,36 @@ int32_t tgn_msg_build_ld(const tgn_msgstore* st, const int64_t* n_id, int32_t nu
   if (st->t_is_float)
     launch_k(msg_build_kernel<float>, dim3(grid), dim3(256), 0, s, *st, n_id, c, agg_mode, memory, last_update,
                                                  memory_dim, time_w, time_b, time_dim, x, ldx, h_out,
-                                                 sin_out, (float*)lu_out, sel_ev, sel_dt);
+                                                 sin_out, (float*)lu_out, sel_ev, sel_dt, gath_n, gath_o, gath_lu);
   else
     launch_k(msg_build_kernel<int64_t>, dim3(grid), dim3(256), 0, s, *st, n_id, c, agg_mode, memory, last_update,
                                                    memory_dim, time_w, time_b, time_dim, x, ldx,
-                                                   h_out, sin_out, (int64_t*)lu_out, sel_ev, sel_dt);
+                                                   h_out, sin_out, (int64_t*)lu_out, sel_ev, sel_dt, gath_n, gath_o, gath_lu);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
+}
+
+int32_t tgn_msg_build_ld(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                         const int32_t* num_dev, int32_t agg_mode, const float* memory,
+                         const int64_t* last_update, int32_t memory_dim, const float* time_w,
+                         const float* time_b, int32_t time_dim, float* x, int32_t ldx, float* h_out,
+                         float* sin_out, void* lu_out, int32_t* sel_ev, float* sel_dt, void* stream) {
+  return msg_build_impl(st, n_id, num, num_dev, agg_mode, memory, last_update, memory_dim, time_w, time_b,
+                        time_dim, x, ldx, h_out, sin_out, lu_out, sel_ev, sel_dt, nullptr, nullptr,
+                        nullptr, stream);
+}
+
+int32_t tgn_msg_build_gathered(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                               const int32_t* num_dev, const float* rows_n, const float* rows_other,
+                               const int64_t* last_update_rows, int32_t memory_dim,
+                               const float* time_w, const float* time_b, int32_t time_dim, float* x,
+                               int32_t ldx, float* h_out, float* sin_out, void* lu_out,
+                               int32_t* sel_ev, float* sel_dt, void* stream) {
+  TGN_REQUIRE(rows_n && rows_other && last_update_rows, "msg_build_gathered: NULL gathered rows");
+  // the dense table arguments are unused in gathered mode; pass the row buffers to satisfy the checks
+  return msg_build_impl(st, n_id, num, num_dev, TGN_AGG_LAST, rows_n, last_update_rows, memory_dim,
+                        time_w, time_b, time_dim, x, ldx, h_out, sin_out, lu_out, sel_ev, sel_dt, rows_n,
+                        rows_other, last_update_rows, stream);
 }
 
 int32_t tgn_msg_build(const tgn_msgstore* st, const int64_t* n_id, int32_t num,

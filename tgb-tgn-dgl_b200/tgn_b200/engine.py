@@ -48,7 +48,7 @@ class TGNEngine:
     def __init__(self, num_nodes: int, raw_dim: int, hidden: int, size_k: int, batch_size: int,
                  device="cuda", lr: float = 1e-4, heads: int = 2, dropout: float = 0.1,
                  log_capacity: int = 1 << 20, seed: int = 0, use_graph: bool = True,
-                 precision: int = 3):
+                 precision: int = 3, rank: int = 0, world: int = 1, group=None):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("TGNEngine runs on CUDA only (no CPU fallback)")
@@ -65,6 +65,12 @@ class TGNEngine:
         self.Din = self.Dt + raw_dim                      # edge_attr width (emb_module.py:28)
         self.lde = _up4(self.Din)
         self.lr, self.dropout, self.seed, self.use_graph, self.prec = lr, dropout, seed, use_graph, precision
+        # owner-partitioned node memory (csrc/partition.cu): node n lives on rank n % world at local
+        # row n // world; ring, message store, weights and batches are replicated
+        if not (0 <= rank < world):
+            raise ValueError("rank must be in [0, world)")
+        self.rank, self.world, self.group = rank, world, group
+        self.Nloc = (num_nodes + world - 1) // world
         D, Dt, HC = self.D, self.Dt, self.HC
         # ---- parameters: one flat buffer (one Adam launch, one memset for all gradients).
         # (name, logical shape, leading dimension): padded columns stay zero for ever -- their
@@ -103,8 +109,8 @@ class TGNEngine:
             v.grad = self._view(self.flat_grad, name, shp)
             self.p[name] = v
         # ---- state
-        self.memory = torch.zeros((num_nodes, D), device=dev)
-        self.last_update = torch.zeros(num_nodes, dtype=torch.long, device=dev)
+        self.memory = torch.zeros((self.Nloc, D), device=dev)          # this rank's shard (all of it if world == 1)
+        self.last_update = torch.zeros(self.Nloc, dtype=torch.long, device=dev)
         self.assoc = torch.zeros(num_nodes, dtype=torch.long, device=dev)
         self.neighbors = torch.zeros((num_nodes, size_k), dtype=torch.long, device=dev)
         self.e_id = torch.full((num_nodes, size_k), -1, dtype=torch.long, device=dev)
@@ -163,6 +169,8 @@ class TGNEngine:
         w.x, w.h = f(Nb, self.ldx), f(Nb, D)
         w.lu, w.sel_ev, w.sel_dt = i64(Nb), i32(Nb), f(Nb)
         w.sn_m = f(Nb, max(self.Dt, 1)) if train else None
+        if self.world > 1:   # staging for the row assembly: [rows of n_id | rows of the other endpoints]
+            w.g_rows, w.g_lu = f(2, Nb, D), i64(Nb)
         w.gi, w.gh, w.z, w.gates = f(Nb, 3 * D), f(Nb, 3 * D), f(Nb, D), f(Nb, 4 * D)
         # attention
         w.proj = f(Nb, 4 * HC)
@@ -189,16 +197,17 @@ class TGNEngine:
             self.p["conv.lin_edge.weight"].copy_(g(gnn_sd, "conv.lin_edge.weight"))
             for k in ("lin_src.weight", "lin_src.bias", "lin_dst.weight", "lin_dst.bias", "lin_final.weight", "lin_final.bias"):
                 self.p[k].copy_(g(lp_sd, k))
-            if "memory" in memory_sd:
-                self.memory.copy_(memory_sd["memory"])
-                self.last_update.copy_(memory_sd["last_update"])
+            if "memory" in memory_sd:   # full [N,D] table: every rank keeps the rows it owns
+                self.memory.copy_(memory_sd["memory"].to(self.dev)[self.rank::self.world])
+                self.last_update.copy_(memory_sd["last_update"].to(self.dev)[self.rank::self.world])
 
     def export_state(self):
         HC = self.HC
         c = lambda k: self.p[k].detach().clone().contiguous()
         mem = {k: c(k) for k in ("time_enc.lin.weight", "time_enc.lin.bias", "memory_updater.weight_ih",
                                  "memory_updater.weight_hh", "memory_updater.bias_ih", "memory_updater.bias_hh")}
-        mem.update(memory=self.memory.clone(), last_update=self.last_update.clone(), _assoc=self.assoc.clone())
+        full_mem, full_lu = self.full_memory()
+        mem.update(memory=full_mem, last_update=full_lu, _assoc=self.assoc.clone())
         gnn = {"time_enc.lin.weight": mem["time_enc.lin.weight"], "time_enc.lin.bias": mem["time_enc.lin.bias"],
                "conv.lin_edge.weight": c("conv.lin_edge.weight")}
         for i, n in enumerate(("query", "key", "value", "skip")):
@@ -207,6 +216,23 @@ class TGNEngine:
         lp = {k: c(k) for k in ("lin_src.weight", "lin_src.bias", "lin_dst.weight", "lin_dst.bias",
                                 "lin_final.weight", "lin_final.bias")}
         return mem, gnn, lp
+
+    def full_memory(self):
+        """(memory [N,D], last_update [N]) reassembled from the shards (all-gather when partitioned)."""
+        if self.world == 1:
+            return self.memory.clone(), self.last_update.clone()
+        import torch.distributed as dist
+        mems = [torch.empty_like(self.memory) for _ in range(self.world)]
+        lus = [torch.empty_like(self.last_update) for _ in range(self.world)]
+        dist.all_gather(mems, self.memory, group=self.group)
+        dist.all_gather(lus, self.last_update, group=self.group)
+        full_mem = torch.stack(mems, 1).reshape(-1, self.D)[:self.N].contiguous()
+        full_lu = torch.stack(lus, 1).reshape(-1)[:self.N].contiguous()
+        return full_mem, full_lu
+
+    def _all_reduce(self, t: Tensor):
+        import torch.distributed as dist
+        dist.all_reduce(t, group=self.group)
 
     def reset_state(self):
         """memory.reset_state() + neighbor_loader.reset_state() (start of every epoch, pyg_epoch_utils.py:15-16)."""
@@ -301,13 +327,42 @@ class TGNEngine:
         check(L.tgn_relabel3(_p(w.nbr_g), w.E, _p(w.E_dev), _p(w.nbr_l), _p(w.roots), w.R, _p(w.R_dev),
                              _p(w.ctr_l), _p(ids), ids.numel(), None, _p(ids_l), _p(self.assoc), s))
 
+    def _assemble_rows(self, w, n_id: Tensor, S: int, S_dev: Optional[Tensor]):
+        """Partitioned memory: every rank writes the memory rows it owns (rows of n_id and of the
+        other endpoints of their stored events) into the zero-filled staging buffer; one all-reduce
+        over NVLink/NVSwitch assembles all of them on every rank.  w.g_rows [2,Nb,D], w.g_lu [Nb]."""
+        D = self.D
+        if S > w.g_rows.shape[1]:
+            raise _cabi.TgnError("row assembly: workspace too small")
+        check(_L().tgn_part_gather(ctypes.byref(self.store.struct()), _p(n_id), S, _p(S_dev), _p(self.memory),
+                                   _p(self.last_update), D, self.rank, self.world, _p(w.g_rows),
+                                   w.g_rows.data_ptr() + 4 * w.g_rows.shape[1] * D, _p(w.g_lu), None, _stream()))
+        self._all_reduce(w.g_rows)
+        self._all_reduce(w.g_lu)
+
+    def _scatter_owned(self, n_id: Tensor, new_mem: Tensor, new_lu: Tensor, memory: Tensor, last_update: Tensor,
+                       src_rows: Optional[Tensor] = None):
+        if self.world == 1:
+            ops.memory_scatter(n_id, new_mem, new_lu, memory, last_update, src_rows=src_rows)
+        else:
+            check(_L().tgn_memory_scatter_owned(_p(n_id), n_id.numel(), None, _p(new_mem), _p(new_lu), 0, _p(src_rows),
+                                                self.D, self.rank, self.world, _p(memory), _p(last_update), _stream()))
+
     def _memory_fwd(self, w, n_id: Tensor, S: int, S_dev: Optional[Tensor]):
         """TGNMemory._get_updated_memory (memory_module.py:152-178): w.z [S,D], w.lu [S]."""
         p, D, L, s = self.p, self.D, _L(), _stream()
-        check(L.tgn_msg_build_ld(ctypes.byref(self.store.struct()), _p(n_id), S, _p(S_dev), ops.AGG_LAST,
-                                 _p(self.memory), _p(self.last_update), D, _p(p["time_enc.lin.weight"]),
-                                 _p(p["time_enc.lin.bias"]), self.Dt, _p(w.x), self.ldx, _p(w.h), _p(w.sn_m), _p(w.lu),
-                                 _p(w.sel_ev), _p(w.sel_dt), s))
+        if self.world == 1:
+            check(L.tgn_msg_build_ld(ctypes.byref(self.store.struct()), _p(n_id), S, _p(S_dev), ops.AGG_LAST,
+                                     _p(self.memory), _p(self.last_update), D, _p(p["time_enc.lin.weight"]),
+                                     _p(p["time_enc.lin.bias"]), self.Dt, _p(w.x), self.ldx, _p(w.h), _p(w.sn_m),
+                                     _p(w.lu), _p(w.sel_ev), _p(w.sel_dt), s))
+        else:
+            self._assemble_rows(w, n_id, S, S_dev)
+            check(L.tgn_msg_build_gathered(ctypes.byref(self.store.struct()), _p(n_id), S, _p(S_dev), _p(w.g_rows),
+                                           w.g_rows.data_ptr() + 4 * w.g_rows.shape[1] * D, _p(w.g_lu), D,
+                                           _p(p["time_enc.lin.weight"]), _p(p["time_enc.lin.bias"]), self.Dt,
+                                           _p(w.x), self.ldx, _p(w.h), _p(w.sn_m), _p(w.lu), _p(w.sel_ev),
+                                           _p(w.sel_dt), _stream()))
         self._timed("gru_gate_gemm", lambda: ops.gemm_batch([
             ops.gemm_desc(w.x, self.flat, w.gi, m=S, n=3 * D, k=self.Dx, lda=self.ldx, ldb=self.ldx, ldc=3 * D,
                           b_off=self.off["memory_updater.weight_ih"], bias=p["memory_updater.bias_ih"], m_dev=S_dev),
@@ -337,8 +392,8 @@ class TGNEngine:
         Train ordering: memory rows first (they are the rows the forward just produced: same
         store, same weights), then the store, then the ring."""
         B = self.B
-        ops.memory_scatter(self.in_ids3[:2 * B], w.z, w.lu, self.memory, self.last_update,
-                           src_rows=w.ids_l[:2 * B])
+        self._scatter_owned(self.in_ids3[:2 * B], w.z, w.lu, self.memory, self.last_update,
+                            src_rows=w.ids_l[:2 * B])
         self.store.update(self.in_ids3[:B], self.in_ids3[B:2 * B], self.in_t_i64, self.in_msg,
                           base_dev=self.log_base_dev)
         check(_L().tgn_nbr_insert(_p(self.in_ids3), self.in_ids3[B:].data_ptr(), _p(self.in_t_f32), B, 0,
@@ -441,6 +496,9 @@ class TGNEngine:
                                      w.d_x.data_ptr() + 4 * (2 * D + self.De), self.ldx,
                                      gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), s))
         main.wait_stream(self.side)
+        if self.world > 1:   # replicated compute: average the gradients so the weight replicas stay bit-identical
+            self._all_reduce(self.flat_grad)
+            self.flat_grad.mul_(1.0 / self.world)
         check(L.tgn_adam_finish(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
                                 self.n_param, self.lr, 0.9, 0.999, 1e-8, _p(self.adam_step_dev), _p(self.step_dev),
                                 _p(self.loss_acc), _p(self.loss), _stream()))
@@ -503,9 +561,14 @@ class TGNEngine:
         ids_l = torch.empty_like(ids)
         self._sample(w, ids, ids_l)
         s = _stream()
-        check(L.tgn_gather_rows(_p(self.memory), _p(w.n_id), w.Nb, _p(w.Nb_dev), D, _p(w.z), s))
-        check(L.tgn_relabel(_p(w.n_id), w.Nb, _p(w.Nb_dev), _p(self.last_update), _p(w.lu), s))
-        self._attention_fwd(w, w.z, w.lu, False)
+        if self.world == 1:
+            check(L.tgn_gather_rows(_p(self.memory), _p(w.n_id), w.Nb, _p(w.Nb_dev), D, _p(w.z), s))
+            check(L.tgn_relabel(_p(w.n_id), w.Nb, _p(w.Nb_dev), _p(self.last_update), _p(w.lu), s))
+            z_in, lu_in = w.z, w.lu
+        else:
+            self._assemble_rows(w, w.n_id, w.Nb, w.Nb_dev)
+            z_in, lu_in = w.g_rows[0], w.g_lu
+        self._attention_fwd(w, z_in, lu_in, False)
         p, off = self.p, self.off
         ops.gemm_batch([
             ops.gemm_desc(w.emb, self.flat, w.hs, m=Nb, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_src.weight"],
@@ -529,7 +592,7 @@ class TGNEngine:
         if getattr(self, "_mw_cap", 0) < S:
             self._mw, self._mw_cap = self._alloc_work(1, 1, max(S, 2 * B), 1, train=False), max(S, 2 * B)
         self._memory_fwd(self._mw, n_upd, S, None)
-        ops.memory_scatter(n_upd, self._mw.z, self._mw.lu, self.memory, self.last_update)
+        self._scatter_owned(n_upd, self._mw.z, self._mw.lu, self.memory, self.last_update)
         ops.nbr_insert(src, dst, t_i.to(torch.float32), 0, self.neighbors, self.e_id, self.t_ring,
                        cur_e_id_dev=self.cur_e_id_dev)
         return pos, negs, gt, ge
@@ -543,16 +606,14 @@ class TGNEngine:
     def flush_to_eval(self):
         """TGNMemory.train(False) (memory_module.py:209-215): every node goes through the updater
         with its stored messages, then the store is cleared."""
-        new_mem = torch.empty_like(self.memory)
-        new_lu = torch.empty_like(self.last_update)
+        new_mem = torch.zeros_like(self.memory)
+        new_lu = torch.zeros_like(self.last_update)
         chunk = 1 << 16
         wm = self._alloc_work(1, 1, min(self.N, chunk), 1, train=False)
         for lo in range(0, self.N, chunk):
             ids = torch.arange(lo, min(self.N, lo + chunk), device=self.dev)
-            n = ids.numel()
-            self._memory_fwd(wm, ids, n, None)
-            new_mem[lo:lo + n] = wm.z[:n]
-            new_lu[lo:lo + n] = wm.lu[:n]
+            self._memory_fwd(wm, ids, ids.numel(), None)
+            self._scatter_owned(ids, wm.z, wm.lu, new_mem, new_lu)
         self.memory.copy_(new_mem)
         self.last_update.copy_(new_lu)
         self.store.reset()

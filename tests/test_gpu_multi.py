@@ -15,5 +15,5 @@ def test_partitioned_engine_matches_single_gpu():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533",
                         os.path.join(REPO, "tests", "dist_partition_check.py")],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "partition check OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

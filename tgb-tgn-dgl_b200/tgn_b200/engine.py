@@ -198,8 +198,11 @@ class TGNEngine:
             for k in ("lin_src.weight", "lin_src.bias", "lin_dst.weight", "lin_dst.bias", "lin_final.weight", "lin_final.bias"):
                 self.p[k].copy_(g(lp_sd, k))
             if "memory" in memory_sd:   # full [N,D] table: every rank keeps the rows it owns
-                self.memory.copy_(memory_sd["memory"].to(self.dev)[self.rank::self.world])
-                self.last_update.copy_(memory_sd["last_update"].to(self.dev)[self.rank::self.world])
+                own = memory_sd["memory"].to(self.dev)[self.rank::self.world]
+                self.memory.zero_()
+                self.last_update.zero_()
+                self.memory[:own.shape[0]].copy_(own)
+                self.last_update[:own.shape[0]].copy_(memory_sd["last_update"].to(self.dev)[self.rank::self.world])
 
     def export_state(self):
         HC = self.HC

@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=400, help="bounded sample of the CPU baseline leg")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     ap.add_argument("--no-eval-dp", action="store_true")
+    ap.add_argument("--no-partitioned", action="store_true")
     ap.add_argument("--eval-batches", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=int, default=3, choices=[1, 3],
@@ -268,6 +269,9 @@ def main():
     roof = dominant_kernel_roofline(eng, dev)
     eng.use_graph = eng_use_graph
 
+    part = None
+    if not args.no_partitioned:
+        part = bench_partitioned(dev, rank, world, min(K_steps, 300), W, args.precision)
     eval_dp = None
     if not args.no_eval_dp:
         eval_dp = bench_eval_dp(dev, rank, world, args.eval_batches, args.precision)
@@ -291,6 +295,8 @@ def main():
                 "top_kernels_eager_us": {k: [v[0], round(v[1], 1)] for k, v in top},
                 "clocks": clocks.summary(), "final_loss": {"device_arm": loss_dev, "e2e_arm": loss_host},
                 "roofline": roof_with_peak(roof, peaks)}
+        if part is not None:
+            line["partitioned_memory"] = part
         if eval_dp is not None:
             line["eval_dp"] = eval_dp
         if world == 1 and not args.no_kernel_rooflines:
@@ -304,9 +310,60 @@ def main():
                                     "sample": f"{done} training steps ({done * B} events) of the same workload (same "
                                               "shape, batch, prefill) on the host CPU: oracle port of the reference's "
                                               "torch-CPU path incl. its Python-dict message store"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL kernels: leave without the collective shutdown (it can block)
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
+
+
+def bench_partitioned(dev, rank, world, steps, warmup, precision):
+    """ONE training job with the node memory partitioned by owner over the ranks (BASELINE.json
+    configs[2]): synthetic tgbl-coin shape (638,486 nodes), batch 600, K=10.  Node n lives on rank
+    n % world; the rows a step needs are assembled on every rank by one all-reduce over
+    NVLink/NVSwitch (csrc/partition.cu), gradients are all-reduced, everything else is replicated.
+    value = events/s of that one job (strong scaling: the batch does not grow with the ranks)."""
+    import torch.distributed as dist
+    from tgn_b200 import synth
+    from tgn_b200.engine import TGNEngine
+    name, prefill = "tgbl-coin", 600_000
+    cfg = synth.SHAPES[name]
+    B, K = cfg["B"], cfg["K"]
+    data = synth.synth_events(name, seed=0, max_events=prefill + (warmup + steps + 8) * B)
+    N, De = data["num_nodes"], data["raw_dim"]
+    eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.1, use_graph=True,
+                    log_capacity=data["src"].size, seed=99, precision=precision, rank=rank, world=world)
+    eng.load_state(*init_state_dicts(De, HIDDEN, N, seed=1))
+    eng.set_events(**{k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")})
+    ring = ring_after(data["src"][:prefill], data["dst"][:prefill], data["t"][:prefill], K, N)
+    eng.prefill(prefill, tuple(torch.from_numpy(a) for a in ring))
+    for _ in range(max(warmup, 6)):
+        eng.train_step(from_device=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.train_step(from_device=True)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    rows = int(eng.w.Nb_dev.item())
+    return {"metric": "train events/sec (TGN step), node memory partitioned by owner", "value": steps * B / (ms / 1e3),
+            "unit": "events/s", "n_gpus": world, "ms_per_step": ms / steps, "steps": steps, "scaling": "strong",
+            "final_loss": float(eng.loss), "rows_per_step": rows,
+            "memory_rows_per_gpu": eng.Nloc, "memory_bytes_per_gpu": eng.Nloc * HIDDEN * 4,
+            "workload": f"synthetic {name} shape: {N} nodes, raw_dim {De}, batch {B}, {K} recent nbrs, dim {HIDDEN}",
+            "collectives_per_step": ("all-reduce of the assembled rows [2,Nb,D] fp32 + last_update [Nb] int64, "
+                                     "all-reduce of the flat gradient") if world > 1 else "none (single GPU)"}
 
 
 def bench_eval_dp(dev, rank, world, n_batches, precision):

@@ -163,7 +163,8 @@ def main():
     config = {"workload": f"synthetic {WORKLOAD} shape: {cfg['N']} nodes, raw_dim {cfg['De']}, batch {B}, "
                           f"{K} recent nbrs, dim {HIDDEN}, Adam lr {LR}, ring prefilled with {args.prefill} events",
               "l2": "inputs differ every step (new batch, new ring/memory rows); weights (~1.2 MB) stay L2-resident by design",
-              "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (step does not shard across batches)"}
+              "parallelism": ("host CPU" if args.impl == "reference" else "single GPU") if world == 1
+              else f"{world} independent replicas (step does not shard across batches)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -441,7 +442,11 @@ def roof_with_peak(r, peaks):
     peak = peaks.get("bf16_tflops", 1590.0)
     ach = r["flops"] / r["seconds"] / 1e12
     return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "traffic": None, "kernel": r["kernel"], "rows_per_launch": r["rows"], "us_per_launch": r["seconds"] * 1e6,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE such launch (ncu --set full on
+            # `tools/kernel_probe.py gru_pair`, profiles/r01_tgemm_gru_pair_instep.txt): operands are read once,
+            # the 12 MB of gate pre-activations stay in the 126 MB L2 for the gate kernel that follows
+            "traffic": 8642304, "traffic_source": "profiles/r01_tgemm_gru_pair_instep.txt",
+            "kernel": r["kernel"], "rows_per_launch": r["rows"], "us_per_launch": r["seconds"] * 1e6,
             "launches_timed": r["launches_timed"],
             "algorithmic_flops_per_launch": r["flops"], "algorithmic_bytes_per_launch": r["bytes"],
             "achieved_gbs": r["bytes"] / r["seconds"] / 1e9,

@@ -10,7 +10,17 @@ which = sys.argv[1]
 dev = "cuda"
 g = torch.Generator(device="cpu").manual_seed(0)
 N = 352_637
-if which.startswith("gemm"):
+if which == "gru_pair":
+    # the step's heaviest launch: gi = x W_ih^T + b_ih and gh = h W_hh^T + b_hh in one tgn_gemm_batch
+    S, Dx, ldx, D = 5_023, 301, 304, 100
+    x = torch.randn(S, ldx, device=dev); h = torch.randn(S, D, device=dev)
+    wih = torch.randn(3 * D, ldx, device=dev); whh = torch.randn(3 * D, D, device=dev)
+    bi = torch.randn(3 * D, device=dev); bh = torch.randn(3 * D, device=dev)
+    gi = torch.empty(S, 3 * D, device=dev); gh = torch.empty(S, 3 * D, device=dev)
+    fn = lambda: ops.gemm_batch([
+        ops.gemm_desc(x, wih, gi, m=S, n=3 * D, k=Dx, lda=ldx, ldb=ldx, ldc=3 * D, bias=bi),
+        ops.gemm_desc(h, whh, gh, m=S, n=3 * D, k=D, lda=D, ldb=D, ldc=3 * D, bias=bh)], 3)
+elif which.startswith("gemm"):
     # gemm3 / gemm1 [ _ld480 : rows padded to a multiple of 128 bytes ] [ _small : 5,023 rows as in the step ]
     S, Dx, D = (5_023 if "small" in which else 65_536), 472, 100
     ld = 480 if "ld480" in which else Dx

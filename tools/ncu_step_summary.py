@@ -1,6 +1,6 @@
 """Summarises an `ncu --metrics gpu__time_duration.sum --csv` launch list of bench.py:
 per-kernel share of ONE steady-state training step (the launches between two
-tgn::unique_mark_kernel launches)."""
+tgn::msg_build_kernel launches; the cycle is one full step, rotated)."""
 import collections, csv, re, sys
 path = sys.argv[1]
 which = int(sys.argv[2]) if len(sys.argv) > 2 else -3
@@ -9,7 +9,7 @@ lines = [l for l in open(path) if l.startswith('"')]
 r = csv.reader(lines); hdr = next(r)
 ki, vi, gi = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Grid Size')
 data = [(row[ki], float(row[vi].replace(',', '')), row[gi]) for row in r]
-starts = [i for i, d in enumerate(data) if 'unique_mark_kernel' in d[0]]
+starts = [i for i, d in enumerate(data) if 'msg_build_kernel' in d[0]]
 step = data[starts[which]:starts[which + 1]]
 tot = sum(v for _, v, _ in step)
 print(f"launches in step: {len(step)}   sum of kernel durations: {tot/1000:.1f} us (ncu: serialised, cold caches)")

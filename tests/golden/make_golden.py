@@ -205,6 +205,36 @@ def gen_embedding(path):
     np.savez_compressed(path, **out)
 
 
+def gen_callers(path):
+    """Host-side callers that import as-is from the reference: dependencyGraph.get_block
+    (dependencyGraph.py:8-28), temporal_dataset.TemporalGraphDataset items (temporal_dataset.py:34-57)
+    collated by torch's DataLoader exactly as utils.py:52-54 does."""
+    from dependencyGraph import get_block
+    from temporal_dataset import TemporalGraphDataset
+    from torch.utils.data import DataLoader
+    rng = np.random.default_rng(11)
+    out = {}
+    cases = [(1, 5), (7, 3), (200, 40), (200, 400), (64, 2)]
+    for c, (B, N) in enumerate(cases):
+        src = rng.integers(0, N, B); dst = rng.integers(0, N, B)
+        t = np.sort(rng.integers(0, 1000, B)).astype(np.float32)
+        blocks = get_block(torch.from_numpy(t), torch.from_numpy(src), torch.from_numpy(dst))
+        out[f"b{c}_src"], out[f"b{c}_dst"], out[f"b{c}_t"] = src, dst, t
+        out[f"b{c}_blocks"] = np.asarray(blocks, dtype=np.int64)
+    out["num_block_cases"] = np.int64(len(cases))
+    E, De, bs = 23, 3, 5
+    src = torch.from_numpy(rng.integers(0, 9, E)); dst = torch.from_numpy(rng.integers(9, 18, E))
+    t = torch.from_numpy(np.sort(rng.integers(0, 500, E))); msg = torch.from_numpy(rng.standard_normal((E, De)).astype(np.float32))
+    blk = list(range(E))
+    for tag, ds in (("plain", TemporalGraphDataset(src, dst, t, msg)), ("blk", TemporalGraphDataset(src, dst, t, msg, batch=blk))):
+        for i, batch in enumerate(DataLoader(ds, batch_size=bs, shuffle=False)):
+            for k, v in batch.items():
+                out[f"dl_{tag}_{i}_{k}"] = v.numpy()
+        out[f"dl_{tag}_batches"] = np.int64(i + 1)
+    out["dl_src"], out["dl_dst"], out["dl_t"], out["dl_msg"], out["dl_bs"] = src.numpy(), dst.numpy(), t.numpy(), msg.numpy(), np.int64(bs)
+    np.savez_compressed(path, **out)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("reference tree not present: golden vectors can only be regenerated where /root/reference exists")
@@ -213,6 +243,7 @@ if __name__ == "__main__":
     gen_aggregators(os.path.join(HERE, "aggregators.npz"))
     gen_memory(os.path.join(HERE, "memory.npz"))
     gen_embedding(os.path.join(HERE, "embedding.npz"))
+    gen_callers(os.path.join(HERE, "callers.npz"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

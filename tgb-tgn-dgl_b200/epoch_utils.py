@@ -70,7 +70,7 @@ def train(model, feats, train_loader, neighbor_loader, neg_dest_sampler, assoc, 
         loss.backward()
         optimizer.step()
         model["memory"].detach()
-        total_loss += float(loss) * src.shape[0]
+        total_loss += float(loss.detach()) * src.shape[0]
     return total_loss
 
 
@@ -90,8 +90,8 @@ def test(model, feats, loader, neighbor_loader, neg_sampler, assoc, device, opti
         z, a = _embed(model, neighbor_loader, feats_dev, [s, d, n.reshape(-1)], device)
         pos_out = model["link_pred"](z[a[s]], z[a[d]])
         neg_out = model["link_pred"](z[a[s]].repeat_interleave(min_size, 0), z[a[n.reshape(-1)]])
-        input_dict = {"y_pred_pos": np.array(pos_out.reshape(-1).cpu()),
-                      "y_pred_neg": np.array(neg_out.reshape(s.numel(), -1).cpu()),
+        input_dict = {"y_pred_pos": pos_out.reshape(-1).cpu().numpy(),
+                      "y_pred_neg": neg_out.reshape(s.numel(), -1).cpu().numpy(),
                       "eval_metric": [metric]}
         perf_list.append(evaluator.eval(input_dict)[metric])
         model["memory"].update_state(s, d, t.to(device).long(), msg.to(device, torch.float32))

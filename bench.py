@@ -159,7 +159,7 @@ def main():
     from tgn_b200 import synth
     cfg = synth.SHAPES[WORKLOAD]
     B, K = cfg["B"], cfg["K"]
-    need = args.prefill + (2 * (W + K_steps) + 8) * B
+    need = args.prefill + (2 * (W + K_steps) + 80) * B
     config = {"workload": f"synthetic {WORKLOAD} shape: {cfg['N']} nodes, raw_dim {cfg['De']}, batch {B}, "
                           f"{K} recent nbrs, dim {HIDDEN}, Adam lr {LR}, ring prefilled with {args.prefill} events",
               "l2": "inputs differ every step (new batch, new ring/memory rows); weights (~1.2 MB) stay L2-resident by design",
@@ -224,21 +224,24 @@ def main():
 
     # ---------------- end-to-end arm: host batches, H2D every step, loss read back every step
     pos = eng.events_done
-    pack = torch.empty(((W + K_steps), 4 * B), dtype=torch.long).pin_memory()
-    msgs = torch.empty(((W + K_steps), B, max(De, 1)), dtype=torch.float32).pin_memory()
-    for s in range(W + K_steps):
+    n_host = W + K_steps + 1                       # one batch of lookahead
+    pack = torch.empty((n_host, 4 * B), dtype=torch.long).pin_memory()
+    msgs = torch.empty((n_host, B, max(De, 1)), dtype=torch.float32).pin_memory()
+    for s in range(n_host):
         sl = slice(pos + s * B, pos + (s + 1) * B)
         pack[s] = torch.cat([ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl]])
         msgs[s] = ev["msg"][sl]
+    # prefetching loader pattern: batch s+1 is copied H2D (and sampled on the forked stream) while batch s trains
+    eng.stage_packed(pack[0], msgs[0])
     for s in range(W):
-        eng.stage_packed(pack[s], msgs[s])
-        float(eng.train_step(from_device=False))
+        eng.stage_packed(pack[s + 1], msgs[s + 1], ahead=True)
+        float(eng.train_step(from_device=False, lookahead=True))
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for s in range(W, W + K_steps):
-        eng.stage_packed(pack[s], msgs[s])
-        loss_host = float(eng.train_step(from_device=False))
+        eng.stage_packed(pack[s + 1], msgs[s + 1], ahead=True)
+        loss_host = float(eng.train_step(from_device=False, lookahead=True))
     f1.record()
     barrier()
     clocks.stop_flag = True

@@ -473,10 +473,11 @@ int32_t tgn_scatter_add_rows(const float* src, const int64_t* rows, int32_t num,
 /* Batch staging (replaces the host DataLoader walk, temporal_dataset.py:34-57 +
  * epoch_utils.py:186-215): slices events [*pos_dev, *pos_dev + batch) of the
  * resident event arrays into ids3 = [src|dst|neg] (int64 [3*batch]), t_i64, t_f32 and
- * msg [batch, raw_dim], then advances *pos_dev by batch. */
+ * msg [batch, raw_dim], then advances *pos_dev by batch.  Events at or past num_events are replaced
+ * by a filler (node 0, t 0, zero message) so that a pipelined step may pre-load one batch ahead. */
 int32_t tgn_batch_load(const int64_t* src_all, const int64_t* dst_all, const int64_t* neg_all,
                        const int64_t* t_all, const float* msg_all, int32_t raw_dim, int32_t batch,
-                       int64_t* pos_dev, int64_t* ids3, int64_t* t_i64, float* t_f32, float* msg,
+                       int64_t num_events, int64_t* pos_dev, int64_t* ids3, int64_t* t_i64, float* t_f32, float* msg,
                        void* stream);
 
 /* LinkPredictor forward (decoder.py:24-27) on gathered rows:

@@ -111,17 +111,26 @@ def test_free_running_training_tracks_oracle():
 
 
 def test_host_staged_batches_equal_device_staged():
+    """three ways to feed the same batches: resident arrays (pipelined), host staging, host staging with
+    one batch of lookahead (the next batch is sampled on the forked stream while the current one trains)"""
     N, De, D, K, B, steps = 300, 8, 16, 4, 32, 8
     _, eng_a, ev = _setup(N, De, D, K, B, B * steps, 11, True)
     _, eng_b, _ = _setup(N, De, D, K, B, B * steps, 11, True)
+    _, eng_c, _ = _setup(N, De, D, K, B, B * steps, 11, True)
     pin = {k: v.pin_memory() for k, v in ev.items()}
+    batch = lambda s: tuple(pin[k][s * B:(s + 1) * B] for k in ("src", "dst", "neg", "t", "msg"))
+    eng_c.stage_batch(*batch(0))
     for s in range(steps):
-        sl = slice(s * B, (s + 1) * B)
         la = float(eng_a.train_step(from_device=True))
-        eng_b.stage_batch(pin["src"][sl], pin["dst"][sl], pin["neg"][sl], pin["t"][sl], pin["msg"][sl])
+        eng_b.stage_batch(*batch(s))
         lb = float(eng_b.train_step(from_device=False))
-        assert abs(la - lb) < 1e-4, (s, la, lb)   # atomics in the gradient reductions: not bitwise
+        eng_c.stage_batch(*batch(min(s + 1, steps - 1)), ahead=True)
+        lc = float(eng_c.train_step(from_device=False, lookahead=True))
+        assert abs(la - lb) < 1e-4 and abs(la - lc) < 1e-4, (s, la, lb, lc)   # atomics in the gradient reductions: not bitwise
     torch.testing.assert_close(eng_a.memory, eng_b.memory, rtol=1e-2, atol=1e-3)
+    torch.testing.assert_close(eng_a.memory, eng_c.memory, rtol=1e-2, atol=1e-3)
+    assert torch.equal(eng_a.e_id, eng_b.e_id) and torch.equal(eng_a.e_id, eng_c.e_id)
+    assert torch.equal(eng_a.last_update, eng_c.last_update)
 
 
 def test_eval_mrr_matches_oracle():

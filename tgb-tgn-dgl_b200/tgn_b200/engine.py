@@ -123,13 +123,15 @@ class TGNEngine:
         self.step_dev = torch.zeros(1, dtype=torch.long, device=dev)       # dropout stream
         self.events_done = 0
         self.events = None
-        self.side = torch.cuda.Stream(device=dev)
+        self.side = torch.cuda.Stream(device=dev)    # state update + sampling of the NEXT batch
+        self.aux = torch.cuda.Stream(device=dev)     # edge branch of the attention / small reductions
         self.w = self._alloc_work(R, E, Nb, batch_size)
-        self.in_i64 = torch.zeros(4 * batch_size, dtype=torch.long, device=dev)  # [src|dst|neg|t]
-        self.in_ids3 = self.in_i64[:3 * batch_size]
-        self.in_t_i64 = self.in_i64[3 * batch_size:]
-        self.in_t_f32 = torch.zeros(batch_size, device=dev)
-        self.in_msg = torch.zeros((batch_size, max(raw_dim, 1)), device=dev)
+        # two slots of {batch inputs, sampling results}: while step i runs on slot `cur`, the forked
+        # stream already loads and samples batch i+1 into the other slot (software pipelining)
+        self.slots = [self._alloc_slot(R, E, Nb, batch_size) for _ in range(2)]
+        self.cur = 0
+        self._primed = None      # "device" / "host": slots[cur] holds a staged AND sampled batch
+        self._bind(0)
         self.loss = torch.zeros((), device=dev)
         self.bounds = (R, E, Nb)
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
@@ -159,12 +161,7 @@ class TGNEngine:
         i64 = lambda *s: torch.zeros(s, dtype=torch.long, device=dev)
         i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)
         w = SimpleNamespace(R=R, E=E, Nb=Nb, B=B)
-        w.roots, w.R_dev = i64(R), i32(1)
-        w.nbr_g, w.ctr_g, w.eid, w.t_e = i64(E), i64(E), i64(E), f(E)
-        w.root_off, w.E_dev = i32(R + 1), i32(1)
-        w.lookup_ws = i64(max(_L().tgn_nbr_lookup_ws_bytes(R, self.K), 16) // 8)
-        w.n_id, w.Nb_dev = i64(Nb), i32(1)
-        w.nbr_l, w.ctr_l = i64(E), i64(R)
+        self._alloc_sample_fields(w, R, E, Nb)
         # memory forward
         w.x, w.h = f(Nb, self.ldx), f(Nb, D)
         w.lu, w.sel_ev, w.sel_dt = i64(Nb), i32(Nb), f(Nb)
@@ -177,12 +174,52 @@ class TGNEngine:
         w.ea, w.sn_e, w.rel = f(E, self.lde), f(E, max(self.Dt, 1)), f(E)
         w.ee, w.alpha, w.emb = f(E, HC), f(E, H), f(Nb, HC)
         if train:
-            w.ids_l = i64(3 * B)
             w.zcat, w.hcat, w.dhcat, w.dzcat = f(3 * B, D), f(3 * B, D), f(3 * B, D), f(3 * B, D)
             w.logits = f(2 * B)
             w.d_proj, w.d_ee, w.d_eat = f(Nb, 4 * HC), f(E, HC), f(E, max(self.Dt, 1))
             w.d_z, w.d_gi, w.d_gh, w.d_x = f(Nb, D), f(Nb, 3 * D), f(Nb, 3 * D), f(Nb, self.ldx)
         return w
+
+    _SAMPLE_FIELDS = ("roots", "R_dev", "nbr_g", "ctr_g", "eid", "t_e", "root_off", "E_dev", "lookup_ws", "n_id",
+                      "Nb_dev", "nbr_l", "ctr_l")
+    _SLOT_FIELDS = _SAMPLE_FIELDS + ("ids_l", "in_i64", "in_ids3", "in_t_i64", "in_t_f32", "in_msg")
+
+    def _alloc_sample_fields(self, w, R: int, E: int, Nb: int):
+        dev = self.dev
+        f = lambda *s: torch.zeros(s, device=dev)
+        i64 = lambda *s: torch.zeros(s, dtype=torch.long, device=dev)
+        i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)
+        w.roots, w.R_dev = i64(R), i32(1)
+        w.nbr_g, w.ctr_g, w.eid, w.t_e = i64(E), i64(E), i64(E), f(E)
+        w.root_off, w.E_dev = i32(R + 1), i32(1)
+        w.lookup_ws = i64(max(_L().tgn_nbr_lookup_ws_bytes(R, self.K), 16) // 8)
+        w.n_id, w.Nb_dev = i64(Nb), i32(1)
+        w.nbr_l, w.ctr_l = i64(E), i64(R)
+
+    def _alloc_slot(self, R: int, E: int, Nb: int, B: int) -> SimpleNamespace:
+        dev = self.dev
+        sl = SimpleNamespace(R=R, E=E, Nb=Nb, B=B)
+        self._alloc_sample_fields(sl, R, E, Nb)
+        sl.ids_l = torch.zeros(3 * B, dtype=torch.long, device=dev)
+        sl.in_i64 = torch.zeros(4 * B, dtype=torch.long, device=dev)      # [src | dst | neg | t]: one H2D copy
+        sl.in_ids3, sl.in_t_i64 = sl.in_i64[:3 * B], sl.in_i64[3 * B:]
+        sl.in_t_f32 = torch.zeros(B, device=dev)
+        sl.in_msg = torch.zeros((B, max(self.De, 1)), device=dev)
+        return sl
+
+    def _bind(self, idx: int):
+        """Points the step workspace (and the in_* attributes) at slot `idx`."""
+        sl = self.slots[idx]
+        for k in self._SLOT_FIELDS:
+            setattr(self.w, k, getattr(sl, k))
+        self.in_i64, self.in_ids3, self.in_t_i64 = sl.in_i64, sl.in_ids3, sl.in_t_i64
+        self.in_t_f32, self.in_msg = sl.in_t_f32, sl.in_msg
+
+    def _unprime(self):
+        """Drops a batch that was pre-sampled but not trained on (mode switch, flush, reset)."""
+        if self._primed == "device":
+            self.pos_dev -= self.B          # the dataset cursor had already moved past it
+        self._primed = None
 
     # ------------------------------------------------------------------ weights / state exchange
     def load_state(self, memory_sd: Dict[str, Tensor], gnn_sd: Dict[str, Tensor], lp_sd: Dict[str, Tensor]):
@@ -247,6 +284,7 @@ class TGNEngine:
         self.log_base_dev.zero_()
         self.pos_dev.zero_()
         self.events_done = 0
+        self._primed = None
         self.store.reset()
 
     # ------------------------------------------------------------------ data
@@ -261,19 +299,23 @@ class TGNEngine:
         if self.store.capacity < need:
             self.store._alloc_log(need)
 
-    def stage_batch_from_device(self):
-        ev = self.events
+    def stage_batch_from_device(self, slot: Optional[int] = None):
+        ev, sl = self.events, self.slots[self.cur if slot is None else slot]
         check(_L().tgn_batch_load(_p(ev["src"]), _p(ev["dst"]), _p(ev["neg"]), _p(ev["t"]), _p(ev["msg"]),
-                                  self.De, self.B, _p(self.pos_dev), _p(self.in_ids3), _p(self.in_t_i64),
-                                  _p(self.in_t_f32), _p(self.in_msg), _stream()))
+                                  self.De, self.B, ev["src"].numel(), _p(self.pos_dev), _p(sl.in_ids3), _p(sl.in_t_i64),
+                                  _p(sl.in_t_f32), _p(sl.in_msg), _stream()))
 
-    def stage_packed(self, ids_t: Tensor, msg: Tensor):
+    def stage_packed(self, ids_t: Tensor, msg: Tensor, ahead: bool = False):
         """End-to-end staging: `ids_t` = pinned host int64 [4B] = [src|dst|neg|t], `msg` pinned
-        host float32 [B, De]; two H2D copies, the float timestamps are derived on the device."""
-        self.in_i64.copy_(ids_t, non_blocking=True)
+        host float32 [B, De]; two H2D copies, the float timestamps are derived on the device.
+        ahead=False: the batch the next train_step(from_device=False) trains on;
+        ahead=True : the batch AFTER that one (train_step(..., lookahead=True) samples it while it
+        trains on the current one -- the prefetching data-loader pattern)."""
+        sl = self.slots[self.cur ^ 1 if ahead else self.cur]
+        sl.in_i64.copy_(ids_t, non_blocking=True)
         if self.De:
-            self.in_msg.copy_(msg, non_blocking=True)
-        self.in_t_f32.copy_(self.in_t_i64)
+            sl.in_msg.copy_(msg, non_blocking=True)
+        sl.in_t_f32.copy_(sl.in_t_i64)
 
     def prefill(self, count: int, ring_state=None):
         """Start from a mid-epoch state: the first `count` events of set_events() are taken as
@@ -288,17 +330,18 @@ class TGNEngine:
         self.pos_dev.fill_(count)
         self.events_done = count
         self.store.size = count
+        self._primed = None
 
-    def stage_batch(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor):
-        """Copies one batch (host or device tensors) into the static step buffers."""
-        B = self.B
-        self.in_ids3[:B].copy_(src, non_blocking=True)
-        self.in_ids3[B:2 * B].copy_(dst, non_blocking=True)
-        self.in_ids3[2 * B:].copy_(neg, non_blocking=True)
-        self.in_t_i64.copy_(t, non_blocking=True)
-        self.in_t_f32.copy_(t, non_blocking=True)
+    def stage_batch(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor, ahead: bool = False):
+        """Copies one batch (host or device tensors) into a slot (see stage_packed for `ahead`)."""
+        B, sl = self.B, self.slots[self.cur ^ 1 if ahead else self.cur]
+        sl.in_ids3[:B].copy_(src, non_blocking=True)
+        sl.in_ids3[B:2 * B].copy_(dst, non_blocking=True)
+        sl.in_ids3[2 * B:].copy_(neg, non_blocking=True)
+        sl.in_t_i64.copy_(t, non_blocking=True)
+        sl.in_t_f32.copy_(t, non_blocking=True)
         if self.De:
-            self.in_msg.copy_(msg, non_blocking=True)
+            sl.in_msg.copy_(msg, non_blocking=True)
 
     # ------------------------------------------------------------------ pieces of the step
     def _timed(self, name: str, fn):
@@ -353,6 +396,10 @@ class TGNEngine:
 
     def _memory_fwd(self, w, n_id: Tensor, S: int, S_dev: Optional[Tensor]):
         """TGNMemory._get_updated_memory (memory_module.py:152-178): w.z [S,D], w.lu [S]."""
+        self._memory_msgs(w, n_id, S, S_dev)
+        self._memory_gru(w, S, S_dev)
+
+    def _memory_msgs(self, w, n_id: Tensor, S: int, S_dev: Optional[Tensor]):
         p, D, L, s = self.p, self.D, _L(), _stream()
         if self.world == 1:
             check(L.tgn_msg_build_ld(ctypes.byref(self.store.struct()), _p(n_id), S, _p(S_dev), ops.AGG_LAST,
@@ -366,6 +413,9 @@ class TGNEngine:
                                            _p(p["time_enc.lin.weight"]), _p(p["time_enc.lin.bias"]), self.Dt,
                                            _p(w.x), self.ldx, _p(w.h), _p(w.sn_m), _p(w.lu), _p(w.sel_ev),
                                            _p(w.sel_dt), _stream()))
+
+    def _memory_gru(self, w, S: int, S_dev: Optional[Tensor]):
+        p, D, L, s = self.p, self.D, _L(), _stream()
         self._timed("gru_gate_gemm", lambda: ops.gemm_batch([
             ops.gemm_desc(w.x, self.flat, w.gi, m=S, n=3 * D, k=self.Dx, lda=self.ldx, ldb=self.ldx, ldc=3 * D,
                           b_off=self.off["memory_updater.weight_ih"], bias=p["memory_updater.bias_ih"], m_dev=S_dev),
@@ -374,21 +424,33 @@ class TGNEngine:
         ], self.prec))
         check(L.tgn_gru_gates_fwd(_p(w.gi), _p(w.gh), _p(w.h), None, S, _p(S_dev), D, _p(w.z), _p(w.gates), s))
 
-    def _attention_fwd(self, w, z: Tensor, lu: Tensor, train: bool):
-        """GraphAttentionEmbedding.forward (emb_module.py:25-29) for the centres (= roots)."""
-        p, D, HC, L, s = self.p, self.D, self.HC, _L(), _stream()
+    def _edge_branch(self, w, lu: Tensor, train: bool):
+        """edge_attr = [cos(w * rel_t + b), msg] and its projection ee = W_edge edge_attr
+        (emb_module.py:26-28 + TransformerConv.lin_edge); independent of the GRU output."""
+        p, HC, L, s = self.p, self.HC, _L(), _stream()
         ev = self.events
-        ops.gemm_batch([ops.gemm_desc(z, self.flat, w.proj, m=w.Nb, n=4 * HC, k=D, lda=D, ldb=D, ldc=4 * HC,
-                                      b_off=self.off["conv.w_node"], bias=p["conv.b_node"], m_dev=w.Nb_dev)], self.prec)
         check(L.tgn_edge_attr_ld(_p(lu), _p(w.nbr_l), _p(ev["t"]), _p(ev["msg"]) if self.De else None, _p(w.eid),
                                  w.E, _p(w.E_dev), self.De, self.Dt, _p(p["time_enc.lin.weight"]),
                                  _p(p["time_enc.lin.bias"]), self.lde, _p(w.ea), _p(w.sn_e) if train else None,
                                  _p(w.rel), s))
         ops.gemm_batch([ops.gemm_desc(w.ea, self.flat, w.ee, m=w.E, n=HC, k=self.Din, lda=self.lde, ldb=self.lde,
                                       ldc=HC, b_off=self.off["conv.lin_edge.weight"], m_dev=w.E_dev)], self.prec)
-        check(L.tgn_attn_core_fwd(_p(w.proj), _p(w.nbr_l), _p(w.root_off), _p(w.ctr_l), w.R, _p(w.R_dev),
-                                  self.H, self.C, _p(w.ee), self.dropout if train else 0.0, self.seed,
-                                  _p(self.step_dev), _p(w.emb), _p(w.alpha), s))
+
+    def _node_proj(self, w, z: Tensor):
+        p, D, HC = self.p, self.D, self.HC
+        ops.gemm_batch([ops.gemm_desc(z, self.flat, w.proj, m=w.Nb, n=4 * HC, k=D, lda=D, ldb=D, ldc=4 * HC,
+                                      b_off=self.off["conv.w_node"], bias=p["conv.b_node"], m_dev=w.Nb_dev)], self.prec)
+
+    def _attention_core(self, w, train: bool):
+        check(_L().tgn_attn_core_fwd(_p(w.proj), _p(w.nbr_l), _p(w.root_off), _p(w.ctr_l), w.R, _p(w.R_dev),
+                                     self.H, self.C, _p(w.ee), self.dropout if train else 0.0, self.seed,
+                                     _p(self.step_dev), _p(w.emb), _p(w.alpha), _stream()))
+
+    def _attention_fwd(self, w, z: Tensor, lu: Tensor, train: bool):
+        """GraphAttentionEmbedding.forward (emb_module.py:25-29) for the centres (= roots)."""
+        self._node_proj(w, z)
+        self._edge_branch(w, lu, train)
+        self._attention_core(w, train)
 
     def _update_state(self, w):
         """memory.update_state + neighbor_loader.insert (memory_module.py:126-138, epoch_utils.py:300).
@@ -434,18 +496,37 @@ class TGNEngine:
         ], self.prec)
         check(L.tgn_scatter_add_rows(_p(w.dzcat), _p(w.ids_l), 3 * B, None, HC, _p(self.d_emb), s))
 
-    def _train_body(self):
+    def _train_body(self, from_device: bool, pipelined: bool):
+        """One step on slot `cur`.  pipelined: slots[cur] is already sampled; the forked stream loads
+        (from_device) and samples the next batch into the other slot after the state update."""
+        self._bind(self.cur)
         w, p, B, D, HC, L = self.w, self.p, self.B, self.D, self.HC, _L()
         off, fg, fl = self.off, self.flat_grad, self.flat
-        main = torch.cuda.current_stream()
+        main, side, aux = torch.cuda.current_stream(), self.side, self.aux
         self.zero_blob.zero_()
-        self._sample(w, self.in_ids3, w.ids_l)
-        self._memory_fwd(w, w.n_id, w.Nb, w.Nb_dev)
-        # ---- state update on a forked stream: it only needs z / last_update of the forward
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):
+        if not pipelined:
+            if from_device:
+                self.stage_batch_from_device()
+            self._sample(w, w.in_ids3, w.ids_l)
+        self._timed("msg_build", lambda: self._memory_msgs(w, w.n_id, w.Nb, w.Nb_dev))
+        # ---- edge branch of the attention on its own stream: needs last_update / edges only
+        aux.wait_stream(main)
+        with torch.cuda.stream(aux):
+            self._edge_branch(w, w.lu, True)
+        self._memory_gru(w, w.Nb, w.Nb_dev)
+        # ---- forked stream: state update (needs z / last_update of the forward only), then the
+        # next batch: load + sample while this step's attention / backward run
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
             self._update_state(w)
-        self._attention_fwd(w, w.z, w.lu, True)
+            if pipelined:
+                nxt = self.slots[self.cur ^ 1]
+                if from_device:
+                    self.stage_batch_from_device(self.cur ^ 1)
+                self._sample(nxt, nxt.in_ids3, nxt.ids_l)
+        self._node_proj(w, w.z)
+        main.wait_stream(aux)
+        self._attention_core(w, True)
         s = _stream()
         # ---- decoder + loss + decoder backward (decoder.py:24-27; BCEWithLogits, pyg-mem-tgn.py:51)
         gptr = lambda name: fg.data_ptr() + 4 * off[name]
@@ -476,10 +557,14 @@ class TGNEngine:
             g.append(ops.gemm_desc(w.d_ee, fl, w.d_eat, m=w.E, n=self.Dt, k=HC, lda=HC, ldb=self.lde, ldc=self.Dt,
                                    trans_b=True, b_off=off["conv.lin_edge.weight"], m_dev=w.E_dev))
         ops.gemm_batch(g, self.prec)
-        ops.colsum(w.d_proj, w.Nb, 4 * HC, 4 * HC, p["conv.b_node"].grad, True, rows_dev=w.Nb_dev)
-        if self.Dt:
-            check(L.tgn_time_bwd_sin(_p(w.rel), None, w.E, _p(w.E_dev), _p(w.sn_e), self.Dt, _p(w.d_eat), self.Dt,
-                                     gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), s))
+        # bias gradient of the node projection and the attention-side TimeEncoder gradient: off the
+        # critical path, next to the GRU backward
+        aux.wait_stream(main)
+        with torch.cuda.stream(aux):
+            ops.colsum(w.d_proj, w.Nb, 4 * HC, 4 * HC, p["conv.b_node"].grad, True, rows_dev=w.Nb_dev)
+            if self.Dt:
+                check(L.tgn_time_bwd_sin(_p(w.rel), None, w.E, _p(w.E_dev), _p(w.sn_e), self.Dt, _p(w.d_eat), self.Dt,
+                                         gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), _stream()))
         # ---- GRU backward (torch.nn.GRUCell, memory_module.py:72,172)
         check(L.tgn_gru_gates_bwd_bias(_p(w.d_z), _p(w.gates), _p(w.h), w.Nb, _p(w.Nb_dev), D, _p(w.d_gi),
                                        _p(w.d_gh), gptr("memory_updater.bias_ih"), gptr("memory_updater.bias_hh"), s))
@@ -498,7 +583,8 @@ class TGNEngine:
             check(L.tgn_time_bwd_sin(_p(w.sel_dt), _p(w.sel_ev), w.Nb, _p(w.Nb_dev), _p(w.sn_m), self.Dt,
                                      w.d_x.data_ptr() + 4 * (2 * D + self.De), self.ldx,
                                      gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), s))
-        main.wait_stream(self.side)
+        main.wait_stream(aux)
+        main.wait_stream(side)
         if self.world > 1:   # replicated compute: average the gradients so the weight replicas stay bit-identical
             self._all_reduce(self.flat_grad)
             self.flat_grad.mul_(1.0 / self.world)
@@ -525,13 +611,32 @@ class TGNEngine:
             self._graphs[key] = g
         g.replay()
 
-    def train_step(self, from_device: bool = True):
-        """One training batch.  from_device=True: slice the next batch out of the resident event
-        arrays (set_events); False: the caller staged it with stage_batch() / stage_packed()."""
-        if from_device:
-            self._run(("train", True), lambda: (self.stage_batch_from_device(), self._train_body()))
+    def train_step(self, from_device: bool = True, lookahead: bool = False):
+        """One training batch; returns the (device) loss of that batch.
+
+        from_device=True : batches are sliced out of the resident event arrays (set_events).  The
+                           step is software-pipelined: while batch i trains, the forked stream loads
+                           and samples batch i+1.
+        from_device=False: the caller staged the batch with stage_batch() / stage_packed().  With
+                           lookahead=True the caller has ALSO staged the following batch
+                           (stage_*(…, ahead=True)); it is sampled during this step, and the next call
+                           trains on it (prefetching data-loader pattern, used by bench.py's e2e arm).
+        """
+        mode = "device" if from_device else "host"
+        pipelined = from_device or lookahead
+        if pipelined:
+            if self._primed != mode:           # first pipelined step: sample the current batch now
+                self._unprime()
+                self._bind(self.cur)
+                if from_device:
+                    self.stage_batch_from_device()
+                self._sample(self.slots[self.cur], self.slots[self.cur].in_ids3, self.slots[self.cur].ids_l)
+                self._primed = mode
         else:
-            self._run(("train", False), self._train_body)
+            self._unprime()
+        self._run(("train", from_device, pipelined, self.cur), lambda: self._train_body(from_device, pipelined))
+        if pipelined:
+            self.cur ^= 1
         self.events_done += self.B
         self.store.size = self.events_done   # host mirror of log_base_dev (graph replays skip the Python body)
         return self.loss
@@ -555,6 +660,7 @@ class TGNEngine:
         `neg` may be any column shard of the full negative matrix (data-parallel evaluation):
         the state update does not depend on it."""
         dev, N, D, HC, L = self.dev, self.N, self.D, self.HC, _L()
+        self._unprime()
         src, dst, neg = src.to(dev, torch.long), dst.to(dev, torch.long), neg.to(dev, torch.long)
         t_i = t.to(dev, torch.long)
         B, Q = neg.shape
@@ -609,6 +715,7 @@ class TGNEngine:
     def flush_to_eval(self):
         """TGNMemory.train(False) (memory_module.py:209-215): every node goes through the updater
         with its stored messages, then the store is cleared."""
+        self._unprime()
         new_mem = torch.zeros_like(self.memory)
         new_lu = torch.zeros_like(self.last_update)
         chunk = 1 << 16

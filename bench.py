@@ -195,7 +195,7 @@ def main():
     data = synth.synth_events(WORKLOAD, seed=rank, max_events=need)
     N, De = data["num_nodes"], data["raw_dim"]
     eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.1, use_graph=True,
-                    log_capacity=data["src"].size, seed=1234 + rank, precision=args.precision)
+                    log_capacity=data["src"].size, seed=1234 + rank, precision=args.precision, fused_zero_grad=True)
     eng.load_state(*init_state_dicts(De, HIDDEN, N, seed=1))
     ev = {k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")}
     eng.set_events(**ev)
@@ -338,7 +338,8 @@ def bench_partitioned(dev, rank, world, steps, warmup, precision):
     data = synth.synth_events(name, seed=0, max_events=prefill + (warmup + steps + 8) * B)
     N, De = data["num_nodes"], data["raw_dim"]
     eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.1, use_graph=True,
-                    log_capacity=data["src"].size, seed=99, precision=precision, rank=rank, world=world)
+                    log_capacity=data["src"].size, seed=99, precision=precision, rank=rank, world=world,
+                    fused_zero_grad=True)
     eng.load_state(*init_state_dicts(De, HIDDEN, N, seed=1))
     eng.set_events(**{k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")})
     ring = ring_after(data["src"][:prefill], data["dst"][:prefill], data["t"][:prefill], K, N)

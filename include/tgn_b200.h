@@ -336,11 +336,15 @@ int32_t tgn_adam_step(float* params, const float* grads, float* exp_avg, float* 
                       int64_t count, float lr, float beta1, float beta2, float eps,
                       float* step_dev, void* stream);
 
-/* tgn_adam_step followed by the end-of-step scalars in one extra launch: *step_counter += 1
- * (nullable; keys the dropout stream) and *loss_out = *loss_acc (nullable). */
-int32_t tgn_adam_finish(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+/* tgn_adam_step with the end-of-step scalars folded in: *step_counter += 1 (nullable; keys the
+ * dropout stream) and *loss_out = *loss_acc (nullable).  With done_counter (device uint32, zero on
+ * first use) everything is ONE launch -- the last block to finish runs the tail -- and
+ * zero_grads != 0 additionally clears grads, *loss_acc and zero_extra[0..zero_extra_count) so the
+ * next step needs no memset. */
+int32_t tgn_adam_finish(float* params, float* grads, float* exp_avg, float* exp_avg_sq,
                         int64_t count, float lr, float beta1, float beta2, float eps, float* step_dev,
-                        int64_t* step_counter, const float* loss_acc, float* loss_out, void* stream);
+                        int64_t* step_counter, float* loss_acc, float* loss_out, uint32_t* done_counter,
+                        int32_t zero_grads, float* zero_extra, int64_t zero_extra_count, void* stream);
 
 /* TimeEncoder forward: out[i,c] = cos(w[c]*t[i] + b[c]) (contract from
  * memory_module.py:203, emb_module.py:27; DGL twin model_utils.py:223-237) */

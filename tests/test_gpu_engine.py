@@ -133,6 +133,24 @@ def test_host_staged_batches_equal_device_staged():
     assert torch.equal(eng_a.last_update, eng_c.last_update)
 
 
+def test_fused_zero_grad_is_equivalent():
+    """Adam clearing the gradients / loss / embedding-gradient rows itself (no per-step memset)
+    trains exactly like the memset variant."""
+    from tgn_b200.engine import TGNEngine
+    N, De, D, K, B, steps = 300, 8, 16, 4, 32, 8
+    ref, eng_a, ev = _setup(N, De, D, K, B, B * steps, 17, True)
+    eng_b = TGNEngine(N, De, D, K, B, device=DEV, lr=1e-3, dropout=0.0, use_graph=True, log_capacity=B * steps,
+                      fused_zero_grad=True)
+    eng_b.load_state(ref["memory"].state_dict(), ref["gnn"].state_dict(), ref["link_pred"].state_dict())
+    eng_b.set_events(**ev)
+    for s in range(steps):
+        la, lb = float(eng_a.train_step()), float(eng_b.train_step())
+        assert abs(la - lb) < 1e-4, (s, la, lb)
+    assert float(eng_b.flat_grad.abs().sum()) == 0.0 and float(eng_b.d_emb.abs().sum()) == 0.0
+    assert float(eng_b.adam_step_dev) == steps and int(eng_b.step_dev) == steps
+    torch.testing.assert_close(eng_a.memory, eng_b.memory, rtol=1e-2, atol=1e-3)
+
+
 def test_eval_mrr_matches_oracle():
     """train a few steps, switch to eval (flush), score one batch against Q negatives."""
     from tgn_b200 import ops, synth

@@ -361,9 +361,21 @@ __global__ void time_encode_bwd_kernel(const float* __restrict__ t, const int32_
 
 // Adam (torch.optim.Adam semantics, no amsgrad, no weight decay) over a flat buffer.
 // step_dev holds the step count as float and is advanced by the kernel.
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+struct AdamTail {          // optional end-of-step work folded into the Adam launch
+  unsigned int* done_ctr;  // zero-initialised; the last block to finish runs the tail and resets it
+  float* adam_step;        // += 1
+  int64_t* step_ctr;       // += 1 (nullable)
+  float* loss_acc;         // -> *loss_out (nullable); cleared afterwards when zero_grads
+  float* loss_out;
+  float* zero_ptr;         // grads are cleared after use; this extra range too (nullable)
+  long long zero_n;
+  int zero_grads;
+};
+
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g,
                             float* __restrict__ m, float* __restrict__ v, long long n, float lr,
-                            float b1, float b2, float eps, const float* __restrict__ step_dev) {
+                            float b1, float b2, float eps, const float* __restrict__ step_dev,
+                            AdamTail tail) {
   pdl_wait();
   pdl_launch();
   const float step = *step_dev + 1.f;
@@ -379,6 +391,27 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
     v[i] = vi;
     const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
     p[i] -= step_size * (mi / denom);
+    if (tail.zero_grads) g[i] = 0.f;
+  }
+  if (tail.done_ctr == nullptr) return;
+  if (tail.zero_grads && tail.zero_ptr)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tail.zero_n;
+         i += (long long)gridDim.x * blockDim.x)
+      tail.zero_ptr[i] = 0.f;
+  // every block has read *step_dev above; the last one to get here may now advance it
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(tail.done_ctr, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    *tail.adam_step += 1.f;
+    if (tail.step_ctr) *tail.step_ctr += 1;
+    if (tail.loss_acc && tail.loss_out) *tail.loss_out = *tail.loss_acc;
+    if (tail.loss_acc && tail.zero_grads) *tail.loss_acc = 0.f;
+    *tail.done_ctr = 0u;
   }
 }
 __global__ void adam_bump_kernel(float* step_dev) {
@@ -386,7 +419,7 @@ __global__ void adam_bump_kernel(float* step_dev) {
   pdl_launch(); *step_dev += 1.f; }
 // end-of-step scalars in one launch: Adam step count, the step counter that keys dropout, loss
 __global__ void step_finish_kernel(float* adam_step, int64_t* step_ctr, const float* loss_acc,
-                                   float* loss_out) {
+                                   float* loss_out) {  // (fallback when no done counter is given)
   pdl_wait();
   pdl_launch();
   *adam_step += 1.f;
@@ -408,26 +441,36 @@ __global__ void __launch_bounds__(128)
   const int r0 = blockIdx.x * rows_per, r1 = min(S, r0 + rows_per);
   for (int j = threadIdx.x; j < D; j += blockDim.x) {
     float sr = 0.f, sz = 0.f, sn = 0.f, shn = 0.f;
-    for (int s = r0; s < r1; ++s) {
-      const float* g = gates + (long long)s * 4 * D;
-      const float r = g[j], z = g[D + j], n = g[2 * D + j], ghn = g[3 * D + j];
-      const float hv = h[(long long)s * D + j];
-      const float go = d_out[(long long)s * D + j];
-      const float dn_pre = go * (1.f - z) * (1.f - n * n);
-      const float dr_pre = dn_pre * ghn * r * (1.f - r);
-      const float dz_pre = go * (hv - n) * z * (1.f - z);
-      float* dgi = d_gi + (long long)s * 3 * D;
-      float* dgh = d_gh + (long long)s * 3 * D;
-      dgi[j] = dr_pre;
-      dgi[D + j] = dz_pre;
-      dgi[2 * D + j] = dn_pre;
-      dgh[j] = dr_pre;
-      dgh[D + j] = dz_pre;
-      dgh[2 * D + j] = dn_pre * r;
-      sr += dr_pre;
-      sz += dz_pre;
-      sn += dn_pre;
-      shn += dn_pre * r;
+    for (int s0 = r0; s0 < r1; s0 += 4) {
+      float r[4], z[4], n[4], ghn[4], hv[4], go[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {  // all loads of four rows first
+        const int s = min(s0 + u, r1 - 1);
+        const float* g = gates + (long long)s * 4 * D;
+        r[u] = g[j]; z[u] = g[D + j]; n[u] = g[2 * D + j]; ghn[u] = g[3 * D + j];
+        hv[u] = h[(long long)s * D + j];
+        go[u] = d_out[(long long)s * D + j];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int s = s0 + u;
+        if (s >= r1) break;
+        const float dn_pre = go[u] * (1.f - z[u]) * (1.f - n[u] * n[u]);
+        const float dr_pre = dn_pre * ghn[u] * r[u] * (1.f - r[u]);
+        const float dz_pre = go[u] * (hv[u] - n[u]) * z[u] * (1.f - z[u]);
+        float* dgi = d_gi + (long long)s * 3 * D;
+        float* dgh = d_gh + (long long)s * 3 * D;
+        dgi[j] = dr_pre;
+        dgi[D + j] = dz_pre;
+        dgi[2 * D + j] = dn_pre;
+        dgh[j] = dr_pre;
+        dgh[D + j] = dz_pre;
+        dgh[2 * D + j] = dn_pre * r[u];
+        sr += dr_pre;
+        sz += dz_pre;
+        sn += dn_pre;
+        shn += dn_pre * r[u];
+      }
     }
     if (r1 > r0) {
       atomicAdd(&d_b_ih[j], sr);
@@ -629,8 +672,8 @@ int32_t tgn_adam_step(float* params, const float* grads, float* exp_avg, float* 
   cudaStream_t s = (cudaStream_t)stream;
   if (count > 0) {
     TGN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "adam_step: NULL pointer");
-    launch_k(adam_kernel, dim3(stride_grid(count, 256)), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, count,
-                                                        lr, beta1, beta2, eps, step_dev);
+    launch_k(adam_kernel, dim3(stride_grid(count, 256)), dim3(256), 0, s, params, const_cast<float*>(grads), exp_avg, exp_avg_sq, count,
+                                                        lr, beta1, beta2, eps, step_dev, AdamTail{});
     TGN_LAUNCH_CHECK();
   }
   launch_k(adam_bump_kernel, dim3(1), dim3(1), 0, s, step_dev);
@@ -638,15 +681,28 @@ int32_t tgn_adam_step(float* params, const float* grads, float* exp_avg, float* 
   return TGN_OK;
 }
 
-int32_t tgn_adam_finish(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+int32_t tgn_adam_finish(float* params, float* grads, float* exp_avg, float* exp_avg_sq,
                         int64_t count, float lr, float beta1, float beta2, float eps, float* step_dev,
-                        int64_t* step_counter, const float* loss_acc, float* loss_out, void* stream) {
-  TGN_REQUIRE(count >= 0 && step_dev, "adam_finish: bad arguments");
+                        int64_t* step_counter, float* loss_acc, float* loss_out, uint32_t* done_counter,
+                        int32_t zero_grads, float* zero_extra, int64_t zero_extra_count, void* stream) {
+  TGN_REQUIRE(count >= 0 && step_dev && zero_extra_count >= 0, "adam_finish: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
+  if (count > 0 && done_counter) {
+    // one launch: the last block to finish advances the counters and hands the loss over
+    TGN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "adam_finish: NULL pointer");
+    AdamTail t;
+    t.done_ctr = done_counter; t.adam_step = step_dev; t.step_ctr = step_counter; t.loss_acc = loss_acc;
+    t.loss_out = loss_out; t.zero_ptr = zero_extra; t.zero_n = zero_extra_count; t.zero_grads = zero_grads;
+    launch_k(adam_kernel, dim3(stride_grid(count, 256)), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq,
+             count, lr, beta1, beta2, eps, step_dev, t);
+    TGN_LAUNCH_CHECK();
+    return TGN_OK;
+  }
+  TGN_REQUIRE(!zero_grads, "adam_finish: fused zero-grad needs done_counter");
   if (count > 0) {
     TGN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "adam_finish: NULL pointer");
-    launch_k(adam_kernel, dim3(stride_grid(count, 256)), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, count,
-                                                        lr, beta1, beta2, eps, step_dev);
+    launch_k(adam_kernel, dim3(stride_grid(count, 256)), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq,
+             count, lr, beta1, beta2, eps, step_dev, AdamTail{});
     TGN_LAUNCH_CHECK();
   }
   launch_k(step_finish_kernel, dim3(1), dim3(1), 0, s, step_dev, step_counter, loss_acc, loss_out);

@@ -66,6 +66,7 @@ _SCALARS = {
     "int32_t": ctypes.c_int32,
     "int64_t": ctypes.c_int64,
     "uint64_t": ctypes.c_uint64,
+    "uint32_t": ctypes.c_uint32,
     "float": ctypes.c_float,
 }
 

@@ -48,7 +48,7 @@ class TGNEngine:
     def __init__(self, num_nodes: int, raw_dim: int, hidden: int, size_k: int, batch_size: int,
                  device="cuda", lr: float = 1e-4, heads: int = 2, dropout: float = 0.1,
                  log_capacity: int = 1 << 20, seed: int = 0, use_graph: bool = True,
-                 precision: int = 3, rank: int = 0, world: int = 1, group=None):
+                 precision: int = 3, rank: int = 0, world: int = 1, group=None, fused_zero_grad: bool = False):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("TGNEngine runs on CUDA only (no CPU fallback)")
@@ -102,6 +102,10 @@ class TGNEngine:
         self.exp_avg = torch.zeros(o, device=dev)
         self.exp_avg_sq = torch.zeros(o, device=dev)
         self.adam_step_dev = torch.zeros(1, device=dev)
+        self.done_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+        # fused_zero_grad: Adam clears the gradients (and the other per-step accumulators) after using
+        # them, so a step starts without a memset; p[...].grad then reads zero after train_step()
+        self.fused_zero_grad = fused_zero_grad
         self.p: Dict[str, Tensor] = {}
         for name, shp, ld in table:
             v = self._view(self.flat, name, shp)
@@ -503,7 +507,8 @@ class TGNEngine:
         w, p, B, D, HC, L = self.w, self.p, self.B, self.D, self.HC, _L()
         off, fg, fl = self.off, self.flat_grad, self.flat
         main, side, aux = torch.cuda.current_stream(), self.side, self.aux
-        self.zero_blob.zero_()
+        if not self.fused_zero_grad:
+            self.zero_blob.zero_()
         if not pipelined:
             if from_device:
                 self.stage_batch_from_device()
@@ -590,7 +595,8 @@ class TGNEngine:
             self.flat_grad.mul_(1.0 / self.world)
         check(L.tgn_adam_finish(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
                                 self.n_param, self.lr, 0.9, 0.999, 1e-8, _p(self.adam_step_dev), _p(self.step_dev),
-                                _p(self.loss_acc), _p(self.loss), _stream()))
+                                _p(self.loss_acc), _p(self.loss), _p(self.done_ctr), int(self.fused_zero_grad),
+                                _p(self.d_emb), self.d_emb.numel(), _stream()))
 
     def _run(self, key: tuple, body):
         if not self.use_graph:

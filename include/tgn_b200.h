@@ -425,12 +425,14 @@ int32_t tgn_time_bwd_sin(const float* t, const int32_t* row_mask, int32_t num, c
                          float* d_w, float* d_b, void* stream);
 /* TransformerConv core with the edge projection ee = W_edge*edge_attr [E,H*C] precomputed
  * (by tgn_gemm_batch): scores, softmax over each centre's edges [row_ptr[c], row_ptr[c+1]),
- * dropout, aggregation, + skip.  Writes out[centre_ids[c], :] and alpha [E,H]. */
+ * dropout, aggregation, + skip.  Writes out[centre_ids[c], :] and alpha [E,H].  max_degree > 0 is a
+ * promise that no centre has more edges (the ring lookup yields at most K): up to 12 edges and
+ * H*C <= 128 select a register-resident single-pass kernel; 0 = unknown. */
 int32_t tgn_attn_core_fwd(const float* proj, const int64_t* nbr_local, const int32_t* row_ptr,
                           const int64_t* centre_ids, int32_t num_centres,
                           const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
                           const float* ee, float dropout_p, uint64_t seed, const int64_t* seed_dev,
-                          float* out, float* alpha, void* stream);
+                          int32_t max_degree, float* out, float* alpha, void* stream);
 /* Backward: zero-fills d_proj [num_rows, 4*H*C], then writes the q and skip blocks of the
  * centre rows, atomically adds the k / v blocks of the neighbour rows and writes d_ee [E,H*C].
  * d_out is read at the centre rows only. */
@@ -438,8 +440,8 @@ int32_t tgn_attn_core_bwd(const float* proj, const int64_t* nbr_local, const int
                           const int64_t* centre_ids, int32_t num_centres,
                           const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
                           const float* ee, const float* alpha, const float* d_out, float dropout_p,
-                          uint64_t seed, const int64_t* seed_dev, int32_t num_rows, float* d_proj,
-                          float* d_ee, void* stream);
+                          uint64_t seed, const int64_t* seed_dev, int32_t max_degree, int32_t num_rows,
+                          float* d_proj, float* d_ee, void* stream);
 /* LinkPredictor tail + BCE-with-logits loss and gradient (decoder.py:24-27, pyg-mem-tgn.py:51).
  * hs [B,D] = lin_src(z_src), hd [2B,D] = lin_dst([z_dst; z_neg]).  Accumulates (+=) loss
  * (mean over positives + mean over negatives), d_w_final, d_b_final, d_b_src, d_b_dst;

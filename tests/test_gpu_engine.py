@@ -75,8 +75,9 @@ def test_train_steps_match_oracle(use_graph):
 
 
 def test_gemm_decoder_path_matches_oracle():
-    """the decoder on batched GEMMs (used when the weights do not fit the fused kernel's shared memory)"""
-    N, De, D, K, B, steps = 400, 12, 32, 5, 50, 4
+    """the decoder on batched GEMMs (used when the weights do not fit the fused kernel's shared memory);
+    K = 14 > 12 also takes the general (any-degree) attention kernels instead of the register-resident ones"""
+    N, De, D, K, B, steps = 400, 12, 32, 14, 50, 6
     ref, eng, ev = _setup(N, De, D, K, B, B * steps, 13, False)
     eng.fused_decoder = False
     loader = orc.TorchNeighborLoader(N, K)

@@ -298,6 +298,183 @@ __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_fwd_kernel(AttnCore
   }
 }
 
+// ---- low-degree fast path (every centre has <= kSmallDeg edges, H*C <= 128): the whole
+// neighbourhood of a centre is fetched into registers with ONE round of independent loads
+// (neighbour ids by one coalesced load + shuffles, then all k / v / ee rows), so a warp pays
+// ~4 dependent memory latencies per centre instead of ~2 per edge group and pass.
+constexpr int kSmallDeg = 12;
+
+template <int H>
+__global__ void __launch_bounds__(kCoreWarps * 32) attn_core_fwd_small_kernel(AttnCoreArgs a) {
+  pdl_wait();
+  pdl_launch();
+  const int HC = a.H * a.C, C = a.C;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nC = a.centres.get();
+  const float inv_sqrt_c = rsqrtf((float)C);
+  const float keep = 1.f - a.dropout_p;
+  const int c0 = 4 * lane;
+  const bool ok = c0 < HC;
+  HeadMask<H> hm;
+  hm.init(c0, C, ok);
+  Philox rng(a.seed + (a.seed_dev ? (uint64_t)*a.seed_dev : 0ull));
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int ci = blockIdx.x * kCoreWarps + wid; ci < nC; ci += gridDim.x * kCoreWarps) {
+    const int64_t row = a.centre_ids ? a.centre_ids[ci] : ci;
+    const int e0 = a.row_ptr[ci];
+    const int deg = min(a.row_ptr[ci + 1] - e0, kSmallDeg);
+    const float* pr = a.proj + row * 4 * HC;
+    const float4 q = ok ? ld4(pr + c0) : z4;
+    const float4 skip = ok ? ld4(pr + 3 * HC + c0) : z4;
+    const int64_t my_j = lane < deg ? a.nbr[e0 + lane] : 0;
+    float4 kk[kSmallDeg], vv[kSmallDeg];
+#pragma unroll
+    for (int g = 0; g < kSmallDeg; ++g) {
+      const int64_t j = __shfl_sync(0xffffffffu, my_j, g);
+      const bool on = ok && g < deg;
+      const float4 eev = on ? ld4(a.ee + (long long)(e0 + g) * HC + c0) : z4;
+      kk[g] = on ? f4_add(ld4(a.proj + j * 4 * HC + HC + c0), eev) : z4;
+      vv[g] = on ? f4_add(ld4(a.proj + j * 4 * HC + 2 * HC + c0), eev) : z4;
+    }
+    float sc[kSmallDeg][H], mx[H], den[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) mx[h] = -INFINITY;
+#pragma unroll
+    for (int g = 0; g < kSmallDeg; ++g) {
+      float part[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) part[h] = 0.f;
+      hm.dot(q, kk[g], part);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        sc[g][h] = warp_sum(part[h]) * inv_sqrt_c;
+        if (g < deg) mx[h] = fmaxf(mx[h], sc[g][h]);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) den[h] = 0.f;
+#pragma unroll
+    for (int g = 0; g < kSmallDeg; ++g)
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        sc[g][h] = g < deg ? expf(sc[g][h] - mx[h]) : 0.f;
+        den[h] += sc[g][h];
+      }
+    float4 acc = z4;
+#pragma unroll
+    for (int g = 0; g < kSmallDeg; ++g) {
+      if (g >= deg) break;  // warp-uniform
+      float pw[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        float p = sc[g][h] / den[h];
+        if (lane == 0) a.alpha[(long long)(e0 + g) * H + h] = p;
+        if (a.dropout_p > 0.f) {
+          const uint4 r = rng((uint64_t)(e0 + g), (uint64_t)h);
+          const float uni = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+          p = uni < keep ? p / keep : 0.f;
+        }
+        pw[h] = p;
+      }
+      const float4 w4 = hm.pick(pw);
+      acc.x = fmaf(w4.x, vv[g].x, acc.x);
+      acc.y = fmaf(w4.y, vv[g].y, acc.y);
+      acc.z = fmaf(w4.z, vv[g].z, acc.z);
+      acc.w = fmaf(w4.w, vv[g].w, acc.w);
+    }
+    if (ok) *reinterpret_cast<float4*>(a.out + row * HC + c0) = f4_add(acc, skip);
+  }
+}
+
+template <int H>
+__global__ void __launch_bounds__(kCoreWarps * 32) attn_core_bwd_small_kernel(AttnCoreArgs a) {
+  pdl_wait();
+  pdl_launch();
+  const int HC = a.H * a.C, C = a.C;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nC = a.centres.get();
+  const float inv_sqrt_c = rsqrtf((float)C);
+  const float keep = 1.f - a.dropout_p;
+  const int c0 = 4 * lane;
+  const bool ok = c0 < HC;
+  HeadMask<H> hm;
+  hm.init(c0, C, ok);
+  Philox rng(a.seed + (a.seed_dev ? (uint64_t)*a.seed_dev : 0ull));
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int ci = blockIdx.x * kCoreWarps + wid; ci < nC; ci += gridDim.x * kCoreWarps) {
+    const int64_t row = a.centre_ids ? a.centre_ids[ci] : ci;
+    const int e0 = a.row_ptr[ci];
+    const int deg = min(a.row_ptr[ci + 1] - e0, kSmallDeg);
+    const float* pr = a.proj + row * 4 * HC;
+    const float4 q = ok ? ld4(pr + c0) : z4;
+    const float4 g4 = ok ? ld4(a.d_out + row * HC + c0) : z4;
+    const int64_t my_j = lane < deg ? a.nbr[e0 + lane] : 0;
+    // lane l < deg*H holds alpha of (edge l / H, head l % H): one coalesced load
+    const float my_al = lane < deg * H ? a.alpha[(long long)e0 * H + lane] : 0.f;
+    float4 kk[kSmallDeg], vv[kSmallDeg];
+    int64_t jn[kSmallDeg];
+#pragma unroll
+    for (int g = 0; g < kSmallDeg; ++g) {
+      jn[g] = __shfl_sync(0xffffffffu, my_j, g);
+      const bool on = ok && g < deg;
+      const float4 eev = on ? ld4(a.ee + (long long)(e0 + g) * HC + c0) : z4;
+      kk[g] = on ? f4_add(ld4(a.proj + jn[g] * 4 * HC + HC + c0), eev) : z4;
+      vv[g] = on ? f4_add(ld4(a.proj + jn[g] * 4 * HC + 2 * HC + c0), eev) : z4;
+    }
+    float al[kSmallDeg][H], dal[kSmallDeg][H], mk[kSmallDeg][H], dot[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) dot[h] = 0.f;
+#pragma unroll
+    for (int g = 0; g < kSmallDeg; ++g) {
+      float part[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) part[h] = 0.f;
+      hm.dot(g4, vv[g], part);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        al[g][h] = (g * H + h < 32) ? __shfl_sync(0xffffffffu, my_al, g * H + h)
+                                    : (g < deg ? a.alpha[(long long)(e0 + g) * H + h] : 0.f);
+        mk[g][h] = 1.f;
+        if (a.dropout_p > 0.f && g < deg) {
+          const uint4 r = rng((uint64_t)(e0 + g), (uint64_t)h);
+          const float uni = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+          mk[g][h] = uni < keep ? 1.f / keep : 0.f;
+        }
+        dal[g][h] = warp_sum(part[h]) * mk[g][h];
+        if (g < deg) dot[h] = fmaf(al[g][h], dal[g][h], dot[h]);
+      }
+    }
+    float4 dq = z4;
+#pragma unroll
+    for (int g = 0; g < kSmallDeg; ++g) {
+      if (g >= deg) break;  // warp-uniform
+      float ds[H], at[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        ds[h] = al[g][h] * (dal[g][h] - dot[h]) * inv_sqrt_c;
+        at[h] = al[g][h] * mk[g][h];
+      }
+      if (!ok) continue;
+      const float4 d4 = hm.pick(ds), a4 = hm.pick(at);
+      dq.x = fmaf(d4.x, kk[g].x, dq.x);
+      dq.y = fmaf(d4.y, kk[g].y, dq.y);
+      dq.z = fmaf(d4.z, kk[g].z, dq.z);
+      dq.w = fmaf(d4.w, kk[g].w, dq.w);
+      const float4 dk = make_float4(d4.x * q.x, d4.y * q.y, d4.z * q.z, d4.w * q.w);
+      const float4 dv = make_float4(a4.x * g4.x, a4.y * g4.y, a4.z * g4.z, a4.w * g4.w);
+      float* dpj = a.d_proj + jn[g] * 4 * HC;
+      red_add_v4(dpj + HC + c0, dk);
+      red_add_v4(dpj + 2 * HC + c0, dv);
+      *reinterpret_cast<float4*>(a.d_ee + (long long)(e0 + g) * HC + c0) = f4_add(dk, dv);
+    }
+    if (ok) {
+      float* dpr = a.d_proj + row * 4 * HC;
+      *reinterpret_cast<float4*>(dpr + c0) = dq;
+      *reinterpret_cast<float4*>(dpr + 3 * HC + c0) = g4;
+    }
+  }
+}
+
 // out_i = sum_e a~_e (v_j + ee_e) + skip_i,  a~ = dropout(alpha), alpha = softmax_e(s_e),
 // s_e = <q_i, k_j + ee_e>/sqrt(C).  Pass A: dot_h = sum_e alpha_e d alpha_e; pass B recomputes
 // d alpha and emits the gradients; neighbour rows of d_proj receive vector reductions.
@@ -814,7 +991,7 @@ int32_t tgn_attn_core_fwd(const float* proj, const int64_t* nbr_local, const int
                           const int64_t* centre_ids, int32_t num_centres,
                           const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
                           const float* ee, float dropout_p, uint64_t seed, const int64_t* seed_dev,
-                          float* out, float* alpha, void* stream) {
+                          int32_t max_degree, float* out, float* alpha, void* stream) {
   if (num_centres == 0) return TGN_OK;
   AttnCoreArgs a;
   int32_t rc = core_args(a, proj, nbr_local, row_ptr, centre_ids, num_centres, num_centres_dev, heads,
@@ -824,6 +1001,15 @@ int32_t tgn_attn_core_fwd(const float* proj, const int64_t* nbr_local, const int
   a.out = out; a.alpha = alpha;
   const int grid = ceil_div(num_centres, kCoreWarps);
   cudaStream_t s = (cudaStream_t)stream;
+  if (max_degree > 0 && max_degree <= kSmallDeg && heads * head_dim <= 128 && heads <= 4) {
+    switch (heads) {
+      case 1: launch_k(attn_core_fwd_small_kernel<1>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+      case 2: launch_k(attn_core_fwd_small_kernel<2>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+      default: launch_k(attn_core_fwd_small_kernel<4>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+    }
+    TGN_LAUNCH_CHECK();
+    return TGN_OK;
+  }
   switch (heads) {
     case 1: launch_k(attn_core_fwd_kernel<1>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
     case 2: launch_k(attn_core_fwd_kernel<2>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
@@ -838,8 +1024,8 @@ int32_t tgn_attn_core_bwd(const float* proj, const int64_t* nbr_local, const int
                           const int64_t* centre_ids, int32_t num_centres,
                           const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
                           const float* ee, const float* alpha, const float* d_out, float dropout_p,
-                          uint64_t seed, const int64_t* seed_dev, int32_t num_rows, float* d_proj,
-                          float* d_ee, void* stream) {
+                          uint64_t seed, const int64_t* seed_dev, int32_t max_degree, int32_t num_rows,
+                          float* d_proj, float* d_ee, void* stream) {
   TGN_REQUIRE(num_rows >= 0, "attn_core_bwd: bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
   if (num_rows > 0) {
@@ -854,6 +1040,15 @@ int32_t tgn_attn_core_bwd(const float* proj, const int64_t* nbr_local, const int
   TGN_REQUIRE(alpha && d_out && d_proj && d_ee, "attn_core_bwd: NULL pointer");
   a.alpha = const_cast<float*>(alpha); a.d_out = d_out; a.d_proj = d_proj; a.d_ee = d_ee;
   const int grid = ceil_div(num_centres, kCoreWarps);
+  if (max_degree > 0 && max_degree <= kSmallDeg && heads * head_dim <= 128 && heads <= 4) {
+    switch (heads) {
+      case 1: launch_k(attn_core_bwd_small_kernel<1>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+      case 2: launch_k(attn_core_bwd_small_kernel<2>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+      default: launch_k(attn_core_bwd_small_kernel<4>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+    }
+    TGN_LAUNCH_CHECK();
+    return TGN_OK;
+  }
   switch (heads) {
     case 1: launch_k(attn_core_bwd_kernel<1>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
     case 2: launch_k(attn_core_bwd_kernel<2>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;

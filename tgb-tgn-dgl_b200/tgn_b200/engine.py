@@ -448,7 +448,7 @@ class TGNEngine:
     def _attention_core(self, w, train: bool):
         check(_L().tgn_attn_core_fwd(_p(w.proj), _p(w.nbr_l), _p(w.root_off), _p(w.ctr_l), w.R, _p(w.R_dev),
                                      self.H, self.C, _p(w.ee), self.dropout if train else 0.0, self.seed,
-                                     _p(self.step_dev), _p(w.emb), _p(w.alpha), _stream()))
+                                     _p(self.step_dev), self.K, _p(w.emb), _p(w.alpha), _stream()))
 
     def _attention_fwd(self, w, z: Tensor, lu: Tensor, train: bool):
         """GraphAttentionEmbedding.forward (emb_module.py:25-29) for the centres (= roots)."""
@@ -546,7 +546,7 @@ class TGNEngine:
         # ---- attention backward
         check(L.tgn_attn_core_bwd(_p(w.proj), _p(w.nbr_l), _p(w.root_off), _p(w.ctr_l), w.R, _p(w.R_dev),
                                   self.H, self.C, _p(w.ee), _p(w.alpha), _p(self.d_emb), self.dropout, self.seed,
-                                  _p(self.step_dev), w.Nb, _p(w.d_proj), _p(w.d_ee), s))
+                                  _p(self.step_dev), self.K, w.Nb, _p(w.d_proj), _p(w.d_ee), s))
         split_e = max(1, min(16, w.E // 512))
         split_n = max(1, min(16, w.Nb // 512))
         g = [  # dW_edge += d_ee^T edge_attr ; dW_node += d_proj^T z ; d z = d_proj W_node

@@ -76,31 +76,58 @@ def init_state_dicts(raw_dim, hidden, num_nodes, seed):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and clock-event (throttle) reasons during the timed regions: NVML polled every few
+    milliseconds (falls back to one `nvidia-smi` query per sample when pynvml is unusable)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.stop_flag = index, False
+        self.sm, self.mx, self.reasons, self.how = [], [], set(), "nvidia-smi"
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h, self.nv, self.how = pynvml.nvmlDeviceGetHandleByIndex(phys), pynvml, "nvml"
+        except Exception:
+            self.h = None
+
+    def _sample_nvml(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(self.h))
+        self.reasons |= {n for n, b in self.BITS.items() if mask & b}
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+        r = [c.strip() for c in out.strip().split(",")]
+        if len(r) > 8 and r[1].replace(".", "").isdigit():
+            self.sm.append(float(r[1]))
+            self.mx.append(float(r[2]))
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            self.reasons |= {n for n, v in zip(names, r[5:9]) if v == "Active"}
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                self._sample_nvml() if self.h is not None else self._sample_smi()
             except Exception:
-                pass
-            time.sleep(0.2)
+                if self.h is not None:
+                    self.h = None       # NVML call failed: fall back to nvidia-smi
+                    self.how = "nvidia-smi"
+            time.sleep(0.005)
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v == "Active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.how}
 
 
 # --------------------------------------------------------------------------- CPU reference arm
@@ -422,24 +449,45 @@ def bench_eval_dp(dev, rank, world, n_batches, precision):
 
 def dominant_kernel_roofline(eng, dev):
     """The kernel with the largest share of the step is tgn::tgemm_kernel (TMA + tcgen05 GEMM,
-    ~30% over its 7 launches); its heaviest launch is the GRU gate GEMM pair
-    gi[S,3D] = x[S,Dx] W_ih^T + b, gh[S,3D] = h[S,D] W_hh^T + b (one launch).  It is timed
-    INSIDE eager training steps with CUDA events on the launching stream (engine probe), so the
-    operands are as warm/cold as in the real step.  Algorithmic work per launch:
-    2*S*(Dx+D)*3D flops; bytes S*(Dx+D)*4 + 3D*(Dx+D)*4 + 2*S*3D*4."""
-    eng.probe = {}
-    for _ in range(24):
-        eng.train_step(from_device=True)
+    ~45% over its 5 launches); its heaviest forward launch is the GRU gate GEMM pair
+    gi[S,3D] = x[S,Dx] W_ih^T + b, gh[S,3D] = h[S,D] W_hh^T + b (one launch).  It is timed on the
+    step's OWN operands (the buffers the last training step left behind, L2-warm as in the step):
+    a CUDA graph of 20 back-to-back launches, CUDA events around the replay, on the launching
+    stream.  Algorithmic work per launch: 2*S*(Dx+D)*3D flops;
+    bytes S*(Dx+D)*4 + 3D*(Dx+D)*4 + 2*S*3D*4."""
+    from tgn_b200 import ops
+    w, p, D = eng.w, eng.p, eng.D
+    S = int(w.Nb_dev.item())
+
+    def launch():
+        ops.gemm_batch([
+            ops.gemm_desc(w.x, eng.flat, w.gi, m=w.Nb, n=3 * D, k=eng.Dx, lda=eng.ldx, ldb=eng.ldx, ldc=3 * D,
+                          b_off=eng.off["memory_updater.weight_ih"], bias=p["memory_updater.bias_ih"], m_dev=w.Nb_dev),
+            ops.gemm_desc(w.h, eng.flat, w.gh, m=w.Nb, n=3 * D, k=D, lda=D, ldb=D, ldc=3 * D,
+                          b_off=eng.off["memory_updater.weight_hh"], bias=p["memory_updater.bias_hh"], m_dev=w.Nb_dev),
+        ], eng.prec)
+    for _ in range(3):
+        launch()
     torch.cuda.synchronize()
-    ev = eng.probe["gru_gate_gemm"][4:]
-    eng.probe = None
-    t = float(np.mean([a.elapsed_time(b) for a, b in ev])) * 1e-3
-    S = int(eng.w.Nb_dev.item())
-    Dx, D = eng.Dx, eng.D
+    reps = 20
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            launch()
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e-3 / reps)
+    t = float(np.median(ts))
+    Dx = eng.Dx
     flops = 2.0 * S * (Dx + D) * 3 * D
     nbytes = 4.0 * (S * (Dx + D) + 3 * D * (Dx + D) + 2 * S * 3 * D)
     return {"kernel": "tgn::tgemm_kernel (GRU gate GEMMs gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh, one launch)",
-            "rows": S, "seconds": t, "flops": flops, "bytes": nbytes, "launches_timed": len(ev), "prec": eng.prec}
+            "rows": S, "seconds": t, "flops": flops, "bytes": nbytes, "launches_timed": reps * 5, "prec": eng.prec}
 
 
 def roof_with_peak(r, peaks):

@@ -412,7 +412,7 @@ def bench_eval_dp(dev, rank, world, n_batches, precision):
     warm = 3
     data = synth.synth_events("tgbl-flight", seed=0, max_events=prefill + (n_batches + warm + 1) * B)
     N, De = data["num_nodes"], data["raw_dim"]
-    eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.1, use_graph=False,
+    eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.1, use_graph=True,
                     log_capacity=data["src"].size, seed=7, precision=precision)
     eng.load_state(*init_state_dicts(De, HIDDEN, N, seed=1))
     ev = {k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")}
@@ -545,7 +545,8 @@ def kernel_rooflines(dev, peaks):
     R, k = 2_000_000, 10
     roots = torch.randint(0, N, (R,), generator=g, dtype=torch.int32).to(dev)
     rts = (torch.rand(R, generator=g) * deg + 12).to(dev)
-    t = _time_launch(lambda: ops.tcsr_sample(indptr, indices, eid, ts, roots, rts, k), flush=flush)
+    coarse = ops.tcsr_build_index(ts)          # skip index, built once per graph (sampler_core.ParallelSampler.__init__)
+    t = _time_launch(lambda: ops.tcsr_sample(indptr, indices, eid, ts, roots, rts, k, coarse=coarse), flush=flush)
     nbytes = R * (8 + 4 * 7 + k * 12 + k * 20 + 8)   # indptr pair, ~log2(deg) probes, k entries in, k rows out, root
     out.append({"kernel": "tgn::tcsr_sample_kernel (recent-10, 2M roots, deg 113)", "bound": "hbm",
                 "achieved": nbytes / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": nbytes / t / 1e9 / hbm,

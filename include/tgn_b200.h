@@ -116,10 +116,17 @@ int32_t tgn_nbr_insert(const int64_t* src, const int64_t* dst, const float* t, i
  *          (Philox-4x32-10 keyed by seed, counter = (root index, draw)).
  * Outputs are compact and ordered by root: nbr/eid/ts/dts[*out_count],
  * col = root index, root_off[num_roots+1].
+ * Skip index (optional, built once per graph): coarse[b] = ts[16 b],
+ * tgn_tcsr_index_len(nnz) floats.  With it the per-root search reads the row's
+ * slice of the index plus ONE 64-byte block of the row instead of log2(deg)
+ * scattered sectors; results are identical.  coarse == NULL -> plain binary
+ * search (nnz ignored).  ts must be 16-byte aligned when coarse is given.
  * ------------------------------------------------------------------------- */
 int64_t tgn_tcsr_sample_ws_bytes(int32_t num_roots);
+int64_t tgn_tcsr_index_len(int64_t nnz);
+int32_t tgn_tcsr_build_index(const float* ts, int64_t nnz, float* coarse, void* stream);
 int32_t tgn_tcsr_sample(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
-                        const float* ts, int32_t num_nodes, const int32_t* root_nodes,
+                        const float* ts, const float* coarse, int64_t nnz, int32_t num_nodes, const int32_t* root_nodes,
                         const float* root_ts, int32_t num_roots, int32_t k, int32_t strategy,
                         float offset, float duration, uint64_t seed, int32_t* out_nbr,
                         int32_t* out_col, int32_t* out_eid, float* out_ts, float* out_dts,

@@ -42,7 +42,7 @@ def test_argument_validation_needs_no_gpu():
                             None, None, None)
     assert rc == _cabi.TGN_EINVAL and b"size_k" in lib.tgn_last_error()
     with pytest.raises(_cabi.TgnError):
-        _cabi.check(lib.tgn_tcsr_sample(None, None, None, None, 10, None, None, 4, 10, 7, 0.0, 0.0, 0,
+        _cabi.check(lib.tgn_tcsr_sample(None, None, None, None, None, 0, 10, None, None, 4, 10, 7, 0.0, 0.0, 0,
                                         None, None, None, None, None, None, None, None, None))
 
 

@@ -135,17 +135,21 @@ def _graph(rng, N, E, tmax):
     return orc.build_tcsr(src, dst, t, N)
 
 
+@pytest.mark.parametrize("skip_index", [False, True])
 @pytest.mark.parametrize("strategy", ["recent", "uniform"])
 @pytest.mark.parametrize("N,E,R,k,dur", [(50, 600, 300, 5, 0.0), (2000, 40000, 3000, 10, 0.0),
-                                         (2000, 40000, 1000, 20, 300.0), (10, 3, 40, 4, 0.0)])
-def test_tcsr_vs_oracle(ops, strategy, N, E, R, k, dur):
+                                         (2000, 40000, 1000, 20, 300.0), (10, 3, 40, 4, 0.0),
+                                         (3, 5000, 500, 10, 40.0)])
+def test_tcsr_vs_oracle(ops, strategy, N, E, R, k, dur, skip_index):
     rng = np.random.default_rng(E + k)
-    indptr, indices, eid, ts = _graph(rng, N, E, 5000)
+    indptr, indices, eid, ts = _graph(rng, N, E, 5000 if N > 3 else 300)     # N=3: long rows, many duplicate stamps
     roots = rng.integers(0, N, R).astype(np.int32)
-    rts = rng.integers(0, 5200, R).astype(np.float32)
+    rts = rng.integers(0, 5200 if N > 3 else 320, R).astype(np.float32)
     ref = orc.tcsr_sample_ref(indptr, indices, eid, ts, roots, rts, k, strategy, 0.0, dur, seed=11)
-    (n, c, e, t, d), off, cnt = ops.tcsr_sample(cu(indptr), cu(indices), cu(eid), cu(ts), cu(roots), cu(rts), k,
-                                                0 if strategy == "recent" else 1, 0.0, dur, 11)
+    ts_d = cu(ts)
+    coarse = ops.tcsr_build_index(ts_d) if skip_index else None
+    (n, c, e, t, d), off, cnt = ops.tcsr_sample(cu(indptr), cu(indices), cu(eid), ts_d, cu(roots), cu(rts), k,
+                                                0 if strategy == "recent" else 1, 0.0, dur, 11, coarse=coarse)
     m = int(cnt.item())
     assert m == ref[0].size
     for got, want in zip((n, c, e, t, d), ref[:5]):
@@ -186,8 +190,17 @@ def test_tcsr_large_properties(ops):
     indptr, indices, eid, ts = _graph(rng, N, E, 100000)
     R, k = 500_000, 10
     roots = rng.integers(0, N, R).astype(np.int32); rts = rng.integers(0, 100000, R).astype(np.float32)
-    (n, c, e, t, d), off, cnt = ops.tcsr_sample(cu(indptr), cu(indices), cu(eid), cu(ts), cu(roots), cu(rts), k)
+    g_d = [cu(indptr), cu(indices), cu(eid), cu(ts)]
+    (n, c, e, t, d), off, cnt = ops.tcsr_sample(*g_d, cu(roots), cu(rts), k)
     m = int(cnt)
+    # the skip-index search returns the identical sample (recent and windowed)
+    coarse = ops.tcsr_build_index(g_d[3])
+    for dur in (0.0, 5000.0):
+        a = ops.tcsr_sample(*g_d, cu(roots), cu(rts), k, 0, 0.0, dur)
+        b = ops.tcsr_sample(*g_d, cu(roots), cu(rts), k, 0, 0.0, dur, coarse=coarse)
+        ma = int(a[2])
+        assert ma == int(b[2]) and torch.equal(a[1], b[1])
+        assert all(torch.equal(x[:ma], y[:ma]) for x, y in zip(a[0], b[0]))
     c, t, d, off = c[:m].long(), t[:m], d[:m], off.long()
     assert m == int(off[-1]) and bool((c[1:] >= c[:-1]).all())
     rt = cu(rts)
@@ -356,6 +369,71 @@ def test_adam_matches_torch(ops):
         ops.adam_step(pg, g.to(DEV), m, v, step, 1e-3)
     torch.testing.assert_close(pg.cpu(), p.detach(), rtol=1e-5, atol=1e-6)
     assert float(step) == 5.0
+
+
+# ------------------------------------------------------------------ decoder kernels
+@pytest.mark.parametrize("B,D,Nb", [(1, 4, 3), (37, 32, 60), (200, 100, 500)])
+def test_dec_fused_matches_autograd(ops, B, D, Nb):
+    """tgn_dec_fused (forward + loss + all decoder gradients, one launch) against torch autograd on the
+    reference decoder (modules/decoder.py:24-27) + BCEWithLogitsLoss (pyg-mem-tgn.py:51)."""
+    from tgn_b200 import _cabi
+    L = _cabi.lib()
+    p = lambda t: None if t is None else t.data_ptr()
+    g = torch.Generator(device="cpu").manual_seed(B * D)
+    emb = torch.randn(Nb, D, generator=g, requires_grad=True)
+    lp = orc.LinkPredictor(D)
+    ids = torch.randint(0, Nb, (3 * B,), generator=g)
+    zs, zd, zn = emb[ids[:B]], emb[ids[B:2 * B]], emb[ids[2 * B:]]
+    logit = lambda a, b: lp.lin_final((lp.lin_src(a) + lp.lin_dst(b)).relu()).view(-1)
+    pos, neg = logit(zs, zd), logit(zs, zn)
+    crit = torch.nn.BCEWithLogitsLoss()
+    loss = crit(pos, torch.ones_like(pos)) + crit(neg, torch.zeros_like(neg))
+    loss.backward()
+    cu = lambda t: t.detach().to(DEV).contiguous()
+    w = {k: cu(v) for k, v in lp.state_dict().items()}
+    out_loss = torch.zeros(1, device=DEV); logits = torch.zeros(2 * B, device=DEV)
+    d_emb = torch.zeros(Nb, D, device=DEV)
+    gr = {k: torch.zeros_like(v) for k, v in w.items()}
+    emb_d, ids_d = cu(emb), cu(ids)      # keep the device copies alive across the asynchronous launch
+    _cabi.check(L.tgn_dec_fused(p(emb_d), p(ids_d), B, D, p(w["lin_src.weight"]), p(w["lin_src.bias"]),
+                                p(w["lin_dst.weight"]), p(w["lin_dst.bias"]), p(w["lin_final.weight"]),
+                                p(w["lin_final.bias"]), p(out_loss), p(logits), p(d_emb), p(gr["lin_src.weight"]),
+                                p(gr["lin_src.bias"]), p(gr["lin_dst.weight"]), p(gr["lin_dst.bias"]),
+                                p(gr["lin_final.weight"]), p(gr["lin_final.bias"]), 0))
+    torch.testing.assert_close(out_loss.cpu()[0], loss.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(logits.cpu(), torch.cat([pos, neg]).detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(d_emb.cpu(), emb.grad, rtol=1e-4, atol=1e-7)
+    for k, v in lp.named_parameters():
+        torch.testing.assert_close(gr[k].cpu(), v.grad, rtol=1e-4, atol=1e-7, msg=lambda m: f"{k}: {m}")
+
+
+def test_score_negs_counts(ops):
+    """tgn_score_negs: sigmoid scores of the positives / negatives and the two TGB rank counts."""
+    from tgn_b200 import _cabi
+    L = _cabi.lib()
+    p = lambda t: None if t is None else t.data_ptr()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    Nb, D, B, Q = 300, 100, 23, 57
+    hs, hd = torch.randn(Nb, D, generator=g), torch.randn(Nb, D, generator=g)
+    wf, bf = torch.randn(D, generator=g) * 0.1, torch.randn(1, generator=g)
+    src, dst = torch.randint(0, Nb, (B,), generator=g), torch.randint(0, Nb, (B,), generator=g)
+    neg = torch.randint(0, Nb, (B, Q), generator=g)
+    neg[:, 5] = dst                                    # exact ties with the positive
+    score = lambda a, b: torch.sigmoid((hs[a] + hd[b]).relu() @ wf + bf)
+    pos_r = score(src, dst)
+    neg_r = score(src.repeat_interleave(Q), neg.reshape(-1)).view(B, Q)
+    cu = lambda t: t.to(DEV).contiguous()
+    pos, negs = torch.zeros(B, device=DEV), torch.zeros(B, Q, device=DEV)
+    gt, ge = torch.zeros(B, dtype=torch.int32, device=DEV), torch.zeros(B, dtype=torch.int32, device=DEV)
+    keep = [cu(x) for x in (hs, hd, src, dst, neg, wf, bf)]   # alive across the asynchronous launch
+    _cabi.check(L.tgn_score_negs(*(p(x) for x in keep[:5]), B, Q, D, p(keep[5]), p(keep[6]),
+                                 p(pos), p(negs), p(gt), p(ge), 0))
+    torch.testing.assert_close(pos.cpu(), pos_r, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(negs.cpu(), neg_r, rtol=1e-5, atol=1e-6)
+    # counts are computed from the kernel's own scores: consistent with them, and ties count as >= only
+    assert torch.equal(gt.cpu().long(), (negs > pos[:, None]).sum(1).cpu()) and torch.equal(ge.cpu().long(), (negs >= pos[:, None]).sum(1).cpu())
+    assert bool((ge > gt).all())
+    assert torch.equal(ops.mrr(pos, negs).cpu(), 1.0 / (0.5 * (gt + ge).float().cpu() + 1.0))
 
 
 # ------------------------------------------------------------------ owner-partitioned memory

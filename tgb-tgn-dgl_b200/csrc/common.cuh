@@ -172,6 +172,41 @@ __device__ __forceinline__ long long lookback_prefix(unsigned long long* ws, int
   return prefix;
 }
 
+// Warp-wide variant: called by ALL 32 lanes of ONE warp of the CTA (tile_sum
+// uniform across the lanes).  Every round inspects 32 predecessors at once, so
+// a tile that becomes ready together with hundreds of others resolves its
+// prefix in a few L2 round trips instead of one per predecessor.
+__device__ __forceinline__ long long lookback_prefix_warp(unsigned long long* ws, int tile,
+                                                          long long tile_sum) {
+  volatile unsigned long long* st = ws + 1;
+  const unsigned long long kAgg = 1ull << 62, kInc = 2ull << 62, kMask = (1ull << 62) - 1;
+  const int lane = threadIdx.x & 31;
+  if (tile == 0) {
+    if (lane == 0) st[0] = kInc | (unsigned long long)tile_sum;
+    return 0;
+  }
+  if (lane == 0) st[tile] = kAgg | (unsigned long long)tile_sum;
+  long long prefix = 0;
+  for (int hi = tile - 1; hi >= 0; hi -= 32) {
+    const int p = hi - lane;
+    unsigned long long v = kInc;                       // lanes before tile 0 read as "inclusive 0"
+    if (p >= 0) {
+      do {
+        v = st[p];
+      } while ((v >> 62) == 0);
+    }
+    const unsigned inc = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+    const int first = inc ? __ffs(inc) - 1 : 32;       // nearest predecessor with an inclusive prefix
+    long long x = lane <= first ? (long long)(v & kMask) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    prefix += x;
+    if (inc) break;
+  }
+  if (lane == 0) st[tile] = kInc | (unsigned long long)(prefix + tile_sum);
+  return prefix;
+}
+
 // Philox-4x32-10 counter-based RNG (Salmon et al. 2011) -- used for uniform
 // neighbour draws and attention dropout so results do not depend on the
 // launch geometry.

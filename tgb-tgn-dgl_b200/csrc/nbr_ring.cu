@@ -71,15 +71,17 @@ __global__ void __launch_bounds__(kLookupThreads)
   }
   if (lane == 0) s_warp_tot[wid] = wtot;
   __syncthreads();
-  if (tid == 0) {
+  if (wid == 0) {
     long long tot = 0;
 #pragma unroll
     for (int w = 0; w < kLookupThreads / 32; ++w) tot += s_warp_tot[w];
-    long long pre = lookback_prefix(ws, tile, tot);
-    s_tile_prefix = pre;
-    if (tile == (ntiles > 0 ? ntiles : 1) - 1) {
-      root_off[R] = (int32_t)(pre + tot);
-      *out_count = (int32_t)(pre + tot);
+    long long pre = lookback_prefix_warp(ws, tile, tot);
+    if (lane == 0) {
+      s_tile_prefix = pre;
+      if (tile == (ntiles > 0 ? ntiles : 1) - 1) {
+        root_off[R] = (int32_t)(pre + tot);
+        *out_count = (int32_t)(pre + tot);
+      }
     }
   }
   __syncthreads();

@@ -4,9 +4,15 @@
 // reference tree, see SURVEY.md B1 for the restated algorithm).
 //
 // One CTA handles a tile of 256 roots:
-//   phase 1  one thread per root: binary search of the timestamp-sorted row for
-//            the candidate window [lo, hi)  (256 independent searches per CTA
-//            keep the memory system busy; a search is a dependent chain)
+//   phase 1  one thread per root: search of the timestamp-sorted row for the
+//            candidate window [lo, hi).  With the skip index (`coarse`, every
+//            16th timestamp, built once per graph by tgn_tcsr_build_index) the
+//            search is: binary search over the row's slice of the index (7
+//            entries = one 32-byte sector at degree 113), then ONE 64-byte
+//            block of the row read with four 128-bit loads and counted --
+//            ~3 dependent memory round trips instead of log2(deg)+1, and the
+//            block read is the same line the most-recent entries are emitted
+//            from.  Without the index: plain binary search.
 //   phase 2  block scan of the per-root output counts + chained scan across
 //            CTAs -> exact output offsets, outputs stay ordered by root
 //   phase 3  the tile's outputs are flattened over the CTA: every lane emits
@@ -30,10 +36,41 @@ __device__ __forceinline__ int lower_bound_f(const float* __restrict__ ts, int l
   return lo;
 }
 
+// Same result through the skip index: coarse[b] = ts[16 b].  Blocks b with
+// 16 b in [lo, hi) are monotone in b; the first such block whose head is
+// >= key bounds the answer to the 16 entries before that head.
+__device__ __forceinline__ int lower_bound_skip(const float* __restrict__ ts,
+                                                const float* __restrict__ coarse, int lo, int hi,
+                                                float key, long long nnz) {
+  if (hi - lo <= 4) return lower_bound_f(ts, lo, hi, key);
+  const int cb = lower_bound_f(coarse, (lo + 15) >> 4, (hi + 15) >> 4, key);
+  if (cb == 0) return lo;
+  const int base = (cb - 1) << 4;                       // aligned 16-entry block holding the answer
+  const int flo = base > lo ? base : lo;
+  const int fhi = (base + 16) < hi ? (base + 16) : hi;
+  if ((long long)base + 16 > nnz) return lower_bound_f(ts, flo, fhi, key);
+  const float4* p = reinterpret_cast<const float4*>(ts + base);
+  const float4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
+  const float v[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w,
+                       v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c += (base + i >= flo && base + i < fhi && v[i] < key) ? 1 : 0;
+  return flo + c;
+}
+
+__global__ void __launch_bounds__(256) tcsr_index_kernel(const float* __restrict__ ts, long long nnz,
+                                                         float* __restrict__ coarse) {
+  const long long nb = (nnz + 15) >> 4;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nb;
+       b += (long long)gridDim.x * blockDim.x)
+    coarse[b] = ts[b << 4];
+}
+
 __global__ void __launch_bounds__(kTcsrTile)
     tcsr_sample_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                        const int32_t* __restrict__ eid, const float* __restrict__ ts,
-                       int num_nodes, const int32_t* __restrict__ root_nodes,
+                       const float* __restrict__ coarse, long long nnz, int num_nodes, const int32_t* __restrict__ root_nodes,
                        const float* __restrict__ root_ts, int R, int k, int strategy,
                        float offset, float duration, uint64_t seed,
                        int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_col,
@@ -61,8 +98,13 @@ __global__ void __launch_bounds__(kTcsrTile)
     if (n >= 0 && n < num_nodes) {
       const int rs = __ldg(indptr + n), re = __ldg(indptr + n + 1);
       const float t_hi = tr + offset;
-      hi = lower_bound_f(ts, rs, re, t_hi);
-      lo = duration > 0.f ? lower_bound_f(ts, rs, hi, t_hi - duration) : rs;
+      if (coarse) {
+        hi = lower_bound_skip(ts, coarse, rs, re, t_hi, nnz);
+        lo = duration > 0.f ? lower_bound_skip(ts, coarse, rs, hi, t_hi - duration, nnz) : rs;
+      } else {
+        hi = lower_bound_f(ts, rs, re, t_hi);
+        lo = duration > 0.f ? lower_bound_f(ts, rs, hi, t_hi - duration) : rs;
+      }
     }
   }
   const int cand = hi - lo;
@@ -86,12 +128,14 @@ __global__ void __launch_bounds__(kTcsrTile)
   if (tid == kTcsrTile - 1) s_pref[kTcsrTile] = wbase + incl;
   __syncthreads();
   const int tile_total = s_pref[kTcsrTile];
-  if (tid == 0) {
-    long long pre = lookback_prefix(ws, tile, tile_total);
-    s_tile_prefix = pre;
-    if (tile == ntiles - 1) {
-      root_off[R] = (int32_t)(pre + tile_total);
-      *out_count = (int32_t)(pre + tile_total);
+  if (wid == 0) {
+    long long pre = lookback_prefix_warp(ws, tile, tile_total);
+    if (lane == 0) {
+      s_tile_prefix = pre;
+      if (tile == ntiles - 1) {
+        root_off[R] = (int32_t)(pre + tile_total);
+        *out_count = (int32_t)(pre + tile_total);
+      }
     }
   }
   __syncthreads();
@@ -139,8 +183,21 @@ int64_t tgn_tcsr_sample_ws_bytes(int32_t num_roots) {
   return (int64_t)(ntiles + 1) * 8;
 }
 
+int64_t tgn_tcsr_index_len(int64_t nnz) { return nnz > 0 ? (nnz + 15) / 16 : 0; }
+
+int32_t tgn_tcsr_build_index(const float* ts, int64_t nnz, float* coarse, void* stream) {
+  TGN_REQUIRE(nnz >= 0, "tcsr_build_index: bad size");
+  if (nnz == 0) return TGN_OK;
+  TGN_REQUIRE(ts && coarse, "tcsr_build_index: NULL pointer");
+  const long long nb = (nnz + 15) / 16;
+  const int grid = (int)((nb + 255) / 256 < 148 * 8 ? (nb + 255) / 256 : 148 * 8);
+  tcsr_index_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ts, nnz, coarse);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
 int32_t tgn_tcsr_sample(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
-                        const float* ts, int32_t num_nodes, const int32_t* root_nodes,
+                        const float* ts, const float* coarse, int64_t nnz, int32_t num_nodes, const int32_t* root_nodes,
                         const float* root_ts, int32_t num_roots, int32_t k, int32_t strategy,
                         float offset, float duration, uint64_t seed, int32_t* out_nbr,
                         int32_t* out_col, int32_t* out_eid, float* out_ts, float* out_dts,
@@ -150,6 +207,8 @@ int32_t tgn_tcsr_sample(const int32_t* indptr, const int32_t* indices, const int
               "tcsr_sample: unknown strategy %d", strategy);
   TGN_REQUIRE(indptr && indices && eid && ts && root_off && out_count && ws,
               "tcsr_sample: NULL pointer");
+  TGN_REQUIRE(!coarse || ((uintptr_t)ts % 16 == 0 && nnz > 0),
+              "tcsr_sample: the skip index needs a 16-byte aligned ts array and its length");
   cudaStream_t s = (cudaStream_t)stream;
   if (num_roots == 0) {
     TGN_CUDA(cudaMemsetAsync(root_off, 0, 4, s));
@@ -161,7 +220,7 @@ int32_t tgn_tcsr_sample(const int32_t* indptr, const int32_t* indices, const int
   const int ntiles = (num_roots + kTcsrTile - 1) / kTcsrTile;
   TGN_CUDA(cudaMemsetAsync(ws, 0, (size_t)(ntiles + 1) * 8, s));
   launch_k(tcsr_sample_kernel, dim3(ntiles), dim3(kTcsrTile), 0, s, 
-      indptr, indices, eid, ts, num_nodes, root_nodes, root_ts, num_roots, k, strategy, offset,
+      indptr, indices, eid, ts, coarse, (long long)nnz, num_nodes, root_nodes, root_ts, num_roots, k, strategy, offset,
       duration, seed, out_nbr, out_col, out_eid, out_ts, out_dts, root_off, out_count,
       (unsigned long long*)ws);
   TGN_LAUNCH_CHECK();

@@ -56,6 +56,7 @@ class ParallelSampler:
         self.indices = as_t(indices, torch.int32)
         self.eid = as_t(eid, torch.int32)
         self.ts = as_t(ts, torch.float32)
+        self.coarse = ops.tcsr_build_index(self.ts) if self.ts.numel() else None   # skip index, once per graph
         self.num_threads = num_thread_per_worker * num_workers
         self.num_layers = num_layers
         self.num_neighbors = list(num_neighbors)
@@ -83,7 +84,7 @@ class ParallelSampler:
                 rt = cur_ts[h if layer > 0 else 0]
                 (nbr, col, eid, ts, dts), off, cnt = ops.tcsr_sample(
                     self.indptr, self.indices, self.eid, self.ts, rn, rt, self.num_neighbors[layer],
-                    strategy, offset=-h * self.window_duration, duration=self.window_duration,
+                    strategy, offset=-h * self.window_duration, duration=self.window_duration, coarse=self.coarse,
                     seed=self.seed + 1315423911 * self._calls + 2654435761 * (layer * self.num_history + h))
                 out.append(dict(roots=rn, root_ts=rt, nbr=nbr, col=col, eid=eid, ts=ts, dts=dts,
                                 root_off=off, count=cnt))

@@ -391,11 +391,11 @@ class TGNEngine:
         self._all_reduce(w.g_lu)
 
     def _scatter_owned(self, n_id: Tensor, new_mem: Tensor, new_lu: Tensor, memory: Tensor, last_update: Tensor,
-                       src_rows: Optional[Tensor] = None):
+                       src_rows: Optional[Tensor] = None, num_dev: Optional[Tensor] = None):
         if self.world == 1:
-            ops.memory_scatter(n_id, new_mem, new_lu, memory, last_update, src_rows=src_rows)
+            ops.memory_scatter(n_id, new_mem, new_lu, memory, last_update, src_rows=src_rows, num_dev=num_dev)
         else:
-            check(_L().tgn_memory_scatter_owned(_p(n_id), n_id.numel(), None, _p(new_mem), _p(new_lu), 0, _p(src_rows),
+            check(_L().tgn_memory_scatter_owned(_p(n_id), n_id.numel(), _p(num_dev), _p(new_mem), _p(new_lu), 0, _p(src_rows),
                                                 self.D, self.rank, self.world, _p(memory), _p(last_update), _stream()))
 
     def _memory_fwd(self, w, n_id: Tensor, S: int, S_dev: Optional[Tensor]):
@@ -648,33 +648,35 @@ class TGNEngine:
         return self.loss
 
     # ------------------------------------------------------------------ evaluation
-    def _eval_work(self, R, E, Nb, B):
-        key = (R, E, Nb)
-        if getattr(self, "_ew_key", None) != key:
-            self._ew, self._ew_key = self._alloc_work(R, E, Nb, B, train=False), key
-            self._ew.hs = torch.empty((Nb, self.D), device=self.dev)
-            self._ew.hd = torch.empty((Nb, self.D), device=self.dev)
-        return self._ew
+    def _eval_ctx(self, B: int, Q: int) -> SimpleNamespace:
+        """Static buffers of the evaluation step for one (batch, negatives) shape."""
+        ctxs = self.__dict__.setdefault("_ectx", {})
+        c = ctxs.get((B, Q))
+        if c is None:
+            dev, D = self.dev, self.D
+            n_ids = B * (2 + Q)
+            R, E, Nb = self._bounds(B, roots=min(self.N, n_ids))
+            c = SimpleNamespace(B=B, Q=Q)
+            c.w = self._alloc_work(R, E, Nb, B, train=False)
+            c.w.hs, c.w.hd = torch.empty((Nb, D), device=dev), torch.empty((Nb, D), device=dev)
+            c.mw = self._alloc_work(1, 1, 2 * B, 1, train=False)         # memory update of the <= 2B touched nodes
+            c.ids = torch.zeros(n_ids, dtype=torch.long, device=dev)      # [src | dst | neg (row-major)]
+            c.ids_l = torch.zeros(n_ids, dtype=torch.long, device=dev)
+            c.t_i = torch.zeros(B, dtype=torch.long, device=dev)
+            c.t_f = torch.zeros(B, device=dev)
+            c.msg = torch.zeros((B, max(self.De, 1)), device=dev)
+            c.pos, c.negs = torch.zeros(B, device=dev), torch.zeros((B, max(Q, 1)), device=dev)
+            c.gt = torch.zeros(B, dtype=torch.int32, device=dev)
+            c.ge = torch.zeros(B, dtype=torch.int32, device=dev)
+            c.n_upd = torch.zeros(2 * B, dtype=torch.long, device=dev)
+            c.U_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            ctxs[(B, Q)] = c
+        return c
 
-    @torch.no_grad()
-    def eval_batch(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor,
-                   want_neg_scores: bool = True):
-        """test() body for one batch (epoch_utils.py:28-157): embeddings of the batch's nodes,
-        scores of the positives and of the [B,Q] negatives, then eval-mode update_state (store
-        first, then memory) and insert.  Returns (pos[B], neg[B,Q] or None, gt[B], ge[B]) with
-        gt/ge = number of negatives scoring above / not below the positive (TGB MRR counts).
-        `neg` may be any column shard of the full negative matrix (data-parallel evaluation):
-        the state update does not depend on it."""
-        dev, N, D, HC, L = self.dev, self.N, self.D, self.HC, _L()
-        self._unprime()
-        src, dst, neg = src.to(dev, torch.long), dst.to(dev, torch.long), neg.to(dev, torch.long)
-        t_i = t.to(dev, torch.long)
-        B, Q = neg.shape
-        ids = torch.cat([src, dst, neg.reshape(-1)]).contiguous()
-        R, E, Nb = self._bounds(B, roots=min(N, ids.numel()))
-        w = self._eval_work(R, E, Nb, B)
-        ids_l = torch.empty_like(ids)
-        self._sample(w, ids, ids_l)
+    def _eval_body(self, c: SimpleNamespace):
+        dev, N, D, L = self.dev, self.N, self.D, _L()
+        B, Q, w, mw = c.B, c.Q, c.w, c.mw
+        self._sample(w, c.ids, c.ids_l)
         s = _stream()
         if self.world == 1:
             check(L.tgn_gather_rows(_p(self.memory), _p(w.n_id), w.Nb, _p(w.Nb_dev), D, _p(w.z), s))
@@ -686,31 +688,52 @@ class TGNEngine:
         self._attention_fwd(w, z_in, lu_in, False)
         p, off = self.p, self.off
         ops.gemm_batch([
-            ops.gemm_desc(w.emb, self.flat, w.hs, m=Nb, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_src.weight"],
+            ops.gemm_desc(w.emb, self.flat, w.hs, m=w.Nb, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_src.weight"],
                           bias=p["lin_src.bias"], m_dev=w.Nb_dev),
-            ops.gemm_desc(w.emb, self.flat, w.hd, m=Nb, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_dst.weight"],
+            ops.gemm_desc(w.emb, self.flat, w.hd, m=w.Nb, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_dst.weight"],
                           bias=p["lin_dst.bias"], m_dev=w.Nb_dev),
         ], self.prec)
-        pos = torch.empty(B, device=dev)
-        negs = torch.empty((B, Q), device=dev) if want_neg_scores else None
-        gt = torch.empty(B, dtype=torch.int32, device=dev)
-        ge = torch.empty(B, dtype=torch.int32, device=dev)
-        check(L.tgn_score_negs(_p(w.hs), _p(w.hd), _p(ids_l), ids_l.data_ptr() + 8 * B, ids_l.data_ptr() + 16 * B,
-                               B, Q, D, _p(p["lin_final.weight"]), _p(p["lin_final.bias"]), _p(pos), _p(negs),
-                               _p(gt), _p(ge), s))
+        check(L.tgn_score_negs(_p(w.hs), _p(w.hd), _p(c.ids_l), c.ids_l.data_ptr() + 8 * B, c.ids_l.data_ptr() + 16 * B,
+                               B, Q, D, _p(p["lin_final.weight"]), _p(p["lin_final.bias"]), _p(c.pos), _p(c.negs),
+                               _p(c.gt), _p(c.ge), _stream()))
         # eval ordering of update_state: store first, then memory (memory_module.py:135-138)
-        self.store.update(src, dst, t_i, msg.to(dev, torch.float32))
-        self.log_base_dev += B
+        src, dst = c.ids[:B], c.ids[B:2 * B]
+        self.store.update(src, dst, c.t_i, c.msg, base_dev=self.log_base_dev)
+        check(L.tgn_unique_mark_rank(_p(c.ids), 2 * B, _p(self.bitmap), N, _p(c.n_upd), 2 * B, None, _p(c.U_dev), 0,
+                                     _stream()))
+        self._memory_fwd(mw, c.n_upd, 2 * B, c.U_dev)
+        self._scatter_owned(c.n_upd, mw.z, mw.lu, self.memory, self.last_update, num_dev=c.U_dev)
+        check(L.tgn_nbr_insert(_p(src), _p(dst), _p(c.t_f), B, 0, _p(self.cur_e_id_dev), self.K, N,
+                               _p(self.neighbors), _p(self.e_id), _p(self.t_ring), _stream()))
+
+    @torch.no_grad()
+    def eval_batch(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor,
+                   want_neg_scores: bool = True):
+        """test() body for one batch (epoch_utils.py:28-157): embeddings of the batch's nodes,
+        scores of the positives and of the [B,Q] negatives, then eval-mode update_state (store
+        first, then memory) and insert.  Returns (pos[B], neg[B,Q] or None, gt[B], ge[B]) with
+        gt/ge = number of negatives scoring above / not below the positive (TGB MRR counts).
+        `neg` may be any column shard of the full negative matrix (data-parallel evaluation):
+        the state update does not depend on it.  All buffers are static per (B, Q) and the step is
+        a captured CUDA graph; the returned tensors are overwritten by the next call of that shape."""
+        self._unprime()
+        B, Q = neg.shape
+        c = self._eval_ctx(B, Q)
+        if self.store.size + B > self.store.capacity:
+            self.store._alloc_log(max(2 * self.store.capacity, self.store.size + B))
+            self._graphs = {k: v for k, v in self._graphs.items() if k[0] != "eval"}   # pointers changed
+        c.ids[:B].copy_(src, non_blocking=True)
+        c.ids[B:2 * B].copy_(dst, non_blocking=True)
+        if Q:
+            c.ids[2 * B:].view(B, Q).copy_(neg, non_blocking=True)
+        c.t_i.copy_(t, non_blocking=True)
+        c.t_f.copy_(c.t_i)
+        if self.De:
+            c.msg.copy_(msg, non_blocking=True)
+        self._run(("eval", B, Q), lambda: self._eval_body(c))
         self.events_done += B
-        n_upd = ops.unique_relabel([src, dst], N)
-        S = n_upd.numel()
-        if getattr(self, "_mw_cap", 0) < S:
-            self._mw, self._mw_cap = self._alloc_work(1, 1, max(S, 2 * B), 1, train=False), max(S, 2 * B)
-        self._memory_fwd(self._mw, n_upd, S, None)
-        self._scatter_owned(n_upd, self._mw.z, self._mw.lu, self.memory, self.last_update)
-        ops.nbr_insert(src, dst, t_i.to(torch.float32), 0, self.neighbors, self.e_id, self.t_ring,
-                       cur_e_id_dev=self.cur_e_id_dev)
-        return pos, negs, gt, ge
+        self.store.size = self.events_done
+        return c.pos, (c.negs[:, :Q] if want_neg_scores else None), c.gt, c.ge
 
     def eval_scores(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor):
         """(pos[B], neg[B,Q]) probabilities of one evaluation batch (see eval_batch)."""

@@ -17,7 +17,7 @@ from . import _cabi
 from ._cabi import AGG_LAST, AGG_MEAN, SAMPLE_RECENT, SAMPLE_UNIFORM, SORT_MAX, check
 
 __all__ = [
-    "unique_relabel", "nbr_lookup", "nbr_insert", "tcsr_sample", "agg_last", "agg_mean",
+    "unique_relabel", "nbr_lookup", "nbr_insert", "tcsr_sample", "tcsr_build_index", "agg_last", "agg_mean",
     "MsgStore", "sgemm", "gru_cell", "time_encode", "temporal_attention", "link_score", "mrr",
     "memory_scatter", "gather_rows", "adam_step",
 ]
@@ -155,10 +155,21 @@ def nbr_insert(src: Tensor, dst: Tensor, t: Tensor, cur_e_id: int, neighbors: Te
 # ---------------------------------------------------------------------------
 # t-CSR sampler
 # ---------------------------------------------------------------------------
+def tcsr_build_index(ts: Tensor) -> Tensor:
+    """Skip index of a t-CSR timestamp array (every 16th entry); build once per graph."""
+    _need(ts, torch.float32, "ts")
+    coarse = torch.empty(max(_L().tgn_tcsr_index_len(ts.numel()), 1), dtype=torch.float32, device=ts.device)
+    check(_L().tgn_tcsr_build_index(_p(ts), ts.numel(), _p(coarse), _stream()))
+    return coarse
+
+
 def tcsr_sample(indptr: Tensor, indices: Tensor, eid: Tensor, ts: Tensor, roots: Tensor,
                 root_ts: Tensor, k: int, strategy: int = SAMPLE_RECENT, offset: float = 0.0,
-                duration: float = 0.0, seed: int = 0):
-    """Returns bound-sized (nbr, col, eid, ts, dts), root_off[R+1], count_dev."""
+                duration: float = 0.0, seed: int = 0, coarse: Optional[Tensor] = None):
+    """Returns bound-sized (nbr, col, eid, ts, dts), root_off[R+1], count_dev.
+    `coarse` = tcsr_build_index(ts) switches the per-root search to the skip index."""
+    if coarse is not None:
+        _need(coarse, torch.float32, "coarse")
     for name, x in (("indptr", indptr), ("indices", indices), ("eid", eid), ("roots", roots)):
         _need(x, torch.int32, name)
     _need(ts, torch.float32, "ts")
@@ -175,7 +186,7 @@ def tcsr_sample(indptr: Tensor, indices: Tensor, eid: Tensor, ts: Tensor, roots:
     off = torch.empty(R + 1, dtype=torch.int32, device=dev)
     cnt = torch.empty(1, dtype=torch.int32, device=dev)
     ws = torch.empty(max(_L().tgn_tcsr_sample_ws_bytes(R), 16) // 8, dtype=torch.int64, device=dev)
-    check(_L().tgn_tcsr_sample(_p(indptr), _p(indices), _p(eid), _p(ts), indptr.numel() - 1,
+    check(_L().tgn_tcsr_sample(_p(indptr), _p(indices), _p(eid), _p(ts), _p(coarse), ts.numel(), indptr.numel() - 1,
                                _p(roots), _p(root_ts), R, k, strategy, offset, duration,
                                int(seed) & 0xFFFFFFFFFFFFFFFF,
                                _p(o_n), _p(o_c), _p(o_e), _p(o_t), _p(o_d), _p(off), _p(cnt),

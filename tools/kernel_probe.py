@@ -1,5 +1,6 @@
 """Launches one hot-path kernel on a large input a few times (for ncu captures / quick timing).
-usage: python tools/kernel_probe.py {gemm3|gemm1|tcsr|lookup|agg_last|agg_mean}"""
+usage: python tools/kernel_probe.py {gemm3|gemm1|gru_pair|tcsr|tcsr_plain|lookup|agg_last|agg_mean}
+TGN_L2_FETCH=32|64|128 sets cudaLimitMaxL2FetchGranularity first (experiment only)."""
 import os, sys
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,6 +9,13 @@ from tgn_b200 import ops
 
 which = sys.argv[1]
 dev = "cuda"
+torch.zeros(1, device=dev)
+if os.environ.get("TGN_L2_FETCH"):
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["TGN_L2_FETCH"])))   # cudaLimitMaxL2FetchGranularity
+    v = ctypes.c_size_t(0); rt.cudaDeviceGetLimit(ctypes.byref(v), 5)
+    print("L2 fetch granularity", rc, v.value)
 g = torch.Generator(device="cpu").manual_seed(0)
 N = 352_637
 if which == "gru_pair":
@@ -26,7 +34,7 @@ elif which.startswith("gemm"):
     ld = 480 if "ld480" in which else Dx
     x = torch.randn(S, ld, device=dev); w = torch.randn(3 * D, ld, device=dev); o = torch.empty(S, 3 * D, device=dev)
     fn = lambda: ops.sgemm(x, w, m=S, n=3 * D, k=Dx, lda=ld, ldb=ld, out=o, prec=3 if which.startswith("gemm3") else 1)
-elif which == "tcsr":
+elif which in ("tcsr", "tcsr_plain"):
     deg = 113
     indptr = (torch.arange(N + 1, dtype=torch.int64) * deg).to(torch.int32).to(dev)
     ts = torch.arange(deg, dtype=torch.float32).repeat(N).to(dev)
@@ -35,7 +43,8 @@ elif which == "tcsr":
     R = 2_000_000
     roots = torch.randint(0, N, (R,), generator=g, dtype=torch.int32).to(dev)
     rts = (torch.rand(R, generator=g) * deg + 12).to(dev)
-    fn = lambda: ops.tcsr_sample(indptr, indices, eid, ts, roots, rts, 10)
+    coarse = ops.tcsr_build_index(ts) if which == "tcsr" else None
+    fn = lambda: ops.tcsr_sample(indptr, indices, eid, ts, roots, rts, 10, coarse=coarse)
 elif which == "lookup":
     K = 10
     nb = torch.randint(0, N, (N, K), generator=g).to(dev); ei = torch.randint(0, 1 << 30, (N, K), generator=g).to(dev)

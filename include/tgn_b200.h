@@ -133,6 +133,23 @@ int32_t tgn_tcsr_sample(const int32_t* indptr, const int32_t* indices, const int
                         int32_t* root_off, int32_t* out_count, void* ws, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * t-CSR construction (TGL gen_graph.py / `python tgb_gen_graph.py --data <name>`,
+ * reference README.md:4-5; output keys indptr/indices/ts/eid, utils.py:73; the
+ * generator script is absent from the reference tree).
+ * Directed entries: (src->dst, eid e) and, with add_reverse, (dst->src, eid e).
+ * Rows are sorted by (ts, eid), ts = float32(t[e]); a self-loop's forward entry
+ * precedes its reverse entry.  t is int64 (t_is_float=0) or float32.
+ * t_sorted != 0 states that t is non-decreasing in e (only the node digits are
+ * sorted then).  *bad_flag becomes 1 if an endpoint is outside [0, num_nodes).
+ * indptr[num_nodes+1]; indices/eid/ts[(add_reverse ? 2 : 1) * num_events].
+ * ------------------------------------------------------------------------- */
+int64_t tgn_tcsr_build_ws_bytes(int64_t num_events, int32_t add_reverse);
+int32_t tgn_tcsr_build(const int64_t* src, const int64_t* dst, const void* t, int32_t t_is_float,
+                       int64_t num_events, int32_t num_nodes, int32_t add_reverse,
+                       int32_t t_sorted, int32_t* indptr, int32_t* indices, int32_t* eid, float* ts,
+                       int32_t* bad_flag, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Message aggregators on materialised messages.
  * tgn_agg_last  = LastAggregator.forward   (modules/msg_agg.py:15-21):
  *   argmax[s] = first i with index[i]==s and maximal t[i]  (M if none)

@@ -157,6 +157,54 @@ def test_tcsr_vs_oracle(ops, strategy, N, E, R, k, dur, skip_index):
     assert np.array_equal(off.cpu().numpy(), ref[5])
 
 
+@pytest.mark.parametrize("N,E,tmax,sorted_t,rev", [(50, 600, 40, True, True), (50, 600, 40, False, True),
+                                                    (3000, 70000, 500, True, True), (3000, 70000, 500, False, False),
+                                                    (1, 5, 3, True, True), (70000, 9000, 10**9, False, True)])
+def test_tcsr_build_matches_oracle(ops, N, E, tmax, sorted_t, rev):
+    """GPU t-CSR builder (TGL gen_graph stand-in) == oracle lexsort by (row, ts, eid), bit for bit;
+    duplicate stamps, self-loops, isolated nodes, unsorted streams, float32 collapse of large stamps."""
+    rng = np.random.default_rng(N + E)
+    src = (rng.random(E) ** 2 * N).astype(np.int64); dst = rng.integers(0, N, E)
+    dst[::7] = src[::7]                                            # self-loops
+    t = rng.integers(0, tmax, E).astype(np.int64)
+    if sorted_t:
+        t = np.sort(t)
+    ref = orc.build_tcsr(src, dst, t, N, add_reverse=rev)
+    got = ops.tcsr_build(cu(src), cu(dst), cu(t), N, add_reverse=rev)
+    for g, w, name in zip(got, ref, ("indptr", "indices", "eid", "ts")):
+        assert np.array_equal(g.cpu().numpy(), w), name
+    gotf = ops.tcsr_build(cu(src), cu(dst), cu(t.astype(np.float32)), N, add_reverse=rev)
+    assert all(torch.equal(a, b) for a, b in zip(got, gotf))
+
+
+def test_tcsr_build_edge_cases(ops):
+    e = ops.tcsr_build(cu(np.zeros(0, np.int64)), cu(np.zeros(0, np.int64)), cu(np.zeros(0, np.int64)), 5)
+    assert e[0].cpu().tolist() == [0] * 6 and e[1].numel() == 0
+    from tgn_b200 import _cabi
+    with pytest.raises(_cabi.TgnError):
+        ops.tcsr_build(cu(np.array([0, 9])), cu(np.array([1, 2])), cu(np.array([0, 1])), 5)
+
+
+def test_tcsr_build_large_feeds_sampler(ops):
+    """4M events (8M entries) of the review shape: rows sorted by (ts, eid), degrees match a bincount,
+    and the sampler on the built graph agrees with the sampler on the oracle-built graph."""
+    rng = np.random.default_rng(9)
+    N, E = 352637, 4_000_000
+    src = (rng.random(E) ** 3 * N).astype(np.int64); dst = rng.integers(0, N, E)
+    t = np.sort(rng.integers(0, 600000, E)).astype(np.int64)
+    indptr, indices, eid, ts = ops.tcsr_build(cu(src), cu(dst), cu(t), N)
+    deg = torch.bincount(torch.cat([cu(src), cu(dst)]), minlength=N)
+    assert torch.equal((indptr[1:] - indptr[:-1]).long(), deg) and int(indptr[-1]) == 2 * E
+    row = torch.repeat_interleave(torch.arange(N, device=DEV), deg)
+    same = row[1:] == row[:-1]
+    assert bool(((ts[1:] > ts[:-1]) | ((ts[1:] == ts[:-1]) & (eid[1:] >= eid[:-1])))[same].all())
+    e64 = eid.long()
+    assert torch.equal(ts, cu(t)[e64].float())
+    assert bool(((indices.long() == cu(dst)[e64]) & (row == cu(src)[e64]) |
+                 (indices.long() == cu(src)[e64]) & (row == cu(dst)[e64])).all())
+    assert torch.equal(torch.bincount(e64, minlength=E), torch.full((E,), 2, device=DEV))
+
+
 def test_tcsr_empty_and_ragged(ops):
     indptr, indices, eid, ts = orc.build_tcsr([0, 0], [1, 1], [3.0, 3.0], 4)   # nodes 2,3 isolated; tie at t=3
     (n, c, e, t, d), off, cnt = ops.tcsr_sample(cu(indptr), cu(indices), cu(eid), cu(ts),

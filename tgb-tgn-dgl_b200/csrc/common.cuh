@@ -172,6 +172,10 @@ __device__ __forceinline__ long long lookback_prefix(unsigned long long* ws, int
   return prefix;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // Warp-wide variant: called by ALL 32 lanes of ONE warp of the CTA (tile_sum
 // uniform across the lanes).  Every round inspects 32 predecessors at once, so
 // a tile that becomes ready together with hundreds of others resolves its
@@ -204,6 +208,53 @@ __device__ __forceinline__ long long lookback_prefix_warp(unsigned long long* ws
     if (inc) break;
   }
   if (lane == 0) st[tile] = kInc | (unsigned long long)(prefix + tile_sum);
+  return prefix;
+}
+
+// Block-wide variant: called by ALL threads of the CTA (blockDim.x a multiple of
+// 32, tile_sum uniform); every thread gets the exclusive prefix.  One round
+// inspects blockDim.x predecessors, so even when every resident tile posts its
+// aggregate at the same moment the prefix resolves in one or two L2 round trips.
+__device__ __forceinline__ long long lookback_prefix_block(unsigned long long* ws, int tile,
+                                                           long long tile_sum) {
+  __shared__ long long s_lb_sum[32];
+  __shared__ int s_lb_first[32];
+  volatile unsigned long long* st = ws + 1;
+  const unsigned long long kAgg = 1ull << 62, kInc = 2ull << 62, kMask = (1ull << 62) - 1;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  if (tile == 0) {
+    if (tid == 0) st[0] = kInc | (unsigned long long)tile_sum;
+    return 0;
+  }
+  if (tid == 0) st[tile] = kAgg | (unsigned long long)tile_sum;
+  long long prefix = 0;
+  for (int hi = tile - 1; hi >= 0; hi -= (int)blockDim.x) {
+    const int p = hi - tid;
+    unsigned long long v = kInc;                       // slots before tile 0 read as "inclusive 0"
+    if (p >= 0) {
+      do {
+        v = st[p];
+      } while ((v >> 62) == 0);
+    }
+    const unsigned inc = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+    const int first = inc ? __ffs(inc) - 1 : 32;       // nearest inclusive predecessor within the warp's window
+    long long x = lane <= first ? (long long)(v & kMask) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) {
+      s_lb_sum[wid] = x;
+      s_lb_first[wid] = first;
+    }
+    __syncthreads();
+    bool done = false;
+    for (int w = 0; w < nw && !done; ++w) {
+      prefix += s_lb_sum[w];
+      done = s_lb_first[w] < 32;
+    }
+    __syncthreads();
+    if (done) break;
+  }
+  if (tid == 0) st[tile] = kInc | (unsigned long long)(prefix + tile_sum);
   return prefix;
 }
 

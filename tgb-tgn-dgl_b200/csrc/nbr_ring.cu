@@ -35,7 +35,6 @@ __global__ void __launch_bounds__(kLookupThreads)
   pdl_wait();
   pdl_launch();
   __shared__ int s_warp_tot[kLookupThreads / 32];
-  __shared__ long long s_tile_prefix;
   const int R = roots.get();
   const int ntiles = (R + tile_roots - 1) / tile_roots;
   const int tile = lookback_take_tile(ws);
@@ -45,47 +44,46 @@ __global__ void __launch_bounds__(kLookupThreads)
   const int nr = min(tile_roots, R - r0);
   const int npairs = nr > 0 ? nr * K : 0;
 
-  int64_t v_e[kLookupPairsPerThread], v_n[kLookupPairsPerThread], v_c[kLookupPairsPerThread];
+  int64_t v_e[kLookupPairsPerThread], v_n[kLookupPairsPerThread];
   float v_t[kLookupPairsPerThread];
   unsigned ball[kLookupPairsPerThread];
   int wtot = 0;
+  // all loads of the thread's 8 pairs are issued before the first ballot: a ballot is a
+  // convergence point the compiler does not move loads across, and one DRAM round trip per
+  // pair (8 in sequence) was the kernel's largest stall
+  int64_t cc[kLookupPairsPerThread];
 #pragma unroll
   for (int j = 0; j < kLookupPairsPerThread; ++j) {
     const int p = wid * (32 * kLookupPairsPerThread) + j * 32 + lane;
-    bool valid = false;
+    cc[j] = -1;
+    if (p < npairs) cc[j] = n_id[r0 + p / K];
+  }
+#pragma unroll
+  for (int j = 0; j < kLookupPairsPerThread; ++j) {
+    const int p = wid * (32 * kLookupPairsPerThread) + j * 32 + lane;
     v_e[j] = -1;
-    if (p < npairs) {
-      const int r = p / K, slot = p - r * K;
-      const int64_t c = n_id[r0 + r];
-      v_c[j] = c;
-      if (c >= 0 && c < num_nodes) {
-        const int64_t at = c * K + slot;
-        v_e[j] = eids[at];
-        v_n[j] = nbrs[at];
-        v_t[j] = ts[at];
-        valid = v_e[j] >= 0;
-      }
+    if (cc[j] >= 0 && cc[j] < num_nodes) {
+      const int64_t at = cc[j] * K + (p % K);
+      v_e[j] = eids[at];
+      v_n[j] = nbrs[at];
+      v_t[j] = ts[at];
     }
-    ball[j] = __ballot_sync(0xffffffffu, valid);
+  }
+#pragma unroll
+  for (int j = 0; j < kLookupPairsPerThread; ++j) {
+    ball[j] = __ballot_sync(0xffffffffu, v_e[j] >= 0);
     wtot += __popc(ball[j]);
   }
   if (lane == 0) s_warp_tot[wid] = wtot;
   __syncthreads();
-  if (wid == 0) {
-    long long tot = 0;
+  long long tot = 0;
 #pragma unroll
-    for (int w = 0; w < kLookupThreads / 32; ++w) tot += s_warp_tot[w];
-    long long pre = lookback_prefix_warp(ws, tile, tot);
-    if (lane == 0) {
-      s_tile_prefix = pre;
-      if (tile == (ntiles > 0 ? ntiles : 1) - 1) {
-        root_off[R] = (int32_t)(pre + tot);
-        *out_count = (int32_t)(pre + tot);
-      }
-    }
+  for (int w = 0; w < kLookupThreads / 32; ++w) tot += s_warp_tot[w];
+  long long base = lookback_prefix_block(ws, tile, tot);
+  if (tid == 0 && tile == (ntiles > 0 ? ntiles : 1) - 1) {
+    root_off[R] = (int32_t)(base + tot);
+    *out_count = (int32_t)(base + tot);
   }
-  __syncthreads();
-  long long base = s_tile_prefix;
   for (int w = 0; w < wid; ++w) base += s_warp_tot[w];
 #pragma unroll
   for (int j = 0; j < kLookupPairsPerThread; ++j) {
@@ -96,7 +94,7 @@ __global__ void __launch_bounds__(kLookupThreads)
       if (slot == 0) root_off[r0 + r] = (int32_t)pos;
       if ((ball[j] >> lane) & 1u) {
         out_nbr[pos] = v_n[j];
-        out_ctr[pos] = v_c[j];
+        out_ctr[pos] = n_id[r0 + r];
         out_eid[pos] = v_e[j];
         out_t[pos] = v_t[j];
         if (l0) {

@@ -128,8 +128,10 @@ __global__ void __launch_bounds__(kTcsrTile)
   if (tid == kTcsrTile - 1) s_pref[kTcsrTile] = wbase + incl;
   __syncthreads();
   const int tile_total = s_pref[kTcsrTile];
+  // warp-wide look-back: this kernel is DRAM-bound (ncu: 5.0 TB/s of sector traffic), and the
+  // block-wide variant's 256 polling threads per CTA cost more than the shorter wait saves
   if (wid == 0) {
-    long long pre = lookback_prefix_warp(ws, tile, tile_total);
+    const long long pre = lookback_prefix_warp(ws, tile, tile_total);
     if (lane == 0) {
       s_tile_prefix = pre;
       if (tile == ntiles - 1) {
@@ -144,30 +146,54 @@ __global__ void __launch_bounds__(kTcsrTile)
 
   // phase 3: flattened emit
   Philox rng(seed);
-  for (int q = tid; q < tile_total; q += kTcsrTile) {
-    int a = 0, b = kTcsrTile;  // largest r with s_pref[r] <= q
-    while (b - a > 1) {
-      int mid = (a + b) >> 1;
-      if (s_pref[mid] <= q) a = mid;
-      else b = mid;
+  constexpr int kU = 4;  // outputs per thread per round: all loads of a round are issued before its stores
+  for (int q0 = tid; q0 < tile_total; q0 += kU * kTcsrTile) {
+    int rr[kU], idx[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int q = q0 + u * kTcsrTile;
+      rr[u] = -1;
+      idx[u] = 0;
+      if (q < tile_total) {
+        int a = 0, b = kTcsrTile;  // largest r with s_pref[r] <= q
+        while (b - a > 1) {
+          int mid = (a + b) >> 1;
+          if (s_pref[mid] <= q) a = mid;
+          else b = mid;
+        }
+        const int r = a, j = q - s_pref[r];
+        const int rlo = s_lo[r], rhi = s_hi[r];
+        const int rc = rhi - rlo;
+        if (strategy == TGN_SAMPLE_RECENT || rc <= k) {
+          idx[u] = rhi - 1 - j;
+        } else {
+          uint4 x = rng((uint64_t)(tile * kTcsrTile + r), (uint64_t)j);
+          idx[u] = rlo + (int)(x.x % (uint32_t)rc);
+        }
+        rr[u] = r;
+      }
     }
-    const int r = a, j = q - s_pref[r];
-    const int rlo = s_lo[r], rhi = s_hi[r];
-    const int rc = rhi - rlo;
-    int idx;
-    if (strategy == TGN_SAMPLE_RECENT || rc <= k) {
-      idx = rhi - 1 - j;
-    } else {
-      uint4 x = rng((uint64_t)(tile * kTcsrTile + r), (uint64_t)j);
-      idx = rlo + (int)(x.x % (uint32_t)rc);
+    float tj[kU];
+    int nb[kU], ei[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (rr[u] >= 0) {
+        tj[u] = __ldg(ts + idx[u]);
+        nb[u] = __ldg(indices + idx[u]);
+        ei[u] = __ldg(eid + idx[u]);
+      }
     }
-    const float tj = __ldg(ts + idx);
-    const long long o = base + q;
-    out_nbr[o] = __ldg(indices + idx);
-    out_eid[o] = __ldg(eid + idx);
-    out_ts[o] = tj;
-    out_dts[o] = s_t[r] - tj;
-    out_col[o] = tile * kTcsrTile + r;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (rr[u] >= 0) {
+        const long long o = base + q0 + u * kTcsrTile;
+        __stcs(out_nbr + o, nb[u]);
+        __stcs(out_eid + o, ei[u]);
+        __stcs(out_ts + o, tj[u]);
+        __stcs(out_dts + o, s_t[rr[u]] - tj[u]);
+        __stcs(out_col + o, tile * kTcsrTile + rr[u]);
+      }
+    }
   }
 }
 

@@ -17,7 +17,7 @@ from . import _cabi
 from ._cabi import AGG_LAST, AGG_MEAN, SAMPLE_RECENT, SAMPLE_UNIFORM, SORT_MAX, check
 
 __all__ = [
-    "unique_relabel", "nbr_lookup", "nbr_insert", "tcsr_sample", "tcsr_build_index", "agg_last", "agg_mean",
+    "unique_relabel", "nbr_lookup", "nbr_insert", "tcsr_sample", "tcsr_build_index", "tcsr_build", "agg_last", "agg_mean",
     "MsgStore", "sgemm", "gru_cell", "time_encode", "temporal_attention", "link_score", "mrr",
     "memory_scatter", "gather_rows", "adam_step",
 ]
@@ -155,6 +155,36 @@ def nbr_insert(src: Tensor, dst: Tensor, t: Tensor, cur_e_id: int, neighbors: Te
 # ---------------------------------------------------------------------------
 # t-CSR sampler
 # ---------------------------------------------------------------------------
+def tcsr_build(src: Tensor, dst: Tensor, t: Tensor, num_nodes: int, add_reverse: bool = True,
+               t_sorted: Optional[bool] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """(indptr int32[N+1], indices int32, eid int32, ts float32) of the t-CSR graph TGL's gen_graph
+    writes to ext_full.npz, built on the device.  `t_sorted=None` checks on the device whether the
+    event stream is chronological (one reduction + host read; building a graph is not a per-batch op)."""
+    src = _need(src, torch.int64, "src")
+    dst = _need(dst, torch.int64, "dst")
+    t = t.contiguous()
+    if t.dtype not in (torch.int64, torch.float32) or not t.is_cuda:
+        raise _cabi.TgnError(f"t must be a CUDA int64 or float32 tensor, got {t.dtype} on {t.device}")
+    E, dev = src.numel(), src.device
+    if dst.numel() != E or t.numel() != E:
+        raise _cabi.TgnError("src, dst, t must have the same length")
+    if t_sorted is None:
+        t_sorted = bool((t[1:] >= t[:-1]).all()) if E > 1 else True
+    n = (2 if add_reverse else 1) * E
+    indptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    eid = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    ts = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(max(_L().tgn_tcsr_build_ws_bytes(E, int(add_reverse)), 256), dtype=torch.uint8, device=dev)
+    check(_L().tgn_tcsr_build(_p(src), _p(dst), _p(t), 1 if t.dtype == torch.float32 else 0, E, num_nodes,
+                              int(add_reverse), int(t_sorted), _p(indptr), _p(indices), _p(eid), _p(ts),
+                              _p(bad), _p(ws), _stream()))
+    if int(bad.item()):
+        raise _cabi.TgnError(f"tcsr_build: an endpoint is outside [0, {num_nodes})")
+    return indptr, indices[:n], eid[:n], ts[:n]
+
+
 def tcsr_build_index(ts: Tensor) -> Tensor:
     """Skip index of a t-CSR timestamp array (every 16th entry); build once per graph."""
     _need(ts, torch.float32, "ts")

@@ -459,7 +459,12 @@ def dominant_kernel_roofline(eng, dev):
     w, p, D = eng.w, eng.p, eng.D
     S = int(w.Nb_dev.item())
 
+    fused = getattr(eng, "fused_gru", False)
+
     def launch():
+        if fused:
+            eng._memory_gru(w, w.Nb, w.Nb_dev)       # tgn_gru_fused_fwd: both gate GEMMs + gate math, one launch
+            return
         ops.gemm_batch([
             ops.gemm_desc(w.x, eng.flat, w.gi, m=w.Nb, n=3 * D, k=eng.Dx, lda=eng.ldx, ldb=eng.ldx, ldc=3 * D,
                           b_off=eng.off["memory_updater.weight_ih"], bias=p["memory_updater.bias_ih"], m_dev=w.Nb_dev),
@@ -485,9 +490,15 @@ def dominant_kernel_roofline(eng, dev):
     t = float(np.median(ts))
     Dx = eng.Dx
     flops = 2.0 * S * (Dx + D) * 3 * D
-    nbytes = 4.0 * (S * (Dx + D) + 3 * D * (Dx + D) + 2 * S * 3 * D)
-    return {"kernel": "tgn::tgemm_kernel (GRU gate GEMMs gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh, one launch)",
-            "rows": S, "seconds": t, "flops": flops, "bytes": nbytes, "launches_timed": reps * 5, "prec": eng.prec}
+    if fused:   # x, h read (h twice: operand + blend), weights, h' and the 4 saved gate planes written
+        nbytes = 4.0 * (S * (Dx + 2 * D) + 3 * D * (Dx + D) + S * 5 * D)
+        name = ("tgn::gru_fused_kernel (GRUCell forward: gi = x W_ih^T, gh = h W_hh^T in TMEM, gate math in the "
+                "epilogue, one launch)")
+    else:
+        nbytes = 4.0 * (S * (Dx + D) + 3 * D * (Dx + D) + 2 * S * 3 * D)
+        name = "tgn::tgemm_kernel (GRU gate GEMMs gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh, one launch)"
+    return {"kernel": name, "rows": S, "seconds": t, "flops": flops, "bytes": nbytes, "launches_timed": reps * 5,
+            "prec": eng.prec, "fused": fused}
 
 
 def roof_with_peak(r, peaks):

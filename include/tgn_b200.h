@@ -314,6 +314,19 @@ typedef struct tgn_gemm_desc {
 int32_t tgn_gemm_batch(const tgn_gemm_desc* problems, int32_t count, int32_t precision,
                        void* stream);
 
+/* Fused GRUCell forward (torch.nn.GRUCell, reference modules/memory_module.py:72,172): both gate
+ * GEMMs on the tcgen05 tensor cores (operands TMA-staged, fp32 accumulators in TMEM: gi in
+ * columns [0,128), gh in [128,256) of a CTA that owns 128 rows x 40 hidden units) and the gate
+ * math in the epilogue -- gi / gh never reach global memory.
+ *   x [num, ldx] (dx live columns), h [num, dim], w_ih [3*dim, ldw_ih], w_hh [3*dim, dim]
+ *   out [num, dim] = h';  gates [num, 4*dim] (nullable) = r, z, n, gh_n for the backward pass
+ * Same results as tgn_gemm_batch + tgn_gru_gates_fwd at the same precision (1: tf32, 3: 3xTF32).
+ * dim, ldx, ldw_ih multiples of 4; all pointers 16-byte aligned; rows >= *num_dev are untouched. */
+int32_t tgn_gru_fused_fwd(const float* x, int32_t ldx, int32_t dx, const float* h, int32_t dim,
+                          const float* w_ih, int32_t ldw_ih, const float* w_hh, const float* b_ih,
+                          const float* b_hh, int32_t num, const int32_t* num_dev, int32_t precision,
+                          float* out, float* gates, void* stream);
+
 /* GRUCell / RNNCell gate math (torch.nn.GRUCell semantics, gate order r,z,n):
  *   gi = x W_ih^T + b_ih [S,3D], gh = h W_hh^T + b_hh [S,3D]  (from tgn_sgemm)
  *   r = sig(gi_r+gh_r), z = sig(gi_z+gh_z), n = tanh(gi_n + r*gh_n)

@@ -373,6 +373,40 @@ def test_gru_cell_fwd_bwd(ops, S, Dx, D):
         torch.testing.assert_close(a.grad.cpu(), b.grad, **tol)
 
 
+@pytest.mark.parametrize("prec", [3, 1])
+@pytest.mark.parametrize("S,Dx,D,live", [(1, 5, 4, 1), (333, 472, 100, 333), (4785, 301, 100, 4700), (130, 64, 40, 129),
+                                          (700, 100, 172, 700)])
+def test_gru_fused_fwd_matches_grucell(ops, S, Dx, D, live, prec):
+    """tgn_gru_fused_fwd (both gate GEMMs in TMEM, gate math in the epilogue) against torch.nn.GRUCell
+    (memory_module.py:72,172) and against the unfused path (tgn_gemm_batch + tgn_gru_gates_fwd)."""
+    torch.manual_seed(S + D)
+    cell = torch.nn.GRUCell(Dx, D)
+    x, h = torch.randn(S, Dx), torch.randn(S, D)
+    ref = cell(x, h).detach()
+    ldx = (Dx + 3) // 4 * 4
+    xp = torch.zeros(S, ldx); xp[:, :Dx] = x
+    wp = torch.zeros(3 * D, ldx); wp[:, :Dx] = cell.weight_ih.detach()
+    xd, hd, wd = xp.to(DEV), h.to(DEV), wp.to(DEV)
+    whh, bih, bhh = (q.detach().to(DEV).contiguous() for q in (cell.weight_hh, cell.bias_ih, cell.bias_hh))
+    out = torch.full((S, D), 7.0, device=DEV); gates = torch.full((S, 4 * D), 7.0, device=DEV)
+    ndev = torch.tensor([live], dtype=torch.int32, device=DEV)
+    ops.gru_fused_fwd(xd, hd, wd, whh, bih, bhh, dx=Dx, ldx=ldx, ldw=ldx, num=S, num_dev=ndev, prec=prec,
+                      out=out, gates=gates)
+    tol = dict(rtol=1e-5, atol=1e-5) if prec == 3 else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(out[:live].cpu(), ref[:live], **tol)
+    assert bool((out[live:] == 7.0).all()) and bool((gates[live:] == 7.0).all())      # dead rows untouched
+    # unfused path at the same precision
+    gi, gh = torch.empty(S, 3 * D, device=DEV), torch.empty(S, 3 * D, device=DEV)
+    ops.gemm_batch([ops.gemm_desc(xd, wd, gi, m=S, n=3 * D, k=Dx, lda=ldx, ldb=ldx, ldc=3 * D, bias=bih),
+                    ops.gemm_desc(hd, whh, gh, m=S, n=3 * D, k=D, lda=D, ldb=D, ldc=3 * D, bias=bhh)], prec)
+    from tgn_b200 import _cabi
+    out2, gates2 = torch.empty(S, D, device=DEV), torch.empty(S, 4 * D, device=DEV)
+    _cabi.check(_cabi.lib().tgn_gru_gates_fwd(gi.data_ptr(), gh.data_ptr(), hd.data_ptr(), None, S, None, D,
+                                              out2.data_ptr(), gates2.data_ptr(), 0))
+    torch.testing.assert_close(out[:live], out2[:live], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(gates[:live], gates2[:live], rtol=1e-6, atol=1e-6)
+
+
 def test_time_encode_fwd_bwd(ops):
     torch.manual_seed(0)
     te = orc.tp.TimeEncoder(100)

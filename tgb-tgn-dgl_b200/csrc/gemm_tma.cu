@@ -429,6 +429,260 @@ __global__ void __launch_bounds__(kGThreads, 1)
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Fused GRUCell forward (torch.nn.GRUCell as used at reference modules/memory_module.py:72,172):
+//   gi = x W_ih^T + b_ih,  gh = h W_hh^T + b_hh,  r = sig(gi_r + gh_r),  z = sig(gi_z + gh_z),
+//   n = tanh(gi_n + r * gh_n),  h' = n + z * (h - n)
+// One CTA owns 128 rows x 40 hidden units.  Its B tile is assembled by the TMA unit from
+// three 40-row boxes of the weight matrix (the r, z and n rows of those units), so the two
+// accumulators in TMEM -- gi in columns [0,128), gh in [128,256) -- hold complete (r, z, n)
+// triples and the gate math runs in the epilogue straight out of TMEM: gi / gh never exist in
+// global memory.  The K loop first sweeps x / W_ih into the gi accumulator, then h / W_hh into
+// the gh accumulator, through the same shared-memory ring, split pass and issuer as
+// tgemm_kernel.  Grid = ceil(S/128) x ceil(D/40) CTAs: one wave at the step's ~5k rows, D = 100.
+// ---------------------------------------------------------------------------
+constexpr int kGruUnits = 40;                       // hidden units per CTA (x 3 gates = 120 of 128 B-tile rows)
+constexpr int kGruBoxBytes = kGruUnits * GK * 4;    // 5120: five 1024-byte swizzle atoms
+
+struct alignas(64) GruMaps {
+  CUtensorMap x, h, wih, whh;
+};
+struct GruParams {
+  const float* h;       // [S, D]
+  const float* b_ih;    // [3D]
+  const float* b_hh;    // [3D]
+  float* out;           // [S, D]
+  float* gates;         // [S, 4D] nullable: r, z, n, gh_n
+  const int32_t* m_dev;
+  int m, dx, D, prec;
+};
+
+template <int N>
+__device__ __forceinline__ void g_tmem_ld(uint32_t taddr, uint32_t* v);
+template <>
+__device__ __forceinline__ void g_tmem_ld<16>(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void g_tmem_ld<4>(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr));
+}
+
+__device__ __forceinline__ float g_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+
+// gate math for NU consecutive units starting at local unit `u` (global unit j0 + u) of one row
+template <int NU>
+__device__ __forceinline__ void gru_epilogue_chunk(const GruParams& P, uint32_t trow, int row,
+                                                   bool row_ok, int j0, int u) {
+  uint32_t ir[NU], iz[NU], in_[NU], hr[NU], hz[NU], hn[NU];
+  g_tmem_ld<NU>(trow + (uint32_t)u, ir);
+  g_tmem_ld<NU>(trow + (uint32_t)(kGruUnits + u), iz);
+  g_tmem_ld<NU>(trow + (uint32_t)(2 * kGruUnits + u), in_);
+  g_tmem_ld<NU>(trow + (uint32_t)(GN + u), hr);
+  g_tmem_ld<NU>(trow + (uint32_t)(GN + kGruUnits + u), hz);
+  g_tmem_ld<NU>(trow + (uint32_t)(GN + 2 * kGruUnits + u), hn);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (!row_ok) return;
+  const int D = P.D;
+#pragma unroll
+  for (int c = 0; c < NU; c += 4) {
+    const int j = j0 + u + c;
+    if (j >= D) break;  // D is a multiple of 4: a float4 is entirely live or entirely dead
+    const float4 bir = *reinterpret_cast<const float4*>(P.b_ih + j);
+    const float4 biz = *reinterpret_cast<const float4*>(P.b_ih + D + j);
+    const float4 bin = *reinterpret_cast<const float4*>(P.b_ih + 2 * D + j);
+    const float4 bhr = *reinterpret_cast<const float4*>(P.b_hh + j);
+    const float4 bhz = *reinterpret_cast<const float4*>(P.b_hh + D + j);
+    const float4 bhn = *reinterpret_cast<const float4*>(P.b_hh + 2 * D + j);
+    const float4 hv = *reinterpret_cast<const float4*>(P.h + (long long)row * D + j);
+    float4 o_r, o_z, o_n, o_g, o_h;
+    const float* pbir = &bir.x; const float* pbiz = &biz.x; const float* pbin = &bin.x;
+    const float* pbhr = &bhr.x; const float* pbhz = &bhz.x; const float* pbhn = &bhn.x;
+    const float* phv = &hv.x;
+    float* por = &o_r.x; float* poz = &o_z.x; float* pon = &o_n.x; float* pog = &o_g.x;
+    float* poh = &o_h.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // same association as the unfused path: (acc + bias) per GEMM, then the gate sums
+      const float r = g_sigmoid((__uint_as_float(ir[c + e]) + pbir[e]) + (__uint_as_float(hr[c + e]) + pbhr[e]));
+      const float z = g_sigmoid((__uint_as_float(iz[c + e]) + pbiz[e]) + (__uint_as_float(hz[c + e]) + pbhz[e]));
+      const float ghn = __uint_as_float(hn[c + e]) + pbhn[e];
+      const float n = tanhf((__uint_as_float(in_[c + e]) + pbin[e]) + r * ghn);
+      por[e] = r; poz[e] = z; pon[e] = n; pog[e] = ghn;
+      poh[e] = n + z * (phv[e] - n);
+    }
+    *reinterpret_cast<float4*>(P.out + (long long)row * D + j) = o_h;
+    if (P.gates) {
+      float* g = P.gates + (long long)row * 4 * D + j;
+      *reinterpret_cast<float4*>(g) = o_r;
+      *reinterpret_cast<float4*>(g + D) = o_z;
+      *reinterpret_cast<float4*>(g + 2 * D) = o_n;
+      *reinterpret_cast<float4*>(g + 3 * D) = o_g;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kGThreads, 1)
+    gru_fused_kernel(const __grid_constant__ GruMaps maps, const __grid_constant__ GruParams P) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ __align__(1024) uint8_t g_smem[];
+  __shared__ __align__(8) uint64_t s_full[kGStages3], s_conv[kGStages3], s_empty[kGStages3], s_acc;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ngroups = (P.D + kGruUnits - 1) / kGruUnits;
+  const int ug = blockIdx.x % ngroups, tm = blockIdx.x / ngroups;
+  const int m0 = tm * GM, j0 = ug * kGruUnits;
+  const bool split3 = P.prec == 3;
+  constexpr int kStages = kGStages3;
+  constexpr int kStageBytes = kGStageBytes3;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g_smem) + 1023) &
+                                             ~(uintptr_t)1023);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < kStages; ++i) {
+      g_mbar_init(&s_full[i], 1);
+      g_mbar_init(&s_conv[i], kGConv);
+      g_mbar_init(&s_empty[i], 1);
+    }
+    g_mbar_init(&s_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wih) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.h) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.whh) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     g_smem_u32(&s_tmem)),
+                 "r"(2 * GN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // the unused B-tile rows (3 x 40 = 120 of 128) are never written by the TMA unit: zero them once
+  // so the split pass and the tensor core never touch uninitialised values
+  for (int s = 0; s < kStages; ++s) {
+    uint8_t* b_hi = smem + (size_t)s * kStageBytes + kGTileBytes + 3 * kGruBoxBytes;
+    for (int i = tid; i < (kGTileBytes - 3 * kGruBoxBytes) / 16; i += kGThreads)
+      reinterpret_cast<float4*>(b_hi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+
+  pdl_wait();
+  pdl_launch();
+  const int M = P.m_dev ? min(*P.m_dev, P.m) : P.m;
+  const int nk1 = (P.dx + GK - 1) / GK, nk2 = (P.D + GK - 1) / GK;
+  const bool live = m0 < M;
+  const int nk = live ? nk1 + nk2 : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % kStages;
+        if (kb >= kStages) g_mbar_wait(&s_empty[s], ((kb / kStages) - 1) & 1);
+        const uint32_t st = g_smem_u32(smem + (size_t)s * kStageBytes);
+        const bool ph2 = kb >= nk1;
+        const int k0 = (ph2 ? kb - nk1 : kb) * GK;
+        const CUtensorMap* ma = ph2 ? &maps.h : &maps.x;
+        const CUtensorMap* mb = ph2 ? &maps.whh : &maps.wih;
+        g_mbar_expect_tx(&s_full[s], kGTileBytes + 3 * kGruBoxBytes);
+        g_tma_2d(st, ma, &s_full[s], k0, m0);
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+          g_tma_2d(st + kGTileBytes + g * kGruBoxBytes, mb, &s_full[s], k0, g * P.D + j0);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = g_idesc(false, false);
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % kStages;
+      g_mbar_wait(split3 ? &s_conv[s] : &s_full[s], (kb / kStages) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const bool ph2 = kb >= nk1;
+        const uint32_t acc = tmem + (ph2 ? (uint32_t)GN : 0u);
+        const bool first = ph2 ? kb == nk1 : kb == 0;
+        const uint32_t a_hi = g_smem_u32(smem + (size_t)s * kStageBytes);
+        const uint32_t b_hi = a_hi + kGTileBytes, a_lo = a_hi + 2 * kGTileBytes,
+                       b_lo = a_hi + 3 * kGTileBytes;
+#pragma unroll
+        for (int kk = 0; kk < GK / 8; ++kk) {
+          const uint64_t dah = g_desc(a_hi + kk * 32u, false);
+          const uint64_t dbh = g_desc(b_hi + kk * 32u, false);
+          g_mma(acc, dah, dbh, idesc, (!first || kk > 0) ? 1u : 0u);
+          if (split3) {
+            const uint64_t dal = g_desc(a_lo + kk * 32u, false);
+            const uint64_t dbl = g_desc(b_lo + kk * 32u, false);
+            g_mma(acc, dah, dbl, idesc, 1u);
+            g_mma(acc, dal, dbh, idesc, 1u);
+          }
+        }
+        g_commit(&s_empty[s]);
+        if (kb == nk - 1) g_commit(&s_acc);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int et = tid - 64;
+    if (split3) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % kStages;
+        g_mbar_wait(&s_full[s], (kb / kStages) & 1);
+        const uint32_t a_hi = g_smem_u32(smem + (size_t)s * kStageBytes);
+        float4 va[4], vb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t o = (uint32_t)(i * kGConv + et) * 16u;
+          va[i] = g_lds4(a_hi + o);
+          vb[i] = g_lds4(a_hi + kGTileBytes + o);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t o = (uint32_t)(i * kGConv + et) * 16u;
+          float4 la, lb;
+          g_split4(va[i], la);
+          g_split4(vb[i], lb);
+          g_sts4(a_hi + 2 * kGTileBytes + o, la);
+          g_sts4(a_hi + 3 * kGTileBytes + o, lb);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        g_mbar_arrive(&s_conv[s]);
+      }
+    }
+    if (nk > 0) {
+      g_mbar_wait(&s_acc, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int q = warp & 3;
+      const int u0 = warp >= 6 ? kGruUnits / 2 : 0;   // warps 2-5: units 0..19, warps 6-9: 20..39
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+      if (j0 + u0 < P.D) {                              // warp-uniform
+        gru_epilogue_chunk<16>(P, trow, row, row_ok, j0, u0);
+        if (j0 + u0 + 16 < P.D) gru_epilogue_chunk<4>(P, trow, row, row_ok, j0, u0 + 16);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * GN));
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -521,6 +775,40 @@ int32_t tgn_gemm_batch(const tgn_gemm_desc* d, int32_t count, int32_t precision,
     attr_set = true;
   }
   launch_k(tgemm_kernel, dim3(tiles), dim3(kGThreads), smem, (cudaStream_t)stream, maps, prm);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_gru_fused_fwd(const float* x, int32_t ldx, int32_t dx, const float* h, int32_t dim,
+                          const float* w_ih, int32_t ldw_ih, const float* w_hh, const float* b_ih,
+                          const float* b_hh, int32_t num, const int32_t* num_dev, int32_t precision,
+                          float* out, float* gates, void* stream) {
+  TGN_REQUIRE(num >= 0 && dim >= 4 && dx >= 1, "gru_fused_fwd: bad sizes");
+  TGN_REQUIRE(precision == 1 || precision == 3, "gru_fused_fwd: precision must be 1 (tf32) or 3 (3xtf32)");
+  TGN_REQUIRE((dim & 3) == 0 && (ldx & 3) == 0 && (ldw_ih & 3) == 0 && ldx >= dx && ldw_ih >= dx,
+              "gru_fused_fwd: dim, ldx, ldw_ih must be multiples of 4 and cover dx");
+  if (num == 0) return TGN_OK;
+  TGN_REQUIRE(x && h && w_ih && w_hh && b_ih && b_hh && out, "gru_fused_fwd: NULL pointer");
+  const uintptr_t al = (uintptr_t)x | (uintptr_t)h | (uintptr_t)w_ih | (uintptr_t)w_hh |
+                       (uintptr_t)b_ih | (uintptr_t)b_hh | (uintptr_t)out | (uintptr_t)gates;
+  TGN_REQUIRE((al & 15) == 0, "gru_fused_fwd: pointers must be 16-byte aligned");
+  GruMaps maps;
+  int rc;
+  if ((rc = make_map(&maps.x, x, num, dx, ldx, GK, GM, false)) != TGN_OK) return rc;
+  if ((rc = make_map(&maps.h, h, num, dim, dim, GK, GM, false)) != TGN_OK) return rc;
+  if ((rc = make_map(&maps.wih, w_ih, 3 * dim, dx, ldw_ih, GK, kGruUnits, false)) != TGN_OK) return rc;
+  if ((rc = make_map(&maps.whh, w_hh, 3 * dim, dim, dim, GK, kGruUnits, false)) != TGN_OK) return rc;
+  GruParams P;
+  P.h = h; P.b_ih = b_ih; P.b_hh = b_hh; P.out = out; P.gates = gates; P.m_dev = num_dev;
+  P.m = num; P.dx = dx; P.D = dim; P.prec = precision;
+  const size_t smem = (size_t)kGStages3 * kGStageBytes3 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TGN_CUDA(cudaFuncSetAttribute(gru_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int tiles = ceil_div(num, GM) * ceil_div(dim, kGruUnits);
+  launch_k(gru_fused_kernel, dim3(tiles), dim3(kGThreads), smem, (cudaStream_t)stream, maps, P);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

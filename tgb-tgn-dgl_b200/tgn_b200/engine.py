@@ -141,6 +141,7 @@ class TGNEngine:
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.training = True
         self.fused_decoder = _L().tgn_dec_fused_smem_bytes(hidden) <= 215 * 1024 and hidden <= 128
+        self.fused_gru = hidden % 4 == 0    # tgn_gru_fused_fwd (TMA strides need 16-byte rows)
         self.probe = None   # bench.py: {"name": [(start_event, stop_event), ...]} filled in eager steps
 
     # ------------------------------------------------------------------ layout helpers
@@ -420,6 +421,14 @@ class TGNEngine:
 
     def _memory_gru(self, w, S: int, S_dev: Optional[Tensor]):
         p, D, L, s = self.p, self.D, _L(), _stream()
+        if self.fused_gru:
+            # both gate GEMMs and the gate math in one launch; gi / gh stay in TMEM
+            self._timed("gru_gate_gemm", lambda: check(L.tgn_gru_fused_fwd(
+                _p(w.x), self.ldx, self.Dx, _p(w.h), D, self.flat.data_ptr() + 4 * self.off["memory_updater.weight_ih"],
+                self.ldx, self.flat.data_ptr() + 4 * self.off["memory_updater.weight_hh"],
+                _p(p["memory_updater.bias_ih"]), _p(p["memory_updater.bias_hh"]), S, _p(S_dev), self.prec,
+                _p(w.z), _p(w.gates), s)))
+            return
         self._timed("gru_gate_gemm", lambda: ops.gemm_batch([
             ops.gemm_desc(w.x, self.flat, w.gi, m=S, n=3 * D, k=self.Dx, lda=self.ldx, ldb=self.ldx, ldc=3 * D,
                           b_off=self.off["memory_updater.weight_ih"], bias=p["memory_updater.bias_ih"], m_dev=S_dev),
@@ -573,6 +582,7 @@ class TGNEngine:
         # ---- GRU backward (torch.nn.GRUCell, memory_module.py:72,172)
         check(L.tgn_gru_gates_bwd_bias(_p(w.d_z), _p(w.gates), _p(w.h), w.Nb, _p(w.Nb_dev), D, _p(w.d_gi),
                                        _p(w.d_gh), gptr("memory_updater.bias_ih"), gptr("memory_updater.bias_hh"), s))
+        c0 = (2 * D + self.De) & ~3
         ops.gemm_batch([
             ops.gemm_desc(w.d_gi, w.x, fg, m=3 * D, n=self.Dx, k=w.Nb, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
                           trans_a=True, trans_b=True, mode=2, split_k=split_n, k_dev=w.Nb_dev,
@@ -580,9 +590,10 @@ class TGNEngine:
             ops.gemm_desc(w.d_gh, w.h, fg, m=3 * D, n=D, k=w.Nb, lda=3 * D, ldb=D, ldc=D, trans_a=True,
                           trans_b=True, mode=2, split_k=split_n, k_dev=w.Nb_dev,
                           c_off=off["memory_updater.weight_hh"]),
-            # d x = d_gi W_ih (only its time-encoding columns are consumed)
-            ops.gemm_desc(w.d_gi, fl, w.d_x, m=w.Nb, n=self.Dx, k=3 * D, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
-                          trans_b=True, b_off=off["memory_updater.weight_ih"], m_dev=w.Nb_dev),
+            # d x = d_gi W_ih: only the time-encoding columns [2D+De, Dx) are consumed, so only those are
+            # computed (from the 16-byte aligned column below them): 1 column tile per row tile instead of 3
+            ops.gemm_desc(w.d_gi, fl, w.d_x, m=w.Nb, n=self.Dx - c0, k=3 * D, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
+                          trans_b=True, b_off=off["memory_updater.weight_ih"] + c0, c_off=c0, m_dev=w.Nb_dev),
         ], self.prec)
         if self.Dt:
             check(L.tgn_time_bwd_sin(_p(w.sel_dt), _p(w.sel_ev), w.Nb, _p(w.Nb_dev), _p(w.sn_m), self.Dt,

@@ -17,7 +17,7 @@ from . import _cabi
 from ._cabi import AGG_LAST, AGG_MEAN, SAMPLE_RECENT, SAMPLE_UNIFORM, SORT_MAX, check
 
 __all__ = [
-    "unique_relabel", "nbr_lookup", "nbr_insert", "tcsr_sample", "tcsr_build_index", "tcsr_build", "agg_last", "agg_mean",
+    "unique_relabel", "nbr_lookup", "nbr_insert", "tcsr_sample", "tcsr_build_index", "tcsr_build", "gru_fused_fwd", "agg_last", "agg_mean",
     "MsgStore", "sgemm", "gru_cell", "time_encode", "temporal_attention", "link_score", "mrr",
     "memory_scatter", "gather_rows", "adam_step",
 ]
@@ -556,6 +556,19 @@ class _GRUFn(torch.autograd.Function):
 def gru_cell(x: Tensor, h: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor,
              num_dev: Optional[Tensor] = None) -> Tensor:
     return _GRUFn.apply(x.contiguous(), h.contiguous(), w_ih, w_hh, b_ih, b_hh, num_dev)
+
+
+def gru_fused_fwd(x: Tensor, h: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor, *, dx: int, ldx: int,
+                  ldw: int, num: int, num_dev: Optional[Tensor] = None, prec: int = 3, out: Optional[Tensor] = None,
+                  gates: Optional[Tensor] = None) -> Tensor:
+    """Fused GRUCell forward (tgn_gru_fused_fwd): gate GEMMs on tcgen05 + gate math in the epilogue.
+    x [num, ldx] with dx live columns, w_ih [3D, ldw]; all operands 16-byte aligned."""
+    D = h.shape[-1]
+    if out is None:
+        out = torch.empty((num, D), dtype=torch.float32, device=h.device)
+    check(_L().tgn_gru_fused_fwd(_p(x), ldx, dx, _p(h), D, _p(w_ih), ldw, _p(w_hh), _p(b_ih), _p(b_hh), num,
+                                 _p(num_dev), prec, _p(out), _p(gates), _stream()))
+    return out
 
 
 def rnn_cell(x: Tensor, h: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor) -> Tensor:

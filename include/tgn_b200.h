@@ -535,6 +535,24 @@ int32_t tgn_link_score(const float* hs, const float* hd, const int64_t* a_rows,
 int32_t tgn_mrr(const float* pos, const float* neg, int32_t num_pos, int32_t num_neg,
                 float* rr_out, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Negatives and the epoch metric on the device (no per-batch host round trip).
+ * tgn_neg_dest_sample = neg_sampler.NegLinkSamplerDest.sample (neg_sampler.py:8-23):
+ *   out[i] uniform over dst_nodes[num_dst], redrawn while == pos_dst[i] (kept if num_dst == 1).
+ * tgn_neg_fill: out[batch, num_neg] uniform over [lo, hi) without pos_dst[i]
+ *   (synthetic stand-in for tgb negative_sampler.query_batch, epoch_utils.py:43).
+ * Both draw from Philox-4x32-10 keyed by seed with counters (row, call): the same (seed, call)
+ * reproduces the same negatives for any launch geometry.
+ * tgn_rank_accum (epoch_utils.py:108-113,163): acc[0] += mean_i 1/(1 + (gt[i]+ge[i])/2),
+ *   acc[1] += 1; epoch MRR = acc[0] / acc[1].  rr_out (nullable) gets the per-positive values.
+ * ------------------------------------------------------------------------- */
+int32_t tgn_neg_dest_sample(const int64_t* dst_nodes, int32_t num_dst, const int64_t* pos_dst,
+                            int32_t batch, uint64_t seed, uint64_t call, int64_t* out, void* stream);
+int32_t tgn_neg_fill(const int64_t* pos_dst, int32_t batch, int32_t num_neg, int64_t lo, int64_t hi,
+                     uint64_t seed, uint64_t call, int64_t* out, void* stream);
+int32_t tgn_rank_accum(const int32_t* gt, const int32_t* ge, int32_t batch, double* acc, float* rr_out,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

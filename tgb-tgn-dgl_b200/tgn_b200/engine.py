@@ -658,6 +658,33 @@ class TGNEngine:
         self.store.size = self.events_done   # host mirror of log_base_dev (graph replays skip the Python body)
         return self.loss
 
+    def train_step_logged(self, **kw) -> Optional[float]:
+        """train_step() with a pipelined loss read-back for logging loops: the device->host copy of
+        THIS step's loss is enqueued into pinned memory behind the step, and the value returned is the
+        loss of the PREVIOUS call (None on the first one) -- the host never waits for the step it has
+        just launched, so the GPU does not idle while the next batch is staged.  flush_loss() returns
+        the last step's loss."""
+        if not hasattr(self, "_loss_pin"):
+            self._loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
+            self._loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._loss_n = 0
+        loss = self.train_step(**kw)
+        i = self._loss_n & 1
+        self._loss_pin[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+        self._loss_ev[i].record()
+        self._loss_n += 1
+        if self._loss_n < 2:
+            return None
+        self._loss_ev[i ^ 1].synchronize()
+        return float(self._loss_pin[i ^ 1])
+
+    def flush_loss(self) -> Optional[float]:
+        if not getattr(self, "_loss_n", 0):
+            return None
+        i = (self._loss_n - 1) & 1
+        self._loss_ev[i].synchronize()
+        return float(self._loss_pin[i])
+
     # ------------------------------------------------------------------ evaluation
     def _eval_ctx(self, B: int, Q: int) -> SimpleNamespace:
         """Static buffers of the evaluation step for one (batch, negatives) shape."""

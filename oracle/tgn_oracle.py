@@ -281,6 +281,62 @@ class TGNMemory(torch.nn.Module):
         super().train(mode)
 
 
+class DyRepMemory(TGNMemory):
+    """modules/memory_module.py:218-421: TGNMemory with a `gru` or `rnn` updater (:259-265) whose
+    messages may use the current embeddings of the batch's nodes instead of their memory (:389-408)."""
+
+    def __init__(self, num_nodes, raw_msg_dim, memory_dim, time_dim, message_module, aggregator_module,
+                 memory_updater_type, use_src_emb_in_msg=False, use_dst_emb_in_msg=False):
+        assert memory_updater_type in ["gru", "rnn"]                          # :258
+        super().__init__(num_nodes, raw_msg_dim, memory_dim, time_dim, message_module, aggregator_module,
+                         memory_updater_type)
+        self.use_src_emb_in_msg, self.use_dst_emb_in_msg = use_src_emb_in_msg, use_dst_emb_in_msg
+        self._emb = None
+
+    def update_state(self, src, dst, t, raw_msg, embeddings=None, assoc=None):   # :316-329
+        self._emb = (embeddings, assoc) if embeddings is not None else None
+        try:
+            super().update_state(src, dst, t, raw_msg)
+        finally:
+            self._emb = None
+
+    def _compute_msg(self, n_id, msg_store, msg_module):                      # :375-412
+        data = [msg_store[i] for i in n_id.tolist()]
+        src, dst, t, raw_msg = list(zip(*data))
+        src, dst, t, raw_msg = torch.cat(src), torch.cat(dst), torch.cat(t), torch.cat(raw_msg)
+        t_rel = t - self.last_update[src]
+        t_enc = self.time_enc(t_rel.to(raw_msg.dtype))
+        z_src, z_dst = self.memory[src], self.memory[dst]
+        if self._emb is not None:
+            emb, assoc = self._emb
+            ids = set(n_id.tolist())
+            if self.use_src_emb_in_msg:                                       # :389-397 (`s in n_id` loop)
+                hit = [i for i, s_ in enumerate(src.tolist()) if s_ in ids]
+                if hit:
+                    z_src[hit] = emb[assoc[src[hit]]]
+            if self.use_dst_emb_in_msg:                                       # :399-408
+                hit = [i for i, d_ in enumerate(dst.tolist()) if d_ in ids]
+                if hit:
+                    z_dst[hit] = emb[assoc[dst[hit]]]
+        return msg_module(z_src, z_dst, raw_msg, t_enc), t, src, dst
+
+
+class TimeEmbedding(torch.nn.Module):
+    """modules/emb_module.py:32-52 (JODIE projection)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.embedding_layer = torch.nn.Linear(1, out_channels)
+        stdv = 1.0                                                            # 1/sqrt(fan_in), fan_in = 1 (:39-43)
+        self.embedding_layer.weight.data.normal_(0, stdv)
+        self.embedding_layer.bias.data.normal_(0, stdv)
+
+    def forward(self, x, last_update, t):
+        rel_t = last_update - t                                               # :49
+        return x * (1 + self.embedding_layer(rel_t.to(x.dtype).unsqueeze(1)))  # :50
+
+
 class GraphAttentionEmbedding(torch.nn.Module):
     """modules/emb_module.py:11-29"""
 

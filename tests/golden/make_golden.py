@@ -205,6 +205,62 @@ def gen_embedding(path):
     np.savez_compressed(path, **out)
 
 
+def gen_variants(path):
+    """DyRepMemory (memory_module.py:218-421: rnn / gru updater, embeddings substituted for memory in the
+    messages, :389-408) and TimeEmbedding (emb_module.py:32-52), both from the unmodified reference."""
+    from modules.memory_module import DyRepMemory
+    from modules.msg_agg import LastAggregator, MeanAggregator
+    from modules.msg_func import IdentityMessage
+    from modules.emb_module import TimeEmbedding
+    out = {}
+    case = 0
+    for (N, De, D, B, steps, aggr, upd, use_s, use_d) in [(40, 6, 8, 10, 6, "last", "rnn", True, True),
+                                                          (60, 4, 12, 16, 5, "mean", "gru", False, True),
+                                                          (50, 3, 8, 12, 5, "last", "rnn", True, False)]:
+        torch.manual_seed(40 + case)
+        rng = np.random.default_rng(50 + case)
+        mem = DyRepMemory(N, De, D, D, IdentityMessage(De, D, D),
+                          LastAggregator() if aggr == "last" else MeanAggregator(), upd,
+                          use_src_emb_in_msg=use_s, use_dst_emb_in_msg=use_d)
+        with torch.no_grad():
+            mem.time_enc.lin.weight.mul_(0.05)
+        out.update(sd_np(mem, f"d{case}_sd"))
+        mem.train()
+        tcur = 0
+        for s in range(steps):
+            src = rng.integers(0, N // 2, B).astype(np.int64); dst = rng.integers(N // 2, N, B).astype(np.int64)
+            t = np.sort(rng.choice(np.arange(tcur + 1, tcur + 200), B, replace=False)).astype(np.int64); tcur = int(t[-1])
+            raw = rng.standard_normal((B, De)).astype(np.float32)
+            q = np.unique(np.concatenate([src, dst, rng.integers(0, N, 6)])).astype(np.int64)
+            if s == steps - 2:
+                mem.eval()
+            z, lu = mem(torch.from_numpy(q))
+            # "current embeddings" of the batch's nodes, addressed through assoc as in the callers
+            emb = rng.standard_normal((q.size, D)).astype(np.float32)
+            assoc = np.zeros(N, np.int64); assoc[q] = np.arange(q.size)
+            pre = f"d{case}_s{s}_"
+            out[pre + "q"], out[pre + "z"], out[pre + "lu"] = q, z.detach().numpy(), lu.detach().numpy()
+            out[pre + "src"], out[pre + "dst"], out[pre + "t"], out[pre + "raw"] = src, dst, t, raw
+            out[pre + "emb"], out[pre + "assoc"] = emb, assoc
+            out[pre + "training"] = np.array(int(mem.training))
+            mem.update_state(torch.from_numpy(src), torch.from_numpy(dst), torch.from_numpy(t),
+                             torch.from_numpy(raw), torch.from_numpy(emb), torch.from_numpy(assoc))
+            mem.detach()
+            out[pre + "memory"] = mem.memory.detach().numpy().copy()
+            out[pre + "last_update"] = mem.last_update.numpy().copy()
+        out[f"d{case}_meta"] = np.array([N, De, D, B, steps, 0 if aggr == "last" else 1, 0 if upd == "gru" else 1,
+                                         int(use_s), int(use_d)])
+        case += 1
+    out["num_cases"] = np.array(case)
+    torch.manual_seed(60)
+    te = TimeEmbedding(16, 16)
+    out.update(sd_np(te, "te_sd"))
+    x = torch.randn(23, 16); lu = torch.randint(0, 500, (23,)); t = torch.randint(0, 500, (23,))
+    out["te_x"], out["te_lu"], out["te_t"] = x.numpy(), lu.numpy(), t.numpy()
+    out["te_out"] = te(x, lu, t).detach().numpy()
+    np.savez_compressed(path, **out)
+
+
 def gen_callers(path):
     """Host-side callers that import as-is from the reference: dependencyGraph.get_block
     (dependencyGraph.py:8-28), temporal_dataset.TemporalGraphDataset items (temporal_dataset.py:34-57)
@@ -244,6 +300,7 @@ if __name__ == "__main__":
     gen_memory(os.path.join(HERE, "memory.npz"))
     gen_embedding(os.path.join(HERE, "embedding.npz"))
     gen_callers(os.path.join(HERE, "callers.npz"))
+    gen_variants(os.path.join(HERE, "variants.npz"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -57,6 +57,41 @@ def test_memory_golden(force_unfused):
             assert np.array_equal(mem.last_update.cpu().numpy(), z[p + "last_update"])
 
 
+def test_dyrep_memory_and_time_embedding_golden():
+    """DyRepMemory (rnn / gru updater, embeddings substituted into the messages, memory_module.py:218-421)
+    and TimeEmbedding (emb_module.py:32-52) against vectors from the unmodified reference."""
+    from modules.memory_module import DyRepMemory
+    from modules.emb_module import TimeEmbedding
+    from modules.msg_agg import LastAggregator, MeanAggregator
+    from modules.msg_func import IdentityMessage
+    z = np.load(os.path.join(G, "variants.npz"))
+    for c in range(int(z["num_cases"])):
+        N, De, D, B, steps, aggr, upd, use_s, use_d = z[f"d{c}_meta"].tolist()
+        mem = DyRepMemory(N, De, D, D, IdentityMessage(De, D, D), LastAggregator() if aggr == 0 else MeanAggregator(),
+                          "gru" if upd == 0 else "rnn", bool(use_s), bool(use_d))
+        load_sd(mem, z, f"d{c}_sd")
+        mem = mem.to(DEV)
+        mem.train()
+        for s in range(steps):
+            p = f"d{c}_s{s}_"
+            if not int(z[p + "training"]) and mem.training:
+                mem.eval()
+            with torch.no_grad():
+                zz, lu = mem(cu(z[p + "q"]))
+            torch.testing.assert_close(zz.cpu(), torch.from_numpy(z[p + "z"]), rtol=1e-5, atol=5e-6)
+            assert np.array_equal(lu.cpu().numpy(), z[p + "lu"])
+            with torch.no_grad():
+                mem.update_state(*(cu(z[p + k]) for k in ("src", "dst", "t", "raw", "emb", "assoc")))
+            mem.detach()
+            torch.testing.assert_close(mem.memory.cpu(), torch.from_numpy(z[p + "memory"]), rtol=1e-5, atol=5e-6)
+            assert np.array_equal(mem.last_update.cpu().numpy(), z[p + "last_update"])
+    te = TimeEmbedding(16, 16)
+    load_sd(te, z, "te_sd")
+    te = te.to(DEV)
+    out = te(cu(z["te_x"]), cu(z["te_lu"]), cu(z["te_t"]))
+    torch.testing.assert_close(out.detach().cpu(), torch.from_numpy(z["te_out"]), rtol=1e-5, atol=1e-5)
+
+
 def _run_memory_pair(N, De, D, B, steps, aggr, seed, ties):
     torch.manual_seed(seed)
     ref = orc.TGNMemory(N, De, D, D, orc.IdentityMessage(De, D, D),
@@ -226,3 +261,55 @@ def test_sampler_core_api_two_layers():
     assert b1.dim_out() == b0.dim_in() and np.array_equal(b1.eid(), r1[2]) and np.array_equal(b1.col(), r1[1])
     s.reset()
     assert s.get_ret() == []
+
+
+def test_two_layer_uniform_embedding_matches_oracle():
+    """BASELINE configs[3] in miniature (comment shape: uniform-20 sampling, 2 attention layers): the
+    two TGL blocks come from sampler_core (uniform draws are Philox draws the oracle restates, so the
+    blocks are compared exactly), then the layers run innermost-first on the drop-in
+    GraphAttentionEmbedding and are compared with the oracle's modules on the same blocks."""
+    import sampler_core
+    from modules.emb_module import GraphAttentionEmbedding
+    from modules.time_enc import TimeEncoder
+    rng = np.random.default_rng(4)
+    N, E, De, D, R = 400, 9000, 2, 32, 48
+    src = rng.integers(0, N, E); dst = rng.integers(0, N, E); t = np.sort(rng.integers(0, 20000, E)).astype(np.float32)
+    feat = torch.from_numpy(rng.standard_normal((E, De)).astype(np.float32))
+    g = orc.build_tcsr(src, dst, t, N)
+    smp = sampler_core.ParallelSampler(*g, 8, 1, 2, [20, 20], False, False, 1, 0.0, seed=9)
+    roots = rng.integers(0, N, R).astype(np.int32); rts = rng.integers(10000, 20000, R).astype(np.float32)
+    smp.sample(roots, rts)
+    b1, b2 = smp.get_ret()
+    assert b2.dim_out() == b1.dim_in() and b1.dim_out() == R
+    # uniform-k semantics: every root draws k entries with replacement (or all when it has <= k), all earlier
+    for blk, k in ((b1, 20), (b2, 20)):
+        cnt = np.bincount(blk.col(), minlength=blk.dim_out())
+        assert cnt.max() <= k and bool((blk.ts()[blk.row()] < blk.ts()[blk.col()]).all())
+    memory = torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32))
+    last_update = torch.from_numpy(rng.integers(0, 10000, N).astype(np.int64))
+    torch.manual_seed(3)
+    te = orc.tp.TimeEncoder(D)
+    with torch.no_grad():
+        te.lin.weight.mul_(0.01)
+    ref = [orc.GraphAttentionEmbedding(D, D, De, te) for _ in range(2)]
+    for r in ref:
+        r.eval()
+    te_g = TimeEncoder(D); te_g.load_state_dict(te.state_dict())
+    gpu = [GraphAttentionEmbedding(D, D, De, te_g) for _ in range(2)]
+    for r, m in zip(ref, gpu):
+        m.load_state_dict(r.state_dict()); m.to(DEV).eval()
+
+    def run(layers, dev):
+        mv = lambda a: a.to(dev)
+        n2 = torch.from_numpy(b2.nodes()).long()
+        ei2 = torch.from_numpy(np.stack([b2.row(), b2.col()])).long()
+        h = layers[0](mv(memory[n2]), mv(last_update[n2]), mv(ei2), mv(torch.from_numpy(b2.ts()[b2.row()]).long()),
+                      mv(feat[torch.from_numpy(b2.eid()).long()]))
+        n1 = torch.from_numpy(b1.nodes()).long()
+        ei1 = torch.from_numpy(np.stack([b1.row(), b1.col()])).long()
+        out = layers[1](h[:b1.dim_in()], mv(last_update[n1]), mv(ei1), mv(torch.from_numpy(b1.ts()[b1.row()]).long()),
+                        mv(feat[torch.from_numpy(b1.eid()).long()]))
+        return out[:R]
+    with torch.no_grad():
+        want, got = run(ref, "cpu"), run(gpu, DEV)
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)

@@ -107,6 +107,32 @@ def test_memory_matches_reference():
             assert np.array_equal(mem.last_update.numpy(), z[p + "last_update"])
 
 
+def test_dyrep_memory_and_time_embedding_match_reference():
+    z = _load("variants.npz")
+    for c in range(int(z["num_cases"])):
+        N, De, D, B, steps, aggr, upd, use_s, use_d = z[f"d{c}_meta"].tolist()
+        mem = orc.DyRepMemory(N, De, D, D, orc.IdentityMessage(De, D, D),
+                              orc.LastAggregator() if aggr == 0 else orc.MeanAggregator(),
+                              "gru" if upd == 0 else "rnn", bool(use_s), bool(use_d))
+        load_sd(mem, z, f"d{c}_sd")
+        mem.train()
+        for s in range(steps):
+            p = f"d{c}_s{s}_"
+            if not int(z[p + "training"]) and mem.training:
+                mem.eval()
+            zz, lu = mem(torch.from_numpy(z[p + "q"]))
+            torch.testing.assert_close(zz.detach(), torch.from_numpy(z[p + "z"]), rtol=1e-5, atol=1e-6)
+            assert np.array_equal(lu.numpy(), z[p + "lu"])
+            mem.update_state(*(torch.from_numpy(z[p + k]) for k in ("src", "dst", "t", "raw", "emb", "assoc")))
+            mem.detach()
+            torch.testing.assert_close(mem.memory.detach(), torch.from_numpy(z[p + "memory"]), rtol=1e-5, atol=1e-6)
+            assert np.array_equal(mem.last_update.numpy(), z[p + "last_update"])
+    te = orc.TimeEmbedding(16, 16)
+    load_sd(te, z, "te_sd")
+    out = te(torch.from_numpy(z["te_x"]), torch.from_numpy(z["te_lu"]), torch.from_numpy(z["te_t"]))
+    torch.testing.assert_close(out.detach(), torch.from_numpy(z["te_out"]), rtol=1e-6, atol=1e-6)
+
+
 # ---------------------------------------------------------------- embedding + decoder
 def test_embedding_and_decoder_match_reference():
     z = _load("embedding.npz")

@@ -470,7 +470,8 @@ int32_t tgn_attn_core_fwd(const float* proj, const int64_t* nbr_local, const int
                           const int32_t* num_centres_dev, int32_t heads, int32_t head_dim,
                           const float* ee, float dropout_p, uint64_t seed, const int64_t* seed_dev,
                           int32_t max_degree, float* out, float* alpha, void* stream);
-/* Backward: zero-fills d_proj [num_rows, 4*H*C], then writes the q and skip blocks of the
+/* Backward: zero-fills d_proj [num_rows, 4*H*C] (num_rows = 0: the caller has already zero-filled
+ * it, e.g. on another stream off the critical path), then writes the q and skip blocks of the
  * centre rows, atomically adds the k / v blocks of the neighbour rows and writes d_ee [E,H*C].
  * d_out is read at the centre rows only. */
 int32_t tgn_attn_core_bwd(const float* proj, const int64_t* nbr_local, const int32_t* row_ptr,

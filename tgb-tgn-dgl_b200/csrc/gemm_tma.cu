@@ -58,6 +58,7 @@ struct GemmParams {
   GemmProb p[kMaxProb];
   int nprob;
   int prec;
+  int stages;  // depth of the shared-memory ring for this launch (<= kGMaxStages)
 };
 
 struct alignas(64) GemmMaps {
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kGThreads, 1)
   const int split = local / P.tiles_m;
   const int m0 = tm * GM, n0 = tn * GN;
   const bool split3 = prm.prec == 3;
-  const int kGStages = split3 ? kGStages3 : kGStages1;
+  const int kGStages = prm.stages;
   const int kGStageBytes = split3 ? kGStageBytes3 : kGStageBytes1;
 
   // ---- prologue: nothing here reads what the preceding kernel wrote, so under programmatic
@@ -768,12 +769,24 @@ int32_t tgn_gemm_batch(const tgn_gemm_desc* d, int32_t count, int32_t precision,
   }
   if (np == 0) return TGN_OK;
   prm.nprob = np;
-  const size_t smem = (size_t)kGStages3 * kGStageBytes3 + 1024;
+  const size_t smem_max = (size_t)kGStages3 * kGStageBytes3 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    TGN_CUDA(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TGN_CUDA(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     attr_set = true;
   }
+  // Ring depth.  A full ring (192 KB) allows one CTA per SM.  A launch of short reductions whose tiles
+  // do not fit one wave of 148 CTAs but fit two CTAs per SM runs with a 64 KB ring instead: all tiles
+  // are resident at once, which beats a second wave for K <= 4 k-blocks (e.g. the node projection of
+  // the attention: 4 column tiles x 38 live row tiles = 152 CTAs).
+  prm.stages = precision == 3 ? kGStages3 : kGStages1;
+  int max_nk = 0;
+  for (int i = 0; i < np; ++i) {
+    const int kk = ceil_div(ceil_div(prm.p[i].k, prm.p[i].split_k), GK);
+    if (kk > max_nk) max_nk = kk;
+  }
+  if (tiles > kNumSMs && tiles <= 2 * kNumSMs && max_nk <= 4) prm.stages = precision == 3 ? 1 : 2;
+  const size_t smem = (size_t)prm.stages * (precision == 3 ? kGStageBytes3 : kGStageBytes1) + 1024;
   launch_k(tgemm_kernel, dim3(tiles), dim3(kGThreads), smem, (cudaStream_t)stream, maps, prm);
   TGN_LAUNCH_CHECK();
   return TGN_OK;

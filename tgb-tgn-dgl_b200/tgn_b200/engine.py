@@ -127,7 +127,8 @@ class TGNEngine:
         self.step_dev = torch.zeros(1, dtype=torch.long, device=dev)       # dropout stream
         self.events_done = 0
         self.events = None
-        self.side = torch.cuda.Stream(device=dev)    # state update + sampling of the NEXT batch
+        self.side = torch.cuda.Stream(device=dev)    # ring insert + sampling of the NEXT batch
+        self.upd = torch.cuda.Stream(device=dev)     # memory / message-store update of this batch
         self.aux = torch.cuda.Stream(device=dev)     # edge branch of the attention / small reductions
         self.w = self._alloc_work(R, E, Nb, batch_size)
         # two slots of {batch inputs, sampling results}: while step i runs on slot `cur`, the forked
@@ -466,14 +467,18 @@ class TGNEngine:
         self._attention_core(w, train)
 
     def _update_state(self, w):
-        """memory.update_state + neighbor_loader.insert (memory_module.py:126-138, epoch_utils.py:300).
-        Train ordering: memory rows first (they are the rows the forward just produced: same
-        store, same weights), then the store, then the ring."""
+        """memory.update_state (memory_module.py:126-138).  Train ordering: memory rows first (they are
+        the rows the forward just produced: same store, same weights), then the store."""
         B = self.B
         self._scatter_owned(self.in_ids3[:2 * B], w.z, w.lu, self.memory, self.last_update,
                             src_rows=w.ids_l[:2 * B])
         self.store.update(self.in_ids3[:B], self.in_ids3[B:2 * B], self.in_t_i64, self.in_msg,
                           base_dev=self.log_base_dev)
+
+    def _ring_insert(self):
+        """neighbor_loader.insert (epoch_utils.py:300).  It needs the batch's ids and times only, and the
+        step's compute never reads the ring (the batch was sampled before), so it does not wait for it."""
+        B = self.B
         check(_L().tgn_nbr_insert(_p(self.in_ids3), self.in_ids3[B:].data_ptr(), _p(self.in_t_f32), B, 0,
                                   _p(self.cur_e_id_dev), self.K, self.N, _p(self.neighbors), _p(self.e_id),
                                   _p(self.t_ring), _stream()))
@@ -515,29 +520,39 @@ class TGNEngine:
         self._bind(self.cur)
         w, p, B, D, HC, L = self.w, self.p, self.B, self.D, self.HC, _L()
         off, fg, fl = self.off, self.flat_grad, self.flat
-        main, side, aux = torch.cuda.current_stream(), self.side, self.aux
+        main, side, aux, upd = torch.cuda.current_stream(), self.side, self.aux, self.upd
         if not self.fused_zero_grad:
             self.zero_blob.zero_()
         if not pipelined:
             if from_device:
                 self.stage_batch_from_device()
             self._sample(w, w.in_ids3, w.ids_l)
+        # ---- forked stream 1, from the start of the step: the batch's events enter the ring, then the
+        # NEXT batch is loaded and sampled (single-CTA, latency-bound kernels: ~100 us of them hide
+        # behind the whole step instead of trailing the GRU)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._ring_insert()
+            if pipelined:
+                nxt = self.slots[self.cur ^ 1]
+                if from_device:
+                    self.stage_batch_from_device(self.cur ^ 1)
+                self._sample(nxt, nxt.in_ids3, nxt.ids_l)
+        # the attention backward accumulates into a zero-filled d_proj (10 MB): cleared here, beside
+        # msg_build, instead of in front of the backward on the dependent chain
+        aux.wait_stream(main)
+        with torch.cuda.stream(aux):
+            w.d_proj.zero_()
         self._timed("msg_build", lambda: self._memory_msgs(w, w.n_id, w.Nb, w.Nb_dev))
         # ---- edge branch of the attention on its own stream: needs last_update / edges only
         aux.wait_stream(main)
         with torch.cuda.stream(aux):
             self._edge_branch(w, w.lu, True)
         self._memory_gru(w, w.Nb, w.Nb_dev)
-        # ---- forked stream: state update (needs z / last_update of the forward only), then the
-        # next batch: load + sample while this step's attention / backward run
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
+        # ---- forked stream 2: memory / store update (needs z / last_update of the forward only)
+        upd.wait_stream(main)
+        with torch.cuda.stream(upd):
             self._update_state(w)
-            if pipelined:
-                nxt = self.slots[self.cur ^ 1]
-                if from_device:
-                    self.stage_batch_from_device(self.cur ^ 1)
-                self._sample(nxt, nxt.in_ids3, nxt.ids_l)
         self._node_proj(w, w.z)
         main.wait_stream(aux)
         self._attention_core(w, True)
@@ -555,26 +570,28 @@ class TGNEngine:
         # ---- attention backward
         check(L.tgn_attn_core_bwd(_p(w.proj), _p(w.nbr_l), _p(w.root_off), _p(w.ctr_l), w.R, _p(w.R_dev),
                                   self.H, self.C, _p(w.ee), _p(w.alpha), _p(self.d_emb), self.dropout, self.seed,
-                                  _p(self.step_dev), self.K, w.Nb, _p(w.d_proj), _p(w.d_ee), s))
+                                  _p(self.step_dev), self.K, 0, _p(w.d_proj), _p(w.d_ee), s))
         split_e = max(1, min(16, w.E // 512))
         split_n = max(1, min(16, w.Nb // 512))
-        g = [  # dW_edge += d_ee^T edge_attr ; dW_node += d_proj^T z ; d z = d_proj W_node
-            ops.gemm_desc(w.d_ee, w.ea, fg, m=HC, n=self.Din, k=w.E, lda=HC, ldb=self.lde, ldc=self.lde,
-                          trans_a=True, trans_b=True, mode=2, split_k=split_e, k_dev=w.E_dev,
-                          c_off=off["conv.lin_edge.weight"]),
-            ops.gemm_desc(w.d_proj, w.z, fg, m=4 * HC, n=D, k=w.Nb, lda=4 * HC, ldb=D, ldc=D, trans_a=True,
-                          trans_b=True, mode=2, split_k=split_n, k_dev=w.Nb_dev, c_off=off["conv.w_node"]),
-            ops.gemm_desc(w.d_proj, fl, w.d_z, m=w.Nb, n=D, k=4 * HC, lda=4 * HC, ldb=D, ldc=D, trans_b=True,
-                          b_off=off["conv.w_node"], m_dev=w.Nb_dev),
-        ]
-        if self.Dt:  # d edge_attr[:, :Dt] = d_ee W_edge[:, :Dt]  (time-encoder gradient)
-            g.append(ops.gemm_desc(w.d_ee, fl, w.d_eat, m=w.E, n=self.Dt, k=HC, lda=HC, ldb=self.lde, ldc=self.Dt,
-                                   trans_b=True, b_off=off["conv.lin_edge.weight"], m_dev=w.E_dev))
-        ops.gemm_batch(g, self.prec)
-        # bias gradient of the node projection and the attention-side TimeEncoder gradient: off the
-        # critical path, next to the GRU backward
-        aux.wait_stream(main)
+        # Only d z = d_proj W_node feeds the GRU backward; it gets its own small launch on the main
+        # stream.  The weight gradients of the attention (and everything that hangs off them) run
+        # beside it on the auxiliary stream: the two launches together fit the 148 SMs.
+        aux.wait_stream(main)       # fork point: both launches depend on the attention backward only
+        ops.gemm_batch([ops.gemm_desc(w.d_proj, fl, w.d_z, m=w.Nb, n=D, k=4 * HC, lda=4 * HC, ldb=D, ldc=D,
+                                      trans_b=True, b_off=off["conv.w_node"], m_dev=w.Nb_dev)], self.prec)
         with torch.cuda.stream(aux):
+            g = [  # dW_edge += d_ee^T edge_attr ; dW_node += d_proj^T z
+                ops.gemm_desc(w.d_ee, w.ea, fg, m=HC, n=self.Din, k=w.E, lda=HC, ldb=self.lde, ldc=self.lde,
+                              trans_a=True, trans_b=True, mode=2, split_k=split_e, k_dev=w.E_dev,
+                              c_off=off["conv.lin_edge.weight"]),
+                ops.gemm_desc(w.d_proj, w.z, fg, m=4 * HC, n=D, k=w.Nb, lda=4 * HC, ldb=D, ldc=D, trans_a=True,
+                              trans_b=True, mode=2, split_k=split_n, k_dev=w.Nb_dev, c_off=off["conv.w_node"]),
+            ]
+            if self.Dt:  # d edge_attr[:, :Dt] = d_ee W_edge[:, :Dt]  (time-encoder gradient)
+                g.append(ops.gemm_desc(w.d_ee, fl, w.d_eat, m=w.E, n=self.Dt, k=HC, lda=HC, ldb=self.lde,
+                                       ldc=self.Dt, trans_b=True, b_off=off["conv.lin_edge.weight"], m_dev=w.E_dev))
+            ops.gemm_batch(g, self.prec)
+            # bias gradient of the node projection and the attention-side TimeEncoder gradient
             ops.colsum(w.d_proj, w.Nb, 4 * HC, 4 * HC, p["conv.b_node"].grad, True, rows_dev=w.Nb_dev)
             if self.Dt:
                 check(L.tgn_time_bwd_sin(_p(w.rel), None, w.E, _p(w.E_dev), _p(w.sn_e), self.Dt, _p(w.d_eat), self.Dt,
@@ -582,25 +599,35 @@ class TGNEngine:
         # ---- GRU backward (torch.nn.GRUCell, memory_module.py:72,172)
         check(L.tgn_gru_gates_bwd_bias(_p(w.d_z), _p(w.gates), _p(w.h), w.Nb, _p(w.Nb_dev), D, _p(w.d_gi),
                                        _p(w.d_gh), gptr("memory_updater.bias_ih"), gptr("memory_updater.bias_hh"), s))
+        # One launch, one wave: the GEMM CTAs hold ~193 KB of shared memory (one per SM), so the split-K
+        # factor of the two weight gradients is chosen to leave SMs for the row tiles of d x -- launched
+        # separately (or with a larger split) d x simply queues behind the weight-gradient CTAs.
         c0 = (2 * D + self.De) & ~3
-        ops.gemm_batch([
+        tiles_dx = (w.Nb + 127) // 128 if self.Dt else 0
+        tiles_w = ((3 * D + 127) // 128) * ((self.Dx + 127) // 128) + ((3 * D + 127) // 128) * ((D + 127) // 128)
+        split_g = max(1, min(split_n, (148 - tiles_dx) // tiles_w))
+        g = [
             ops.gemm_desc(w.d_gi, w.x, fg, m=3 * D, n=self.Dx, k=w.Nb, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
-                          trans_a=True, trans_b=True, mode=2, split_k=split_n, k_dev=w.Nb_dev,
+                          trans_a=True, trans_b=True, mode=2, split_k=split_g, k_dev=w.Nb_dev,
                           c_off=off["memory_updater.weight_ih"]),
             ops.gemm_desc(w.d_gh, w.h, fg, m=3 * D, n=D, k=w.Nb, lda=3 * D, ldb=D, ldc=D, trans_a=True,
-                          trans_b=True, mode=2, split_k=split_n, k_dev=w.Nb_dev,
+                          trans_b=True, mode=2, split_k=split_g, k_dev=w.Nb_dev,
                           c_off=off["memory_updater.weight_hh"]),
-            # d x = d_gi W_ih: only the time-encoding columns [2D+De, Dx) are consumed, so only those are
-            # computed (from the 16-byte aligned column below them): 1 column tile per row tile instead of 3
-            ops.gemm_desc(w.d_gi, fl, w.d_x, m=w.Nb, n=self.Dx - c0, k=3 * D, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
-                          trans_b=True, b_off=off["memory_updater.weight_ih"] + c0, c_off=c0, m_dev=w.Nb_dev),
-        ], self.prec)
+        ]
+        if self.Dt:
+            # d x = d_gi W_ih: only the time-encoding columns [2D+De, Dx) are consumed (memory-side
+            # TimeEncoder gradient), so only those are computed, from the 16-byte aligned column below them
+            g.append(ops.gemm_desc(w.d_gi, fl, w.d_x, m=w.Nb, n=self.Dx - c0, k=3 * D, lda=3 * D, ldb=self.ldx,
+                                   ldc=self.ldx, trans_b=True, b_off=off["memory_updater.weight_ih"] + c0, c_off=c0,
+                                   m_dev=w.Nb_dev))
+        ops.gemm_batch(g, self.prec)
         if self.Dt:
             check(L.tgn_time_bwd_sin(_p(w.sel_dt), _p(w.sel_ev), w.Nb, _p(w.Nb_dev), _p(w.sn_m), self.Dt,
                                      w.d_x.data_ptr() + 4 * (2 * D + self.De), self.ldx,
                                      gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), s))
         main.wait_stream(aux)
         main.wait_stream(side)
+        main.wait_stream(upd)
         if self.world > 1:   # replicated compute: average the gradients so the weight replicas stay bit-identical
             self._all_reduce(self.flat_grad)
             self.flat_grad.mul_(1.0 / self.world)

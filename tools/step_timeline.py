@@ -1,0 +1,50 @@
+"""Timeline of ONE steady-state training step as the GPU ran it (CUDA-graph replay, all streams):
+kernel start / end times from CUPTI (torch.profiler), relative to the step's first kernel.
+This is what the serialised ncu launch list cannot show: which launches overlap, and where the
+dependent chain waits.   usage: python tools/step_timeline.py [--prefill N] [--precision 3]"""
+import argparse, json, os, sys, tempfile
+import numpy as np
+import torch
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "tgb-tgn-dgl_b200"))
+import bench
+from tgn_b200 import synth
+from tgn_b200.engine import TGNEngine
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--prefill", type=int, default=300_000)
+ap.add_argument("--precision", type=int, default=3)
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+cfg = synth.SHAPES[bench.WORKLOAD]
+B, K = cfg["B"], cfg["K"]
+data = synth.synth_events(bench.WORKLOAD, seed=0, max_events=a.prefill + 200 * B)
+N, De = data["num_nodes"], data["raw_dim"]
+eng = TGNEngine(N, De, bench.HIDDEN, K, B, device=dev, lr=bench.LR, dropout=0.1, use_graph=True,
+                log_capacity=data["src"].size, seed=1234, precision=a.precision, fused_zero_grad=True)
+eng.load_state(*bench.init_state_dicts(De, bench.HIDDEN, N, seed=1))
+eng.set_events(**{k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")})
+ring = bench.ring_after(data["src"][:a.prefill], data["dst"][:a.prefill], data["t"][:a.prefill], K, N)
+eng.prefill(a.prefill, tuple(torch.from_numpy(x) for x in ring))
+for _ in range(30):
+    eng.train_step(from_device=True)
+torch.cuda.synchronize()
+from torch.profiler import ProfilerActivity, profile
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(6):
+        eng.train_step(from_device=True)
+    torch.cuda.synchronize()
+path = os.path.join(tempfile.mkdtemp(), "trace.json")
+prof.export_chrome_trace(path)
+ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
+ev.sort(key=lambda e: e["ts"])
+starts = [i for i, e in enumerate(ev) if "msg_build" in e["name"]]
+lo, hi = starts[-3], starts[-2]
+t0 = ev[lo]["ts"]
+streams = sorted({e["args"].get("stream") for e in ev[lo:hi]})
+print(f"step = {ev[hi]['ts'] - t0:.1f} us between two msg_build launches; streams {streams}")
+print(f"{'start':>8s} {'end':>8s} {'dur':>7s}  st  kernel")
+for e in ev[lo:hi]:
+    name = e["name"].split("(")[0].replace("void ", "").replace("tgn::", "")[:48]
+    print(f"{e['ts'] - t0:8.1f} {e['ts'] - t0 + e['dur']:8.1f} {e['dur']:7.1f}  {streams.index(e['args'].get('stream')):2d}  "
+          f"{name}  grid={e['args'].get('grid')}")

@@ -429,6 +429,12 @@ __global__ void step_finish_kernel(float* adam_step, int64_t* step_ctr, const fl
 
 // gru_gates_bwd with the two bias gradients (column sums of d_gi / d_gh) folded in: one CTA
 // per row chunk, thread j owns column j of every gate block, partial sums leave as atomics.
+constexpr int kGbU = 8;  // rows in flight per thread
+__device__ __forceinline__ float ld_nc_v(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 __global__ void __launch_bounds__(128)
     gru_gates_bwd_bias_kernel(const float* __restrict__ d_out, const float* __restrict__ gates,
                               const float* __restrict__ h, DevCount num, int D,
@@ -441,20 +447,24 @@ __global__ void __launch_bounds__(128)
   const int r0 = blockIdx.x * rows_per, r1 = min(S, r0 + rows_per);
   for (int j = threadIdx.x; j < D; j += blockDim.x) {
     float sr = 0.f, sz = 0.f, sn = 0.f, shn = 0.f;
-    for (int s0 = r0; s0 < r1; s0 += 4) {
-      float r[4], z[4], n[4], ghn[4], hv[4], go[4];
+    for (int s0 = r0; s0 < r1; s0 += kGbU) {
+      float r[kGbU], z[kGbU], n[kGbU], ghn[kGbU], hv[kGbU], go[kGbU];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {  // all loads of four rows first
+      for (int u = 0; u < kGbU; ++u) {  // all loads of the row group first (one round trip per group)
         const int s = min(s0 + u, r1 - 1);
         const float* g = gates + (long long)s * 4 * D;
-        r[u] = g[j]; z[u] = g[D + j]; n[u] = g[2 * D + j]; ghn[u] = g[3 * D + j];
-        hv[u] = h[(long long)s * D + j];
-        go[u] = d_out[(long long)s * D + j];
+        // volatile loads: nvcc otherwise sinks every row's (read-only) loads next to their use -- one
+        // memory round trip per row instead of one per group, which was this kernel's whole duration
+        r[u] = ld_nc_v(g + j); z[u] = ld_nc_v(g + D + j); n[u] = ld_nc_v(g + 2 * D + j);
+        ghn[u] = ld_nc_v(g + 3 * D + j);
+        hv[u] = ld_nc_v(h + (long long)s * D + j);
+        go[u] = ld_nc_v(d_out + (long long)s * D + j);
       }
+      asm volatile("" ::: "memory");   // volatile asm statements keep their order: all loads are issued first
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kGbU; ++u) {
         const int s = s0 + u;
-        if (s >= r1) break;
+        if (s >= r1) continue;
         const float dn_pre = go[u] * (1.f - z[u]) * (1.f - n[u] * n[u]);
         const float dr_pre = dn_pre * ghn[u] * r[u] * (1.f - r[u]);
         const float dz_pre = go[u] * (hv[u] - n[u]) * z[u] * (1.f - z[u]);
@@ -544,8 +554,8 @@ int32_t tgn_gru_gates_bwd_bias(const float* d_out, const float* gates, const flo
   TGN_REQUIRE(num >= 0 && dim >= 1, "gru_gates_bwd_bias: bad sizes");
   if (num == 0) return TGN_OK;
   TGN_REQUIRE(d_out && gates && h && d_gi && d_gh && d_b_ih && d_b_hh, "gru_gates_bwd_bias: NULL pointer");
-  int grid = ceil_div(num, 16);
-  if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+  int grid = ceil_div(num, kGbU);  // one or two row groups per CTA: the kernel is a short dependent chain
+  if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
   launch_k(gru_gates_bwd_bias_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, 
       d_out, gates, h, DevCount{num_dev, num}, dim, d_gi, d_gh, d_b_ih, d_b_hh);
   TGN_LAUNCH_CHECK();

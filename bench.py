@@ -162,6 +162,17 @@ def run_cpu_reference(data, steps, warmup, prefill, budget_s):
     return done, t_timed
 
 
+_JSON_FD = None
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,6 +189,12 @@ def main():
     ap.add_argument("--precision", type=int, default=3, choices=[1, 3],
                     help="tensor-core GEMM mode: 3 = 3xTF32 (fp32-level accuracy), 1 = single-pass tf32")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): libraries that write to fd 1 (NCCL prints its version
+    # banner there) are sent to stderr, the JSON line goes to the saved descriptor
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -207,7 +224,7 @@ def main():
                 "cpu_baseline": {"value": val, "unit": "events/s", "cores": torch.get_num_threads(), "kind": "port",
                                  "sample": f"{done} of {K_steps} requested steps (150 s budget), oracle port of the reference's torch-CPU path"},
                 "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     if not torch.cuda.is_available():
@@ -344,7 +361,7 @@ def main():
                                     "sample": f"{done} training steps ({done * B} events) of the same workload (same "
                                               "shape, batch, prefill) on the host CPU: oracle port of the reference's "
                                               "torch-CPU path incl. its Python-dict message store"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # captured graphs hold NCCL kernels: leave without the collective shutdown (it can block)
         torch.cuda.synchronize()

@@ -269,16 +269,14 @@ def main():
     # ---------------- end-to-end arm: host batches, H2D every step, loss read back every step
     pos = eng.events_done
     n_host = W + K_steps + 1                       # one batch of lookahead
-    pack = torch.empty((n_host, 4 * B), dtype=torch.long).pin_memory()
-    msgs = torch.empty((n_host, B, max(De, 1)), dtype=torch.float32).pin_memory()
+    host = torch.empty((n_host, eng.packed_nbytes()), dtype=torch.uint8).pin_memory()   # one H2D copy per batch
     for s in range(n_host):
         sl = slice(pos + s * B, pos + (s + 1) * B)
-        pack[s] = torch.cat([ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl]])
-        msgs[s] = ev["msg"][sl]
+        eng.pack_host_batch(host[s], ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl], ev["msg"][sl])
     # prefetching loader pattern: batch s+1 is copied H2D (and sampled on the forked stream) while batch s trains
-    eng.stage_packed(pack[0], msgs[0])
+    eng.stage_packed1(host[0])
     for s in range(W):
-        eng.stage_packed(pack[s + 1], msgs[s + 1], ahead=True)
+        eng.stage_packed1(host[s + 1], ahead=True)
         float(eng.train_step(from_device=False, lookahead=True))
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -286,7 +284,7 @@ def main():
     # every step's loss is read back on the host; the read of step s is taken after step s+1 has been
     # launched (train_step_logged: async D2H into pinned memory), the last one before the timer stops
     for s in range(W, W + K_steps):
-        eng.stage_packed(pack[s + 1], msgs[s + 1], ahead=True)
+        eng.stage_packed1(host[s + 1], ahead=True)
         eng.train_step_logged(from_device=False, lookahead=True)
     loss_host = eng.flush_loss()
     f1.record()
@@ -339,7 +337,7 @@ def main():
                 "dtype": "tf32x3 (fp32-accurate split, fp32 accumulate)" if args.precision == 3 else "tf32",
                 "data": "synthetic", "config": config,
                 "e2e": {"value": world * K_steps * B / (ms_e2e / 1e3), "unit": "events/s",
-                        "h2d_bytes_per_step": 4 * B * 8 + B * De * 4, "d2h_bytes_per_step": 4,
+                        "h2d_bytes_per_step": eng.packed_nbytes(), "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / K_steps},
                 "gpu_launches": len(ours) * K_steps,
                 "launches_per_step": {"tgn_kernels": len(ours), "all_kernels": len(kern)},

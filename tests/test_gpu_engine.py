@@ -132,6 +132,32 @@ def test_host_staged_batches_equal_device_staged():
     torch.testing.assert_close(eng_a.memory, eng_c.memory, rtol=1e-2, atol=1e-3)
     assert torch.equal(eng_a.e_id, eng_b.e_id) and torch.equal(eng_a.e_id, eng_c.e_id)
     assert torch.equal(eng_a.last_update, eng_c.last_update)
+    assert torch.equal(eng_a.t_ring, eng_b.t_ring) and torch.equal(eng_a.t_ring, eng_c.t_ring)
+
+
+def test_single_copy_staging_and_lagged_loss():
+    """stage_packed1 (one pinned H2D copy per batch, float ring timestamps derived inside the step) with
+    train_step_logged (loss read back one step late) == the resident-array path."""
+    N, De, D, K, B, steps = 300, 8, 16, 4, 32, 8
+    _, eng_a, ev = _setup(N, De, D, K, B, B * steps, 11, True)
+    _, eng_d, _ = _setup(N, De, D, K, B, B * steps, 11, True)
+    host = torch.empty((steps, eng_d.packed_nbytes()), dtype=torch.uint8).pin_memory()
+    for s in range(steps):
+        sl = slice(s * B, (s + 1) * B)
+        eng_d.pack_host_batch(host[s], ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl], ev["msg"][sl])
+    ref_losses = [float(eng_a.train_step(from_device=True)) for _ in range(steps)]
+    got = []
+    eng_d.stage_packed1(host[0])
+    for s in range(steps):
+        eng_d.stage_packed1(host[min(s + 1, steps - 1)], ahead=True)
+        got.append(eng_d.train_step_logged(from_device=False, lookahead=True))
+    got = got[1:] + [eng_d.flush_loss()]
+    assert got[0] is not None and len(got) == steps
+    for s, (a, b) in enumerate(zip(ref_losses, got)):
+        assert abs(a - b) < 1e-4, (s, a, b)
+    torch.testing.assert_close(eng_a.memory, eng_d.memory, rtol=1e-2, atol=1e-3)
+    assert torch.equal(eng_a.e_id, eng_d.e_id) and torch.equal(eng_a.t_ring, eng_d.t_ring)
+    assert torch.equal(eng_a.last_update, eng_d.last_update)
 
 
 def test_fused_zero_grad_is_equivalent():

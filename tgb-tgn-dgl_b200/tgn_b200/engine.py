@@ -133,11 +133,20 @@ class TGNEngine:
         self.w = self._alloc_work(R, E, Nb, batch_size)
         # two slots of {batch inputs, sampling results}: while step i runs on slot `cur`, the forked
         # stream already loads and samples batch i+1 into the other slot (software pipelining)
-        self.slots = [self._alloc_slot(R, E, Nb, batch_size) for _ in range(2)]
+        # three slots in rotation: step s trains on slot s%3 and samples batch s+1 into slot (s+1)%3, so a
+        # host loader can copy batch s+1 into its slot while step s-1 is still running (stage_packed1)
+        self.nslots = 3
+        self.slots = [self._alloc_slot(R, E, Nb, batch_size) for _ in range(self.nslots)]
         self.cur = 0
+        self.copy_stream = torch.cuda.Stream(device=dev)    # H2D of host-staged batches
+        self.loss_stream = torch.cuda.Stream(device=dev)    # D2H of the per-step loss (train_step_logged)
+        self._slot_free = [torch.cuda.Event() for _ in range(self.nslots)]    # last step that used the slot is done
+        self._slot_ready = [torch.cuda.Event() for _ in range(self.nslots)]   # its staged batch has landed
+        self._slot_async = [False] * self.nslots
         self._primed = None      # "device" / "host": slots[cur] holds a staged AND sampled batch
         self._bind(0)
-        self.loss = torch.zeros((), device=dev)
+        self.loss_slots = torch.zeros(3, device=dev)   # loss of the step that trained on slot i (a lagged host
+        self.loss = self.loss_slots[0]                 # read of step s survives until step s+3 overwrites it)
         self.bounds = (R, E, Nb)
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.training = True
@@ -207,10 +216,14 @@ class TGNEngine:
         sl = SimpleNamespace(R=R, E=E, Nb=Nb, B=B)
         self._alloc_sample_fields(sl, R, E, Nb)
         sl.ids_l = torch.zeros(3 * B, dtype=torch.long, device=dev)
-        sl.in_i64 = torch.zeros(4 * B, dtype=torch.long, device=dev)      # [src | dst | neg | t]: one H2D copy
+        # one contiguous staging region per slot: [src | dst | neg | t] int64 followed by msg [B, De] float32,
+        # so a host batch is ONE H2D copy (stage_packed1); in_i64 / in_msg are views of it
+        De1 = max(self.De, 1)
+        sl.in_raw = torch.zeros(32 * B + 4 * B * De1, dtype=torch.uint8, device=dev)
+        sl.in_i64 = sl.in_raw[:32 * B].view(torch.long)
         sl.in_ids3, sl.in_t_i64 = sl.in_i64[:3 * B], sl.in_i64[3 * B:]
         sl.in_t_f32 = torch.zeros(B, device=dev)
-        sl.in_msg = torch.zeros((B, max(self.De, 1)), device=dev)
+        sl.in_msg = sl.in_raw[32 * B:].view(torch.float32).view(B, De1)
         return sl
 
     def _bind(self, idx: int):
@@ -220,6 +233,9 @@ class TGNEngine:
             setattr(self.w, k, getattr(sl, k))
         self.in_i64, self.in_ids3, self.in_t_i64 = sl.in_i64, sl.in_ids3, sl.in_t_i64
         self.in_t_f32, self.in_msg = sl.in_t_f32, sl.in_msg
+
+    def _next_slot(self) -> int:
+        return (self.cur + 1) % self.nslots
 
     def _unprime(self):
         """Drops a batch that was pre-sampled but not trained on (mode switch, flush, reset)."""
@@ -317,11 +333,39 @@ class TGNEngine:
         ahead=False: the batch the next train_step(from_device=False) trains on;
         ahead=True : the batch AFTER that one (train_step(..., lookahead=True) samples it while it
         trains on the current one -- the prefetching data-loader pattern)."""
-        sl = self.slots[self.cur ^ 1 if ahead else self.cur]
+        sl = self.slots[self._next_slot() if ahead else self.cur]
         sl.in_i64.copy_(ids_t, non_blocking=True)
         if self.De:
             sl.in_msg.copy_(msg, non_blocking=True)
-        sl.in_t_f32.copy_(sl.in_t_i64)
+        # (the float32 timestamps the ring wants are derived inside the step that consumes the batch)
+
+    def packed_nbytes(self) -> int:
+        """Size of the single-copy host batch of stage_packed1()."""
+        return 32 * self.B + 4 * self.B * max(self.De, 1)
+
+    def pack_host_batch(self, out: Tensor, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor) -> Tensor:
+        """Fills `out` (pinned uint8 [packed_nbytes()]) with [src | dst | neg | t] int64 + msg float32."""
+        B = self.B
+        out[:32 * B].view(torch.long).copy_(torch.cat([src, dst, neg, t]))
+        if self.De:
+            out[32 * B:].view(torch.float32).view(B, self.De).copy_(msg)
+        return out
+
+    def stage_packed1(self, buf: Tensor, ahead: bool = False):
+        """End-to-end staging with ONE H2D copy: `buf` = pinned host uint8 [packed_nbytes()] laid out by
+        pack_host_batch().  `ahead` as in stage_packed."""
+        if not ahead:
+            self.slots[self.cur].in_raw.copy_(buf, non_blocking=True)
+            return
+        # the slot of batch s+1 was last used two steps ago, so this copy runs on its own stream while
+        # step s-1 is still executing; train_step waits for it (an event that has usually fired already)
+        idx = self._next_slot()
+        cs = self.copy_stream
+        cs.wait_event(self._slot_free[idx])
+        with torch.cuda.stream(cs):
+            self.slots[idx].in_raw.copy_(buf, non_blocking=True)
+            self._slot_ready[idx].record(cs)
+        self._slot_async[idx] = True
 
     def prefill(self, count: int, ring_state=None):
         """Start from a mid-epoch state: the first `count` events of set_events() are taken as
@@ -340,7 +384,7 @@ class TGNEngine:
 
     def stage_batch(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor, ahead: bool = False):
         """Copies one batch (host or device tensors) into a slot (see stage_packed for `ahead`)."""
-        B, sl = self.B, self.slots[self.cur ^ 1 if ahead else self.cur]
+        B, sl = self.B, self.slots[self._next_slot() if ahead else self.cur]
         sl.in_ids3[:B].copy_(src, non_blocking=True)
         sl.in_ids3[B:2 * B].copy_(dst, non_blocking=True)
         sl.in_ids3[2 * B:].copy_(neg, non_blocking=True)
@@ -532,11 +576,13 @@ class TGNEngine:
         # behind the whole step instead of trailing the GRU)
         side.wait_stream(main)
         with torch.cuda.stream(side):
+            if not from_device:     # host-staged batch: int64 stamps -> the ring's float32 (neighbor_loader.py:21)
+                self.in_t_f32.copy_(self.in_t_i64)
             self._ring_insert()
             if pipelined:
-                nxt = self.slots[self.cur ^ 1]
+                nxt = self.slots[self._next_slot()]
                 if from_device:
-                    self.stage_batch_from_device(self.cur ^ 1)
+                    self.stage_batch_from_device(self._next_slot())
                 self._sample(nxt, nxt.in_ids3, nxt.ids_l)
         # the attention backward accumulates into a zero-filled d_proj (10 MB): cleared here, beside
         # msg_build, instead of in front of the backward on the dependent chain
@@ -633,7 +679,7 @@ class TGNEngine:
             self.flat_grad.mul_(1.0 / self.world)
         check(L.tgn_adam_finish(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
                                 self.n_param, self.lr, 0.9, 0.999, 1e-8, _p(self.adam_step_dev), _p(self.step_dev),
-                                _p(self.loss_acc), _p(self.loss), _p(self.done_ctr), int(self.fused_zero_grad),
+                                _p(self.loss_acc), self.loss_slots.data_ptr() + 4 * self.cur, _p(self.done_ctr), int(self.fused_zero_grad),
                                 _p(self.d_emb), self.d_emb.numel(), _stream()))
 
     def _run(self, key: tuple, body):
@@ -678,9 +724,16 @@ class TGNEngine:
                 self._primed = mode
         else:
             self._unprime()
+        main = torch.cuda.current_stream()
+        nxt = self._next_slot()
+        if pipelined and self._slot_async[nxt]:          # the batch staged ahead on the copy stream has landed
+            main.wait_event(self._slot_ready[nxt])
+            self._slot_async[nxt] = False
         self._run(("train", from_device, pipelined, self.cur), lambda: self._train_body(from_device, pipelined))
+        self._slot_free[self.cur].record(main)
+        self.loss = self.loss_slots[self.cur]
         if pipelined:
-            self.cur ^= 1
+            self.cur = nxt
         self.events_done += self.B
         self.store.size = self.events_done   # host mirror of log_base_dev (graph replays skip the Python body)
         return self.loss
@@ -694,11 +747,17 @@ class TGNEngine:
         if not hasattr(self, "_loss_pin"):
             self._loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
             self._loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._loss_done = [torch.cuda.Event(), torch.cuda.Event()]
             self._loss_n = 0
-        loss = self.train_step(**kw)
         i = self._loss_n & 1
-        self._loss_pin[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
-        self._loss_ev[i].record()
+        main, ls = torch.cuda.current_stream(), self.loss_stream
+        main.wait_event(self._loss_ev[i])      # the read of two steps ago (same pinned word) is done: long since
+        loss = self.train_step(**kw)
+        self._loss_done[i].record(main)
+        ls.wait_event(self._loss_done[i])      # the copy runs beside the next step, not between two steps
+        with torch.cuda.stream(ls):
+            self._loss_pin[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+            self._loss_ev[i].record(ls)
         self._loss_n += 1
         if self._loss_n < 2:
             return None

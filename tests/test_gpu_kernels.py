@@ -587,3 +587,39 @@ def test_partitioned_memory_rows_assemble_exactly(ops, world):
         _cabi.check(L.tgn_memory_scatter_owned(p(n_id), S, None, p(new_mem), p(new_lu), 0, None, D, r, world,
                                                p(mem_loc), p(lu_loc), 0))
         assert torch.equal(mem_loc[:own.shape[0]], full_m[r::world]) and torch.equal(lu_loc[:own.shape[0]], full_l[r::world])
+
+
+@pytest.mark.parametrize("H,C", [(2, 50), (1, 32), (4, 16)])
+def test_attn_core_small_path_equals_general_path_with_dropout(ops, H, C):
+    """The register-resident low-degree attention kernels (lane-parallel Philox dropout masks) against the
+    general kernels (one draw per (edge, head)): same seed -> same mask, so outputs, attention weights and
+    all gradients agree; also checks that forward and backward apply the SAME mask."""
+    from tgn_b200 import _cabi
+    L = _cabi.lib()
+    p = lambda t: None if t is None else t.data_ptr()
+    g = torch.Generator(device="cpu").manual_seed(H * C)
+    R, Nb, K, HC = 77, 300, 10, H * C
+    deg = torch.randint(0, K + 1, (R,), generator=g)
+    row_ptr = torch.zeros(R + 1, dtype=torch.int32); row_ptr[1:] = deg.cumsum(0).int()
+    E = int(row_ptr[-1])
+    nbr = torch.randint(0, Nb, (E,), generator=g)
+    centres = torch.randperm(Nb, generator=g)[:R]
+    proj, ee = torch.randn(Nb, 4 * HC, generator=g), torch.randn(E, HC, generator=g)
+    d_out = torch.randn(Nb, HC, generator=g)
+    dev = [x.to(DEV).contiguous() for x in (proj, nbr, row_ptr, centres, ee, d_out)]
+    res = []
+    for max_deg in (K, 0):                       # K: small path, 0: general path
+        out, alpha = torch.zeros(Nb, HC, device=DEV), torch.zeros(E, H, device=DEV)
+        d_proj, d_ee = torch.zeros(Nb, 4 * HC, device=DEV), torch.zeros(E, HC, device=DEV)
+        _cabi.check(L.tgn_attn_core_fwd(p(dev[0]), p(dev[1]), p(dev[2]), p(dev[3]), R, None, H, C, p(dev[4]), 0.3,
+                                        99, None, max_deg, p(out), p(alpha), 0))
+        _cabi.check(L.tgn_attn_core_bwd(p(dev[0]), p(dev[1]), p(dev[2]), p(dev[3]), R, None, H, C, p(dev[4]),
+                                        p(alpha), p(dev[5]), 0.3, 99, None, max_deg, Nb, p(d_proj), p(d_ee), 0))
+        res.append((out, alpha, d_proj, d_ee))
+    for a, b, name in zip(res[0], res[1], ("out", "alpha", "d_proj", "d_ee")):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5, msg=lambda m: f"{name}: {m}")
+    # dropout really happened (30 % of the (edge, head) pairs carry no weight into `out`)
+    out_nodrop = torch.zeros(Nb, HC, device=DEV); al2 = torch.zeros(E, H, device=DEV)
+    _cabi.check(L.tgn_attn_core_fwd(p(dev[0]), p(dev[1]), p(dev[2]), p(dev[3]), R, None, H, C, p(dev[4]), 0.0,
+                                    99, None, K, p(out_nodrop), p(al2), 0))
+    assert not torch.allclose(out_nodrop, res[0][0])

@@ -304,6 +304,32 @@ __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_fwd_kernel(AttnCore
 // ~4 dependent memory latencies per centre instead of ~2 per edge group and pass.
 constexpr int kSmallDeg = 12;
 
+// Dropout masks of one centre's (edge, head) pairs, lane-parallel: pair p = g*H + h is drawn by lane
+// p % 32 in round p / 32 (same Philox counters (edge, head) and word as the per-pair draw of the
+// general kernels, so the mask is bit-identical) -- one Philox evaluation per lane instead of
+// kSmallDeg*H evaluations repeated by every lane, which was a third of these kernels' instructions.
+template <int H>
+struct SmallMask {
+  static constexpr int kRounds = (kSmallDeg * H + 31) / 32;
+  float u[kRounds];
+  __device__ __forceinline__ void draw(const Philox& rng, int e0, int deg, int lane) {
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const int p = r * 32 + lane;
+      u[r] = 2.f;  // > any keep probability: unused pairs are "dropped"
+      if (p < deg * H) {
+        const uint4 x = rng((uint64_t)(e0 + p / H), (uint64_t)(p % H));
+        u[r] = (float)(x.x >> 8) * (1.0f / 16777216.0f);
+      }
+    }
+  }
+  // uniform variate of (edge g, head h); g, h are compile-time after unrolling
+  __device__ __forceinline__ float get(int g, int h) const {
+    const int p = g * H + h;
+    return __shfl_sync(0xffffffffu, u[p / 32], p % 32);
+  }
+};
+
 template <int H>
 __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_fwd_small_kernel(AttnCoreArgs a) {
   pdl_wait();
@@ -361,6 +387,8 @@ __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_fwd_small_kernel(At
         den[h] += sc[g][h];
       }
     float4 acc = z4;
+    SmallMask<H> sm;
+    if (a.dropout_p > 0.f) sm.draw(rng, e0, deg, lane);
 #pragma unroll
     for (int g = 0; g < kSmallDeg; ++g) {
       if (g >= deg) break;  // warp-uniform
@@ -369,11 +397,7 @@ __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_fwd_small_kernel(At
       for (int h = 0; h < H; ++h) {
         float p = sc[g][h] / den[h];
         if (lane == 0) a.alpha[(long long)(e0 + g) * H + h] = p;
-        if (a.dropout_p > 0.f) {
-          const uint4 r = rng((uint64_t)(e0 + g), (uint64_t)h);
-          const float uni = (float)(r.x >> 8) * (1.0f / 16777216.0f);
-          p = uni < keep ? p / keep : 0.f;
-        }
+        if (a.dropout_p > 0.f) p = sm.get(g, h) < keep ? p / keep : 0.f;
         pw[h] = p;
       }
       const float4 w4 = hm.pick(pw);
@@ -422,6 +446,8 @@ __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_bwd_small_kernel(At
       vv[g] = on ? f4_add(ld4(a.proj + jn[g] * 4 * HC + 2 * HC + c0), eev) : z4;
     }
     float al[kSmallDeg][H], dal[kSmallDeg][H], mk[kSmallDeg][H], dot[H];
+    SmallMask<H> sm;
+    if (a.dropout_p > 0.f) sm.draw(rng, e0, deg, lane);
 #pragma unroll
     for (int h = 0; h < H; ++h) dot[h] = 0.f;
 #pragma unroll
@@ -435,10 +461,9 @@ __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_bwd_small_kernel(At
         al[g][h] = (g * H + h < 32) ? __shfl_sync(0xffffffffu, my_al, g * H + h)
                                     : (g < deg ? a.alpha[(long long)(e0 + g) * H + h] : 0.f);
         mk[g][h] = 1.f;
-        if (a.dropout_p > 0.f && g < deg) {
-          const uint4 r = rng((uint64_t)(e0 + g), (uint64_t)h);
-          const float uni = (float)(r.x >> 8) * (1.0f / 16777216.0f);
-          mk[g][h] = uni < keep ? 1.f / keep : 0.f;
+        if (a.dropout_p > 0.f) {   // (warp-uniform branch; pairs past the degree are never used)
+          const float uni = sm.get(g, h);
+          if (g < deg) mk[g][h] = uni < keep ? 1.f / keep : 0.f;
         }
         dal[g][h] = warp_sum(part[h]) * mk[g][h];
         if (g < deg) dot[h] = fmaf(al[g][h], dal[g][h], dot[h]);

@@ -493,13 +493,17 @@ int32_t tgn_dec_loss(const float* hs, const float* hd, const float* w_final, con
  * on rows of emb [*,dim], BCE-with-logits loss, and all gradients (exact fp32):
  * loss (+=), d_emb rows (+=, atomics), d_w_src/d_w_dst [dim,dim] (+=), biases, d_w_final, d_b_final
  * (+=); logits [2B] optional.  Needs tgn_dec_fused_smem_bytes(dim) <= 220 KB of shared memory
- * (dim <= 116); larger decoders use tgn_gemm_batch + tgn_dec_loss. */
+ * (dim <= 116); larger decoders use tgn_gemm_batch + tgn_dec_loss.
+ * Deferred weight gradients: with z_rows and g_rows given (both [3B,dim]) d_w_src / d_w_dst are NOT
+ * touched; the kernel writes z_rows = [z_src; z_dst; z_neg] and g_rows = [g_src; g_pos; g_neg] (the
+ * gradients of the hidden layer) and the caller forms d_w_src += g_src^T z_src,
+ * d_w_dst += [g_pos; g_neg]^T [z_dst; z_neg] with tgn_gemm_batch off the dependent chain. */
 int64_t tgn_dec_fused_smem_bytes(int32_t dim);
 int32_t tgn_dec_fused(const float* emb, const int64_t* ids_local, int32_t batch, int32_t dim,
                       const float* w_src, const float* b_src, const float* w_dst, const float* b_dst,
                       const float* w_final, const float* b_final, float* loss, float* logits,
                       float* d_emb, float* d_w_src, float* d_b_src, float* d_w_dst, float* d_b_dst,
-                      float* d_w_final, float* d_b_final, void* stream);
+                      float* d_w_final, float* d_b_final, float* z_rows, float* g_rows, void* stream);
 /* TGB evaluation scoring (epoch_utils.py:99-113, decoder.py:24-27): for positive i the score of
  * (src_rows[i], dst_rows[i]) and of its num_neg negatives (src_rows[i], neg_rows[i,q]) as sigmoid
  * outputs; gt_out[i] = #{neg > pos}, ge_out[i] = #{neg >= pos} (the two counts of the TGB MRR

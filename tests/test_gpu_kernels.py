@@ -481,7 +481,21 @@ def test_dec_fused_matches_autograd(ops, B, D, Nb):
                                 p(w["lin_dst.weight"]), p(w["lin_dst.bias"]), p(w["lin_final.weight"]),
                                 p(w["lin_final.bias"]), p(out_loss), p(logits), p(d_emb), p(gr["lin_src.weight"]),
                                 p(gr["lin_src.bias"]), p(gr["lin_dst.weight"]), p(gr["lin_dst.bias"]),
-                                p(gr["lin_final.weight"]), p(gr["lin_final.bias"]), 0))
+                                p(gr["lin_final.weight"]), p(gr["lin_final.bias"]), None, None, 0))
+    # deferred weight gradients: same launch without the [D,D] accumulators; dW formed from the emitted rows
+    out2 = torch.zeros(1, device=DEV); d_emb2 = torch.zeros(Nb, D, device=DEV)
+    gr2 = {k: torch.zeros_like(v) for k, v in w.items()}
+    z_rows, g_rows = torch.zeros(3 * B, D, device=DEV), torch.zeros(3 * B, D, device=DEV)
+    _cabi.check(L.tgn_dec_fused(p(emb_d), p(ids_d), B, D, p(w["lin_src.weight"]), p(w["lin_src.bias"]),
+                                p(w["lin_dst.weight"]), p(w["lin_dst.bias"]), p(w["lin_final.weight"]),
+                                p(w["lin_final.bias"]), p(out2), None, p(d_emb2), None,
+                                p(gr2["lin_src.bias"]), None, p(gr2["lin_dst.bias"]),
+                                p(gr2["lin_final.weight"]), p(gr2["lin_final.bias"]), p(z_rows), p(g_rows), 0))
+    torch.testing.assert_close(out2, out_loss, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(d_emb2, d_emb, rtol=1e-5, atol=1e-7)
+    assert torch.equal(z_rows, emb_d[ids_d])
+    torch.testing.assert_close(g_rows[:B].t() @ z_rows[:B], gr["lin_src.weight"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(g_rows[B:].t() @ z_rows[B:], gr["lin_dst.weight"], rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(out_loss.cpu()[0], loss.detach(), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(logits.cpu(), torch.cat([pos, neg]).detach(), rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(d_emb.cpu(), emb.grad, rtol=1e-4, atol=1e-7)

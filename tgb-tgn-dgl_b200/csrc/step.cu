@@ -696,6 +696,11 @@ __global__ void __launch_bounds__(kDecWarps * 32)
 constexpr int kDecThreads = 512;  // thread (c, q): channel c = tid & 127, reduction quarter q = tid >> 7
 constexpr int kDecQ = kDecThreads / 128;
 
+// kDefer: the two [D,D] weight gradients are NOT formed here; the kernel writes the gathered inputs
+// z_rows [3B,D] = [z_src; z_dst; z_neg] and the hidden-layer gradients g_rows [3B,D] = [gs; g0; g1]
+// instead, and the caller forms dW_src = gs^T z_src, dW_dst = [g0;g1]^T [z_dst;z_neg] as two small
+// tensor-core GEMMs off the dependent chain (no shared-memory accumulators, no 20k-atomic flush per CTA).
+template <bool kDefer>
 __global__ void __launch_bounds__(kDecThreads)
     dec_fused_kernel(const float* __restrict__ emb, const int64_t* __restrict__ ids_l, int B, int D,
                      const float* __restrict__ Ws, const float* __restrict__ bs,
@@ -703,16 +708,17 @@ __global__ void __launch_bounds__(kDecThreads)
                      const float* __restrict__ wf, const float* __restrict__ bf,
                      float* __restrict__ loss, float* __restrict__ logits, float* __restrict__ d_emb,
                      float* __restrict__ dWs, float* __restrict__ dbs, float* __restrict__ dWd,
-                     float* __restrict__ dbd, float* __restrict__ dwf, float* __restrict__ dbf) {
+                     float* __restrict__ dbd, float* __restrict__ dwf, float* __restrict__ dbf,
+                     float* __restrict__ z_rows, float* __restrict__ g_rows) {
   pdl_wait();
   pdl_launch();
   extern __shared__ float sm[];
   const int ld = D + 1;
   float* sWs = sm;
   float* sWd = sWs + D * ld;
-  float* sAs = sWd + D * ld;   // dWs accumulator
-  float* sAd = sAs + D * ld;   // dWd accumulator
-  float* sz = sAd + D * ld;    // [3][D] z_src, z_dst, z_neg
+  float* sAs = sWd + D * ld;   // dWs accumulator (absent with kDefer)
+  float* sAd = sAs + D * ld;   // dWd accumulator (absent with kDefer)
+  float* sz = kDefer ? sWd + D * ld : sAd + D * ld;    // [3][D] z_src, z_dst, z_neg
   float* sg = sz + 3 * D;      // [3][D] dhs, g0, g1
   __shared__ float s_p[3][kDecQ][128];  // partial sums of the quarters
   __shared__ float s_h[2][128];
@@ -726,8 +732,10 @@ __global__ void __launch_bounds__(kDecThreads)
     const int r = i / D, k = i - r * D;
     sWs[r * ld + k] = Ws[i];
     sWd[r * ld + k] = Wd[i];
-    sAs[r * ld + k] = 0.f;
-    sAd[r * ld + k] = 0.f;
+    if (!kDefer) {
+      sAs[r * ld + k] = 0.f;
+      sAd[r * ld + k] = 0.f;
+    }
   }
   const float invB = 1.f / (float)B;
   const float bfv = bf[0];
@@ -736,9 +744,15 @@ __global__ void __launch_bounds__(kDecThreads)
     const int64_t rs = ids_l[ev], rd = ids_l[B + ev], rn = ids_l[2 * B + ev];
     __syncthreads();  // weights staged / previous event fully consumed
     for (int k = tid; k < D; k += kDecThreads) {
-      sz[k] = emb[rs * D + k];
-      sz[D + k] = emb[rd * D + k];
-      sz[2 * D + k] = emb[rn * D + k];
+      const float a = emb[rs * D + k], b = emb[rd * D + k], c2 = emb[rn * D + k];
+      sz[k] = a;
+      sz[D + k] = b;
+      sz[2 * D + k] = c2;
+      if (kDefer) {
+        z_rows[(long long)ev * D + k] = a;
+        z_rows[(long long)(B + ev) * D + k] = b;
+        z_rows[(long long)(2 * B + ev) * D + k] = c2;
+      }
     }
     __syncthreads();
     // ---- forward partials: output channel c, inputs [k0, k1)
@@ -811,13 +825,20 @@ __global__ void __launch_bounds__(kDecThreads)
         sg[c] = gs;
         sg[D + c] = g0;
         sg[2 * D + c] = g1;
+        if (kDefer) {
+          g_rows[(long long)ev * D + c] = gs;
+          g_rows[(long long)(B + ev) * D + c] = g0;
+          g_rows[(long long)(2 * B + ev) * D + c] = g1;
+        }
       }
-      float* as = sAs + c * ld;
-      float* ad = sAd + c * ld;
+      if (!kDefer) {
+        float* as = sAs + c * ld;
+        float* ad = sAd + c * ld;
 #pragma unroll 5
-      for (int k = k0; k < k1; ++k) {
-        as[k] = fmaf(gs, sz[k], as[k]);
-        ad[k] = fmaf(g0, sz[D + k], fmaf(g1, sz[2 * D + k], ad[k]));
+        for (int k = k0; k < k1; ++k) {
+          as[k] = fmaf(gs, sz[k], as[k]);
+          ad[k] = fmaf(g0, sz[D + k], fmaf(g1, sz[2 * D + k], ad[k]));
+        }
       }
     }
     __syncthreads();
@@ -851,11 +872,13 @@ __global__ void __launch_bounds__(kDecThreads)
   }
   __syncthreads();
   // ---- flush the weight-gradient accumulators
-  for (int i = tid; i < D * D; i += kDecThreads) {
-    const int r = i / D, k = i - r * D;
-    const float a = sAs[r * ld + k], b = sAd[r * ld + k];
-    if (a != 0.f) atomicAdd(&dWs[i], a);
-    if (b != 0.f) atomicAdd(&dWd[i], b);
+  if (!kDefer) {
+    for (int i = tid; i < D * D; i += kDecThreads) {
+      const int r = i / D, k = i - r * D;
+      const float a = sAs[r * ld + k], b = sAd[r * ld + k];
+      if (a != 0.f) atomicAdd(&dWs[i], a);
+      if (b != 0.f) atomicAdd(&dWd[i], b);
+    }
   }
   if (tid == 0) {
     if (loss_acc != 0.f) atomicAdd(loss, loss_acc);
@@ -1109,24 +1132,38 @@ int32_t tgn_dec_fused(const float* emb, const int64_t* ids_local, int32_t batch,
                       const float* w_src, const float* b_src, const float* w_dst, const float* b_dst,
                       const float* w_final, const float* b_final, float* loss, float* logits,
                       float* d_emb, float* d_w_src, float* d_b_src, float* d_w_dst, float* d_b_dst,
-                      float* d_w_final, float* d_b_final, void* stream) {
+                      float* d_w_final, float* d_b_final, float* z_rows, float* g_rows, void* stream) {
   TGN_REQUIRE(batch >= 1 && dim >= 1, "dec_fused: bad sizes");
-  const int64_t smem = tgn_dec_fused_smem_bytes(dim);
+  const bool defer = z_rows != nullptr || g_rows != nullptr;
+  const int64_t smem = defer ? ((int64_t)2 * dim * (dim + 1) + 6 * dim) * (int64_t)sizeof(float)
+                             : tgn_dec_fused_smem_bytes(dim);
   TGN_REQUIRE(smem <= 215 * 1024 && dim <= 128,
               "dec_fused: dim %d does not fit shared memory (use the GEMM path)", dim);
   TGN_REQUIRE(emb && ids_local && w_src && b_src && w_dst && b_dst && w_final && b_final && loss &&
-                  d_emb && d_w_src && d_b_src && d_w_dst && d_b_dst && d_w_final && d_b_final,
+                  d_emb && d_b_src && d_b_dst && d_w_final && d_b_final,
               "dec_fused: NULL pointer");
-  static int64_t attr_smem = 0;
-  if (smem > attr_smem) {
-    TGN_CUDA(cudaFuncSetAttribute(dec_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  TGN_REQUIRE(defer ? (z_rows && g_rows) : (d_w_src && d_w_dst),
+              "dec_fused: give d_w_src/d_w_dst, or z_rows AND g_rows for deferred weight gradients");
+  static int64_t attr_smem[2] = {0, 0};
+  if (smem > attr_smem[defer]) {
+    if (defer)
+      TGN_CUDA(cudaFuncSetAttribute(dec_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      TGN_CUDA(cudaFuncSetAttribute(dec_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[defer] = smem;
   }
-  int grid = ceil_div(batch, 2);  // ~2 events per CTA: balances the event walk against the flush
+  // ~2 events per CTA balances the event walk against the accumulator flush; without the flush
+  // (deferred weight gradients) the only per-CTA fixed cost is staging the two weight matrices
+  int grid = ceil_div(batch, 2);
   if (grid > kNumSMs) grid = kNumSMs;
-  launch_k(dec_fused_kernel, dim3(grid), dim3(kDecThreads), (size_t)smem, (cudaStream_t)stream, 
-      emb, ids_local, batch, dim, w_src, b_src, w_dst, b_dst, w_final, b_final, loss, logits, d_emb,
-      d_w_src, d_b_src, d_w_dst, d_b_dst, d_w_final, d_b_final);
+  if (defer)
+    launch_k(dec_fused_kernel<true>, dim3(grid), dim3(kDecThreads), (size_t)smem, (cudaStream_t)stream,
+             emb, ids_local, batch, dim, w_src, b_src, w_dst, b_dst, w_final, b_final, loss, logits, d_emb,
+             d_w_src, d_b_src, d_w_dst, d_b_dst, d_w_final, d_b_final, z_rows, g_rows);
+  else
+    launch_k(dec_fused_kernel<false>, dim3(grid), dim3(kDecThreads), (size_t)smem, (cudaStream_t)stream,
+             emb, ids_local, batch, dim, w_src, b_src, w_dst, b_dst, w_final, b_final, loss, logits, d_emb,
+             d_w_src, d_b_src, d_w_dst, d_b_dst, d_w_final, d_b_final, z_rows, g_rows);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

@@ -609,10 +609,18 @@ class TGNEngine:
             check(L.tgn_dec_fused(_p(w.emb), _p(w.ids_l), B, D, _p(p["lin_src.weight"]), _p(p["lin_src.bias"]),
                                   _p(p["lin_dst.weight"]), _p(p["lin_dst.bias"]), _p(p["lin_final.weight"]),
                                   _p(p["lin_final.bias"]), _p(self.loss_acc), _p(w.logits), _p(self.d_emb),
-                                  gptr("lin_src.weight"), gptr("lin_src.bias"), gptr("lin_dst.weight"),
-                                  gptr("lin_dst.bias"), gptr("lin_final.weight"), gptr("lin_final.bias"), s))
+                                  None, gptr("lin_src.bias"), None,
+                                  gptr("lin_dst.bias"), gptr("lin_final.weight"), gptr("lin_final.bias"),
+                                  _p(w.zcat), _p(w.dhcat), s))
+            dec_wgrad = [  # dW_src += g_src^T z_src ; dW_dst += [g_pos; g_neg]^T [z_dst; z_neg]  (aux stream, below)
+                ops.gemm_desc(w.dhcat, w.zcat, fg, m=D, n=D, k=B, lda=D, ldb=D, ldc=D, trans_a=True, trans_b=True,
+                              mode=2, c_off=off["lin_src.weight"]),
+                ops.gemm_desc(w.dhcat, w.zcat, fg, m=D, n=D, k=2 * B, lda=D, ldb=D, ldc=D, trans_a=True,
+                              trans_b=True, mode=2, a_off=B * D, b_off=B * D, c_off=off["lin_dst.weight"]),
+            ]
         else:
             self._decoder_gemm_path(w, s)
+            dec_wgrad = []
         # ---- attention backward
         check(L.tgn_attn_core_bwd(_p(w.proj), _p(w.nbr_l), _p(w.root_off), _p(w.ctr_l), w.R, _p(w.R_dev),
                                   self.H, self.C, _p(w.ee), _p(w.alpha), _p(self.d_emb), self.dropout, self.seed,
@@ -637,6 +645,8 @@ class TGNEngine:
                 g.append(ops.gemm_desc(w.d_ee, fl, w.d_eat, m=w.E, n=self.Dt, k=HC, lda=HC, ldb=self.lde,
                                        ldc=self.Dt, trans_b=True, b_off=off["conv.lin_edge.weight"], m_dev=w.E_dev))
             ops.gemm_batch(g, self.prec)
+            if dec_wgrad:
+                ops.gemm_batch(dec_wgrad, self.prec)
             # bias gradient of the node projection and the attention-side TimeEncoder gradient
             ops.colsum(w.d_proj, w.Nb, 4 * HC, 4 * HC, p["conv.b_node"].grad, True, rows_dev=w.Nb_dev)
             if self.Dt:

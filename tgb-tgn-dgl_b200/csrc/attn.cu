@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_fwd_kernel(AttnArgs a
           const long long mr = a.msg_rows ? a.msg_rows[eid[u]] : eid[u];
           const float rt = attn_rel_t(a, jn[u], mr);
           for (int d = lane; d < a.Dt; d += 32)
-            ea[d * kEB + u] = cosf(__fmaf_rn(rt, a.time_w[d], a.time_b[d]));
+            ea[d * kEB + u] = cos_fr(__fmaf_rn(rt, a.time_w[d], a.time_b[d]));
           const float* mp = a.msg + mr * a.De;
           for (int d = lane; d < a.De; d += 32) ea[(a.Dt + d) * kEB + u] = mp[d];
         } else {

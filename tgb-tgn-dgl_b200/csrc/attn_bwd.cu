@@ -203,7 +203,7 @@ __global__ void attn_edge_attr_kernel(EdgeAttrArgs a) {
                                      : (float)reinterpret_cast<const int64_t*>(a.t_edge)[pr];
         rt = l - t;
       }
-      a.ea[x] = cosf(__fmaf_rn(rt, a.time_w[d], a.time_b[d]));
+      a.ea[x] = cos_fr(__fmaf_rn(rt, a.time_w[d], a.time_b[d]));
       if (d == 0 && a.rel) a.rel[e] = rt;
     } else {
       const long long mr = a.msg_rows ? a.msg_rows[e] : e;

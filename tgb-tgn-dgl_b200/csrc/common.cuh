@@ -172,6 +172,22 @@ __device__ __forceinline__ long long lookback_prefix(unsigned long long* ws, int
   return prefix;
 }
 
+// Full-range sine / cosine for the TimeEncoder (arguments w*dt+b reach 1e6 rad on the wiki shape).
+// CUDA's sincosf switches to a Payne-Hanek reduction through local memory beyond |x| = 105615; a
+// double-precision reduction by 2*pi of the SAME fp32 argument is two FP64 instructions and keeps
+// the result within 2e-7 of the exactly reduced one (the parity bar is 1e-5).
+__device__ __forceinline__ float reduce_2pi(float x) {
+  if (fabsf(x) > 105615.0f) {
+    const double a = (double)x;
+    const double k = rint(a * 0.15915494309189535);
+    x = (float)fma(-k, 6.283185307179586, a);
+  }
+  return x;
+}
+__device__ __forceinline__ void sincos_fr(float x, float* s, float* c) { sincosf(reduce_2pi(x), s, c); }
+__device__ __forceinline__ float cos_fr(float x) { return cosf(reduce_2pi(x)); }
+__device__ __forceinline__ float sin_fr(float x) { return sinf(reduce_2pi(x)); }
+
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

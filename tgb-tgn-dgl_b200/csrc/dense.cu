@@ -233,7 +233,7 @@ __global__ void time_encode_kernel(const float* __restrict__ t, int num,
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(e / D), c = (int)(e - (long long)i * D);
-    out[e] = cosf(__fmaf_rn(t[i], w[c], b[c]));
+    out[e] = cos_fr(__fmaf_rn(t[i], w[c], b[c]));
   }
 }
 
@@ -339,7 +339,7 @@ __global__ void time_encode_bwd_kernel(const float* __restrict__ t, const int32_
     for (int r = r0 + ry; r < r1; r += 8) {
       if (mask && mask[r] < 0) continue;
       const float tt = t[r];
-      const float ds = -sinf(__fmaf_rn(tt, wc, bc)) * g[(long long)r * ldg + c];
+      const float ds = -sin_fr(__fmaf_rn(tt, wc, bc)) * g[(long long)r * ldg + c];
       aw = fmaf(ds, tt, aw);
       ab += ds;
     }

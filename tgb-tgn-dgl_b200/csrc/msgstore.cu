@@ -265,7 +265,7 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
       for (int c = lane; c < De; c += 32) xr[2 * Dm + c] = rw[c];
       for (int c = lane; c < Dt; c += 32) {
         float sv, cv;
-        sincosf(__fmaf_rn(dt, time_w[c], time_b[c]), &sv, &cv);
+        sincos_fr(__fmaf_rn(dt, time_w[c], time_b[c]), &sv, &cv);
         xr[2 * Dm + De + c] = cv;
         if (sin_out) sin_out[(long long)s * Dt + c] = sv;  // for tgn_time_bwd_sin
       }
@@ -302,7 +302,7 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
               } else if (c < 2 * Dm + De) v = st.ev_msg[(long long)e * De + (c - 2 * Dm)];
               else {
                 const int cc = c - 2 * Dm - De;
-                v = cosf(__fmaf_rn(rel_time<T>(te, lu), time_w[cc], time_b[cc]));
+                v = cos_fr(__fmaf_rn(rel_time<T>(te, lu), time_w[cc], time_b[cc]));
               }
               acc += v;
             }

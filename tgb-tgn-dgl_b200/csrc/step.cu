@@ -59,7 +59,7 @@ __global__ void edge_attr_ld_kernel(EdgeAttr2Args a) {
     if (d < a.Dt) {
       const float rt = (float)(a.lu[a.nbr[e]] - a.t_edge[mr]);
       float sv, cv;
-      sincosf(__fmaf_rn(rt, a.time_w[d], a.time_b[d]), &sv, &cv);
+      sincos_fr(__fmaf_rn(rt, a.time_w[d], a.time_b[d]), &sv, &cv);
       a.ea[x] = cv;
       if (a.sn) a.sn[(long long)e * a.Dt + d] = sv;
       if (d == 0 && a.rel) a.rel[e] = rt;

@@ -246,3 +246,22 @@ def test_eval_counts_are_additive_over_negative_shards():
             assert torch.equal(e.memory, engs[0].memory) and torch.equal(e.last_update, engs[0].last_update)
             assert torch.equal(e.e_id, engs[0].e_id)
     assert int(engs[0].e_id.ge(0).sum()) > 0 and float(engs[0].memory.abs().sum()) > 0
+
+
+def test_multi_step_graph_equals_single_steps():
+    """train_steps(n): three steps per captured graph (+ remainder) == n single-step launches."""
+    N, De, D, K, B, steps = 300, 8, 16, 4, 32, 26
+    # (small lr: two identical engines drift apart after ~15 steps at lr 1e-3 -- split-K atomics give
+    # rounding-level gradient noise that Adam amplifies; the comparison is about the step plumbing)
+    _, eng_a, ev = _setup(N, De, D, K, B, B * steps, 13, True, lr=1e-6)
+    _, eng_b, _ = _setup(N, De, D, K, B, B * steps, 13, True, lr=1e-6)
+    la = [float(eng_a.train_step(from_device=True)) for _ in range(steps)]
+    done = 0
+    for n in (1, 9, 2, 14):            # eager warm-up calls, capture, replays, remainders
+        lb = float(eng_b.train_steps(n))
+        done += n
+        assert abs(lb - la[done - 1]) < 1e-4, (done, lb, la[done - 1])
+    assert done == steps and eng_b.events_done == eng_a.events_done
+    torch.testing.assert_close(eng_a.memory, eng_b.memory, rtol=1e-2, atol=1e-3)
+    assert torch.equal(eng_a.e_id, eng_b.e_id) and torch.equal(eng_a.last_update, eng_b.last_update)
+    assert torch.equal(eng_a.t_ring, eng_b.t_ring)

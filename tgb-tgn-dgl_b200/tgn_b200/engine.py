@@ -692,11 +692,14 @@ class TGNEngine:
                                 _p(self.loss_acc), self.loss_slots.data_ptr() + 4 * self.cur, _p(self.done_ctr), int(self.fused_zero_grad),
                                 _p(self.d_emb), self.d_emb.numel(), _stream()))
 
-    def _run(self, key: tuple, body):
+    def _run(self, key: tuple, body, capture: bool = True):
         if not self.use_graph:
             body()
             return
         g = self._graphs.get(key)
+        if g is None and not capture:      # caller does not want a capture (sync + ~10 ms) at this point
+            body()
+            return
         if g is None:
             # warm-up: the first calls of every configuration run eagerly
             cnt = self._graphs.get(("warm",) + key, 0)
@@ -711,7 +714,7 @@ class TGNEngine:
             self._graphs[key] = g
         g.replay()
 
-    def train_step(self, from_device: bool = True, lookahead: bool = False):
+    def train_step(self, from_device: bool = True, lookahead: bool = False, _capture: bool = True):
         """One training batch; returns the (device) loss of that batch.
 
         from_device=True : batches are sliced out of the resident event arrays (set_events).  The
@@ -739,7 +742,8 @@ class TGNEngine:
         if pipelined and self._slot_async[nxt]:          # the batch staged ahead on the copy stream has landed
             main.wait_event(self._slot_ready[nxt])
             self._slot_async[nxt] = False
-        self._run(("train", from_device, pipelined, self.cur), lambda: self._train_body(from_device, pipelined))
+        self._run(("train", from_device, pipelined, self.cur), lambda: self._train_body(from_device, pipelined),
+                  capture=_capture)
         self._slot_free[self.cur].record(main)
         self.loss = self.loss_slots[self.cur]
         if pipelined:
@@ -747,6 +751,31 @@ class TGNEngine:
         self.events_done += self.B
         self.store.size = self.events_done   # host mirror of log_base_dev (graph replays skip the Python body)
         return self.loss
+
+    def train_steps(self, n: int):
+        """n consecutive training batches from the resident event arrays (set_events).  The slot rotation
+        has period `nslots`, so `nslots` steps are captured as ONE graph: one launch per three steps, no
+        launch gap at the two inner step boundaries.  The remainder runs step by step.  Returns the
+        (device) loss of the last batch."""
+        done = 0
+        if n > 0 and self._primed != "device":
+            self.train_step(from_device=True)
+            done = 1
+        while self.use_graph and n - done >= self.nslots:
+            self._run(("train_multi", self.cur), self._multi_body)
+            done += self.nslots
+            self.events_done += self.nslots * self.B
+            self.store.size = self.events_done
+            self.loss = self.loss_slots[(self.cur - 1) % self.nslots]
+        while done < n:          # remainder: replays the single-step graph if it exists, else runs eagerly
+            self.train_step(from_device=True, _capture=False)
+            done += 1
+        return self.loss
+
+    def _multi_body(self):
+        for _ in range(self.nslots):
+            self._train_body(True, True)
+            self.cur = self._next_slot()
 
     def train_step_logged(self, **kw) -> Optional[float]:
         """train_step() with a pipelined loss read-back for logging loops: the device->host copy of

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kGThreads, 1)
 #pragma unroll
     for (int i = 0; i < kGMaxStages; ++i) {
       g_mbar_init(&s_full[i], 1);
-      g_mbar_init(&s_conv[i], kGConv);
+      g_mbar_init(&s_conv[i], kGConv / 32);   // one arrival per split warp
       g_mbar_init(&s_empty[i], 1);
     }
     g_mbar_init(&s_acc, 1);
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kGThreads, 1)
         const int s = kb % kGStages;
         g_mbar_wait(&s_full[s], (kb / kGStages) & 1);
         if (!split3 && kb != nk - 1) {  // tf32 mode: only the masked last block is touched
-          g_mbar_arrive(&s_conv[s]);
+          if (lane == 0) g_mbar_arrive(&s_conv[s]);
           continue;
         }
         const uint32_t a_hi = g_smem_u32(smem + (size_t)s * kGStageBytes);
@@ -348,7 +348,8 @@ __global__ void __launch_bounds__(kGThreads, 1)
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic -> async proxy
-        g_mbar_arrive(&s_conv[s]);
+        __syncwarp();                                  // one arrival per warp: 8 barrier updates per
+        if (lane == 0) g_mbar_arrive(&s_conv[s]);      // k-block instead of 256 serialised ones
       }
     }
     if (nk > 0) {
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(kGThreads, 1)
 #pragma unroll
     for (int i = 0; i < kStages; ++i) {
       g_mbar_init(&s_full[i], 1);
-      g_mbar_init(&s_conv[i], kGConv);
+      g_mbar_init(&s_conv[i], kGConv / 32);   // one arrival per split warp
       g_mbar_init(&s_empty[i], 1);
     }
     g_mbar_init(&s_acc, 1);
@@ -660,7 +661,8 @@ __global__ void __launch_bounds__(kGThreads, 1)
           g_sts4(a_hi + 3 * kGTileBytes + o, lb);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        g_mbar_arrive(&s_conv[s]);
+        __syncwarp();
+        if (lane == 0) g_mbar_arrive(&s_conv[s]);
       }
     }
     if (nk > 0) {

@@ -28,14 +28,14 @@ if which == "gru_pair":
     fn = lambda: ops.gemm_batch([
         ops.gemm_desc(x, wih, gi, m=S, n=3 * D, k=Dx, lda=ldx, ldb=ldx, ldc=3 * D, bias=bi),
         ops.gemm_desc(h, whh, gh, m=S, n=3 * D, k=D, lda=D, ldb=D, ldc=3 * D, bias=bh)], 3)
-elif which == "gru_fused":
+elif which in ("gru_fused", "gru_fused1"):
     # the step's GRUCell forward as one launch (tgn_gru_fused_fwd) on step-sized operands
     S, Dx, ldx, D = 5_023, 301, 304, 100
     x = torch.randn(S, ldx, device=dev); h = torch.randn(S, D, device=dev)
     wih = torch.randn(3 * D, ldx, device=dev); whh = torch.randn(3 * D, D, device=dev)
     bi = torch.randn(3 * D, device=dev); bh = torch.randn(3 * D, device=dev)
     z = torch.empty(S, D, device=dev); gates = torch.empty(S, 4 * D, device=dev)
-    fn = lambda: ops.gru_fused_fwd(x, h, wih, whh, bi, bh, dx=Dx, ldx=ldx, ldw=ldx, num=S, prec=3, out=z, gates=gates)
+    fn = lambda: ops.gru_fused_fwd(x, h, wih, whh, bi, bh, dx=Dx, ldx=ldx, ldw=ldx, num=S, prec=3 if which == "gru_fused" else 1, out=z, gates=gates)
 elif which.startswith("gemm"):
     # gemm3 / gemm1 [ _ld480 : rows padded to a multiple of 128 bytes ] [ _small : 5,023 rows as in the step ]
     S, Dx, D = (5_023 if "small" in which else 65_536), 472, 100

@@ -369,8 +369,9 @@ def main():
 def bench_partitioned(dev, rank, world, steps, warmup, precision):
     """ONE training job with the node memory partitioned by owner over the ranks (BASELINE.json
     configs[2]): synthetic tgbl-coin shape (638,486 nodes), batch 600, K=10.  Node n lives on rank
-    n % world; the rows a step needs are assembled on every rank by one all-reduce over
-    NVLink/NVSwitch (csrc/partition.cu), gradients are all-reduced, everything else is replicated.
+    n % world; the shards are symmetric memory mapped into every rank, so the rows a step needs are read
+    straight out of their owners' HBM over NVLink/NVSwitch (tgn_part_gather_p2p between two device-side
+    rank barriers; csrc/partition.cu), gradients are all-reduced, everything else is replicated.
     value = events/s of that one job (strong scaling: the batch does not grow with the ranks)."""
     import torch.distributed as dist
     from tgn_b200 import synth
@@ -410,8 +411,9 @@ def bench_partitioned(dev, rank, world, steps, warmup, precision):
             "final_loss": float(eng.loss), "rows_per_step": rows,
             "memory_rows_per_gpu": eng.Nloc, "memory_bytes_per_gpu": eng.Nloc * HIDDEN * 4,
             "workload": f"synthetic {name} shape: {N} nodes, raw_dim {De}, batch {B}, {K} recent nbrs, dim {HIDDEN}",
-            "collectives_per_step": ("all-reduce of the assembled rows [2,Nb,D] fp32 + last_update [Nb] int64, "
-                                     "all-reduce of the flat gradient") if world > 1 else "none (single GPU)"}
+            "exchange": eng.part_exchange,
+            "collectives_per_step": ("peer-memory row gather between two signal-pad rank barriers (no data "
+                                     "collective), all-reduce of the flat gradient") if world > 1 else "none (single GPU)"}
 
 
 def bench_eval_dp(dev, rank, world, n_batches, precision):

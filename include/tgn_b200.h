@@ -256,6 +256,15 @@ int32_t tgn_part_gather(const tgn_msgstore* st, const int64_t* n_id, int32_t num
                         const int64_t* last_update_local, int32_t memory_dim, int32_t rank,
                         int32_t world, float* rows_n, float* rows_other, int64_t* lu_out,
                         int64_t* other_out, void* stream);
+/* Peer-memory variant of tgn_part_gather: peer_memory / peer_last_update are HOST arrays of `world`
+ * device pointers to every rank's shard, mapped into this process (NVLink peer access, e.g. torch
+ * symmetric memory); every row is read from its owner's HBM directly, so no all-reduce follows.
+ * The caller separates it from the scatters of the previous and of the current step with rank
+ * barriers.  world <= 16. */
+int32_t tgn_part_gather_p2p(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                            const int32_t* num_dev, const void* const* peer_memory,
+                            const void* const* peer_last_update, int32_t memory_dim, int32_t world,
+                            float* rows_n, float* rows_other, int64_t* lu_out, void* stream);
 int32_t tgn_msg_build_gathered(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
                                const int32_t* num_dev, const float* rows_n, const float* rows_other,
                                const int64_t* last_update_rows, int32_t memory_dim,

@@ -1,5 +1,5 @@
 """Run under torchrun on >= 2 GPUs (see tests/test_gpu_multi.py): the owner-partitioned engine
-(world ranks, NCCL all-reduce row assembly) against the unpartitioned engine on the same events
+(world ranks; peer-memory row assembly over symmetric memory, and the NCCL all-reduce assembly) against the unpartitioned engine on the same events
 and weights -- per-step loss, reassembled memory / last_update, neighbour ring, weights."""
 import os
 import sys
@@ -36,11 +36,11 @@ def main():
         ref["memory"].time_enc.lin.weight.mul_(0.002)
     ev = dict(src=torch.from_numpy(src), dst=torch.from_numpy(dst), t=torch.from_numpy(t),
               msg=torch.from_numpy(msg), neg=torch.from_numpy(neg))
-    for use_graph in (False, True):
+    for use_graph, exchange in ((False, "p2p"), (True, "p2p"), (True, "allreduce")):
         engs = []
         for part in (False, True):
             eng = TGNEngine(N, De, D, K, B, device=dev, lr=1e-5, dropout=0.0, use_graph=use_graph, log_capacity=E,
-                            rank=rank if part else 0, world=world if part else 1)
+                            rank=rank if part else 0, world=world if part else 1, part_exchange=exchange)
             eng.load_state(ref["memory"].state_dict(), ref["gnn"].state_dict(), ref["link_pred"].state_dict())
             eng.set_events(**ev)
             engs.append(eng)
@@ -67,7 +67,8 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
-        print(f"partition check OK: world={world}, {steps} steps eager + graph, losses / memory / ring / weights agree",
+        print(f"partition check OK: world={world}, {steps} steps eager + graph, peer-memory and all-reduce row "
+              f"assembly, losses / memory / ring / weights agree",
               flush=True)
     # the captured graphs hold NCCL kernels; tearing the communicator down underneath them can block,
     # so leave without the collective shutdown

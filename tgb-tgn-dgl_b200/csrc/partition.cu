@@ -64,6 +64,55 @@ __global__ void part_gather_kernel(tgn_msgstore st, const int64_t* __restrict__ 
   }
 }
 
+// Peer-memory variant: every rank's shard is mapped into this process (NVLink / NVSwitch peer access,
+// torch symmetric memory), so the rows are read straight out of their owners' HBM -- no staging buffer,
+// no all-reduce.  The caller brackets the launch with two rank barriers (all scatters of the previous
+// step done / all gathers done before anyone scatters again).
+constexpr int kMaxPeers = 16;
+struct PeerShards {
+  const float* mem[kMaxPeers];
+  const int64_t* lu[kMaxPeers];
+};
+
+template <typename T>
+__global__ void part_gather_p2p_kernel(tgn_msgstore st, const int64_t* __restrict__ n_id, DevCount num,
+                                       int bound, PeerShards peers, int Dm, int world,
+                                       float* __restrict__ g_n, float* __restrict__ g_o,
+                                       int64_t* __restrict__ g_lu) {
+  pdl_wait();
+  pdl_launch();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int S = num.get();
+  const T* ev_t = reinterpret_cast<const T*>(st.ev_t);
+  for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < bound; s += gridDim.x * wpb) {
+    float* gn = g_n + (long long)s * Dm;
+    float* go = g_o + (long long)s * Dm;
+    int64_t n = -1, other = -1;
+    if (s < S) {
+      n = n_id[s];
+      if (n >= 0 && n < st.num_nodes) {
+        const int sc = st.s_cnt[n], dc = st.d_cnt[n];
+        if (sc + dc > 0) {
+          const int es = sc > 0 ? st.s_last[n] : -1, ed = dc > 0 ? st.d_last[n] : -1;
+          const T ts_ = es >= 0 ? ev_t[es] : (T)0, td_ = ed >= 0 ? ev_t[ed] : (T)0;
+          const bool pick_s = es >= 0 && (ed < 0 || ts_ >= td_);
+          other = pick_s ? st.ev_dst[es] : st.ev_src[ed];
+        }
+      } else {
+        n = -1;
+      }
+    }
+    const float* pn = n >= 0 ? peers.mem[n % world] + (n / world) * Dm : nullptr;
+    const float* po = other >= 0 ? peers.mem[other % world] + (other / world) * Dm : nullptr;
+    for (int c = lane; c < Dm; c += 32) {
+      gn[c] = pn ? pn[c] : 0.f;
+      go[c] = po ? po[c] : 0.f;
+    }
+    if (lane == 0) g_lu[s] = n >= 0 ? peers.lu[n % world][n / world] : 0;
+  }
+}
+
 template <typename T>
 __global__ void memory_scatter_owned_kernel(const int64_t* __restrict__ n_id, DevCount num,
                                             const float* __restrict__ new_mem,
@@ -113,6 +162,35 @@ int32_t tgn_part_gather(const tgn_msgstore* st, const int64_t* n_id, int32_t num
   else
     launch_k(part_gather_kernel<int64_t>, dim3(grid), dim3(256), 0, s, *st, n_id, c, num, memory_local,
              last_update_local, memory_dim, rank, world, rows_n, rows_other, lu_out, other_out);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_part_gather_p2p(const tgn_msgstore* st, const int64_t* n_id, int32_t num,
+                            const int32_t* num_dev, const void* const* peer_memory,
+                            const void* const* peer_last_update, int32_t memory_dim, int32_t world,
+                            float* rows_n, float* rows_other, int64_t* lu_out, void* stream) {
+  TGN_REQUIRE(st && st->num_nodes > 0, "part_gather_p2p: store is NULL");
+  TGN_REQUIRE(num >= 0 && memory_dim >= 1 && world >= 1 && world <= kMaxPeers,
+              "part_gather_p2p: bad sizes (world <= %d)", kMaxPeers);
+  if (num == 0) return TGN_OK;
+  TGN_REQUIRE(n_id && peer_memory && peer_last_update && rows_n && rows_other && lu_out,
+              "part_gather_p2p: NULL pointer");
+  PeerShards peers;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    peers.mem[r] = r < world ? (const float*)peer_memory[r] : nullptr;
+    peers.lu[r] = r < world ? (const int64_t*)peer_last_update[r] : nullptr;
+    TGN_REQUIRE(r >= world || (peers.mem[r] && peers.lu[r]), "part_gather_p2p: peer %d has no mapping", r);
+  }
+  const int grid = stride_grid((long long)num * 32, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  DevCount c{num_dev, num};
+  if (st->t_is_float)
+    launch_k(part_gather_p2p_kernel<float>, dim3(grid), dim3(256), 0, s, *st, n_id, c, num, peers, memory_dim,
+             world, rows_n, rows_other, lu_out);
+  else
+    launch_k(part_gather_p2p_kernel<int64_t>, dim3(grid), dim3(256), 0, s, *st, n_id, c, num, peers,
+             memory_dim, world, rows_n, rows_other, lu_out);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

@@ -48,7 +48,8 @@ class TGNEngine:
     def __init__(self, num_nodes: int, raw_dim: int, hidden: int, size_k: int, batch_size: int,
                  device="cuda", lr: float = 1e-4, heads: int = 2, dropout: float = 0.1,
                  log_capacity: int = 1 << 20, seed: int = 0, use_graph: bool = True,
-                 precision: int = 3, rank: int = 0, world: int = 1, group=None, fused_zero_grad: bool = False):
+                 precision: int = 3, rank: int = 0, world: int = 1, group=None, fused_zero_grad: bool = False,
+                 part_exchange: str = "p2p"):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("TGNEngine runs on CUDA only (no CPU fallback)")
@@ -113,8 +114,30 @@ class TGNEngine:
             v.grad = self._view(self.flat_grad, name, shp)
             self.p[name] = v
         # ---- state
-        self.memory = torch.zeros((self.Nloc, D), device=dev)          # this rank's shard (all of it if world == 1)
-        self.last_update = torch.zeros(self.Nloc, dtype=torch.long, device=dev)
+        # this rank's shard (all of it if world == 1).  Partitioned + "p2p": the shards are torch symmetric
+        # memory, mapped into every rank (NVLink / NVSwitch peer access): the row assembly reads remote rows
+        # straight out of their owners' HBM (tgn_part_gather_p2p) between two device-side rank barriers,
+        # instead of staging owned rows and all-reducing 2*Nb*D floats ("allreduce").
+        if part_exchange not in ("p2p", "allreduce"):
+            raise ValueError("part_exchange must be 'p2p' or 'allreduce'")
+        self.part_exchange = part_exchange if world > 1 else "none"
+        if self.part_exchange == "p2p":
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            self.memory = symm_mem.empty((self.Nloc, D), dtype=torch.float32, device=dev)
+            self.last_update = symm_mem.empty((self.Nloc,), dtype=torch.long, device=dev)
+            self.memory.zero_()
+            self.last_update.zero_()
+            self._symm_mem = symm_mem.rendezvous(self.memory, grp)
+            self._symm_lu = symm_mem.rendezvous(self.last_update, grp)
+            self._peer_mem = (ctypes.c_void_p * world)(*[int(p) for p in self._symm_mem.buffer_ptrs])
+            self._peer_lu = (ctypes.c_void_p * world)(*[int(p) for p in self._symm_lu.buffer_ptrs])
+            torch.cuda.synchronize()
+            self._symm_mem.barrier(channel=0)
+        else:
+            self.memory = torch.zeros((self.Nloc, D), device=dev)
+            self.last_update = torch.zeros(self.Nloc, dtype=torch.long, device=dev)
         self.assoc = torch.zeros(num_nodes, dtype=torch.long, device=dev)
         self.neighbors = torch.zeros((num_nodes, size_k), dtype=torch.long, device=dev)
         self.e_id = torch.full((num_nodes, size_k), -1, dtype=torch.long, device=dev)
@@ -430,6 +453,15 @@ class TGNEngine:
         D = self.D
         if S > w.g_rows.shape[1]:
             raise _cabi.TgnError("row assembly: workspace too small")
+        if self.part_exchange == "p2p":
+            # barrier 0: every rank's owner-side writes of the previous step / batch are complete;
+            # barrier 1: every rank has read its rows before anyone's next scatter can start
+            self._symm_mem.barrier(channel=0)
+            check(_L().tgn_part_gather_p2p(ctypes.byref(self.store.struct()), _p(n_id), S, _p(S_dev), self._peer_mem,
+                                           self._peer_lu, D, self.world, _p(w.g_rows),
+                                           w.g_rows.data_ptr() + 4 * w.g_rows.shape[1] * D, _p(w.g_lu), _stream()))
+            self._symm_mem.barrier(channel=1)
+            return
         check(_L().tgn_part_gather(ctypes.byref(self.store.struct()), _p(n_id), S, _p(S_dev), _p(self.memory),
                                    _p(self.last_update), D, self.rank, self.world, _p(w.g_rows),
                                    w.g_rows.data_ptr() + 4 * w.g_rows.shape[1] * D, _p(w.g_lu), None, _stream()))

@@ -184,6 +184,8 @@ def main():
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     ap.add_argument("--no-eval-dp", action="store_true")
     ap.add_argument("--no-partitioned", action="store_true")
+    ap.add_argument("--part-exchange", default="p2p", choices=["p2p", "allreduce"],
+                    help="row assembly of the partitioned-memory leg: peer reads over symmetric memory, or NCCL all-reduce")
     ap.add_argument("--eval-batches", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=int, default=3, choices=[1, 3],
@@ -318,7 +320,7 @@ def main():
 
     part = None
     if not args.no_partitioned:
-        part = bench_partitioned(dev, rank, world, min(K_steps, 300), W, args.precision)
+        part = bench_partitioned(dev, rank, world, min(K_steps, 300), W, args.precision, args.part_exchange)
     eval_dp = None
     if not args.no_eval_dp:
         eval_dp = bench_eval_dp(dev, rank, world, args.eval_batches, args.precision)
@@ -366,7 +368,7 @@ def main():
         os._exit(0)
 
 
-def bench_partitioned(dev, rank, world, steps, warmup, precision):
+def bench_partitioned(dev, rank, world, steps, warmup, precision, exchange="p2p"):
     """ONE training job with the node memory partitioned by owner over the ranks (BASELINE.json
     configs[2]): synthetic tgbl-coin shape (638,486 nodes), batch 600, K=10.  Node n lives on rank
     n % world; the shards are symmetric memory mapped into every rank, so the rows a step needs are read
@@ -383,7 +385,7 @@ def bench_partitioned(dev, rank, world, steps, warmup, precision):
     N, De = data["num_nodes"], data["raw_dim"]
     eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.1, use_graph=True,
                     log_capacity=data["src"].size, seed=99, precision=precision, rank=rank, world=world,
-                    fused_zero_grad=True)
+                    fused_zero_grad=True, part_exchange=exchange)
     eng.load_state(*init_state_dicts(De, HIDDEN, N, seed=1))
     eng.set_events(**{k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")})
     ring = ring_after(data["src"][:prefill], data["dst"][:prefill], data["t"][:prefill], K, N)

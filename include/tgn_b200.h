@@ -58,6 +58,10 @@ const char* tgn_last_error(void);
  * change).  Enabled by default; returns the previous setting. */
 int32_t tgn_set_pdl(int32_t enabled);
 
+/* cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDefault, stream): the host <-> device staging copies of the
+ * end-to-end path (pinned batch in, loss word out) without a framework call per copy. */
+int32_t tgn_memcpy_async(void* dst, const void* src, int64_t nbytes, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Sorted-unique + relabel by bitmap ranking.
  * Replaces torch.cat([...]).unique() + `_assoc[n_id] = arange` at

@@ -173,6 +173,13 @@ int32_t tgn_set_pdl(int32_t enabled) {
   return old;
 }
 
+int32_t tgn_memcpy_async(void* dst, const void* src, int64_t nbytes, void* stream) {
+  TGN_REQUIRE(nbytes >= 0 && (nbytes == 0 || (dst && src)), "memcpy_async: bad arguments");
+  if (nbytes == 0) return TGN_OK;
+  TGN_CUDA(cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return TGN_OK;
+}
+
 int64_t tgn_bitmap_bytes(int64_t num_nodes) {
   if (num_nodes < 0) return 0;
   return (l0_words(num_nodes) + l1_words(num_nodes)) * 4;

@@ -169,7 +169,8 @@ class TGNEngine:
         self._primed = None      # "device" / "host": slots[cur] holds a staged AND sampled batch
         self._bind(0)
         self.loss_slots = torch.zeros(3, device=dev)   # loss of the step that trained on slot i (a lagged host
-        self.loss = self.loss_slots[0]                 # read of step s survives until step s+3 overwrites it)
+        self._loss_views = [self.loss_slots[i] for i in range(3)]
+        self.loss = self._loss_views[0]                # read of step s survives until step s+3 overwrites it)
         self.bounds = (R, E, Nb)
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.training = True
@@ -385,9 +386,11 @@ class TGNEngine:
         idx = self._next_slot()
         cs = self.copy_stream
         cs.wait_event(self._slot_free[idx])
-        with torch.cuda.stream(cs):
-            self.slots[idx].in_raw.copy_(buf, non_blocking=True)
-            self._slot_ready[idx].record(cs)
+        raw = self.slots[idx].in_raw
+        if buf.numel() != raw.numel() or buf.dtype != torch.uint8 or not buf.is_contiguous():
+            raise _cabi.TgnError("stage_packed1: buf must be a contiguous uint8 tensor of packed_nbytes() bytes")
+        check(_L().tgn_memcpy_async(raw.data_ptr(), buf.data_ptr(), raw.numel(), cs.cuda_stream))
+        self._slot_ready[idx].record(cs)
         self._slot_async[idx] = True
 
     def prefill(self, count: int, ring_state=None):
@@ -777,7 +780,7 @@ class TGNEngine:
         self._run(("train", from_device, pipelined, self.cur), lambda: self._train_body(from_device, pipelined),
                   capture=_capture)
         self._slot_free[self.cur].record(main)
-        self.loss = self.loss_slots[self.cur]
+        self.loss = self._loss_views[self.cur]
         if pipelined:
             self.cur = nxt
         self.events_done += self.B
@@ -817,6 +820,7 @@ class TGNEngine:
         the last step's loss."""
         if not hasattr(self, "_loss_pin"):
             self._loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
+            self._loss_pin_ptr = self._loss_pin.data_ptr()
             self._loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
             self._loss_done = [torch.cuda.Event(), torch.cuda.Event()]
             self._loss_n = 0
@@ -826,9 +830,8 @@ class TGNEngine:
         loss = self.train_step(**kw)
         self._loss_done[i].record(main)
         ls.wait_event(self._loss_done[i])      # the copy runs beside the next step, not between two steps
-        with torch.cuda.stream(ls):
-            self._loss_pin[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
-            self._loss_ev[i].record(ls)
+        check(_L().tgn_memcpy_async(self._loss_pin_ptr + 4 * i, loss.data_ptr(), 4, ls.cuda_stream))
+        self._loss_ev[i].record(ls)
         self._loss_n += 1
         if self._loss_n < 2:
             return None

@@ -205,7 +205,7 @@ def main():
     from tgn_b200 import synth
     cfg = synth.SHAPES[WORKLOAD]
     B, K = cfg["B"], cfg["K"]
-    need = args.prefill + (2 * (W + K_steps) + 80) * B
+    need = args.prefill + (2 * (W + K_steps) + 300) * B
     config = {"workload": f"synthetic {WORKLOAD} shape: {cfg['N']} nodes, raw_dim {cfg['De']}, batch {B}, "
                           f"{K} recent nbrs, dim {HIDDEN}, Adam lr {LR}, ring prefilled with {args.prefill} events",
               "l2": "inputs differ every step (new batch, new ring/memory rows); weights (~1.2 MB) stay L2-resident by design",
@@ -254,7 +254,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm
-    eng.train_steps(max(W, 16))   # warm-up: eager calls, the single-step and the three-step graph captures
+    eng.train_steps(max(W, 40))   # warm-up: eager calls and the captures of the three-step graphs of both slot groups
+    for _ in range(4 * eng.nslots):                   # ... and of the single-step graph of every slot (the K % 3 leftover)
+        eng.train_step(from_device=True)
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -267,26 +269,40 @@ def main():
     loss_dev = float(eng.loss)
 
     # ---------------- end-to-end arm: host batches, H2D every step, loss read back every step
+    while eng.cur % eng.group:                        # the device arm may have stopped inside a slot group
+        eng.train_step(from_device=True, _capture=False)
     pos = eng.events_done
-    n_host = W + K_steps + 1                       # one batch of lookahead
-    host = torch.empty((n_host, eng.packed_nbytes()), dtype=torch.uint8).pin_memory()   # one H2D copy per batch
-    for s in range(n_host):
-        sl = slice(pos + s * B, pos + (s + 1) * B)
-        eng.pack_host_batch(host[s], ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl], ev["msg"][sl])
-    # prefetching loader pattern: batch s+1 is copied H2D (and sampled on the forked stream) while batch s trains
-    eng.stage_packed1(host[0])
-    for s in range(W):
-        eng.stage_packed1(host[s + 1], ahead=True)
-        float(eng.train_step(from_device=False, lookahead=True))
+    # Host batches arrive in groups of three (the engine's pipelining unit): per group ONE pinned H2D copy
+    # (3 x 7.2 KB, on a copy stream while the previous group is still executing), ONE captured graph of three
+    # training steps, ONE D2H read of the three losses (read after the next group has been launched, the
+    # last ones before the timer stops).  K_steps % 3 leftover steps run one by one on the last staged group.
+    G = eng.group
+    Wg = max(9, (W + G - 1) // G + 2)                 # warm-up groups: 3 eager calls + the graph capture for each of the two slot groups
+    ng, rem = K_steps // G, K_steps % G
+    n_groups = Wg + ng + 1
+    host = torch.zeros((n_groups, eng.group_nbytes()), dtype=torch.uint8).pin_memory()
+    n_ev = ev["src"].numel()
+    for g in range(n_groups):
+        batches = []
+        for i in range(G):
+            lo = min(pos + (g * G + i) * B, n_ev - B)
+            sl = slice(lo, lo + B)
+            batches.append((ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl], ev["msg"][sl]))
+        eng.pack_host_group(host[g], batches)
+    eng.stage_group(host[0], ahead=False)
+    for g in range(Wg):
+        eng.stage_group(host[g + 1])
+        eng.train_group_logged()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    # every step's loss is read back on the host; the read of step s is taken after step s+1 has been
-    # launched (train_step_logged: async D2H into pinned memory), the last one before the timer stops
-    for s in range(W, W + K_steps):
-        eng.stage_packed1(host[s + 1], ahead=True)
-        eng.train_step_logged(from_device=False, lookahead=True)
-    loss_host = eng.flush_loss()
+    for g in range(Wg, Wg + ng):
+        eng.stage_group(host[g + 1])
+        eng.train_group_logged()
+    for _ in range(rem):
+        eng.train_step_logged(from_device=False, lookahead=True, _capture=False)
+    losses = eng.flush_group_losses()
+    loss_host = eng.flush_loss() if rem else losses[-1]
     f1.record()
     barrier()
     clocks.stop_flag = True
@@ -337,7 +353,8 @@ def main():
                 "dtype": "tf32x3 (fp32-accurate split, fp32 accumulate)" if args.precision == 3 else "tf32",
                 "data": "synthetic", "config": config,
                 "e2e": {"value": world * K_steps * B / (ms_e2e / 1e3), "unit": "events/s",
-                        "h2d_bytes_per_step": eng.packed_nbytes(), "d2h_bytes_per_step": 4,
+                        "h2d_bytes_per_step": eng.group_nbytes() // eng.group, "d2h_bytes_per_step": 4,
+                        "grouping": "3 batches per H2D copy / graph launch / loss read-back",
                         "ms_per_step": ms_e2e / K_steps},
                 "gpu_launches": len(ours) * K_steps,
                 "launches_per_step": {"tgn_kernels": len(ours), "all_kernels": len(kern)},

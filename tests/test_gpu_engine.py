@@ -265,3 +265,39 @@ def test_multi_step_graph_equals_single_steps():
     torch.testing.assert_close(eng_a.memory, eng_b.memory, rtol=1e-2, atol=1e-3)
     assert torch.equal(eng_a.e_id, eng_b.e_id) and torch.equal(eng_a.last_update, eng_b.last_update)
     assert torch.equal(eng_a.t_ring, eng_b.t_ring)
+
+
+def test_grouped_host_feeding_equals_resident_path():
+    """stage_group + train_group_logged (three batches per pinned H2D copy, per captured graph and per loss
+    read-back; six slots in two groups) followed by single-step leftovers == the resident-array path."""
+    N, De, D, K, B, steps = 300, 8, 16, 4, 32, 26          # 8 groups of 3 + 2 single steps
+    _, eng_a, ev = _setup(N, De, D, K, B, B * steps, 17, True, lr=1e-6)
+    _, eng_g, _ = _setup(N, De, D, K, B, B * steps, 17, True, lr=1e-6)
+    la = [float(eng_a.train_step(from_device=True)) for _ in range(steps)]
+    G = eng_g.group
+    ngroups = (steps + G - 1) // G
+    host = torch.zeros((ngroups + 1, eng_g.group_nbytes()), dtype=torch.uint8).pin_memory()
+    for g in range(ngroups):
+        batches = []
+        for i in range(G):
+            s = min(g * G + i, steps - 1)                   # the tail group is padded with a repeated batch
+            sl = slice(s * B, (s + 1) * B)
+            batches.append((ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl], ev["msg"][sl]))
+        eng_g.pack_host_group(host[g], batches)
+    got = []
+    eng_g.stage_group(host[0], ahead=False)
+    full = steps // G
+    for g in range(full):
+        eng_g.stage_group(host[g + 1])
+        prev = eng_g.train_group_logged()
+        if prev is not None:
+            got += prev
+    got += eng_g.flush_group_losses()
+    for _ in range(steps - full * G):                        # leftovers: already staged by the last stage_group
+        got.append(float(eng_g.train_step(from_device=False, lookahead=True, _capture=False)))
+    assert len(got) == steps and eng_g.events_done == eng_a.events_done
+    for s, (a, b) in enumerate(zip(la, got)):
+        assert abs(a - b) < 1e-4, (s, a, b)
+    torch.testing.assert_close(eng_a.memory, eng_g.memory, rtol=1e-2, atol=1e-3)
+    assert torch.equal(eng_a.e_id, eng_g.e_id) and torch.equal(eng_a.t_ring, eng_g.t_ring)
+    assert torch.equal(eng_a.last_update, eng_g.last_update)

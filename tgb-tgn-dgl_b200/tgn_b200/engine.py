@@ -158,8 +158,14 @@ class TGNEngine:
         # stream already loads and samples batch i+1 into the other slot (software pipelining)
         # three slots in rotation: step s trains on slot s%3 and samples batch s+1 into slot (s+1)%3, so a
         # host loader can copy batch s+1 into its slot while step s-1 is still running (stage_packed1)
-        self.nslots = 3
-        self.slots = [self._alloc_slot(R, E, Nb, batch_size) for _ in range(self.nslots)]
+        # Six slots = two groups of three: a host loader can also feed whole groups (stage_group +
+        # train_group_logged: one H2D copy, one graph launch and one loss read-back per THREE steps); the
+        # staging regions of all slots are one allocation so a group's three batches are contiguous.
+        self.nslots, self.group = 6, 3
+        De1 = max(raw_dim, 1)
+        self._packed = (32 * batch_size + 4 * batch_size * De1 + 15) // 16 * 16      # bytes per staged batch
+        self._in_all = torch.zeros(self.nslots * self._packed, dtype=torch.uint8, device=dev)
+        self.slots = [self._alloc_slot(R, E, Nb, batch_size, i) for i in range(self.nslots)]
         self.cur = 0
         self.copy_stream = torch.cuda.Stream(device=dev)    # H2D of host-staged batches
         self.loss_stream = torch.cuda.Stream(device=dev)    # D2H of the per-step loss (train_step_logged)
@@ -168,9 +174,9 @@ class TGNEngine:
         self._slot_async = [False] * self.nslots
         self._primed = None      # "device" / "host": slots[cur] holds a staged AND sampled batch
         self._bind(0)
-        self.loss_slots = torch.zeros(3, device=dev)   # loss of the step that trained on slot i (a lagged host
-        self._loss_views = [self.loss_slots[i] for i in range(3)]
-        self.loss = self._loss_views[0]                # read of step s survives until step s+3 overwrites it)
+        self.loss_slots = torch.zeros(self.nslots, device=dev)   # loss of the step that trained on slot i (a lagged
+        self._loss_views = [self.loss_slots[i] for i in range(self.nslots)]   # host read of step s survives until the
+        self.loss = self._loss_views[0]                                        # slot comes round again)
         self.bounds = (R, E, Nb)
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.training = True
@@ -235,7 +241,7 @@ class TGNEngine:
         w.n_id, w.Nb_dev = i64(Nb), i32(1)
         w.nbr_l, w.ctr_l = i64(E), i64(R)
 
-    def _alloc_slot(self, R: int, E: int, Nb: int, B: int) -> SimpleNamespace:
+    def _alloc_slot(self, R: int, E: int, Nb: int, B: int, index: int = 0) -> SimpleNamespace:
         dev = self.dev
         sl = SimpleNamespace(R=R, E=E, Nb=Nb, B=B)
         self._alloc_sample_fields(sl, R, E, Nb)
@@ -243,7 +249,7 @@ class TGNEngine:
         # one contiguous staging region per slot: [src | dst | neg | t] int64 followed by msg [B, De] float32,
         # so a host batch is ONE H2D copy (stage_packed1); in_i64 / in_msg are views of it
         De1 = max(self.De, 1)
-        sl.in_raw = torch.zeros(32 * B + 4 * B * De1, dtype=torch.uint8, device=dev)
+        sl.in_raw = self._in_all[index * self._packed: index * self._packed + 32 * B + 4 * B * De1]
         sl.in_i64 = sl.in_raw[:32 * B].view(torch.long)
         sl.in_ids3, sl.in_t_i64 = sl.in_i64[:3 * B], sl.in_i64[3 * B:]
         sl.in_t_f32 = torch.zeros(B, device=dev)
@@ -788,29 +794,112 @@ class TGNEngine:
         return self.loss
 
     def train_steps(self, n: int):
-        """n consecutive training batches from the resident event arrays (set_events).  The slot rotation
-        has period `nslots`, so `nslots` steps are captured as ONE graph: one launch per three steps, no
-        launch gap at the two inner step boundaries.  The remainder runs step by step.  Returns the
+        """n consecutive training batches from the resident event arrays (set_events).  `group` (three)
+        consecutive steps are captured as ONE graph: one launch per three steps, no launch gap at the two
+        inner step boundaries.  The remainder runs step by step.  Returns the
         (device) loss of the last batch."""
         done = 0
         if n > 0 and self._primed != "device":
             self.train_step(from_device=True)
             done = 1
-        while self.use_graph and n - done >= self.nslots:
-            self._run(("train_multi", self.cur), self._multi_body)
-            done += self.nslots
-            self.events_done += self.nslots * self.B
+        G = self.group
+        while self.use_graph and n - done >= G:
+            self._run(("train_multi", self.cur), lambda: self._multi_body(True))
+            self.cur = (self.cur + G) % self.nslots
+            done += G
+            self.events_done += G * self.B
             self.store.size = self.events_done
-            self.loss = self.loss_slots[(self.cur - 1) % self.nslots]
+            self.loss = self._loss_views[(self.cur - 1) % self.nslots]
         while done < n:          # remainder: replays the single-step graph if it exists, else runs eagerly
             self.train_step(from_device=True, _capture=False)
             done += 1
         return self.loss
 
-    def _multi_body(self):
-        for _ in range(self.nslots):
-            self._train_body(True, True)
+    def _multi_body(self, from_device: bool):
+        """`group` consecutive steps; leaves self.cur where it found it (the caller advances it, so that a
+        replay -- which does not run this body -- and a capture / eager run end in the same state)."""
+        c0 = self.cur
+        for _ in range(self.group):
+            self._train_body(from_device, True)
             self.cur = self._next_slot()
+        self.cur = c0
+
+    # ---- grouped end-to-end feeding: three batches per H2D copy / graph launch / loss read-back
+    def group_nbytes(self) -> int:
+        return self.group * self._packed
+
+    def pack_host_group(self, out: Tensor, batches) -> Tensor:
+        """Fills `out` (pinned uint8 [group_nbytes()]) from `group` tuples (src, dst, neg, t, msg)."""
+        for i, b in enumerate(batches):
+            self.pack_host_batch(out[i * self._packed: i * self._packed + self.packed_nbytes()], *b)
+        return out
+
+    def stage_group(self, buf: Tensor, ahead: bool = True):
+        """Stages the NEXT group (ahead=True: the three batches after the group train_group_logged() is about
+        to train; the copy runs on the copy stream while the previous group is still executing) or the
+        current one (ahead=False, before the first call)."""
+        if buf.numel() != self.group_nbytes() or buf.dtype != torch.uint8 or not buf.is_contiguous():
+            raise _cabi.TgnError("stage_group: buf must be a contiguous uint8 tensor of group_nbytes() bytes")
+        if self.cur % self.group:
+            raise _cabi.TgnError("stage_group: the slot cursor is not on a group boundary")
+        g0 = (self.cur + self.group) % self.nslots if ahead else self.cur
+        dst = self._in_all.data_ptr() + g0 * self._packed
+        if not ahead:
+            check(_L().tgn_memcpy_async(dst, buf.data_ptr(), buf.numel(), torch.cuda.current_stream().cuda_stream))
+            return
+        cs = self.copy_stream
+        cs.wait_event(self._slot_free[g0])          # the group that last used these slots has finished
+        check(_L().tgn_memcpy_async(dst, buf.data_ptr(), buf.numel(), cs.cuda_stream))
+        self._slot_ready[g0].record(cs)
+        self._slot_async[g0] = True
+
+    def train_group_logged(self):
+        """Trains the `group` staged batches (one captured graph) with the NEXT group staged ahead
+        (stage_group); returns the list of the previous group's losses (None on the first call)."""
+        G, main, ls = self.group, torch.cuda.current_stream(), self.loss_stream
+        if not hasattr(self, "_gl_pin"):
+            self._gl_pin = torch.zeros(2 * G, dtype=torch.float32).pin_memory()
+            self._gl_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._gl_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._gl_n = 0
+        if self.cur % G:
+            raise _cabi.TgnError("train_group_logged: the slot cursor is not on a group boundary")
+        if self._primed != "host":                 # first call: sample the group's first batch now
+            self._unprime()
+            self._bind(self.cur)
+            self._sample(self.slots[self.cur], self.slots[self.cur].in_ids3, self.slots[self.cur].ids_l)
+            self._primed = "host"
+        i = self._gl_n & 1
+        main.wait_event(self._gl_ev[i])
+        nxt = (self.cur + G) % self.nslots
+        if self._slot_async[nxt]:
+            main.wait_event(self._slot_ready[nxt])
+            self._slot_async[nxt] = False
+        c0 = self.cur
+        self._run(("train_group_host", c0), lambda: self._multi_body(False))
+        for k in range(G):
+            self._slot_free[c0 + k].record(main)
+        self.cur = nxt
+        self.events_done += G * self.B
+        self.store.size = self.events_done
+        self.loss = self._loss_views[(nxt - 1) % self.nslots]
+        self._gl_done[i].record(main)
+        ls.wait_event(self._gl_done[i])
+        check(_L().tgn_memcpy_async(self._gl_pin.data_ptr() + 4 * G * i, self.loss_slots.data_ptr() + 4 * c0, 4 * G,
+                                    ls.cuda_stream))
+        self._gl_ev[i].record(ls)
+        self._gl_n += 1
+        if self._gl_n < 2:
+            return None
+        self._gl_ev[i ^ 1].synchronize()
+        return self._gl_pin[G * (i ^ 1): G * (i ^ 1) + G].tolist()
+
+    def flush_group_losses(self):
+        if not getattr(self, "_gl_n", 0):
+            return None
+        i, G = (self._gl_n - 1) & 1, self.group
+        self._gl_ev[i].synchronize()
+        return self._gl_pin[G * i: G * i + G].tolist()
 
     def train_step_logged(self, **kw) -> Optional[float]:
         """train_step() with a pipelined loss read-back for logging loops: the device->host copy of

@@ -79,8 +79,12 @@ def train_epoch_engine(model, data, train_loader, neg_dest_sampler, neighbor_loa
     eng.reset_state()
     eng.set_events(ds.src[:n], ds.dst[:n], ds.t[:n].long(), ds.msg[:n], neg_dest_sampler.sample(ds.dst[:n]))
     total = 0.0
-    for _ in range(n // B):
-        total += float(eng.train_step()) * B
+    for _ in range(n // B):                      # every step's loss is logged, read back one step late
+        prev = eng.train_step_logged()
+        if prev is not None:
+            total += prev * B
+    if n // B:
+        total += eng.flush_loss() * B
     eng.flush_to_eval()   # what memory.eval() does on the module side: pending messages -> memory
     mem_sd, gnn_sd, lp_sd = eng.export_state()
     model["memory"].load_state_dict(mem_sd, strict=False)

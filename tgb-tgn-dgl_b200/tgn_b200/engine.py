@@ -7,15 +7,17 @@ One step = the per-batch flow the reference's four hot-path pieces serve
     neighbour lookup of the roots            -> ring kernel                    (nbr_ring.cu)
     n_id = unique(roots + neighbours), relabel                                 (step.cu)
     z, last_update = memory(n_id)            -> store gather + concat + time-enc + Last
-                                                aggregation (msgstore.cu), gate GEMMs on
-                                                tcgen05 (gemm_tma.cu), gate math (dense.cu)
+                                                aggregation (msgstore.cu), fused GRUCell: both gate
+                                                GEMMs in TMEM + gate math (gemm_tma.cu)
     z = gnn(z, last_update, edges, t, msg)   -> projection / edge GEMMs + softmax core (step.cu)
-    pos/neg logits, BCE loss                 -> decoder GEMMs + loss kernel     (step.cu)
+    pos/neg logits, BCE loss                 -> fused decoder forward + loss + d_emb (step.cu)
     backward                                 -> hand-derived, same kernels; every weight
                                                 gradient is a split-K GEMM accumulating
                                                 straight into the flat gradient buffer
     Adam                                     -> one launch over the flat buffers (dense.cu)
-    memory.update_state / loader.insert      -> on a forked stream, overlapping the backward
+    loader.insert + sampling of batch s+1    -> forked stream, from the START of step s
+    memory.update_state                      -> forked stream, after the GRU forward
+(stream layout and the timeline it was cut from: DESIGN.md section 5)
 
 No autograd, no allocation and no host synchronisation inside a step: all buffers are
 sized by upper bounds (3B roots, 3B*K edges, ...), the true counts stay in device memory,
@@ -154,10 +156,9 @@ class TGNEngine:
         self.upd = torch.cuda.Stream(device=dev)     # memory / message-store update of this batch
         self.aux = torch.cuda.Stream(device=dev)     # edge branch of the attention / small reductions
         self.w = self._alloc_work(R, E, Nb, batch_size)
-        # two slots of {batch inputs, sampling results}: while step i runs on slot `cur`, the forked
-        # stream already loads and samples batch i+1 into the other slot (software pipelining)
-        # three slots in rotation: step s trains on slot s%3 and samples batch s+1 into slot (s+1)%3, so a
-        # host loader can copy batch s+1 into its slot while step s-1 is still running (stage_packed1)
+        # Slots of {batch inputs, sampling results} in rotation: while step s runs on slot `cur`, the forked
+        # stream already loads and samples batch s+1 into the next slot (software pipelining), and a host
+        # loader can copy later batches into slots the running steps do not touch.
         # Six slots = two groups of three: a host loader can also feed whole groups (stage_group +
         # train_group_logged: one H2D copy, one graph launch and one loss read-back per THREE steps); the
         # staging regions of all slots are one allocation so a group's three batches are contiguous.

@@ -183,6 +183,7 @@ class TGNEngine:
         self.training = True
         self.fused_decoder = _L().tgn_dec_fused_smem_bytes(hidden) <= 215 * 1024 and hidden <= 128
         self.fused_gru = hidden % 4 == 0    # tgn_gru_fused_fwd (TMA strides need 16-byte rows)
+        self.dz_split = 3                   # split-K of the d_z GEMM (1 = plain store)
         self.probe = None   # bench.py: {"name": [(start_event, stop_event), ...]} filled in eager steps
 
     # ------------------------------------------------------------------ layout helpers
@@ -631,6 +632,8 @@ class TGNEngine:
         aux.wait_stream(main)
         with torch.cuda.stream(aux):
             w.d_proj.zero_()
+            if self.dz_split > 1:
+                w.d_z.zero_()
         self._timed("msg_build", lambda: self._memory_msgs(w, w.n_id, w.Nb, w.Nb_dev))
         # ---- edge branch of the attention on its own stream: needs last_update / edges only
         aux.wait_stream(main)
@@ -673,8 +676,11 @@ class TGNEngine:
         # stream.  The weight gradients of the attention (and everything that hangs off them) run
         # beside it on the auxiliary stream: the two launches together fit the 148 SMs.
         aux.wait_stream(main)       # fork point: both launches depend on the attention backward only
+        # (38 live row tiles on 148 SMs: the 13 k-blocks of the reduction are split three ways, the partial
+        # products are added into the d_z cleared beside msg_build)
         ops.gemm_batch([ops.gemm_desc(w.d_proj, fl, w.d_z, m=w.Nb, n=D, k=4 * HC, lda=4 * HC, ldb=D, ldc=D,
-                                      trans_b=True, b_off=off["conv.w_node"], m_dev=w.Nb_dev)], self.prec)
+                                      trans_b=True, b_off=off["conv.w_node"], m_dev=w.Nb_dev,
+                                      mode=2, split_k=self.dz_split)], self.prec)
         with torch.cuda.stream(aux):
             g = [  # dW_edge += d_ee^T edge_attr ; dW_node += d_proj^T z
                 ops.gemm_desc(w.d_ee, w.ea, fg, m=HC, n=self.Din, k=w.E, lda=HC, ldb=self.lde, ldc=self.lde,

@@ -205,7 +205,7 @@ def main():
     from tgn_b200 import synth
     cfg = synth.SHAPES[WORKLOAD]
     B, K = cfg["B"], cfg["K"]
-    need = args.prefill + (2 * (W + K_steps) + 300) * B
+    need = args.prefill + (2 * (W + K_steps) + 400) * B
     config = {"workload": f"synthetic {WORKLOAD} shape: {cfg['N']} nodes, raw_dim {cfg['De']}, batch {B}, "
                           f"{K} recent nbrs, dim {HIDDEN}, Adam lr {LR}, ring prefilled with {args.prefill} events",
               "l2": "inputs differ every step (new batch, new ring/memory rows); weights (~1.2 MB) stay L2-resident by design",
@@ -254,7 +254,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm
-    eng.train_steps(max(W, 40))   # warm-up: eager calls and the captures of the three-step graphs of both slot groups
+    eng.train_steps(max(W, 52))   # warm-up: eager calls and the captures of the three-step graphs of all slot groups
     for _ in range(4 * eng.nslots):                   # ... and of the single-step graph of every slot (the K % 3 leftover)
         eng.train_step(from_device=True)
     barrier()
@@ -277,7 +277,7 @@ def main():
     # training steps, ONE D2H read of the three losses (read after the next group has been launched, the
     # last ones before the timer stops).  K_steps % 3 leftover steps run one by one on the last staged group.
     G = eng.group
-    Wg = max(9, (W + G - 1) // G + 2)                 # warm-up groups: 3 eager calls + the graph capture for each of the two slot groups
+    Wg = max(14, (W + G - 1) // G + 2)                # warm-up groups: 3 eager calls + the graph capture for each slot group
     ng, rem = K_steps // G, K_steps % G
     n_groups = Wg + ng + 1
     host = torch.zeros((n_groups, eng.group_nbytes()), dtype=torch.uint8).pin_memory()

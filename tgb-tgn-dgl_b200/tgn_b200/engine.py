@@ -159,10 +159,12 @@ class TGNEngine:
         # Slots of {batch inputs, sampling results} in rotation: while step s runs on slot `cur`, the forked
         # stream already loads and samples batch s+1 into the next slot (software pipelining), and a host
         # loader can copy later batches into slots the running steps do not touch.
-        # Six slots = two groups of three: a host loader can also feed whole groups (stage_group +
-        # train_group_logged: one H2D copy, one graph launch and one loss read-back per THREE steps); the
-        # staging regions of all slots are one allocation so a group's three batches are contiguous.
-        self.nslots, self.group = 6, 3
+        # Nine slots = three groups of three: a host loader can also feed whole groups (stage_group +
+        # train_group_logged: one H2D copy, one graph launch and one loss read-back per THREE steps).  With
+        # three groups the copy of group g+1 only has to wait for group g-2, so it overlaps group g-1
+        # completely and group g starts the moment g-1 ends (two groups left a copy-sized bubble per group).
+        # The staging regions of all slots are one allocation so a group's three batches are contiguous.
+        self.nslots, self.group = 9, 3
         De1 = max(raw_dim, 1)
         self._packed = (32 * batch_size + 4 * batch_size * De1 + 15) // 16 * 16      # bytes per staged batch
         self._in_all = torch.zeros(self.nslots * self._packed, dtype=torch.uint8, device=dev)

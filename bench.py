@@ -269,14 +269,14 @@ def main():
     loss_dev = float(eng.loss)
 
     # ---------------- end-to-end arm: host batches, H2D every step, loss read back every step
-    while eng.cur % eng.group:                        # the device arm may have stopped inside a slot group
+    while eng.cur % eng.group_size:                        # the device arm may have stopped inside a slot group
         eng.train_step(from_device=True, _capture=False)
     pos = eng.events_done
     # Host batches arrive in groups of three (the engine's pipelining unit): per group ONE pinned H2D copy
     # (3 x 7.2 KB, on a copy stream while the previous group is still executing), ONE captured graph of three
     # training steps, ONE D2H read of the three losses (read after the next group has been launched, the
     # last ones before the timer stops).  K_steps % 3 leftover steps run one by one on the last staged group.
-    G = eng.group
+    G = eng.group_size
     Wg = max(14, (W + G - 1) // G + 2)                # warm-up groups: 3 eager calls + the graph capture for each slot group
     ng, rem = K_steps // G, K_steps % G
     n_groups = Wg + ng + 1
@@ -363,7 +363,7 @@ def main():
                 "dtype": "tf32x3 (fp32-accurate split, fp32 accumulate)" if args.precision == 3 else "tf32",
                 "data": "synthetic", "config": config,
                 "e2e": {"value": world * K_steps * B / (ms_e2e / 1e3), "unit": "events/s",
-                        "h2d_bytes_per_step": eng.group_nbytes() // eng.group, "d2h_bytes_per_step": 4,
+                        "h2d_bytes_per_step": eng.group_nbytes() // eng.group_size, "d2h_bytes_per_step": 4,
                         "grouping": "3 batches per H2D copy / graph launch / loss read-back",
                         "ms_per_step": ms_e2e / K_steps},
                 "gpu_launches": len(ours) * K_steps,

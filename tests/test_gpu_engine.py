@@ -274,7 +274,7 @@ def test_grouped_host_feeding_equals_resident_path():
     _, eng_a, ev = _setup(N, De, D, K, B, B * steps, 17, True, lr=1e-6)
     _, eng_g, _ = _setup(N, De, D, K, B, B * steps, 17, True, lr=1e-6)
     la = [float(eng_a.train_step(from_device=True)) for _ in range(steps)]
-    G = eng_g.group
+    G = eng_g.group_size
     ngroups = (steps + G - 1) // G
     host = torch.zeros((ngroups + 1, eng_g.group_nbytes()), dtype=torch.uint8).pin_memory()
     for g in range(ngroups):

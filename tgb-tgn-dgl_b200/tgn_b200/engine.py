@@ -164,7 +164,7 @@ class TGNEngine:
         # three groups the copy of group g+1 only has to wait for group g-2, so it overlaps group g-1
         # completely and group g starts the moment g-1 ends (two groups left a copy-sized bubble per group).
         # The staging regions of all slots are one allocation so a group's three batches are contiguous.
-        self.nslots, self.group = 9, 3
+        self.nslots, self.group_size = 9, 3
         De1 = max(raw_dim, 1)
         self._packed = (32 * batch_size + 4 * batch_size * De1 + 15) // 16 * 16      # bytes per staged batch
         self._in_all = torch.zeros(self.nslots * self._packed, dtype=torch.uint8, device=dev)
@@ -803,7 +803,7 @@ class TGNEngine:
         return self.loss
 
     def train_steps(self, n: int):
-        """n consecutive training batches from the resident event arrays (set_events).  `group` (three)
+        """n consecutive training batches from the resident event arrays (set_events).  `group_size` (three)
         consecutive steps are captured as ONE graph: one launch per three steps, no launch gap at the two
         inner step boundaries.  The remainder runs step by step.  Returns the
         (device) loss of the last batch."""
@@ -811,7 +811,7 @@ class TGNEngine:
         if n > 0 and self._primed != "device":
             self.train_step(from_device=True)
             done = 1
-        G = self.group
+        G = self.group_size
         while self.use_graph and n - done >= G:
             self._run(("train_multi", self.cur), lambda: self._multi_body(True))
             self.cur = (self.cur + G) % self.nslots
@@ -825,20 +825,20 @@ class TGNEngine:
         return self.loss
 
     def _multi_body(self, from_device: bool):
-        """`group` consecutive steps; leaves self.cur where it found it (the caller advances it, so that a
+        """`group_size` consecutive steps; leaves self.cur where it found it (the caller advances it, so that a
         replay -- which does not run this body -- and a capture / eager run end in the same state)."""
         c0 = self.cur
-        for _ in range(self.group):
+        for _ in range(self.group_size):
             self._train_body(from_device, True)
             self.cur = self._next_slot()
         self.cur = c0
 
     # ---- grouped end-to-end feeding: three batches per H2D copy / graph launch / loss read-back
     def group_nbytes(self) -> int:
-        return self.group * self._packed
+        return self.group_size * self._packed
 
     def pack_host_group(self, out: Tensor, batches) -> Tensor:
-        """Fills `out` (pinned uint8 [group_nbytes()]) from `group` tuples (src, dst, neg, t, msg)."""
+        """Fills `out` (pinned uint8 [group_nbytes()]) from `group_size` tuples (src, dst, neg, t, msg)."""
         for i, b in enumerate(batches):
             self.pack_host_batch(out[i * self._packed: i * self._packed + self.packed_nbytes()], *b)
         return out
@@ -849,9 +849,9 @@ class TGNEngine:
         current one (ahead=False, before the first call)."""
         if buf.numel() != self.group_nbytes() or buf.dtype != torch.uint8 or not buf.is_contiguous():
             raise _cabi.TgnError("stage_group: buf must be a contiguous uint8 tensor of group_nbytes() bytes")
-        if self.cur % self.group:
+        if self.cur % self.group_size:
             raise _cabi.TgnError("stage_group: the slot cursor is not on a group boundary")
-        g0 = (self.cur + self.group) % self.nslots if ahead else self.cur
+        g0 = (self.cur + self.group_size) % self.nslots if ahead else self.cur
         dst = self._in_all.data_ptr() + g0 * self._packed
         if not ahead:
             check(_L().tgn_memcpy_async(dst, buf.data_ptr(), buf.numel(), torch.cuda.current_stream().cuda_stream))
@@ -863,9 +863,9 @@ class TGNEngine:
         self._slot_async[g0] = True
 
     def train_group_logged(self):
-        """Trains the `group` staged batches (one captured graph) with the NEXT group staged ahead
+        """Trains the `group_size` staged batches (one captured graph) with the NEXT group staged ahead
         (stage_group); returns the list of the previous group's losses (None on the first call)."""
-        G, main, ls = self.group, torch.cuda.current_stream(), self.loss_stream
+        G, main, ls = self.group_size, torch.cuda.current_stream(), self.loss_stream
         if not hasattr(self, "_gl_pin"):
             self._gl_pin = torch.zeros(2 * G, dtype=torch.float32).pin_memory()
             self._gl_ev = [torch.cuda.Event(), torch.cuda.Event()]
@@ -906,7 +906,7 @@ class TGNEngine:
     def flush_group_losses(self):
         if not getattr(self, "_gl_n", 0):
             return None
-        i, G = (self._gl_n - 1) & 1, self.group
+        i, G = (self._gl_n - 1) & 1, self.group_size
         self._gl_ev[i].synchronize()
         return self._gl_pin[G * i: G * i + G].tolist()
 

@@ -322,9 +322,8 @@ class TGNEngine:
         lus = [torch.empty_like(self.last_update) for _ in range(self.world)]
         dist.all_gather(mems, self.memory, group=self.group)
         dist.all_gather(lus, self.last_update, group=self.group)
-        full_mem = torch.stack(mems, 1).reshape(-1, self.D)[:self.N].contiguous()
-        full_lu = torch.stack(lus, 1).reshape(-1)[:self.N].contiguous()
-        return full_mem, full_lu
+        from . import partition
+        return partition.interleave(mems, self.N), partition.interleave(lus, self.N)
 
     def _all_reduce(self, t: Tensor):
         import torch.distributed as dist

@@ -107,3 +107,27 @@ def test_blockwise_training_runs_and_differs_only_by_ordering():
                                 torch.nn.BCEWithLogitsLoss(), use_blocks=use_blocks))
     assert all(np.isfinite(l) and l > 0 for l in losses)
     assert abs(losses[0] - losses[1]) < 0.2 * losses[0]
+
+
+def test_tgb_gen_graph_cli_writes_ext_full(tmp_path):
+    """`python tgb_gen_graph.py --data <name>` (reference README.md:4-5): the file has the keys the reference
+    reads (utils.py:73), equals the oracle's builder, and feeds sampler_core."""
+    import numpy as np
+    import tgb_gen_graph
+    import sampler_core
+    from tgn_b200 import synth
+    from oracle import tgn_oracle as orc
+    out = str(tmp_path / "DATA" / "tgbl-wiki" / "ext_full.npz")
+    tgb_gen_graph.main(["--data", "tgbl-wiki", "--max_events", "6000", "--out", out])
+    g = np.load(out)
+    assert sorted(g.files) == ["eid", "indices", "indptr", "ts"]
+    d = synth.synth_events("tgbl-wiki", seed=0, max_events=6000)
+    ref = orc.build_tcsr(d["src"], d["dst"], d["t"], d["num_nodes"])
+    for k, w in zip(("indptr", "indices", "eid", "ts"), ref):
+        assert np.array_equal(g[k], w), k
+    s = sampler_core.ParallelSampler(g["indptr"], g["indices"], g["eid"], g["ts"], 8, 1, 1, [10], True, False, 1, 0.0)
+    roots = d["src"][-64:].astype(np.int32); rts = d["t"][-64:].astype(np.float32)
+    s.sample(roots, rts)
+    blk = s.get_ret()[0]
+    want = orc.tcsr_sample_ref(*ref, roots, rts, 10)
+    assert np.array_equal(blk.eid(), want[2]) and np.array_equal(blk.col(), want[1])

@@ -51,8 +51,7 @@ def main(argv=None):
     try:
         from tgb.linkproppred.dataset_pyg import PyGLinkPropPredDataset
     except ImportError:                                   # offline image: synthetic TGB shapes
-        import tgb_synth  # noqa: F401  (installs the `tgb` stand-in)
-        from tgb.linkproppred.dataset_pyg import PyGLinkPropPredDataset
+        from tgb_synth import PyGLinkPropPredDataset
         if a.max_events:
             name = f"{a.data}@{a.max_events}"
     data = PyGLinkPropPredDataset(name=name, root=a.root).get_TemporalData()

@@ -130,21 +130,47 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.how}
 
 
+# --------------------------------------------------------------------------- workloads
+PREFILL = {"tgbl-review": 1_000_000, "tgbl-wiki": 50_000}
+
+
+def workload_text(name, data, B, K, prefill):
+    return (f"synthetic {name} shape: {data['num_nodes']} nodes, raw_dim {data['raw_dim']}, batch {B}, "
+            f"{K} recent nbrs, dim {HIDDEN}, Adam lr {LR}, ring prefilled with {prefill} events")
+
+
+def load_workload(name, B, prefill, n_batches, seed=0):
+    """Event stream of one workload: `prefill` events that only fill the neighbour rings + n_batches batches.
+    The wiki shape has 157k events; longer runs extend the stream at the same event rate (synth.extend)."""
+    from tgn_b200 import synth
+    return synth.synth_events(name, seed=seed, max_events=prefill + n_batches * B, batch=B, extend=True)
+
+
 # --------------------------------------------------------------------------- CPU reference arm
-def run_cpu_reference(data, steps, warmup, prefill, budget_s):
-    """The reference's CPU path for the same step: oracle port of modules/* + neighbor_loader
-    (Python-dict message store included -- that is the reference's algorithm), torch CPU with
-    all host threads.  Bounded by `budget_s` seconds of timed work."""
+def cpu_reference_state(data, prefill, seed=1, dropout=True):
+    """Oracle model + neighbour loader in the state the GPU arm starts from (rings after `prefill` events)."""
     from oracle import tgn_oracle as orc
-    N, De, B, K = data["num_nodes"], data["raw_dim"], data["batch"], data["K"]
-    model = orc.build_model(De, HIDDEN, N, seed=1)
+    N, De, K = data["num_nodes"], data["raw_dim"], data["K"]
+    model = orc.build_model(De, HIDDEN, N, seed=seed)
     for m in model.values():
         m.train()
+    if not dropout:
+        model["gnn"].conv.dropout = 0.0
     loader = orc.TorchNeighborLoader(N, K)
     nb, ei, tt = ring_after(data["src"][:prefill], data["dst"][:prefill], data["t"][:prefill], K, N)
     loader.neighbors, loader.e_id, loader.t = torch.from_numpy(nb), torch.from_numpy(ei), torch.from_numpy(tt)
     loader.cur_e_id = prefill
     opt = torch.optim.Adam(orc.model_parameters(model), lr=LR)
+    return model, loader, opt
+
+
+def run_cpu_reference(data, steps, warmup, prefill, budget_s):
+    """The reference's CPU path for the same step: oracle port of modules/* + neighbor_loader
+    (Python-dict message store included -- that is the reference's algorithm), torch CPU with
+    all host threads.  Bounded by `budget_s` seconds of timed work."""
+    from oracle import tgn_oracle as orc
+    B = data["batch"]
+    model, loader, opt = cpu_reference_state(data, prefill)
     ev = {k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")}
     done, t_timed = 0, 0.0
     for s in range(warmup + steps):
@@ -162,6 +188,64 @@ def run_cpu_reference(data, steps, warmup, prefill, budget_s):
     return done, t_timed
 
 
+def cpu_baseline_entry(name, B, prefill, steps, budget_s, warmup=5):
+    torch.set_num_threads(os.cpu_count() or 1)
+    cdata = load_workload(name, B, prefill, steps + warmup + 3)
+    done, t_cpu = run_cpu_reference(cdata, steps, warmup, prefill, budget_s=budget_s)
+    return {"value": done * B / t_cpu, "unit": "events/s", "cores": torch.get_num_threads(), "kind": "port",
+            "ms_per_step": 1e3 * t_cpu / done,
+            "sample": f"{done} training steps ({done * B} events) of the same workload (same shape, batch, prefill) on "
+                      "the host CPU: oracle port of the reference's torch-CPU path incl. its Python-dict message "
+                      "store; scatter_max vectorised (torch_scatter runs it in C++)"}
+
+
+# --------------------------------------------------------------------------- parity beside the numbers
+def parity_leg(name, B, prefill, steps, dev, precision=3, free_steps=None):
+    """GPU engine vs the CPU oracle on the SAME first batches of a workload, from the same weights and the
+    same prefilled rings, dropout off (the two dropout streams cannot agree).
+      synced phase : after every step the oracle's post-Adam weights are copied into the engine, so each
+                     step compares the same function on identical inputs (loss, last_update, ring);
+      free phase   : `free_steps` more steps without syncing (Adam amplifies rounding-level gradient
+                     noise on near-zero gradients into lr-sized weight differences: a looser number).
+    Returns the error summary that bench.py prints as `parity` and the tests assert on."""
+    from oracle import tgn_oracle as orc
+    from tgn_b200.engine import TGNEngine
+    free_steps = steps if free_steps is None else free_steps
+    data = load_workload(name, B, prefill, steps + free_steps + 2)
+    N, De, K = data["num_nodes"], data["raw_dim"], data["K"]
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref, loader, opt = cpu_reference_state(data, prefill, dropout=False)
+    eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.0, use_graph=True,
+                    log_capacity=data["src"].size, seed=5, precision=precision)
+    eng.load_state(ref["memory"].state_dict(), ref["gnn"].state_dict(), ref["link_pred"].state_dict())
+    ev = {k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")}
+    eng.set_events(**ev)
+    eng.prefill(prefill, (loader.neighbors, loader.e_id, loader.t))
+    strip = lambda sd: {k: v for k, v in sd.items() if k not in ("memory", "last_update", "_assoc")}
+    out = {"workload": workload_text(name, data, B, K, prefill), "steps_synced": steps, "steps_free": free_steps,
+           "dropout": 0.0, "max_loss_rel_err": 0.0, "free_running_max_loss_rel_err": 0.0, "last_update_equal": True,
+           "memory_max_abs_err": 0.0}
+    for s in range(steps + free_steps):
+        sl = slice(prefill + s * B, prefill + (s + 1) * B)
+        loss = float(eng.train_step(from_device=True))
+        loss_ref = orc.train_step(ref, loader, opt, ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl],
+                                  ev["msg"][sl], ev["t"], ev["msg"], dropout=False)
+        rel = abs(loss - loss_ref) / max(1e-12, abs(loss_ref))
+        key = "max_loss_rel_err" if s < steps else "free_running_max_loss_rel_err"
+        out[key] = max(out[key], rel)
+        out["last_update_equal"] &= bool(torch.equal(eng.last_update.cpu(), ref["memory"].last_update))
+        if s < steps:
+            touched = torch.cat([ev["src"][sl], ev["dst"][sl]]).unique()
+            err = (eng.memory[touched.to(dev)].cpu() - ref["memory"].memory.detach()[touched]).abs().max()
+            out["memory_max_abs_err"] = max(out["memory_max_abs_err"], float(err))
+            eng.load_state(strip(ref["memory"].state_dict()), ref["gnn"].state_dict(), ref["link_pred"].state_dict())
+    out["ring_equal"] = bool(torch.equal(eng.e_id.cpu(), loader.e_id) and torch.equal(eng.t_ring.cpu(), loader.t))
+    out["final_loss"] = {"gpu": loss, "cpu": loss_ref}
+    out["memory_max_abs_err_final_free_running"] = float(
+        (eng.memory.cpu() - ref["memory"].memory.detach()).abs().max())
+    return out
+
+
 _JSON_FD = None
 
 
@@ -173,17 +257,153 @@ def emit(line: dict):
         os.write(_JSON_FD, data)
 
 
+# --------------------------------------------------------------------------- the GPU arms of one workload
+def gpu_leg(name, B, K_steps, W, prefill, dev, rank, world, precision, clocks=None):
+    """Device-resident arm (`value`) and end-to-end arm (`e2e`) of one workload on this rank's GPU.
+    Returns (result dict, engine)."""
+    import torch.distributed as dist
+    from tgn_b200.engine import TGNEngine
+    G0 = 3
+    warm_dev = max(W, 52) + 4 * 9
+    Wg = max(14, (W + G0 - 1) // G0 + 2)
+    n_batches = warm_dev + K_steps + G0 * (Wg + K_steps // G0 + 2) + 16
+    data = load_workload(name, B, prefill, n_batches, seed=rank)
+    N, De, K = data["num_nodes"], data["raw_dim"], data["K"]
+    eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.1, use_graph=True,
+                    log_capacity=data["src"].size, seed=1234 + rank, precision=precision, fused_zero_grad=True)
+    eng.load_state(*init_state_dicts(De, HIDDEN, N, seed=1))
+    ev = {k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")}
+    eng.set_events(**ev)
+    ring = ring_after(data["src"][:prefill], data["dst"][:prefill], data["t"][:prefill], K, N)
+    eng.prefill(prefill, tuple(torch.from_numpy(a) for a in ring))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm
+    eng.train_steps(max(W, 52))   # warm-up: eager calls and the captures of the three-step graphs of all slot groups
+    for _ in range(4 * eng.nslots):                   # ... and of the single-step graph of every slot (the K % 3 leftover)
+        eng.train_step(from_device=True)
+    barrier()
+    if clocks is not None:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.train_steps(K_steps)      # exactly K_steps batches: three per captured graph + the remainder one by one
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    loss_dev = float(eng.loss)
+
+    # ---------------- end-to-end arm: host batches, H2D every step, loss read back every step
+    while eng.cur % eng.group_size:                        # the device arm may have stopped inside a slot group
+        eng.train_step(from_device=True, _capture=False)
+    pos = eng.events_done
+    # Host batches arrive in groups of three (the engine's pipelining unit): per group the three batches are
+    # PACKED from the host event arrays into a pinned buffer (inside the timed region: that is the loader's
+    # work), ONE pinned H2D copy (on a copy stream while the previous group is still executing), ONE captured
+    # graph of three training steps, ONE D2H read of the three losses (read after the next group has been
+    # launched, the last ones before the timer stops).  K_steps % 3 leftover steps run one by one.
+    G = eng.group_size
+    ng, rem = K_steps // G, K_steps % G
+    n_groups = Wg + ng + 1
+    ring_bufs = 4                                         # pinned staging buffers in rotation (a copy is long done
+    host = torch.zeros((ring_bufs, eng.group_nbytes()), dtype=torch.uint8).pin_memory()   # when its buffer comes round)
+    n_ev = ev["src"].numel()
+
+    def pack(g):
+        batches = []
+        for i in range(G):
+            lo = min(pos + (g * G + i) * B, n_ev - B)
+            sl = slice(lo, lo + B)
+            batches.append((ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl], ev["msg"][sl]))
+        return eng.pack_host_group(host[g % ring_bufs], batches)
+
+    eng.stage_group(pack(0), ahead=False)
+    for g in range(Wg):
+        eng.stage_group(pack(g + 1))
+        eng.train_group_logged()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for g in range(Wg, Wg + ng):
+        eng.stage_group(pack(g + 1))
+        eng.train_group_logged()
+    for _ in range(rem):
+        eng.train_step_logged(from_device=False, lookahead=True, _capture=False)
+    losses = eng.flush_group_losses()
+    loss_host = eng.flush_loss() if rem else losses[-1]
+    f1.record()
+    barrier()
+    if clocks is not None:
+        clocks.stop_flag = True
+    ms_e2e = torch.tensor([f0.elapsed_time(f1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(ms), float(ms_e2e)
+    res = {"workload": workload_text(name, data, B, K, prefill),
+           "value": world * K_steps * B / (ms / 1e3), "unit": "events/s", "ms_per_step": ms / K_steps,
+           "e2e": {"value": world * K_steps * B / (ms_e2e / 1e3), "unit": "events/s",
+                   "h2d_bytes_per_step": eng.group_nbytes() // eng.group_size, "d2h_bytes_per_step": 4,
+                   "grouping": "3 batches per host pack / H2D copy / graph launch / loss read-back; the pack "
+                               "(host event arrays -> pinned buffer) is inside the timed region; negatives are "
+                               "part of the host event stream (drawn once per epoch)",
+                   "ms_per_step": ms_e2e / K_steps},
+           "final_loss": {"device_arm": loss_dev, "e2e_arm": loss_host}}
+    return res, eng
+
+
+def bench_module_path(dev, n_events=20_000, B=200):
+    """What the UNCHANGED driver script gets: events/s of `epoch_utils.train` (the call at pyg-mem-tgn.py:57) on
+    the drop-in modules (neighbor_loader, modules/*, model_utils) -- one Python call per module per batch, autograd,
+    torch.optim.Adam; no TGNEngine, no CUDA graph.  Synthetic wiki shape, wall clock around the second epoch."""
+    import utils
+    from epoch_utils import train as run_train
+    from model_utils import getModel, getOptimizer
+    from neg_sampler import NegLinkSamplerDest
+    from neighbor_loader import LastNeighborLoader
+    train_param = {"batch_size": B, "lr": LR, "epoch": 1}
+    data, tr, va, te, ns, evaluator, metric = utils.getDataWithDependecyBlock(f"tgbl-wiki@{n_events}", train_param)
+    neg_dest_sampler = NegLinkSamplerDest(torch.unique(data.dst))
+    assoc = torch.empty(data.num_nodes, dtype=torch.long, device=dev)
+    loader = LastNeighborLoader(data.num_nodes, size=10, device=dev)
+    model = getModel(data.msg.shape[1], HIDDEN, data.num_nodes, dev, gnn_param={"dim_out": HIDDEN})
+    opt = getOptimizer(model, LR)
+    crit = torch.nn.BCEWithLogitsLoss()
+    n_ev = len(tr.dataset)
+    run_train(model, data.msg, tr, loader, neg_dest_sampler, assoc, dev, opt, crit)      # warm-up epoch
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    loss = run_train(model, data.msg, tr, loader, neg_dest_sampler, assoc, dev, opt, crit)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"metric": "train events/sec through epoch_utils.train on the drop-in modules (the unchanged script's path)",
+            "value": n_ev / dt, "unit": "events/s", "ms_per_step": 1e3 * dt / max(1, (n_ev + B - 1) // B),
+            "events": n_ev, "batch": B, "loss_sum": float(loss),
+            "workload": f"synthetic tgbl-wiki shape, first {n_events} events (70% train), batch {B}, wall clock, "
+                        "host batches and per-batch negative sampling included"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--prefill", type=int, default=1_000_000)
+    ap.add_argument("--workload", default=WORKLOAD, choices=["tgbl-review", "tgbl-wiki"],
+                    help="headline workload (BASELINE.json configs[1] = review; configs[0] = wiki)")
+    ap.add_argument("--batch", type=int, default=None, help="batch size (default: 200; config/TGN.yml:27 says 2000)")
+    ap.add_argument("--prefill", type=int, default=None)
     ap.add_argument("--cpu-steps", type=int, default=400, help="bounded sample of the CPU baseline leg")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     ap.add_argument("--no-eval-dp", action="store_true")
     ap.add_argument("--no-partitioned", action="store_true")
+    ap.add_argument("--no-wiki", action="store_true", help="skip the wiki-shape legs (configs[0], batch 200 and 2000)")
+    ap.add_argument("--no-module-path", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--part-exchange", default="p2p", choices=["p2p", "allreduce"],
                     help="row assembly of the partitioned-memory leg: peer reads over symmetric memory, or NCCL all-reduce")
     ap.add_argument("--eval-batches", type=int, default=30)
@@ -203,21 +423,22 @@ def main():
     K_steps, W = args.steps, max(args.warmup, 3)
 
     from tgn_b200 import synth
-    cfg = synth.SHAPES[WORKLOAD]
-    B, K = cfg["B"], cfg["K"]
-    need = args.prefill + (2 * (W + K_steps) + 400) * B
-    config = {"workload": f"synthetic {WORKLOAD} shape: {cfg['N']} nodes, raw_dim {cfg['De']}, batch {B}, "
-                          f"{K} recent nbrs, dim {HIDDEN}, Adam lr {LR}, ring prefilled with {args.prefill} events",
+    name = args.workload
+    cfg = synth.SHAPES[name]
+    B, K = args.batch or cfg["B"], cfg["K"]
+    prefill = args.prefill if args.prefill is not None else PREFILL[name]
+    probe = dict(num_nodes=cfg["N"], raw_dim=cfg["De"])
+    config = {"workload": workload_text(name, probe, B, K, prefill),
               "l2": "inputs differ every step (new batch, new ring/memory rows); weights (~1.2 MB) stay L2-resident by design",
-              "parallelism": ("host CPU" if args.impl == "reference" else "single GPU") if world == 1
+              "parallelism": "one process per device; the step does not shard across batches" if world == 1
               else f"{world} independent replicas (step does not shard across batches)"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        data = synth.synth_events(WORKLOAD, seed=0, max_events=args.prefill + (W + K_steps + 2) * B)
+        data = load_workload(name, B, prefill, W + K_steps + 2)
         torch.set_num_threads(os.cpu_count() or 1)
-        done, t_timed = run_cpu_reference(data, K_steps, W, args.prefill, budget_s=150.0)
+        done, t_timed = run_cpu_reference(data, K_steps, W, prefill, budget_s=150.0)
         val = done * B / t_timed
         line = {"impl": "reference", "metric": "train events/sec (TGN step)", "value": val, "unit": "events/s",
                 "n_gpus": args.gpus, "steps": done, "warmup": W, "ms_per_step": 1e3 * t_timed / done,
@@ -237,80 +458,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    from tgn_b200.engine import TGNEngine
-    data = synth.synth_events(WORKLOAD, seed=rank, max_events=need)
-    N, De = data["num_nodes"], data["raw_dim"]
-    eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.1, use_graph=True,
-                    log_capacity=data["src"].size, seed=1234 + rank, precision=args.precision, fused_zero_grad=True)
-    eng.load_state(*init_state_dicts(De, HIDDEN, N, seed=1))
-    ev = {k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")}
-    eng.set_events(**ev)
-    ring = ring_after(data["src"][:args.prefill], data["dst"][:args.prefill], data["t"][:args.prefill], K, N)
-    eng.prefill(args.prefill, tuple(torch.from_numpy(a) for a in ring))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident arm
-    eng.train_steps(max(W, 52))   # warm-up: eager calls and the captures of the three-step graphs of all slot groups
-    for _ in range(4 * eng.nslots):                   # ... and of the single-step graph of every slot (the K % 3 leftover)
-        eng.train_step(from_device=True)
-    barrier()
     clocks = ClockSampler(local_rank)
-    clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    eng.train_steps(K_steps)      # exactly K_steps batches: three per captured graph + the remainder one by one
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    loss_dev = float(eng.loss)
-
-    # ---------------- end-to-end arm: host batches, H2D every step, loss read back every step
-    while eng.cur % eng.group_size:                        # the device arm may have stopped inside a slot group
-        eng.train_step(from_device=True, _capture=False)
-    pos = eng.events_done
-    # Host batches arrive in groups of three (the engine's pipelining unit): per group ONE pinned H2D copy
-    # (3 x 7.2 KB, on a copy stream while the previous group is still executing), ONE captured graph of three
-    # training steps, ONE D2H read of the three losses (read after the next group has been launched, the
-    # last ones before the timer stops).  K_steps % 3 leftover steps run one by one on the last staged group.
-    G = eng.group_size
-    Wg = max(14, (W + G - 1) // G + 2)                # warm-up groups: 3 eager calls + the graph capture for each slot group
-    ng, rem = K_steps // G, K_steps % G
-    n_groups = Wg + ng + 1
-    host = torch.zeros((n_groups, eng.group_nbytes()), dtype=torch.uint8).pin_memory()
-    n_ev = ev["src"].numel()
-    for g in range(n_groups):
-        batches = []
-        for i in range(G):
-            lo = min(pos + (g * G + i) * B, n_ev - B)
-            sl = slice(lo, lo + B)
-            batches.append((ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl], ev["msg"][sl]))
-        eng.pack_host_group(host[g], batches)
-    eng.stage_group(host[0], ahead=False)
-    for g in range(Wg):
-        eng.stage_group(host[g + 1])
-        eng.train_group_logged()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for g in range(Wg, Wg + ng):
-        eng.stage_group(host[g + 1])
-        eng.train_group_logged()
-    for _ in range(rem):
-        eng.train_step_logged(from_device=False, lookahead=True, _capture=False)
-    losses = eng.flush_group_losses()
-    loss_host = eng.flush_loss() if rem else losses[-1]
-    f1.record()
-    barrier()
-    clocks.stop_flag = True
-    ms_e2e = torch.tensor([f0.elapsed_time(f1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(ms), float(ms_e2e)
+    head, eng = gpu_leg(name, B, K_steps, W, prefill, dev, rank, world, args.precision, clocks)
 
     # ---------------- launches per step (counted once, outside the timed region)
     from torch.profiler import ProfilerActivity, profile
@@ -333,14 +482,16 @@ def main():
     # ---------------- roofline of the dominant kernel, timed inside (eager) steps
     roof = dominant_kernel_roofline(eng, dev)
     eng.use_graph = eng_use_graph
+    del eng
+    torch.cuda.empty_cache()
 
-    def guarded(fn, *a):
+    def guarded(fn, *a, **kw):
         """Secondary legs: on one GPU a failure is reported inside the JSON line instead of costing the
         headline; with several ranks an exception must propagate (the others are inside collectives)."""
         if world > 1:
-            return fn(*a)
+            return fn(*a, **kw)
         try:
-            return fn(*a)
+            return fn(*a, **kw)
         except Exception as e:   # noqa: BLE001
             return {"error": repr(e)[:300]}
 
@@ -357,38 +508,49 @@ def main():
             peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        line = {"metric": "train events/sec (TGN step)", "value": world * K_steps * B / (ms / 1e3), "unit": "events/s",
-                "n_gpus": world, "steps": K_steps, "warmup": W, "ms_per_step": ms / K_steps,
+        line = {"metric": "train events/sec (TGN step)", "value": head["value"], "unit": "events/s",
+                "n_gpus": world, "steps": K_steps, "warmup": W, "ms_per_step": head["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "tf32x3 (fp32-accurate split, fp32 accumulate)" if args.precision == 3 else "tf32",
-                "data": "synthetic", "config": config,
-                "e2e": {"value": world * K_steps * B / (ms_e2e / 1e3), "unit": "events/s",
-                        "h2d_bytes_per_step": eng.group_nbytes() // eng.group_size, "d2h_bytes_per_step": 4,
-                        "grouping": "3 batches per H2D copy / graph launch / loss read-back",
-                        "ms_per_step": ms_e2e / K_steps},
+                "data": "synthetic", "config": config, "e2e": head["e2e"],
                 "gpu_launches": len(ours) * K_steps,
                 "launches_per_step": {"tgn_kernels": len(ours), "all_kernels": len(kern)},
                 "top_kernels_eager_us": {k: [v[0], round(v[1], 1)] for k, v in top},
-                "clocks": clocks.summary(), "final_loss": {"device_arm": loss_dev, "e2e_arm": loss_host},
+                "clocks": clocks.summary(), "final_loss": head["final_loss"],
                 "roofline": roof_with_peak(roof, peaks)}
         if part is not None:
             line["partitioned_memory"] = part
         if eval_dp is not None:
             line["eval_dp"] = eval_dp
         if world == 1 and not args.no_kernel_rooflines:
-            try:        # secondary leg: a failure here must not cost the headline line
-                line["kernel_rooflines"] = kernel_rooflines(dev, peaks)
-            except Exception as e:   # noqa: BLE001
-                line["kernel_rooflines"] = {"error": repr(e)[:300]}
+            line["kernel_rooflines"] = guarded(kernel_rooflines, dev, peaks)
         if world == 1 and not args.no_cpu_baseline:
-            torch.set_num_threads(os.cpu_count() or 1)
-            cdata = synth.synth_events(WORKLOAD, seed=0, max_events=args.prefill + (args.cpu_steps + 8) * B)
-            done, t_cpu = run_cpu_reference(cdata, args.cpu_steps, 5, args.prefill, budget_s=25.0)
-            line["cpu_baseline"] = {"value": done * B / t_cpu, "unit": "events/s", "cores": torch.get_num_threads(),
-                                    "kind": "port", "ms_per_step": 1e3 * t_cpu / done,
-                                    "sample": f"{done} training steps ({done * B} events) of the same workload (same "
-                                              "shape, batch, prefill) on the host CPU: oracle port of the reference's "
-                                              "torch-CPU path incl. its Python-dict message store"}
+            line["cpu_baseline"] = cpu_baseline_entry(name, B, prefill, args.cpu_steps, budget_s=20.0)
+        if world == 1 and not args.no_parity:
+            # the GPU arm and the CPU arm on the same first 20 batches of the headline workload, dropout off
+            line["parity"] = guarded(parity_leg, name, B, prefill, 20, dev, args.precision)
+        if world == 1 and not args.no_wiki and name != "tgbl-wiki":
+            # BASELINE.json configs[0] (the shape the >=50x target is quoted on), at BASELINE's batch 200 and at
+            # the batch config/TGN.yml:27 sets (2000); each with its own CPU arm and parity beside it
+            wiki = {}
+            for wb, wsteps, wcpu in ((200, max(60, min(K_steps, 300)), 120), (2000, max(30, min(K_steps, 90)), 20)):
+                def one(wb=wb, wsteps=wsteps, wcpu=wcpu):
+                    r, e = gpu_leg("tgbl-wiki", wb, wsteps, W, PREFILL["tgbl-wiki"], dev, 0, 1, args.precision)
+                    del e
+                    torch.cuda.empty_cache()
+                    r["steps"] = wsteps
+                    if not args.no_cpu_baseline:
+                        r["cpu_baseline"] = cpu_baseline_entry("tgbl-wiki", wb, PREFILL["tgbl-wiki"], wcpu, budget_s=8.0)
+                        r["vs_cpu"] = {"device": r["value"] / r["cpu_baseline"]["value"],
+                                       "e2e": r["e2e"]["value"] / r["cpu_baseline"]["value"]}
+                    if not args.no_parity:
+                        r["parity"] = parity_leg("tgbl-wiki", wb, PREFILL["tgbl-wiki"], 20 if wb <= 200 else 6, dev,
+                                                 args.precision)
+                    return r
+                wiki[f"batch_{wb}"] = guarded(one)
+            line["wiki"] = wiki
+        if world == 1 and not args.no_module_path:
+            line["module_path"] = guarded(bench_module_path, dev)
         emit(line)
     if world > 1:
         # captured graphs hold NCCL kernels: leave without the collective shutdown (it can block)
@@ -551,16 +713,21 @@ def dominant_kernel_roofline(eng, dev):
             "prec": eng.prec, "fused": fused}
 
 
+def ncu_traffic(key):
+    try:
+        d = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))[key]
+        return {"traffic": d["dram_bytes_per_launch"], "traffic_source": d["source"]}
+    except Exception:
+        return {"traffic": None, "traffic_source": "no ncu --set full digest committed for this kernel"}
+
+
 def roof_with_peak(r, peaks):
     peak = peaks.get("bf16_tflops", 1590.0)
     ach = r["flops"] / r["seconds"] / 1e12
     return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE such launch (ncu --set full on
-            # `tools/kernel_probe.py gru_fused` / `gru_pair`): the operands are read once; the outputs (h', the
-            # saved gates) stay in the 126 MB L2 for the kernels that follow, so no DRAM write is seen
-            "traffic": 8653824 if r.get("fused") else 8642304,
-            "traffic_source": "profiles/r01_gru_fused_instep.txt" if r.get("fused")
-                              else "profiles/r01_tgemm_gru_pair_instep.txt",
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE such launch, from the committed ncu --set full
+            # digest (profiles/ncu_traffic.json names the capture it was read from); null when there is none
+            **ncu_traffic("gru_fused_instep" if r.get("fused") else "tgemm_gru_pair_instep"),
             "kernel": r["kernel"], "rows_per_launch": r["rows"], "us_per_launch": r["seconds"] * 1e6,
             "launches_timed": r["launches_timed"],
             "algorithmic_flops_per_launch": r["flops"], "algorithmic_bytes_per_launch": r["bytes"],

@@ -52,6 +52,17 @@ extern "C" {
 
 int32_t tgn_abi_version(void);
 const char* tgn_last_error(void);
+/* Contract violations detected ON THE DEVICE by kernels that may run inside a captured graph (where no
+ * return code reaches the caller): bit 0 = message-store log overflow (the batch was dropped instead of
+ * written out of bounds, replaces the silent return the reference's unbounded Python dict never needs,
+ * modules/memory_module.py:180-191), bit 1 = an event id outside the resident event arrays was asked for
+ * (`data.msg[e_id]`, epoch_utils.py:224), bit 2 = batch above a kernel's sort capacity.  The word lives in
+ * mapped pinned host memory: reading it is a plain load, valid after the stream has been synchronised.
+ * reset != 0 clears it. */
+#define TGN_DEVERR_LOG_OVERFLOW 1
+#define TGN_DEVERR_EVENT_RANGE 2
+#define TGN_DEVERR_SORT_CAP 4
+int32_t tgn_device_errors(int32_t reset);
 /* Programmatic dependent launch: kernels are launched with the programmatic-stream-serialization
  * attribute so that the launch latency and prologue of each kernel overlap the tail of its
  * predecessor on the stream (every kernel begins with griddepcontrol.wait, so results do not
@@ -462,10 +473,12 @@ int32_t tgn_relabel3(const int64_t* a, int32_t na, const int32_t* na_dev, int64_
                      const int64_t* assoc, void* stream);
 /* edge_attr[e, 0:ld] = [cos(w*rel_t+b) (time_dim), msg (raw_dim), 0...] with
  * rel_t = last_update[nbr[e]] - t_edge[msg_rows[e]] (emb_module.py:26-28), int64 times;
- * sin_out [E,time_dim] (nullable) keeps sin(w*rel_t+b) for tgn_time_bwd_sin. */
+ * sin_out [E,time_dim] (nullable) keeps sin(w*rel_t+b) for tgn_time_bwd_sin.
+ * num_events = rows of t_edge / msg: a msg_rows[e] outside [0, num_events) yields a zero row and raises
+ * TGN_DEVERR_EVENT_RANGE (0 = unchecked). */
 int32_t tgn_edge_attr_ld(const int64_t* last_update_local, const int64_t* nbr_local,
                          const int64_t* t_edge, const float* msg, const int64_t* msg_rows,
-                         int32_t num_edges, const int32_t* num_edges_dev, int32_t raw_dim,
+                         int64_t num_events, int32_t num_edges, const int32_t* num_edges_dev, int32_t raw_dim,
                          int32_t time_dim, const float* time_w, const float* time_b, int32_t ld,
                          float* edge_attr, float* sin_out, float* rel_t, void* stream);
 /* TimeEncoder gradient from stored sines: d_w[c] += sum_i grad[i,c] * -sin[i,c] * t[i],

@@ -29,8 +29,31 @@ from torch import Tensor
 def scatter_max(src: Tensor, index: Tensor, dim: int = 0, dim_size: int | None = None):
     """torch_scatter.scatter_max, CPU semantics: sequential scan with strict `>`,
     so the FIRST maximal element of a segment wins; empty segments give value 0
-    and argmax == src.size(0) (the sentinel modules/msg_agg.py:19 tests for)."""
+    and argmax == src.size(0) (the sentinel modules/msg_agg.py:19 tests for).
+
+    Vectorised (the real package runs a C++ loop here, so a per-element Python loop
+    would handicap the CPU baseline): two stable sorts -- by value descending, then by
+    segment -- leave, at the head of every segment, its largest value with the smallest
+    original position among equals, i.e. exactly the winner of the strict-`>` scan."""
     assert dim == 0 and src.dim() == 1
+    n = src.size(0)
+    size = int(dim_size if dim_size is not None else (int(index.max()) + 1 if n else 0))
+    out = torch.zeros(size, dtype=src.dtype)
+    arg = torch.full((size,), n, dtype=torch.long)
+    if n:
+        order = torch.argsort(src, descending=True, stable=True)
+        order = order[torch.argsort(index[order], stable=True)]
+        seg = index[order]
+        head = torch.ones(n, dtype=torch.bool)
+        head[1:] = seg[1:] != seg[:-1]
+        win = order[head]
+        out[seg[head]] = src[win]
+        arg[seg[head]] = win
+    return out, arg
+
+
+def scatter_max_loop(src: Tensor, index: Tensor, dim: int = 0, dim_size: int | None = None):
+    """The same rule as an explicit sequential scan (small cases; pins scatter_max in tests)."""
     n = src.size(0)
     size = int(dim_size if dim_size is not None else (int(index.max()) + 1 if n else 0))
     out = torch.zeros(size, dtype=src.dtype)

@@ -291,6 +291,15 @@ def gen_callers(path):
     np.savez_compressed(path, **out)
 
 
+def vendor_driver(path):
+    """The reference's CLI driver, byte for byte, as a DATA fixture (`.txt`, never imported from here):
+    tests/test_gpu_unchanged_driver.py copies it to a scratch directory as pyg-mem-tgn.py and runs it
+    unchanged on top of this package's drop-in modules; tests/test_oracle_golden.py checks it is still
+    identical to /root/reference/pyg-mem-tgn.py wherever the reference tree is present."""
+    import shutil
+    shutil.copyfile(os.path.join(REF, "pyg-mem-tgn.py"), path)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("reference tree not present: golden vectors can only be regenerated where /root/reference exists")
@@ -301,6 +310,7 @@ if __name__ == "__main__":
     gen_embedding(os.path.join(HERE, "embedding.npz"))
     gen_callers(os.path.join(HERE, "callers.npz"))
     gen_variants(os.path.join(HERE, "variants.npz"))
+    vendor_driver(os.path.join(HERE, "ref_driver_pyg-mem-tgn.py.txt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

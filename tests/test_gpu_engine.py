@@ -301,3 +301,91 @@ def test_grouped_host_feeding_equals_resident_path():
     torch.testing.assert_close(eng_a.memory, eng_g.memory, rtol=1e-2, atol=1e-3)
     assert torch.equal(eng_a.e_id, eng_g.e_id) and torch.equal(eng_a.t_ring, eng_g.t_ring)
     assert torch.equal(eng_a.last_update, eng_g.last_update)
+
+
+def test_log_growth_drops_graphs_and_keeps_training():
+    """re-allocating the message-store log used to leave captured graphs replaying against freed
+    buffers.  _grow_log drops every graph; the run continues bit-compatibly with an engine that never grew."""
+    N, De, D, K, B, steps = 300, 8, 16, 4, 32, 16
+    _, eng_a, ev = _setup(N, De, D, K, B, B * steps, 23, True, lr=1e-6)
+    _, eng_b, _ = _setup(N, De, D, K, B, B * steps, 23, True, lr=1e-6)
+    for s in range(steps):
+        if s == 8:
+            assert any(k[0] == "train" for k in eng_b._graphs if isinstance(k, tuple))
+            old_ptr = eng_b.store.ev_src.data_ptr()
+            eng_b._grow_log(4 * eng_b.store.capacity)
+            assert eng_b._graphs == {} and eng_b.store.ev_src.data_ptr() != old_ptr
+        la, lb = float(eng_a.train_step()), float(eng_b.train_step())
+        assert abs(la - lb) < 1e-4, (s, la, lb)
+    eng_b.check_device_errors()
+    assert torch.equal(eng_a.last_update, eng_b.last_update) and torch.equal(eng_a.e_id, eng_b.e_id)
+    torch.testing.assert_close(eng_a.memory, eng_b.memory, rtol=1e-2, atol=1e-3)
+
+
+def test_stepping_past_the_resident_events_is_refused():
+    """edge features are events['msg'][e_id]; an e_id past the resident arrays must not be read."""
+    from tgn_b200 import _cabi
+    N, De, D, K, B = 300, 8, 16, 4, 32
+    _, eng, ev = _setup(N, De, D, K, B, B * 3, 29, False)
+    for _ in range(3):
+        eng.train_step()
+    with pytest.raises(_cabi.TgnError, match="resident events"):
+        eng.train_step()
+    with pytest.raises(_cabi.TgnError, match="resident events"):
+        eng.eval_batch(ev["src"][:B], ev["dst"][:B], ev["neg"][:B].view(B, 1), ev["t"][:B], ev["msg"][:B])
+
+
+def test_device_error_word_flags_out_of_range_event_rows():
+    """tgn_edge_attr_ld with a row id outside [0, num_events): zero row + TGN_DEVERR_EVENT_RANGE, no fault."""
+    from tgn_b200 import _cabi, ops
+    L = _cabi.lib()
+    L.tgn_device_errors(1)
+    E, De, Dt, n_ev = 6, 3, 4, 10
+    lu = torch.zeros(4, dtype=torch.long, device=DEV)
+    nbr = torch.zeros(E, dtype=torch.long, device=DEV)
+    t_ev = torch.arange(n_ev, dtype=torch.long, device=DEV)
+    msg = torch.ones((n_ev, De), device=DEV)
+    rows = torch.tensor([0, 1, 2, 10, 3, -1], dtype=torch.long, device=DEV)
+    tw, tb = torch.ones(Dt, device=DEV), torch.zeros(Dt, device=DEV)
+    ea = torch.full((E, 8), 7.0, device=DEV)
+    p = ops._p
+    _cabi.check(L.tgn_edge_attr_ld(p(lu), p(nbr), p(t_ev), p(msg), p(rows), n_ev, E, None, De, Dt, p(tw), p(tb), 8,
+                                   p(ea), None, None, ops._stream()))
+    torch.cuda.synchronize()
+    assert L.tgn_device_errors(0) & 2
+    assert L.tgn_device_errors(1) & 2 and L.tgn_device_errors(0) == 0
+    assert float(ea[3].abs().sum()) == 0.0 and float(ea[5].abs().sum()) == 0.0
+    assert torch.equal(ea[0, Dt:Dt + De], torch.ones(De, device=DEV))
+
+
+def test_tail_batch_engine_shares_state():
+    """A second step geometry on the same training state (TGNEngine(share=...)): the events that do not fill a
+    whole batch are trained as one shorter batch, like the reference's last DataLoader batch (ADVICE r1:
+    run_tgn.py --engine used to drop them, shifting every later e_id)."""
+    from tgn_b200.engine import TGNEngine
+    N, De, D, K, B, tail = 400, 12, 32, 5, 50, 17
+    steps = 4
+    E = B * steps + tail
+    ref, eng, ev = _setup(N, De, D, K, B, E, 31, True)
+    tail_eng = TGNEngine(N, De, D, K, tail, device=DEV, lr=1e-3, dropout=0.0, use_graph=False, share=eng)
+    loader = orc.TorchNeighborLoader(N, K)
+    opt = torch.optim.Adam(orc.model_parameters(ref), lr=1e-3)
+    strip = lambda sd: {k: v for k, v in sd.items() if k not in ("memory", "last_update", "_assoc")}
+    lo = 0
+    for s in range(steps + 1):
+        n = B if s < steps else tail
+        sl = slice(lo, lo + n)
+        lo += n
+        if s < steps:
+            loss = float(eng.train_step(from_device=True))
+        else:
+            eng.handover()
+            loss = float(tail_eng.train_step(from_device=True))
+        loss_ref = orc.train_step(ref, loader, opt, ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl],
+                                  ev["msg"][sl], ev["t"], ev["msg"], dropout=False)
+        assert abs(loss - loss_ref) < 1e-4 * max(1.0, abs(loss_ref)), (s, loss, loss_ref)
+        eng.load_state(strip(ref["memory"].state_dict()), ref["gnn"].state_dict(), ref["link_pred"].state_dict())
+    assert eng.events_done == E and tail_eng.ring_pos == E and float(eng.adam_step_dev) == steps + 1
+    assert torch.equal(eng.last_update.cpu(), ref["memory"].last_update)
+    assert torch.equal(eng.e_id.cpu(), loader.e_id)
+    torch.testing.assert_close(eng.memory.cpu(), ref["memory"].memory.detach(), rtol=1e-4, atol=1e-5)

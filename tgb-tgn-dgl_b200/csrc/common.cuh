@@ -38,6 +38,31 @@ int set_err(int code, const char* fmt, ...);
                             __LINE__, cudaGetErrorString(e__));               \
   } while (0)
 
+// Device-side error word: one int32 in mapped pinned host memory (allocated on first use, portable
+// across devices).  Kernels that detect a contract violation they cannot report through a return
+// code (a log overflow or an out-of-range event id inside a captured graph) OR a bit into it and
+// carry on without touching memory out of bounds; the host reads it with tgn_device_errors() --
+// a plain memory read, no CUDA call.
+#define TGN_DEVERR_LOG_OVERFLOW 1   /* message-store log full: events were dropped */
+#define TGN_DEVERR_EVENT_RANGE 2    /* an e_id outside the resident event arrays was dereferenced */
+#define TGN_DEVERR_SORT_CAP 4       /* a batch exceeded a kernel's in-shared-memory sort capacity */
+int32_t* dev_err_word();
+__device__ __forceinline__ void flag_dev_err(int32_t* w, int bit) {
+  if (w) atomicOr_system(reinterpret_cast<int*>(w), bit);
+}
+
+// Opt-in to > 48 KB of dynamic shared memory.  cudaFuncSetAttribute is per DEVICE, so the "already
+// done" cache is a bit per device ordinal (a process that drives several GPUs sets it on each).
+template <typename F>
+static inline cudaError_t smem_optin(F func, int bytes, unsigned long long& done_mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && ((done_mask >> dev) & 1ull)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done_mask |= 1ull << dev;
+  return e;
+}
+
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -357,14 +357,11 @@ int32_t tgn_tc_gemm(const float* a, const int64_t* a_rows, const float* b, const
     return tgn_gemm_batch(&d, 1, precision, stream);
   }
   const size_t smem = (size_t)kStages * kStageFloats * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TGN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TGN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TGN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TGN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static unsigned long long m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+  TGN_CUDA(smem_optin(tc_gemm_kernel<false, false>, (int)smem, m0));
+  TGN_CUDA(smem_optin(tc_gemm_kernel<false, true>, (int)smem, m1));
+  TGN_CUDA(smem_optin(tc_gemm_kernel<true, false>, (int)smem, m2));
+  TGN_CUDA(smem_optin(tc_gemm_kernel<true, true>, (int)smem, m3));
   TcArgs g;
   g.a = a; g.a_rows = a_rows; g.b = b; g.bias = bias; g.c = c;
   g.m = DevCount{m_dev, m}; g.k = DevCount{k_dev, k};

@@ -772,11 +772,8 @@ int32_t tgn_gemm_batch(const tgn_gemm_desc* d, int32_t count, int32_t precision,
   if (np == 0) return TGN_OK;
   prm.nprob = np;
   const size_t smem_max = (size_t)kGStages3 * kGStageBytes3 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TGN_CUDA(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  TGN_CUDA(smem_optin(tgemm_kernel, (int)smem_max, attr_mask));
   // Ring depth.  A full ring (192 KB) allows one CTA per SM.  A launch of short reductions whose tiles
   // do not fit one wave of 148 CTAs but fit two CTAs per SM runs with a 64 KB ring instead: all tiles
   // are resident at once, which beats a second wave for K <= 4 k-blocks (e.g. the node projection of
@@ -817,11 +814,8 @@ int32_t tgn_gru_fused_fwd(const float* x, int32_t ldx, int32_t dx, const float* 
   P.h = h; P.b_ih = b_ih; P.b_hh = b_hh; P.out = out; P.gates = gates; P.m_dev = num_dev;
   P.m = num; P.dx = dx; P.D = dim; P.prec = precision;
   const size_t smem = (size_t)kGStages3 * kGStageBytes3 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TGN_CUDA(cudaFuncSetAttribute(gru_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  TGN_CUDA(smem_optin(gru_fused_kernel, (int)smem, attr_mask));
   const int tiles = ceil_div(num, GM) * ceil_div(dim, kGruUnits);
   launch_k(gru_fused_kernel, dim3(tiles), dim3(kGThreads), smem, (cudaStream_t)stream, maps, P);
   TGN_LAUNCH_CHECK();

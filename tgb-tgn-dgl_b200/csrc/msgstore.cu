@@ -79,12 +79,15 @@ __global__ void __launch_bounds__(1024, 1)
     msgstore_update_kernel(tgn_msgstore st, const int64_t* __restrict__ src,
                            const int64_t* __restrict__ dst, const T* __restrict__ t,
                            const float* __restrict__ raw, int B, int P, int64_t base_host,
-                           int64_t* __restrict__ base_dev) {
+                           int64_t* __restrict__ base_dev, int32_t* err) {
   pdl_wait();
   pdl_launch();
   extern __shared__ unsigned long long s_key[];
   const int64_t base = base_dev ? *base_dev : base_host;
-  if (base + B > st.capacity) return;  // caller sizes the log; never write out of bounds
+  if (base + B > st.capacity) {  // caller sizes the log; never write out of bounds -- but say so
+    if (threadIdx.x == 0) flag_dev_err(err, TGN_DEVERR_LOG_OVERFLOW);
+    return;
+  }
   T* ev_t = reinterpret_cast<T*>(st.ev_t);
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
     st.ev_src[base + i] = src[i];
@@ -351,21 +354,16 @@ int32_t tgn_msgstore_update(const tgn_msgstore* st, const int64_t* src, const in
               batch, (long long)st->capacity);
   int P = 2;
   while (P < batch) P <<= 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TGN_CUDA(cudaFuncSetAttribute(msgstore_update_kernel<int64_t>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TGN_SORT_MAX * 8));
-    TGN_CUDA(cudaFuncSetAttribute(msgstore_update_kernel<float>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TGN_SORT_MAX * 8));
-    attr_set = true;
-  }
+  static unsigned long long mi = 0, mf = 0;
+  TGN_CUDA(smem_optin(msgstore_update_kernel<int64_t>, TGN_SORT_MAX * 8, mi));
+  TGN_CUDA(smem_optin(msgstore_update_kernel<float>, TGN_SORT_MAX * 8, mf));
   cudaStream_t s = (cudaStream_t)stream;
   if (st->t_is_float)
     launch_k(msgstore_update_kernel<float>, dim3(1), dim3(1024), (size_t)P * 8, s, 
-        *st, src, dst, (const float*)t, raw_msg, batch, P, base, base_dev);
+        *st, src, dst, (const float*)t, raw_msg, batch, P, base, base_dev, dev_err_word());
   else
     launch_k(msgstore_update_kernel<int64_t>, dim3(1), dim3(1024), (size_t)P * 8, s, 
-        *st, src, dst, (const int64_t*)t, raw_msg, batch, P, base, base_dev);
+        *st, src, dst, (const int64_t*)t, raw_msg, batch, P, base, base_dev, dev_err_word());
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

@@ -266,12 +266,8 @@ int32_t tgn_nbr_insert(const int64_t* src, const int64_t* dst, const float* t, i
   TGN_REQUIRE(src && dst && t && neighbors && e_id && t_state, "nbr_insert: NULL pointer");
   int P = 2;
   while (P < 2 * batch) P <<= 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TGN_CUDA(cudaFuncSetAttribute(nbr_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TGN_SORT_MAX * 8));
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  TGN_CUDA(smem_optin(nbr_insert_kernel, TGN_SORT_MAX * 8, attr_mask));
   launch_k(nbr_insert_kernel, dim3(1), dim3(1024), (size_t)P * 8, (cudaStream_t)stream, 
       src, dst, t, batch, P, cur_e_id, cur_e_id_dev, size_k, num_nodes, neighbors, e_id, t_state);
   TGN_LAUNCH_CHECK();

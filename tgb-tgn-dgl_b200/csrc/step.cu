@@ -45,6 +45,8 @@ struct EdgeAttr2Args {
   float* ea;     // [E, ld]
   float* sn;     // [E, Dt] sin(w*rel+b) (nullable)
   float* rel;    // [E]
+  long long num_events;  // rows of t_edge / msg (0 = unchecked)
+  int32_t* err;
 };
 
 __global__ void edge_attr_ld_kernel(EdgeAttr2Args a) {
@@ -56,6 +58,13 @@ __global__ void edge_attr_ld_kernel(EdgeAttr2Args a) {
        x += (long long)gridDim.x * blockDim.x) {
     const int e = (int)(x / a.ld), d = (int)(x - (long long)e * a.ld);
     const long long mr = a.msg_rows ? a.msg_rows[e] : e;
+    if (a.num_events > 0 && (mr < 0 || mr >= a.num_events)) {  // the ring names an event that is not resident
+      if (d == 0) flag_dev_err(a.err, TGN_DEVERR_EVENT_RANGE);
+      a.ea[x] = 0.f;
+      if (d < a.Dt && a.sn) a.sn[(long long)e * a.Dt + d] = 0.f;
+      if (d == 0 && a.rel) a.rel[e] = 0.f;
+      continue;
+    }
     if (d < a.Dt) {
       const float rt = (float)(a.lu[a.nbr[e]] - a.t_edge[mr]);
       float sv, cv;
@@ -985,10 +994,10 @@ int32_t tgn_relabel3(const int64_t* a, int32_t na, const int32_t* na_dev, int64_
 
 int32_t tgn_edge_attr_ld(const int64_t* last_update_local, const int64_t* nbr_local,
                          const int64_t* t_edge, const float* msg, const int64_t* msg_rows,
-                         int32_t num_edges, const int32_t* num_edges_dev, int32_t raw_dim,
+                         int64_t num_events, int32_t num_edges, const int32_t* num_edges_dev, int32_t raw_dim,
                          int32_t time_dim, const float* time_w, const float* time_b, int32_t ld,
                          float* edge_attr, float* sin_out, float* rel_t, void* stream) {
-  TGN_REQUIRE(num_edges >= 0 && raw_dim >= 0 && time_dim >= 0 && ld >= raw_dim + time_dim && ld >= 1,
+  TGN_REQUIRE(num_events >= 0 && num_edges >= 0 && raw_dim >= 0 && time_dim >= 0 && ld >= raw_dim + time_dim && ld >= 1,
               "edge_attr_ld: bad sizes");
   if (num_edges == 0) return TGN_OK;
   TGN_REQUIRE(last_update_local && nbr_local && t_edge && (msg || raw_dim == 0) && edge_attr &&
@@ -998,6 +1007,7 @@ int32_t tgn_edge_attr_ld(const int64_t* last_update_local, const int64_t* nbr_lo
   a.lu = last_update_local; a.nbr = nbr_local; a.t_edge = t_edge; a.msg = msg; a.msg_rows = msg_rows;
   a.edges = DevCount{num_edges_dev, num_edges}; a.De = raw_dim; a.Dt = time_dim; a.ld = ld;
   a.time_w = time_w; a.time_b = time_b; a.ea = edge_attr; a.sn = sin_out; a.rel = rel_t;
+  a.num_events = num_events; a.err = dev_err_word();
   launch_k(edge_attr_ld_kernel, dim3(stride_grid((long long)num_edges * ld, 256)), dim3(256), 0, (cudaStream_t)stream, a);
   TGN_LAUNCH_CHECK();
   return TGN_OK;

@@ -28,6 +28,18 @@ int& pdl_flag() {
   return flag;
 }
 
+int32_t* dev_err_word() {
+  static int32_t* word = [] {
+    int32_t* p = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&p), sizeof(int32_t),
+                      cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
+      return static_cast<int32_t*>(nullptr);
+    *p = 0;
+    return p;
+  }();
+  return word;
+}
+
 static inline int64_t l0_groups(int64_t n) { return (n + 1023) / 1024; }
 static inline int64_t l0_words(int64_t n) { return l0_groups(n) * 32; }
 static inline int64_t l1_words(int64_t n) { return (l0_groups(n) + 31) / 32; }
@@ -167,6 +179,13 @@ extern "C" {
 
 int32_t tgn_abi_version(void) { return TGN_ABI_VERSION; }
 const char* tgn_last_error(void) { return tgn::err_buf(); }
+int32_t tgn_device_errors(int32_t reset) {
+  volatile int32_t* w = tgn::dev_err_word();
+  if (!w) return 0;
+  const int32_t v = *w;
+  if (reset) *w = 0;
+  return v;
+}
 int32_t tgn_set_pdl(int32_t enabled) {
   const int old = tgn::pdl_flag();
   tgn::pdl_flag() = enabled ? 1 : 0;

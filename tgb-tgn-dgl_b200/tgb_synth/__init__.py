@@ -10,6 +10,8 @@ optional size cap "name@events" (e.g. "tgbl-wiki@20000") for quick runs.
 from types import SimpleNamespace
 from typing import List
 
+import zlib
+
 import numpy as np
 import torch
 
@@ -47,7 +49,8 @@ class NegativeSampler:
         dst = torch.as_tensor(pos_dst).cpu().numpy()
         t = torch.as_tensor(pos_t).cpu().numpy()
         # deterministic per (split, first event of the batch): the same batch always gets the same negatives
-        key = (hash(split_mode) & 0xFFFF) * 1_000_003 + int(src[0]) * 7919 + int(dst[0]) * 104_729 + int(t[0])
+        # (zlib.crc32, not hash(): str hashes are randomised per process, and every rank / run must draw the same)
+        key = (zlib.crc32(str(split_mode).encode()) & 0xFFFF) * 1_000_003 + int(src[0]) * 7919 + int(dst[0]) * 104_729 + int(t[0])
         neg = synth.eval_negatives(src, dst, self.num_nodes, self.num_neg, seed=(self.seed + key) & 0x7FFFFFFF,
                                    dst_lo=self.dst_lo)
         return neg.tolist()

@@ -51,7 +51,11 @@ class TGNEngine:
                  device="cuda", lr: float = 1e-4, heads: int = 2, dropout: float = 0.1,
                  log_capacity: int = 1 << 20, seed: int = 0, use_graph: bool = True,
                  precision: int = 3, rank: int = 0, world: int = 1, group=None, fused_zero_grad: bool = False,
-                 part_exchange: str = "p2p"):
+                 part_exchange: str = "p2p", share: Optional["TGNEngine"] = None):
+        """share: another engine of the same model (nodes, dims, K, world) whose weights, Adam moments, node
+        memory, neighbour ring, message store, event arrays and cursors this one USES instead of allocating
+        its own -- a second step geometry (another batch size, e.g. the tail batch of an epoch) on the same
+        training state.  Only one of the engines may be stepping at a time."""
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("TGNEngine runs on CUDA only (no CPU fallback)")
@@ -97,14 +101,17 @@ class TGNEngine:
         self.n_param = o
         # gradients, the loss scalar and the embedding-gradient rows share one zero-filled blob
         R, E, Nb = self._bounds(batch_size)
+        if share is not None and (share.N, share.De, share.D, share.K, share.H, share.world, share.rank) != \
+                (num_nodes, raw_dim, hidden, size_k, heads, world, rank):
+            raise ValueError("share: the two engines must describe the same model and partition")
         self.zero_blob = torch.zeros(o + 4 + Nb * HC, device=dev)
-        self.flat = torch.zeros(o, device=dev)
+        self.flat = torch.zeros(o, device=dev) if share is None else share.flat
         self.flat_grad = self.zero_blob[:o]
         self.loss_acc = self.zero_blob[o:o + 1]
         self.d_emb = self.zero_blob[o + 4:].view(Nb, HC)
-        self.exp_avg = torch.zeros(o, device=dev)
-        self.exp_avg_sq = torch.zeros(o, device=dev)
-        self.adam_step_dev = torch.zeros(1, device=dev)
+        self.exp_avg = torch.zeros(o, device=dev) if share is None else share.exp_avg
+        self.exp_avg_sq = torch.zeros(o, device=dev) if share is None else share.exp_avg_sq
+        self.adam_step_dev = torch.zeros(1, device=dev) if share is None else share.adam_step_dev
         self.done_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
         # fused_zero_grad: Adam clears the gradients (and the other per-step accumulators) after using
         # them, so a step starts without a memset; p[...].grad then reads zero after train_step()
@@ -123,7 +130,18 @@ class TGNEngine:
         if part_exchange not in ("p2p", "allreduce"):
             raise ValueError("part_exchange must be 'p2p' or 'allreduce'")
         self.part_exchange = part_exchange if world > 1 else "none"
-        if self.part_exchange == "p2p":
+        self._shared_with = share
+        if share is not None:
+            if share._shared_with is not None:
+                raise ValueError("share: pass the engine that owns the state, not one of its siblings")
+            share.__dict__.setdefault("_siblings", []).append(self)
+            self.part_exchange = share.part_exchange
+            for k in ("memory", "last_update", "assoc", "neighbors", "e_id", "t_ring", "store", "bitmap",
+                      "cur_e_id_dev", "log_base_dev", "pos_dev", "step_dev", "_symm_mem", "_symm_lu", "_peer_mem",
+                      "_peer_lu"):
+                if hasattr(share, k):
+                    setattr(self, k, getattr(share, k))
+        elif self.part_exchange == "p2p":
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm_mem
             grp = group if group is not None else dist.group.WORLD
@@ -137,21 +155,24 @@ class TGNEngine:
             self._peer_lu = (ctypes.c_void_p * world)(*[int(p) for p in self._symm_lu.buffer_ptrs])
             torch.cuda.synchronize()
             self._symm_mem.barrier(channel=0)
-        else:
+        elif share is None:
             self.memory = torch.zeros((self.Nloc, D), device=dev)
             self.last_update = torch.zeros(self.Nloc, dtype=torch.long, device=dev)
-        self.assoc = torch.zeros(num_nodes, dtype=torch.long, device=dev)
-        self.neighbors = torch.zeros((num_nodes, size_k), dtype=torch.long, device=dev)
-        self.e_id = torch.full((num_nodes, size_k), -1, dtype=torch.long, device=dev)
-        self.t_ring = torch.full((num_nodes, size_k), -1.0, device=dev)
-        self.store = ops.MsgStore(num_nodes, raw_dim, dev, capacity=log_capacity, t_dtype=torch.int64)
-        self.bitmap = torch.zeros(_L().tgn_bitmap_bytes(num_nodes) // 4, dtype=torch.int32, device=dev)
-        self.cur_e_id_dev = torch.zeros(1, dtype=torch.long, device=dev)   # ring event counter
-        self.log_base_dev = torch.zeros(1, dtype=torch.long, device=dev)   # store log position
-        self.pos_dev = torch.zeros(1, dtype=torch.long, device=dev)        # dataset cursor
-        self.step_dev = torch.zeros(1, dtype=torch.long, device=dev)       # dropout stream
-        self.events_done = 0
-        self.events = None
+        if share is None:
+            self.assoc = torch.zeros(num_nodes, dtype=torch.long, device=dev)
+            self.neighbors = torch.zeros((num_nodes, size_k), dtype=torch.long, device=dev)
+            self.e_id = torch.full((num_nodes, size_k), -1, dtype=torch.long, device=dev)
+            self.t_ring = torch.full((num_nodes, size_k), -1.0, device=dev)
+            self.store = ops.MsgStore(num_nodes, raw_dim, dev, capacity=log_capacity, t_dtype=torch.int64)
+            self.bitmap = torch.zeros(_L().tgn_bitmap_bytes(num_nodes) // 4, dtype=torch.int32, device=dev)
+            self.cur_e_id_dev = torch.zeros(1, dtype=torch.long, device=dev)   # ring event counter
+            self.log_base_dev = torch.zeros(1, dtype=torch.long, device=dev)   # store log position
+            self.pos_dev = torch.zeros(1, dtype=torch.long, device=dev)        # dataset cursor
+            self.step_dev = torch.zeros(1, dtype=torch.long, device=dev)       # dropout stream
+        # host mirrors of the device cursors (a graph replay does not run Python): events_done = log_base_dev
+        # (message-store log position, reset by flush_to_eval), ring_pos = cur_e_id_dev (the e_id the NEXT
+        # inserted event gets; e_id == row of the resident event arrays)
+        self._cur = SimpleNamespace(events_done=0, ring_pos=0, events=None) if share is None else share._cur
         self.side = torch.cuda.Stream(device=dev)    # ring insert + sampling of the NEXT batch
         self.upd = torch.cuda.Stream(device=dev)     # memory / message-store update of this batch
         self.aux = torch.cuda.Stream(device=dev)     # edge branch of the attention / small reductions
@@ -187,6 +208,57 @@ class TGNEngine:
         self.fused_gru = hidden % 4 == 0    # tgn_gru_fused_fwd (TMA strides need 16-byte rows)
         self.dz_split = 3                   # split-K of the d_z GEMM (1 = plain store)
         self.probe = None   # bench.py: {"name": [(start_event, stop_event), ...]} filled in eager steps
+
+    events_done = property(lambda self: self._cur.events_done,
+                           lambda self, v: setattr(self._cur, "events_done", v))
+    ring_pos = property(lambda self: self._cur.ring_pos, lambda self, v: setattr(self._cur, "ring_pos", v))
+    events = property(lambda self: self._cur.events, lambda self, v: setattr(self._cur, "events", v))
+
+    def _family(self):
+        root = self
+        while root._shared_with is not None:
+            root = root._shared_with
+        return [root] + list(getattr(root, "_siblings", []))
+
+    def _advance(self, n_events: int):
+        """host mirrors after n_events more events have been queued (graph replays do not run Python)"""
+        self._cur.events_done += n_events
+        self._cur.ring_pos += n_events
+        self.store.size = self._cur.events_done
+
+    def _grow_log(self, need: int):
+        """Re-allocates the message-store log.  Captured graphs hold the old ev_* / perm pointers BY VALUE, so
+        every graph (of this engine and of the engines sharing its state) is dropped and re-captured."""
+        torch.cuda.synchronize()
+        self.store._alloc_log(int(need))
+        for e in self._family():
+            e._graphs = {}
+
+    def _reserve(self, n_events: int):
+        """Host-side guard in front of every replay: the log has room for the events about to be appended
+        (the kernel would drop them and raise TGN_DEVERR_LOG_OVERFLOW), and the resident event arrays cover
+        every e_id the ring is about to hand out (edge features are events['msg'][e_id], epoch_utils.py:224)."""
+        self.check_device_errors()
+        if self.events_done + n_events > self.store.capacity:
+            self._grow_log(max(2 * self.store.capacity, self.events_done + n_events))
+        if self.events is not None and self.ring_pos + n_events > self.events["src"].numel():
+            raise _cabi.TgnError(
+                f"ring event id {self.ring_pos + n_events} would pass the {self.events['src'].numel()} resident events: "
+                "set_events() must hold EVERY event the neighbour ring can name (train + val + test), e_id == row")
+
+    def check_device_errors(self):
+        """Raises if a kernel flagged a contract violation (see tgn_device_errors in include/tgn_b200.h);
+        a plain host read, valid for work that has completed."""
+        v = _L().tgn_device_errors(1)
+        if v:
+            names = [n for b, n in ((1, "message-store log overflow (events dropped)"),
+                                    (2, "event id outside the resident event arrays"),
+                                    (4, "batch above a kernel's sort capacity")) if v & b]
+            raise _cabi.TgnError("device-side error flag: " + "; ".join(names))
+
+    def handover(self):
+        """Call before stepping an engine that shares this one's state (share=): drops the pre-sampled batch."""
+        self._unprime()
 
     # ------------------------------------------------------------------ layout helpers
     def _bounds(self, B: int, roots: Optional[int] = None):
@@ -339,20 +411,36 @@ class TGNEngine:
         self.log_base_dev.zero_()
         self.pos_dev.zero_()
         self.events_done = 0
+        self.ring_pos = 0
         self._primed = None
         self.store.reset()
 
     # ------------------------------------------------------------------ data
     def set_events(self, src: Tensor, dst: Tensor, t: Tensor, msg: Tensor, neg: Optional[Tensor] = None):
-        """Device-resident event arrays (the whole split).  `t` int64, `msg` [E, De].
-        e_id of the ring == row of these arrays, like data.msg[e_id] in the reference."""
+        """Device-resident event arrays.  `t` int64, `msg` [E, De].  e_id of the ring == row of these arrays,
+        like data.msg[e_id] in the reference (epoch_utils.py:224): they must hold EVERY event the ring can
+        name -- when evaluation follows training on the same ring, pass train + val + test in stream order
+        (_reserve() refuses to step past their end; the kernel flags TGN_DEVERR_EVENT_RANGE).  Host-staged
+        batches (stage_*) feed the step's own batch only; they do not replace these arrays."""
         dev = self.dev
+        new = dict(src=src, dst=dst, t=t, msg=msg, neg=neg)
+        old = self.events
+        if old is not None and all((old[k] is None) == (new[k] is None) and
+                                   (new[k] is None or tuple(old[k].shape) == tuple(new[k].shape)) for k in new):
+            for k, v in new.items():      # same sizes (a new epoch's negatives): refill in place, the captured
+                if v is not None:         # graphs keep pointing at these buffers
+                    old[k].copy_(v)
+            return
+        if old is not None:               # different arrays: the graphs hold the old pointers
+            torch.cuda.synchronize()
+            for e in self._family():
+                e._graphs = {}
         self.events = dict(src=src.to(dev, torch.long).contiguous(), dst=dst.to(dev, torch.long).contiguous(),
                            t=t.to(dev, torch.long).contiguous(), msg=msg.to(dev, torch.float32).contiguous(),
                            neg=None if neg is None else neg.to(dev, torch.long).contiguous())
         need = self.events["src"].numel()
         if self.store.capacity < need:
-            self.store._alloc_log(need)
+            self._grow_log(need)
 
     def stage_batch_from_device(self, slot: Optional[int] = None):
         ev, sl = self.events, self.slots[self.cur if slot is None else slot]
@@ -414,6 +502,7 @@ class TGNEngine:
         self.log_base_dev.fill_(count)
         self.pos_dev.fill_(count)
         self.events_done = count
+        self.ring_pos = count
         self.store.size = count
         self._primed = None
 
@@ -531,8 +620,11 @@ class TGNEngine:
         (emb_module.py:26-28 + TransformerConv.lin_edge); independent of the GRU output."""
         p, HC, L, s = self.p, self.HC, _L(), _stream()
         ev = self.events
+        if ev is None:
+            raise _cabi.TgnError("TGNEngine needs set_events(): edge features and times are events['msg'/'t'][e_id] "
+                                 "(data.msg[e_id], epoch_utils.py:224) for every e_id the ring holds")
         check(L.tgn_edge_attr_ld(_p(lu), _p(w.nbr_l), _p(ev["t"]), _p(ev["msg"]) if self.De else None, _p(w.eid),
-                                 w.E, _p(w.E_dev), self.De, self.Dt, _p(p["time_enc.lin.weight"]),
+                                 ev["t"].numel(), w.E, _p(w.E_dev), self.De, self.Dt, _p(p["time_enc.lin.weight"]),
                                  _p(p["time_enc.lin.bias"]), self.lde, _p(w.ea), _p(w.sn_e) if train else None,
                                  _p(w.rel), s))
         ops.gemm_batch([ops.gemm_desc(w.ea, self.flat, w.ee, m=w.E, n=HC, k=self.Din, lda=self.lde, ldb=self.lde,
@@ -776,6 +868,7 @@ class TGNEngine:
         """
         mode = "device" if from_device else "host"
         pipelined = from_device or lookahead
+        self._reserve(self.B)
         if pipelined:
             if self._primed != mode:           # first pipelined step: sample the current batch now
                 self._unprime()
@@ -797,8 +890,7 @@ class TGNEngine:
         self.loss = self._loss_views[self.cur]
         if pipelined:
             self.cur = nxt
-        self.events_done += self.B
-        self.store.size = self.events_done   # host mirror of log_base_dev (graph replays skip the Python body)
+        self._advance(self.B)
         return self.loss
 
     def train_steps(self, n: int):
@@ -812,11 +904,11 @@ class TGNEngine:
             done = 1
         G = self.group_size
         while self.use_graph and n - done >= G:
+            self._reserve(G * self.B)
             self._run(("train_multi", self.cur), lambda: self._multi_body(True))
             self.cur = (self.cur + G) % self.nslots
             done += G
-            self.events_done += G * self.B
-            self.store.size = self.events_done
+            self._advance(G * self.B)
             self.loss = self._loss_views[(self.cur - 1) % self.nslots]
         while done < n:          # remainder: replays the single-step graph if it exists, else runs eagerly
             self.train_step(from_device=True, _capture=False)
@@ -884,12 +976,12 @@ class TGNEngine:
             main.wait_event(self._slot_ready[nxt])
             self._slot_async[nxt] = False
         c0 = self.cur
+        self._reserve(G * self.B)
         self._run(("train_group_host", c0), lambda: self._multi_body(False))
         for k in range(G):
             self._slot_free[c0 + k].record(main)
         self.cur = nxt
-        self.events_done += G * self.B
-        self.store.size = self.events_done
+        self._advance(G * self.B)
         self.loss = self._loss_views[(nxt - 1) % self.nslots]
         self._gl_done[i].record(main)
         ls.wait_event(self._gl_done[i])
@@ -1014,9 +1106,7 @@ class TGNEngine:
         self._unprime()
         B, Q = neg.shape
         c = self._eval_ctx(B, Q)
-        if self.store.size + B > self.store.capacity:
-            self.store._alloc_log(max(2 * self.store.capacity, self.store.size + B))
-            self._graphs = {k: v for k, v in self._graphs.items() if k[0] != "eval"}   # pointers changed
+        self._reserve(B)
         c.ids[:B].copy_(src, non_blocking=True)
         c.ids[B:2 * B].copy_(dst, non_blocking=True)
         if Q:
@@ -1026,8 +1116,7 @@ class TGNEngine:
         if self.De:
             c.msg.copy_(msg, non_blocking=True)
         self._run(("eval", B, Q), lambda: self._eval_body(c))
-        self.events_done += B
-        self.store.size = self.events_done
+        self._advance(B)
         return c.pos, (c.negs[:, :Q] if want_neg_scores else None), c.gt, c.ge
 
     def eval_scores(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor):

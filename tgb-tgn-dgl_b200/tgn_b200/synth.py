@@ -24,12 +24,17 @@ SHAPES = {
 }
 
 
-def synth_events(name: str, seed: int = 0, max_events: Optional[int] = None) -> Dict[str, np.ndarray]:
+def synth_events(name: str, seed: int = 0, max_events: Optional[int] = None, batch: Optional[int] = None,
+                 extend: bool = False) -> Dict[str, np.ndarray]:
     """Returns numpy arrays: src, dst (int64), t (int64, sorted), msg (float32 [E, De]),
-    neg (int64, one negative destination per event), plus num_nodes / raw_dim / split sizes."""
+    neg (int64, one negative destination per event), plus num_nodes / raw_dim / split sizes.
+    `batch` overrides the shape's default batch size (config/TGN.yml:27 says 2000 where BASELINE.json
+    says 200).  extend=True lets `max_events` exceed the dataset's event count (same nodes, same
+    event rate: the time span grows with it) -- throughput runs on the small wiki shape need more
+    batches than its 157k events hold."""
     cfg = SHAPES[name]
     rng = np.random.default_rng(seed)
-    E = cfg["E"] if max_events is None else min(cfg["E"], int(max_events))
+    E = cfg["E"] if max_events is None else (int(max_events) if extend else min(cfg["E"], int(max_events)))
     N = cfg["N"]
     if cfg["bip"] is not None:
         ns, nd = cfg["bip"]
@@ -46,7 +51,7 @@ def synth_events(name: str, seed: int = 0, max_events: Optional[int] = None) -> 
     n_train = int(E * 0.70)
     n_val = int(E * 0.15)
     return dict(src=src, dst=dst, t=t, msg=msg, neg=neg, num_nodes=N, raw_dim=cfg["De"],
-                n_train=n_train, n_val=n_val, n_test=E - n_train - n_val, batch=cfg["B"], K=cfg["K"])
+                n_train=n_train, n_val=n_val, n_test=E - n_train - n_val, batch=cfg["B"] if batch is None else int(batch), K=cfg["K"])
 
 
 def sample_negatives(pos_dst: np.ndarray, dst_nodes: np.ndarray, rng) -> np.ndarray:

@@ -46,8 +46,12 @@ def _oracle_epoch(ref, data, train_loader, val_loader, neg_dest_sampler, ns, eva
     return total, float(np.mean(perf))
 
 
-@pytest.mark.parametrize("use_blocks", [False])
-def test_driver_sequence_matches_oracle(use_blocks):
+@pytest.mark.parametrize("use_engine", [None, False])
+def test_driver_sequence_matches_oracle(use_engine):
+    """use_engine=None: what the unchanged script gets -- train() recognises the standard model and runs the
+    epoch on TGNEngine attached to the modules' state; False: the module-by-module loop.  Both against the
+    oracle's epoch."""
+    use_blocks = False
     import utils
     from epoch_utils import test as run_test, train as run_train
     from model_utils import getModel, getOptimizer
@@ -78,10 +82,53 @@ def test_driver_sequence_matches_oracle(use_blocks):
     neighbor_loader = LastNeighborLoader(data.num_nodes, size=K, device=device)
     torch.manual_seed(5)
     loss = run_train(model, data.msg, tr, neighbor_loader, neg_dest_sampler, assoc, device, optimizer, criterion,
-                     use_blocks=use_blocks)
+                     use_blocks=use_blocks, use_engine=use_engine)
+    if use_engine is None:
+        import epoch_utils
+        assert len(epoch_utils._ENGINES) == 1, "the standard model must take the engine path"
+        assert neighbor_loader.cur_e_id == len(tr.dataset) and model["memory"].store.size == len(tr.dataset)
     mrr = run_test(model, data.msg, va, neighbor_loader, ns, assoc, device, optimizer, criterion, evaluator, metric, "val")
     assert abs(loss - loss_ref) < 2e-3 * abs(loss_ref), (loss, loss_ref)
     assert abs(mrr - mrr_ref) < 0.005, (mrr, mrr_ref)
+
+
+def test_engine_epochs_equal_module_epochs_and_keep_the_optimizer():
+    """Two epochs (train + validation each) through epoch_utils on the engine path and on the module path, same
+    seeds: per-epoch loss sums and validation MRR agree, and the torch optimizer carries Adam's moments and
+    step count across the epochs on both paths (the engine hands them back after every epoch)."""
+    import utils
+    from epoch_utils import test as run_test, train as run_train
+    from model_utils import getModel, getOptimizer
+    from neg_sampler import NegLinkSamplerDest
+    from neighbor_loader import LastNeighborLoader
+    train_param = {"batch_size": 100, "lr": 1e-4, "epoch": 2}
+    data, tr, va, te, ns, evaluator, metric = utils.getDataWithDependecyBlock("tgbl-wiki@2500", train_param)
+    device = torch.device(DEV)
+    res = {}
+    for use_engine in (None, False):
+        torch.manual_seed(0)
+        model = getModel(data.msg.shape[1], 100, data.num_nodes, device)
+        with torch.no_grad():
+            model["memory"].time_enc.lin.weight.mul_(0.002)    # free-running Adam: keep cos() well-conditioned
+        model["gnn"].conv.dropout = 0.0
+        opt = getOptimizer(model, 1e-4)
+        nl = LastNeighborLoader(data.num_nodes, size=10, device=device)
+        nds = NegLinkSamplerDest(torch.unique(data.dst))
+        out = []
+        torch.manual_seed(1)
+        for _ in range(2):
+            loss = run_train(model, data.msg, tr, nl, nds, None, device, opt, torch.nn.BCEWithLogitsLoss(),
+                             use_engine=use_engine)
+            mrr = run_test(model, data.msg, va, nl, ns, None, device, opt, None, evaluator, metric, "val")
+            out.append((loss, mrr))
+        p0 = next(iter(model["link_pred"].parameters()))
+        res[use_engine] = (out, float(opt.state[p0]["step"]), opt.state[p0]["exp_avg"].clone())
+    n_steps = 2 * len(tr)
+    assert res[None][1] == n_steps and res[False][1] == n_steps, (res[None][1], res[False][1], n_steps)
+    for (la, ma), (lb, mb) in zip(res[None][0], res[False][0]):
+        assert abs(la - lb) < 2e-3 * abs(lb), (la, lb)
+        assert abs(ma - mb) < 0.005, (ma, mb)
+    torch.testing.assert_close(res[None][2], res[False][2], rtol=5e-2, atol=1e-6)
 
 
 def test_blockwise_training_runs_and_differs_only_by_ordering():

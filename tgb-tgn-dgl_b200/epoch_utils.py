@@ -14,6 +14,15 @@ edge timestamps come from the neighbour loader's fourth output (:220); edge feat
 `use_blocks=True` additionally honours the dependency-aware block ids `b` of each batch
 (dependencyGraph.py): the events of a batch are processed block by block, each block seeing the
 memory and neighbour state left by the previous one.
+
+Fast path.  When `train` is handed exactly what the driver script builds (pyg-mem-tgn.py:44-51 on this
+package's model_utils: TGNMemory with IdentityMessage + LastAggregator + GRUCell, GraphAttentionEmbedding,
+LinkPredictor, torch.optim.Adam with default betas, BCEWithLogitsLoss, a TensorBatchLoader) the epoch runs
+on tgn_b200.engine.TGNEngine -- the same step as one captured CUDA graph -- ATTACHED to the modules' own
+state tensors (memory, last_update, message store, neighbour ring): after the epoch the modules, the
+neighbour loader and the optimizer are in the state the module-by-module loop leaves them in, so `test`
+(and a later module-path `train`) continue from it.  The unchanged script therefore gets the engine's
+throughput.  `use_engine=False` forces the module-by-module loop; anything non-standard falls back to it.
 """
 import numpy as np
 import torch
@@ -41,12 +50,108 @@ def _logits(link_pred, z_src, z_dst):
     return link_pred.logits(z_src, z_dst) if hasattr(link_pred, "logits") else link_pred(z_src, z_dst)
 
 
+_ENGINES = {}
+
+
+def _engine_eligible(model, feats, train_loader, neighbor_loader, optimizer, criterion, use_blocks) -> bool:
+    from modules.decoder import LinkPredictor
+    from modules.emb_module import GraphAttentionEmbedding
+    from modules.memory_module import TGNMemory
+    from modules.msg_agg import LastAggregator
+    from modules.msg_func import IdentityMessage
+    from temporal_dataset import TensorBatchLoader
+    if use_blocks or set(model.keys()) != {"memory", "gnn", "link_pred"}:
+        return False
+    mem, gnn, lp = model["memory"], model["gnn"], model["link_pred"]
+    if not (type(mem) is TGNMemory and type(gnn) is GraphAttentionEmbedding and type(lp) is LinkPredictor):
+        return False
+    if not (type(mem.msg_s_module) is IdentityMessage and type(mem.aggr_module) is LastAggregator and
+            isinstance(mem.memory_updater, torch.nn.GRUCell) and gnn.time_enc is mem.time_enc):
+        return False
+    if not (mem.memory_dim == mem.time_dim and mem.memory_dim % 4 == 0 and mem.memory_dim % gnn.conv.heads == 0 and
+            gnn.conv.heads * gnn.conv.out_channels == mem.memory_dim and mem.memory.is_cuda):
+        return False
+    if type(optimizer) is not torch.optim.Adam or len(optimizer.param_groups) != 1:
+        return False
+    g = optimizer.param_groups[0]
+    if not (tuple(g["betas"]) == (0.9, 0.999) and g["eps"] == 1e-8 and g["weight_decay"] == 0 and
+            not g.get("amsgrad") and not g.get("maximize")):
+        return False
+    want = {id(p) for k in ("memory", "gnn", "link_pred") for p in model[k].parameters()}
+    if {id(p) for p in g["params"]} != want:
+        return False
+    if type(criterion) is not torch.nn.BCEWithLogitsLoss or criterion.reduction != "mean" or \
+            criterion.weight is not None or criterion.pos_weight is not None:
+        return False
+    if type(train_loader) is not TensorBatchLoader or train_loader.drop_last:
+        return False
+    ds = train_loader.dataset
+    n = len(ds)
+    # edge features are feats[e_id] with e_id = position in the stream (epoch_utils.py:224): the training
+    # events must be the first rows of `feats`
+    if n < 1 or feats.shape[0] < n or feats.shape[1] != ds.msg.shape[1] or n // train_loader.batch_size < 1:
+        return False
+    probe = torch.linspace(0, n - 1, min(n, 64)).long()
+    return bool(torch.equal(feats[probe].to(ds.msg.dtype).cpu(), ds.msg[probe].cpu()))
+
+
+def _train_engine(model, train_loader, neighbor_loader, neg_dest_sampler, device, optimizer):
+    from tgn_b200.engine import TGNEngine
+    mem, gnn = model["memory"], model["gnn"]
+    ds, B = train_loader.dataset, train_loader.batch_size
+    n_all = len(ds)
+    n, tail = (n_all // B) * B, n_all % B
+    lr = optimizer.param_groups[0]["lr"]
+    key = (id(mem), id(neighbor_loader), B, tail, float(gnn.conv.dropout), mem.memory.data_ptr())
+    if key not in _ENGINES:
+        _ENGINES.clear()            # one model at a time: drop the graphs / workspaces of the previous one
+        kw = dict(device=mem.memory.device, lr=lr, heads=gnn.conv.heads, dropout=float(gnn.conv.dropout))
+        eng = TGNEngine(mem.num_nodes, mem.raw_msg_dim, mem.memory_dim, neighbor_loader.size, B, log_capacity=16, **kw)
+        eng.attach_modules(mem, neighbor_loader)
+        tail_eng = TGNEngine(mem.num_nodes, mem.raw_msg_dim, mem.memory_dim, neighbor_loader.size, tail, share=eng,
+                             use_graph=False, **kw) if tail else None
+        _ENGINES[key] = (eng, tail_eng)
+    eng, tail_eng = _ENGINES[key]
+    if eng.lr != lr:                # the captured graphs hold the learning rate by value
+        eng.lr = lr
+        eng._graphs = {}
+        if tail_eng is not None:
+            tail_eng.lr = lr
+    eng.sync_from_modules(model, optimizer)
+    eng.begin_epoch_on_modules()
+    # one negative per positive, drawn batch by batch exactly as the module loop draws them (same use of
+    # torch's generator, epoch_utils.py:198), then the whole epoch is resident
+    neg = torch.cat([neg_dest_sampler.sample(ds.dst[lo:lo + B]) for lo in range(0, n_all, B)])
+    # the loader hands out float32 timestamps (temporal_dataset.py:42) and update_state gets t.long()
+    eng.set_events(ds.src, ds.dst, ds.t.float().long(), ds.msg, neg)
+    total = 0.0
+    for _ in range(n // B):                       # every step's loss is logged, read back one step late
+        prev = eng.train_step_logged()
+        if prev is not None:
+            total += prev * B
+    total += eng.flush_loss() * B
+    if tail_eng is not None:
+        eng.handover()
+        total += float(tail_eng.train_step(from_device=True)) * tail
+        tail_eng.handover()
+    torch.cuda.synchronize()
+    eng.check_device_errors()
+    eng.end_epoch_on_modules()
+    eng.sync_to_modules(model, optimizer)
+    mem.detach()
+    return total
+
+
 def train(model, feats, train_loader, neighbor_loader, neg_dest_sampler, assoc, device, optimizer, criterion,
-          use_blocks: bool = False):
+          use_blocks: bool = False, use_engine=None):
     for m in model.values():
         m.train()
     model["memory"].reset_state()
     neighbor_loader.reset_state()
+    if use_engine is None:
+        use_engine = _engine_eligible(model, feats, train_loader, neighbor_loader, optimizer, criterion, use_blocks)
+    if use_engine:
+        return _train_engine(model, train_loader, neighbor_loader, neg_dest_sampler, device, optimizer)
     feats_dev = _device_feats(feats, device)
     total_loss = 0.0
     for batch in train_loader:

@@ -91,6 +91,7 @@ class TGNEngine:
                  ("lin_src.weight", (D, D), D), ("lin_src.bias", (D,), None),
                  ("lin_dst.weight", (D, D), D), ("lin_dst.bias", (D,), None),
                  ("lin_final.weight", (1, D), D), ("lin_final.bias", (1,), None)]
+        self._table = table
         self.off: Dict[str, int] = {}
         self.ld: Dict[str, int] = {}
         o = 0
@@ -368,6 +369,111 @@ class TGNEngine:
                 self.last_update.zero_()
                 self.memory[:own.shape[0]].copy_(own)
                 self.last_update[:own.shape[0]].copy_(memory_sd["last_update"].to(self.dev)[self.rank::self.world])
+
+    # ---- the drop-in modules as the owners of the state (epoch_utils.train on the engine)
+    def attach_modules(self, memory_module, neighbor_loader):
+        """Makes the engine step ON the drop-in modules' own state tensors instead of private copies:
+        TGNMemory.memory / last_update / message store and LastNeighborLoader.neighbors / e_id / t / _assoc.
+        After an engine epoch the modules therefore ARE in the state the reference's loop would have left
+        them in (memory in train mode with its messages pending, memory_module.py:126-138) -- no copy, no
+        flush; `memory.eval()` then flushes through the module's own code path.  Single GPU, before the
+        first step."""
+        if self.world != 1 or self._graphs or self._shared_with is not None:
+            raise _cabi.TgnError("attach_modules: single-GPU engines only, before the first step")
+        m, nl = memory_module, neighbor_loader
+        ok = (m.memory.is_cuda and m.memory.is_contiguous() and tuple(m.memory.shape) == (self.N, self.D) and
+              m.memory.dtype == torch.float32 and tuple(nl.neighbors.shape) == (self.N, self.K) and
+              nl.t.dtype == torch.float32 and nl.e_id.dtype == torch.long)
+        if not ok:
+            raise _cabi.TgnError("attach_modules: module state does not match the engine's shapes / dtypes")
+        st = m.store
+        if st.t_dtype != torch.int64:
+            st._set_t_dtype(torch.empty(0, dtype=torch.long))
+        self.memory, self.last_update = m.memory.detach(), m.last_update
+        self.neighbors, self.e_id, self.t_ring, self.assoc = nl.neighbors, nl.e_id, nl.t, nl._assoc
+        self.store = st
+        self._attached = (m, nl)
+
+    def begin_epoch_on_modules(self):
+        """Cursors to the start of an epoch whose state tensors the modules have just reset
+        (memory.reset_state(), neighbor_loader.reset_state(): pyg_epoch_utils.py:15-16)."""
+        m, nl = self._attached
+        self.cur_e_id_dev.fill_(int(nl.cur_e_id))
+        self.log_base_dev.fill_(int(m.store.size))
+        self.pos_dev.zero_()
+        self.events_done, self.ring_pos = int(m.store.size), int(nl.cur_e_id)
+        self._primed = None
+
+    def end_epoch_on_modules(self):
+        m, nl = self._attached
+        self._unprime()
+        m.store.size = self.events_done
+        nl.cur_e_id = self.ring_pos
+
+    def _flat_named(self, flat: Tensor):
+        return {name: self._view(flat, name, shp) for name, shp, _ in self._table}
+
+    def _copy_in(self, views, mem_sd, gnn_sd, lp_sd):
+        g = lambda sd, k: sd[k].to(self.dev, torch.float32)
+        with torch.no_grad():
+            for k in ("time_enc.lin.weight", "time_enc.lin.bias", "memory_updater.weight_ih",
+                      "memory_updater.weight_hh", "memory_updater.bias_ih", "memory_updater.bias_hh"):
+                views[k].copy_(g(mem_sd, k).view(views[k].shape))
+            views["conv.w_node"].copy_(torch.cat([g(gnn_sd, f"conv.lin_{n}.weight") for n in ("query", "key", "value", "skip")]))
+            views["conv.b_node"].copy_(torch.cat([g(gnn_sd, f"conv.lin_{n}.bias") for n in ("query", "key", "value", "skip")]))
+            views["conv.lin_edge.weight"].copy_(g(gnn_sd, "conv.lin_edge.weight"))
+            for k in ("lin_src.weight", "lin_src.bias", "lin_dst.weight", "lin_dst.bias", "lin_final.weight", "lin_final.bias"):
+                views[k].copy_(g(lp_sd, k).view(views[k].shape))
+
+    def _copy_out(self, views, mem_t, gnn_t, lp_t):
+        """inverse of _copy_in: writes the flat views into the tensors of three name->tensor dicts"""
+        HC = self.HC
+        with torch.no_grad():
+            for k in ("time_enc.lin.weight", "time_enc.lin.bias", "memory_updater.weight_ih",
+                      "memory_updater.weight_hh", "memory_updater.bias_ih", "memory_updater.bias_hh"):
+                mem_t[k].copy_(views[k].view(mem_t[k].shape))
+            for i, n in enumerate(("query", "key", "value", "skip")):
+                gnn_t[f"conv.lin_{n}.weight"].copy_(views["conv.w_node"][i * HC:(i + 1) * HC])
+                gnn_t[f"conv.lin_{n}.bias"].copy_(views["conv.b_node"][i * HC:(i + 1) * HC])
+            gnn_t["conv.lin_edge.weight"].copy_(views["conv.lin_edge.weight"])
+            for k in ("lin_src.weight", "lin_src.bias", "lin_dst.weight", "lin_dst.bias", "lin_final.weight", "lin_final.bias"):
+                lp_t[k].copy_(views[k].view(lp_t[k].shape))
+
+    def sync_from_modules(self, model, optimizer=None):
+        """weights (and, when the optimizer has stepped before, torch.optim.Adam's moments and step count)
+        of the module triple -> the engine's flat buffers"""
+        named = [dict(model[k].named_parameters()) for k in ("memory", "gnn", "link_pred")]
+        self._copy_in(self._flat_named(self.flat), *named)
+        if optimizer is None:
+            return
+        params = [p for d in named for p in d.values()]
+        if not all(p in optimizer.state and "exp_avg" in optimizer.state[p] for p in params):
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
+            self.adam_step_dev.zero_()
+            return
+        for key, flat in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+            self._copy_in(self._flat_named(flat), *[{n: optimizer.state[p][key] for n, p in d.items()} for d in named])
+        self.adam_step_dev.fill_(float(optimizer.state[params[0]]["step"]))
+
+    def sync_to_modules(self, model, optimizer=None):
+        named = [dict(model[k].named_parameters()) for k in ("memory", "gnn", "link_pred")]
+        self._copy_out(self._flat_named(self.flat), *named)
+        if optimizer is None:
+            return
+        step = float(self.adam_step_dev)
+        for d in named:
+            for p in d.values():
+                st = optimizer.state[p]
+                if "exp_avg" not in st:
+                    st["step"] = torch.tensor(0.0)
+                    st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(p), torch.zeros_like(p)
+                if torch.is_tensor(st["step"]):
+                    st["step"].fill_(step)
+                else:
+                    st["step"] = step
+        for key, flat in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+            self._copy_out(self._flat_named(flat), *[{n: optimizer.state[p][key] for n, p in d.items()} for d in named])
 
     def export_state(self):
         HC = self.HC

@@ -584,6 +584,17 @@ int32_t tgn_neg_fill(const int64_t* pos_dst, int32_t batch, int32_t num_neg, int
 int32_t tgn_rank_accum(const int32_t* gt, const int32_t* ge, int32_t batch, double* acc, float* rr_out,
                        void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Dependency-aware block ids (dependencyGraph.py:8-28 get_block, :33-49 dependecyAwareBatch): the event
+ * stream is cut into consecutive batches of `batch` events (the DataLoader's, utils.py:52-54); inside a
+ * batch, walking in order, block_ids[i] = 1 + the highest block id already given to either endpoint of
+ * event i in this batch (0 if neither was seen).  One CTA per batch (shared-memory sort of the 2*batch
+ * endpoint keys, then relaxation of the <= 2-predecessor recurrence).  num_blocks (nullable) gets the
+ * number of blocks per batch [ceil(num_events / batch)].  2*batch <= TGN_SORT_MAX; node ids in [0, 2^42).
+ * ------------------------------------------------------------------------- */
+int32_t tgn_dep_blocks(const int64_t* src, const int64_t* dst, int64_t num_events, int32_t batch,
+                       int32_t* block_ids, int32_t* num_blocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,7 +114,7 @@ def _train_engine(model, train_loader, neighbor_loader, neg_dest_sampler, device
     eng, tail_eng = _ENGINES[key]
     if eng.lr != lr:                # the captured graphs hold the learning rate by value
         eng.lr = lr
-        eng._graphs = {}
+        eng._drop_graphs()
         if tail_eng is not None:
             tail_eng.lr = lr
     eng.sync_from_modules(model, optimizer)

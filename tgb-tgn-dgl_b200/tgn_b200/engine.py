@@ -204,6 +204,7 @@ class TGNEngine:
         self.loss = self._loss_views[0]                                        # slot comes round again)
         self.bounds = (R, E, Nb)
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._graph_store_gen = None      # generation of the message-store log the captured graphs point into
         self.training = True
         self.fused_decoder = _L().tgn_dec_fused_smem_bytes(hidden) <= 215 * 1024 and hidden <= 128
         self.fused_gru = hidden % 4 == 0    # tgn_gru_fused_fwd (TMA strides need 16-byte rows)
@@ -230,16 +231,25 @@ class TGNEngine:
     def _grow_log(self, need: int):
         """Re-allocates the message-store log.  Captured graphs hold the old ev_* / perm pointers BY VALUE, so
         every graph (of this engine and of the engines sharing its state) is dropped and re-captured."""
-        torch.cuda.synchronize()
         self.store._alloc_log(int(need))
+        self._drop_graphs()
+
+    def _drop_graphs(self):
+        """Forgets every captured graph of this engine and of the engines sharing its state (they hold device
+        addresses and scalars by value); the next calls run eagerly and re-capture."""
+        torch.cuda.synchronize()
         for e in self._family():
             e._graphs = {}
+            e._graph_store_gen = None
 
     def _reserve(self, n_events: int):
         """Host-side guard in front of every replay: the log has room for the events about to be appended
         (the kernel would drop them and raise TGN_DEVERR_LOG_OVERFLOW), and the resident event arrays cover
         every e_id the ring is about to hand out (edge features are events['msg'][e_id], epoch_utils.py:224)."""
         self.check_device_errors()
+        if any(e._graph_store_gen not in (None, self.store.generation) for e in self._family()):
+            # the log arrays moved behind the engine's back (a module-path update_state grew the shared store)
+            self._drop_graphs()
         if self.events_done + n_events > self.store.capacity:
             self._grow_log(max(2 * self.store.capacity, self.events_done + n_events))
         if self.events is not None and self.ring_pos + n_events > self.events["src"].numel():
@@ -538,9 +548,7 @@ class TGNEngine:
                     old[k].copy_(v)
             return
         if old is not None:               # different arrays: the graphs hold the old pointers
-            torch.cuda.synchronize()
-            for e in self._family():
-                e._graphs = {}
+            self._drop_graphs()
         self.events = dict(src=src.to(dev, torch.long).contiguous(), dst=dst.to(dev, torch.long).contiguous(),
                            t=t.to(dev, torch.long).contiguous(), msg=msg.to(dev, torch.float32).contiguous(),
                            neg=None if neg is None else neg.to(dev, torch.long).contiguous())
@@ -956,6 +964,7 @@ class TGNEngine:
                 return
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
+            self._graph_store_gen = self.store.generation
             with torch.cuda.graph(g):
                 body()
             self._graphs[key] = g

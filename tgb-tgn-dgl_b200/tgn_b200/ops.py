@@ -258,6 +258,18 @@ def agg_mean(msg: Tensor, index: Tensor, dim_size: int) -> Tensor:
     return out
 
 
+def dep_blocks(src: Tensor, dst: Tensor, batch: int, want_counts: bool = False):
+    """dependencyGraph.get_block for every consecutive batch of `batch` events of the stream (src, dst) in
+    one launch; returns int32 block ids [E] (and the number of blocks per batch)."""
+    src, dst = _need(src, torch.int64, "src"), _need(dst, torch.int64, "dst")
+    E = src.numel()
+    out = torch.empty(E, dtype=torch.int32, device=src.device)
+    nb = (E + batch - 1) // batch
+    cnt = torch.empty(nb, dtype=torch.int32, device=src.device) if want_counts else None
+    check(_L().tgn_dep_blocks(_p(src), _p(dst), E, int(batch), _p(out), _p(cnt), _stream()))
+    return (out, cnt) if want_counts else out
+
+
 # ---------------------------------------------------------------------------
 # message store
 # ---------------------------------------------------------------------------
@@ -296,6 +308,9 @@ class MsgStore:
         self.s_perm, self.d_perm = s_perm, d_perm
         self.capacity = capacity
         self._struct = None
+        # bumped whenever the log arrays move: whoever baked their addresses into a captured CUDA graph
+        # (tgn_b200.engine) compares it before a replay
+        self.generation = getattr(self, "generation", 0) + 1
 
     def struct(self) -> _cabi.MsgStoreStruct:
         if self._struct is None:
@@ -316,6 +331,7 @@ class MsgStore:
             self.t_dtype = t.dtype
             self.ev_t = torch.empty(self.capacity, dtype=t.dtype, device=self.device)
             self._struct = None
+            self.generation += 1
 
     def reset(self):
         self.size = 0

@@ -1114,6 +1114,7 @@ class TGNEngine:
             return None
         i, G = (self._gl_n - 1) & 1, self.group_size
         self._gl_ev[i].synchronize()
+        self._gl_n = 0
         return self._gl_pin[G * i: G * i + G].tolist()
 
     def train_step_logged(self, **kw) -> Optional[float]:
@@ -1147,6 +1148,7 @@ class TGNEngine:
             return None
         i = (self._loss_n - 1) & 1
         self._loss_ev[i].synchronize()
+        self._loss_n = 0        # the log is drained: the next train_step_logged() starts a fresh lag (returns None)
         return float(self._loss_pin[i])
 
     # ------------------------------------------------------------------ evaluation

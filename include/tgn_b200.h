@@ -585,6 +585,26 @@ int32_t tgn_rank_accum(const int32_t* gt, const int32_t* ge, int32_t batch, doub
                        void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * EdgeGATConv attention core of the reference's live DGL stack (model_utils.py:565-612).
+ * Per head: el'_e = el[src(e)] + ee[e] (:594), z_e = LeakyReLU(el'_e + er[dst(e)]) (:595-596),
+ * a = edge_softmax by destination then attention dropout (:597), s[v] = sum_e a_e * el'_e (:560-563,599 --
+ * the reference aggregates the LOGIT part el_prime, a scalar per head, not the projected features).
+ * el/er [N,H] and ee [E,H] are the attn_l/attn_r/attn_e-weighted projections (:587-589), which the
+ * caller folds into skinny weights.  Edges are addressed through a CSR by destination: row_ptr [N+1]
+ * and edge_perm [E] (nullable = edges already grouped); src [E] by edge id.  alpha_out [E,H] keeps the
+ * softmax weights before dropout; the dropout mask is Philox(seed; edge, head) in both passes.
+ * Backward: d_el must be zero-filled (atomic accumulation over sources).
+ * ------------------------------------------------------------------------- */
+int32_t tgn_egat_attn_fwd(const float* el, const float* er, const float* ee, const int32_t* row_ptr,
+                          const int32_t* edge_perm, const int64_t* src, int32_t num_nodes, int32_t num_edges,
+                          int32_t heads, float negative_slope, float dropout_p, uint64_t seed, float* s_out,
+                          float* alpha_out, void* stream);
+int32_t tgn_egat_attn_bwd(const float* el, const float* er, const float* ee, const int32_t* row_ptr,
+                          const int32_t* edge_perm, const int64_t* src, int32_t num_nodes, int32_t num_edges,
+                          int32_t heads, float negative_slope, float dropout_p, uint64_t seed, const float* alpha,
+                          const float* d_s, float* d_el, float* d_er, float* d_ee, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Dependency-aware block ids (dependencyGraph.py:8-28 get_block, :33-49 dependecyAwareBatch): the event
  * stream is cut into consecutive batches of `batch` events (the DataLoader's, utils.py:52-54); inside a
  * batch, walking in order, block_ids[i] = 1 + the highest block id already given to either endpoint of

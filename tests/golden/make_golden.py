@@ -291,6 +291,74 @@ def gen_callers(path):
     np.savez_compressed(path, **out)
 
 
+def gen_dgl_twins(path):
+    """The DGL-flavoured twins from the UNMODIFIED reference model_utils.py, imported on top of
+    tests/dgl_standin (minimal `dgl`): TimeEncode, TemporalEdgePreprocess, EdgeGATConv, TemporalTransformerConv
+    (eval mode: its 0.6 dropouts are identities; gradients by autograd), MemoryOperation (gru and rnn),
+    EdgePredictor.  Inputs, parameters, outputs and gradients are frozen."""
+    sys.path.insert(0, os.path.join(REPO, "tests", "dgl_standin"))
+    import warnings
+    warnings.simplefilter("ignore")
+    import dgl
+    mu = importlib.import_module("model_utils")
+    out = {}
+    g_ = torch.Generator().manual_seed(41)
+    cases = [dict(N=12, E=30, De=5, D=8, H=4), dict(N=40, E=300, De=172, D=100, H=8), dict(N=9, E=0, De=3, D=8, H=2),
+             dict(N=30, E=90, De=1, D=16, H=8)]
+    out["num_cases"] = np.int64(len(cases))
+    for c, cfg in enumerate(cases):
+        N, E, De, D, H = cfg["N"], cfg["E"], cfg["De"], cfg["D"], cfg["H"]
+        torch.manual_seed(100 + c)
+        te = mu.TimeEncode(D)
+        conv = mu.TemporalTransformerConv(De, D, te, D, H, allow_zero_in_degree=True).eval()
+        src = torch.randint(0, N, (E,), generator=g_); dst = torch.randint(0, max(N - 3, 1), (E,), generator=g_)
+        node_ts = (torch.rand(N, 1, generator=g_) * 1000).floor()
+        edge_ts = (torch.rand(E, 1, generator=g_) * 1000).floor() + 1000
+        feats = torch.randn(E, De, generator=g_)
+        mem = torch.randn(N, D, generator=g_)
+        g = dgl.graph((src, dst), num_nodes=N)
+        g.ndata["timestamp"], g.edata["timestamp"], g.edata["feats"] = node_ts, edge_ts, feats
+        efeat = conv.preprocessor(g.local_var())
+        rst = conv(g, mem)
+        w = torch.randn_like(rst)
+        (rst * w).sum().backward()
+        pre = f"c{c}_"
+        for k, v in dict(src=src, dst=dst, node_ts=node_ts, edge_ts=edge_ts, feats=feats, mem=mem, efeat=efeat,
+                         out=rst, out_w=w).items():
+            out[pre + k] = v.detach().numpy().copy()
+        out[pre + "cfg"] = np.asarray([N, E, De, D, H], np.int64)
+        for k, v in conv.state_dict().items():
+            out[pre + "p." + k] = v.detach().numpy().copy()
+        for k, v in conv.named_parameters():
+            out[pre + "g." + k] = (v.grad if v.grad is not None else torch.zeros_like(v)).detach().numpy().copy()
+        # MemoryOperation on the same graph (it is defined but never instantiated by the reference, SURVEY 0.2)
+        for cell in ("gru", "rnn"):
+            torch.manual_seed(200 + c)
+            mm = mu.MemoryModule(N, D)
+            mm.memory.data.copy_(mem)
+            mm.last_update_t.data.copy_(node_ts.view(-1))
+            mo = mu.MemoryOperation(cell, mm, De, te)
+            g2 = dgl.graph((src, dst), num_nodes=N)
+            g2.ndata[dgl.NID] = torch.arange(N)
+            g2.edata["timestamp"], g2.edata["feats"] = edge_ts.view(-1), feats
+            if E:
+                res = mo(g2)
+                out[pre + f"mo_{cell}_memory"] = res.ndata["memory"].detach().numpy().copy()
+                out[pre + f"mo_{cell}_ts"] = res.ndata["timestamp"].detach().numpy().copy()
+            for k, v in mo.updater.state_dict().items():
+                out[pre + f"mo_{cell}.{k}"] = v.detach().numpy().copy()
+    # EdgePredictor (model_utils.py:165-195), incl. the tile() pairing of several negatives per positive
+    torch.manual_seed(7)
+    ep = mu.EdgePredictor(16, 16)
+    hs, hp, hn = torch.randn(5, 16, generator=g_), torch.randn(5, 16, generator=g_), torch.randn(15, 16, generator=g_)
+    pos, neg = ep(hs, hp, hn, neg_samples=3)
+    for k, v in dict(hs=hs, hp=hp, hn=hn, pos=pos, neg=neg).items():
+        out["ep_" + k] = v.detach().numpy().copy()
+    for k, v in ep.state_dict().items():
+        out["ep_p." + k] = v.detach().numpy().copy()
+    np.savez_compressed(path, **out)
+
+
 def vendor_driver(path):
     """The reference's CLI driver, byte for byte, as a DATA fixture (`.txt`, never imported from here):
     tests/test_gpu_unchanged_driver.py copies it to a scratch directory as pyg-mem-tgn.py and runs it
@@ -311,6 +379,7 @@ if __name__ == "__main__":
     gen_callers(os.path.join(HERE, "callers.npz"))
     gen_variants(os.path.join(HERE, "variants.npz"))
     vendor_driver(os.path.join(HERE, "ref_driver_pyg-mem-tgn.py.txt"))
+    gen_dgl_twins(os.path.join(HERE, "dgl_twins.npz"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

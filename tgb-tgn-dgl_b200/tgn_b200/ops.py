@@ -797,6 +797,46 @@ def temporal_attention(x: Tensor, w_node: Tensor, b_node: Tensor, w_edge: Tensor
                          centre_ids, heads, dropout_p, seed, counts)
 
 
+class _EgatFn(torch.autograd.Function):
+    """EdgeGATConv attention core (model_utils.py:594-599) on csrc/egat.cu: s[v,h] = sum_e a_e * (el[src]+ee)."""
+
+    @staticmethod
+    def forward(ctx, el, er, ee, src, row_ptr, perm, slope, p, seed):
+        N, H = el.shape
+        E = ee.shape[0]
+        s = torch.empty((N, H), dtype=torch.float32, device=el.device)
+        alpha = torch.empty((E, H), dtype=torch.float32, device=el.device)
+        check(_L().tgn_egat_attn_fwd(_p(el), _p(er), _p(ee), _p(row_ptr), _p(perm), _p(src), N, E, H, float(slope),
+                                     float(p), int(seed), _p(s), _p(alpha), _stream()))
+        ctx.save_for_backward(el, er, ee, src, row_ptr, perm, alpha)
+        ctx.cfg = (float(slope), float(p), int(seed))
+        ctx.mark_non_differentiable(alpha)
+        return s, alpha
+
+    @staticmethod
+    def backward(ctx, d_s, _d_alpha):
+        el, er, ee, src, row_ptr, perm, alpha = ctx.saved_tensors
+        slope, p, seed = ctx.cfg
+        N, H = el.shape
+        E = ee.shape[0]
+        d_el = torch.zeros_like(el)
+        d_er, d_ee = torch.empty_like(er), torch.empty_like(ee)
+        check(_L().tgn_egat_attn_bwd(_p(el), _p(er), _p(ee), _p(row_ptr), _p(perm), _p(src), N, E, H, slope, p, seed,
+                                     _p(alpha), _p(d_s.contiguous()), _p(d_el), _p(d_er), _p(d_ee), _stream()))
+        return d_el, d_er, d_ee, None, None, None, None, None, None
+
+
+def egat_attention(el: Tensor, er: Tensor, ee: Tensor, src: Tensor, dst: Tensor, negative_slope: float = 0.2,
+                   dropout_p: float = 0.0, seed: int = 0):
+    """(s [N,H], alpha [E,H]) of the reference's EdgeGATConv for logits el/er [N,H], ee [E,H] and the edge
+    list (src, dst) [E]; alpha is the softmax weight before dropout (what get_attention returns in eval)."""
+    N = el.shape[0]
+    src, dst = _need(src, torch.int64, "src"), _need(dst, torch.int64, "dst")
+    row_ptr, perm = group_edges_by_centre(dst, N)
+    return _EgatFn.apply(el.contiguous().float(), er.contiguous().float(), ee.contiguous().float(), src, row_ptr,
+                         perm.contiguous(), negative_slope, dropout_p, seed)
+
+
 def group_edges_by_centre(centre_local: Tensor, num_rows: int):
     """CSR over centres for an arbitrary edge list: returns (row_ptr[num_rows+1], edge_perm[E]).
     A stable counting sort -- plumbing for callers that hand GraphAttentionEmbedding an

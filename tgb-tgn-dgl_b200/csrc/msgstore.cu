@@ -74,34 +74,47 @@ __device__ void store_direction(const int64_t* __restrict__ key_nodes, const T* 
   __syncthreads();
 }
 
+// grid = 2 + copy CTAs: CTA 0 indexes the batch by source, CTA 1 by destination (each with its own
+// shared-memory sort), the others append the batch to the event log.  All of them read the log position
+// at the start; it is advanced by a one-thread kernel behind this one (stream order).
 template <typename T>
 __global__ void __launch_bounds__(1024, 1)
     msgstore_update_kernel(tgn_msgstore st, const int64_t* __restrict__ src,
                            const int64_t* __restrict__ dst, const T* __restrict__ t,
                            const float* __restrict__ raw, int B, int P, int64_t base_host,
-                           int64_t* __restrict__ base_dev, int32_t* err) {
+                           const int64_t* __restrict__ base_dev, int32_t* err) {
   pdl_wait();
   pdl_launch();
   extern __shared__ unsigned long long s_key[];
   const int64_t base = base_dev ? *base_dev : base_host;
   if (base + B > st.capacity) {  // caller sizes the log; never write out of bounds -- but say so
-    if (threadIdx.x == 0) flag_dev_err(err, TGN_DEVERR_LOG_OVERFLOW);
+    if (threadIdx.x == 0 && blockIdx.x == 0) flag_dev_err(err, TGN_DEVERR_LOG_OVERFLOW);
     return;
   }
+  if (blockIdx.x == 0) {
+    store_direction<T>(src, t, B, P, base, st.num_nodes, s_key, st.s_perm, st.s_start, st.s_cnt, st.s_last);
+    return;
+  }
+  if (blockIdx.x == 1) {
+    store_direction<T>(dst, t, B, P, base, st.num_nodes, s_key, st.d_perm, st.d_start, st.d_cnt, st.d_last);
+    return;
+  }
+  const int nc = gridDim.x - 2, c = blockIdx.x - 2;
   T* ev_t = reinterpret_cast<T*>(st.ev_t);
-  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+  for (int i = c * blockDim.x + threadIdx.x; i < B; i += nc * blockDim.x) {
     st.ev_src[base + i] = src[i];
     st.ev_dst[base + i] = dst[i];
     ev_t[base + i] = t[i];
   }
   const long long nraw = (long long)B * st.raw_dim;
   float* dm = st.ev_msg + base * st.raw_dim;
-  for (long long i = threadIdx.x; i < nraw; i += blockDim.x) dm[i] = raw[i];
-  store_direction<T>(src, t, B, P, base, st.num_nodes, s_key, st.s_perm, st.s_start, st.s_cnt,
-                     st.s_last);
-  store_direction<T>(dst, t, B, P, base, st.num_nodes, s_key, st.d_perm, st.d_start, st.d_cnt,
-                     st.d_last);
-  if (base_dev && threadIdx.x == 0) *base_dev = base + B;
+  for (long long i = (long long)c * blockDim.x + threadIdx.x; i < nraw; i += (long long)nc * blockDim.x) dm[i] = raw[i];
+}
+
+__global__ void msgstore_advance_kernel(int64_t* p, int64_t by, int64_t capacity) {
+  pdl_wait();
+  pdl_launch();
+  if (*p + by <= capacity) *p += by;   // an overflowing batch was dropped (and flagged) by the update kernel
 }
 
 __global__ void msgstore_reset_kernel(tgn_msgstore st) {
@@ -358,13 +371,20 @@ int32_t tgn_msgstore_update(const tgn_msgstore* st, const int64_t* src, const in
   TGN_CUDA(smem_optin(msgstore_update_kernel<int64_t>, TGN_SORT_MAX * 8, mi));
   TGN_CUDA(smem_optin(msgstore_update_kernel<float>, TGN_SORT_MAX * 8, mf));
   cudaStream_t s = (cudaStream_t)stream;
+  const long long copy_items = (long long)batch * (st->raw_dim > 3 ? st->raw_dim : 3);
+  int copy_ctas = (int)((copy_items + 8191) / 8192);
+  copy_ctas = copy_ctas < 1 ? 1 : (copy_ctas > 30 ? 30 : copy_ctas);
   if (st->t_is_float)
-    launch_k(msgstore_update_kernel<float>, dim3(1), dim3(1024), (size_t)P * 8, s, 
-        *st, src, dst, (const float*)t, raw_msg, batch, P, base, base_dev, dev_err_word());
+    launch_k(msgstore_update_kernel<float>, dim3(2 + copy_ctas), dim3(1024), (size_t)P * 8, s,
+        *st, src, dst, (const float*)t, raw_msg, batch, P, base, (const int64_t*)base_dev, dev_err_word());
   else
-    launch_k(msgstore_update_kernel<int64_t>, dim3(1), dim3(1024), (size_t)P * 8, s, 
-        *st, src, dst, (const int64_t*)t, raw_msg, batch, P, base, base_dev, dev_err_word());
+    launch_k(msgstore_update_kernel<int64_t>, dim3(2 + copy_ctas), dim3(1024), (size_t)P * 8, s,
+        *st, src, dst, (const int64_t*)t, raw_msg, batch, P, base, (const int64_t*)base_dev, dev_err_word());
   TGN_LAUNCH_CHECK();
+  if (base_dev) {
+    launch_k(msgstore_advance_kernel, dim3(1), dim3(1), 0, s, base_dev, (int64_t)batch, (int64_t)st->capacity);
+    TGN_LAUNCH_CHECK();
+  }
   return TGN_OK;
 }
 

@@ -135,10 +135,94 @@ __device__ __forceinline__ void block_bitonic_sort(unsigned long long* s, int P)
   }
 }
 
+// Merge of one node's run into its ring row by ONE WARP (K <= 32): lane i holds old slot i and the
+// i-th newest entry of the run.  Every candidate computes its rank among all candidates with shuffles
+// (descending value, ties to the lower candidate index: old slots before new entries, exactly the order
+// a stable top-k of cat[old row, dense new block] yields, neighbor_loader.py:91-104) and writes itself
+// to slot `rank` if rank < K.  e_id and t are ranked independently (neighbor_loader.py:99-100); the
+// dense block's -1 padding (neighbor_loader.py:77-82) takes part in the t ranking.
+__device__ __forceinline__ void insert_merge_warp(const unsigned long long* __restrict__ s_key, int q,
+                                                  int64_t node, int B, int K, int64_t cur,
+                                                  const int64_t* __restrict__ src,
+                                                  const int64_t* __restrict__ dst,
+                                                  const float* __restrict__ t,
+                                                  int64_t* __restrict__ nbrs, int64_t* __restrict__ eids,
+                                                  float* __restrict__ ts) {
+  const int lane = threadIdx.x & 31;
+  // run length (capped at K): entries q, q-1, ... with the same node
+  int taken = 0;
+  {
+    const bool mine = lane < K && q - lane >= 0 && (int64_t)(s_key[q - lane] >> 16) == node;
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    taken = __ffs(~m) - 1;              // number of leading set bits (contiguous run)
+    if (taken < 0 || taken > K) taken = K;
+  }
+  const bool has_old = lane < K, has_new = lane < taken;
+  int64_t oe = -1, on = 0, ne = -1, nn = 0;
+  float ot = -1.f, nt = -1.f;
+  if (has_old) {
+    oe = eids[node * K + lane];
+    on = nbrs[node * K + lane];
+    ot = ts[node * K + lane];
+  }
+  if (has_new) {
+    const int j = (int)(s_key[q - lane] & 0xffffu);
+    const int ev = j < B ? j : j - B;
+    ne = cur + ev;
+    nn = j < B ? src[ev] : dst[ev];
+    nt = t[ev];
+  }
+  // candidate index: old slot i -> i, new entry i -> K + i  (the dense block lists the run in sorted order,
+  // i.e. new entry `taken-1-i` comes first; ties between new entries only occur for identical duplicates)
+  int r_oe = 0, r_ne = 0, r_ot = 0, r_nt = 0, cnt_ge = 0;
+  for (int i = 0; i < 32; ++i) {
+    const int64_t xe = __shfl_sync(0xffffffffu, oe, i), ye = __shfl_sync(0xffffffffu, ne, i);
+    const float xt = __shfl_sync(0xffffffffu, ot, i), yt = __shfl_sync(0xffffffffu, nt, i);
+    const bool vo = i < K, vn = i < taken;
+    // e_id ranks
+    if (vo) {
+      r_oe += (xe > oe) || (xe == oe && i < lane);
+      r_ne += (xe >= ne);                                   // an old slot precedes every new entry on ties
+    }
+    if (vn) {
+      r_oe += (ye > oe);
+      r_ne += (ye > ne) || (ye == ne && i > lane);          // dense order: older run position (higher i) first
+    }
+    // t ranks
+    if (vo) {
+      r_ot += (xt > ot) || (xt == ot && i < lane);
+      r_nt += (xt >= nt);
+      cnt_ge += (xt >= -1.f);
+    }
+    if (vn) {
+      r_ot += (yt > ot);
+      r_nt += (yt > nt) || (yt == nt && i > lane);
+      cnt_ge += (yt >= -1.f);
+    }
+  }
+  const int n_fill = K - taken;          // -1 padding of the dense block: after old and new on ties
+  if (ot < -1.f) r_ot += n_fill;
+  if (nt < -1.f) r_nt += n_fill;
+  __syncwarp();
+  if (has_old && r_oe < K) {
+    eids[node * K + r_oe] = oe;
+    nbrs[node * K + r_oe] = on;
+  }
+  if (has_new && r_ne < K) {
+    eids[node * K + r_ne] = ne;
+    nbrs[node * K + r_ne] = nn;
+  }
+  if (has_old && r_ot < K) ts[node * K + r_ot] = ot;
+  if (has_new && r_nt < K) ts[node * K + r_nt] = nt;
+  if (lane < n_fill && cnt_ge + lane < K) ts[node * K + cnt_ge + lane] = -1.f;
+}
+
+// Several CTAs: each sorts the 2B keys in its own shared memory (a few microseconds; cheaper than a grid
+// barrier) and merges a strided share of the node runs, one warp per run.
 __global__ void __launch_bounds__(1024, 1)
     nbr_insert_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                       const float* __restrict__ t, int B, int P, int64_t cur_host,
-                      int64_t* __restrict__ cur_dev, int K, int64_t num_nodes,
+                      const int64_t* __restrict__ cur_dev, int K, int64_t num_nodes,
                       int64_t* __restrict__ nbrs, int64_t* __restrict__ eids,
                       float* __restrict__ ts) {
   pdl_wait();
@@ -157,12 +241,23 @@ __global__ void __launch_bounds__(1024, 1)
   }
   __syncthreads();
   block_bitonic_sort(s_key, P);
-  for (int q = threadIdx.x; q < n; q += blockDim.x) {
+  if (K <= 32) {
+    const int warps = blockDim.x >> 5;
+    for (int q = blockIdx.x * warps + (threadIdx.x >> 5); q < n; q += gridDim.x * warps) {
+      const unsigned long long key = s_key[q];
+      const int64_t node = (int64_t)(key >> 16);
+      const bool run_end = (q == n - 1) || ((int64_t)(s_key[q + 1] >> 16) != node);
+      if (!run_end || node < 0 || node >= num_nodes) continue;   // warp-uniform
+      insert_merge_warp(s_key, q, node, B, K, cur, src, dst, t, nbrs, eids, ts);
+    }
+    return;
+  }
+  // K > 32: one thread per run with local candidate arrays (rare configuration)
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
     const unsigned long long key = s_key[q];
     const int64_t node = (int64_t)(key >> 16);
     const bool run_end = (q == n - 1) || ((int64_t)(s_key[q + 1] >> 16) != node);
     if (!run_end || node < 0 || node >= num_nodes) continue;
-    // candidates: old row (K) + the last <=K entries of the run
     int64_t ce[2 * kMaxK], cn[2 * kMaxK];
     float ct[2 * kMaxK];
     int m = 0;
@@ -184,18 +279,14 @@ __global__ void __launch_bounds__(1024, 1)
       ++m;
       ++taken;
     }
-    // the dense [n,K] block of the reference is padded with -1 (neighbor_loader.py:77-82)
     const int n_fill = K - taken;
-    // top-K of e_id, descending (neighbor_loader.py:99) -- selection sort on the prefix
     for (int a = 0; a < K; ++a) {
       int best = a;
       for (int b = a + 1; b < m; ++b)
         if (ce[b] > ce[best]) best = b;
       int64_t te = ce[a]; ce[a] = ce[best]; ce[best] = te;
       int64_t tn = cn[a]; cn[a] = cn[best]; cn[best] = tn;
-      // t is ranked independently below, keep ct aligned with its own values only
     }
-    // top-K of t, descending, independent of e_id (neighbor_loader.py:100)
     float tt[3 * kMaxK];
     for (int a = 0; a < m; ++a) tt[a] = ct[a];
     int mt = m;
@@ -212,8 +303,13 @@ __global__ void __launch_bounds__(1024, 1)
       ts[node * K + s] = tt[s];
     }
   }
-  __syncthreads();
-  if (cur_dev && threadIdx.x == 0) *cur_dev = cur + B;
+}
+
+// the event counter moves after every CTA of the insert has read it (stream order)
+__global__ void advance_i64_kernel(int64_t* p, int64_t by) {
+  pdl_wait();
+  pdl_launch();
+  *p += by;
 }
 
 }  // namespace tgn
@@ -268,9 +364,16 @@ int32_t tgn_nbr_insert(const int64_t* src, const int64_t* dst, const float* t, i
   while (P < 2 * batch) P <<= 1;
   static unsigned long long attr_mask = 0;
   TGN_CUDA(smem_optin(nbr_insert_kernel, TGN_SORT_MAX * 8, attr_mask));
-  launch_k(nbr_insert_kernel, dim3(1), dim3(1024), (size_t)P * 8, (cudaStream_t)stream, 
-      src, dst, t, batch, P, cur_e_id, cur_e_id_dev, size_k, num_nodes, neighbors, e_id, t_state);
+  // one warp merges one node run: ~2B/3 runs on TGB-like streams; 32 warps per CTA
+  int grid = (2 * batch + 32 * 24 - 1) / (32 * 24);
+  grid = grid < 1 ? 1 : (grid > 16 ? 16 : grid);
+  launch_k(nbr_insert_kernel, dim3(grid), dim3(1024), (size_t)P * 8, (cudaStream_t)stream,
+      src, dst, t, batch, P, cur_e_id, (const int64_t*)cur_e_id_dev, size_k, num_nodes, neighbors, e_id, t_state);
   TGN_LAUNCH_CHECK();
+  if (cur_e_id_dev) {
+    launch_k(advance_i64_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, cur_e_id_dev, (int64_t)batch);
+    TGN_LAUNCH_CHECK();
+  }
   return TGN_OK;
 }
 

@@ -709,6 +709,13 @@ constexpr int kDecQ = kDecThreads / 128;
 // z_rows [3B,D] = [z_src; z_dst; z_neg] and the hidden-layer gradients g_rows [3B,D] = [gs; g0; g1]
 // instead, and the caller forms dW_src = gs^T z_src, dW_dst = [g0;g1]^T [z_dst;z_neg] as two small
 // tensor-core GEMMs off the dependent chain (no shared-memory accumulators, no 20k-atomic flush per CTA).
+constexpr int kDecEv = 4;          // events per pass (= kDecQ: the quarter index doubles as the event slot)
+constexpr int kDecVec = 3 * kDecEv;  // [row s|d|n][event] values per channel in the staged tiles
+
+// A pass handles kDecEv events.  Thread (c, q):
+//   GEMV phases     channel c, reduction quarter q, ALL kDecEv events at once: one weight load feeds
+//                   kDecEv (x3 rows) FMAs, the events' inputs come as three broadcast float4 loads;
+//   pointwise phases channel c of event slot q (bias, relu, final layer, loss gradient).
 template <bool kDefer>
 __global__ void __launch_bounds__(kDecThreads)
     dec_fused_kernel(const float* __restrict__ emb, const int64_t* __restrict__ ids_l, int B, int D,
@@ -721,18 +728,17 @@ __global__ void __launch_bounds__(kDecThreads)
                      float* __restrict__ z_rows, float* __restrict__ g_rows) {
   pdl_wait();
   pdl_launch();
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int ld = D + 1;
-  float* sWs = sm;
+  float* sz = sm;                        // [D][kDecVec] inputs      (16-byte aligned rows)
+  float* sg = sz + D * kDecVec;          // [D][kDecVec] hidden-layer gradients
+  float* sWs = sg + D * kDecVec;
   float* sWd = sWs + D * ld;
   float* sAs = sWd + D * ld;   // dWs accumulator (absent with kDefer)
   float* sAd = sAs + D * ld;   // dWd accumulator (absent with kDefer)
-  float* sz = kDefer ? sWd + D * ld : sAd + D * ld;    // [3][D] z_src, z_dst, z_neg
-  float* sg = sz + 3 * D;      // [3][D] dhs, g0, g1
-  __shared__ float s_p[3][kDecQ][128];  // partial sums of the quarters
-  __shared__ float s_h[2][128];
-  __shared__ float s_part[2][4];
-  __shared__ float s_logit[2];
+  __shared__ float s_p[kDecVec][kDecQ][128];  // partial sums of the quarters
+  __shared__ float s_part[kDecEv][2][4];
+  __shared__ int64_t s_row[kDecEv][3];
   const int tid = threadIdx.x, lane = tid & 31;
   const int c = tid & 127, q = tid >> 7;
   const int per = (D + kDecQ - 1) / kDecQ;
@@ -748,139 +754,161 @@ __global__ void __launch_bounds__(kDecThreads)
   }
   const float invB = 1.f / (float)B;
   const float bfv = bf[0];
-  float loss_acc = 0.f, dbf_acc = 0.f;
-  for (int ev = blockIdx.x; ev < B; ev += gridDim.x) {
-    const int64_t rs = ids_l[ev], rd = ids_l[B + ev], rn = ids_l[2 * B + ev];
-    __syncthreads();  // weights staged / previous event fully consumed
-    for (int k = tid; k < D; k += kDecThreads) {
-      const float a = emb[rs * D + k], b = emb[rd * D + k], c2 = emb[rn * D + k];
-      sz[k] = a;
-      sz[D + k] = b;
-      sz[2 * D + k] = c2;
-      if (kDefer) {
-        z_rows[(long long)ev * D + k] = a;
-        z_rows[(long long)(B + ev) * D + k] = b;
-        z_rows[(long long)(2 * B + ev) * D + k] = c2;
-      }
+  float loss_acc = 0.f, dbf_acc = 0.f, dwf_acc = 0.f, dbs_acc = 0.f;
+  const int npass = (B + kDecEv - 1) / kDecEv;
+  for (int pass = blockIdx.x; pass < npass; pass += gridDim.x) {
+    const int e0 = pass * kDecEv;
+    __syncthreads();  // weights staged / previous pass fully consumed
+    if (tid < kDecVec) {
+      const int row = tid / kDecEv, slot = tid - row * kDecEv;
+      s_row[slot][row] = e0 + slot < B ? ids_l[row * B + e0 + slot] : -1;
     }
     __syncthreads();
-    // ---- forward partials: output channel c, inputs [k0, k1)
+    for (int i = tid; i < kDecVec * D; i += kDecThreads) {
+      const int v = i / D, k = i - v * D;           // v = row * kDecEv + slot
+      const int row = v / kDecEv, slot = v - row * kDecEv;
+      const int64_t r = s_row[slot][row];
+      const float x = r >= 0 ? emb[r * D + k] : 0.f;
+      sz[k * kDecVec + v] = x;
+      if (kDefer && r >= 0) z_rows[((long long)row * B + e0 + slot) * D + k] = x;
+    }
+    __syncthreads();
+    // ---- forward partials: output channel c, inputs [k0, k1), all events of the pass
     {
-      float hs = 0.f, hp = 0.f, hn = 0.f;
+      float hs[kDecEv] = {}, hp[kDecEv] = {}, hn[kDecEv] = {};
       if (c < D) {
         const float* ws = sWs + c * ld;
         const float* wd = sWd + c * ld;
-#pragma unroll 5
         for (int k = k0; k < k1; ++k) {
-          hs = fmaf(ws[k], sz[k], hs);
-          const float w = wd[k];
-          hp = fmaf(w, sz[D + k], hp);
-          hn = fmaf(w, sz[2 * D + k], hn);
+          const float a = ws[k], b = wd[k];
+          const float4 zs = *reinterpret_cast<const float4*>(sz + k * kDecVec);
+          const float4 zd = *reinterpret_cast<const float4*>(sz + k * kDecVec + 4);
+          const float4 zn = *reinterpret_cast<const float4*>(sz + k * kDecVec + 8);
+          hs[0] = fmaf(a, zs.x, hs[0]); hs[1] = fmaf(a, zs.y, hs[1]); hs[2] = fmaf(a, zs.z, hs[2]); hs[3] = fmaf(a, zs.w, hs[3]);
+          hp[0] = fmaf(b, zd.x, hp[0]); hp[1] = fmaf(b, zd.y, hp[1]); hp[2] = fmaf(b, zd.z, hp[2]); hp[3] = fmaf(b, zd.w, hp[3]);
+          hn[0] = fmaf(b, zn.x, hn[0]); hn[1] = fmaf(b, zn.y, hn[1]); hn[2] = fmaf(b, zn.z, hn[2]); hn[3] = fmaf(b, zn.w, hn[3]);
         }
       }
-      s_p[0][q][c] = hs;
-      s_p[1][q][c] = hp;
-      s_p[2][q][c] = hn;
+#pragma unroll
+      for (int e = 0; e < kDecEv; ++e) {
+        s_p[e][q][c] = hs[e];
+        s_p[kDecEv + e][q][c] = hp[e];
+        s_p[2 * kDecEv + e][q][c] = hn[e];
+      }
     }
     __syncthreads();
-    if (q == 0) {
+    // ---- pointwise: channel c of event slot q
+    const bool live = e0 + q < B;
+    float h0 = 0.f, h1 = 0.f;
+    {
       float p0 = 0.f, p1 = 0.f;
-      if (c < D) {
+      if (c < D && live) {
         float hs = bs[c], hp = bd[c], hn = hp;
 #pragma unroll
         for (int j = 0; j < kDecQ; ++j) {
-          hs += s_p[0][j][c];
-          hp += s_p[1][j][c];
-          hn += s_p[2][j][c];
+          hs += s_p[q][j][c];
+          hp += s_p[kDecEv + q][j][c];
+          hn += s_p[2 * kDecEv + q][j][c];
         }
-        const float h0 = fmaxf(hs + hp, 0.f), h1 = fmaxf(hs + hn, 0.f);
-        s_h[0][c] = h0;
-        s_h[1][c] = h1;
+        h0 = fmaxf(hs + hp, 0.f);
+        h1 = fmaxf(hs + hn, 0.f);
         p0 = wf[c] * h0;
         p1 = wf[c] * h1;
       }
       p0 = warp_sum(p0);
       p1 = warp_sum(p1);
       if (lane == 0) {
-        s_part[0][tid >> 5] = p0;
-        s_part[1][tid >> 5] = p1;
+        s_part[q][0][(tid >> 5) & 3] = p0;
+        s_part[q][1][(tid >> 5) & 3] = p1;
       }
     }
     __syncthreads();
-    if (tid < 2) {
-      const float v = bfv + s_part[tid][0] + s_part[tid][1] + s_part[tid][2] + s_part[tid][3];
-      s_logit[tid] = v;
-      if (logits) logits[tid * B + ev] = v;
-    }
-    __syncthreads();
-    const float l0 = s_logit[0], l1 = s_logit[1];
-    const float dl0 = (1.f / (1.f + expf(-l0)) - 1.f) * invB;
-    const float dl1 = (1.f / (1.f + expf(-l1))) * invB;
-    if (tid == 0) {
-      // softplus(x) = max(x,0) + log1p(exp(-|x|)); x = -logit for the positive pair
-      loss_acc += (fmaxf(-l0, 0.f) + log1pf(expf(-fabsf(l0))) + fmaxf(l1, 0.f) + log1pf(expf(-fabsf(l1)))) * invB;
-      dbf_acc += dl0 + dl1;
-    }
-    // ---- backward through the final layer / relu; weight-gradient rows over [k0, k1)
-    if (c < D) {
-      const float h0 = s_h[0][c], h1 = s_h[1][c];
-      const float w = wf[c];
-      const float g0 = h0 > 0.f ? dl0 * w : 0.f, g1 = h1 > 0.f ? dl1 * w : 0.f;
-      const float gs = g0 + g1;
-      if (q == 0) {
-        atomicAdd(&dwf[c], dl0 * h0 + dl1 * h1);
-        atomicAdd(&dbs[c], gs);
-        atomicAdd(&dbd[c], gs);
-        sg[c] = gs;
-        sg[D + c] = g0;
-        sg[2 * D + c] = g1;
-        if (kDefer) {
-          g_rows[(long long)ev * D + c] = gs;
-          g_rows[(long long)(B + ev) * D + c] = g0;
-          g_rows[(long long)(2 * B + ev) * D + c] = g1;
+    {
+      const float l0 = bfv + s_part[q][0][0] + s_part[q][0][1] + s_part[q][0][2] + s_part[q][0][3];
+      const float l1 = bfv + s_part[q][1][0] + s_part[q][1][1] + s_part[q][1][2] + s_part[q][1][3];
+      const float dl0 = live ? (1.f / (1.f + expf(-l0)) - 1.f) * invB : 0.f;
+      const float dl1 = live ? (1.f / (1.f + expf(-l1))) * invB : 0.f;
+      if (c == 0 && live) {
+        if (logits) {
+          logits[e0 + q] = l0;
+          logits[B + e0 + q] = l1;
         }
+        // softplus(x) = max(x,0) + log1p(exp(-|x|)); x = -logit for the positive pair
+        loss_acc += (fmaxf(-l0, 0.f) + log1pf(expf(-fabsf(l0))) + fmaxf(l1, 0.f) + log1pf(expf(-fabsf(l1)))) * invB;
+        dbf_acc += dl0 + dl1;
       }
-      if (!kDefer) {
-        float* as = sAs + c * ld;
-        float* ad = sAd + c * ld;
-#pragma unroll 5
-        for (int k = k0; k < k1; ++k) {
-          as[k] = fmaf(gs, sz[k], as[k]);
-          ad[k] = fmaf(g0, sz[D + k], fmaf(g1, sz[2 * D + k], ad[k]));
+      // ---- backward through the final layer / relu
+      if (c < D) {
+        const float w = wf[c];
+        const float g0 = h0 > 0.f ? dl0 * w : 0.f, g1 = h1 > 0.f ? dl1 * w : 0.f;
+        const float gs = g0 + g1;
+        dwf_acc += dl0 * h0 + dl1 * h1;
+        dbs_acc += gs;
+        sg[c * kDecVec + q] = gs;
+        sg[c * kDecVec + kDecEv + q] = g0;
+        sg[c * kDecVec + 2 * kDecEv + q] = g1;
+        if (kDefer && live) {
+          g_rows[(long long)(e0 + q) * D + c] = gs;
+          g_rows[(long long)(B + e0 + q) * D + c] = g0;
+          g_rows[(long long)(2 * B + e0 + q) * D + c] = g1;
         }
       }
     }
     __syncthreads();
+    if (!kDefer && c < D) {   // weight-gradient rows of channel c over [k0, k1), all events of the pass
+      float* as = sAs + c * ld;
+      float* ad = sAd + c * ld;
+      const float4 gs = *reinterpret_cast<const float4*>(sg + c * kDecVec);
+      const float4 g0 = *reinterpret_cast<const float4*>(sg + c * kDecVec + 4);
+      const float4 g1 = *reinterpret_cast<const float4*>(sg + c * kDecVec + 8);
+      for (int k = k0; k < k1; ++k) {
+        const float4 zs = *reinterpret_cast<const float4*>(sz + k * kDecVec);
+        const float4 zd = *reinterpret_cast<const float4*>(sz + k * kDecVec + 4);
+        const float4 zn = *reinterpret_cast<const float4*>(sz + k * kDecVec + 8);
+        as[k] += gs.x * zs.x + gs.y * zs.y + gs.z * zs.z + gs.w * zs.w;
+        ad[k] += g0.x * zd.x + g0.y * zd.y + g0.z * zd.z + g0.w * zd.w +
+                 g1.x * zn.x + g1.y * zn.y + g1.z * zn.z + g1.w * zn.w;
+      }
+    }
     // ---- input gradients: input channel c, outputs [k0, k1) (column walks of the weights)
     {
-      float ds = 0.f, dd = 0.f, dn = 0.f;
+      float ds[kDecEv] = {}, dd[kDecEv] = {}, dn[kDecEv] = {};
       if (c < D) {
-#pragma unroll 5
         for (int r = k0; r < k1; ++r) {
-          ds = fmaf(sWs[r * ld + c], sg[r], ds);
-          const float w = sWd[r * ld + c];
-          dd = fmaf(w, sg[D + r], dd);
-          dn = fmaf(w, sg[2 * D + r], dn);
+          const float a = sWs[r * ld + c], b = sWd[r * ld + c];
+          const float4 gs = *reinterpret_cast<const float4*>(sg + r * kDecVec);
+          const float4 g0 = *reinterpret_cast<const float4*>(sg + r * kDecVec + 4);
+          const float4 g1 = *reinterpret_cast<const float4*>(sg + r * kDecVec + 8);
+          ds[0] = fmaf(a, gs.x, ds[0]); ds[1] = fmaf(a, gs.y, ds[1]); ds[2] = fmaf(a, gs.z, ds[2]); ds[3] = fmaf(a, gs.w, ds[3]);
+          dd[0] = fmaf(b, g0.x, dd[0]); dd[1] = fmaf(b, g0.y, dd[1]); dd[2] = fmaf(b, g0.z, dd[2]); dd[3] = fmaf(b, g0.w, dd[3]);
+          dn[0] = fmaf(b, g1.x, dn[0]); dn[1] = fmaf(b, g1.y, dn[1]); dn[2] = fmaf(b, g1.z, dn[2]); dn[3] = fmaf(b, g1.w, dn[3]);
         }
       }
-      s_p[0][q][c] = ds;
-      s_p[1][q][c] = dd;
-      s_p[2][q][c] = dn;
+#pragma unroll
+      for (int e = 0; e < kDecEv; ++e) {
+        s_p[e][q][c] = ds[e];
+        s_p[kDecEv + e][q][c] = dd[e];
+        s_p[2 * kDecEv + e][q][c] = dn[e];
+      }
     }
     __syncthreads();
-    if (tid < 3 * 128) {  // three gradient rows, one per 128-thread group
-      const int which = tid >> 7;
-      if (c < D) {
+    if (c < D && live) {   // the three gradient rows of event slot q
+#pragma unroll
+      for (int row = 0; row < 3; ++row) {
         float v = 0.f;
 #pragma unroll
-        for (int j = 0; j < kDecQ; ++j) v += s_p[which][j][c];
-        const int64_t row = which == 0 ? rs : (which == 1 ? rd : rn);
-        atomicAdd(&d_emb[row * D + c], v);
+        for (int j = 0; j < kDecQ; ++j) v += s_p[row * kDecEv + q][j][c];
+        atomicAdd(&d_emb[s_row[q][row] * D + c], v);
       }
     }
   }
   __syncthreads();
-  // ---- flush the weight-gradient accumulators
+  // ---- flush the per-thread and shared accumulators
+  if (c < D && (dwf_acc != 0.f || dbs_acc != 0.f)) {
+    atomicAdd(&dwf[c], dwf_acc);
+    atomicAdd(&dbs[c], dbs_acc);
+    atomicAdd(&dbd[c], dbs_acc);
+  }
   if (!kDefer) {
     for (int i = tid; i < D * D; i += kDecThreads) {
       const int r = i / D, k = i - r * D;
@@ -889,10 +917,8 @@ __global__ void __launch_bounds__(kDecThreads)
       if (b != 0.f) atomicAdd(&dWd[i], b);
     }
   }
-  if (tid == 0) {
-    if (loss_acc != 0.f) atomicAdd(loss, loss_acc);
-    if (dbf_acc != 0.f) atomicAdd(dbf, dbf_acc);
-  }
+  if (loss_acc != 0.f) atomicAdd(loss, loss_acc);
+  if (dbf_acc != 0.f) atomicAdd(dbf, dbf_acc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1135,7 +1161,7 @@ int32_t tgn_dec_loss(const float* hs, const float* hd, const float* w_final, con
 }
 
 int64_t tgn_dec_fused_smem_bytes(int32_t dim) {
-  return ((int64_t)4 * dim * (dim + 1) + 6 * dim) * (int64_t)sizeof(float);
+  return ((int64_t)4 * dim * (dim + 1) + 2 * kDecVec * dim) * (int64_t)sizeof(float);
 }
 
 int32_t tgn_dec_fused(const float* emb, const int64_t* ids_local, int32_t batch, int32_t dim,
@@ -1145,7 +1171,7 @@ int32_t tgn_dec_fused(const float* emb, const int64_t* ids_local, int32_t batch,
                       float* d_w_final, float* d_b_final, float* z_rows, float* g_rows, void* stream) {
   TGN_REQUIRE(batch >= 1 && dim >= 1, "dec_fused: bad sizes");
   const bool defer = z_rows != nullptr || g_rows != nullptr;
-  const int64_t smem = defer ? ((int64_t)2 * dim * (dim + 1) + 6 * dim) * (int64_t)sizeof(float)
+  const int64_t smem = defer ? ((int64_t)2 * dim * (dim + 1) + 2 * kDecVec * dim) * (int64_t)sizeof(float)
                              : tgn_dec_fused_smem_bytes(dim);
   TGN_REQUIRE(smem <= 215 * 1024 && dim <= 128,
               "dec_fused: dim %d does not fit shared memory (use the GEMM path)", dim);
@@ -1162,9 +1188,9 @@ int32_t tgn_dec_fused(const float* emb, const int64_t* ids_local, int32_t batch,
       TGN_CUDA(cudaFuncSetAttribute(dec_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem[defer] = smem;
   }
-  // ~2 events per CTA balances the event walk against the accumulator flush; without the flush
-  // (deferred weight gradients) the only per-CTA fixed cost is staging the two weight matrices
-  int grid = ceil_div(batch, 2);
+  // one pass = kDecEv events; a CTA's fixed cost is staging the two weight matrices (and, without
+  // deferred weight gradients, the accumulator flush)
+  int grid = ceil_div(batch, kDecEv);
   if (grid > kNumSMs) grid = kNumSMs;
   if (defer)
     launch_k(dec_fused_kernel<true>, dim3(grid), dim3(kDecThreads), (size_t)smem, (cudaStream_t)stream,

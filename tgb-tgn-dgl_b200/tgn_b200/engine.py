@@ -864,11 +864,14 @@ class TGNEngine:
                                   None, gptr("lin_src.bias"), None,
                                   gptr("lin_dst.bias"), gptr("lin_final.weight"), gptr("lin_final.bias"),
                                   _p(w.zcat), _p(w.dhcat), s))
+            # (one CTA per [D,D] gradient walks the whole batch: beyond ~256 events the reduction is split)
+            split_d = max(1, min(16, B // 128))
             dec_wgrad = [  # dW_src += g_src^T z_src ; dW_dst += [g_pos; g_neg]^T [z_dst; z_neg]  (aux stream, below)
                 ops.gemm_desc(w.dhcat, w.zcat, fg, m=D, n=D, k=B, lda=D, ldb=D, ldc=D, trans_a=True, trans_b=True,
-                              mode=2, c_off=off["lin_src.weight"]),
+                              mode=2, split_k=split_d, c_off=off["lin_src.weight"]),
                 ops.gemm_desc(w.dhcat, w.zcat, fg, m=D, n=D, k=2 * B, lda=D, ldb=D, ldc=D, trans_a=True,
-                              trans_b=True, mode=2, a_off=B * D, b_off=B * D, c_off=off["lin_dst.weight"]),
+                              trans_b=True, mode=2, split_k=split_d, a_off=B * D, b_off=B * D,
+                              c_off=off["lin_dst.weight"]),
             ]
         else:
             self._decoder_gemm_path(w, s)
@@ -917,6 +920,11 @@ class TGNEngine:
         tiles_dx = (w.Nb + 127) // 128 if self.Dt else 0
         tiles_w = ((3 * D + 127) // 128) * ((self.Dx + 127) // 128) + ((3 * D + 127) // 128) * ((D + 127) // 128)
         split_g = max(1, min(split_n, (148 - tiles_dx) // tiles_w))
+        if split_g < 4:
+            # larger batches (coin B=600, wiki B=2000): the bound-sized d x tiles alone exceed one wave, and a
+            # weight-gradient CTA that walks ALL rows (hundreds of k-blocks) becomes the step's longest launch
+            # (196 us measured at B=600).  Give every split <= ~24 k-blocks and accept a second wave.
+            split_g = max(split_g, min(16, (w.Nb // 32 + 23) // 24))
         g = [
             ops.gemm_desc(w.d_gi, w.x, fg, m=3 * D, n=self.Dx, k=w.Nb, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
                           trans_a=True, trans_b=True, mode=2, split_k=split_g, k_dev=w.Nb_dev,

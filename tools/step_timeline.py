@@ -14,11 +14,14 @@ from tgn_b200.engine import TGNEngine
 ap = argparse.ArgumentParser()
 ap.add_argument("--prefill", type=int, default=300_000)
 ap.add_argument("--precision", type=int, default=3)
+ap.add_argument("--workload", default=bench.WORKLOAD)
+ap.add_argument("--batch", type=int, default=None)
+ap.add_argument("--eval", type=int, default=0, help="Q > 0: timeline of one evaluation batch with Q negatives per positive")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
-cfg = synth.SHAPES[bench.WORKLOAD]
-B, K = cfg["B"], cfg["K"]
-data = synth.synth_events(bench.WORKLOAD, seed=0, max_events=a.prefill + 200 * B)
+cfg = synth.SHAPES[a.workload]
+B, K = a.batch or cfg["B"], cfg["K"]
+data = synth.synth_events(a.workload, seed=0, max_events=a.prefill + 200 * B, batch=B, extend=True)
 N, De = data["num_nodes"], data["raw_dim"]
 eng = TGNEngine(N, De, bench.HIDDEN, K, B, device=dev, lr=bench.LR, dropout=0.1, use_graph=True,
                 log_capacity=data["src"].size, seed=1234, precision=a.precision, fused_zero_grad=True)
@@ -26,23 +29,46 @@ eng.load_state(*bench.init_state_dicts(De, bench.HIDDEN, N, seed=1))
 eng.set_events(**{k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")})
 ring = bench.ring_after(data["src"][:a.prefill], data["dst"][:a.prefill], data["t"][:a.prefill], K, N)
 eng.prefill(a.prefill, tuple(torch.from_numpy(x) for x in ring))
-for _ in range(30):
-    eng.train_step(from_device=True)
-torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile
-with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    for _ in range(6):
+if a.eval:
+    ev_t = {k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg")}
+    def batch(b):
+        sl = slice(a.prefill + b * B, a.prefill + (b + 1) * B)
+        neg = torch.from_numpy(synth.eval_negatives(data["src"][sl], data["dst"][sl], N, a.eval, seed=1000 + b))
+        return tuple(x.to(dev) for x in (ev_t["src"][sl], ev_t["dst"][sl], neg, ev_t["t"][sl], ev_t["msg"][sl]))
+    bs = [batch(b) for b in range(12)]
+    for b in bs[:8]:
+        eng.eval_batch(*b)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for b in bs[8:]:
+            eng.eval_batch(*b)
+        torch.cuda.synchronize()
+    marker = "unique_mark"
+else:
+    for _ in range(30):
         eng.train_step(from_device=True)
     torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(6):
+            eng.train_step(from_device=True)
+        torch.cuda.synchronize()
+    marker = "msg_build"
 path = os.path.join(tempfile.mkdtemp(), "trace.json")
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
 ev.sort(key=lambda e: e["ts"])
-starts = [i for i, e in enumerate(ev) if "msg_build" in e["name"]]
+starts = [i for i, e in enumerate(ev) if marker in e["name"]]
+if a.eval:      # the first unique_mark of every batch: keep starts that are >200 us apart
+    keep = [starts[0]]
+    for i in starts[1:]:
+        if ev[i]["ts"] - ev[keep[-1]]["ts"] > 200:
+            keep.append(i)
+    starts = keep
 lo, hi = starts[-3], starts[-2]
 t0 = ev[lo]["ts"]
 streams = sorted({e["args"].get("stream") for e in ev[lo:hi]})
-print(f"step = {ev[hi]['ts'] - t0:.1f} us between two msg_build launches; streams {streams}")
+print(f"{a.workload} B={B}{' eval Q=%d' % a.eval if a.eval else ''}: step = {ev[hi]['ts'] - t0:.1f} us between two {marker} launches; streams {streams}")
 print(f"{'start':>8s} {'end':>8s} {'dur':>7s}  st  kernel")
 for e in ev[lo:hi]:
     name = e["name"].split("(")[0].replace("void ", "").replace("tgn::", "")[:48]

@@ -523,7 +523,10 @@ int32_t tgn_dec_loss(const float* hs, const float* hd, const float* w_final, con
  * Deferred weight gradients: with z_rows and g_rows given (both [3B,dim]) d_w_src / d_w_dst are NOT
  * touched; the kernel writes z_rows = [z_src; z_dst; z_neg] and g_rows = [g_src; g_pos; g_neg] (the
  * gradients of the hidden layer) and the caller forms d_w_src += g_src^T z_src,
- * d_w_dst += [g_pos; g_neg]^T [z_dst; z_neg] with tgn_gemm_batch off the dependent chain. */
+ * d_w_dst += [g_pos; g_neg]^T [z_dst; z_neg] with tgn_gemm_batch off the dependent chain.
+ * Stream contract: w_src / w_dst are staged into shared memory AHEAD of the programmatic-launch wait, so
+ * the launch immediately in front of this one on the stream must not be the one that writes them (in the
+ * training step the optimiser runs a whole step earlier); every other input is read after the wait. */
 int64_t tgn_dec_fused_smem_bytes(int32_t dim);
 int32_t tgn_dec_fused(const float* emb, const int64_t* ids_local, int32_t batch, int32_t dim,
                       const float* w_src, const float* b_src, const float* w_dst, const float* b_dst,

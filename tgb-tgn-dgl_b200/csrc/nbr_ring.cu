@@ -172,32 +172,53 @@ __device__ __forceinline__ void insert_merge_warp(const unsigned long long* __re
     nn = j < B ? src[ev] : dst[ev];
     nt = t[ev];
   }
-  // candidate index: old slot i -> i, new entry i -> K + i  (the dense block lists the run in sorted order,
-  // i.e. new entry `taken-1-i` comes first; ties between new entries only occur for identical duplicates)
+  // Ranks in the total order "value descending; ties: old slots before new entries, old by slot, new by
+  // run position (older first)".  Ring rows are written in rank order, so the old row is normally already
+  // sorted (descending): then an old slot's rank is its index plus the new entries above it, a new entry's
+  // rank a ballot over the old row plus a count over the few new entries -- O(taken) warp operations.  A
+  // row that is not sorted (state loaded from elsewhere) takes the generic all-pairs loop.
   int r_oe = 0, r_ne = 0, r_ot = 0, r_nt = 0, cnt_ge = 0;
-  for (int i = 0; i < 32; ++i) {
-    const int64_t xe = __shfl_sync(0xffffffffu, oe, i), ye = __shfl_sync(0xffffffffu, ne, i);
-    const float xt = __shfl_sync(0xffffffffu, ot, i), yt = __shfl_sync(0xffffffffu, nt, i);
-    const bool vo = i < K, vn = i < taken;
-    // e_id ranks
-    if (vo) {
-      r_oe += (xe > oe) || (xe == oe && i < lane);
-      r_ne += (xe >= ne);                                   // an old slot precedes every new entry on ties
-    }
-    if (vn) {
+  const int64_t oe_next = __shfl_down_sync(0xffffffffu, oe, 1);
+  const float ot_next = __shfl_down_sync(0xffffffffu, ot, 1);
+  const bool unsorted = lane + 1 < K && (oe_next > oe || ot_next > ot);
+  if (!__any_sync(0xffffffffu, unsorted)) {
+    r_oe = lane;
+    r_ot = lane;
+    cnt_ge = __popc(__ballot_sync(0xffffffffu, has_old && ot >= -1.f)) +
+             __popc(__ballot_sync(0xffffffffu, has_new && nt >= -1.f));
+    for (int i = 0; i < taken; ++i) {
+      const int64_t ye = __shfl_sync(0xffffffffu, ne, i);
+      const float yt = __shfl_sync(0xffffffffu, nt, i);
       r_oe += (ye > oe);
-      r_ne += (ye > ne) || (ye == ne && i > lane);          // dense order: older run position (higher i) first
-    }
-    // t ranks
-    if (vo) {
-      r_ot += (xt > ot) || (xt == ot && i < lane);
-      r_nt += (xt >= nt);
-      cnt_ge += (xt >= -1.f);
-    }
-    if (vn) {
       r_ot += (yt > ot);
+      r_ne += (ye > ne) || (ye == ne && i > lane);
       r_nt += (yt > nt) || (yt == nt && i > lane);
-      cnt_ge += (yt >= -1.f);
+      const int ge_e = __popc(__ballot_sync(0xffffffffu, has_old && oe >= ye));
+      const int ge_t = __popc(__ballot_sync(0xffffffffu, has_old && ot >= yt));
+      if (lane == i) {
+        r_ne += ge_e;
+        r_nt += ge_t;
+      }
+    }
+  } else {
+    for (int i = 0; i < 32; ++i) {
+      const int64_t xe = __shfl_sync(0xffffffffu, oe, i), ye = __shfl_sync(0xffffffffu, ne, i);
+      const float xt = __shfl_sync(0xffffffffu, ot, i), yt = __shfl_sync(0xffffffffu, nt, i);
+      const bool vo = i < K, vn = i < taken;
+      if (vo) {
+        r_oe += (xe > oe) || (xe == oe && i < lane);
+        r_ne += (xe >= ne);
+        r_ot += (xt > ot) || (xt == ot && i < lane);
+        r_nt += (xt >= nt);
+        cnt_ge += (xt >= -1.f);
+      }
+      if (vn) {
+        r_oe += (ye > oe);
+        r_ne += (ye > ne) || (ye == ne && i > lane);
+        r_ot += (yt > ot);
+        r_nt += (yt > nt) || (yt == nt && i > lane);
+        cnt_ge += (yt >= -1.f);
+      }
     }
   }
   const int n_fill = K - taken;          // -1 padding of the dense block: after old and new on ties
@@ -365,8 +386,8 @@ int32_t tgn_nbr_insert(const int64_t* src, const int64_t* dst, const float* t, i
   static unsigned long long attr_mask = 0;
   TGN_CUDA(smem_optin(nbr_insert_kernel, TGN_SORT_MAX * 8, attr_mask));
   // one warp merges one node run: ~2B/3 runs on TGB-like streams; 32 warps per CTA
-  int grid = (2 * batch + 32 * 24 - 1) / (32 * 24);
-  grid = grid < 1 ? 1 : (grid > 16 ? 16 : grid);
+  int grid = (2 * batch + 32 * 4 - 1) / (32 * 4);
+  grid = grid < 1 ? 1 : (grid > 32 ? 32 : grid);
   launch_k(nbr_insert_kernel, dim3(grid), dim3(1024), (size_t)P * 8, (cudaStream_t)stream,
       src, dst, t, batch, P, cur_e_id, (const int64_t*)cur_e_id_dev, size_k, num_nodes, neighbors, e_id, t_state);
   TGN_LAUNCH_CHECK();

@@ -726,8 +726,6 @@ __global__ void __launch_bounds__(kDecThreads)
                      float* __restrict__ dWs, float* __restrict__ dbs, float* __restrict__ dWd,
                      float* __restrict__ dbd, float* __restrict__ dwf, float* __restrict__ dbf,
                      float* __restrict__ z_rows, float* __restrict__ g_rows) {
-  pdl_wait();
-  pdl_launch();
   extern __shared__ __align__(16) float sm[];
   const int ld = D + 1;
   float* sz = sm;                        // [D][kDecVec] inputs      (16-byte aligned rows)
@@ -752,6 +750,11 @@ __global__ void __launch_bounds__(kDecThreads)
       sAd[r * ld + k] = 0.f;
     }
   }
+  // The weights were written by the optimiser of the PREVIOUS step -- at least two launches back, which a
+  // programmatic launch chain has always completed (the predecessor released this kernel only after its own
+  // griddepcontrol.wait returned) -- so they are staged ahead of the wait, beside the predecessor's tail.
+  pdl_wait();
+  pdl_launch();
   const float invB = 1.f / (float)B;
   const float bfv = bf[0];
   float loss_acc = 0.f, dbf_acc = 0.f, dwf_acc = 0.f, dbs_acc = 0.f;

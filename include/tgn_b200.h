@@ -588,6 +588,32 @@ int32_t tgn_rank_accum(const int32_t* gt, const int32_t* ge, int32_t batch, doub
                        void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Owner-side compute for the partitioned node memory (modules/memory_module.py:126-150,
+ * modules/msg_func.py:17-18): rank r builds the messages and runs the GRU only for the rows of a step it
+ * owns (n % world == r), publishes h' / last_update' to every rank's row table through the peer mapping,
+ * runs the GRU backward on its rows, and the optimiser sums the partial gradients out of peer memory.
+ *   tgn_part_select_owned  own_nodes / own_pos [<= num]: owned entries of n_id and their positions, in
+ *                          position order; *own_count_dev = how many.
+ *   tgn_part_publish       peer_rows[p][own_pos[i], :] = rows[i, :], peer_last_update[p][own_pos[i]] =
+ *                          last_update[i] for every rank p (128-bit stores over NVLink; dim % 4 == 0).
+ *                          The caller brackets it with rank barriers.
+ *   tgn_adam_finish_peers  tgn_adam_finish with gradient = grads_replicated[i] + sum_p
+ *                          peer_grads_partial[p][i]; grads_replicated is ONE rank's copy of the replicated
+ *                          part (all ranks pass the same mapping, so the weight replicas stay bit-identical).
+ *                          No gradient clearing (peers may still be reading): the caller clears after a barrier.
+ * ------------------------------------------------------------------------- */
+int32_t tgn_part_select_owned(const int64_t* n_id, int32_t num, const int32_t* num_dev, int32_t rank,
+                              int32_t world, int64_t* own_nodes, int64_t* own_pos, int32_t* own_count_dev,
+                              void* stream);
+int32_t tgn_part_publish(const float* rows, const int64_t* last_update, const int64_t* own_pos, int32_t num,
+                         const int32_t* num_dev, int32_t dim, void* const* peer_rows, void* const* peer_last_update,
+                         int32_t world, void* stream);
+int32_t tgn_adam_finish_peers(float* params, const float* grads_replicated, const void* const* peer_grads_partial,
+                              int32_t world, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
+                              float beta1, float beta2, float eps, float* step_dev, int64_t* step_counter,
+                              const float* loss_acc, float* loss_out, uint32_t* done_counter, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * EdgeGATConv attention core of the reference's live DGL stack (model_utils.py:565-612).
  * Per head: el'_e = el[src(e)] + ee[e] (:594), z_e = LeakyReLU(el'_e + er[dst(e)]) (:595-596),
  * a = edge_softmax by destination then attention dropout (:597), s[v] = sum_e a_e * el'_e (:560-563,599 --

@@ -36,11 +36,16 @@ def main():
         ref["memory"].time_enc.lin.weight.mul_(0.002)
     ev = dict(src=torch.from_numpy(src), dst=torch.from_numpy(dst), t=torch.from_numpy(t),
               msg=torch.from_numpy(msg), neg=torch.from_numpy(neg))
-    for use_graph, exchange in ((False, "p2p"), (True, "p2p"), (True, "allreduce")):
+    # owner: every rank runs the message build + GRU (+ their backward) only for the rows it owns, publishes
+    # them over the peer mapping and the optimiser sums the partial gradients out of peer memory;
+    # replicated: every rank computes all rows (round-1 design), gradients averaged by NCCL
+    for use_graph, exchange, compute in ((False, "p2p", "owner"), (True, "p2p", "owner"), (True, "p2p", "replicated"),
+                                         (True, "allreduce", "replicated")):
         engs = []
         for part in (False, True):
             eng = TGNEngine(N, De, D, K, B, device=dev, lr=1e-5, dropout=0.0, use_graph=use_graph, log_capacity=E,
-                            rank=rank if part else 0, world=world if part else 1, part_exchange=exchange)
+                            rank=rank if part else 0, world=world if part else 1, part_exchange=exchange,
+                            part_compute=compute)
             eng.load_state(ref["memory"].state_dict(), ref["gnn"].state_dict(), ref["link_pred"].state_dict())
             eng.set_events(**ev)
             engs.append(eng)
@@ -49,7 +54,7 @@ def main():
             la, lb = float(single.train_step()), float(parted.train_step())
             # lr is tiny on purpose: Adam turns the rounding noise of atomically reduced gradients into
             # lr-sized weight differences, which would otherwise dominate a free-running comparison
-            assert abs(la - lb) < 3e-4 * max(1.0, abs(la)), (use_graph, s, la, lb)
+            assert abs(la - lb) < 3e-4 * max(1.0, abs(la)), (use_graph, exchange, compute, s, la, lb)
         fm, fl = parted.full_memory()
         torch.testing.assert_close(fm, single.memory, rtol=2e-3, atol=2e-4)
         assert torch.equal(fl, single.last_update)
@@ -60,6 +65,8 @@ def main():
         dist.broadcast(w0, 0)
         assert torch.equal(w0, parted.flat)
         # eval path on the partitioned state
+        assert parted.owner_compute == (compute == "owner")
+        parted.check_device_errors()
         parted.flush_to_eval(); single.flush_to_eval()
         fm, fl = parted.full_memory()
         torch.testing.assert_close(fm, single.memory, rtol=2e-3, atol=2e-4)
@@ -67,8 +74,8 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
-        print(f"partition check OK: world={world}, {steps} steps eager + graph, peer-memory and all-reduce row "
-              f"assembly, losses / memory / ring / weights agree",
+        print(f"partition check OK: world={world}, {steps} steps eager + graph, owner-side and replicated compute, "
+              f"peer-memory and all-reduce row assembly, losses / memory / ring / weights agree",
               flush=True)
     # the captured graphs hold NCCL kernels; tearing the communicator down underneath them can block,
     # so leave without the collective shutdown

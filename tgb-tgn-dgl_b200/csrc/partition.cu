@@ -136,6 +136,122 @@ __global__ void memory_scatter_owned_kernel(const int64_t* __restrict__ n_id, De
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Owner-side compute (north_star "node memory split by node-id owner"): of the rows n_id of a
+// step, rank r runs the message build and the GRU only for the nodes it owns (n % P == r) and PUBLISHES
+// the resulting rows h' / last_update' into every rank's row table through the peer mapping; the GRU
+// backward likewise runs on the owned rows only, and the partial weight gradients are summed inside the
+// optimiser kernel straight out of the peers' gradient buffers.
+// ---------------------------------------------------------------------------
+// own_nodes / own_pos: the owned entries of n_id and their positions, in position order (single CTA:
+// a block scan per 1024 ids keeps the order deterministic, so reductions over the owned rows are too).
+__global__ void __launch_bounds__(1024)
+    part_select_owned_kernel(const int64_t* __restrict__ n_id, DevCount num, int rank, int world,
+                             int64_t* __restrict__ own_nodes, int64_t* __restrict__ own_pos,
+                             int32_t* __restrict__ own_count) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int S = num.get();
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int s0 = 0; s0 < S; s0 += 1024) {
+    const int s = s0 + tid;
+    int64_t n = -1;
+    if (s < S) n = n_id[s];
+    const bool own = n >= 0 && (int)(n % world) == rank;
+    const unsigned ball = __ballot_sync(0xffffffffu, own);
+    if (lane == 0) s_warp[wid] = __popc(ball);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int c = s_warp[w];
+      before += w < wid ? c : 0;
+      total += c;
+    }
+    if (own) {
+      const int pos = s_base + before + __popc(ball & lanemask_lt());
+      own_nodes[pos] = n;
+      own_pos[pos] = s;
+    }
+    __syncthreads();
+    if (tid == 0) s_base += total;
+    __syncthreads();
+  }
+  if (tid == 0) *own_count = s_base;
+}
+
+struct PeerTables {
+  float* rows[kMaxPeers];
+  int64_t* lu[kMaxPeers];
+};
+
+__global__ void part_publish_kernel(const float* __restrict__ rows, const int64_t* __restrict__ lu,
+                                    const int64_t* __restrict__ own_pos, DevCount num, int D, int world,
+                                    PeerTables peers) {
+  pdl_wait();
+  pdl_launch();
+  const int S = num.get();
+  const int D4 = D >> 2;   // D % 4 == 0 (engine requirement): 128-bit stores over NVLink
+  const long long total = (long long)S * D4 * world;
+  for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total;
+       x += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(x / ((long long)S * D4));
+    const long long y = x - (long long)p * S * D4;
+    const int i = (int)(y / D4), c = (int)(y - (long long)i * D4);
+    const int64_t pos = own_pos[i];
+    reinterpret_cast<float4*>(peers.rows[p] + pos * D)[c] = reinterpret_cast<const float4*>(rows + (long long)i * D)[c];
+    if (c == 0) peers.lu[p][pos] = lu[i];
+  }
+}
+
+struct PeerGrads {
+  const float* part[kMaxPeers];
+};
+
+// torch.optim.Adam step whose gradient is rep[i] + sum_p part[p][i]: `rep` = the replicated part of the
+// gradient as rank 0 computed it (every rank reads the SAME copy, so the weight replicas stay bit-identical),
+// part[p] = rank p's partial sums over the rows it owns.  Same arithmetic as adam_kernel (dense.cu).
+__global__ void adam_peers_kernel(float* __restrict__ p, const float* __restrict__ rep, PeerGrads pg, int world,
+                                  float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                                  float b1, float b2, float eps, float* __restrict__ step_dev,
+                                  int64_t* __restrict__ step_ctr, const float* __restrict__ loss_acc,
+                                  float* __restrict__ loss_out, unsigned* __restrict__ done_ctr) {
+  pdl_wait();
+  pdl_launch();
+  const float step = *step_dev + 1.f;
+  const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float gi = rep[i];
+    for (int r = 0; r < world; ++r) gi += pg.part[r][i];
+    const float mi = m[i] + (1.f - b1) * (gi - m[i]);
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] -= step_size * (mi / denom);
+  }
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(done_ctr, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    *step_dev += 1.f;
+    if (step_ctr) *step_ctr += 1;
+    if (loss_acc && loss_out) *loss_out = *loss_acc;
+    *done_ctr = 0u;
+  }
+}
+
 }  // namespace tgn
 
 using namespace tgn;
@@ -213,6 +329,55 @@ int32_t tgn_memory_scatter_owned(const int64_t* n_id, int32_t num, const int32_t
   else
     launch_k(memory_scatter_owned_kernel<int64_t>, dim3(grid), dim3(256), 0, s, n_id, c, new_mem,
              (const int64_t*)new_lu, src_rows, dim, rank, world, memory_local, last_update_local);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_part_select_owned(const int64_t* n_id, int32_t num, const int32_t* num_dev, int32_t rank,
+                              int32_t world, int64_t* own_nodes, int64_t* own_pos, int32_t* own_count_dev,
+                              void* stream) {
+  TGN_REQUIRE(num >= 0 && world >= 1 && rank >= 0 && rank < world, "part_select_owned: bad sizes / rank");
+  TGN_REQUIRE(own_count_dev && (num == 0 || (n_id && own_nodes && own_pos)), "part_select_owned: NULL pointer");
+  launch_k(part_select_owned_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, n_id, DevCount{num_dev, num},
+           rank, world, own_nodes, own_pos, own_count_dev);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_part_publish(const float* rows, const int64_t* last_update, const int64_t* own_pos, int32_t num,
+                         const int32_t* num_dev, int32_t dim, void* const* peer_rows, void* const* peer_last_update,
+                         int32_t world, void* stream) {
+  TGN_REQUIRE(num >= 0 && dim >= 4 && dim % 4 == 0 && world >= 1 && world <= kMaxPeers,
+              "part_publish: bad sizes (dim %% 4 == 0, world <= %d)", kMaxPeers);
+  if (num == 0) return TGN_OK;
+  TGN_REQUIRE(rows && last_update && own_pos && peer_rows && peer_last_update, "part_publish: NULL pointer");
+  PeerTables t;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    t.rows[r] = r < world ? (float*)peer_rows[r] : nullptr;
+    t.lu[r] = r < world ? (int64_t*)peer_last_update[r] : nullptr;
+    TGN_REQUIRE(r >= world || (t.rows[r] && t.lu[r]), "part_publish: peer %d has no mapping", r);
+  }
+  launch_k(part_publish_kernel, dim3(stride_grid((long long)num * (dim / 4) * world, 256)), dim3(256), 0,
+           (cudaStream_t)stream, rows, last_update, own_pos, DevCount{num_dev, num}, dim, world, t);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_adam_finish_peers(float* params, const float* grads_replicated, const void* const* peer_grads_partial,
+                              int32_t world, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
+                              float beta1, float beta2, float eps, float* step_dev, int64_t* step_counter,
+                              const float* loss_acc, float* loss_out, uint32_t* done_counter, void* stream) {
+  TGN_REQUIRE(count >= 1 && world >= 1 && world <= kMaxPeers && step_dev && done_counter,
+              "adam_finish_peers: bad arguments");
+  TGN_REQUIRE(params && grads_replicated && peer_grads_partial && exp_avg && exp_avg_sq, "adam_finish_peers: NULL pointer");
+  PeerGrads pg;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    pg.part[r] = r < world ? (const float*)peer_grads_partial[r] : nullptr;
+    TGN_REQUIRE(r >= world || pg.part[r], "adam_finish_peers: peer %d has no mapping", r);
+  }
+  launch_k(adam_peers_kernel, dim3(stride_grid(count, 256)), dim3(256), 0, (cudaStream_t)stream, params,
+           grads_replicated, pg, world, exp_avg, exp_avg_sq, (long long)count, lr, beta1, beta2, eps, step_dev,
+           step_counter, loss_acc, loss_out, done_counter);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

@@ -51,7 +51,7 @@ class TGNEngine:
                  device="cuda", lr: float = 1e-4, heads: int = 2, dropout: float = 0.1,
                  log_capacity: int = 1 << 20, seed: int = 0, use_graph: bool = True,
                  precision: int = 3, rank: int = 0, world: int = 1, group=None, fused_zero_grad: bool = False,
-                 part_exchange: str = "p2p", share: Optional["TGNEngine"] = None):
+                 part_exchange: str = "p2p", share: Optional["TGNEngine"] = None, part_compute: str = "owner"):
         """share: another engine of the same model (nodes, dims, K, world) whose weights, Adam moments, node
         memory, neighbour ring, message store, event arrays and cursors this one USES instead of allocating
         its own -- a second step geometry (another batch size, e.g. the tail batch of an epoch) on the same
@@ -105,11 +105,31 @@ class TGNEngine:
         if share is not None and (share.N, share.De, share.D, share.K, share.H, share.world, share.rank) != \
                 (num_nodes, raw_dim, hidden, size_k, heads, world, rank):
             raise ValueError("share: the two engines must describe the same model and partition")
-        self.zero_blob = torch.zeros(o + 4 + Nb * HC, device=dev)
+        # Partitioned memory with owner-side compute (world > 1, peer exchange): the gradient blob is symmetric
+        # memory -- [replicated part | loss | PARTIAL sums over the rows this rank owns | d_emb] -- because the
+        # optimiser of every rank reads rank 0's replicated part and all ranks' partial parts out of peer memory.
+        if part_compute not in ("owner", "replicated"):
+            raise ValueError("part_compute must be 'owner' or 'replicated'")
+        self.owner_compute = world > 1 and part_exchange == "p2p" and part_compute == "owner" and share is None
+        if self.owner_compute:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            self.zero_blob = symm_mem.empty((o + 4 + o + Nb * HC,), dtype=torch.float32, device=dev)
+            self.zero_blob.zero_()
+            self._symm_grad = symm_mem.rendezvous(self.zero_blob, grp)
+            self._peer_grad_part = (ctypes.c_void_p * world)(*[int(q) + 4 * (o + 4) for q in self._symm_grad.buffer_ptrs])
+            self._grad_rep0 = int(self._symm_grad.buffer_ptrs[0])
+            self.flat_grad_part = self.zero_blob[o + 4:o + 4 + o]
+            self.d_emb = self.zero_blob[o + 4 + o:].view(Nb, HC)
+            fused_zero_grad = False      # peers read this rank's gradients: they are cleared after a barrier instead
+        else:
+            self.zero_blob = torch.zeros(o + 4 + Nb * HC, device=dev)
+            self.flat_grad_part = None
+            self.d_emb = self.zero_blob[o + 4:].view(Nb, HC)
         self.flat = torch.zeros(o, device=dev) if share is None else share.flat
         self.flat_grad = self.zero_blob[:o]
         self.loss_acc = self.zero_blob[o:o + 1]
-        self.d_emb = self.zero_blob[o + 4:].view(Nb, HC)
         self.exp_avg = torch.zeros(o, device=dev) if share is None else share.exp_avg
         self.exp_avg_sq = torch.zeros(o, device=dev) if share is None else share.exp_avg_sq
         self.adam_step_dev = torch.zeros(1, device=dev) if share is None else share.adam_step_dev
@@ -178,6 +198,22 @@ class TGNEngine:
         self.upd = torch.cuda.Stream(device=dev)     # memory / message-store update of this batch
         self.aux = torch.cuda.Stream(device=dev)     # edge branch of the attention / small reductions
         self.w = self._alloc_work(R, E, Nb, batch_size)
+        if self.owner_compute:
+            # every rank's table of the step's rows (h', last_update'): owners publish into it over NVLink
+            self.w.z = symm_mem.empty((Nb, D), dtype=torch.float32, device=dev)
+            self.w.lu = symm_mem.empty((Nb,), dtype=torch.long, device=dev)
+            self.w.z.zero_()
+            self.w.lu.zero_()
+            hz, hl = symm_mem.rendezvous(self.w.z, grp), symm_mem.rendezvous(self.w.lu, grp)
+            self._symm_rows = (hz, hl)
+            self._peer_z = (ctypes.c_void_p * world)(*[int(q) for q in hz.buffer_ptrs])
+            self._peer_rowlu = (ctypes.c_void_p * world)(*[int(q) for q in hl.buffer_ptrs])
+            # workspace of the rows this rank owns (any share of the Nb rows of a step can be its own)
+            self.wo = self._alloc_work(1, 1, Nb, 1)
+            self.wo.own_n = torch.zeros(Nb, dtype=torch.long, device=dev)
+            self.wo.own_pos = torch.zeros(Nb, dtype=torch.long, device=dev)
+            self.wo.So_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
         # Slots of {batch inputs, sampling results} in rotation: while step s runs on slot `cur`, the forked
         # stream already loads and samples batch s+1 into the next slot (software pipelining), and a host
         # loader can copy later batches into slots the running steps do not touch.
@@ -711,6 +747,28 @@ class TGNEngine:
                                            _p(w.x), self.ldx, _p(w.h), _p(w.sn_m), _p(w.lu), _p(w.sel_ev),
                                            _p(w.sel_dt), _stream()))
 
+    def _memory_fwd_owner(self, w):
+        """Owner-side TGNMemory._get_updated_memory (memory_module.py:152-178): this rank builds the messages
+        (its own rows are local, the other endpoint's row of each message comes out of its owner's shard over
+        NVLink) and runs the GRU for the rows of n_id it owns, then publishes h' / last_update' into every
+        rank's row table w.z / w.lu.  Rank barrier B makes the tables complete before anyone reads them, and
+        orders all remote reads of this step before the owners' memory write-back."""
+        wo, D, L, p = self.wo, self.D, _L(), self.p
+        st = ctypes.byref(self.store.struct())
+        check(L.tgn_part_select_owned(_p(w.n_id), w.Nb, _p(w.Nb_dev), self.rank, self.world, _p(wo.own_n),
+                                      _p(wo.own_pos), _p(wo.So_dev), _stream()))
+        g_o = wo.g_rows.data_ptr() + 4 * wo.g_rows.shape[1] * D
+        check(L.tgn_part_gather_p2p(st, _p(wo.own_n), w.Nb, _p(wo.So_dev), self._peer_mem, self._peer_lu, D,
+                                    self.world, _p(wo.g_rows), g_o, _p(wo.g_lu), _stream()))
+        check(L.tgn_msg_build_gathered(st, _p(wo.own_n), w.Nb, _p(wo.So_dev), _p(wo.g_rows), g_o, _p(wo.g_lu), D,
+                                       _p(p["time_enc.lin.weight"]), _p(p["time_enc.lin.bias"]), self.Dt,
+                                       _p(wo.x), self.ldx, _p(wo.h), _p(wo.sn_m), _p(wo.lu), _p(wo.sel_ev),
+                                       _p(wo.sel_dt), _stream()))
+        self._memory_gru(wo, w.Nb, wo.So_dev)
+        check(L.tgn_part_publish(_p(wo.z), _p(wo.lu), _p(wo.own_pos), w.Nb, _p(wo.So_dev), D, self._peer_z,
+                                 self._peer_rowlu, self.world, _stream()))
+        self._symm_mem.barrier(channel=1)
+
     def _memory_gru(self, w, S: int, S_dev: Optional[Tensor]):
         p, D, L, s = self.p, self.D, _L(), _stream()
         if self.fused_gru:
@@ -815,6 +873,12 @@ class TGNEngine:
         w, p, B, D, HC, L = self.w, self.p, self.B, self.D, self.HC, _L()
         off, fg, fl = self.off, self.flat_grad, self.flat
         main, side, aux, upd = torch.cuda.current_stream(), self.side, self.aux, self.upd
+        own = self.owner_compute
+        if own:
+            # rank barrier A: every rank has finished the previous step -- its optimiser has read this rank's
+            # gradients and its owner-side memory writes have landed -- before gradients are cleared here and
+            # memory rows are read out of the peers' shards
+            self._symm_mem.barrier(channel=0)
         if not self.fused_zero_grad:
             self.zero_blob.zero_()
         if not pipelined:
@@ -841,12 +905,16 @@ class TGNEngine:
             w.d_proj.zero_()
             if self.dz_split > 1:
                 w.d_z.zero_()
-        self._timed("msg_build", lambda: self._memory_msgs(w, w.n_id, w.Nb, w.Nb_dev))
+        if own:
+            self._memory_fwd_owner(w)
+        else:
+            self._timed("msg_build", lambda: self._memory_msgs(w, w.n_id, w.Nb, w.Nb_dev))
         # ---- edge branch of the attention on its own stream: needs last_update / edges only
         aux.wait_stream(main)
         with torch.cuda.stream(aux):
             self._edge_branch(w, w.lu, True)
-        self._memory_gru(w, w.Nb, w.Nb_dev)
+        if not own:
+            self._memory_gru(w, w.Nb, w.Nb_dev)
         # ---- forked stream 2: memory / store update (needs z / last_update of the forward only)
         upd.wait_stream(main)
         with torch.cuda.stream(upd):
@@ -910,9 +978,16 @@ class TGNEngine:
             if self.Dt:
                 check(L.tgn_time_bwd_sin(_p(w.rel), None, w.E, _p(w.E_dev), _p(w.sn_e), self.Dt, _p(w.d_eat), self.Dt,
                                          gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), _stream()))
-        # ---- GRU backward (torch.nn.GRUCell, memory_module.py:72,172)
-        check(L.tgn_gru_gates_bwd_bias(_p(w.d_z), _p(w.gates), _p(w.h), w.Nb, _p(w.Nb_dev), D, _p(w.d_gi),
-                                       _p(w.d_gh), gptr("memory_updater.bias_ih"), gptr("memory_updater.bias_hh"), s))
+        # ---- GRU backward (torch.nn.GRUCell, memory_module.py:72,172).  Owner-side compute: only on the rows
+        # this rank owns (gm = their workspace, rows_dev = how many), gradients into the PARTIAL buffer that the
+        # optimiser sums over the ranks
+        gm, rows_dev, fgm = w, w.Nb_dev, fg
+        if own:
+            gm, rows_dev, fgm = self.wo, self.wo.So_dev, self.flat_grad_part
+            check(L.tgn_gather_rows(_p(w.d_z), _p(gm.own_pos), w.Nb, _p(rows_dev), D, _p(gm.d_z), s))
+        gptr_m = lambda name: fgm.data_ptr() + 4 * off[name]
+        check(L.tgn_gru_gates_bwd_bias(_p(gm.d_z), _p(gm.gates), _p(gm.h), w.Nb, _p(rows_dev), D, _p(gm.d_gi),
+                                       _p(gm.d_gh), gptr_m("memory_updater.bias_ih"), gptr_m("memory_updater.bias_hh"), s))
         # One launch, one wave: the GEMM CTAs hold ~193 KB of shared memory (one per SM), so the split-K
         # factor of the two weight gradients is chosen to leave SMs for the row tiles of d x -- launched
         # separately (or with a larger split) d x simply queues behind the weight-gradient CTAs.
@@ -926,27 +1001,36 @@ class TGNEngine:
             # (196 us measured at B=600).  Give every split <= ~24 k-blocks and accept a second wave.
             split_g = max(split_g, min(16, (w.Nb // 32 + 23) // 24))
         g = [
-            ops.gemm_desc(w.d_gi, w.x, fg, m=3 * D, n=self.Dx, k=w.Nb, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
-                          trans_a=True, trans_b=True, mode=2, split_k=split_g, k_dev=w.Nb_dev,
+            ops.gemm_desc(gm.d_gi, gm.x, fgm, m=3 * D, n=self.Dx, k=w.Nb, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
+                          trans_a=True, trans_b=True, mode=2, split_k=split_g, k_dev=rows_dev,
                           c_off=off["memory_updater.weight_ih"]),
-            ops.gemm_desc(w.d_gh, w.h, fg, m=3 * D, n=D, k=w.Nb, lda=3 * D, ldb=D, ldc=D, trans_a=True,
-                          trans_b=True, mode=2, split_k=split_g, k_dev=w.Nb_dev,
+            ops.gemm_desc(gm.d_gh, gm.h, fgm, m=3 * D, n=D, k=w.Nb, lda=3 * D, ldb=D, ldc=D, trans_a=True,
+                          trans_b=True, mode=2, split_k=split_g, k_dev=rows_dev,
                           c_off=off["memory_updater.weight_hh"]),
         ]
         if self.Dt:
             # d x = d_gi W_ih: only the time-encoding columns [2D+De, Dx) are consumed (memory-side
             # TimeEncoder gradient), so only those are computed, from the 16-byte aligned column below them
-            g.append(ops.gemm_desc(w.d_gi, fl, w.d_x, m=w.Nb, n=self.Dx - c0, k=3 * D, lda=3 * D, ldb=self.ldx,
+            g.append(ops.gemm_desc(gm.d_gi, fl, gm.d_x, m=w.Nb, n=self.Dx - c0, k=3 * D, lda=3 * D, ldb=self.ldx,
                                    ldc=self.ldx, trans_b=True, b_off=off["memory_updater.weight_ih"] + c0, c_off=c0,
-                                   m_dev=w.Nb_dev))
+                                   m_dev=rows_dev))
         ops.gemm_batch(g, self.prec)
         if self.Dt:
-            check(L.tgn_time_bwd_sin(_p(w.sel_dt), _p(w.sel_ev), w.Nb, _p(w.Nb_dev), _p(w.sn_m), self.Dt,
-                                     w.d_x.data_ptr() + 4 * (2 * D + self.De), self.ldx,
-                                     gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), s))
+            check(L.tgn_time_bwd_sin(_p(gm.sel_dt), _p(gm.sel_ev), w.Nb, _p(rows_dev), _p(gm.sn_m), self.Dt,
+                                     gm.d_x.data_ptr() + 4 * (2 * D + self.De), self.ldx,
+                                     gptr_m("time_enc.lin.weight"), gptr_m("time_enc.lin.bias"), s))
         main.wait_stream(aux)
         main.wait_stream(side)
         main.wait_stream(upd)
+        if own:
+            # rank barrier C: every rank's gradients are final; then one optimiser launch that reads rank 0's
+            # replicated part and sums the partial parts of all ranks out of peer memory (no NCCL in the graph)
+            self._symm_mem.barrier(channel=2)
+            check(L.tgn_adam_finish_peers(_p(self.flat), self._grad_rep0, self._peer_grad_part, self.world,
+                                          _p(self.exp_avg), _p(self.exp_avg_sq), self.n_param, self.lr, 0.9, 0.999,
+                                          1e-8, _p(self.adam_step_dev), _p(self.step_dev), _p(self.loss_acc),
+                                          self.loss_slots.data_ptr() + 4 * self.cur, _p(self.done_ctr), _stream()))
+            return
         if self.world > 1:   # replicated compute: average the gradients so the weight replicas stay bit-identical
             self._all_reduce(self.flat_grad)
             self.flat_grad.mul_(1.0 / self.world)

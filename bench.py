@@ -409,10 +409,15 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=400, help="bounded sample of the CPU baseline leg")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     ap.add_argument("--no-eval-dp", action="store_true")
+    ap.add_argument("--only-eval-dp", action="store_true", help="run just the data-parallel evaluation leg (development)")
+    ap.add_argument("--eval-replicated", action="store_true", help="eval leg: every rank embeds every root (round-1 design)")
     ap.add_argument("--no-partitioned", action="store_true")
+    ap.add_argument("--only-partitioned", action="store_true", help="run just the partitioned-memory leg (development)")
     ap.add_argument("--no-wiki", action="store_true", help="skip the wiki-shape legs (configs[0], batch 200 and 2000)")
     ap.add_argument("--no-module-path", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--part-compute", default="owner", choices=["owner", "replicated"],
+                    help="partitioned-memory leg: owner-side compute of the memory path, or the replicated round-1 design")
     ap.add_argument("--part-exchange", default="p2p", choices=["p2p", "allreduce"],
                     help="row assembly of the partitioned-memory leg: peer reads over symmetric memory, or NCCL all-reduce")
     ap.add_argument("--eval-batches", type=int, default=30)
@@ -467,6 +472,25 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    if args.only_eval_dp:
+        r = bench_eval_dp(dev, rank, world, args.eval_batches, args.precision, shard=not args.eval_replicated)
+        if rank == 0:
+            emit(r)
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+        return
+    if args.only_partitioned:
+        part = bench_partitioned(dev, rank, world, max(60, min(K_steps, 300)), W, args.precision, args.part_exchange,
+                                 args.part_compute)
+        if rank == 0:
+            emit(part)
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+        return
     clocks = ClockSampler(local_rank)
     head, eng = gpu_leg(name, B, K_steps, W, prefill, dev, rank, world, args.precision, clocks)
 
@@ -506,10 +530,11 @@ def main():
 
     part = None
     if not args.no_partitioned:
-        part = guarded(bench_partitioned, dev, rank, world, min(K_steps, 300), W, args.precision, args.part_exchange)
+        part = guarded(bench_partitioned, dev, rank, world, max(60, min(K_steps, 300)), W, args.precision,
+                       args.part_exchange, args.part_compute)
     eval_dp = None
     if not args.no_eval_dp:
-        eval_dp = guarded(bench_eval_dp, dev, rank, world, args.eval_batches, args.precision)
+        eval_dp = guarded(bench_eval_dp, dev, rank, world, args.eval_batches, args.precision, not args.eval_replicated)
 
     if rank == 0:
         peaks = {}
@@ -569,7 +594,7 @@ def main():
         os._exit(0)
 
 
-def bench_partitioned(dev, rank, world, steps, warmup, precision, exchange="p2p"):
+def bench_partitioned(dev, rank, world, steps, warmup, precision, exchange="p2p", compute="owner"):
     """ONE training job with the node memory partitioned by owner over the ranks (BASELINE.json
     configs[2]): synthetic tgbl-coin shape (638,486 nodes), batch 600, K=10.  Node n lives on rank
     n % world; the shards are symmetric memory mapped into every rank, so the rows a step needs are read
@@ -582,24 +607,24 @@ def bench_partitioned(dev, rank, world, steps, warmup, precision, exchange="p2p"
     name, prefill = "tgbl-coin", 600_000
     cfg = synth.SHAPES[name]
     B, K = cfg["B"], cfg["K"]
-    data = synth.synth_events(name, seed=0, max_events=prefill + (warmup + steps + 8) * B)
+    data = synth.synth_events(name, seed=0, max_events=prefill + (max(warmup, 52) + 4 * 9 + steps + 12) * B)
     N, De = data["num_nodes"], data["raw_dim"]
     eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.1, use_graph=True,
                     log_capacity=data["src"].size, seed=99, precision=precision, rank=rank, world=world,
-                    fused_zero_grad=True, part_exchange=exchange)
+                    fused_zero_grad=True, part_exchange=exchange, part_compute=compute)
     eng.load_state(*init_state_dicts(De, HIDDEN, N, seed=1))
     eng.set_events(**{k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")})
     ring = ring_after(data["src"][:prefill], data["dst"][:prefill], data["t"][:prefill], K, N)
     eng.prefill(prefill, tuple(torch.from_numpy(a) for a in ring))
-    for _ in range(max(warmup, 6)):
+    eng.train_steps(max(warmup, 52))          # eager warm-up calls + the captures of the three-step graphs
+    for _ in range(4 * eng.nslots):             # ... and of the single-step graphs (steps % 3 leftovers)
         eng.train_step(from_device=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
-        eng.train_step(from_device=True)
+    eng.train_steps(steps)
     e1.record()
     if world > 1:
         dist.barrier()
@@ -609,17 +634,31 @@ def bench_partitioned(dev, rank, world, steps, warmup, precision, exchange="p2p"
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     rows = int(eng.w.Nb_dev.item())
+    owned = int(eng.wo.So_dev.item()) if eng.owner_compute else rows
+    eng.check_device_errors()
+    D = HIDDEN
+    # bytes this rank moves over NVLink per step (owner compute): rows published to the P-1 peers, remote rows
+    # read for the messages (other endpoints, (P-1)/P of them remote), gradients read by the optimiser
+    nvl = (owned * (4 * D + 8) * (world - 1) + owned * 4 * D * (world - 1) // max(world, 1)
+           + 4 * eng.n_param * (world - 1 + (1 if rank else 0))) if eng.owner_compute else None
     return {"metric": "train events/sec (TGN step), node memory partitioned by owner", "value": steps * B / (ms / 1e3),
+            "compute": ("owner-side: message build + GRU forward/backward only on owned rows" if eng.owner_compute
+                        else ("replicated on every rank" if world > 1 else "single GPU")),
+            "rows_owned_last_step": owned, "nvlink_bytes_per_step_per_rank": nvl,
             "unit": "events/s", "n_gpus": world, "ms_per_step": ms / steps, "steps": steps, "scaling": "strong",
             "final_loss": float(eng.loss), "rows_per_step": rows,
             "memory_rows_per_gpu": eng.Nloc, "memory_bytes_per_gpu": eng.Nloc * HIDDEN * 4,
             "workload": f"synthetic {name} shape: {N} nodes, raw_dim {De}, batch {B}, {K} recent nbrs, dim {HIDDEN}",
             "exchange": eng.part_exchange,
-            "collectives_per_step": ("peer-memory row gather between two signal-pad rank barriers (no data "
-                                     "collective), all-reduce of the flat gradient") if world > 1 else "none (single GPU)"}
+            "collectives_per_step": ("none (single GPU)" if world == 1 else
+                                     "no NCCL call: remote memory rows read and result rows published over the peer "
+                                     "mapping, partial gradients summed inside the optimiser kernel out of peer memory; "
+                                     "three signal-pad rank barriers" if eng.owner_compute else
+                                     "peer-memory row gather between two signal-pad rank barriers, NCCL all-reduce of "
+                                     "the flat gradient")}
 
 
-def bench_eval_dp(dev, rank, world, n_batches, precision):
+def bench_eval_dp(dev, rank, world, n_batches, precision, shard=True):
     """TGB evaluation with the negatives scored data-parallel (BASELINE.json configs[4]): synthetic
     tgbl-flight shape (18,143 nodes, D_e=16), 200 positives x 999 negatives per batch, negative
     columns sharded round-robin over the ranks, one all-reduce of the 2*B rank counts per batch
@@ -645,13 +684,13 @@ def bench_eval_dp(dev, rank, world, n_batches, precision):
         sl = slice(prefill + b * B, prefill + (b + 1) * B)
         neg = torch.from_numpy(synth.eval_negatives(data["src"][sl], data["dst"][sl], N, Q, seed=1000 + b))
         batches.append(tuple(x.to(dev) for x in (ev["src"][sl], ev["dst"][sl], neg, ev["t"][sl], ev["msg"][sl])))
-    dist_eval.evaluate_dp(eng, batches[:warm], rank, world)
+    dist_eval.evaluate_dp(eng, batches[:warm], rank, world, shard_embeddings=shard)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    mrr = dist_eval.evaluate_dp(eng, batches[warm:], rank, world)
+    mrr = dist_eval.evaluate_dp(eng, batches[warm:], rank, world, shard_embeddings=shard)
     e1.record()
     if world > 1:
         dist.barrier()
@@ -665,7 +704,10 @@ def bench_eval_dp(dev, rank, world, n_batches, precision):
             "ms_per_batch": ms / n_batches, "batches": n_batches, "mrr": mrr, "scaling": "strong",
             "workload": f"synthetic tgbl-flight shape: {N} nodes, raw_dim {De}, batch {B}, {Q} negatives, "
                         f"ring prefilled with {prefill} events",
-            "collective": "one all-reduce(sum) of 2*B int32 rank counts per batch" if world > 1 else "none"}
+            "embedding": ("sharded: every root embedded on one rank, decoder-projected rows all-gathered" if shard
+                          else "replicated: every rank embeds every root"),
+            "collective": (("one all-gather of the projected rows [2, roots/P, 100] fp32 + " if shard else "") +
+                           "one all-reduce(sum) of 2*B int32 rank counts per batch") if world > 1 else "none"}
 
 
 def dominant_kernel_roofline(eng, dev):

@@ -538,6 +538,11 @@ int32_t tgn_dec_fused(const float* emb, const int64_t* ids_local, int32_t batch,
  * outputs; gt_out[i] = #{neg > pos}, ge_out[i] = #{neg >= pos} (the two counts of the TGB MRR
  * rank = 1 + (gt + ge)/2, additive over shards of the negatives, so data-parallel evaluation
  * all-reduces 2 integers per positive).  neg_out [num_pos, num_neg] is optional. */
+/* out[i] = in[offset + i*stride] while that entry exists (i < *out_count_dev), -1 beyond: one rank's
+ * round-robin share of a sorted unique root list (data-parallel evaluation embeds every root on exactly
+ * one rank, epoch_utils.py:74-99). */
+int32_t tgn_stride_select(const int64_t* in, int32_t num_in, const int32_t* num_in_dev, int32_t offset,
+                          int32_t stride, int64_t* out, int32_t out_cap, int32_t* out_count_dev, void* stream);
 int32_t tgn_score_negs(const float* hs, const float* hd, const int64_t* src_rows,
                        const int64_t* dst_rows, const int64_t* neg_rows, int32_t num_pos,
                        int32_t num_neg, int32_t dim, const float* w_final, const float* b_final,

@@ -389,3 +389,29 @@ def test_tail_batch_engine_shares_state():
     assert torch.equal(eng.last_update.cpu(), ref["memory"].last_update)
     assert torch.equal(eng.e_id.cpu(), loader.e_id)
     torch.testing.assert_close(eng.memory.cpu(), ref["memory"].memory.detach(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("Q,dense", [(20, False), (37, True)])
+def test_sharded_embedding_eval_equals_replicated_eval(Q, dense):
+    """eval_batch_dp (roots dealt to ranks, decoder-projected rows gathered, own negative columns scored) with a
+    single rank == eval_batch: same scores, same TGB counts, same state afterwards.  `dense` = the candidates
+    cover the graph several times, every node is treated as a root (no unique / relabel of the candidate list)."""
+    from tgn_b200 import synth
+    N, De, D, K, B, steps = (60 if dense else 300), 8, 16, 5, 40, 5
+    _, eng_a, ev = _setup(N, De, D, K, B, B * steps, 21, False)
+    _, eng_b, _ = _setup(N, De, D, K, B, B * steps, 21, False)
+    for e in (eng_a, eng_b):
+        e.flush_to_eval()
+    for s in range(steps):
+        sl = slice(s * B, (s + 1) * B)
+        src, dst, t, msg = ev["src"][sl], ev["dst"][sl], ev["t"][sl], ev["msg"][sl]
+        neg = torch.from_numpy(synth.eval_negatives(src.numpy(), dst.numpy(), N, Q, seed=s, dst_lo=N // 2))
+        pos_a, _, gt_a, ge_a = eng_a.eval_batch(src, dst, neg, t, msg, want_neg_scores=False)
+        pos_b, gt_b, ge_b = eng_b.eval_batch_dp(src, dst, neg, t, msg, 0, 1)
+        assert eng_b._eval_ctx_dp(B, Q, 0, 1).dense == dense
+        torch.testing.assert_close(pos_a, pos_b, rtol=1e-5, atol=1e-6)
+        assert torch.equal(gt_a, gt_b) and torch.equal(ge_a, ge_b), s
+        torch.cuda.synchronize()
+        assert torch.equal(eng_a.last_update, eng_b.last_update) and torch.equal(eng_a.e_id, eng_b.e_id)
+        torch.testing.assert_close(eng_a.memory, eng_b.memory, rtol=1e-5, atol=1e-6)
+    eng_b.check_device_errors()

@@ -943,6 +943,10 @@ __global__ void __launch_bounds__(256)
   __shared__ float s_pos;
   __shared__ int s_gt, s_ge;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // blockIdx.y = part of the negative columns (the chain index -> row -> reduce of one negative is ~1 us per
+  // warp iteration, so a positive's Q negatives are spread over gridDim.y CTAs); counts add up atomically
+  const int parts = gridDim.y, part = blockIdx.y;
+  const int qlo = (int)((long long)Q * part / parts), qhi = (int)((long long)Q * (part + 1) / parts);
   for (int i = blockIdx.x; i < B; i += gridDim.x) {
     __syncthreads();
     const float* pa = hs + src_rows[i] * D;
@@ -960,13 +964,13 @@ __global__ void __launch_bounds__(256)
       if (lane == 0) {
         const float p = 1.f / (1.f + expf(-(acc + bf[0])));
         s_pos = p;
-        pos_out[i] = p;
+        if (part == 0) pos_out[i] = p;
       }
     }
     __syncthreads();
     const float p = s_pos;
     int gt = 0, ge = 0;
-    for (int q = wid; q < Q; q += nw) {
+    for (int q = qlo + wid; q < qhi; q += nw) {
       const float* pb = hd + neg_rows[(long long)i * Q + q] * D;
       float acc = 0.f;
       for (int c = lane; c < D; c += 32) acc = fmaf(fmaxf(s_a[c] + pb[c], 0.f), s_a[D + c], acc);
@@ -982,10 +986,28 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      gt_out[i] = s_gt;
-      ge_out[i] = s_ge;
+      if (parts == 1) {
+        gt_out[i] = s_gt;
+        ge_out[i] = s_ge;
+      } else {            // zero-filled by the wrapper
+        atomicAdd(&gt_out[i], s_gt);
+        atomicAdd(&ge_out[i], s_ge);
+      }
     }
   }
+}
+
+// out[i] = in[offset + i * stride] for the entries that exist, -1 beyond (ids < 0 are ignored by the
+// marking kernels); *out_count = how many exist.  Picks one rank's share of a sorted root list.
+__global__ void stride_select_kernel(const int64_t* __restrict__ in, DevCount n_in, int offset, int stride,
+                                     int64_t* __restrict__ out, int out_cap, int32_t* __restrict__ out_count) {
+  pdl_wait();
+  pdl_launch();
+  const int n = n_in.get();
+  const int cnt = n > offset ? (n - offset + stride - 1) / stride : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < out_cap; i += gridDim.x * blockDim.x)
+    out[i] = i < cnt ? in[offset + (long long)i * stride] : -1;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && out_count) *out_count = cnt < out_cap ? cnt : out_cap;
 }
 
 __global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ rows,
@@ -1218,9 +1240,26 @@ int32_t tgn_score_negs(const float* hs, const float* hd, const int64_t* src_rows
                   b_final && pos_out && gt_out && ge_out,
               "score_negs: NULL pointer");
   int grid = num_pos < 8 * kNumSMs ? num_pos : 8 * kNumSMs;
-  launch_k(score_negs_kernel, dim3(grid), dim3(256), (size_t)2 * dim * sizeof(float), (cudaStream_t)stream, 
+  int parts = (num_neg + 127) / 128;
+  parts = parts < 1 ? 1 : (parts > 8 ? 8 : parts);
+  if (parts > 1) {
+    TGN_CUDA(cudaMemsetAsync(gt_out, 0, (size_t)num_pos * sizeof(int32_t), (cudaStream_t)stream));
+    TGN_CUDA(cudaMemsetAsync(ge_out, 0, (size_t)num_pos * sizeof(int32_t), (cudaStream_t)stream));
+  }
+  launch_k(score_negs_kernel, dim3(grid, parts), dim3(256), (size_t)2 * dim * sizeof(float), (cudaStream_t)stream, 
       hs, hd, src_rows, dst_rows, neg_rows, num_pos, num_neg, dim, w_final, b_final, pos_out,
       neg_out, gt_out, ge_out);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_stride_select(const int64_t* in, int32_t num_in, const int32_t* num_in_dev, int32_t offset,
+                          int32_t stride, int64_t* out, int32_t out_cap, int32_t* out_count_dev, void* stream) {
+  TGN_REQUIRE(num_in >= 0 && offset >= 0 && stride >= 1 && out_cap >= 0, "stride_select: bad sizes");
+  if (out_cap == 0) return TGN_OK;
+  TGN_REQUIRE(in && out, "stride_select: NULL pointer");
+  launch_k(stride_select_kernel, dim3(stride_grid(out_cap, 256)), dim3(256), 0, (cudaStream_t)stream, in,
+           DevCount{num_in_dev, num_in}, offset, stride, out, out_cap, out_count_dev);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

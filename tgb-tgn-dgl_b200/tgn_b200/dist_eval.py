@@ -59,10 +59,18 @@ def eval_batch_dp(count_fn: Callable[[Tensor], Tuple[Tensor, Tensor]], neg: Tens
     return reciprocal_ranks(gt, ge)
 
 
-def evaluate_dp(engine, batches, rank: int = 0, world: int = 1, group=None) -> float:
+def evaluate_dp(engine, batches, rank: int = 0, world: int = 1, group=None, shard_embeddings: bool = False) -> float:
     """epoch loop of test() (epoch_utils.py:28-165) on TGNEngine replicas: `batches` yields
-    (src, dst, neg[B,Q], t, msg); returns the epoch MRR (mean of per-batch means)."""
+    (src, dst, neg[B,Q], t, msg); returns the epoch MRR (mean of per-batch means).
+    shard_embeddings=True: TGNEngine.eval_batch_dp -- every root of a batch is embedded on exactly one rank and
+    the decoder-projected rows are all-gathered, instead of every rank embedding every root."""
     per_batch: List[Tensor] = []
+    if shard_embeddings:
+        for src, dst, neg, t, msg in batches:
+            _, gt, ge = engine.eval_batch_dp(src, dst, neg, t, msg, rank, world, group)
+            gt, ge = reduce_counts(gt, ge, group)
+            per_batch.append(reciprocal_ranks(gt, ge).mean())
+        return float(torch.stack(per_batch).mean())
     for src, dst, neg, t, msg in batches:
         def count_fn(shard, _a=(src, dst, t, msg)):
             _, _, gt, ge = engine.eval_batch(_a[0], _a[1], shard, _a[2], _a[3], want_neg_scores=False)

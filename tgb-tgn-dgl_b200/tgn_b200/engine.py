@@ -680,8 +680,10 @@ class TGNEngine:
         e1.record()
         self.probe.setdefault(name, []).append((e0, e1))
 
-    def _sample(self, w, ids: Tensor, ids_l: Tensor):
-        """roots -> neighbour lookup -> union -> relabel; everything bound-sized, counts on device."""
+    def _sample(self, w, ids: Tensor, ids_l: Tensor, ids_dev: Optional[Tensor] = None):
+        """roots -> neighbour lookup -> union -> relabel; everything bound-sized, counts on device.
+        ids_dev: device count of the valid prefix of `ids` (entries beyond it must be -1: the marking
+        kernels ignore them, the relabel stops in front of them)."""
         N, K = self.N, self.K
         L, s = _L(), _stream()
         if ids.numel() <= 8192:   # small id list: marking folded into the single-CTA ranking launch
@@ -695,7 +697,7 @@ class TGNEngine:
                                _p(w.root_off), _p(w.E_dev), _p(self.bitmap), _p(w.lookup_ws), s))
         check(L.tgn_unique_rank(_p(self.bitmap), N, _p(w.n_id), w.Nb, _p(self.assoc), _p(w.Nb_dev), 0, s))
         check(L.tgn_relabel3(_p(w.nbr_g), w.E, _p(w.E_dev), _p(w.nbr_l), _p(w.roots), w.R, _p(w.R_dev),
-                             _p(w.ctr_l), _p(ids), ids.numel(), None, _p(ids_l), _p(self.assoc), s))
+                             _p(w.ctr_l), _p(ids), ids.numel(), _p(ids_dev), _p(ids_l), _p(self.assoc), s))
 
     def _assemble_rows(self, w, n_id: Tensor, S: int, S_dev: Optional[Tensor]):
         """Partitioned memory: every rank writes the memory rows it owns (rows of n_id and of the
@@ -1327,6 +1329,127 @@ class TGNEngine:
         self._run(("eval", B, Q), lambda: self._eval_body(c))
         self._advance(B)
         return c.pos, (c.negs[:, :Q] if want_neg_scores else None), c.gt, c.ge
+
+    # ---- data-parallel evaluation with the EMBEDDING sharded as well (epoch_utils.py:74-113)
+    def _eval_ctx_dp(self, B: int, Q: int, rank: int, P: int) -> SimpleNamespace:
+        ctxs = self.__dict__.setdefault("_ectx", {})
+        c = ctxs.get(("dp", B, Q, rank, P))
+        if c is not None:
+            return c
+        dev, D, N = self.dev, self.D, self.N
+        n_ids = B * (2 + Q)
+        c = SimpleNamespace(B=B, Q=Q, rank=rank, P=P, n_ids=n_ids)
+        # the candidates of a batch cover (nearly) every node (flight: 200 x 1001 ids over 18k nodes): every
+        # node is a root, no unique / relabel of the 200k ids is needed, rank r embeds the nodes r, r+P, ...
+        c.dense = n_ids >= 4 * N
+        c.Rall = N if c.dense else min(N, n_ids)
+        c.Rm = (c.Rall + P - 1) // P
+        R, E, Nb = self._bounds(B, roots=c.Rm)
+        c.w = self._alloc_work(R, E, Nb, B, train=False)
+        c.mw = self._alloc_work(1, 1, 2 * B, 1, train=False)
+        i64 = lambda *s_: torch.zeros(s_, dtype=torch.long, device=dev)
+        i32 = lambda *s_: torch.zeros(s_, dtype=torch.int32, device=dev)
+        c.ids, c.ids_g = i64(n_ids), i64(n_ids)
+        c.t_i, c.t_f = i64(B), torch.zeros(B, device=dev)
+        c.msg = torch.zeros((B, max(self.De, 1)), device=dev)
+        c.pos, c.gt, c.ge = torch.zeros(B, device=dev), i32(B), i32(B)
+        c.n_upd, c.U_dev = i64(2 * B), i32(1)
+        c.roots_all, c.Rall_dev = i64(c.Rall), i32(1)
+        c.my_roots, c.Rm_dev, c.my_l = torch.full((c.Rm,), -1, dtype=torch.long, device=dev), i32(1), i64(c.Rm)
+        if c.dense:
+            mine = torch.arange(rank, N, P, device=dev)
+            c.my_roots[:mine.numel()] = mine
+            c.Rm_dev.fill_(mine.numel())
+        c.e_r = torch.zeros((c.Rm, D), device=dev)
+        c.send = torch.zeros((2, c.Rm, D), device=dev)               # [lin_src(emb) | lin_dst(emb)] of my centres
+        c.recv = torch.zeros((P, 2, c.Rm, D), device=dev) if P > 1 else c.send.view(1, 2, c.Rm, D)
+        c.Qr = len(range(rank, Q, P))
+        c.src_rows, c.dst_rows, c.neg_rows = i64(B), i64(B), i64(B, max(c.Qr, 1))
+        ctxs[("dp", B, Q, rank, P)] = c
+        return c
+
+    def _eval_body_dp(self, c: SimpleNamespace, group):
+        N, D, L = self.N, self.D, _L()
+        B, Q, P, rank, w, mw = c.B, c.Q, c.P, c.rank, c.w, c.mw
+        main, upd = torch.cuda.current_stream(), self.upd
+        if not c.dense:      # global rank of every candidate in the sorted unique root list; my share of the roots
+            if c.n_ids <= 8192:
+                check(L.tgn_unique_mark_rank(_p(c.ids), c.n_ids, _p(self.bitmap), N, _p(c.roots_all), c.Rall,
+                                             _p(self.assoc), _p(c.Rall_dev), 0, _stream()))
+            else:
+                check(L.tgn_unique_mark(_p(c.ids), c.n_ids, None, N, _p(self.bitmap), _stream()))
+                check(L.tgn_unique_rank(_p(self.bitmap), N, _p(c.roots_all), c.Rall, _p(self.assoc), _p(c.Rall_dev), 0,
+                                        _stream()))
+            check(L.tgn_relabel(_p(c.ids), c.n_ids, None, _p(self.assoc), _p(c.ids_g), _stream()))
+            check(L.tgn_stride_select(_p(c.roots_all), c.Rall, _p(c.Rall_dev), rank, P, _p(c.my_roots), c.Rm,
+                                      _p(c.Rm_dev), _stream()))
+        self._sample(w, c.my_roots, c.my_l, ids_dev=c.Rm_dev)
+        s = _stream()
+        check(L.tgn_gather_rows(_p(self.memory), _p(w.n_id), w.Nb, _p(w.Nb_dev), D, _p(w.z), s))
+        check(L.tgn_relabel(_p(w.n_id), w.Nb, _p(w.Nb_dev), _p(self.last_update), _p(w.lu), s))
+        # ---- forked: the batch's state update (store first, then memory: memory_module.py:135-138; then the ring).
+        # It needs the batch only, and may start once this batch's sampling and memory reads are issued.
+        upd.wait_stream(main)
+        with torch.cuda.stream(upd):
+            src, dst = c.ids[:B], c.ids[B:2 * B]
+            self.store.update(src, dst, c.t_i, c.msg, base_dev=self.log_base_dev)
+            check(L.tgn_unique_mark_rank(_p(c.ids), 2 * B, _p(self.bitmap), N, _p(c.n_upd), 2 * B, None, _p(c.U_dev), 0,
+                                         _stream()))
+            self._memory_fwd(mw, c.n_upd, 2 * B, c.U_dev)
+            self._scatter_owned(c.n_upd, mw.z, mw.lu, self.memory, self.last_update, num_dev=c.U_dev)
+            check(L.tgn_nbr_insert(_p(src), _p(dst), _p(c.t_f), B, 0, _p(self.cur_e_id_dev), self.K, N,
+                                   _p(self.neighbors), _p(self.e_id), _p(self.t_ring), _stream()))
+        self._attention_fwd(w, w.z, w.lu, False)
+        p, off = self.p, self.off
+        check(L.tgn_gather_rows(_p(w.emb), _p(c.my_l), c.Rm, _p(c.Rm_dev), D, _p(c.e_r), _stream()))
+        ops.gemm_batch([
+            ops.gemm_desc(c.e_r, self.flat, c.send, m=c.Rm, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_src.weight"],
+                          bias=p["lin_src.bias"], m_dev=c.Rm_dev),
+            ops.gemm_desc(c.e_r, self.flat, c.send, m=c.Rm, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_dst.weight"],
+                          bias=p["lin_dst.bias"], m_dev=c.Rm_dev, c_off=c.Rm * D),
+        ], self.prec)
+        if P > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(c.recv, c.send, group=group)
+        # row of global root g in the gathered table: block of its rank (g % P), position g // P
+        g = c.ids if c.dense else c.ids_g
+        rows = (g % P) * (2 * c.Rm) + g // P
+        c.src_rows.copy_(rows[:B])
+        c.dst_rows.copy_(rows[B:2 * B])
+        if c.Qr:
+            c.neg_rows.copy_(rows[2 * B:].view(B, Q)[:, rank::P])
+        check(L.tgn_score_negs(_p(c.recv), c.recv.data_ptr() + 4 * c.Rm * D, _p(c.src_rows), _p(c.dst_rows),
+                               _p(c.neg_rows), B, c.Qr, D, _p(p["lin_final.weight"]), _p(p["lin_final.bias"]),
+                               _p(c.pos), None, _p(c.gt), _p(c.ge), _stream()))
+        main.wait_stream(upd)
+
+    @torch.no_grad()
+    def eval_batch_dp(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor, rank: int = 0,
+                      world: int = 1, group=None):
+        """eval_batch for data-parallel evaluation over `world` model replicas, with the embedding sharded too:
+        `neg` is the FULL [B, Q] negative matrix on every rank.  The roots of the batch (unique candidates) are
+        dealt round-robin; each rank samples / gathers / embeds only its roots and projects them through the
+        decoder's two linears, ONE all-gather assembles the projected rows on every rank, and each rank scores
+        its column shard of the negatives.  Returns (pos[B], gt[B], ge[B]) with the counts of THIS rank's
+        columns (sum them over the ranks: dist_eval.reduce_counts).  The state update is replicated and runs on
+        a forked stream beside the embedding."""
+        if self.world != 1:
+            raise _cabi.TgnError("eval_batch_dp runs on model replicas (world == 1 engines), one per rank")
+        self._unprime()
+        B, Q = neg.shape
+        c = self._eval_ctx_dp(B, Q, rank, world)
+        self._reserve(B)
+        c.ids[:B].copy_(src, non_blocking=True)
+        c.ids[B:2 * B].copy_(dst, non_blocking=True)
+        if Q:
+            c.ids[2 * B:].view(B, Q).copy_(neg, non_blocking=True)
+        c.t_i.copy_(t, non_blocking=True)
+        c.t_f.copy_(c.t_i)
+        if self.De:
+            c.msg.copy_(msg, non_blocking=True)
+        self._run(("eval_dp", B, Q, rank, world), lambda: self._eval_body_dp(c, group))
+        self._advance(B)
+        return c.pos, c.gt, c.ge
 
     def eval_scores(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor):
         """(pos[B], neg[B,Q]) probabilities of one evaluation batch (see eval_batch)."""

@@ -66,11 +66,12 @@ def evaluate_dp(engine, batches, rank: int = 0, world: int = 1, group=None, shar
     the decoder-projected rows are all-gathered, instead of every rank embedding every root."""
     per_batch: List[Tensor] = []
     if shard_embeddings:
+        # counts all-reduced and the epoch metric accumulated inside the captured step: one host read per epoch
+        if hasattr(engine, "mrr_acc"):
+            engine.mrr_acc.zero_()
         for src, dst, neg, t, msg in batches:
-            _, gt, ge = engine.eval_batch_dp(src, dst, neg, t, msg, rank, world, group)
-            gt, ge = reduce_counts(gt, ge, group)
-            per_batch.append(reciprocal_ranks(gt, ge).mean())
-        return float(torch.stack(per_batch).mean())
+            engine.eval_batch_dp(src, dst, neg, t, msg, rank, world, group, reduce=True)
+        return engine.epoch_mrr()
     for src, dst, neg, t, msg in batches:
         def count_fn(shard, _a=(src, dst, t, msg)):
             _, _, gt, ge = engine.eval_batch(_a[0], _a[1], shard, _a[2], _a[3], want_neg_scores=False)

@@ -1352,7 +1352,9 @@ class TGNEngine:
         c.ids, c.ids_g = i64(n_ids), i64(n_ids)
         c.t_i, c.t_f = i64(B), torch.zeros(B, device=dev)
         c.msg = torch.zeros((B, max(self.De, 1)), device=dev)
-        c.pos, c.gt, c.ge = torch.zeros(B, device=dev), i32(B), i32(B)
+        c.pos, c.cnt = torch.zeros(B, device=dev), i32(2, B)
+        c.gt, c.ge = c.cnt[0], c.cnt[1]              # one tensor: the two counts travel in ONE all-reduce
+        c.rr = torch.zeros(B, device=dev)
         c.n_upd, c.U_dev = i64(2 * B), i32(1)
         c.roots_all, c.Rall_dev = i64(c.Rall), i32(1)
         c.my_roots, c.Rm_dev, c.my_l = torch.full((c.Rm,), -1, dtype=torch.long, device=dev), i32(1), i64(c.Rm)
@@ -1421,23 +1423,36 @@ class TGNEngine:
         check(L.tgn_score_negs(_p(c.recv), c.recv.data_ptr() + 4 * c.Rm * D, _p(c.src_rows), _p(c.dst_rows),
                                _p(c.neg_rows), B, c.Qr, D, _p(p["lin_final.weight"]), _p(p["lin_final.bias"]),
                                _p(c.pos), None, _p(c.gt), _p(c.ge), _stream()))
+        if c.reduce:
+            # the TGB rank needs the counts over ALL columns: one all-reduce of 2*B int32 inside the graph, then
+            # the batch's mean reciprocal rank is added to the epoch accumulator on the device (epoch_utils.py:113,163)
+            if P > 1:
+                import torch.distributed as dist
+                dist.all_reduce(c.cnt, group=group)
+            check(L.tgn_rank_accum(_p(c.gt), _p(c.ge), B, _p(self.mrr_acc), _p(c.rr), _stream()))
         main.wait_stream(upd)
 
     @torch.no_grad()
     def eval_batch_dp(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor, rank: int = 0,
-                      world: int = 1, group=None):
+                      world: int = 1, group=None, reduce: bool = False):
         """eval_batch for data-parallel evaluation over `world` model replicas, with the embedding sharded too:
         `neg` is the FULL [B, Q] negative matrix on every rank.  The roots of the batch (unique candidates) are
         dealt round-robin; each rank samples / gathers / embeds only its roots and projects them through the
         decoder's two linears, ONE all-gather assembles the projected rows on every rank, and each rank scores
         its column shard of the negatives.  Returns (pos[B], gt[B], ge[B]) with the counts of THIS rank's
         columns (sum them over the ranks: dist_eval.reduce_counts).  The state update is replicated and runs on
-        a forked stream beside the embedding."""
+        a forked stream beside the embedding.
+        reduce=True: the counts are all-reduced INSIDE the captured step and the batch's mean reciprocal rank is
+        added to self.mrr_acc (float64 [2] on the device: sum of per-batch means, number of batches; read it once
+        per epoch with epoch_mrr()); the returned counts are then the global ones."""
         if self.world != 1:
             raise _cabi.TgnError("eval_batch_dp runs on model replicas (world == 1 engines), one per rank")
         self._unprime()
         B, Q = neg.shape
         c = self._eval_ctx_dp(B, Q, rank, world)
+        c.reduce = reduce
+        if not hasattr(self, "mrr_acc"):
+            self.mrr_acc = torch.zeros(2, dtype=torch.float64, device=self.dev)
         self._reserve(B)
         c.ids[:B].copy_(src, non_blocking=True)
         c.ids[B:2 * B].copy_(dst, non_blocking=True)
@@ -1447,9 +1462,17 @@ class TGNEngine:
         c.t_f.copy_(c.t_i)
         if self.De:
             c.msg.copy_(msg, non_blocking=True)
-        self._run(("eval_dp", B, Q, rank, world), lambda: self._eval_body_dp(c, group))
+        self._run(("eval_dp", B, Q, rank, world, reduce), lambda: self._eval_body_dp(c, group))
         self._advance(B)
         return c.pos, c.gt, c.ge
+
+    def epoch_mrr(self, reset: bool = True) -> float:
+        """mean over the batches of the per-batch mean reciprocal rank accumulated by eval_batch_dp(reduce=True)
+        (epoch_utils.py:163); ONE host read per epoch."""
+        acc = self.mrr_acc.tolist()
+        if reset:
+            self.mrr_acc.zero_()
+        return acc[0] / max(acc[1], 1.0)
 
     def eval_scores(self, src: Tensor, dst: Tensor, neg: Tensor, t: Tensor, msg: Tensor):
         """(pos[B], neg[B,Q]) probabilities of one evaluation batch (see eval_batch)."""

@@ -115,14 +115,23 @@ class TGNEngine:
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm_mem
             grp = group if group is not None else dist.group.WORLD
-            self.zero_blob = symm_mem.empty((o + 4 + o + Nb * HC,), dtype=torch.float32, device=dev)
-            self.zero_blob.zero_()
-            self._symm_grad = symm_mem.rendezvous(self.zero_blob, grp)
-            self._peer_grad_part = (ctypes.c_void_p * world)(*[int(q) + 4 * (o + 4) for q in self._symm_grad.buffer_ptrs])
-            self._grad_rep0 = int(self._symm_grad.buffer_ptrs[0])
-            self.flat_grad_part = self.zero_blob[o + 4:o + 4 + o]
-            self.d_emb = self.zero_blob[o + 4 + o:].view(Nb, HC)
-            fused_zero_grad = False      # peers read this rank's gradients: they are cleared after a barrier instead
+            # THREE blobs in rotation (blob = slot % 3; nine slots): the optimiser of a slow rank may still be
+            # reading this rank's gradients of step s while this rank already clears and fills the blob of step
+            # s+1; a blob comes round again three steps later, after two more rank barriers.  That removes the
+            # barrier between one step's optimiser and the next step's gradient clear.
+            self._grad_blobs = []
+            for _ in range(3):
+                blob = symm_mem.empty((o + 4 + o + Nb * HC,), dtype=torch.float32, device=dev)
+                blob.zero_()
+                h = symm_mem.rendezvous(blob, grp)
+                self._grad_blobs.append(SimpleNamespace(
+                    blob=blob, handle=h, rep0=int(h.buffer_ptrs[0]),
+                    peer_part=(ctypes.c_void_p * world)(*[int(q) + 4 * (o + 4) for q in h.buffer_ptrs]),
+                    grad=blob[:o], loss=blob[o:o + 1], part=blob[o + 4:o + 4 + o], d_emb=blob[o + 4 + o:].view(Nb, HC)))
+            g0 = self._grad_blobs[0]
+            self.zero_blob, self._grad_rep0, self._peer_grad_part = g0.blob, g0.rep0, g0.peer_part
+            self.flat_grad_part, self.d_emb = g0.part, g0.d_emb
+            fused_zero_grad = False      # peers read this rank's gradients: a blob is cleared when its turn comes again
         else:
             self.zero_blob = torch.zeros(o + 4 + Nb * HC, device=dev)
             self.flat_grad_part = None
@@ -386,6 +395,10 @@ class TGNEngine:
             setattr(self.w, k, getattr(sl, k))
         self.in_i64, self.in_ids3, self.in_t_i64 = sl.in_i64, sl.in_ids3, sl.in_t_i64
         self.in_t_f32, self.in_msg = sl.in_t_f32, sl.in_msg
+        if getattr(self, "owner_compute", False):      # this step's gradient blob (rotation of three)
+            g = self._grad_blobs[idx % 3]
+            self.zero_blob, self._grad_rep0, self._peer_grad_part = g.blob, g.rep0, g.peer_part
+            self.flat_grad, self.loss_acc, self.flat_grad_part, self.d_emb = g.grad, g.loss, g.part, g.d_emb
 
     def _next_slot(self) -> int:
         return (self.cur + 1) % self.nslots
@@ -876,11 +889,8 @@ class TGNEngine:
         off, fg, fl = self.off, self.flat_grad, self.flat
         main, side, aux, upd = torch.cuda.current_stream(), self.side, self.aux, self.upd
         own = self.owner_compute
-        if own:
-            # rank barrier A: every rank has finished the previous step -- its optimiser has read this rank's
-            # gradients and its owner-side memory writes have landed -- before gradients are cleared here and
-            # memory rows are read out of the peers' shards
-            self._symm_mem.barrier(channel=0)
+        # (owner-side compute: no barrier here.  The previous step's barrier C, in front of its optimiser, came
+        # after every rank's memory write-back, so the peers' shards are current; the gradient blobs rotate.)
         if not self.fused_zero_grad:
             self.zero_blob.zero_()
         if not pipelined:

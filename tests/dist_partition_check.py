@@ -56,6 +56,9 @@ def main():
             # lr-sized weight differences, which would otherwise dominate a free-running comparison
             assert abs(la - lb) < 3e-4 * max(1.0, abs(la)), (use_graph, exchange, compute, s, la, lb)
         fm, fl = parted.full_memory()
+        bad = ((fm - single.memory).abs() > 2e-4 + 2e-3 * single.memory.abs()).any(1).nonzero().view(-1)
+        if rank == 0:
+            print(f"config graph={use_graph} {exchange} {compute}: rows off {bad.numel()} (owners {sorted(set((bad % world).tolist()))})", flush=True)
         torch.testing.assert_close(fm, single.memory, rtol=2e-3, atol=2e-4)
         assert torch.equal(fl, single.last_update)
         assert torch.equal(parted.e_id, single.e_id)

@@ -28,6 +28,7 @@ modules and the CPU oracle.
 from __future__ import annotations
 
 import ctypes
+import os
 from types import SimpleNamespace
 from typing import Dict, Optional
 
@@ -891,6 +892,8 @@ class TGNEngine:
         own = self.owner_compute
         # (owner-side compute: no barrier here.  The previous step's barrier C, in front of its optimiser, came
         # after every rank's memory write-back, so the peers' shards are current; the gradient blobs rotate.)
+        if own and os.environ.get("TGN_PART_BARRIER_A") == "1":
+            self._symm_mem.barrier(channel=0)
         if not self.fused_zero_grad:
             self.zero_blob.zero_()
         if not pipelined:
@@ -986,7 +989,8 @@ class TGNEngine:
             if dec_wgrad:
                 ops.gemm_batch(dec_wgrad, self.prec)
             # bias gradient of the node projection and the attention-side TimeEncoder gradient
-            ops.colsum(w.d_proj, w.Nb, 4 * HC, 4 * HC, p["conv.b_node"].grad, True, rows_dev=w.Nb_dev)
+            ops.colsum(w.d_proj, w.Nb, 4 * HC, 4 * HC, fg[off["conv.b_node"]:off["conv.b_node"] + 4 * HC], True,
+                       rows_dev=w.Nb_dev)
             if self.Dt:
                 check(L.tgn_time_bwd_sin(_p(w.rel), None, w.E, _p(w.E_dev), _p(w.sn_e), self.Dt, _p(w.d_eat), self.Dt,
                                          gptr("time_enc.lin.weight"), gptr("time_enc.lin.bias"), _stream()))

@@ -415,6 +415,8 @@ def main():
     ap.add_argument("--only-partitioned", action="store_true", help="run just the partitioned-memory leg (development)")
     ap.add_argument("--no-wiki", action="store_true", help="skip the wiki-shape legs (configs[0], batch 200 and 2000)")
     ap.add_argument("--no-module-path", action="store_true")
+    ap.add_argument("--no-tcsr", action="store_true", help="skip the configs[3] leg (t-CSR uniform-20, 2 layers)")
+    ap.add_argument("--only-tcsr", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--part-compute", default="owner", choices=["owner", "replicated"],
                     help="partitioned-memory leg: owner-side compute of the memory path, or the replicated round-1 design")
@@ -472,6 +474,15 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    if args.only_tcsr:
+        r = bench_tcsr_two_layer(dev, rank, world)
+        if rank == 0:
+            emit(r)
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+        return
     if args.only_eval_dp:
         r = bench_eval_dp(dev, rank, world, args.eval_batches, args.precision, shard=not args.eval_replicated)
         if rank == 0:
@@ -536,6 +547,9 @@ def main():
     if not args.no_eval_dp:
         eval_dp = guarded(bench_eval_dp, dev, rank, world, args.eval_batches, args.precision, not args.eval_replicated)
 
+    tcsr_leg = None
+    if not args.no_tcsr:
+        tcsr_leg = guarded(bench_tcsr_two_layer, dev, rank, world)
     if rank == 0:
         peaks = {}
         try:
@@ -556,6 +570,8 @@ def main():
             line["partitioned_memory"] = part
         if eval_dp is not None:
             line["eval_dp"] = eval_dp
+        if tcsr_leg is not None:
+            line["tcsr_two_layer"] = tcsr_leg
         if world == 1 and not args.no_kernel_rooflines:
             line["kernel_rooflines"] = guarded(kernel_rooflines, dev, peaks)
         if world == 1 and not args.no_cpu_baseline:
@@ -708,6 +724,69 @@ def bench_eval_dp(dev, rank, world, n_batches, precision, shard=True):
                           else "replicated: every rank embeds every root"),
             "collective": (("one all-gather of the projected rows [2, roots/P, 100] fp32 + " if shard else "") +
                            "one all-reduce(sum) of 2*B int32 rank counts per batch") if world > 1 else "none"}
+
+
+def bench_tcsr_two_layer(dev, rank, world, steps=40, events=4_000_000):
+    """BASELINE.json configs[3]: TGN on the synthetic tgbl-comment shape (994,790 nodes, raw_dim 2), UNIFORM-20
+    sampling over the t-CSR graph, TWO attention layers (tgn_b200.tcsr_trainer.TCSRTrainer; t-CSR built on the
+    device by tgn_tcsr_build from the first `events` events of the stream).  N > 1: independent replicas.
+    Also the statistical check of the uniform draws on the live graph: the normalised position of a draw inside
+    its root's candidate range must average 1/2."""
+    import torch.distributed as dist
+    from tgn_b200 import ops, synth
+    from tgn_b200.tcsr_trainer import TCSRTrainer
+    cfg = synth.SHAPES["tgbl-comment"]
+    B, K = cfg["B"], cfg["K"]
+    data = synth.synth_events("tgbl-comment", seed=rank, max_events=events)
+    N, De, E = data["num_nodes"], data["raw_dim"], data["src"].size
+    s_d, d_d, t_d = (torch.from_numpy(data[k]).to(dev) for k in ("src", "dst", "t"))
+    t0 = time.perf_counter()
+    indptr, indices, eid, ts = ops.tcsr_build(s_d, d_d, t_d, N, t_sorted=True)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    tr = TCSRTrainer(indptr, indices, eid, ts, N, De, HIDDEN, [K, K], False, torch.from_numpy(data["msg"]), device=dev,
+                     lr=LR, dropout=0.1, seed=7 + rank)
+    tr.train()
+    ev = {k: torch.from_numpy(data[k]).to(dev) for k in ("src", "dst", "neg", "t")}
+    msg = torch.from_numpy(data["msg"]).to(dev)
+    lo0 = E - (steps + 8) * B                     # the tail of the stream: roots with long histories
+    def step(i):
+        sl = slice(lo0 + i * B, lo0 + (i + 1) * B)
+        return tr.train_step(ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl], msg[sl])
+    for i in range(8):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tr.sampled_edges = 0
+    t0 = time.perf_counter()
+    for i in range(8, 8 + steps):
+        loss = step(i)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt)
+    # uniform-draw statistics on the live graph: hub roots, draws inside [row start, first entry >= t)
+    deg = (indptr[1:] - indptr[:-1]).long()
+    hubs = torch.topk(deg, 2000).indices.to(torch.int32)
+    rts = torch.full((hubs.numel(),), float(t_d[-1]) + 1.0, device=dev)
+    (nbr, col, se, sts, dts), off, cnt = ops.tcsr_sample(indptr, indices, eid, ts, hubs, rts, K, ops.SAMPLE_UNIFORM, seed=99,
+                                                         coarse=tr.sampler.coarse)
+    n = int(cnt.item())
+    rows = hubs[col[:n].long()].long()
+    lo = indptr[rows].long()
+    mean_pos = float(((sts[:n] - ts[lo]) / (ts[lo + deg[rows] - 1] - ts[lo]).clamp(min=1.0)).mean())
+    return {"metric": "train events/sec, t-CSR uniform-20 sampling, 2 attention layers (module path)",
+            "value": world * steps * B / dt, "unit": "events/s", "n_gpus": world, "ms_per_step": 1e3 * dt / steps,
+            "steps": steps, "final_loss": float(loss), "sampled_nbrs_per_s": world * tr.sampled_edges / dt,
+            "sampled_edges_per_step": tr.sampled_edges / steps,
+            "workload": f"synthetic tgbl-comment shape: {N} nodes, raw_dim {De}, first {E} events ({2 * E} t-CSR entries), "
+                        f"batch {B}, uniform-{K} x 2 layers, dim {HIDDEN}",
+            "tcsr_build_s": build_s, "parallelism": "independent replicas" if world > 1 else "single GPU",
+            "uniform_check": {"hub_roots": int(hubs.numel()), "draws": n,
+                              "mean_normalised_time_of_draw": mean_pos,
+                              "expected": "~0.5 (event times are uniform over the span, draws uniform over the row)"}}
 
 
 def dominant_kernel_roofline(eng, dev):

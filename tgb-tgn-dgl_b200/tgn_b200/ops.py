@@ -46,6 +46,13 @@ def _need(t: Tensor, dtype, name: str) -> Tensor:
 _bitmaps = {}
 
 
+def _ext() -> bool:
+    """True when the torch C++ extension (torch.ops.tgn.*, setup.py build_ext) is built: the sampler and
+    aggregator entry points then go through it instead of ctypes (same C-ABI underneath)."""
+    from . import torch_ext
+    return torch_ext.available()
+
+
 def _bitmap(num_nodes: int, device) -> Tensor:
     key = (int(num_nodes), str(device))
     bm = _bitmaps.get(key)
@@ -103,6 +110,8 @@ def nbr_lookup_raw(n_id: Tensor, neighbors: Tensor, e_id: Tensor, t: Tensor, bit
     """Bound-sized outputs + device count (no host sync).  Returns
     (nbr_global, centre_global, e_id, t, root_off, count_dev)."""
     n_id = _need(n_id, torch.int64, "n_id")
+    if num_roots_dev is None and _ext():
+        return tuple(torch.ops.tgn.nbr_lookup(n_id, neighbors, e_id, t, bitmap))
     N, K = neighbors.shape
     R = n_id.numel()
     dev = n_id.device
@@ -147,6 +156,9 @@ def nbr_insert(src: Tensor, dst: Tensor, t: Tensor, cur_e_id: int, neighbors: Te
     src = _need(src, torch.int64, "src")
     dst = _need(dst, torch.int64, "dst")
     t = _need(t, torch.float32, "t")
+    if cur_e_id_dev is None and _ext() and src.numel():
+        torch.ops.tgn.nbr_insert(src, dst, t, int(cur_e_id), neighbors, e_id, t_state)
+        return
     N, K = neighbors.shape
     check(_L().tgn_nbr_insert(_p(src), _p(dst), _p(t), src.numel(), cur_e_id, _p(cur_e_id_dev), K, N,
                               _p(neighbors), _p(e_id), _p(t_state), _stream()))
@@ -205,6 +217,12 @@ def tcsr_sample(indptr: Tensor, indices: Tensor, eid: Tensor, ts: Tensor, roots:
     _need(ts, torch.float32, "ts")
     root_ts = _need(root_ts, torch.float32, "root_ts")
     roots = roots.contiguous()
+    if _ext():
+        s64 = int(seed) & 0xFFFFFFFFFFFFFFFF          # same 64 bits as the ctypes route, as a signed schema int
+        s64 = s64 - (1 << 64) if s64 >= (1 << 63) else s64
+        o = torch.ops.tgn.tcsr_sample(indptr, indices, eid, ts, coarse, roots, root_ts, int(k), int(strategy),
+                                      float(offset), float(duration), s64)
+        return tuple(o[:5]), o[5], o[6]
     R = roots.numel()
     dev = roots.device
     cap = max(R * k, 1)

@@ -51,7 +51,7 @@ class ParallelSampler:
         if dev.type != "cuda":
             raise RuntimeError("sampler_core (B200 build) needs a CUDA device; there is no CPU fallback")
         self.device = dev
-        as_t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a)).to(dt).to(dev)
+        as_t = lambda a, dt: (a if torch.is_tensor(a) else torch.as_tensor(np.ascontiguousarray(a))).to(dev, dt).contiguous()
         self.indptr = as_t(indptr, torch.int32)
         self.indices = as_t(indices, torch.int32)
         self.eid = as_t(eid, torch.int32)

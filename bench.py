@@ -326,9 +326,16 @@ def gpu_leg(name, B, K_steps, W, prefill, dev, rank, world, precision, clocks=No
         return eng.pack_host_group(host[g % ring_bufs], batches)
 
     eng.stage_group(pack(0), ahead=False)
+    # the K_steps % 3 leftover steps of the timed region run one by one on the slots that follow the last whole
+    # group: whenever the warm-up passes that slot group it steps through it singly, so their graphs exist too
+    c_final = (eng.cur + G * (Wg + ng)) % eng.nslots
     for g in range(Wg):
         eng.stage_group(pack(g + 1))
-        eng.train_group_logged()
+        if rem and eng.cur == c_final:
+            for _ in range(G):
+                eng.train_step_logged(from_device=False, lookahead=True)
+        else:
+            eng.train_group_logged()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
@@ -336,7 +343,7 @@ def gpu_leg(name, B, K_steps, W, prefill, dev, rank, world, precision, clocks=No
         eng.stage_group(pack(g + 1))
         eng.train_group_logged()
     for _ in range(rem):
-        eng.train_step_logged(from_device=False, lookahead=True, _capture=False)
+        eng.train_step_logged(from_device=False, lookahead=True)
     losses = eng.flush_group_losses()
     loss_host = eng.flush_loss() if rem else losses[-1]
     f1.record()

@@ -591,6 +591,10 @@ int32_t tgn_neg_fill(const int64_t* pos_dst, int32_t batch, int32_t num_neg, int
                      uint64_t seed, uint64_t call, int64_t* out, void* stream);
 int32_t tgn_rank_accum(const int32_t* gt, const int32_t* ge, int32_t batch, double* acc, float* rr_out,
                        void* stream);
+/* Training-batch AP / AUC on the device (epoch_utils.py:312-317: sklearn average_precision_score and
+ * roc_auc_score of sigmoid(logits) per batch, their means printed per epoch): logits = [num_pos positives |
+ * num_neg negatives]; acc[0] += AP, acc[1] += AUC, acc[2] += 1.  No per-batch host copy. */
+int32_t tgn_ap_auc_accum(const float* logits, int32_t num_pos, int32_t num_neg, double* acc, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Owner-side compute for the partitioned node memory (modules/memory_module.py:126-150,

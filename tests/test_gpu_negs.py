@@ -121,3 +121,29 @@ def test_evaluate_table_equals_host_list_evaluation():
     m = evaluate_table(eng, ev["src"][:nb * B], ev["dst"][:nb * B], ev["t"][:nb * B], ev["msg"][:nb * B],
                        SyntheticNegatives(Q, N // 2, N), B)
     assert 0.0 < m <= 1.0
+
+
+def test_ap_auc_accum_matches_sklearn():
+    """tgn_ap_auc_accum == sklearn's average_precision_score / roc_auc_score on sigmoid(logits), the per-batch
+    metrics the reference computes on the host (epoch_utils.py:312-315), including tied scores."""
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    from tgn_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    acc = torch.zeros(3, dtype=torch.float64, device=DEV)
+    want_ap, want_auc = 0.0, 0.0
+    cases = [(200, 200), (37, 37), (5, 11), (2000, 2000)]
+    for i, (P, Nn) in enumerate(cases):
+        pos = torch.randn(P, generator=g) + 0.5
+        neg = torch.randn(Nn, generator=g)
+        if i == 1:                       # heavy ties, saturated sigmoids
+            pos, neg = (pos * 2).round() / 2, (neg * 2).round() / 2
+            pos[:3], neg[:3] = 40.0, 40.0
+        y_pred = torch.cat([pos, neg]).sigmoid().numpy()
+        y_true = np.r_[np.ones(P), np.zeros(Nn)]
+        want_ap += average_precision_score(y_true, y_pred)
+        want_auc += roc_auc_score(y_true, y_pred)
+        ops.ap_auc_accum(pos.to(DEV), neg.to(DEV), acc)
+    got = acc.tolist()
+    assert got[2] == len(cases)
+    # (the kernel evaluates the sigmoid itself: a last-bit difference can split or merge a tie)
+    assert abs(got[0] - want_ap) < 2e-4 * len(cases) and abs(got[1] - want_auc) < 2e-4 * len(cases), (got, want_ap, want_auc)

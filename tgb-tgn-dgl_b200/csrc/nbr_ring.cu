@@ -22,7 +22,16 @@ constexpr int kLookupThreads = 256;
 constexpr int kLookupPairsPerThread = 8;
 constexpr int kLookupTilePairs = kLookupThreads * kLookupPairsPerThread;  // 2048
 constexpr int kMaxK = 64;
+constexpr int kLookupThreePassTiles = 64;   // from here on count -> scan -> emit replaces the chained scan
 
+// kMode 0: single pass, output offsets by a chained scan across CTAs (decoupled look-back) -- one launch,
+//           what the training step uses (a few tiles);
+// kMode 1: COUNT pass of the large-launch path: only the e_id slots are read, ws[1 + tile] = valid slots;
+// kMode 2: EMIT pass: ws[1 + tile] holds the tile's exclusive offset (nbr_tile_scan_kernel ran in between).
+// On launches of thousands of tiles the look-back serialises (ncu, round 1: DRAM 36 % busy, a third of the
+// samples spinning on predecessor tiles); count -> scan -> emit re-reads 80 B of 488 B per root and has no
+// inter-CTA dependency at all.
+template <int kMode>
 __global__ void __launch_bounds__(kLookupThreads)
     nbr_lookup_kernel(const int64_t* __restrict__ n_id, DevCount roots, int K, int tile_roots,
                       int64_t num_nodes, const int64_t* __restrict__ nbrs,
@@ -37,8 +46,11 @@ __global__ void __launch_bounds__(kLookupThreads)
   __shared__ int s_warp_tot[kLookupThreads / 32];
   const int R = roots.get();
   const int ntiles = (R + tile_roots - 1) / tile_roots;
-  const int tile = lookback_take_tile(ws);
-  if (tile >= (ntiles > 0 ? ntiles : 1)) return;
+  const int tile = kMode == 0 ? lookback_take_tile(ws) : (int)blockIdx.x;
+  if (tile >= (ntiles > 0 ? ntiles : 1)) {
+    if (kMode == 1 && threadIdx.x == 0) ws[1 + tile] = 0ull;   // tiles beyond the live root count
+    return;
+  }
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int r0 = tile * tile_roots;
   const int nr = min(tile_roots, R - r0);
@@ -65,8 +77,10 @@ __global__ void __launch_bounds__(kLookupThreads)
     if (cc[j] >= 0 && cc[j] < num_nodes) {
       const int64_t at = cc[j] * K + (p % K);
       v_e[j] = eids[at];
-      v_n[j] = nbrs[at];
-      v_t[j] = ts[at];
+      if (kMode != 1) {
+        v_n[j] = nbrs[at];
+        v_t[j] = ts[at];
+      }
     }
   }
 #pragma unroll
@@ -79,7 +93,11 @@ __global__ void __launch_bounds__(kLookupThreads)
   long long tot = 0;
 #pragma unroll
   for (int w = 0; w < kLookupThreads / 32; ++w) tot += s_warp_tot[w];
-  long long base = lookback_prefix_block(ws, tile, tot);
+  if (kMode == 1) {
+    if (tid == 0) ws[1 + tile] = (unsigned long long)tot;
+    return;
+  }
+  long long base = kMode == 0 ? lookback_prefix_block(ws, tile, tot) : (long long)ws[1 + tile];
   if (tid == 0 && tile == (ntiles > 0 ? ntiles : 1) - 1) {
     root_off[R] = (int32_t)(base + tot);
     *out_count = (int32_t)(base + tot);
@@ -110,6 +128,39 @@ __global__ void __launch_bounds__(kLookupThreads)
       }
     }
     base += __popc(ball[j]);
+  }
+}
+
+// exclusive scan of the per-tile counts in ws[1 .. ntiles] (in place), one CTA
+__global__ void __launch_bounds__(1024) nbr_tile_scan_kernel(unsigned long long* __restrict__ ws, int ntiles) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ long long s_warp[32];
+  __shared__ long long s_base;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < ntiles; t0 += 1024) {
+    const int t = t0 + tid;
+    const long long c = t < ntiles ? (long long)ws[1 + t] : 0;
+    long long incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    long long before = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      const long long x = s_warp[w];
+      before += w < wid ? x : 0;
+      total += x;
+    }
+    if (t < ntiles) ws[1 + t] = (unsigned long long)(s_base + before + incl - c);
+    __syncthreads();
+    if (tid == 0) s_base += total;
+    __syncthreads();
   }
 }
 
@@ -361,13 +412,25 @@ int32_t tgn_nbr_lookup(const int64_t* n_id, int32_t num_roots, const int32_t* nu
   cudaStream_t s = (cudaStream_t)stream;
   const int tr = lookup_tile_roots(size_k);
   const int ntiles = num_roots > 0 ? (num_roots + tr - 1) / tr : 1;
-  TGN_CUDA(cudaMemsetAsync(ws, 0, (size_t)(ntiles + 1) * 8, s));
   uint32_t* l0 = (uint32_t*)bitmap;
   uint32_t* l1 = l0 ? l0 + ((num_nodes + 1023) / 1024) * 32 : nullptr;
   DevCount rc{num_roots_dev, num_roots};
-  launch_k(nbr_lookup_kernel, dim3(ntiles), dim3(kLookupThreads), 0, s, 
+  unsigned long long* w = (unsigned long long*)ws;
+  if (ntiles >= kLookupThreePassTiles) {   // large launch: count -> scan -> emit, no inter-CTA dependency
+    launch_k(nbr_lookup_kernel<1>, dim3(ntiles), dim3(kLookupThreads), 0, s, n_id, rc, size_k, tr, num_nodes,
+             neighbors, e_id, t, out_nbr, out_centre, out_eid, out_t, root_off, out_count, l0, l1, w);
+    TGN_LAUNCH_CHECK();
+    launch_k(nbr_tile_scan_kernel, dim3(1), dim3(1024), 0, s, w, ntiles);
+    TGN_LAUNCH_CHECK();
+    launch_k(nbr_lookup_kernel<2>, dim3(ntiles), dim3(kLookupThreads), 0, s, n_id, rc, size_k, tr, num_nodes,
+             neighbors, e_id, t, out_nbr, out_centre, out_eid, out_t, root_off, out_count, l0, l1, w);
+    TGN_LAUNCH_CHECK();
+    return TGN_OK;
+  }
+  TGN_CUDA(cudaMemsetAsync(ws, 0, (size_t)(ntiles + 1) * 8, s));
+  launch_k(nbr_lookup_kernel<0>, dim3(ntiles), dim3(kLookupThreads), 0, s,
       n_id, rc, size_k, tr, num_nodes, neighbors, e_id, t, out_nbr, out_centre, out_eid, out_t,
-      root_off, out_count, l0, l1, (unsigned long long*)ws);
+      root_off, out_count, l0, l1, w);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

@@ -111,6 +111,58 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Per-batch average precision and ROC AUC of the training logits (epoch_utils.py:312-315: sklearn's
+// average_precision_score / roc_auc_score on sigmoid([pos; neg]) against [1...; 0...]), accumulated on the
+// device.  For P positives and Nn negatives with scores s:
+//   AUC = (sum_{i pos} sum_{j neg} [s_i > s_j] + 0.5 [s_i == s_j]) / (P Nn)
+//   AP  = (1/P) sum_{i pos} tp(s_i) / (tp(s_i) + fp(s_i)),  tp / fp = positives / negatives with score >= s_i
+// (sklearn sums precision x recall-increment over the distinct thresholds; every positive tied at a threshold
+// carries that threshold's precision, which is the same sum).  One CTA; scores staged in shared memory.
+__global__ void __launch_bounds__(1024) ap_auc_kernel(const float* __restrict__ logits, int P, int Nn,
+                                                      double* __restrict__ acc) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ float s_sc[];
+  __shared__ double s_part[2][32];
+  const int n = P + Nn;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_sc[i] = 1.f / (1.f + expf(-logits[i]));
+  __syncthreads();
+  double ap = 0.0, auc = 0.0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float v = s_sc[i];
+    int tp = 0, fp = 0, gt = 0, eq = 0;
+    for (int j = 0; j < P; ++j) tp += s_sc[j] >= v;
+    for (int j = P; j < n; ++j) {
+      const float u = s_sc[j];
+      fp += u >= v;
+      gt += v > u;
+      eq += v == u;
+    }
+    ap += (double)tp / (double)(tp + fp);
+    auc += (double)gt + 0.5 * (double)eq;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ap += __shfl_xor_sync(0xffffffffu, ap, o);
+    auc += __shfl_xor_sync(0xffffffffu, auc, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_part[0][threadIdx.x >> 5] = ap;
+    s_part[1][threadIdx.x >> 5] = auc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      a += s_part[0][w];
+      b += s_part[1][w];
+    }
+    acc[0] += a / (double)P;
+    acc[1] += b / ((double)P * (double)Nn);
+    acc[2] += 1.0;
+  }
+}
+
 }  // namespace tgn
 
 using namespace tgn;
@@ -136,6 +188,18 @@ int32_t tgn_neg_fill(const int64_t* pos_dst, int32_t batch, int32_t num_neg, int
   TGN_REQUIRE(pos_dst && out, "neg_fill: NULL pointer");
   launch_k(neg_fill_kernel, dim3(stride_grid((long long)batch * ((num_neg + 3) / 4), 256)), dim3(256), 0,
            (cudaStream_t)stream, pos_dst, batch, num_neg, lo, hi, seed, call, out);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_ap_auc_accum(const float* logits, int32_t num_pos, int32_t num_neg, double* acc, void* stream) {
+  TGN_REQUIRE(num_pos >= 1 && num_neg >= 1 && (int64_t)num_pos + num_neg <= 48 * 1024,
+              "ap_auc_accum: need 1 <= positives, negatives and at most 49152 scores");
+  TGN_REQUIRE(logits && acc, "ap_auc_accum: NULL pointer");
+  const size_t smem = (size_t)(num_pos + num_neg) * sizeof(float);
+  static unsigned long long attr_mask = 0;
+  TGN_CUDA(smem_optin(ap_auc_kernel, 48 * 1024 * 4, attr_mask));
+  launch_k(ap_auc_kernel, dim3(1), dim3(1024), smem, (cudaStream_t)stream, logits, num_pos, num_neg, acc);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

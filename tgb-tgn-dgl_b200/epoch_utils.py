@@ -105,7 +105,8 @@ def _train_engine(model, train_loader, neighbor_loader, neg_dest_sampler, device
     key = (id(mem), id(neighbor_loader), B, tail, float(gnn.conv.dropout), mem.memory.data_ptr())
     if key not in _ENGINES:
         _ENGINES.clear()            # one model at a time: drop the graphs / workspaces of the previous one
-        kw = dict(device=mem.memory.device, lr=lr, heads=gnn.conv.heads, dropout=float(gnn.conv.dropout))
+        kw = dict(device=mem.memory.device, lr=lr, heads=gnn.conv.heads, dropout=float(gnn.conv.dropout),
+                  track_metrics=True)
         eng = TGNEngine(mem.num_nodes, mem.raw_msg_dim, mem.memory_dim, neighbor_loader.size, B, log_capacity=16, **kw)
         eng.attach_modules(mem, neighbor_loader)
         tail_eng = TGNEngine(mem.num_nodes, mem.raw_msg_dim, mem.memory_dim, neighbor_loader.size, tail, share=eng,
@@ -119,6 +120,7 @@ def _train_engine(model, train_loader, neighbor_loader, neg_dest_sampler, device
             tail_eng.lr = lr
     eng.sync_from_modules(model, optimizer)
     eng.begin_epoch_on_modules()
+    eng.metric_acc.zero_()
     # one negative per positive, drawn batch by batch exactly as the module loop draws them (same use of
     # torch's generator, epoch_utils.py:198), then the whole epoch is resident
     neg = torch.cat([neg_dest_sampler.sample(ds.dst[lo:lo + B]) for lo in range(0, n_all, B)])
@@ -139,6 +141,8 @@ def _train_engine(model, train_loader, neighbor_loader, neg_dest_sampler, device
     eng.end_epoch_on_modules()
     eng.sync_to_modules(model, optimizer)
     mem.detach()
+    ap, auc = eng.epoch_metrics()
+    print("ap and auc: ", ap, auc)                       # epoch_utils.py:317
     return total
 
 
@@ -154,6 +158,8 @@ def train(model, feats, train_loader, neighbor_loader, neg_dest_sampler, assoc, 
         return _train_engine(model, train_loader, neighbor_loader, neg_dest_sampler, device, optimizer)
     feats_dev = _device_feats(feats, device)
     total_loss = 0.0
+    from tgn_b200 import ops
+    metric_acc = torch.zeros(3, dtype=torch.float64, device=device)   # per-batch AP / AUC, summed on the device
     for batch in train_loader:
         optimizer.zero_grad()
         src, pos_dst, t, msg = batch["src"], batch["dst"], batch["t"], batch["msg"]
@@ -162,12 +168,15 @@ def train(model, feats, train_loader, neighbor_loader, neg_dest_sampler, assoc, 
         groups = [torch.arange(src.numel())] if b is None else \
             [(torch.as_tensor(b) == k).nonzero(as_tuple=True)[0] for k in range(int(torch.as_tensor(b).max()) + 1)]
         loss = 0.0
+        pos_all, neg_all = [], []
         for g in groups:
             s, d, n = src[g].to(device), pos_dst[g].to(device), neg_dst[g].to(device)
             tt, mm = t[g].to(device), msg[g].to(device, torch.float32)
             z, a = _embed(model, neighbor_loader, feats_dev, [s, d, n], device)
             pos_out = _logits(model["link_pred"], z[a[s]], z[a[d]])
             neg_out = _logits(model["link_pred"], z[a[s]], z[a[n]])
+            pos_all.append(pos_out.detach().reshape(-1))
+            neg_all.append(neg_out.detach().reshape(-1))
             part = criterion(pos_out, torch.ones_like(pos_out)) + criterion(neg_out, torch.zeros_like(neg_out))
             loss = loss + part * (g.numel() / src.numel())
             model["memory"].update_state(s, d, tt.long(), mm)
@@ -176,6 +185,10 @@ def train(model, feats, train_loader, neighbor_loader, neg_dest_sampler, assoc, 
         optimizer.step()
         model["memory"].detach()
         total_loss += float(loss.detach()) * src.shape[0]
+        # epoch_utils.py:312-315 (sklearn on the host, every batch) -> one kernel, no host copy
+        ops.ap_auc_accum(torch.cat(pos_all), torch.cat(neg_all), metric_acc)
+    acc = metric_acc.tolist()
+    print("ap and auc: ", acc[0] / max(acc[2], 1.0), acc[1] / max(acc[2], 1.0))   # epoch_utils.py:317
     return total_loss
 
 

@@ -52,7 +52,8 @@ class TGNEngine:
                  device="cuda", lr: float = 1e-4, heads: int = 2, dropout: float = 0.1,
                  log_capacity: int = 1 << 20, seed: int = 0, use_graph: bool = True,
                  precision: int = 3, rank: int = 0, world: int = 1, group=None, fused_zero_grad: bool = False,
-                 part_exchange: str = "p2p", share: Optional["TGNEngine"] = None, part_compute: str = "owner"):
+                 part_exchange: str = "p2p", share: Optional["TGNEngine"] = None, part_compute: str = "owner",
+                 track_metrics: bool = False):
         """share: another engine of the same model (nodes, dims, K, world) whose weights, Adam moments, node
         memory, neighbour ring, message store, event arrays and cursors this one USES instead of allocating
         its own -- a second step geometry (another batch size, e.g. the tail batch of an epoch) on the same
@@ -256,6 +257,10 @@ class TGNEngine:
         self.fused_gru = hidden % 4 == 0    # tgn_gru_fused_fwd (TMA strides need 16-byte rows)
         self.dz_split = 3                   # split-K of the d_z GEMM (1 = plain store)
         self.probe = None   # bench.py: {"name": [(start_event, stop_event), ...]} filled in eager steps
+        # per-batch AP / AUC of the training logits, accumulated on the device (epoch_utils.py:312-317)
+        self.track_metrics = track_metrics
+        self.metric_acc = (torch.zeros(3, dtype=torch.float64, device=dev) if share is None
+                           else share.metric_acc)
 
     events_done = property(lambda self: self._cur.events_done,
                            lambda self, v: setattr(self._cur, "events_done", v))
@@ -312,6 +317,15 @@ class TGNEngine:
                                     (2, "event id outside the resident event arrays"),
                                     (4, "batch above a kernel's sort capacity")) if v & b]
             raise _cabi.TgnError("device-side error flag: " + "; ".join(names))
+
+    def epoch_metrics(self, reset: bool = True):
+        """(mean AP, mean AUC) over the batches trained since the last reset (track_metrics=True): what the
+        reference prints as "ap and auc" at the end of train() (epoch_utils.py:317).  One host read."""
+        a = self.metric_acc.tolist()
+        if reset:
+            self.metric_acc.zero_()
+        n = max(a[2], 1.0)
+        return a[0] / n, a[1] / n
 
     def handover(self):
         """Call before stepping an engine that shares this one's state (share=): drops the pre-sampled batch."""
@@ -959,6 +973,10 @@ class TGNEngine:
         else:
             self._decoder_gemm_path(w, s)
             dec_wgrad = []
+        if self.track_metrics:      # off the chain: the update stream has been idle since the store update
+            upd.wait_stream(main)
+            with torch.cuda.stream(upd):
+                check(L.tgn_ap_auc_accum(_p(w.logits), B, B, _p(self.metric_acc), _stream()))
         # ---- attention backward
         check(L.tgn_attn_core_bwd(_p(w.proj), _p(w.nbr_l), _p(w.root_off), _p(w.ctr_l), w.R, _p(w.R_dev),
                                   self.H, self.C, _p(w.ee), _p(w.alpha), _p(self.d_emb), self.dropout, self.seed,

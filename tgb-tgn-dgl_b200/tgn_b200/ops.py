@@ -276,6 +276,12 @@ def agg_mean(msg: Tensor, index: Tensor, dim_size: int) -> Tensor:
     return out
 
 
+def ap_auc_accum(pos_logits: Tensor, neg_logits: Tensor, acc: Tensor):
+    """acc (float64 [3] on the device) += (AP, AUC, 1) of one training batch (epoch_utils.py:312-315)."""
+    logits = torch.cat([pos_logits.detach().reshape(-1), neg_logits.detach().reshape(-1)]).float().contiguous()
+    check(_L().tgn_ap_auc_accum(_p(logits), pos_logits.numel(), neg_logits.numel(), _p(acc), _stream()))
+
+
 def dep_blocks(src: Tensor, dst: Tensor, batch: int, want_counts: bool = False):
     """dependencyGraph.get_block for every consecutive batch of `batch` events of the stream (src, dst) in
     one launch; returns int32 block ids [E] (and the number of blocks per batch)."""

@@ -269,7 +269,9 @@ def gpu_leg(name, B, K_steps, W, prefill, dev, rank, world, precision, clocks=No
     from tgn_b200.engine import TGNEngine
     G0 = 3
     warm_dev = max(W, 52) + 4 * 9
-    Wg = max(14, (W + G0 - 1) // G0 + 2)
+    # warm-up groups of the e2e arm: 3 eager calls + the capture per slot group; with a K % 3 leftover the slot
+    # group the leftover lands on is additionally stepped through singly (4 more passes)
+    Wg = max(14, (W + G0 - 1) // G0 + 2) + (13 if K_steps % G0 else 0)
     n_batches = warm_dev + K_steps + G0 * (Wg + K_steps // G0 + 2) + 16
     data = load_workload(name, B, prefill, n_batches, seed=rank)
     N, De, K = data["num_nodes"], data["raw_dim"], data["K"]
@@ -329,9 +331,12 @@ def gpu_leg(name, B, K_steps, W, prefill, dev, rank, world, precision, clocks=No
     # the K_steps % 3 leftover steps of the timed region run one by one on the slots that follow the last whole
     # group: whenever the warm-up passes that slot group it steps through it singly, so their graphs exist too
     c_final = (eng.cur + G * (Wg + ng)) % eng.nslots
+    visits = 0
     for g in range(Wg):
         eng.stage_group(pack(g + 1))
         if rem and eng.cur == c_final:
+            visits += 1
+        if rem and eng.cur == c_final and visits > 4:      # (the first four passes capture this group's own graph)
             for _ in range(G):
                 eng.train_step_logged(from_device=False, lookahead=True)
         else:

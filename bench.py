@@ -662,7 +662,7 @@ def bench_partitioned(dev, rank, world, steps, warmup, precision, exchange="p2p"
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     rows = int(eng.w.Nb_dev.item())
-    owned = int(eng.wo.So_dev.item()) if eng.owner_compute else rows
+    owned = int(eng.w.So_dev.item()) if eng.owner_compute else rows
     eng.check_device_errors()
     D = HIDDEN
     # bytes this rank moves over NVLink per step (owner compute): rows published to the P-1 peers, remote rows

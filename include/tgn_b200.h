@@ -62,6 +62,7 @@ const char* tgn_last_error(void);
 #define TGN_DEVERR_LOG_OVERFLOW 1
 #define TGN_DEVERR_EVENT_RANGE 2
 #define TGN_DEVERR_SORT_CAP 4
+#define TGN_DEVERR_OWNER_CAP 8   /* partitioned memory: one rank owns more rows of a step than its buffers hold */
 int32_t tgn_device_errors(int32_t reset);
 /* Programmatic dependent launch: kernels are launched with the programmatic-stream-serialization
  * attribute so that the launch latency and prologue of each kernel overlap the tail of its
@@ -601,24 +602,26 @@ int32_t tgn_ap_auc_accum(const float* logits, int32_t num_pos, int32_t num_neg, 
  * modules/msg_func.py:17-18): rank r builds the messages and runs the GRU only for the rows of a step it
  * owns (n % world == r), publishes h' / last_update' to every rank's row table through the peer mapping,
  * runs the GRU backward on its rows, and the optimiser sums the partial gradients out of peer memory.
- *   tgn_part_select_owned  own_nodes / own_pos [<= num]: owned entries of n_id and their positions, in
- *                          position order; *own_count_dev = how many.
+ *   tgn_part_select_owned  own_nodes / own_pos [own_cap]: owned entries of n_id and their positions, in
+ *                          position order; *own_count_dev = how many (clamped to own_cap, which raises
+ *                          TGN_DEVERR_OWNER_CAP).
  *   tgn_part_publish       peer_rows[p][own_pos[i], :] = rows[i, :], peer_last_update[p][own_pos[i]] =
  *                          last_update[i] for every rank p (128-bit stores over NVLink; dim % 4 == 0).
  *                          The caller brackets it with rank barriers.
  *   tgn_adam_finish_peers  tgn_adam_finish with gradient = grads_replicated[i] + sum_p
  *                          peer_grads_partial[p][i]; grads_replicated is ONE rank's copy of the replicated
- *                          part (all ranks pass the same mapping, so the weight replicas stay bit-identical).
+ *                          part (all ranks pass the same mapping, so the weight replicas stay bit-identical);
+ *                          only the first partial_count parameters (the memory path) have partial sums.
  *                          No gradient clearing (peers may still be reading): the caller clears after a barrier.
  * ------------------------------------------------------------------------- */
 int32_t tgn_part_select_owned(const int64_t* n_id, int32_t num, const int32_t* num_dev, int32_t rank,
-                              int32_t world, int64_t* own_nodes, int64_t* own_pos, int32_t* own_count_dev,
-                              void* stream);
+                              int32_t world, int64_t* own_nodes, int64_t* own_pos, int32_t own_cap,
+                              int32_t* own_count_dev, void* stream);
 int32_t tgn_part_publish(const float* rows, const int64_t* last_update, const int64_t* own_pos, int32_t num,
                          const int32_t* num_dev, int32_t dim, void* const* peer_rows, void* const* peer_last_update,
                          int32_t world, void* stream);
 int32_t tgn_adam_finish_peers(float* params, const float* grads_replicated, const void* const* peer_grads_partial,
-                              int32_t world, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
+                              int32_t world, int64_t partial_count, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
                               float beta1, float beta2, float eps, float* step_dev, int64_t* step_counter,
                               const float* loss_acc, float* loss_out, uint32_t* done_counter, void* stream);
 

@@ -46,6 +46,7 @@ int set_err(int code, const char* fmt, ...);
 #define TGN_DEVERR_LOG_OVERFLOW 1   /* message-store log full: events were dropped */
 #define TGN_DEVERR_EVENT_RANGE 2    /* an e_id outside the resident event arrays was dereferenced */
 #define TGN_DEVERR_SORT_CAP 4       /* a batch exceeded a kernel's in-shared-memory sort capacity */
+#define TGN_DEVERR_OWNER_CAP 8      /* one rank's share of a step's rows exceeded the bound its buffers were sized for */
 int32_t* dev_err_word();
 __device__ __forceinline__ void flag_dev_err(int32_t* w, int bit) {
   if (w) atomicOr_system(reinterpret_cast<int*>(w), bit);

@@ -85,11 +85,12 @@ __global__ void part_gather_p2p_kernel(tgn_msgstore st, const int64_t* __restric
   const int wpb = blockDim.x >> 5;
   const int S = num.get();
   const T* ev_t = reinterpret_cast<const T*>(st.ev_t);
-  for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < bound; s += gridDim.x * wpb) {
+  // (rows beyond the live count are not touched: every consumer clamps to the same device count)
+  for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < S && s < bound; s += gridDim.x * wpb) {
     float* gn = g_n + (long long)s * Dm;
     float* go = g_o + (long long)s * Dm;
     int64_t n = -1, other = -1;
-    if (s < S) {
+    {
       n = n_id[s];
       if (n >= 0 && n < st.num_nodes) {
         const int sc = st.s_cnt[n], dc = st.d_cnt[n];
@@ -148,12 +149,12 @@ __global__ void memory_scatter_owned_kernel(const int64_t* __restrict__ n_id, De
 // a block scan per 1024 ids keeps the order deterministic, so reductions over the owned rows are too).
 __global__ void __launch_bounds__(1024)
     part_select_owned_kernel(const int64_t* __restrict__ n_id, DevCount num, int rank, int world,
-                             int64_t* __restrict__ own_nodes, int64_t* __restrict__ own_pos,
-                             int32_t* __restrict__ own_count) {
+                             int64_t* __restrict__ own_nodes, int64_t* __restrict__ own_pos, int cap,
+                             int32_t* __restrict__ own_count, int32_t* err) {
   pdl_wait();
   pdl_launch();
   __shared__ int s_warp[32];
-  __shared__ int s_base;
+  __shared__ int s_base, s_total;
   const int S = num.get();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) s_base = 0;
@@ -166,22 +167,35 @@ __global__ void __launch_bounds__(1024)
     const unsigned ball = __ballot_sync(0xffffffffu, own);
     if (lane == 0) s_warp[wid] = __popc(ball);
     __syncthreads();
-    int before = 0, total = 0;
-    for (int w = 0; w < 32; ++w) {
-      const int c = s_warp[w];
-      before += w < wid ? c : 0;
-      total += c;
+    // prefix over the 32 warp counts by the first warp, once, instead of 32 shared reads per thread
+    if (wid == 0) {
+      const int c = s_warp[lane];
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      s_warp[lane] = incl - c;
+      if (lane == 31) s_total = incl;
     }
+    __syncthreads();
+    const int before = s_warp[wid], total = s_total;
     if (own) {
       const int pos = s_base + before + __popc(ball & lanemask_lt());
-      own_nodes[pos] = n;
-      own_pos[pos] = s;
+      if (pos < cap) {
+        own_nodes[pos] = n;
+        own_pos[pos] = s;
+      }
     }
     __syncthreads();
     if (tid == 0) s_base += total;
     __syncthreads();
   }
-  if (tid == 0) *own_count = s_base;
+  if (tid == 0) {
+    if (s_base > cap) flag_dev_err(err, TGN_DEVERR_OWNER_CAP);   // the caller's bound on one rank's share was too small
+    *own_count = s_base < cap ? s_base : cap;
+  }
 }
 
 struct PeerTables {
@@ -216,7 +230,7 @@ struct PeerGrads {
 // gradient as rank 0 computed it (every rank reads the SAME copy, so the weight replicas stay bit-identical),
 // part[p] = rank p's partial sums over the rows it owns.  Same arithmetic as adam_kernel (dense.cu).
 __global__ void adam_peers_kernel(float* __restrict__ p, const float* __restrict__ rep, PeerGrads pg, int world,
-                                  float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                                  long long n_part, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
                                   float b1, float b2, float eps, float* __restrict__ step_dev,
                                   int64_t* __restrict__ step_ctr, const float* __restrict__ loss_acc,
                                   float* __restrict__ loss_out, unsigned* __restrict__ done_ctr) {
@@ -229,7 +243,8 @@ __global__ void adam_peers_kernel(float* __restrict__ p, const float* __restrict
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float gi = rep[i];
-    for (int r = 0; r < world; ++r) gi += pg.part[r][i];
+    if (i < n_part)      // only the memory-path parameters (a prefix of the flat layout) have partial sums
+      for (int r = 0; r < world; ++r) gi += pg.part[r][i];
     const float mi = m[i] + (1.f - b1) * (gi - m[i]);
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
@@ -334,12 +349,12 @@ int32_t tgn_memory_scatter_owned(const int64_t* n_id, int32_t num, const int32_t
 }
 
 int32_t tgn_part_select_owned(const int64_t* n_id, int32_t num, const int32_t* num_dev, int32_t rank,
-                              int32_t world, int64_t* own_nodes, int64_t* own_pos, int32_t* own_count_dev,
-                              void* stream) {
-  TGN_REQUIRE(num >= 0 && world >= 1 && rank >= 0 && rank < world, "part_select_owned: bad sizes / rank");
+                              int32_t world, int64_t* own_nodes, int64_t* own_pos, int32_t own_cap,
+                              int32_t* own_count_dev, void* stream) {
+  TGN_REQUIRE(num >= 0 && own_cap >= 0 && world >= 1 && rank >= 0 && rank < world, "part_select_owned: bad sizes / rank");
   TGN_REQUIRE(own_count_dev && (num == 0 || (n_id && own_nodes && own_pos)), "part_select_owned: NULL pointer");
   launch_k(part_select_owned_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, n_id, DevCount{num_dev, num},
-           rank, world, own_nodes, own_pos, own_count_dev);
+           rank, world, own_nodes, own_pos, own_cap, own_count_dev, dev_err_word());
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }
@@ -364,10 +379,11 @@ int32_t tgn_part_publish(const float* rows, const int64_t* last_update, const in
 }
 
 int32_t tgn_adam_finish_peers(float* params, const float* grads_replicated, const void* const* peer_grads_partial,
-                              int32_t world, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
+                              int32_t world, int64_t partial_count, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
                               float beta1, float beta2, float eps, float* step_dev, int64_t* step_counter,
                               const float* loss_acc, float* loss_out, uint32_t* done_counter, void* stream) {
-  TGN_REQUIRE(count >= 1 && world >= 1 && world <= kMaxPeers && step_dev && done_counter,
+  TGN_REQUIRE(count >= 1 && partial_count >= 0 && partial_count <= count && world >= 1 && world <= kMaxPeers &&
+                  step_dev && done_counter,
               "adam_finish_peers: bad arguments");
   TGN_REQUIRE(params && grads_replicated && peer_grads_partial && exp_avg && exp_avg_sq, "adam_finish_peers: NULL pointer");
   PeerGrads pg;
@@ -376,7 +392,7 @@ int32_t tgn_adam_finish_peers(float* params, const float* grads_replicated, cons
     TGN_REQUIRE(r >= world || pg.part[r], "adam_finish_peers: peer %d has no mapping", r);
   }
   launch_k(adam_peers_kernel, dim3(stride_grid(count, 256)), dim3(256), 0, (cudaStream_t)stream, params,
-           grads_replicated, pg, world, exp_avg, exp_avg_sq, (long long)count, lr, beta1, beta2, eps, step_dev,
+           grads_replicated, pg, world, (long long)partial_count, exp_avg, exp_avg_sq, (long long)count, lr, beta1, beta2, eps, step_dev,
            step_counter, loss_acc, loss_out, done_counter);
   TGN_LAUNCH_CHECK();
   return TGN_OK;

@@ -219,11 +219,9 @@ class TGNEngine:
             self._symm_rows = (hz, hl)
             self._peer_z = (ctypes.c_void_p * world)(*[int(q) for q in hz.buffer_ptrs])
             self._peer_rowlu = (ctypes.c_void_p * world)(*[int(q) for q in hl.buffer_ptrs])
-            # workspace of the rows this rank owns (any share of the Nb rows of a step can be its own)
-            self.wo = self._alloc_work(1, 1, Nb, 1)
-            self.wo.own_n = torch.zeros(Nb, dtype=torch.long, device=dev)
-            self.wo.own_pos = torch.zeros(Nb, dtype=torch.long, device=dev)
-            self.wo.So_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            # workspace of the rows this rank owns
+            self.So_b = self._owner_bound(Nb)
+            self.wo = self._alloc_work(1, 1, self.So_b, 1)
             torch.cuda.synchronize()
         # Slots of {batch inputs, sampling results} in rotation: while step s runs on slot `cur`, the forked
         # stream already loads and samples batch s+1 into the next slot (software pipelining), and a host
@@ -315,7 +313,9 @@ class TGNEngine:
         if v:
             names = [n for b, n in ((1, "message-store log overflow (events dropped)"),
                                     (2, "event id outside the resident event arrays"),
-                                    (4, "batch above a kernel's sort capacity")) if v & b]
+                                    (4, "batch above a kernel's sort capacity"),
+                                    (8, "partitioned memory: one rank owns more rows of a step than its buffers hold"))
+                     if v & b]
             raise _cabi.TgnError("device-side error flag: " + "; ".join(names))
 
     def epoch_metrics(self, reset: bool = True):
@@ -336,6 +336,12 @@ class TGNEngine:
         R = 3 * B if roots is None else roots
         E = R * self.K
         return R, E, min(self.N, R + E)
+
+    def _owner_bound(self, Nb: int) -> int:
+        """Rows of a step one rank is sized for under owner-side compute: twice the even share (ownership is
+        node id mod world over essentially random ids); tgn_part_select_owned flags TGN_DEVERR_OWNER_CAP if a
+        step ever exceeds it."""
+        return min(Nb, max(1024, 2 * ((Nb + self.world - 1) // self.world)))
 
     def _view(self, flat: Tensor, name: str, shp) -> Tensor:
         o, ld = self.off[name], self.ld[name]
@@ -373,7 +379,7 @@ class TGNEngine:
         return w
 
     _SAMPLE_FIELDS = ("roots", "R_dev", "nbr_g", "ctr_g", "eid", "t_e", "root_off", "E_dev", "lookup_ws", "n_id",
-                      "Nb_dev", "nbr_l", "ctr_l")
+                      "Nb_dev", "nbr_l", "ctr_l", "own_n", "own_pos", "So_dev")
     _SLOT_FIELDS = _SAMPLE_FIELDS + ("ids_l", "in_i64", "in_ids3", "in_t_i64", "in_t_f32", "in_msg")
 
     def _alloc_sample_fields(self, w, R: int, E: int, Nb: int):
@@ -387,6 +393,9 @@ class TGNEngine:
         w.lookup_ws = i64(max(_L().tgn_nbr_lookup_ws_bytes(R, self.K), 16) // 8)
         w.n_id, w.Nb_dev = i64(Nb), i32(1)
         w.nbr_l, w.ctr_l = i64(E), i64(R)
+        # owner-side compute: the rows of n_id this rank owns (picked right behind the sampling, off the chain)
+        So = self._owner_bound(Nb) if getattr(self, "owner_compute", False) else 1
+        w.own_n, w.own_pos, w.So_dev = i64(So), i64(So), i32(1)
 
     def _alloc_slot(self, R: int, E: int, Nb: int, B: int, index: int = 0) -> SimpleNamespace:
         dev = self.dev
@@ -708,7 +717,7 @@ class TGNEngine:
         e1.record()
         self.probe.setdefault(name, []).append((e0, e1))
 
-    def _sample(self, w, ids: Tensor, ids_l: Tensor, ids_dev: Optional[Tensor] = None):
+    def _sample(self, w, ids: Tensor, ids_l: Tensor, ids_dev: Optional[Tensor] = None, owner_select: bool = False):
         """roots -> neighbour lookup -> union -> relabel; everything bound-sized, counts on device.
         ids_dev: device count of the valid prefix of `ids` (entries beyond it must be -1: the marking
         kernels ignore them, the relabel stops in front of them)."""
@@ -726,6 +735,9 @@ class TGNEngine:
         check(L.tgn_unique_rank(_p(self.bitmap), N, _p(w.n_id), w.Nb, _p(self.assoc), _p(w.Nb_dev), 0, s))
         check(L.tgn_relabel3(_p(w.nbr_g), w.E, _p(w.E_dev), _p(w.nbr_l), _p(w.roots), w.R, _p(w.R_dev),
                              _p(w.ctr_l), _p(ids), ids.numel(), _p(ids_dev), _p(ids_l), _p(self.assoc), s))
+        if owner_select and self.owner_compute:
+            check(L.tgn_part_select_owned(_p(w.n_id), w.Nb, _p(w.Nb_dev), self.rank, self.world, _p(w.own_n),
+                                          _p(w.own_pos), w.own_n.numel(), _p(w.So_dev), s))
 
     def _assemble_rows(self, w, n_id: Tensor, S: int, S_dev: Optional[Tensor]):
         """Partitioned memory: every rank writes the memory rows it owns (rows of n_id and of the
@@ -783,19 +795,17 @@ class TGNEngine:
         NVLink) and runs the GRU for the rows of n_id it owns, then publishes h' / last_update' into every
         rank's row table w.z / w.lu.  Rank barrier B makes the tables complete before anyone reads them, and
         orders all remote reads of this step before the owners' memory write-back."""
-        wo, D, L, p = self.wo, self.D, _L(), self.p
+        wo, D, L, p, Sb = self.wo, self.D, _L(), self.p, self.So_b
         st = ctypes.byref(self.store.struct())
-        check(L.tgn_part_select_owned(_p(w.n_id), w.Nb, _p(w.Nb_dev), self.rank, self.world, _p(wo.own_n),
-                                      _p(wo.own_pos), _p(wo.So_dev), _stream()))
         g_o = wo.g_rows.data_ptr() + 4 * wo.g_rows.shape[1] * D
-        check(L.tgn_part_gather_p2p(st, _p(wo.own_n), w.Nb, _p(wo.So_dev), self._peer_mem, self._peer_lu, D,
+        check(L.tgn_part_gather_p2p(st, _p(w.own_n), Sb, _p(w.So_dev), self._peer_mem, self._peer_lu, D,
                                     self.world, _p(wo.g_rows), g_o, _p(wo.g_lu), _stream()))
-        check(L.tgn_msg_build_gathered(st, _p(wo.own_n), w.Nb, _p(wo.So_dev), _p(wo.g_rows), g_o, _p(wo.g_lu), D,
+        check(L.tgn_msg_build_gathered(st, _p(w.own_n), Sb, _p(w.So_dev), _p(wo.g_rows), g_o, _p(wo.g_lu), D,
                                        _p(p["time_enc.lin.weight"]), _p(p["time_enc.lin.bias"]), self.Dt,
                                        _p(wo.x), self.ldx, _p(wo.h), _p(wo.sn_m), _p(wo.lu), _p(wo.sel_ev),
                                        _p(wo.sel_dt), _stream()))
-        self._memory_gru(wo, w.Nb, wo.So_dev)
-        check(L.tgn_part_publish(_p(wo.z), _p(wo.lu), _p(wo.own_pos), w.Nb, _p(wo.So_dev), D, self._peer_z,
+        self._memory_gru(wo, Sb, w.So_dev)
+        check(L.tgn_part_publish(_p(wo.z), _p(wo.lu), _p(w.own_pos), Sb, _p(w.So_dev), D, self._peer_z,
                                  self._peer_rowlu, self.world, _stream()))
         self._symm_mem.barrier(channel=1)
 
@@ -913,7 +923,7 @@ class TGNEngine:
         if not pipelined:
             if from_device:
                 self.stage_batch_from_device()
-            self._sample(w, w.in_ids3, w.ids_l)
+            self._sample(w, w.in_ids3, w.ids_l, owner_select=True)
         # ---- forked stream 1, from the start of the step: the batch's events enter the ring, then the
         # NEXT batch is loaded and sampled (single-CTA, latency-bound kernels: ~100 us of them hide
         # behind the whole step instead of trailing the GRU)
@@ -926,7 +936,7 @@ class TGNEngine:
                 nxt = self.slots[self._next_slot()]
                 if from_device:
                     self.stage_batch_from_device(self._next_slot())
-                self._sample(nxt, nxt.in_ids3, nxt.ids_l)
+                self._sample(nxt, nxt.in_ids3, nxt.ids_l, owner_select=True)
         # the attention backward accumulates into a zero-filled d_proj (10 MB): cleared here, beside
         # msg_build, instead of in front of the backward on the dependent chain
         aux.wait_stream(main)
@@ -1015,42 +1025,42 @@ class TGNEngine:
         # ---- GRU backward (torch.nn.GRUCell, memory_module.py:72,172).  Owner-side compute: only on the rows
         # this rank owns (gm = their workspace, rows_dev = how many), gradients into the PARTIAL buffer that the
         # optimiser sums over the ranks
-        gm, rows_dev, fgm = w, w.Nb_dev, fg
+        gm, rows_dev, fgm, rows_b = w, w.Nb_dev, fg, w.Nb
         if own:
-            gm, rows_dev, fgm = self.wo, self.wo.So_dev, self.flat_grad_part
-            check(L.tgn_gather_rows(_p(w.d_z), _p(gm.own_pos), w.Nb, _p(rows_dev), D, _p(gm.d_z), s))
+            gm, rows_dev, fgm, rows_b = self.wo, w.So_dev, self.flat_grad_part, self.So_b
+            check(L.tgn_gather_rows(_p(w.d_z), _p(w.own_pos), rows_b, _p(rows_dev), D, _p(gm.d_z), s))
         gptr_m = lambda name: fgm.data_ptr() + 4 * off[name]
-        check(L.tgn_gru_gates_bwd_bias(_p(gm.d_z), _p(gm.gates), _p(gm.h), w.Nb, _p(rows_dev), D, _p(gm.d_gi),
+        check(L.tgn_gru_gates_bwd_bias(_p(gm.d_z), _p(gm.gates), _p(gm.h), rows_b, _p(rows_dev), D, _p(gm.d_gi),
                                        _p(gm.d_gh), gptr_m("memory_updater.bias_ih"), gptr_m("memory_updater.bias_hh"), s))
         # One launch, one wave: the GEMM CTAs hold ~193 KB of shared memory (one per SM), so the split-K
         # factor of the two weight gradients is chosen to leave SMs for the row tiles of d x -- launched
         # separately (or with a larger split) d x simply queues behind the weight-gradient CTAs.
         c0 = (2 * D + self.De) & ~3
-        tiles_dx = (w.Nb + 127) // 128 if self.Dt else 0
+        tiles_dx = (rows_b + 127) // 128 if self.Dt else 0
         tiles_w = ((3 * D + 127) // 128) * ((self.Dx + 127) // 128) + ((3 * D + 127) // 128) * ((D + 127) // 128)
         split_g = max(1, min(split_n, (148 - tiles_dx) // tiles_w))
         if split_g < 4:
             # larger batches (coin B=600, wiki B=2000): the bound-sized d x tiles alone exceed one wave, and a
             # weight-gradient CTA that walks ALL rows (hundreds of k-blocks) becomes the step's longest launch
             # (196 us measured at B=600).  Give every split <= ~24 k-blocks and accept a second wave.
-            split_g = max(split_g, min(16, (w.Nb // 32 + 23) // 24))
+            split_g = max(split_g, min(16, (rows_b // 32 + 23) // 24))
         g = [
-            ops.gemm_desc(gm.d_gi, gm.x, fgm, m=3 * D, n=self.Dx, k=w.Nb, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
+            ops.gemm_desc(gm.d_gi, gm.x, fgm, m=3 * D, n=self.Dx, k=rows_b, lda=3 * D, ldb=self.ldx, ldc=self.ldx,
                           trans_a=True, trans_b=True, mode=2, split_k=split_g, k_dev=rows_dev,
                           c_off=off["memory_updater.weight_ih"]),
-            ops.gemm_desc(gm.d_gh, gm.h, fgm, m=3 * D, n=D, k=w.Nb, lda=3 * D, ldb=D, ldc=D, trans_a=True,
+            ops.gemm_desc(gm.d_gh, gm.h, fgm, m=3 * D, n=D, k=rows_b, lda=3 * D, ldb=D, ldc=D, trans_a=True,
                           trans_b=True, mode=2, split_k=split_g, k_dev=rows_dev,
                           c_off=off["memory_updater.weight_hh"]),
         ]
         if self.Dt:
             # d x = d_gi W_ih: only the time-encoding columns [2D+De, Dx) are consumed (memory-side
             # TimeEncoder gradient), so only those are computed, from the 16-byte aligned column below them
-            g.append(ops.gemm_desc(gm.d_gi, fl, gm.d_x, m=w.Nb, n=self.Dx - c0, k=3 * D, lda=3 * D, ldb=self.ldx,
+            g.append(ops.gemm_desc(gm.d_gi, fl, gm.d_x, m=rows_b, n=self.Dx - c0, k=3 * D, lda=3 * D, ldb=self.ldx,
                                    ldc=self.ldx, trans_b=True, b_off=off["memory_updater.weight_ih"] + c0, c_off=c0,
                                    m_dev=rows_dev))
         ops.gemm_batch(g, self.prec)
         if self.Dt:
-            check(L.tgn_time_bwd_sin(_p(gm.sel_dt), _p(gm.sel_ev), w.Nb, _p(rows_dev), _p(gm.sn_m), self.Dt,
+            check(L.tgn_time_bwd_sin(_p(gm.sel_dt), _p(gm.sel_ev), rows_b, _p(rows_dev), _p(gm.sn_m), self.Dt,
                                      gm.d_x.data_ptr() + 4 * (2 * D + self.De), self.ldx,
                                      gptr_m("time_enc.lin.weight"), gptr_m("time_enc.lin.bias"), s))
         main.wait_stream(aux)
@@ -1061,7 +1071,7 @@ class TGNEngine:
             # replicated part and sums the partial parts of all ranks out of peer memory (no NCCL in the graph)
             self._symm_mem.barrier(channel=2)
             check(L.tgn_adam_finish_peers(_p(self.flat), self._grad_rep0, self._peer_grad_part, self.world,
-                                          _p(self.exp_avg), _p(self.exp_avg_sq), self.n_param, self.lr, 0.9, 0.999,
+                                          off["conv.w_node"], _p(self.exp_avg), _p(self.exp_avg_sq), self.n_param, self.lr, 0.9, 0.999,
                                           1e-8, _p(self.adam_step_dev), _p(self.step_dev), _p(self.loss_acc),
                                           self.loss_slots.data_ptr() + 4 * self.cur, _p(self.done_ctr), _stream()))
             return
@@ -1116,7 +1126,8 @@ class TGNEngine:
                 self._bind(self.cur)
                 if from_device:
                     self.stage_batch_from_device()
-                self._sample(self.slots[self.cur], self.slots[self.cur].in_ids3, self.slots[self.cur].ids_l)
+                self._sample(self.slots[self.cur], self.slots[self.cur].in_ids3, self.slots[self.cur].ids_l,
+                             owner_select=True)
                 self._primed = mode
         else:
             self._unprime()
@@ -1208,7 +1219,8 @@ class TGNEngine:
         if self._primed != "host":                 # first call: sample the group's first batch now
             self._unprime()
             self._bind(self.cur)
-            self._sample(self.slots[self.cur], self.slots[self.cur].in_ids3, self.slots[self.cur].ids_l)
+            self._sample(self.slots[self.cur], self.slots[self.cur].in_ids3, self.slots[self.cur].ids_l,
+                         owner_select=True)
             self._primed = "host"
         i = self._gl_n & 1
         main.wait_event(self._gl_ev[i])

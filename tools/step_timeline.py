@@ -18,13 +18,19 @@ ap.add_argument("--workload", default=bench.WORKLOAD)
 ap.add_argument("--batch", type=int, default=None)
 ap.add_argument("--eval", type=int, default=0, help="Q > 0: timeline of one evaluation batch with Q negatives per positive")
 a = ap.parse_args()
-dev = torch.device("cuda", 0)
+rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+torch.cuda.set_device(dev)
+if world > 1:          # torchrun: ONE job with the node memory partitioned by owner (timeline of rank 0)
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
 cfg = synth.SHAPES[a.workload]
 B, K = a.batch or cfg["B"], cfg["K"]
 data = synth.synth_events(a.workload, seed=0, max_events=a.prefill + 200 * B, batch=B, extend=True)
 N, De = data["num_nodes"], data["raw_dim"]
 eng = TGNEngine(N, De, bench.HIDDEN, K, B, device=dev, lr=bench.LR, dropout=0.1, use_graph=True,
-                log_capacity=data["src"].size, seed=1234, precision=a.precision, fused_zero_grad=True)
+                log_capacity=data["src"].size, seed=1234, precision=a.precision, fused_zero_grad=True,
+                rank=rank, world=world)
 eng.load_state(*bench.init_state_dicts(De, bench.HIDDEN, N, seed=1))
 eng.set_events(**{k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")})
 ring = bench.ring_after(data["src"][:a.prefill], data["dst"][:a.prefill], data["t"][:a.prefill], K, N)
@@ -53,7 +59,9 @@ else:
         for _ in range(6):
             eng.train_step(from_device=True)
         torch.cuda.synchronize()
-    marker = "msg_build"
+    marker = "part_select_owned" if world > 1 else "msg_build"
+if rank:
+    torch.cuda.synchronize(); dist.barrier(); os._exit(0)
 path = os.path.join(tempfile.mkdtemp(), "trace.json")
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
@@ -74,3 +82,6 @@ for e in ev[lo:hi]:
     name = e["name"].split("(")[0].replace("void ", "").replace("tgn::", "")[:48]
     print(f"{e['ts'] - t0:8.1f} {e['ts'] - t0 + e['dur']:8.1f} {e['dur']:7.1f}  {streams.index(e['args'].get('stream')):2d}  "
           f"{name}  grid={e['args'].get('grid')}")
+
+if world > 1:
+    sys.stdout.flush(); torch.cuda.synchronize(); dist.barrier(); os._exit(0)

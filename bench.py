@@ -430,6 +430,7 @@ def main():
     ap.add_argument("--no-tcsr", action="store_true", help="skip the configs[3] leg (t-CSR uniform-20, 2 layers)")
     ap.add_argument("--only-tcsr", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-tf32", action="store_true", help="skip the single-pass tf32 variant of the headline workload")
     ap.add_argument("--part-compute", default="owner", choices=["owner", "replicated"],
                     help="partitioned-memory leg: owner-side compute of the memory path, or the replicated round-1 design")
     ap.add_argument("--part-exchange", default="p2p", choices=["p2p", "allreduce"],
@@ -613,6 +614,18 @@ def main():
             line["wiki"] = wiki
         if world == 1 and not args.no_module_path:
             line["script_path"] = guarded(bench_module_path, dev)
+        if world == 1 and not args.no_tf32 and args.precision == 3:
+            # north_star allows the GRU / projections in tf32 (2e-2 bar): the same workload with single-pass tf32
+            # tensor-core GEMMs, its own parity numbers beside it (the headline stays the fp32-accurate 3xTF32 mode)
+            def tf32_leg():
+                r, e = gpu_leg(name, B, max(60, min(K_steps, 300)), W, prefill, dev, 0, 1, 1)
+                del e
+                torch.cuda.empty_cache()
+                if not args.no_parity:
+                    r["parity"] = parity_leg(name, B, prefill, 10, dev, 1, free_steps=0)
+                r["dtype"] = "tf32 (single pass), fp32 accumulate"
+                return r
+            line["tf32"] = guarded(tf32_leg)
         emit(line)
     if world > 1:
         # captured graphs hold NCCL kernels: leave without the collective shutdown (it can block)

@@ -544,6 +544,11 @@ int32_t tgn_dec_fused(const float* emb, const int64_t* ids_local, int32_t batch,
  * one rank, epoch_utils.py:74-99). */
 int32_t tgn_stride_select(const int64_t* in, int32_t num_in, const int32_t* num_in_dev, int32_t offset,
                           int32_t stride, int64_t* out, int32_t out_cap, int32_t* out_count_dev, void* stream);
+/* Data-parallel evaluation: rows of a batch's candidates in the all-gathered table of projected root rows
+ * laid out [world][2][block_rows/2][dim] (root with global index g: row (g % world) * block_rows + g / world).
+ * global_index = [src (B) | dst (B) | neg (B x Q)]; neg_rows [B, Qr] gets this rank's columns rank, rank+world, ... */
+int32_t tgn_dp_rows(const int64_t* global_index, int32_t num_pos, int32_t num_neg, int32_t rank, int32_t world,
+                    int64_t block_rows, int64_t* src_rows, int64_t* dst_rows, int64_t* neg_rows, void* stream);
 int32_t tgn_score_negs(const float* hs, const float* hd, const int64_t* src_rows,
                        const int64_t* dst_rows, const int64_t* neg_rows, int32_t num_pos,
                        int32_t num_neg, int32_t dim, const float* w_final, const float* b_final,

@@ -997,6 +997,36 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Rows of the candidates of one evaluation batch inside the all-gathered table of projected root rows
+// [P][2][Rm][D]: global root index g lives in the block of rank g % P at position g / P, i.e. row
+// (g % P) * block_rows + g / P.  g = [src (B) | dst (B) | neg (B x Q, row-major)]; this rank scores the negative
+// columns rank, rank + P, ... (Qr of them).
+__global__ void dp_rows_kernel(const int64_t* __restrict__ g, int B, int Q, int rank, int P, int64_t block_rows,
+                               int64_t* __restrict__ src_rows, int64_t* __restrict__ dst_rows,
+                               int64_t* __restrict__ neg_rows) {
+  pdl_wait();
+  pdl_launch();
+  const int Qr = Q > rank ? (Q - rank + P - 1) / P : 0;
+  const long long total = 2ll * B + (long long)B * Qr;
+  for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total;
+       x += (long long)gridDim.x * blockDim.x) {
+    long long srcpos;
+    int64_t* out;
+    if (x < B) {
+      srcpos = x; out = src_rows + x;
+    } else if (x < 2ll * B) {
+      srcpos = x; out = dst_rows + (x - B);
+    } else {
+      const long long y = x - 2ll * B;
+      const long long i = y / Qr, q = y - i * Qr;
+      srcpos = 2ll * B + i * Q + rank + q * P;
+      out = neg_rows + y;
+    }
+    const int64_t v = g[srcpos];
+    *out = (v % P) * block_rows + v / P;
+  }
+}
+
 // out[i] = in[offset + i * stride] for the entries that exist, -1 beyond (ids < 0 are ignored by the
 // marking kernels); *out_count = how many exist.  Picks one rank's share of a sorted root list.
 __global__ void stride_select_kernel(const int64_t* __restrict__ in, DevCount n_in, int offset, int stride,
@@ -1249,6 +1279,18 @@ int32_t tgn_score_negs(const float* hs, const float* hd, const int64_t* src_rows
   launch_k(score_negs_kernel, dim3(grid, parts), dim3(256), (size_t)2 * dim * sizeof(float), (cudaStream_t)stream, 
       hs, hd, src_rows, dst_rows, neg_rows, num_pos, num_neg, dim, w_final, b_final, pos_out,
       neg_out, gt_out, ge_out);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_dp_rows(const int64_t* global_index, int32_t num_pos, int32_t num_neg, int32_t rank, int32_t world,
+                    int64_t block_rows, int64_t* src_rows, int64_t* dst_rows, int64_t* neg_rows, void* stream) {
+  TGN_REQUIRE(num_pos >= 1 && num_neg >= 0 && world >= 1 && rank >= 0 && rank < world && block_rows >= 1,
+              "dp_rows: bad sizes / rank");
+  TGN_REQUIRE(global_index && src_rows && dst_rows && (neg_rows || num_neg <= rank), "dp_rows: NULL pointer");
+  const int qr = num_neg > rank ? (num_neg - rank + world - 1) / world : 0;
+  launch_k(dp_rows_kernel, dim3(stride_grid(2ll * num_pos + (long long)num_pos * qr, 256)), dim3(256), 0,
+           (cudaStream_t)stream, global_index, num_pos, num_neg, rank, world, block_rows, src_rows, dst_rows, neg_rows);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

@@ -1457,13 +1457,10 @@ class TGNEngine:
         if P > 1:
             import torch.distributed as dist
             dist.all_gather_into_tensor(c.recv, c.send, group=group)
-        # row of global root g in the gathered table: block of its rank (g % P), position g // P
+        # row of global root g in the gathered table: block of its rank (g % P), position g // P -- one kernel for
+        # the sources, the destinations and this rank's negative columns
         g = c.ids if c.dense else c.ids_g
-        rows = (g % P) * (2 * c.Rm) + g // P
-        c.src_rows.copy_(rows[:B])
-        c.dst_rows.copy_(rows[B:2 * B])
-        if c.Qr:
-            c.neg_rows.copy_(rows[2 * B:].view(B, Q)[:, rank::P])
+        check(L.tgn_dp_rows(_p(g), B, Q, rank, P, 2 * c.Rm, _p(c.src_rows), _p(c.dst_rows), _p(c.neg_rows), _stream()))
         check(L.tgn_score_negs(_p(c.recv), c.recv.data_ptr() + 4 * c.Rm * D, _p(c.src_rows), _p(c.dst_rows),
                                _p(c.neg_rows), B, c.Qr, D, _p(p["lin_final.weight"]), _p(p["lin_final.bias"]),
                                _p(c.pos), None, _p(c.gt), _p(c.ge), _stream()))

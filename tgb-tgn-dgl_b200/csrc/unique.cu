@@ -163,6 +163,97 @@ __global__ void __launch_bounds__(1024, 1)
   if (tid == 0) *out_count = s_base;
 }
 
+// Several CTAs: each CTA recomputes the per-group counts and their scan (a few KB of bitmap -- cheaper than a
+// grid barrier) and emits a strided share of the live groups, one warp per group as above.  Nothing is cleared
+// here: other CTAs may still be counting the same words; unique_clear_kernel follows when the marks are not kept.
+__global__ void __launch_bounds__(1024, 1)
+    unique_rank_mc_kernel(const uint32_t* __restrict__ l0, const uint32_t* __restrict__ l1, int64_t n_groups,
+                          int64_t* __restrict__ out_ids, int32_t out_cap, int64_t* __restrict__ assoc,
+                          int32_t* __restrict__ out_count) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ int s_warp[32];
+  __shared__ int s_off[1024];
+  __shared__ int s_base, s_total;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int64_t g0 = 0; g0 < n_groups; g0 += 1024) {
+    const int64_t g = g0 + tid;
+    int cnt = 0;
+    if (g < n_groups && ((l1[g >> 5] >> (g & 31)) & 1u)) {
+      const uint4* p = reinterpret_cast<const uint4*>(l0 + g * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 v = p[q];
+        cnt += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+      }
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int v = s_warp[lane];
+      int iv = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, iv, o);
+        if (lane >= o) iv += y;
+      }
+      s_warp[lane] = iv - v;
+      if (lane == 31) s_total = iv;
+    }
+    __syncthreads();
+    s_off[tid] = cnt > 0 ? s_base + s_warp[wid] + (incl - cnt) : -1;
+    __syncthreads();
+    for (int gl = blockIdx.x * 32 + wid; gl < 1024 && g0 + gl < n_groups; gl += gridDim.x * 32) {
+      const int gbase = s_off[gl];
+      if (gbase < 0) continue;  // warp-uniform
+      uint32_t bits = l0[(g0 + gl) * 32 + lane];
+      const int c = __popc(bits);
+      int pre = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += y;
+      }
+      int pos = gbase + pre - c;
+      const int64_t id0 = ((g0 + gl) << 10) + (lane << 5);
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int64_t id = id0 + b;
+        if (pos < out_cap) out_ids[pos] = id;
+        if (assoc) assoc[id] = pos;
+        ++pos;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_base += s_total;
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && tid == 0) *out_count = s_base;
+}
+
+// one CTA per L1 word (32 groups x 32 words): clears the words of the marked groups, then the L1 word itself
+__global__ void __launch_bounds__(1024) unique_clear_kernel(uint32_t* __restrict__ l0, uint32_t* __restrict__ l1,
+                                                            int64_t n_groups) {
+  pdl_wait();
+  pdl_launch();
+  const int64_t w1 = blockIdx.x;
+  const uint32_t live = l1[w1];
+  const int grp = threadIdx.x >> 5, word = threadIdx.x & 31;
+  const int64_t g = w1 * 32 + grp;
+  if (((live >> grp) & 1u) && g < n_groups) l0[g * 32 + word] = 0u;
+  __syncthreads();
+  if (threadIdx.x == 0 && live) l1[w1] = 0u;
+}
+
 __global__ void relabel_kernel(const int64_t* __restrict__ ids, DevCount cnt,
                                const int64_t* __restrict__ assoc, int64_t* __restrict__ out) {
   pdl_wait();
@@ -224,8 +315,21 @@ int32_t tgn_unique_rank(void* bitmap, int64_t num_nodes, int64_t* out_ids, int32
               "unique_rank: bad arguments");
   uint32_t* l0 = (uint32_t*)bitmap;
   uint32_t* l1 = l0 + l0_words(num_nodes);
-  launch_k(unique_rank_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, 
-      l0, l1, l0_groups(num_nodes), l1_words(num_nodes), out_ids, out_cap, assoc, out_count,
+  const int64_t ng = l0_groups(num_nodes);
+  if (ng >= 16) {   // enough groups to share: several CTAs emit, a second launch clears the marks
+    int grid = (int)((ng + 3) / 4);
+    grid = grid > 16 ? 16 : grid;
+    launch_k(unique_rank_mc_kernel, dim3(grid), dim3(1024), 0, (cudaStream_t)stream, (const uint32_t*)l0,
+             (const uint32_t*)l1, ng, out_ids, out_cap, assoc, out_count);
+    TGN_LAUNCH_CHECK();
+    if (!keep_marks) {
+      launch_k(unique_clear_kernel, dim3((unsigned)l1_words(num_nodes)), dim3(1024), 0, (cudaStream_t)stream, l0, l1, ng);
+      TGN_LAUNCH_CHECK();
+    }
+    return TGN_OK;
+  }
+  launch_k(unique_rank_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream,
+      l0, l1, ng, l1_words(num_nodes), out_ids, out_cap, assoc, out_count,
       keep_marks, nullptr, 0, num_nodes);
   TGN_LAUNCH_CHECK();
   return TGN_OK;

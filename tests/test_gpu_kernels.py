@@ -107,16 +107,21 @@ def test_ring_vs_oracle_random(ops, N, K, B, steps, bip):
     assert out[1].shape == (2, 0) and out[0].tolist() == [1, 2, 3]
 
 
-def test_ring_large_lookup_properties(ops):
+@pytest.mark.parametrize("N,K,R,sort_rows", [(994790, 10, 200_200, True), (100_000, 7, 60_000, False),
+                                             (50_000, 3, 120_000, False), (30_000, 64, 9_000, True)])
+def test_ring_large_lookup_properties(ops, N, K, R, sort_rows):
     """eval-sized lookup (200 x 1001 roots worth of nodes on the comment shape): size-independent
-    properties -- edge order follows roots, every emitted slot is valid, counts add up."""
-    N, K = 994790, 10
-    g = torch.Generator(device=DEV).manual_seed(0)
+    properties -- edge order follows roots, every emitted slot is valid, counts add up.  The large-launch
+    path (count pass: one thread per root, 128-bit row loads for even K; emit pass) with odd K, tiles of more
+    roots than a count CTA has threads (K = 3), K = 64, and rows whose empty slots are not at the end."""
+    g = torch.Generator(device=DEV).manual_seed(K)
     e_id = torch.randint(-1, 10_000_000, (N, K), device=DEV, generator=g)
-    e_id = torch.sort(e_id, dim=1, descending=True).values
+    e_id[torch.rand((N, K), device=DEV, generator=g) < 0.3] = -1
+    if sort_rows:
+        e_id = torch.sort(e_id, dim=1, descending=True).values
     nbrs = torch.randint(0, N, (N, K), device=DEV, generator=g)
     t = torch.rand((N, K), device=DEV, generator=g)
-    roots = torch.unique(torch.randint(0, N, (200_200,), device=DEV, generator=g))
+    roots = torch.unique(torch.randint(0, N, (R,), device=DEV, generator=g))
     assoc = torch.zeros(N, dtype=torch.int64, device=DEV)
     ids, ei, eo, to, off = ops.nbr_lookup(roots, nbrs, e_id, t, assoc)
     valid = e_id[roots] >= 0

@@ -24,17 +24,103 @@ constexpr int kLookupTilePairs = kLookupThreads * kLookupPairsPerThread;  // 204
 constexpr int kMaxK = 64;
 constexpr int kLookupThreePassTiles = 64;   // from here on count -> scan -> emit replaces the chained scan
 
+constexpr int kCountThreads = 512;
+constexpr int kCountTiles = 8;              // tiles of the emit pass per CTA of the count pass
+constexpr int kCountVecs = 8;               // row loads a thread of the count pass keeps in flight
+
+// floor(p / d) for 0 <= p < 2^20 / d by one (wide) multiply (mul = 2^20 / d + 1, host side)
+__device__ __forceinline__ int fast_div20(int p, uint32_t mul) {
+  return (int)(((unsigned long long)(uint32_t)p * mul) >> 20);
+}
+
+// Large launches (>= kLookupThreePassTiles tiles): COUNT pass.  One thread per root reads the root's e_id row
+// with 128-bit loads (64-bit when K is odd) and counts its valid slots; a CTA covers kCountTiles tiles of the
+// emit pass and leaves ws[1 + tile] = valid slots of the tile and ws[1 + ntiles + cta] = their sum.  The emit
+// pass derives its offset from those two levels itself (no scan launch, no atomics, nothing to clear).
+// Round 2 history (1M roots, K = 10): the count pass first used the emit pass's (root, slot)-pair mapping
+// with runtime divisions (~50 instructions per PAIR, 39 us) and a one-CTA scan sat between the two passes;
+// a (root, 16-byte chunk) mapping flattened over the CTA measured 33 us, a thread per root 26 us; L2
+// eviction hints on the ring rows / output stores changed nothing; an emit pass that stages the rows through
+// shared memory with 4/8-byte cp.async (five CTAs per SM instead of three) measured 155 us against 100 us;
+// prefetch.global.L2 of the rows of tiles two waves ahead made both passes slower (count 25 -> 37 us, emit
+// 101 -> 116 us).
+template <int kVec>
+__global__ void __launch_bounds__(kCountThreads)
+    nbr_count_kernel(const int64_t* __restrict__ n_id, DevCount roots, int K, int tile_roots, int ntiles_host,
+                     int64_t num_nodes, const int64_t* __restrict__ eids, unsigned long long* __restrict__ ws) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ int s_cnt[kCountTiles];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int R = roots.get();
+  if (tid < kCountTiles) s_cnt[tid] = 0;
+  __syncthreads();
+  const int t0 = blockIdx.x * kCountTiles;
+  const int r0 = t0 * tile_roots;
+  const int nr = max(0, min(kCountTiles * tile_roots, R - r0));
+  for (int i0 = 0; i0 < nr; i0 += kCountThreads) {      // (whole warps enter: the reduction below shuffles)
+    const int i = i0 + tid;
+    int c = 0, q = 0;
+    if (i < nr) {
+      q = i / tile_roots;
+      const int64_t node = n_id[r0 + i];
+      if (node >= 0 && node < num_nodes) {
+        const int64_t* row = eids + node * K;
+        if (kVec == 2) {
+          for (int s0 = 0; s0 < K; s0 += 2 * kCountVecs) {
+            longlong2 v[kCountVecs];
+#pragma unroll
+            for (int u = 0; u < kCountVecs; ++u) {
+              v[u] = make_longlong2(-1, -1);
+              if (s0 + 2 * u < K) v[u] = *reinterpret_cast<const longlong2*>(row + s0 + 2 * u);
+            }
+#pragma unroll
+            for (int u = 0; u < kCountVecs; ++u) c += (v[u].x >= 0) + (v[u].y >= 0);
+          }
+        } else {
+          for (int s0 = 0; s0 < K; s0 += 2 * kCountVecs) {
+            long long v[2 * kCountVecs];
+#pragma unroll
+            for (int u = 0; u < 2 * kCountVecs; ++u) {
+              v[u] = -1;
+              if (s0 + u < K) v[u] = row[s0 + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 2 * kCountVecs; ++u) c += v[u] >= 0;
+          }
+        }
+      }
+    }
+    // consecutive roots share a tile almost always: one shared-memory add per warp
+    const int q0 = __shfl_sync(0xffffffffu, q, 0);
+    if (__ballot_sync(0xffffffffu, q != q0) == 0u) {
+      c = warp_sum_i(c);
+      if (lane == 0 && c) atomicAdd(&s_cnt[q0], c);
+    } else if (c) {
+      atomicAdd(&s_cnt[q], c);
+    }
+  }
+  __syncthreads();
+  if (tid < kCountTiles && t0 + tid < ntiles_host) ws[1 + t0 + tid] = (unsigned long long)s_cnt[tid];
+  if (tid == 0) {
+    long long tot = 0;
+#pragma unroll
+    for (int k = 0; k < kCountTiles; ++k) tot += s_cnt[k];
+    ws[1 + ntiles_host + blockIdx.x] = (unsigned long long)tot;
+  }
+}
+
 // kMode 0: single pass, output offsets by a chained scan across CTAs (decoupled look-back) -- one launch,
 //           what the training step uses (a few tiles);
-// kMode 1: COUNT pass of the large-launch path: only the e_id slots are read, ws[1 + tile] = valid slots;
-// kMode 2: EMIT pass: ws[1 + tile] holds the tile's exclusive offset (nbr_tile_scan_kernel ran in between).
+// kMode 2: EMIT pass of the large-launch path: the tile's exclusive offset is the sum of the count pass's
+//           group totals below its group and of the tile counts below it inside the group.
 // On launches of thousands of tiles the look-back serialises (ncu, round 1: DRAM 36 % busy, a third of the
-// samples spinning on predecessor tiles); count -> scan -> emit re-reads 80 B of 488 B per root and has no
+// samples spinning on predecessor tiles); count -> emit re-reads 80 B of 488 B per root and has no
 // inter-CTA dependency at all.
-template <int kMode>
-__global__ void __launch_bounds__(kLookupThreads)
-    nbr_lookup_kernel(const int64_t* __restrict__ n_id, DevCount roots, int K, int tile_roots,
-                      int64_t num_nodes, const int64_t* __restrict__ nbrs,
+template <int kMode, int kThreads, int kPairs, int kMinCtas, typename IdT>
+__global__ void __launch_bounds__(kThreads, kMinCtas)
+    nbr_lookup_kernel(const int64_t* __restrict__ n_id, DevCount roots, int K, uint32_t k_mul, int tile_roots,
+                      int ntiles_host, int64_t num_nodes, const int64_t* __restrict__ nbrs,
                       const int64_t* __restrict__ eids, const float* __restrict__ ts,
                       int64_t* __restrict__ out_nbr, int64_t* __restrict__ out_ctr,
                       int64_t* __restrict__ out_eid, float* __restrict__ out_t,
@@ -43,80 +129,101 @@ __global__ void __launch_bounds__(kLookupThreads)
                       unsigned long long* __restrict__ ws) {
   pdl_wait();
   pdl_launch();
-  __shared__ int s_warp_tot[kLookupThreads / 32];
+  __shared__ int s_warp_tot[kThreads / 32];
+  __shared__ long long s_warp_pre[kThreads / 32];
   const int R = roots.get();
   const int ntiles = (R + tile_roots - 1) / tile_roots;
   const int tile = kMode == 0 ? lookback_take_tile(ws) : (int)blockIdx.x;
-  if (tile >= (ntiles > 0 ? ntiles : 1)) {
-    if (kMode == 1 && threadIdx.x == 0) ws[1 + tile] = 0ull;   // tiles beyond the live root count
-    return;
-  }
+  if (tile >= (ntiles > 0 ? ntiles : 1)) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int r0 = tile * tile_roots;
   const int nr = min(tile_roots, R - r0);
   const int npairs = nr > 0 ? nr * K : 0;
 
-  int64_t v_e[kLookupPairsPerThread], v_n[kLookupPairsPerThread];
-  float v_t[kLookupPairsPerThread];
-  unsigned ball[kLookupPairsPerThread];
+  // emit pass: this thread's share of the two-level prefix (loads issued ahead of the row gathers)
+  long long pre = 0;
+  if (kMode == 2) {
+    const int g = tile / kCountTiles;
+    for (int i = tid; i < g; i += kThreads) pre += (long long)ws[1 + ntiles_host + i];
+    const int f = g * kCountTiles + tid;
+    if (f < tile) pre += (long long)ws[1 + f];
+  }
+
+  // IdT = int32_t when num_nodes < 2^31: centre and neighbour ids are held in one register each, which takes
+  // the kernel from 80 to 64 registers (four resident CTAs per SM instead of three)
+  int64_t v_e[kPairs];
+  IdT v_n[kPairs];
+  float v_t[kPairs];
+  unsigned ball[kPairs];
   int wtot = 0;
   // all loads of the thread's 8 pairs are issued before the first ballot: a ballot is a
   // convergence point the compiler does not move loads across, and one DRAM round trip per
   // pair (8 in sequence) was the kernel's largest stall
-  int64_t cc[kLookupPairsPerThread];
+  IdT cc[kPairs];
 #pragma unroll
-  for (int j = 0; j < kLookupPairsPerThread; ++j) {
-    const int p = wid * (32 * kLookupPairsPerThread) + j * 32 + lane;
+  for (int j = 0; j < kPairs; ++j) {
+    const int p = wid * (32 * kPairs) + j * 32 + lane;
     cc[j] = -1;
-    if (p < npairs) cc[j] = n_id[r0 + p / K];
-  }
-#pragma unroll
-  for (int j = 0; j < kLookupPairsPerThread; ++j) {
-    const int p = wid * (32 * kLookupPairsPerThread) + j * 32 + lane;
-    v_e[j] = -1;
-    if (cc[j] >= 0 && cc[j] < num_nodes) {
-      const int64_t at = cc[j] * K + (p % K);
-      v_e[j] = eids[at];
-      if (kMode != 1) {
-        v_n[j] = nbrs[at];
-        v_t[j] = ts[at];
-      }
+    if (p < npairs) {
+      const int64_t c = n_id[r0 + fast_div20(p, k_mul)];
+      cc[j] = (c >= 0 && c < num_nodes) ? (IdT)c : (IdT)-1;
     }
   }
 #pragma unroll
-  for (int j = 0; j < kLookupPairsPerThread; ++j) {
+  for (int j = 0; j < kPairs; ++j) {
+    const int p = wid * (32 * kPairs) + j * 32 + lane;
+    v_e[j] = -1;
+    if (cc[j] >= 0) {
+      const int64_t at = (int64_t)cc[j] * K + (p - fast_div20(p, k_mul) * K);
+      v_e[j] = eids[at];
+      v_n[j] = (IdT)nbrs[at];
+      v_t[j] = ts[at];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kPairs; ++j) {
     ball[j] = __ballot_sync(0xffffffffu, v_e[j] >= 0);
     wtot += __popc(ball[j]);
   }
-  if (lane == 0) s_warp_tot[wid] = wtot;
+  if (kMode == 2) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+  }
+  if (lane == 0) {
+    s_warp_tot[wid] = wtot;
+    if (kMode == 2) s_warp_pre[wid] = pre;
+  }
   __syncthreads();
   long long tot = 0;
 #pragma unroll
-  for (int w = 0; w < kLookupThreads / 32; ++w) tot += s_warp_tot[w];
-  if (kMode == 1) {
-    if (tid == 0) ws[1 + tile] = (unsigned long long)tot;
-    return;
+  for (int w = 0; w < kThreads / 32; ++w) tot += s_warp_tot[w];
+  long long base;
+  if (kMode == 0) {
+    base = lookback_prefix_block(ws, tile, tot);
+  } else {
+    base = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) base += s_warp_pre[w];
   }
-  long long base = kMode == 0 ? lookback_prefix_block(ws, tile, tot) : (long long)ws[1 + tile];
   if (tid == 0 && tile == (ntiles > 0 ? ntiles : 1) - 1) {
     root_off[R] = (int32_t)(base + tot);
     *out_count = (int32_t)(base + tot);
   }
   for (int w = 0; w < wid; ++w) base += s_warp_tot[w];
 #pragma unroll
-  for (int j = 0; j < kLookupPairsPerThread; ++j) {
-    const int p = wid * (32 * kLookupPairsPerThread) + j * 32 + lane;
+  for (int j = 0; j < kPairs; ++j) {
     const long long pos = base + __popc(ball[j] & lanemask_lt());
+    const int p = wid * (32 * kPairs) + j * 32 + lane;
     if (p < npairs) {
-      const int r = p / K, slot = p - r * K;
-      if (slot == 0) root_off[r0 + r] = (int32_t)pos;
+      const int r = fast_div20(p, k_mul);
+      if (p == r * K) root_off[r0 + r] = (int32_t)pos;
       if ((ball[j] >> lane) & 1u) {
-        out_nbr[pos] = v_n[j];
-        out_ctr[pos] = n_id[r0 + r];
+        out_nbr[pos] = (int64_t)v_n[j];
+        out_ctr[pos] = (int64_t)cc[j];
         out_eid[pos] = v_e[j];
         out_t[pos] = v_t[j];
         if (l0) {
-          const int64_t id = v_n[j];
+          const int64_t id = (int64_t)v_n[j];
           if (id >= 0 && id < num_nodes) {
             uint32_t old = atomicOr(&l0[id >> 5], 1u << (id & 31));
             if (old == 0) {
@@ -128,39 +235,6 @@ __global__ void __launch_bounds__(kLookupThreads)
       }
     }
     base += __popc(ball[j]);
-  }
-}
-
-// exclusive scan of the per-tile counts in ws[1 .. ntiles] (in place), one CTA
-__global__ void __launch_bounds__(1024) nbr_tile_scan_kernel(unsigned long long* __restrict__ ws, int ntiles) {
-  pdl_wait();
-  pdl_launch();
-  __shared__ long long s_warp[32];
-  __shared__ long long s_base;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (int t0 = 0; t0 < ntiles; t0 += 1024) {
-    const int t = t0 + tid;
-    const long long c = t < ntiles ? (long long)ws[1 + t] : 0;
-    long long incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const long long y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    if (lane == 31) s_warp[wid] = incl;
-    __syncthreads();
-    long long before = 0, total = 0;
-    for (int w = 0; w < 32; ++w) {
-      const long long x = s_warp[w];
-      before += w < wid ? x : 0;
-      total += x;
-    }
-    if (t < ntiles) ws[1 + t] = (unsigned long long)(s_base + before + incl - c);
-    __syncthreads();
-    if (tid == 0) s_base += total;
-    __syncthreads();
   }
 }
 
@@ -396,7 +470,8 @@ int64_t tgn_nbr_lookup_ws_bytes(int32_t num_roots, int32_t size_k) {
   if (size_k < 1 || size_k > kMaxK || num_roots < 0) return 0;
   int tr = lookup_tile_roots(size_k);
   int ntiles = num_roots > 0 ? (num_roots + tr - 1) / tr : 1;
-  return (int64_t)(ntiles + 1) * 8;
+  // ticket | per-tile words | per-group totals of the count pass
+  return (int64_t)(1 + ntiles + (ntiles + kCountTiles - 1) / kCountTiles) * 8;
 }
 
 int32_t tgn_nbr_lookup(const int64_t* n_id, int32_t num_roots, const int32_t* num_roots_dev,
@@ -412,24 +487,34 @@ int32_t tgn_nbr_lookup(const int64_t* n_id, int32_t num_roots, const int32_t* nu
   cudaStream_t s = (cudaStream_t)stream;
   const int tr = lookup_tile_roots(size_k);
   const int ntiles = num_roots > 0 ? (num_roots + tr - 1) / tr : 1;
+  const uint32_t k_mul = (1u << 20) / (uint32_t)size_k + 1u;   // fast_div20: pair index < 2048 <= 2^20 / 64
   uint32_t* l0 = (uint32_t*)bitmap;
   uint32_t* l1 = l0 ? l0 + ((num_nodes + 1023) / 1024) * 32 : nullptr;
   DevCount rc{num_roots_dev, num_roots};
   unsigned long long* w = (unsigned long long*)ws;
-  if (ntiles >= kLookupThreePassTiles) {   // large launch: count -> scan -> emit, no inter-CTA dependency
-    launch_k(nbr_lookup_kernel<1>, dim3(ntiles), dim3(kLookupThreads), 0, s, n_id, rc, size_k, tr, num_nodes,
-             neighbors, e_id, t, out_nbr, out_centre, out_eid, out_t, root_off, out_count, l0, l1, w);
+  if (ntiles >= kLookupThreePassTiles) {   // large launch: count -> emit, no inter-CTA dependency
+    const int groups = (ntiles + kCountTiles - 1) / kCountTiles;
+    if ((size_k & 1) == 0 && (reinterpret_cast<uintptr_t>(e_id) & 15) == 0)
+      launch_k(nbr_count_kernel<2>, dim3(groups), dim3(kCountThreads), 0, s, n_id, rc, size_k, tr, ntiles,
+               num_nodes, e_id, w);
+    else
+      launch_k(nbr_count_kernel<1>, dim3(groups), dim3(kCountThreads), 0, s, n_id, rc, size_k, tr, ntiles,
+               num_nodes, e_id, w);
     TGN_LAUNCH_CHECK();
-    launch_k(nbr_tile_scan_kernel, dim3(1), dim3(1024), 0, s, w, ntiles);
-    TGN_LAUNCH_CHECK();
-    launch_k(nbr_lookup_kernel<2>, dim3(ntiles), dim3(kLookupThreads), 0, s, n_id, rc, size_k, tr, num_nodes,
-             neighbors, e_id, t, out_nbr, out_centre, out_eid, out_t, root_off, out_count, l0, l1, w);
+    if (num_nodes < (1ll << 31))
+      launch_k(nbr_lookup_kernel<2, 256, 8, 4, int32_t>, dim3(ntiles), dim3(kLookupThreads), 0, s, n_id, rc, size_k,
+               k_mul, tr, ntiles, num_nodes, neighbors, e_id, t, out_nbr, out_centre, out_eid, out_t, root_off,
+               out_count, l0, l1, w);
+    else
+      launch_k(nbr_lookup_kernel<2, 256, 8, 3, int64_t>, dim3(ntiles), dim3(kLookupThreads), 0, s, n_id, rc, size_k,
+               k_mul, tr, ntiles, num_nodes, neighbors, e_id, t, out_nbr, out_centre, out_eid, out_t, root_off,
+               out_count, l0, l1, w);
     TGN_LAUNCH_CHECK();
     return TGN_OK;
   }
   TGN_CUDA(cudaMemsetAsync(ws, 0, (size_t)(ntiles + 1) * 8, s));
-  launch_k(nbr_lookup_kernel<0>, dim3(ntiles), dim3(kLookupThreads), 0, s,
-      n_id, rc, size_k, tr, num_nodes, neighbors, e_id, t, out_nbr, out_centre, out_eid, out_t,
+  launch_k(nbr_lookup_kernel<0, 256, 8, 3, int64_t>, dim3(ntiles), dim3(kLookupThreads), 0, s,
+      n_id, rc, size_k, k_mul, tr, ntiles, num_nodes, neighbors, e_id, t, out_nbr, out_centre, out_eid, out_t,
       root_off, out_count, l0, l1, w);
   TGN_LAUNCH_CHECK();
   return TGN_OK;

@@ -53,8 +53,10 @@ class TGNEngine:
                  log_capacity: int = 1 << 20, seed: int = 0, use_graph: bool = True,
                  precision: int = 3, rank: int = 0, world: int = 1, group=None, fused_zero_grad: bool = False,
                  part_exchange: str = "p2p", share: Optional["TGNEngine"] = None, part_compute: str = "owner",
-                 track_metrics: bool = False):
-        """share: another engine of the same model (nodes, dims, K, world) whose weights, Adam moments, node
+                 track_metrics: bool = False, group_size: int = 3):
+        """group_size: training steps per captured graph / host group (train_steps, train_group_logged); the
+        staging slots are three such groups.
+        share: another engine of the same model (nodes, dims, K, world) whose weights, Adam moments, node
         memory, neighbour ring, message store, event arrays and cursors this one USES instead of allocating
         its own -- a second step geometry (another batch size, e.g. the tail batch of an epoch) on the same
         training state.  Only one of the engines may be stepping at a time."""
@@ -231,7 +233,9 @@ class TGNEngine:
         # three groups the copy of group g+1 only has to wait for group g-2, so it overlaps group g-1
         # completely and group g starts the moment g-1 ends (two groups left a copy-sized bubble per group).
         # The staging regions of all slots are one allocation so a group's three batches are contiguous.
-        self.nslots, self.group_size = 9, 3
+        if group_size < 1:
+            raise ValueError("group_size must be >= 1")
+        self.nslots, self.group_size = 3 * group_size, group_size
         De1 = max(raw_dim, 1)
         self._packed = (32 * batch_size + 4 * batch_size * De1 + 15) // 16 * 16      # bytes per staged batch
         self._in_all = torch.zeros(self.nslots * self._packed, dtype=torch.uint8, device=dev)

@@ -16,6 +16,8 @@ ap.add_argument("--prefill", type=int, default=300_000)
 ap.add_argument("--precision", type=int, default=3)
 ap.add_argument("--workload", default=bench.WORKLOAD)
 ap.add_argument("--batch", type=int, default=None)
+ap.add_argument("--group", action="store_true", help="profile train_steps() (three steps per captured graph) and print "
+                "the window between two consecutive steps INSIDE one graph replay")
 ap.add_argument("--eval", type=int, default=0, help="Q > 0: timeline of one evaluation batch with Q negatives per positive")
 a = ap.parse_args()
 rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -51,6 +53,13 @@ if a.eval:
             eng.eval_batch(*b)
         torch.cuda.synchronize()
     marker = "unique_mark"
+elif a.group:
+    eng.train_steps(61)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        eng.train_steps(12)
+        torch.cuda.synchronize()
+    marker = "part_select_owned" if world > 1 else "msg_build"
 else:
     for _ in range(30):
         eng.train_step(from_device=True)
@@ -74,6 +83,11 @@ if a.eval:      # the first unique_mark of every batch: keep starts that are >20
             keep.append(i)
     starts = keep
 lo, hi = starts[-3], starts[-2]
+if a.group:     # the closest pair of consecutive steps: both inside one graph replay
+    gaps = [ev[starts[i + 1]]["ts"] - ev[starts[i]]["ts"] for i in range(len(starts) - 1)]
+    print("step starts (us apart):", " ".join(f"{g:.1f}" for g in gaps))
+    i = max(range(len(starts) - 3), key=lambda j: -(ev[starts[j + 3]]["ts"] - ev[starts[j]]["ts"]))
+    lo, hi = starts[i], starts[i + 3]      # three consecutive steps, the tightest such window
 t0 = ev[lo]["ts"]
 streams = sorted({e["args"].get("stream") for e in ev[lo:hi]})
 print(f"{a.workload} B={B}{' eval Q=%d' % a.eval if a.eval else ''}: step = {ev[hi]['ts'] - t0:.1f} us between two {marker} launches; streams {streams}")

@@ -458,6 +458,7 @@ struct GruParams {
   float* gates;         // [S, 4D] nullable: r, z, n, gh_n
   const int32_t* m_dev;
   int m, dx, D, prec;
+  int late_pdl;         // 1: dependents are released after the last MMA has been issued (not at kernel start)
 };
 
 template <int N>
@@ -536,7 +537,7 @@ __device__ __forceinline__ void gru_epilogue_chunk(const GruParams& P, uint32_t 
 __global__ void __launch_bounds__(kGThreads, 1)
     gru_fused_kernel(const __grid_constant__ GruMaps maps, const __grid_constant__ GruParams P) {
   pdl_wait();
-  pdl_launch();
+  if (!P.late_pdl) pdl_launch();
   extern __shared__ __align__(1024) uint8_t g_smem[];
   __shared__ __align__(8) uint64_t s_full[kGStages3], s_conv[kGStages3], s_empty[kGStages3], s_acc;
   __shared__ uint32_t s_tmem;
@@ -584,7 +585,7 @@ __global__ void __launch_bounds__(kGThreads, 1)
   const uint32_t tmem = s_tmem;
 
   pdl_wait();
-  pdl_launch();
+  if (!P.late_pdl) pdl_launch();
   const int M = P.m_dev ? min(*P.m_dev, P.m) : P.m;
   const int nk1 = (P.dx + GK - 1) / GK, nk2 = (P.D + GK - 1) / GK;
   const bool live = m0 < M;
@@ -637,6 +638,7 @@ __global__ void __launch_bounds__(kGThreads, 1)
       }
       __syncwarp();
     }
+    if (P.late_pdl) pdl_launch();     // (dead tiles: nk = 0, released at once)
   } else {
     const int et = tid - 64;
     if (split3) {
@@ -774,17 +776,18 @@ int32_t tgn_gemm_batch(const tgn_gemm_desc* d, int32_t count, int32_t precision,
   const size_t smem_max = (size_t)kGStages3 * kGStageBytes3 + 1024;
   static unsigned long long attr_mask = 0;
   TGN_CUDA(smem_optin(tgemm_kernel, (int)smem_max, attr_mask));
-  // Ring depth.  A full ring (192 KB) allows one CTA per SM.  A launch of short reductions whose tiles
-  // do not fit one wave of 148 CTAs but fit two CTAs per SM runs with a 64 KB ring instead: all tiles
-  // are resident at once, which beats a second wave for K <= 4 k-blocks (e.g. the node projection of
-  // the attention: 4 column tiles x 38 live row tiles = 152 CTAs).
+  // Ring depth.  A full ring (192 KB) allows one CTA per SM.  A launch of short reductions (K <= 4
+  // k-blocks) whose tiles do not fit one wave of 148 CTAs runs with a 64 KB ring instead: three CTAs per
+  // SM overlap each other's load / split / MMA / epilogue phases, which beats further waves of deeply
+  // pipelined CTAs (the node projection of the attention: 4 column tiles x 38 live row tiles = 152 CTAs;
+  // the evaluation's edge projection: 1,418 tiles, batch 0.604 -> 0.582 ms).
   prm.stages = precision == 3 ? kGStages3 : kGStages1;
   int max_nk = 0;
   for (int i = 0; i < np; ++i) {
     const int kk = ceil_div(ceil_div(prm.p[i].k, prm.p[i].split_k), GK);
     if (kk > max_nk) max_nk = kk;
   }
-  if (tiles > kNumSMs && tiles <= 2 * kNumSMs && max_nk <= 4) prm.stages = precision == 3 ? 1 : 2;
+  if (tiles > kNumSMs && max_nk <= 4) prm.stages = precision == 3 ? 1 : 2;
   const size_t smem = (size_t)prm.stages * (precision == 3 ? kGStageBytes3 : kGStageBytes1) + 1024;
   launch_k(tgemm_kernel, dim3(tiles), dim3(kGThreads), smem, (cudaStream_t)stream, maps, prm);
   TGN_LAUNCH_CHECK();
@@ -813,6 +816,7 @@ int32_t tgn_gru_fused_fwd(const float* x, int32_t ldx, int32_t dx, const float* 
   GruParams P;
   P.h = h; P.b_ih = b_ih; P.b_hh = b_hh; P.out = out; P.gates = gates; P.m_dev = num_dev;
   P.m = num; P.dx = dx; P.D = dim; P.prec = precision;
+  P.late_pdl = 0;     // A/B on the review step (tools/ab_env.py): 147.9 vs 149.1 us, inside the run-to-run spread
   const size_t smem = (size_t)kGStages3 * kGStageBytes3 + 1024;
   static unsigned long long attr_mask = 0;
   TGN_CUDA(smem_optin(gru_fused_kernel, (int)smem, attr_mask));

@@ -209,7 +209,7 @@ class TGNEngine:
         self._cur = SimpleNamespace(events_done=0, ring_pos=0, events=None) if share is None else share._cur
         self.side = torch.cuda.Stream(device=dev)    # ring insert + sampling of the NEXT batch
         self.upd = torch.cuda.Stream(device=dev)     # memory / message-store update of this batch
-        self.aux = torch.cuda.Stream(device=dev)     # edge branch of the attention / small reductions
+        self.aux = torch.cuda.Stream(device=dev, priority=0)   # edge branch of the attention / small reductions
         self.w = self._alloc_work(R, E, Nb, batch_size)
         if self.owner_compute:
             # every rank's table of the step's rows (h', last_update'): owners publish into it over NVLink

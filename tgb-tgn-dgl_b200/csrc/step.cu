@@ -49,33 +49,68 @@ struct EdgeAttr2Args {
   int32_t* err;
 };
 
-__global__ void edge_attr_ld_kernel(EdgeAttr2Args a) {
+// One warp per edge, lanes over the columns of the row (coalesced 128-byte stores); the edge's scalars
+// (event row, its time stamp, the neighbour's last_update) are fetched once per edge for kEdgesPerWarp edges
+// at a time, all ahead of the first use.  Round 2: the first version mapped one thread to one OUTPUT ELEMENT
+// with a 64-bit division and four dependent scalar loads per element (130 us for the 181k edges of a flight
+// evaluation batch -- instruction-bound); kSin = false (evaluation) computes the cosine only.
+constexpr int kEdgesPerWarp = 4;
+template <bool kSin>
+__global__ void __launch_bounds__(256) edge_attr_ld_kernel(EdgeAttr2Args a) {
   pdl_wait();
   pdl_launch();
   const int E = a.edges.get();
-  const long long total = (long long)E * a.ld;
-  for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total;
-       x += (long long)gridDim.x * blockDim.x) {
-    const int e = (int)(x / a.ld), d = (int)(x - (long long)e * a.ld);
-    const long long mr = a.msg_rows ? a.msg_rows[e] : e;
-    if (a.num_events > 0 && (mr < 0 || mr >= a.num_events)) {  // the ring names an event that is not resident
-      if (d == 0) flag_dev_err(a.err, TGN_DEVERR_EVENT_RANGE);
-      a.ea[x] = 0.f;
-      if (d < a.Dt && a.sn) a.sn[(long long)e * a.Dt + d] = 0.f;
-      if (d == 0 && a.rel) a.rel[e] = 0.f;
-      continue;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int e0 = warp * kEdgesPerWarp; e0 < E; e0 += nwarps * kEdgesPerWarp) {
+    long long mr[kEdgesPerWarp], nb[kEdgesPerWarp];
+#pragma unroll
+    for (int u = 0; u < kEdgesPerWarp; ++u) {
+      const int e = e0 + u;
+      mr[u] = -1;
+      nb[u] = 0;
+      if (e < E) {
+        mr[u] = a.msg_rows ? a.msg_rows[e] : e;
+        nb[u] = a.nbr[e];
+      }
     }
-    if (d < a.Dt) {
-      const float rt = (float)(a.lu[a.nbr[e]] - a.t_edge[mr]);
-      float sv, cv;
-      sincos_fr(__fmaf_rn(rt, a.time_w[d], a.time_b[d]), &sv, &cv);
-      a.ea[x] = cv;
-      if (a.sn) a.sn[(long long)e * a.Dt + d] = sv;
-      if (d == 0 && a.rel) a.rel[e] = rt;
-    } else if (d < a.Dt + a.De) {
-      a.ea[x] = a.msg[mr * a.De + (d - a.Dt)];
-    } else {
-      a.ea[x] = 0.f;
+    float rt[kEdgesPerWarp];
+    bool ok[kEdgesPerWarp];
+#pragma unroll
+    for (int u = 0; u < kEdgesPerWarp; ++u) {
+      ok[u] = e0 + u < E && !(a.num_events > 0 && (mr[u] < 0 || mr[u] >= a.num_events));
+      rt[u] = ok[u] ? (float)(a.lu[nb[u]] - a.t_edge[mr[u]]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kEdgesPerWarp; ++u) {
+      const int e = e0 + u;
+      if (e >= E) break;                                  // warp-uniform
+      float* row = a.ea + (long long)e * a.ld;
+      if (!ok[u]) {   // the ring names an event that is not resident
+        if (lane == 0) flag_dev_err(a.err, TGN_DEVERR_EVENT_RANGE);
+        for (int d = lane; d < a.ld; d += 32) row[d] = 0.f;
+        if (kSin)
+          for (int d = lane; d < a.Dt; d += 32) a.sn[(long long)e * a.Dt + d] = 0.f;
+        if (lane == 0 && a.rel) a.rel[e] = 0.f;
+        continue;
+      }
+      for (int d = lane; d < a.ld; d += 32) {
+        float v = 0.f;
+        if (d < a.Dt) {
+          const float arg = __fmaf_rn(rt[u], a.time_w[d], a.time_b[d]);
+          if (kSin) {
+            float sv;
+            sincos_fr(arg, &sv, &v);
+            a.sn[(long long)e * a.Dt + d] = sv;
+          } else {
+            v = cos_fr(arg);
+          }
+        } else if (d < a.Dt + a.De) {
+          v = a.msg[mr[u] * a.De + (d - a.Dt)];
+        }
+        row[d] = v;
+      }
+      if (lane == 0 && a.rel) a.rel[e] = rt[u];
     }
   }
 }
@@ -1089,7 +1124,9 @@ int32_t tgn_edge_attr_ld(const int64_t* last_update_local, const int64_t* nbr_lo
   a.edges = DevCount{num_edges_dev, num_edges}; a.De = raw_dim; a.Dt = time_dim; a.ld = ld;
   a.time_w = time_w; a.time_b = time_b; a.ea = edge_attr; a.sn = sin_out; a.rel = rel_t;
   a.num_events = num_events; a.err = dev_err_word();
-  launch_k(edge_attr_ld_kernel, dim3(stride_grid((long long)num_edges * ld, 256)), dim3(256), 0, (cudaStream_t)stream, a);
+  const int grid = stride_grid((long long)ceil_div(num_edges, kEdgesPerWarp) * 32, 256);
+  if (sin_out) launch_k(edge_attr_ld_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a);
+  else launch_k(edge_attr_ld_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

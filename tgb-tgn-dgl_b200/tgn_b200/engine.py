@@ -1393,6 +1393,8 @@ class TGNEngine:
         c.Rall = N if c.dense else min(N, n_ids)
         c.Rm = (c.Rall + P - 1) // P
         R, E, Nb = self._bounds(B, roots=c.Rm)
+        if c.dense:
+            Nb = N      # dense: the row of node n in every per-node table of the step IS n (no unique / relabel)
         c.w = self._alloc_work(R, E, Nb, B, train=False)
         c.mw = self._alloc_work(1, 1, 2 * B, 1, train=False)
         i64 = lambda *s_: torch.zeros(s_, dtype=torch.long, device=dev)
@@ -1410,6 +1412,10 @@ class TGNEngine:
             mine = torch.arange(rank, N, P, device=dev)
             c.my_roots[:mine.numel()] = mine
             c.Rm_dev.fill_(mine.numel())
+            # identity relabelling: centres are addressed by their global ids, the neighbour lookup's global ids
+            # are used as rows directly, every node has a row
+            c.w.ctr_l, c.w.R_dev, c.my_l = c.my_roots, c.Rm_dev, c.my_roots
+            c.w.Nb_dev.fill_(N)
         c.e_r = torch.zeros((c.Rm, D), device=dev)
         c.send = torch.zeros((2, c.Rm, D), device=dev)               # [lin_src(emb) | lin_dst(emb)] of my centres
         c.recv = torch.zeros((P, 2, c.Rm, D), device=dev) if P > 1 else c.send.view(1, 2, c.Rm, D)
@@ -1433,10 +1439,20 @@ class TGNEngine:
             check(L.tgn_relabel(_p(c.ids), c.n_ids, None, _p(self.assoc), _p(c.ids_g), _stream()))
             check(L.tgn_stride_select(_p(c.roots_all), c.Rall, _p(c.Rall_dev), rank, P, _p(c.my_roots), c.Rm,
                                       _p(c.Rm_dev), _stream()))
-        self._sample(w, c.my_roots, c.my_l, ids_dev=c.Rm_dev)
-        s = _stream()
-        check(L.tgn_gather_rows(_p(self.memory), _p(w.n_id), w.Nb, _p(w.Nb_dev), D, _p(w.z), s))
-        check(L.tgn_relabel(_p(w.n_id), w.Nb, _p(w.Nb_dev), _p(self.last_update), _p(w.lu), s))
+        if c.dense:
+            # every node is a root of SOME rank and (through the hubs) a neighbour of every rank's roots: the step
+            # works on all N rows in place -- one ring lookup of this rank's roots, a snapshot of memory /
+            # last_update (the forked state update below rewrites the touched rows), no unique / relabel launches
+            check(L.tgn_nbr_lookup(_p(c.my_roots), c.Rm, _p(c.Rm_dev), self.K, N, _p(self.neighbors), _p(self.e_id),
+                                   _p(self.t_ring), _p(w.nbr_l), _p(w.ctr_g), _p(w.eid), _p(w.t_e), _p(w.root_off),
+                                   _p(w.E_dev), None, _p(w.lookup_ws), _stream()))
+            w.z.copy_(self.memory)
+            w.lu.copy_(self.last_update)
+        else:
+            self._sample(w, c.my_roots, c.my_l, ids_dev=c.Rm_dev)
+            s = _stream()
+            check(L.tgn_gather_rows(_p(self.memory), _p(w.n_id), w.Nb, _p(w.Nb_dev), D, _p(w.z), s))
+            check(L.tgn_relabel(_p(w.n_id), w.Nb, _p(w.Nb_dev), _p(self.last_update), _p(w.lu), s))
         # ---- forked: the batch's state update (store first, then memory: memory_module.py:135-138; then the ring).
         # It needs the batch only, and may start once this batch's sampling and memory reads are issued.
         upd.wait_stream(main)

@@ -352,9 +352,9 @@ constexpr int kSmallDeg = 12;
 // p % 32 in round p / 32 (same Philox counters (edge, head) and word as the per-pair draw of the
 // general kernels, so the mask is bit-identical) -- one Philox evaluation per lane instead of
 // kSmallDeg*H evaluations repeated by every lane, which was a third of these kernels' instructions.
-template <int H>
+template <int H, int kDeg = kSmallDeg>
 struct SmallMask {
-  static constexpr int kRounds = (kSmallDeg * H + 31) / 32;
+  static constexpr int kRounds = (kDeg * H + 31) / 32;
   float u[kRounds];
   __device__ __forceinline__ void draw(const Philox& rng, int e0, int deg, int lane) {
 #pragma unroll
@@ -374,8 +374,10 @@ struct SmallMask {
   }
 };
 
-template <int H>
-__global__ void __launch_bounds__(kCoreWarps * 32) attn_core_fwd_small_kernel(AttnCoreArgs a) {
+// kDeg = register-resident edge slots per centre (10 for the TGN default of 10 neighbours: 131 registers, four
+// CTAs per SM on evaluation-sized launches; 12 otherwise)
+template <int H, int kDeg, int kMinCtas>
+__global__ void __launch_bounds__(kCoreWarps * 32, kMinCtas) attn_core_fwd_small_kernel(AttnCoreArgs a) {
   pdl_wait();
   pdl_launch();
   const int HC = a.H * a.C, C = a.C;
@@ -392,25 +394,25 @@ __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_fwd_small_kernel(At
   for (int ci = blockIdx.x * kCoreWarps + wid; ci < nC; ci += gridDim.x * kCoreWarps) {
     const int64_t row = a.centre_ids ? a.centre_ids[ci] : ci;
     const int e0 = a.row_ptr[ci];
-    const int deg = min(a.row_ptr[ci + 1] - e0, kSmallDeg);
+    const int deg = min(a.row_ptr[ci + 1] - e0, kDeg);
     const float* pr = a.proj + row * 4 * HC;
     const float4 q = ok ? ld4(pr + c0) : z4;
     const float4 skip = ok ? ld4(pr + 3 * HC + c0) : z4;
     const int64_t my_j = lane < deg ? a.nbr[e0 + lane] : 0;
-    float4 kk[kSmallDeg], vv[kSmallDeg];
+    float4 kk[kDeg], vv[kDeg];
 #pragma unroll
-    for (int g = 0; g < kSmallDeg; ++g) {
+    for (int g = 0; g < kDeg; ++g) {
       const int64_t j = __shfl_sync(0xffffffffu, my_j, g);
       const bool on = ok && g < deg;
       const float4 eev = on ? ld4(a.ee + (long long)(e0 + g) * HC + c0) : z4;
       kk[g] = on ? f4_add(ld4(a.proj + j * 4 * HC + HC + c0), eev) : z4;
       vv[g] = on ? f4_add(ld4(a.proj + j * 4 * HC + 2 * HC + c0), eev) : z4;
     }
-    float sc[kSmallDeg][H], mx[H], den[H];
+    float sc[kDeg][H], mx[H], den[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) mx[h] = -INFINITY;
 #pragma unroll
-    for (int g = 0; g < kSmallDeg; ++g) {
+    for (int g = 0; g < kDeg; ++g) {
       float part[H];
 #pragma unroll
       for (int h = 0; h < H; ++h) part[h] = 0.f;
@@ -424,17 +426,17 @@ __global__ void __launch_bounds__(kCoreWarps * 32) attn_core_fwd_small_kernel(At
 #pragma unroll
     for (int h = 0; h < H; ++h) den[h] = 0.f;
 #pragma unroll
-    for (int g = 0; g < kSmallDeg; ++g)
+    for (int g = 0; g < kDeg; ++g)
 #pragma unroll
       for (int h = 0; h < H; ++h) {
         sc[g][h] = g < deg ? expf(sc[g][h] - mx[h]) : 0.f;
         den[h] += sc[g][h];
       }
     float4 acc = z4;
-    SmallMask<H> sm;
+    SmallMask<H, kDeg> sm;
     if (a.dropout_p > 0.f) sm.draw(rng, e0, deg, lane);
 #pragma unroll
-    for (int g = 0; g < kSmallDeg; ++g) {
+    for (int g = 0; g < kDeg; ++g) {
       if (g >= deg) break;  // warp-uniform
       float pw[H];
 #pragma unroll
@@ -1179,9 +1181,14 @@ int32_t tgn_attn_core_fwd(const float* proj, const int64_t* nbr_local, const int
   cudaStream_t s = (cudaStream_t)stream;
   if (max_degree > 0 && max_degree <= kSmallDeg && heads * head_dim <= 128 && heads <= 4) {
     switch (heads) {
-      case 1: launch_k(attn_core_fwd_small_kernel<1>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
-      case 2: launch_k(attn_core_fwd_small_kernel<2>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
-      default: launch_k(attn_core_fwd_small_kernel<4>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+      case 1: launch_k(attn_core_fwd_small_kernel<1, kSmallDeg, 3>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
+      case 2:
+        if (max_degree <= 10 && num_centres > 8 * kNumSMs * kCoreWarps)   // occupancy only pays on multi-wave launches
+          launch_k(attn_core_fwd_small_kernel<2, 10, 4>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a);
+        else
+          launch_k(attn_core_fwd_small_kernel<2, kSmallDeg, 3>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a);
+        break;
+      default: launch_k(attn_core_fwd_small_kernel<4, kSmallDeg, 2>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
     }
     TGN_LAUNCH_CHECK();
     return TGN_OK;

@@ -18,6 +18,7 @@ ap.add_argument("--workload", default=bench.WORKLOAD)
 ap.add_argument("--batch", type=int, default=None)
 ap.add_argument("--group", action="store_true", help="profile train_steps() (three steps per captured graph) and print "
                 "the window between two consecutive steps INSIDE one graph replay")
+ap.add_argument("--dp", action="store_true", help="with --eval: the sharded evaluation step eval_batch_dp (one rank)")
 ap.add_argument("--eval", type=int, default=0, help="Q > 0: timeline of one evaluation batch with Q negatives per positive")
 a = ap.parse_args()
 rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -45,14 +46,15 @@ if a.eval:
         neg = torch.from_numpy(synth.eval_negatives(data["src"][sl], data["dst"][sl], N, a.eval, seed=1000 + b))
         return tuple(x.to(dev) for x in (ev_t["src"][sl], ev_t["dst"][sl], neg, ev_t["t"][sl], ev_t["msg"][sl]))
     bs = [batch(b) for b in range(12)]
+    run = (lambda b: eng.eval_batch_dp(*b, 0, 1, reduce=True)) if a.dp else (lambda b: eng.eval_batch(*b))
     for b in bs[:8]:
-        eng.eval_batch(*b)
+        run(b)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for b in bs[8:]:
-            eng.eval_batch(*b)
+            run(b)
         torch.cuda.synchronize()
-    marker = "unique_mark"
+    marker = "nbr_count" if a.dp else "unique_mark"
 elif a.group:
     eng.train_steps(61)
     torch.cuda.synchronize()

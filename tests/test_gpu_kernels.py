@@ -293,7 +293,7 @@ def test_aggregators_golden_and_ties(ops):
 @pytest.mark.parametrize("ta", [False, True])
 @pytest.mark.parametrize("tb", [False, True])
 @pytest.mark.parametrize("m,n,k,split", [(1, 1, 1, 1), (65, 300, 472, 1), (600, 400, 100, 1), (300, 472, 4000, 8),
-                                         (129, 63, 17, 2), (5023, 300, 472, 1)])
+                                         (129, 63, 17, 2), (5023, 300, 472, 1), (50_000, 300, 472, 1)])
 def test_sgemm(ops, prec, ta, tb, m, n, k, split):
     """prec 0: fp32 CUDA cores; 3: tcgen05 3xTF32 (same tolerance); 1: tcgen05 tf32 (2e-2 bar)."""
     g = torch.Generator(device="cpu").manual_seed(m * n + k)
@@ -356,6 +356,45 @@ def test_tma_gemm_device_reduction_length(ops, prec, m, n, k, ta, tb, split, liv
         torch.testing.assert_close(out.cpu().double(), ref, rtol=2e-2, atol=2e-3 * scale)
     else:
         torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-5, atol=1e-5 * max(4.0, live ** 0.5) * 2)
+
+
+@pytest.mark.parametrize("prec", [3, 1])
+def test_tma_gemm_persistent_multiwave(ops, prec):
+    """Launches of several waves of tiles take the persistent kernel (one CTA per SM walking tiles, TMEM
+    double-buffered accumulators): a batch of three problems in ONE launch -- a store problem with a device row
+    count and a bias (rows past the count untouched, column tail of a 300-wide output), a transposed split-K
+    problem with a device reduction length that ends inside a k-block (atomic accumulation into a pre-filled
+    C), and a short-K problem -- against float64."""
+    g = torch.Generator(device="cpu").manual_seed(7)
+    m0, n0, k0, live0 = 30_000, 300, 116, 25_001
+    A0 = torch.randn(m0, k0, generator=g); B0 = torch.randn(n0, k0, generator=g); bias0 = torch.randn(n0, generator=g)
+    C0 = torch.full((m0, n0), 7.0, device=DEV)
+    m1, n1, k1, live1, split1 = 300, 472, 40_000, 39_987, 48
+    A1 = torch.randn(k1, m1, generator=g); B1 = torch.randn(k1, n1, generator=g)
+    A1[live1:] = 1e30; B1[live1:] = -1e30
+    C1 = torch.ones(m1, n1, device=DEV)
+    m2, n2, k2 = 20_000, 100, 100
+    A2 = torch.randn(m2, k2, generator=g); B2 = torch.randn(n2, k2, generator=g)
+    C2 = torch.zeros(m2, n2, device=DEV)
+    d = lambda t: t.to(DEV)
+    A0d, B0d, b0d, A1d, B1d, A2d, B2d = map(d, (A0, B0, bias0, A1, B1, A2, B2))
+    mdev = torch.tensor([live0], dtype=torch.int32, device=DEV)
+    kdev = torch.tensor([live1], dtype=torch.int32, device=DEV)
+    ops.gemm_batch([
+        ops.gemm_desc(A0d, B0d, C0, m=m0, n=n0, k=k0, lda=k0, ldb=k0, ldc=n0, bias=b0d, m_dev=mdev),
+        ops.gemm_desc(A1d, B1d, C1, m=m1, n=n1, k=k1, lda=m1, ldb=n1, ldc=n1, trans_a=True, trans_b=True, mode=2,
+                      split_k=split1, k_dev=kdev),
+        ops.gemm_desc(A2d, B2d, C2, m=m2, n=n2, k=k2, lda=k2, ldb=k2, ldc=n2, mode=1),
+    ], prec)
+    tol = (lambda k, ref: dict(rtol=2e-2, atol=2e-3 * float(ref.abs().max()))) if prec == 1 else \
+          (lambda k, ref: dict(rtol=1e-5, atol=2e-5 * max(4.0, k ** 0.5)))
+    ref0 = A0[:live0].double() @ B0.double().t() + bias0.double()
+    torch.testing.assert_close(C0[:live0].cpu().double(), ref0, **tol(k0, ref0))
+    assert bool((C0[live0:] == 7.0).all())
+    ref1 = A1[:live1].double().t() @ B1[:live1].double() + 1.0
+    torch.testing.assert_close(C1.cpu().double(), ref1, **tol(live1, ref1))
+    ref2 = A2.double() @ B2.double().t()
+    torch.testing.assert_close(C2.cpu().double(), ref2, **tol(k2, ref2))
 
 
 @pytest.mark.parametrize("S,Dx,D", [(1, 5, 3), (333, 472, 100), (4000, 274, 100)])

@@ -23,6 +23,7 @@
 //               vector reductions (split-K)
 //   precision 1: operands go to the tensor core as they land (tf32 mantissa), no split pass.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "../../include/tgn_b200.h"
 #include "common.cuh"
@@ -433,6 +434,305 @@ __global__ void __launch_bounds__(kGThreads, 1)
 
 
 // ---------------------------------------------------------------------------
+// Persistent variant for launches of several waves of tiles (evaluation, flush, module path, large batches):
+// one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the shared-memory ring runs on across
+// tile boundaries and the accumulator is double-buffered in TMEM (2 x 128 columns), so the epilogue of tile i
+// (four dedicated warps) overlaps the loads, the split pass and the MMAs of tile i + 1.  tgemm_kernel pays its
+// prologue, the pipeline fill and the epilogue once PER TILE (ncu, round 1: 17 us per 15-k-block tile, the
+// tensor pipe idle most of it).
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-9 split / mask pass | warps 10-13 epilogue
+// ---------------------------------------------------------------------------
+constexpr int kPThreads = 448;
+constexpr int kPEpiWarp0 = 10;
+
+struct TileInfo {
+  int pi, m0, n0, split, M, kbeg, kend, nk;
+  bool live, tail_mask;
+};
+
+__device__ __forceinline__ TileInfo g_tile_info(const GemmParams& prm, int t) {
+  TileInfo ti;
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxProb; ++i)
+    if (i < prm.nprob && t >= prm.p[i].tile_begin) pi = i;
+  const GemmProb& P = prm.p[pi];
+  int local = t - P.tile_begin;
+  const int tn = local % P.tiles_n;
+  local /= P.tiles_n;
+  const int tm = local % P.tiles_m;
+  ti.pi = pi;
+  ti.split = local / P.tiles_m;
+  ti.m0 = tm * GM;
+  ti.n0 = tn * GN;
+  ti.M = P.m_dev ? min(*P.m_dev, P.m) : P.m;
+  const int K = P.k_dev ? min(*P.k_dev, P.k) : P.k;
+  const int kchunk = ((K + P.split_k - 1) / P.split_k + GK - 1) / GK * GK;
+  ti.kbeg = ti.split * kchunk;
+  ti.kend = min(K, ti.kbeg + kchunk);
+  int nk = ti.kend > ti.kbeg ? (ti.kend - ti.kbeg + GK - 1) / GK : 0;
+  ti.live = ti.m0 < ti.M && !(nk == 0 && P.mode != 0);
+  if (!ti.live) nk = 0;
+  ti.nk = nk;
+  ti.tail_mask = nk > 0 && ti.kend < P.k && ((ti.kend - ti.kbeg) & (GK - 1)) != 0;
+  return ti;
+}
+
+__global__ void __launch_bounds__(kPThreads, 1)
+    tgemm_persist_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmParams prm,
+                         int total_tiles) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ __align__(1024) uint8_t g_smem[];
+  __shared__ __align__(8) uint64_t s_full[kGMaxStages], s_conv[kGMaxStages], s_empty[kGMaxStages];
+  __shared__ __align__(8) uint64_t s_accf[2], s_acce[2];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool split3 = prm.prec == 3;
+  const int S = prm.stages;
+  const int kStageBytes = split3 ? kGStageBytes3 : kGStageBytes1;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g_smem) + 1023) &
+                                             ~(uintptr_t)1023);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < kGMaxStages; ++i) {
+      g_mbar_init(&s_full[i], 1);
+      g_mbar_init(&s_conv[i], kGConv / 32);
+      g_mbar_init(&s_empty[i], 1);
+    }
+    g_mbar_init(&s_accf[0], 1);
+    g_mbar_init(&s_accf[1], 1);
+    g_mbar_init(&s_acce[0], 4);      // one arrival per epilogue warp
+    g_mbar_init(&s_acce[1], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < prm.nprob; ++i) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[i]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[i]) : "memory");
+    }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     g_smem_u32(&s_tmem)),
+                 "r"(2 * GN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileInfo ti = g_tile_info(prm, t);
+        const GemmProb& P = prm.p[ti.pi];
+        const CUtensorMap* ma = &maps.a[ti.pi];
+        const CUtensorMap* mb = &maps.b[ti.pi];
+        for (int kb = 0; kb < ti.nk; ++kb, ++it) {
+          const int s = it % S;
+          if (it >= S) g_mbar_wait(&s_empty[s], ((it / S) - 1) & 1);
+          const uint32_t st = g_smem_u32(smem + (size_t)s * kStageBytes);
+          const int k0 = ti.kbeg + kb * GK;
+          g_mbar_expect_tx(&s_full[s], 2 * kGTileBytes);
+          if (!P.a_mn) {
+            g_tma_2d(st, ma, &s_full[s], k0, ti.m0);
+          } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) g_tma_2d(st + b * 4096, ma, &s_full[s], ti.m0 + 32 * b, k0);
+          }
+          if (!P.b_mn) {
+            g_tma_2d(st + kGTileBytes, mb, &s_full[s], k0, ti.n0);
+          } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              g_tma_2d(st + kGTileBytes + b * 4096, mb, &s_full[s], ti.n0 + 32 * b, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    int it = 0, acc_it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileInfo ti = g_tile_info(prm, t);
+      if (ti.nk == 0) continue;
+      const GemmProb& P = prm.p[ti.pi];
+      const int buf = acc_it & 1;
+      if (acc_it >= 2) g_mbar_wait(&s_acce[buf], ((acc_it >> 1) - 1) & 1);   // the epilogue has drained this buffer
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem + (uint32_t)(buf * GN);
+      const uint32_t idesc = g_idesc(P.a_mn != 0, P.b_mn != 0);
+      const uint32_t a_step = P.a_mn ? 1024u : 32u, b_step = P.b_mn ? 1024u : 32u;
+      for (int kb = 0; kb < ti.nk; ++kb, ++it) {
+        const int s = it % S;
+        g_mbar_wait(&s_conv[s], (it / S) & 1);     // (the split warps arrive for every k-block in this kernel)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t a_hi = g_smem_u32(smem + (size_t)s * kStageBytes);
+          const uint32_t b_hi = a_hi + kGTileBytes, a_lo = a_hi + 2 * kGTileBytes,
+                         b_lo = a_hi + 3 * kGTileBytes;
+#pragma unroll
+          for (int kk = 0; kk < GK / 8; ++kk) {
+            const uint64_t dah = g_desc(a_hi + kk * a_step, P.a_mn != 0);
+            const uint64_t dbh = g_desc(b_hi + kk * b_step, P.b_mn != 0);
+            g_mma(acc, dah, dbh, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            if (split3) {
+              const uint64_t dal = g_desc(a_lo + kk * a_step, P.a_mn != 0);
+              const uint64_t dbl = g_desc(b_lo + kk * b_step, P.b_mn != 0);
+              g_mma(acc, dah, dbl, idesc, 1u);
+              g_mma(acc, dal, dbh, idesc, 1u);
+            }
+          }
+          g_commit(&s_empty[s]);
+          if (kb == ti.nk - 1) g_commit(&s_accf[buf]);
+        }
+        __syncwarp();
+      }
+      ++acc_it;
+    }
+  } else if (warp < kPEpiWarp0) {
+    // ===== split / mask pass: warps 2..9 =====
+    const int et = tid - 64;  // 0..255
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileInfo ti = g_tile_info(prm, t);
+      const GemmProb& P = prm.p[ti.pi];
+      for (int kb = 0; kb < ti.nk; ++kb, ++it) {
+        const int s = it % S;
+        g_mbar_wait(&s_full[s], (it / S) & 1);
+        const bool masked = ti.tail_mask && kb == ti.nk - 1;
+        if (split3 || masked) {
+          const uint32_t a_hi = g_smem_u32(smem + (size_t)s * kStageBytes);
+          const int klive = masked ? ti.kend - (ti.kbeg + kb * GK) : GK;
+          float4 va[4], vb[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t o = (uint32_t)(i * kGConv + et) * 16u;
+            va[i] = g_lds4(a_hi + o);
+            vb[i] = g_lds4(a_hi + kGTileBytes + o);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int idx = i * kGConv + et;
+            const uint32_t o = (uint32_t)idx * 16u;
+            float4 la, lb;
+            if (klive < GK) {
+              g_mask4(va[i], idx, P.a_mn != 0, klive);
+              g_mask4(vb[i], idx, P.b_mn != 0, klive);
+            }
+            if (split3) {
+              g_split4(va[i], la);
+              g_split4(vb[i], lb);
+              g_sts4(a_hi + 2 * kGTileBytes + o, la);
+              g_sts4(a_hi + 3 * kGTileBytes + o, lb);
+            }
+            if (klive < GK) {
+              g_sts4(a_hi + o, va[i]);
+              g_sts4(a_hi + kGTileBytes + o, vb[i]);
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) g_mbar_arrive(&s_conv[s]);
+      }
+    }
+  } else {
+    // ===== epilogue: warps 10..13, TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    int acc_it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileInfo ti = g_tile_info(prm, t);
+      if (!ti.live) continue;
+      const GemmProb& P = prm.p[ti.pi];
+      const int buf = acc_it & 1;
+      if (ti.nk > 0) {
+        g_mbar_wait(&s_accf[buf], (acc_it >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      const int row = ti.m0 + q * 32 + lane;
+      const bool row_ok = row < ti.M;
+      float* crow = P.c + (long long)row * P.ldc;
+      const bool vec_ok = (P.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.c) & 15) == 0);
+      const bool add_bias = P.bias != nullptr && ti.split == 0;
+#pragma unroll 1
+      for (int cc = 0; cc < GN; cc += 32) {
+        const int c0 = ti.n0 + cc;
+        if (c0 >= P.n) break;  // warp-uniform
+        uint32_t v[32];
+        if (ti.nk > 0) {
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GN + cc);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+              "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
+                "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                "=r"(v[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if (!row_ok) continue;
+        const bool full = c0 + 32 <= P.n;
+        if (full && vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (add_bias) {
+              const float4 b4 = *reinterpret_cast<const float4*>(P.bias + c0 + j);
+              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            }
+            float4* dst = reinterpret_cast<float4*>(crow + c0 + j);
+            if (P.mode == 2) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x),
+                           "f"(o.y), "f"(o.z), "f"(o.w)
+                           : "memory");
+            } else if (P.mode == 1) {
+              const float4 old = *dst;
+              *dst = make_float4(old.x + o.x, old.y + o.y, old.z + o.z, old.w + o.w);
+            } else {
+              *dst = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = c0 + j;
+            if (n < P.n) {
+              float x = __uint_as_float(v[j]);
+              if (add_bias) x += P.bias[n];
+              if (P.mode == 2) atomicAdd(crow + n, x);
+              else if (P.mode == 1) crow[n] += x;
+              else crow[n] = x;
+            }
+          }
+        }
+      }
+      if (ti.nk > 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) g_mbar_arrive(&s_acce[buf]);
+        ++acc_it;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * GN));
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Fused GRUCell forward (torch.nn.GRUCell as used at reference modules/memory_module.py:72,172):
 //   gi = x W_ih^T + b_ih,  gh = h W_hh^T + b_hh,  r = sig(gi_r + gh_r),  z = sig(gi_z + gh_z),
 //   n = tanh(gi_n + r * gh_n),  h' = n + z * (h - n)
@@ -788,6 +1088,16 @@ int32_t tgn_gemm_batch(const tgn_gemm_desc* d, int32_t count, int32_t precision,
     if (kk > max_nk) max_nk = kk;
   }
   if (tiles > kNumSMs && max_nk <= 4) prm.stages = precision == 3 ? 1 : 2;
+  static const int persist_min = getenv("TGN_GEMM_PERSIST") ? atoi(getenv("TGN_GEMM_PERSIST")) : 2 * kNumSMs;
+  if (tiles > persist_min) {
+    // several waves of tiles: one persistent CTA per SM, full-depth ring, accumulators double-buffered in TMEM
+    prm.stages = precision == 3 ? kGStages3 : kGStages1;
+    static unsigned long long attr_mask_p = 0;
+    TGN_CUDA(smem_optin(tgemm_persist_kernel, (int)smem_max, attr_mask_p));
+    launch_k(tgemm_persist_kernel, dim3(kNumSMs), dim3(kPThreads), smem_max, (cudaStream_t)stream, maps, prm, tiles);
+    TGN_LAUNCH_CHECK();
+    return TGN_OK;
+  }
   const size_t smem = (size_t)prm.stages * (precision == 3 ? kGStageBytes3 : kGStageBytes1) + 1024;
   launch_k(tgemm_kernel, dim3(tiles), dim3(kGThreads), smem, (cudaStream_t)stream, maps, prm);
   TGN_LAUNCH_CHECK();

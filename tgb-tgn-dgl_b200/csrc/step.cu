@@ -13,7 +13,6 @@
 //   tgn_scatter_add_rows  dst[rows[i],:] += src[i,:]
 //   tgn_time_bwd_sin      TimeEncoder gradient from stored sines
 #include "../../include/tgn_b200.h"
-#include <stdlib.h>
 #include "common.cuh"
 
 namespace tgn {
@@ -50,44 +49,14 @@ struct EdgeAttr2Args {
   int32_t* err;
 };
 
-__global__ void edge_attr_ld_elem_kernel(EdgeAttr2Args a) {
-  pdl_wait();
-  pdl_launch();
-  const int E = a.edges.get();
-  const long long total = (long long)E * a.ld;
-  for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total;
-       x += (long long)gridDim.x * blockDim.x) {
-    const int e = (int)(x / a.ld), d = (int)(x - (long long)e * a.ld);
-    const long long mr = a.msg_rows ? a.msg_rows[e] : e;
-    if (a.num_events > 0 && (mr < 0 || mr >= a.num_events)) {  // the ring names an event that is not resident
-      if (d == 0) flag_dev_err(a.err, TGN_DEVERR_EVENT_RANGE);
-      a.ea[x] = 0.f;
-      if (d < a.Dt && a.sn) a.sn[(long long)e * a.Dt + d] = 0.f;
-      if (d == 0 && a.rel) a.rel[e] = 0.f;
-      continue;
-    }
-    if (d < a.Dt) {
-      const float rt = (float)(a.lu[a.nbr[e]] - a.t_edge[mr]);
-      float sv, cv;
-      sincos_fr(__fmaf_rn(rt, a.time_w[d], a.time_b[d]), &sv, &cv);
-      a.ea[x] = cv;
-      if (a.sn) a.sn[(long long)e * a.Dt + d] = sv;
-      if (d == 0 && a.rel) a.rel[e] = rt;
-    } else if (d < a.Dt + a.De) {
-      a.ea[x] = a.msg[mr * a.De + (d - a.Dt)];
-    } else {
-      a.ea[x] = 0.f;
-    }
-  }
-}
-
 // One warp per edge, lanes over the columns of the row (coalesced 128-byte stores); the edge's scalars
 // (event row, its time stamp, the neighbour's last_update) are fetched once per edge for kEdgesPerWarp edges
 // at a time, all ahead of the first use.  Round 2: the first version mapped one thread to one OUTPUT ELEMENT
 // with a 64-bit division and four dependent scalar loads per element (130 us for the 181k edges of a flight
 // evaluation batch -- instruction-bound); kSin = false (evaluation) computes the cosine only.
-// kEdgesPerWarp = 1 on step-sized launches (a few thousand edges: every edge gets its own warp, latency matters),
-// 4 on large ones.
+// kEdgesPerWarp = 1 on step-sized launches (a few thousand edges: every edge gets its own warp, latency matters:
+// wiki B=200 step 147 us against 159 us with four edges per warp and 150 us with the per-element kernel), 4 on
+// large ones.
 template <bool kSin, int kEdgesPerWarp>
 __global__ void __launch_bounds__(256) edge_attr_ld_kernel(EdgeAttr2Args a) {
   pdl_wait();
@@ -1162,17 +1131,6 @@ int32_t tgn_edge_attr_ld(const int64_t* last_update_local, const int64_t* nbr_lo
   const bool small = num_edges <= kNumSMs * 8 * 8;      // one warp per edge still fits one wave
   const int grid = stride_grid((long long)ceil_div(num_edges, small ? 1 : 4) * 32, 256);
   cudaStream_t st = (cudaStream_t)stream;
-  static const int ev = getenv("TGN_EDGE_VAR") ? atoi(getenv("TGN_EDGE_VAR")) : 0;
-  if (ev == 1) {
-    launch_k(edge_attr_ld_elem_kernel, dim3(stride_grid((long long)num_edges * ld, 256)), dim3(256), 0, st, a);
-    return TGN_OK;
-  }
-  if (ev == 2) {
-    const int g4 = stride_grid((long long)ceil_div(num_edges, 4) * 32, 256);
-    if (sin_out) launch_k(edge_attr_ld_kernel<true, 4>, dim3(g4), dim3(256), 0, st, a);
-    else launch_k(edge_attr_ld_kernel<false, 4>, dim3(g4), dim3(256), 0, st, a);
-    return TGN_OK;
-  }
   if (sin_out && small) launch_k(edge_attr_ld_kernel<true, 1>, dim3(grid), dim3(256), 0, st, a);
   else if (sin_out) launch_k(edge_attr_ld_kernel<true, 4>, dim3(grid), dim3(256), 0, st, a);
   else if (small) launch_k(edge_attr_ld_kernel<false, 1>, dim3(grid), dim3(256), 0, st, a);

@@ -397,6 +397,9 @@ __global__ void __launch_bounds__(kCoreWarps * 32, kMinCtas) attn_core_fwd_small
     const int64_t row = a.centre_ids ? a.centre_ids[ci] : ci;
     const int e0 = a.row_ptr[ci];
     const int deg = min(a.row_ptr[ci + 1] - e0, kDeg);
+    // the centre's edge rows are contiguous (deg x HC floats, streamed from DRAM): request them now, one 128-byte
+    // line per lane, so they arrive while the neighbour ids and the k / v rows (L2-resident table) are fetched
+    if (lane * 32 < deg * HC) prefetch_l2(a.ee + (long long)e0 * HC + lane * 32);
     const float* pr = a.proj + row * 4 * HC;
     const float4 q = ok ? ld4(pr + c0) : z4;
     const float4 skip = ok ? ld4(pr + 3 * HC + c0) : z4;

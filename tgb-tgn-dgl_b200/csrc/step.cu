@@ -1012,15 +1012,29 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     const float p = s_pos;
     int gt = 0, ge = 0;
-    for (int q = qlo + wid; q < qhi; q += nw) {
-      const float* pb = hd + neg_rows[(long long)i * Q + q] * D;
-      float acc = 0.f;
-      for (int c = lane; c < D; c += 32) acc = fmaf(fmaxf(s_a[c] + pb[c], 0.f), s_a[D + c], acc);
-      acc = warp_sum(acc);
-      const float v = 1.f / (1.f + expf(-(acc + bf[0])));
-      gt += v > p;
-      ge += v >= p;
-      if (neg_out && lane == 0) neg_out[(long long)i * Q + q] = v;
+    // four negatives per warp iteration: their row indices, then their rows, are fetched together (one chain of
+    // two dependent latencies per FOUR candidates; per-candidate arithmetic and its order are unchanged)
+    constexpr int kU = 4;
+    for (int q0 = qlo + wid * kU; q0 < qhi; q0 += nw * kU) {
+      const float* pb[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        pb[u] = q0 + u < qhi ? hd + neg_rows[(long long)i * Q + q0 + u] * D : nullptr;
+      float acc[kU] = {};
+      for (int c = lane; c < D; c += 32) {
+        const float sa = s_a[c], sw = s_a[D + c];
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          if (pb[u]) acc[u] = fmaf(fmaxf(sa + pb[u][c], 0.f), sw, acc[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (!pb[u]) break;      // warp-uniform
+        const float v = 1.f / (1.f + expf(-(warp_sum(acc[u]) + bf[0])));
+        gt += v > p;
+        ge += v >= p;
+        if (neg_out && lane == 0) neg_out[(long long)i * Q + q0 + u] = v;
+      }
     }
     if (lane == 0) {
       atomicAdd(&s_gt, gt);

@@ -747,8 +747,15 @@ def bench_eval_dp(dev, rank, world, n_batches, precision, shard=True):
                         f"ring prefilled with {prefill} events",
             "embedding": ("sharded: every root embedded on one rank, decoder-projected rows all-gathered" if shard
                           else "replicated: every rank embeds every root"),
-            "collective": (("one all-gather of the projected rows [2, roots/P, 100] fp32 + " if shard else "") +
-                           "one all-reduce(sum) of 2*B int32 rank counts per batch") if world > 1 else "none"}
+            "collective": "none" if world == 1 else (
+                ("no NCCL call in the step: every rank writes its projected rows [2, roots/P, 100] fp32 and its 2*B int32 "
+                 "rank counts into every rank's symmetric-memory tables (peer stores over NVLink), two device-side rank "
+                 "barriers; the counts are summed locally in rank order"
+                 if shard and os.environ.get("TGN_EVAL_EXCHANGE", "peer") == "peer" else
+                 ("one all-gather of the projected rows [2, roots/P, 100] fp32 + " if shard else "") +
+                 "one all-reduce(sum) of 2*B int32 rank counts per batch")),
+            "nvlink_bytes_per_batch_per_rank": (None if world == 1 or not shard else
+                                                 (world - 1) * (8 * HIDDEN * ((N + world - 1) // world) + 8 * B))}
 
 
 def bench_tcsr_two_layer(dev, rank, world, steps=40, events=4_000_000):

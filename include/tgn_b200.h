@@ -625,6 +625,13 @@ int32_t tgn_part_select_owned(const int64_t* n_id, int32_t num, const int32_t* n
 int32_t tgn_part_publish(const float* rows, const int64_t* last_update, const int64_t* own_pos, int32_t num,
                          const int32_t* num_dev, int32_t dim, void* const* peer_rows, void* const* peer_last_update,
                          int32_t world, void* stream);
+/* Sharded evaluation (epoch_utils.py:74-113 data-parallel over model replicas): writes one block of `nbytes`
+ * bytes at `table_offset_bytes` of EVERY rank's table (peer_tables[r] = rank r's mapping of the symmetric
+ * allocation): the all-gather of the decoder-projected rows / of the per-rank TGB counts as peer stores over
+ * NVLink, no collective call.  Sizes, offset and src 16-byte aligned.  The caller separates it from the
+ * readers with a rank barrier. */
+int32_t tgn_peer_bcast(const void* src, int64_t nbytes, void* const* peer_tables, int64_t table_offset_bytes,
+                       int32_t world, void* stream);
 int32_t tgn_adam_finish_peers(float* params, const float* grads_replicated, const void* const* peer_grads_partial,
                               int32_t world, int64_t partial_count, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
                               float beta1, float beta2, float eps, float* step_dev, int64_t* step_counter,

@@ -222,6 +222,24 @@ __global__ void part_publish_kernel(const float* __restrict__ rows, const int64_
   }
 }
 
+// Writes one block of `n16` 16-byte words into the SAME place of every rank's table (peer stores over
+// NVLink / NVSwitch): the all-gather of the sharded evaluation (every rank's block lands at its own offset of
+// every peer's table) without a collective call.
+struct PeerDst {
+  int4* dst[kMaxPeers];
+};
+__global__ void peer_bcast_kernel(const int4* __restrict__ src, long long n16, int world, PeerDst peers) {
+  pdl_wait();
+  pdl_launch();
+  const long long total = n16 * world;
+  for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total;
+       x += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(x / n16);
+    const long long i = x - (long long)p * n16;
+    peers.dst[p][i] = src[i];
+  }
+}
+
 struct PeerGrads {
   const float* part[kMaxPeers];
 };
@@ -374,6 +392,25 @@ int32_t tgn_part_publish(const float* rows, const int64_t* last_update, const in
   }
   launch_k(part_publish_kernel, dim3(stride_grid((long long)num * (dim / 4) * world, 256)), dim3(256), 0,
            (cudaStream_t)stream, rows, last_update, own_pos, DevCount{num_dev, num}, dim, world, t);
+  TGN_LAUNCH_CHECK();
+  return TGN_OK;
+}
+
+int32_t tgn_peer_bcast(const void* src, int64_t nbytes, void* const* peer_tables, int64_t table_offset_bytes,
+                       int32_t world, void* stream) {
+  TGN_REQUIRE(nbytes >= 0 && table_offset_bytes >= 0 && world >= 1 && world <= kMaxPeers,
+              "peer_bcast: bad sizes (world <= %d)", kMaxPeers);
+  if (nbytes == 0) return TGN_OK;
+  TGN_REQUIRE(src && peer_tables, "peer_bcast: NULL pointer");
+  TGN_REQUIRE(nbytes % 16 == 0 && table_offset_bytes % 16 == 0 && ((uintptr_t)src & 15) == 0,
+              "peer_bcast: block size, table offset and source must be multiples of 16 bytes");
+  PeerDst d;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    d.dst[r] = r < world ? reinterpret_cast<int4*>((char*)peer_tables[r] + table_offset_bytes) : nullptr;
+    TGN_REQUIRE(r >= world || (peer_tables[r] && ((uintptr_t)d.dst[r] & 15) == 0), "peer_bcast: peer %d has no (aligned) mapping", r);
+  }
+  launch_k(peer_bcast_kernel, dim3(stride_grid(nbytes / 16 * world, 256)), dim3(256), 0, (cudaStream_t)stream,
+           (const int4*)src, (long long)(nbytes / 16), world, d);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

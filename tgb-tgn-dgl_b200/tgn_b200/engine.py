@@ -1379,7 +1379,7 @@ class TGNEngine:
         return c.pos, (c.negs[:, :Q] if want_neg_scores else None), c.gt, c.ge
 
     # ---- data-parallel evaluation with the EMBEDDING sharded as well (epoch_utils.py:74-113)
-    def _eval_ctx_dp(self, B: int, Q: int, rank: int, P: int) -> SimpleNamespace:
+    def _eval_ctx_dp(self, B: int, Q: int, rank: int, P: int, group=None) -> SimpleNamespace:
         ctxs = self.__dict__.setdefault("_ectx", {})
         c = ctxs.get(("dp", B, Q, rank, P))
         if c is not None:
@@ -1418,7 +1418,26 @@ class TGNEngine:
             c.w.Nb_dev.fill_(N)
         c.e_r = torch.zeros((c.Rm, D), device=dev)
         c.send = torch.zeros((2, c.Rm, D), device=dev)               # [lin_src(emb) | lin_dst(emb)] of my centres
-        c.recv = torch.zeros((P, 2, c.Rm, D), device=dev) if P > 1 else c.send.view(1, 2, c.Rm, D)
+        # Exchange between the ranks.  "peer" (default): the gathered table and the table of per-rank counts are
+        # torch symmetric memory; every rank WRITES its block into every rank's table (tgn_peer_bcast: 128-bit
+        # stores over NVLink / NVSwitch) and a device-side rank barrier separates writers from readers -- no
+        # collective call in the captured step.  "nccl": all_gather_into_tensor + all_reduce (round-2 first design).
+        c.peer = P > 1 and os.environ.get("TGN_EVAL_EXCHANGE", "peer") == "peer" and (c.Rm * D) % 2 == 0 and B % 2 == 0
+        if c.peer:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            c.recv = symm_mem.empty((P, 2, c.Rm, D), dtype=torch.float32, device=dev)
+            c.cnt_table = symm_mem.empty((P, 2, B), dtype=torch.int32, device=dev)
+            c.recv.zero_()
+            c.cnt_table.zero_()
+            c.h_recv, c.h_cnt = symm_mem.rendezvous(c.recv, grp), symm_mem.rendezvous(c.cnt_table, grp)
+            c.peer_recv = (ctypes.c_void_p * P)(*[int(q) for q in c.h_recv.buffer_ptrs])
+            c.peer_cnt = (ctypes.c_void_p * P)(*[int(q) for q in c.h_cnt.buffer_ptrs])
+            torch.cuda.synchronize()
+            c.h_recv.barrier(channel=0)
+        else:
+            c.recv = torch.zeros((P, 2, c.Rm, D), device=dev) if P > 1 else c.send.view(1, 2, c.Rm, D)
         c.Qr = len(range(rank, Q, P))
         c.src_rows, c.dst_rows, c.neg_rows = i64(B), i64(B), i64(B, max(c.Qr, 1))
         ctxs[("dp", B, Q, rank, P)] = c
@@ -1474,7 +1493,11 @@ class TGNEngine:
             ops.gemm_desc(c.e_r, self.flat, c.send, m=c.Rm, n=D, k=D, lda=D, ldb=D, ldc=D, b_off=off["lin_dst.weight"],
                           bias=p["lin_dst.bias"], m_dev=c.Rm_dev, c_off=c.Rm * D),
         ], self.prec)
-        if P > 1:
+        if c.peer:
+            # the previous batch's end-of-step barrier guarantees every rank has finished reading its table
+            check(L.tgn_peer_bcast(_p(c.send), 4 * c.send.numel(), c.peer_recv, 4 * c.send.numel() * rank, P, _stream()))
+            c.h_recv.barrier(channel=0)
+        elif P > 1:
             import torch.distributed as dist
             dist.all_gather_into_tensor(c.recv, c.send, group=group)
         # row of global root g in the gathered table: block of its rank (g % P), position g // P -- one kernel for
@@ -1485,12 +1508,20 @@ class TGNEngine:
                                _p(c.neg_rows), B, c.Qr, D, _p(p["lin_final.weight"]), _p(p["lin_final.bias"]),
                                _p(c.pos), None, _p(c.gt), _p(c.ge), _stream()))
         if c.reduce:
-            # the TGB rank needs the counts over ALL columns: one all-reduce of 2*B int32 inside the graph, then
-            # the batch's mean reciprocal rank is added to the epoch accumulator on the device (epoch_utils.py:113,163)
-            if P > 1:
+            # the TGB rank needs the counts over ALL columns: the per-rank counts are exchanged (peer writes into
+            # every rank's [P, 2, B] table + barrier + a local sum in rank order: integers, so every rank gets the
+            # same totals; or one all-reduce of 2*B int32), then the batch's mean reciprocal rank is added to the
+            # epoch accumulator on the device (epoch_utils.py:113,163)
+            if c.peer:
+                check(L.tgn_peer_bcast(_p(c.cnt), 4 * c.cnt.numel(), c.peer_cnt, 4 * c.cnt.numel() * rank, P, _stream()))
+                c.h_recv.barrier(channel=1)
+                torch.sum(c.cnt_table, dim=0, dtype=torch.int32, out=c.cnt)
+            elif P > 1:
                 import torch.distributed as dist
                 dist.all_reduce(c.cnt, group=group)
             check(L.tgn_rank_accum(_p(c.gt), _p(c.ge), B, _p(self.mrr_acc), _p(c.rr), _stream()))
+        elif c.peer:
+            c.h_recv.barrier(channel=1)      # nobody overwrites a table that a slower rank is still scoring from
         main.wait_stream(upd)
 
     @torch.no_grad()
@@ -1510,7 +1541,7 @@ class TGNEngine:
             raise _cabi.TgnError("eval_batch_dp runs on model replicas (world == 1 engines), one per rank")
         self._unprime()
         B, Q = neg.shape
-        c = self._eval_ctx_dp(B, Q, rank, world)
+        c = self._eval_ctx_dp(B, Q, rank, world, group)
         c.reduce = reduce
         if not hasattr(self, "mrr_acc"):
             self.mrr_acc = torch.zeros(2, dtype=torch.float64, device=self.dev)

@@ -31,7 +31,8 @@ def test_library_loads_and_reports_version():
     lib = _cabi.lib()
     assert lib.tgn_abi_version() == 1
     assert lib.tgn_bitmap_bytes(9227) == (10 * 32 + 1) * 4   # 10 groups of 1024 nodes + 1 summary word
-    assert lib.tgn_nbr_lookup_ws_bytes(600, 10) == (3 + 1) * 8
+    # ticket word + one word per 2048-slot tile (3) + one word per group of 8 tiles (count pass of large launches)
+    assert lib.tgn_nbr_lookup_ws_bytes(600, 10) == (1 + 3 + 1) * 8
 
 
 def test_argument_validation_needs_no_gpu():

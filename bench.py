@@ -267,8 +267,11 @@ def gpu_leg(name, B, K_steps, W, prefill, dev, rank, world, precision, clocks=No
     Returns (result dict, engine)."""
     import torch.distributed as dist
     from tgn_b200.engine import TGNEngine
-    G0 = 3
-    warm_dev = max(W, 52) + 4 * 9
+    # batches per captured graph / host group (TGNEngine group_size): three, unless another small group size
+    # divides K_steps and three does not (the driver's --steps 20 -> groups of four: no leftover single steps)
+    G0 = next((g for g in (3, 4, 5, 2) if K_steps % g == 0), 3)
+    warm_steps = max(W, 13 * G0 + 1)        # eager calls + the capture of the multi-step graph of every slot group
+    warm_dev = warm_steps + 4 * 3 * G0
     # warm-up groups of the e2e arm: 3 eager calls + the capture per slot group; with a K % 3 leftover the slot
     # group the leftover lands on is additionally stepped through singly (4 more passes)
     Wg = max(14, (W + G0 - 1) // G0 + 2) + (13 if K_steps % G0 else 0)
@@ -276,7 +279,8 @@ def gpu_leg(name, B, K_steps, W, prefill, dev, rank, world, precision, clocks=No
     data = load_workload(name, B, prefill, n_batches, seed=rank)
     N, De, K = data["num_nodes"], data["raw_dim"], data["K"]
     eng = TGNEngine(N, De, HIDDEN, K, B, device=dev, lr=LR, dropout=0.1, use_graph=True,
-                    log_capacity=data["src"].size, seed=1234 + rank, precision=precision, fused_zero_grad=True)
+                    log_capacity=data["src"].size, seed=1234 + rank, precision=precision, fused_zero_grad=True,
+                    group_size=G0)
     eng.load_state(*init_state_dicts(De, HIDDEN, N, seed=1))
     ev = {k: torch.from_numpy(data[k]) for k in ("src", "dst", "t", "msg", "neg")}
     eng.set_events(**ev)
@@ -289,7 +293,7 @@ def gpu_leg(name, B, K_steps, W, prefill, dev, rank, world, precision, clocks=No
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm
-    eng.train_steps(max(W, 52))   # warm-up: eager calls and the captures of the three-step graphs of all slot groups
+    eng.train_steps(warm_steps)   # warm-up: eager calls and the captures of the multi-step graphs of all slot groups
     for _ in range(4 * eng.nslots):                   # ... and of the single-step graph of every slot (the K % 3 leftover)
         eng.train_step(from_device=True)
     barrier()
@@ -319,13 +323,20 @@ def gpu_leg(name, B, K_steps, W, prefill, dev, rank, world, precision, clocks=No
     host = torch.zeros((ring_bufs, eng.group_nbytes()), dtype=torch.uint8).pin_memory()   # when its buffer comes round)
     n_ev = ev["src"].numel()
 
+    views = [eng.group_views(host[r]) for r in range(ring_bufs)]     # numpy views of the pinned buffers
+    src_h, dst_h, neg_h, t_h, msg_h = (data[k] for k in ("src", "dst", "neg", "t", "msg"))
+
     def pack(g):
-        batches = []
-        for i in range(G):
+        """the host loader: the group's batches go from the host event arrays into the pinned staging buffer"""
+        for i, (vs, vd, vn, vt, vm) in enumerate(views[g % ring_bufs]):
             lo = min(pos + (g * G + i) * B, n_ev - B)
-            sl = slice(lo, lo + B)
-            batches.append((ev["src"][sl], ev["dst"][sl], ev["neg"][sl], ev["t"][sl], ev["msg"][sl]))
-        return eng.pack_host_group(host[g % ring_bufs], batches)
+            vs[:] = src_h[lo:lo + B]
+            vd[:] = dst_h[lo:lo + B]
+            vn[:] = neg_h[lo:lo + B]
+            vt[:] = t_h[lo:lo + B]
+            if De:
+                vm[:] = msg_h[lo:lo + B]
+        return host[g % ring_bufs]
 
     eng.stage_group(pack(0), ahead=False)
     # the K_steps % 3 leftover steps of the timed region run one by one on the slots that follow the last whole
@@ -364,7 +375,7 @@ def gpu_leg(name, B, K_steps, W, prefill, dev, rank, world, precision, clocks=No
            "value": world * K_steps * B / (ms / 1e3), "unit": "events/s", "ms_per_step": ms / K_steps,
            "e2e": {"value": world * K_steps * B / (ms_e2e / 1e3), "unit": "events/s",
                    "h2d_bytes_per_step": eng.group_nbytes() // eng.group_size, "d2h_bytes_per_step": 4,
-                   "grouping": "3 batches per host pack / H2D copy / graph launch / loss read-back; the pack "
+                   "grouping": f"{G} batches per host pack / H2D copy / graph launch / loss read-back; the pack "
                                "(host event arrays -> pinned buffer) is inside the timed region; negatives are "
                                "part of the host event stream (drawn once per epoch)",
                    "ms_per_step": ms_e2e / K_steps},

@@ -1190,6 +1190,22 @@ class TGNEngine:
             self.pack_host_batch(out[i * self._packed: i * self._packed + self.packed_nbytes()], *b)
         return out
 
+    def group_views(self, buf: Tensor):
+        """numpy views of a pinned group buffer (uint8 [group_nbytes()]), one tuple (src, dst, neg, t, msg) per batch
+        slot: a host loader fills a group with plain array assignments -- ~20 us per group of four batches instead
+        of ~150 us of small tensor ops through pack_host_group (same layout)."""
+        if buf.numel() != self.group_nbytes() or buf.dtype != torch.uint8 or not buf.is_contiguous() or buf.is_cuda:
+            raise _cabi.TgnError("group_views: buf must be a contiguous host uint8 tensor of group_nbytes() bytes")
+        import numpy as np
+        B, De, raw = self.B, self.De, buf.numpy()
+        views = []
+        for i in range(self.group_size):
+            o = raw[i * self._packed: i * self._packed + self.packed_nbytes()]
+            ids = o[:32 * B].view(np.int64)
+            msg = o[32 * B:].view(np.float32).reshape(B, max(De, 1))
+            views.append((ids[:B], ids[B:2 * B], ids[2 * B:3 * B], ids[3 * B:], msg))
+        return views
+
     def stage_group(self, buf: Tensor, ahead: bool = True):
         """Stages the NEXT group (ahead=True: the three batches after the group train_group_logged() is about
         to train; the copy runs on the copy stream while the previous group is still executing) or the

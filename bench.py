@@ -383,7 +383,7 @@ def gpu_leg(name, B, K_steps, W, prefill, dev, rank, world, precision, clocks=No
     return res, eng
 
 
-def bench_module_path(dev, n_events=20_000, B=200):
+def bench_module_path(dev, n_events=60_000, B=200):
     """What the UNCHANGED driver script gets: events/s of `epoch_utils.train` (the call at pyg-mem-tgn.py:57) on
     the drop-in modules.  Two numbers on the same data:
       script_path : train() as the script calls it -- it recognises the standard model (model_utils.getModel,

@@ -126,12 +126,27 @@ def _train_engine(model, train_loader, neighbor_loader, neg_dest_sampler, device
     neg = torch.cat([neg_dest_sampler.sample(ds.dst[lo:lo + B]) for lo in range(0, n_all, B)])
     # the loader hands out float32 timestamps (temporal_dataset.py:42) and update_state gets t.long()
     eng.set_events(ds.src, ds.dst, ds.t.float().long(), ds.msg, neg)
-    total = 0.0
-    for _ in range(n // B):                       # every step's loss is logged, read back one step late
-        prev = eng.train_step_logged()
-        if prev is not None:
-            total += prev * B
-    total += eng.flush_loss() * B
+    # Every step's loss enters the epoch total (epoch_utils.py:305), summed ON THE DEVICE in float64: the steps run as
+    # captured graphs of `group_size` batches (no per-step host round trip), the group's per-slot loss words are
+    # added to the accumulator behind each replay, and the host reads the total once per epoch.
+    steps, G = n // B, eng.group_size
+    acc = torch.zeros((), dtype=torch.float64, device=mem.memory.device)
+    idx_cache = eng.__dict__.setdefault("_loss_idx", {})
+    done = 0
+    if steps:
+        acc += eng.train_step(from_device=True)           # primes the sampling pipeline
+        done = 1
+    while eng.use_graph and steps - done >= G:
+        c0 = eng.cur
+        if c0 not in idx_cache:
+            idx_cache[c0] = torch.tensor([(c0 + k) % eng.nslots for k in range(G)], device=mem.memory.device)
+        eng.train_steps(G)
+        acc += eng.loss_slots.index_select(0, idx_cache[c0]).sum()
+        done += G
+    while done < steps:
+        acc += eng.train_step(from_device=True, _capture=False)
+        done += 1
+    total = float(acc) * B
     if tail_eng is not None:
         eng.handover()
         total += float(tail_eng.train_step(from_device=True)) * tail

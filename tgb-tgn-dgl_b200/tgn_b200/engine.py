@@ -490,6 +490,7 @@ class TGNEngine:
         self.pos_dev.zero_()
         self.events_done, self.ring_pos = int(m.store.size), int(nl.cur_e_id)
         self._primed = None
+        self.cur = 0        # every epoch walks the slots from the same start: the captured graphs are keyed by slot
 
     def end_epoch_on_modules(self):
         m, nl = self._attached

@@ -534,6 +534,20 @@ int32_t tgn_dec_fused(const float* emb, const int64_t* ids_local, int32_t batch,
                       const float* w_final, const float* b_final, float* loss, float* logits,
                       float* d_emb, float* d_w_src, float* d_b_src, float* d_w_dst, float* d_b_dst,
                       float* d_w_final, float* d_b_final, float* z_rows, float* g_rows, void* stream);
+/* tgn_attn_core_fwd + tgn_dec_fused as ONE launch (emb_module.py:25-29 feeding decoder.py:24-27 at
+ * pyg_epoch_utils.py:118-119): the decoder's input rows are not gathered from an embedding table, they are
+ * computed in the kernel -- ids_root[3*batch] = index of every batch id (src | dst | neg) in the root list
+ * (row_ptr / centre_ids are indexed by it), ids_local[3*batch] = its row in d_emb.  Two heads, <= 10 edges per
+ * centre, heads * head_dim <= 128.  alpha [E, heads] gets the softmax weights for tgn_attn_core_bwd; the two
+ * [D,D] weight gradients are deferred (z_rows / g_rows as in tgn_dec_fused). */
+int32_t tgn_dec_attn_fused(const float* proj, const int64_t* nbr_local, const int32_t* row_ptr,
+                           const int64_t* centre_ids, int32_t num_centres, int32_t heads, int32_t head_dim,
+                           const float* ee, float dropout_p, uint64_t seed, const int64_t* seed_dev,
+                           int32_t max_degree, float* alpha, const int64_t* ids_root, const int64_t* ids_local,
+                           int32_t batch, const float* w_src, const float* b_src, const float* w_dst,
+                           const float* b_dst, const float* w_final, const float* b_final, float* loss,
+                           float* logits, float* d_emb, float* d_b_src, float* d_b_dst, float* d_w_final,
+                           float* d_b_final, float* z_rows, float* g_rows, void* stream);
 /* TGB evaluation scoring (epoch_utils.py:99-113, decoder.py:24-27): for positive i the score of
  * (src_rows[i], dst_rows[i]) and of its num_neg negatives (src_rows[i], neg_rows[i,q]) as sigmoid
  * outputs; gt_out[i] = #{neg > pos}, ge_out[i] = #{neg >= pos} (the two counts of the TGB MRR

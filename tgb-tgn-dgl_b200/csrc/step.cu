@@ -376,7 +376,82 @@ struct SmallMask {
   }
 };
 
-// kDeg = register-resident edge slots per centre (10 for the TGN default of 10 neighbours: 131 registers, four
+// One centre of the low-degree path, by one warp: returns the lane's four output channels (aggregation + skip)
+// and leaves the softmax weights in a.alpha.  Shared by the stand-alone kernel and the decoder-fused one.
+template <int H, int kDeg>
+__device__ __forceinline__ float4 attn_small_fwd_row(const AttnCoreArgs& a, int ci, int lane, const HeadMask<H>& hm,
+                                                     const Philox& rng, float inv_sqrt_c, float keep, bool ok, int c0,
+                                                     int64_t* row_out) {
+  const int HC = a.H * a.C;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t row = a.centre_ids ? a.centre_ids[ci] : ci;
+  *row_out = row;
+  const int e0 = a.row_ptr[ci];
+  const int deg = min(a.row_ptr[ci + 1] - e0, kDeg);
+  // the centre's edge rows are contiguous (deg x HC floats, streamed from DRAM): request them now, one 128-byte
+  // line per lane, so they arrive while the neighbour ids and the k / v rows (L2-resident table) are fetched
+  if (lane * 32 < deg * HC) prefetch_l2(a.ee + (long long)e0 * HC + lane * 32);
+  const float* pr = a.proj + row * 4 * HC;
+  const float4 q = ok ? ld4(pr + c0) : z4;
+  const float4 skip = ok ? ld4(pr + 3 * HC + c0) : z4;
+  const int64_t my_j = lane < deg ? a.nbr[e0 + lane] : 0;
+  float4 kk[kDeg], vv[kDeg];
+#pragma unroll
+  for (int g = 0; g < kDeg; ++g) {
+    const int64_t j = __shfl_sync(0xffffffffu, my_j, g);
+    const bool on = ok && g < deg;
+    const float4 eev = on ? ld4(a.ee + (long long)(e0 + g) * HC + c0) : z4;
+    kk[g] = on ? f4_add(ld4(a.proj + j * 4 * HC + HC + c0), eev) : z4;
+    vv[g] = on ? f4_add(ld4(a.proj + j * 4 * HC + 2 * HC + c0), eev) : z4;
+  }
+  float sc[kDeg][H], mx[H], den[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) mx[h] = -INFINITY;
+#pragma unroll
+  for (int g = 0; g < kDeg; ++g) {
+    float part[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) part[h] = 0.f;
+    hm.dot(q, kk[g], part);
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      sc[g][h] = warp_sum(part[h]) * inv_sqrt_c;
+      if (g < deg) mx[h] = fmaxf(mx[h], sc[g][h]);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < H; ++h) den[h] = 0.f;
+#pragma unroll
+  for (int g = 0; g < kDeg; ++g)
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      sc[g][h] = g < deg ? expf(sc[g][h] - mx[h]) : 0.f;
+      den[h] += sc[g][h];
+    }
+  float4 acc = z4;
+  SmallMask<H, kDeg> sm;
+  if (a.dropout_p > 0.f) sm.draw(rng, e0, deg, lane);
+#pragma unroll
+  for (int g = 0; g < kDeg; ++g) {
+    if (g >= deg) break;  // warp-uniform
+    float pw[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float p = sc[g][h] / den[h];
+      if (lane == 0) a.alpha[(long long)(e0 + g) * H + h] = p;
+      if (a.dropout_p > 0.f) p = sm.get(g, h) < keep ? p / keep : 0.f;
+      pw[h] = p;
+    }
+    const float4 w4 = hm.pick(pw);
+    acc.x = fmaf(w4.x, vv[g].x, acc.x);
+    acc.y = fmaf(w4.y, vv[g].y, acc.y);
+    acc.z = fmaf(w4.z, vv[g].z, acc.z);
+    acc.w = fmaf(w4.w, vv[g].w, acc.w);
+  }
+  return f4_add(acc, skip);
+}
+
+// kDeg = register-resident edge slots per centre (10 for the TGN default of 10 neighbours: 125 registers, four
 // CTAs per SM on evaluation-sized launches; 12 otherwise)
 template <int H, int kDeg, int kMinCtas>
 __global__ void __launch_bounds__(kCoreWarps * 32, kMinCtas) attn_core_fwd_small_kernel(AttnCoreArgs a) {
@@ -392,72 +467,10 @@ __global__ void __launch_bounds__(kCoreWarps * 32, kMinCtas) attn_core_fwd_small
   HeadMask<H> hm;
   hm.init(c0, C, ok);
   Philox rng(a.seed + (a.seed_dev ? (uint64_t)*a.seed_dev : 0ull));
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int ci = blockIdx.x * kCoreWarps + wid; ci < nC; ci += gridDim.x * kCoreWarps) {
-    const int64_t row = a.centre_ids ? a.centre_ids[ci] : ci;
-    const int e0 = a.row_ptr[ci];
-    const int deg = min(a.row_ptr[ci + 1] - e0, kDeg);
-    // the centre's edge rows are contiguous (deg x HC floats, streamed from DRAM): request them now, one 128-byte
-    // line per lane, so they arrive while the neighbour ids and the k / v rows (L2-resident table) are fetched
-    if (lane * 32 < deg * HC) prefetch_l2(a.ee + (long long)e0 * HC + lane * 32);
-    const float* pr = a.proj + row * 4 * HC;
-    const float4 q = ok ? ld4(pr + c0) : z4;
-    const float4 skip = ok ? ld4(pr + 3 * HC + c0) : z4;
-    const int64_t my_j = lane < deg ? a.nbr[e0 + lane] : 0;
-    float4 kk[kDeg], vv[kDeg];
-#pragma unroll
-    for (int g = 0; g < kDeg; ++g) {
-      const int64_t j = __shfl_sync(0xffffffffu, my_j, g);
-      const bool on = ok && g < deg;
-      const float4 eev = on ? ld4(a.ee + (long long)(e0 + g) * HC + c0) : z4;
-      kk[g] = on ? f4_add(ld4(a.proj + j * 4 * HC + HC + c0), eev) : z4;
-      vv[g] = on ? f4_add(ld4(a.proj + j * 4 * HC + 2 * HC + c0), eev) : z4;
-    }
-    float sc[kDeg][H], mx[H], den[H];
-#pragma unroll
-    for (int h = 0; h < H; ++h) mx[h] = -INFINITY;
-#pragma unroll
-    for (int g = 0; g < kDeg; ++g) {
-      float part[H];
-#pragma unroll
-      for (int h = 0; h < H; ++h) part[h] = 0.f;
-      hm.dot(q, kk[g], part);
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        sc[g][h] = warp_sum(part[h]) * inv_sqrt_c;
-        if (g < deg) mx[h] = fmaxf(mx[h], sc[g][h]);
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < H; ++h) den[h] = 0.f;
-#pragma unroll
-    for (int g = 0; g < kDeg; ++g)
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        sc[g][h] = g < deg ? expf(sc[g][h] - mx[h]) : 0.f;
-        den[h] += sc[g][h];
-      }
-    float4 acc = z4;
-    SmallMask<H, kDeg> sm;
-    if (a.dropout_p > 0.f) sm.draw(rng, e0, deg, lane);
-#pragma unroll
-    for (int g = 0; g < kDeg; ++g) {
-      if (g >= deg) break;  // warp-uniform
-      float pw[H];
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        float p = sc[g][h] / den[h];
-        if (lane == 0) a.alpha[(long long)(e0 + g) * H + h] = p;
-        if (a.dropout_p > 0.f) p = sm.get(g, h) < keep ? p / keep : 0.f;
-        pw[h] = p;
-      }
-      const float4 w4 = hm.pick(pw);
-      acc.x = fmaf(w4.x, vv[g].x, acc.x);
-      acc.y = fmaf(w4.y, vv[g].y, acc.y);
-      acc.z = fmaf(w4.z, vv[g].z, acc.z);
-      acc.w = fmaf(w4.w, vv[g].w, acc.w);
-    }
-    if (ok) *reinterpret_cast<float4*>(a.out + row * HC + c0) = f4_add(acc, skip);
+    int64_t row;
+    const float4 o = attn_small_fwd_row<H, kDeg>(a, ci, lane, hm, rng, inv_sqrt_c, keep, ok, c0, &row);
+    if (ok) *reinterpret_cast<float4*>(a.out + row * HC + c0) = o;
   }
 }
 
@@ -758,7 +771,12 @@ constexpr int kDecVec = 3 * kDecEv;  // [row s|d|n][event] values per channel in
 //   GEMV phases     channel c, reduction quarter q, ALL kDecEv events at once: one weight load feeds
 //                   kDecEv (x3 rows) FMAs, the events' inputs come as three broadcast float4 loads;
 //   pointwise phases channel c of event slot q (bias, relu, final layer, loss gradient).
-template <bool kDefer>
+// kAttn: the kernel does not gather its inputs from an embedding table -- warp v of a pass COMPUTES the attention
+// output row of occurrence v (attn_small_fwd_row: H = 2, <= 10 edges per centre; ids_r = index of every batch id in
+// the root list) straight into the staged tile, so the attention forward is not a launch (and a link of the
+// step's dependent chain) of its own.  A node that occurs in several events is computed once per occurrence
+// (identical bits; its softmax weights are written more than once with the same values).
+template <bool kDefer, bool kAttn>
 __global__ void __launch_bounds__(kDecThreads)
     dec_fused_kernel(const float* __restrict__ emb, const int64_t* __restrict__ ids_l, int B, int D,
                      const float* __restrict__ Ws, const float* __restrict__ bs,
@@ -767,7 +785,8 @@ __global__ void __launch_bounds__(kDecThreads)
                      float* __restrict__ loss, float* __restrict__ logits, float* __restrict__ d_emb,
                      float* __restrict__ dWs, float* __restrict__ dbs, float* __restrict__ dWd,
                      float* __restrict__ dbd, float* __restrict__ dwf, float* __restrict__ dbf,
-                     float* __restrict__ z_rows, float* __restrict__ g_rows) {
+                     float* __restrict__ z_rows, float* __restrict__ g_rows, AttnCoreArgs at,
+                     const int64_t* __restrict__ ids_r) {
   extern __shared__ __align__(16) float sm[];
   const int ld = D + 1;
   float* sz = sm;                        // [D][kDecVec] inputs      (16-byte aligned rows)
@@ -809,13 +828,39 @@ __global__ void __launch_bounds__(kDecThreads)
       s_row[slot][row] = e0 + slot < B ? ids_l[row * B + e0 + slot] : -1;
     }
     __syncthreads();
-    for (int i = tid; i < kDecVec * D; i += kDecThreads) {
-      const int v = i / D, k = i - v * D;           // v = row * kDecEv + slot
-      const int row = v / kDecEv, slot = v - row * kDecEv;
-      const int64_t r = s_row[slot][row];
-      const float x = r >= 0 ? emb[r * D + k] : 0.f;
-      sz[k * kDecVec + v] = x;
-      if (kDefer && r >= 0) z_rows[((long long)row * B + e0 + slot) * D + k] = x;
+    if (kAttn) {
+      const int v = tid >> 5;                        // warp v: occurrence v = row * kDecEv + slot of the pass
+      if (v < kDecVec) {
+        const int row = v / kDecEv, slot = v - row * kDecEv;
+        const bool live = e0 + slot < B;
+        const int c0 = 4 * lane;
+        const bool ok = c0 < D;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+          HeadMask<2> hm;
+          hm.init(c0, at.C, ok);
+          Philox rng(at.seed + (at.seed_dev ? (uint64_t)*at.seed_dev : 0ull));
+          int64_t rr;
+          o = attn_small_fwd_row<2, 10>(at, (int)ids_r[row * B + e0 + slot], lane, hm, rng, rsqrtf((float)at.C),
+                                        1.f - at.dropout_p, ok, c0, &rr);
+        }
+        if (ok) {
+          sz[(c0 + 0) * kDecVec + v] = o.x;
+          sz[(c0 + 1) * kDecVec + v] = o.y;
+          sz[(c0 + 2) * kDecVec + v] = o.z;
+          sz[(c0 + 3) * kDecVec + v] = o.w;
+          if (kDefer && live) *reinterpret_cast<float4*>(z_rows + ((long long)row * B + e0 + slot) * D + c0) = o;
+        }
+      }
+    } else {
+      for (int i = tid; i < kDecVec * D; i += kDecThreads) {
+        const int v = i / D, k = i - v * D;           // v = row * kDecEv + slot
+        const int row = v / kDecEv, slot = v - row * kDecEv;
+        const int64_t r = s_row[slot][row];
+        const float x = r >= 0 ? emb[r * D + k] : 0.f;
+        sz[k * kDecVec + v] = x;
+        if (kDefer && r >= 0) z_rows[((long long)row * B + e0 + slot) * D + k] = x;
+      }
     }
     __syncthreads();
     // ---- forward partials: output channel c, inputs [k0, k1), all events of the pass
@@ -1286,42 +1331,93 @@ int64_t tgn_dec_fused_smem_bytes(int32_t dim) {
   return ((int64_t)4 * dim * (dim + 1) + 2 * kDecVec * dim) * (int64_t)sizeof(float);
 }
 
+static int32_t dec_fused_launch(const float* emb, const int64_t* ids_local, int32_t batch, int32_t dim,
+                                const float* w_src, const float* b_src, const float* w_dst, const float* b_dst,
+                                const float* w_final, const float* b_final, float* loss, float* logits,
+                                float* d_emb, float* d_w_src, float* d_b_src, float* d_w_dst, float* d_b_dst,
+                                float* d_w_final, float* d_b_final, float* z_rows, float* g_rows,
+                                const AttnCoreArgs* attn, const int64_t* ids_root, void* stream);
+
 int32_t tgn_dec_fused(const float* emb, const int64_t* ids_local, int32_t batch, int32_t dim,
                       const float* w_src, const float* b_src, const float* w_dst, const float* b_dst,
                       const float* w_final, const float* b_final, float* loss, float* logits,
                       float* d_emb, float* d_w_src, float* d_b_src, float* d_w_dst, float* d_b_dst,
                       float* d_w_final, float* d_b_final, float* z_rows, float* g_rows, void* stream) {
+  TGN_REQUIRE(emb, "dec_fused: NULL pointer");
+  return dec_fused_launch(emb, ids_local, batch, dim, w_src, b_src, w_dst, b_dst, w_final, b_final, loss, logits, d_emb,
+                          d_w_src, d_b_src, d_w_dst, d_b_dst, d_w_final, d_b_final, z_rows, g_rows, nullptr, nullptr,
+                          stream);
+}
+
+int32_t tgn_dec_attn_fused(const float* proj, const int64_t* nbr_local, const int32_t* row_ptr,
+                           const int64_t* centre_ids, int32_t num_centres, int32_t heads, int32_t head_dim,
+                           const float* ee, float dropout_p, uint64_t seed, const int64_t* seed_dev,
+                           int32_t max_degree, float* alpha, const int64_t* ids_root, const int64_t* ids_local,
+                           int32_t batch, const float* w_src, const float* b_src, const float* w_dst,
+                           const float* b_dst, const float* w_final, const float* b_final, float* loss,
+                           float* logits, float* d_emb, float* d_b_src, float* d_b_dst, float* d_w_final,
+                           float* d_b_final, float* z_rows, float* g_rows, void* stream) {
+  TGN_REQUIRE(heads == 2 && max_degree >= 1 && max_degree <= 10 && heads * head_dim <= 128 && head_dim % 2 == 0,
+              "dec_attn_fused: two heads, at most 10 edges per centre, heads * head_dim <= 128 (use tgn_attn_core_fwd "
+              "+ tgn_dec_fused otherwise)");
+  TGN_REQUIRE(alpha && ids_root && z_rows && g_rows, "dec_attn_fused: NULL pointer");
+  AttnCoreArgs a;
+  int32_t rc = core_args(a, proj, nbr_local, row_ptr, centre_ids, num_centres, nullptr, heads, head_dim, ee, dropout_p,
+                         seed, seed_dev);
+  if (rc) return rc;
+  a.alpha = alpha;
+  a.out = nullptr;
+  return dec_fused_launch(nullptr, ids_local, batch, heads * head_dim, w_src, b_src, w_dst, b_dst, w_final, b_final,
+                          loss, logits, d_emb, nullptr, d_b_src, nullptr, d_b_dst, d_w_final, d_b_final, z_rows,
+                          g_rows, &a, ids_root, stream);
+}
+
+static int32_t dec_fused_launch(const float* emb, const int64_t* ids_local, int32_t batch, int32_t dim,
+                      const float* w_src, const float* b_src, const float* w_dst, const float* b_dst,
+                      const float* w_final, const float* b_final, float* loss, float* logits,
+                                float* d_emb, float* d_w_src, float* d_b_src, float* d_w_dst, float* d_b_dst,
+                                float* d_w_final, float* d_b_final, float* z_rows, float* g_rows,
+                                const AttnCoreArgs* attn, const int64_t* ids_root, void* stream) {
   TGN_REQUIRE(batch >= 1 && dim >= 1, "dec_fused: bad sizes");
   const bool defer = z_rows != nullptr || g_rows != nullptr;
   const int64_t smem = defer ? ((int64_t)2 * dim * (dim + 1) + 2 * kDecVec * dim) * (int64_t)sizeof(float)
                              : tgn_dec_fused_smem_bytes(dim);
   TGN_REQUIRE(smem <= 215 * 1024 && dim <= 128,
               "dec_fused: dim %d does not fit shared memory (use the GEMM path)", dim);
-  TGN_REQUIRE(emb && ids_local && w_src && b_src && w_dst && b_dst && w_final && b_final && loss &&
+  TGN_REQUIRE(ids_local && w_src && b_src && w_dst && b_dst && w_final && b_final && loss &&
                   d_emb && d_b_src && d_b_dst && d_w_final && d_b_final,
               "dec_fused: NULL pointer");
   TGN_REQUIRE(defer ? (z_rows && g_rows) : (d_w_src && d_w_dst),
               "dec_fused: give d_w_src/d_w_dst, or z_rows AND g_rows for deferred weight gradients");
-  static int64_t attr_smem[2] = {0, 0};
-  if (smem > attr_smem[defer]) {
-    if (defer)
-      TGN_CUDA(cudaFuncSetAttribute(dec_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static int64_t attr_smem[3] = {0, 0, 0};
+  const int variant = attn ? 2 : (defer ? 1 : 0);
+  if (smem > attr_smem[variant]) {
+    if (attn)
+      TGN_CUDA(cudaFuncSetAttribute(dec_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else if (defer)
+      TGN_CUDA(cudaFuncSetAttribute(dec_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else
-      TGN_CUDA(cudaFuncSetAttribute(dec_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem[defer] = smem;
+      TGN_CUDA(cudaFuncSetAttribute(dec_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[variant] = smem;
   }
   // one pass = kDecEv events; a CTA's fixed cost is staging the two weight matrices (and, without
   // deferred weight gradients, the accumulator flush)
   int grid = ceil_div(batch, kDecEv);
   if (grid > kNumSMs) grid = kNumSMs;
-  if (defer)
-    launch_k(dec_fused_kernel<true>, dim3(grid), dim3(kDecThreads), (size_t)smem, (cudaStream_t)stream,
+  AttnCoreArgs none;
+  memset(&none, 0, sizeof(none));
+  if (attn)
+    launch_k(dec_fused_kernel<true, true>, dim3(grid), dim3(kDecThreads), (size_t)smem, (cudaStream_t)stream,
              emb, ids_local, batch, dim, w_src, b_src, w_dst, b_dst, w_final, b_final, loss, logits, d_emb,
-             d_w_src, d_b_src, d_w_dst, d_b_dst, d_w_final, d_b_final, z_rows, g_rows);
+             d_w_src, d_b_src, d_w_dst, d_b_dst, d_w_final, d_b_final, z_rows, g_rows, *attn, ids_root);
+  else if (defer)
+    launch_k(dec_fused_kernel<true, false>, dim3(grid), dim3(kDecThreads), (size_t)smem, (cudaStream_t)stream,
+             emb, ids_local, batch, dim, w_src, b_src, w_dst, b_dst, w_final, b_final, loss, logits, d_emb,
+             d_w_src, d_b_src, d_w_dst, d_b_dst, d_w_final, d_b_final, z_rows, g_rows, none, ids_root);
   else
-    launch_k(dec_fused_kernel<false>, dim3(grid), dim3(kDecThreads), (size_t)smem, (cudaStream_t)stream,
+    launch_k(dec_fused_kernel<false, false>, dim3(grid), dim3(kDecThreads), (size_t)smem, (cudaStream_t)stream,
              emb, ids_local, batch, dim, w_src, b_src, w_dst, b_dst, w_final, b_final, loss, logits, d_emb,
-             d_w_src, d_b_src, d_w_dst, d_b_dst, d_w_final, d_b_final, z_rows, g_rows);
+             d_w_src, d_b_src, d_w_dst, d_b_dst, d_w_final, d_b_final, z_rows, g_rows, none, ids_root);
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }

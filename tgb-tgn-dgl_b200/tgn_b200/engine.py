@@ -170,7 +170,7 @@ class TGNEngine:
                 raise ValueError("share: pass the engine that owns the state, not one of its siblings")
             share.__dict__.setdefault("_siblings", []).append(self)
             self.part_exchange = share.part_exchange
-            for k in ("memory", "last_update", "assoc", "neighbors", "e_id", "t_ring", "store", "bitmap",
+            for k in ("memory", "last_update", "assoc", "assoc_r", "neighbors", "e_id", "t_ring", "store", "bitmap",
                       "cur_e_id_dev", "log_base_dev", "pos_dev", "step_dev", "_symm_mem", "_symm_lu", "_peer_mem",
                       "_peer_lu"):
                 if hasattr(share, k):
@@ -194,6 +194,7 @@ class TGNEngine:
             self.last_update = torch.zeros(self.Nloc, dtype=torch.long, device=dev)
         if share is None:
             self.assoc = torch.zeros(num_nodes, dtype=torch.long, device=dev)
+            self.assoc_r = torch.zeros(num_nodes, dtype=torch.long, device=dev)    # rank of a node in the ROOT list of its batch
             self.neighbors = torch.zeros((num_nodes, size_k), dtype=torch.long, device=dev)
             self.e_id = torch.full((num_nodes, size_k), -1, dtype=torch.long, device=dev)
             self.t_ring = torch.full((num_nodes, size_k), -1.0, device=dev)
@@ -257,6 +258,10 @@ class TGNEngine:
         self.training = True
         self.fused_decoder = _L().tgn_dec_fused_smem_bytes(hidden) <= 215 * 1024 and hidden <= 128
         self.fused_gru = hidden % 4 == 0    # tgn_gru_fused_fwd (TMA strides need 16-byte rows)
+        # attention forward computed inside the decoder launch (tgn_dec_attn_fused): two heads, <= 10 neighbours
+        self.fused_attn_dec = (self.fused_decoder and heads == 2 and size_k <= 10 and self.HC == hidden and
+                               hidden <= 128 and (hidden // heads) % 2 == 0 and
+                               os.environ.get("TGN_FUSED_ATTN_DEC", "1") == "1")
         self.dz_split = 3                   # split-K of the d_z GEMM (1 = plain store)
         self.probe = None   # bench.py: {"name": [(start_event, stop_event), ...]} filled in eager steps
         # per-batch AP / AUC of the training logits, accumulated on the device (epoch_utils.py:312-317)
@@ -384,7 +389,7 @@ class TGNEngine:
 
     _SAMPLE_FIELDS = ("roots", "R_dev", "nbr_g", "ctr_g", "eid", "t_e", "root_off", "E_dev", "lookup_ws", "n_id",
                       "Nb_dev", "nbr_l", "ctr_l", "own_n", "own_pos", "So_dev")
-    _SLOT_FIELDS = _SAMPLE_FIELDS + ("ids_l", "in_i64", "in_ids3", "in_t_i64", "in_t_f32", "in_msg")
+    _SLOT_FIELDS = _SAMPLE_FIELDS + ("ids_l", "ids_r", "in_i64", "in_ids3", "in_t_i64", "in_t_f32", "in_msg")
 
     def _alloc_sample_fields(self, w, R: int, E: int, Nb: int):
         dev = self.dev
@@ -406,6 +411,7 @@ class TGNEngine:
         sl = SimpleNamespace(R=R, E=E, Nb=Nb, B=B)
         self._alloc_sample_fields(sl, R, E, Nb)
         sl.ids_l = torch.zeros(3 * B, dtype=torch.long, device=dev)
+        sl.ids_r = torch.zeros(3 * B, dtype=torch.long, device=dev)      # index of every batch id in the root list
         # one contiguous staging region per slot: [src | dst | neg | t] int64 followed by msg [B, De] float32,
         # so a host batch is ONE H2D copy (stage_packed1); in_i64 / in_msg are views of it
         De1 = max(self.De, 1)
@@ -722,18 +728,23 @@ class TGNEngine:
         e1.record()
         self.probe.setdefault(name, []).append((e0, e1))
 
-    def _sample(self, w, ids: Tensor, ids_l: Tensor, ids_dev: Optional[Tensor] = None, owner_select: bool = False):
+    def _sample(self, w, ids: Tensor, ids_l: Tensor, ids_dev: Optional[Tensor] = None, owner_select: bool = False,
+                ids_r: Optional[Tensor] = None):
         """roots -> neighbour lookup -> union -> relabel; everything bound-sized, counts on device.
         ids_dev: device count of the valid prefix of `ids` (entries beyond it must be -1: the marking
         kernels ignore them, the relabel stops in front of them)."""
         N, K = self.N, self.K
         L, s = _L(), _stream()
+        # ids_r (training slots): the rank of every batch id in the root list, for the attention-fused decoder
+        rank_of = _p(self.assoc_r) if ids_r is not None else None
         if ids.numel() <= 8192:   # small id list: marking folded into the single-CTA ranking launch
-            check(L.tgn_unique_mark_rank(_p(ids), ids.numel(), _p(self.bitmap), N, _p(w.roots), w.R, None,
+            check(L.tgn_unique_mark_rank(_p(ids), ids.numel(), _p(self.bitmap), N, _p(w.roots), w.R, rank_of,
                                          _p(w.R_dev), 1, s))
         else:
             check(L.tgn_unique_mark(_p(ids), ids.numel(), None, N, _p(self.bitmap), s))
-            check(L.tgn_unique_rank(_p(self.bitmap), N, _p(w.roots), w.R, None, _p(w.R_dev), 1, s))
+            check(L.tgn_unique_rank(_p(self.bitmap), N, _p(w.roots), w.R, rank_of, _p(w.R_dev), 1, s))
+        if ids_r is not None:
+            check(L.tgn_relabel(_p(ids), ids.numel(), _p(ids_dev), _p(self.assoc_r), _p(ids_r), s))
         check(L.tgn_nbr_lookup(_p(w.roots), w.R, _p(w.R_dev), K, N, _p(self.neighbors), _p(self.e_id),
                                _p(self.t_ring), _p(w.nbr_g), _p(w.ctr_g), _p(w.eid), _p(w.t_e),
                                _p(w.root_off), _p(w.E_dev), _p(self.bitmap), _p(w.lookup_ws), s))
@@ -928,7 +939,7 @@ class TGNEngine:
         if not pipelined:
             if from_device:
                 self.stage_batch_from_device()
-            self._sample(w, w.in_ids3, w.ids_l, owner_select=True)
+            self._sample(w, w.in_ids3, w.ids_l, owner_select=True, ids_r=w.ids_r)
         # ---- forked stream 1, from the start of the step: the batch's events enter the ring, then the
         # NEXT batch is loaded and sampled (single-CTA, latency-bound kernels: ~100 us of them hide
         # behind the whole step instead of trailing the GRU)
@@ -941,7 +952,7 @@ class TGNEngine:
                 nxt = self.slots[self._next_slot()]
                 if from_device:
                     self.stage_batch_from_device(self._next_slot())
-                self._sample(nxt, nxt.in_ids3, nxt.ids_l, owner_select=True)
+                self._sample(nxt, nxt.in_ids3, nxt.ids_l, owner_select=True, ids_r=nxt.ids_r)
         # the attention backward accumulates into a zero-filled d_proj (10 MB): cleared here, beside
         # msg_build, instead of in front of the backward on the dependent chain
         aux.wait_stream(main)
@@ -965,17 +976,29 @@ class TGNEngine:
             self._update_state(w)
         self._node_proj(w, w.z)
         main.wait_stream(aux)
-        self._attention_core(w, True)
+        if not self.fused_attn_dec:
+            self._attention_core(w, True)
         s = _stream()
         # ---- decoder + loss + decoder backward (decoder.py:24-27; BCEWithLogits, pyg-mem-tgn.py:51)
         gptr = lambda name: fg.data_ptr() + 4 * off[name]
-        if self.fused_decoder:
+        if self.fused_attn_dec:
+            # the attention forward of every (event, endpoint) occurrence runs inside the decoder launch: one link
+            # of the dependent chain less, no embedding table
+            check(L.tgn_dec_attn_fused(_p(w.proj), _p(w.nbr_l), _p(w.root_off), _p(w.ctr_l), w.R, self.H, self.C,
+                                       _p(w.ee), self.dropout, self.seed, _p(self.step_dev), self.K, _p(w.alpha),
+                                       _p(w.ids_r), _p(w.ids_l), B, _p(p["lin_src.weight"]), _p(p["lin_src.bias"]),
+                                       _p(p["lin_dst.weight"]), _p(p["lin_dst.bias"]), _p(p["lin_final.weight"]),
+                                       _p(p["lin_final.bias"]), _p(self.loss_acc), _p(w.logits), _p(self.d_emb),
+                                       gptr("lin_src.bias"), gptr("lin_dst.bias"), gptr("lin_final.weight"),
+                                       gptr("lin_final.bias"), _p(w.zcat), _p(w.dhcat), s))
+        elif self.fused_decoder:
             check(L.tgn_dec_fused(_p(w.emb), _p(w.ids_l), B, D, _p(p["lin_src.weight"]), _p(p["lin_src.bias"]),
                                   _p(p["lin_dst.weight"]), _p(p["lin_dst.bias"]), _p(p["lin_final.weight"]),
                                   _p(p["lin_final.bias"]), _p(self.loss_acc), _p(w.logits), _p(self.d_emb),
                                   None, gptr("lin_src.bias"), None,
                                   gptr("lin_dst.bias"), gptr("lin_final.weight"), gptr("lin_final.bias"),
                                   _p(w.zcat), _p(w.dhcat), s))
+        if self.fused_decoder:
             # (one CTA per [D,D] gradient walks the whole batch: beyond ~256 events the reduction is split)
             split_d = max(1, min(16, B // 128))
             dec_wgrad = [  # dW_src += g_src^T z_src ; dW_dst += [g_pos; g_neg]^T [z_dst; z_neg]  (aux stream, below)
@@ -1132,7 +1155,7 @@ class TGNEngine:
                 if from_device:
                     self.stage_batch_from_device()
                 self._sample(self.slots[self.cur], self.slots[self.cur].in_ids3, self.slots[self.cur].ids_l,
-                             owner_select=True)
+                             owner_select=True, ids_r=self.slots[self.cur].ids_r)
                 self._primed = mode
         else:
             self._unprime()
@@ -1241,7 +1264,7 @@ class TGNEngine:
             self._unprime()
             self._bind(self.cur)
             self._sample(self.slots[self.cur], self.slots[self.cur].in_ids3, self.slots[self.cur].ids_l,
-                         owner_select=True)
+                         owner_select=True, ids_r=self.slots[self.cur].ids_r)
             self._primed = "host"
         i = self._gl_n & 1
         main.wait_event(self._gl_ev[i])

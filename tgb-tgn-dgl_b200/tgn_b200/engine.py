@@ -259,8 +259,10 @@ class TGNEngine:
         self.fused_decoder = _L().tgn_dec_fused_smem_bytes(hidden) <= 215 * 1024 and hidden <= 128
         self.fused_gru = hidden % 4 == 0    # tgn_gru_fused_fwd (TMA strides need 16-byte rows)
         # attention forward computed inside the decoder launch (tgn_dec_attn_fused): two heads, <= 10 neighbours
+        # (up to ~one decoder pass per SM: at B = 2000 the 500 passes of 148 CTAs would walk what the stand-alone
+        # attention kernel spreads over 1,500 CTAs -- measured 0.358 against 0.325 ms per wiki step)
         self.fused_attn_dec = (self.fused_decoder and heads == 2 and size_k <= 10 and self.HC == hidden and
-                               hidden <= 128 and (hidden // heads) % 2 == 0 and
+                               hidden <= 128 and (hidden // heads) % 2 == 0 and batch_size <= 600 and
                                os.environ.get("TGN_FUSED_ATTN_DEC", "1") == "1")
         self.dz_split = 3                   # split-K of the d_z GEMM (1 = plain store)
         self.probe = None   # bench.py: {"name": [(start_event, stop_event), ...]} filled in eager steps

@@ -415,3 +415,64 @@ def test_sharded_embedding_eval_equals_replicated_eval(Q, dense):
         assert torch.equal(eng_a.last_update, eng_b.last_update) and torch.equal(eng_a.e_id, eng_b.e_id)
         torch.testing.assert_close(eng_a.memory, eng_b.memory, rtol=1e-5, atol=1e-6)
     eng_b.check_device_errors()
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.3])
+def test_attention_fused_decoder_equals_separate_launches(dropout):
+    """tgn_dec_attn_fused (attention forward of every (event, endpoint) occurrence computed inside the decoder
+    launch) against tgn_attn_core_fwd + tgn_dec_fused on the same batches, from the same weights: same losses,
+    same memory / last_update / ring, same weights after Adam -- with attention dropout as well (the Philox mask is
+    keyed by (edge, head, step), so both routes draw the same mask).  Duplicated nodes inside a batch (hub
+    sources) exercise the per-occurrence recomputation."""
+    N, De, D, K, B, steps = 300, 6, 32, 5, 40, 8
+    engs = []
+    for fused in (True, False):
+        _, eng, _ = _setup(N, De, D, K, B, B * (steps + 2), 33, False)
+        eng.dropout = dropout
+        assert eng.fused_attn_dec
+        eng.fused_attn_dec = fused
+        engs.append(eng)
+    a, b = engs
+    for s in range(steps):
+        la = float(a.train_step(from_device=True))
+        lb = float(b.train_step(from_device=True))
+        assert abs(la - lb) <= 2e-6 * max(1.0, abs(lb)), (s, la, lb)
+        # the two routes' gradients agree to rounding (the atomic accumulation order differs from run to run on
+        # either route); Adam amplifies that on near-zero gradients, so the weights are re-synced after the check
+        torch.testing.assert_close(a.flat_grad, b.flat_grad, rtol=1e-3, atol=2e-5)
+        torch.testing.assert_close(a.memory, b.memory, rtol=1e-5, atol=2e-6)
+        for x, y in ((a.flat, b.flat), (a.exp_avg, b.exp_avg), (a.exp_avg_sq, b.exp_avg_sq)):
+            x.copy_(y)
+    assert torch.equal(a.last_update, b.last_update) and torch.equal(a.e_id, b.e_id)
+    a.check_device_errors()
+
+
+def test_peer_bcast_writes_a_block_into_every_table():
+    """tgn_peer_bcast with the 'peers' being three tables of this device: the block lands at the same offset of
+    each, nothing else is touched (the multi-rank use is covered by tests/dist_eval_check.py on 2 GPUs)."""
+    import ctypes
+    from tgn_b200 import _cabi
+    L = _cabi.lib()
+    tables = [torch.full((64,), float(i), device=DEV) for i in range(3)]
+    src = torch.arange(16, dtype=torch.float32, device=DEV) + 100
+    ptrs = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in tables])
+    _cabi.check(L.tgn_peer_bcast(src.data_ptr(), 64, ptrs, 32 * 4, 3, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    for i, t in enumerate(tables):
+        assert torch.equal(t[32:48], src) and bool((t[:32] == i).all()) and bool((t[48:] == i).all())
+    rc = L.tgn_peer_bcast(src.data_ptr(), 60, ptrs, 0, 3, None)          # not a multiple of 16 bytes
+    assert rc == _cabi.TGN_EINVAL
+
+
+def test_group_views_layout_equals_pack_host_group():
+    """The numpy views a host loader fills (TGNEngine.group_views) address exactly the layout pack_host_group
+    writes -- the layout stage_group copies to the device."""
+    _, eng, ev = _setup(100, 3, 16, 5, 8, 8 * 12, 5, False)
+    G, B = eng.group_size, 8
+    a = torch.zeros(eng.group_nbytes(), dtype=torch.uint8)
+    b = torch.zeros(eng.group_nbytes(), dtype=torch.uint8)
+    batches = [tuple(ev[k][i * B:(i + 1) * B] for k in ("src", "dst", "neg", "t", "msg")) for i in range(G)]
+    eng.pack_host_group(a, batches)
+    for (vs, vd, vn, vt, vm), (s_, d_, n_, t_, m_) in zip(eng.group_views(b), batches):
+        vs[:], vd[:], vn[:], vt[:], vm[:] = s_.numpy(), d_.numpy(), n_.numpy(), t_.numpy(), m_.numpy()
+    assert torch.equal(a, b)

@@ -871,9 +871,15 @@ class TGNEngine:
                                      _p(self.step_dev), self.K, _p(w.emb), _p(w.alpha), _stream()))
 
     def _attention_fwd(self, w, z: Tensor, lu: Tensor, train: bool):
-        """GraphAttentionEmbedding.forward (emb_module.py:25-29) for the centres (= roots)."""
-        self._node_proj(w, z)
+        """GraphAttentionEmbedding.forward (emb_module.py:25-29) for the centres (= roots).  The node projection
+        (a GEMM over the rows) and the edge branch (time encoding + edge projection) are independent: the
+        projection runs on the auxiliary stream beside the edge branch."""
+        main, aux = torch.cuda.current_stream(), self.aux
+        aux.wait_stream(main)
+        with torch.cuda.stream(aux):
+            self._node_proj(w, z)
         self._edge_branch(w, lu, train)
+        main.wait_stream(aux)
         self._attention_core(w, train)
 
     def _update_state(self, w):

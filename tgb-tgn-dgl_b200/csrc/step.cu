@@ -378,23 +378,36 @@ struct SmallMask {
 
 // One centre of the low-degree path, by one warp: returns the lane's four output channels (aggregation + skip)
 // and leaves the softmax weights in a.alpha.  Shared by the stand-alone kernel and the decoder-fused one.
-template <int H, int kDeg>
-__device__ __forceinline__ float4 attn_small_fwd_row(const AttnCoreArgs& a, int ci, int lane, const HeadMask<H>& hm,
-                                                     const Philox& rng, float inv_sqrt_c, float keep, bool ok, int c0,
-                                                     int64_t* row_out) {
-  const int HC = a.H * a.C;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int64_t row = a.centre_ids ? a.centre_ids[ci] : ci;
-  *row_out = row;
-  const int e0 = a.row_ptr[ci];
-  const int deg = min(a.row_ptr[ci + 1] - e0, kDeg);
+// The scalars of one centre: its row, its first edge, its degree (capped), and in lane l the id of neighbour l.
+struct CentreHead {
+  int64_t row, my_j;
+  int e0, deg;
+};
+template <int kDeg>
+__device__ __forceinline__ CentreHead attn_centre_head(const AttnCoreArgs& a, int ci, int lane) {
+  CentreHead h;
+  h.row = a.centre_ids ? a.centre_ids[ci] : ci;
+  h.e0 = a.row_ptr[ci];
+  h.deg = min(a.row_ptr[ci + 1] - h.e0, kDeg);
   // the centre's edge rows are contiguous (deg x HC floats, streamed from DRAM): request them now, one 128-byte
   // line per lane, so they arrive while the neighbour ids and the k / v rows (L2-resident table) are fetched
-  if (lane * 32 < deg * HC) prefetch_l2(a.ee + (long long)e0 * HC + lane * 32);
+  if (lane * 32 < h.deg * a.H * a.C) prefetch_l2(a.ee + (long long)h.e0 * (a.H * a.C) + lane * 32);
+  h.my_j = lane < h.deg ? a.nbr[h.e0 + lane] : 0;
+  return h;
+}
+
+template <int H, int kDeg>
+__device__ __forceinline__ float4 attn_small_fwd_row(const AttnCoreArgs& a, const CentreHead& ch, int lane,
+                                                     const HeadMask<H>& hm, const Philox& rng, float inv_sqrt_c,
+                                                     float keep, bool ok, int c0) {
+  const int HC = a.H * a.C;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t row = ch.row;
+  const int e0 = ch.e0, deg = ch.deg;
   const float* pr = a.proj + row * 4 * HC;
   const float4 q = ok ? ld4(pr + c0) : z4;
   const float4 skip = ok ? ld4(pr + 3 * HC + c0) : z4;
-  const int64_t my_j = lane < deg ? a.nbr[e0 + lane] : 0;
+  const int64_t my_j = ch.my_j;
   float4 kk[kDeg], vv[kDeg];
 #pragma unroll
   for (int g = 0; g < kDeg; ++g) {
@@ -467,10 +480,18 @@ __global__ void __launch_bounds__(kCoreWarps * 32, kMinCtas) attn_core_fwd_small
   HeadMask<H> hm;
   hm.init(c0, C, ok);
   Philox rng(a.seed + (a.seed_dev ? (uint64_t)*a.seed_dev : 0ull));
-  for (int ci = blockIdx.x * kCoreWarps + wid; ci < nC; ci += gridDim.x * kCoreWarps) {
-    int64_t row;
-    const float4 o = attn_small_fwd_row<H, kDeg>(a, ci, lane, hm, rng, inv_sqrt_c, keep, ok, c0, &row);
-    if (ok) *reinterpret_cast<float4*>(a.out + row * HC + c0) = o;
+  // a warp that walks several centres (capped grids of evaluation-sized launches) fetches the NEXT centre's
+  // scalars -- two dependent round trips -- while it computes the current one
+  const int stride = gridDim.x * kCoreWarps;
+  int ci = blockIdx.x * kCoreWarps + wid;
+  if (ci >= nC) return;
+  CentreHead cur = attn_centre_head<kDeg>(a, ci, lane);
+  for (; ci < nC; ci += stride) {
+    CentreHead nxt = cur;
+    if (ci + stride < nC) nxt = attn_centre_head<kDeg>(a, ci + stride, lane);
+    const float4 o = attn_small_fwd_row<H, kDeg>(a, cur, lane, hm, rng, inv_sqrt_c, keep, ok, c0);
+    if (ok) *reinterpret_cast<float4*>(a.out + cur.row * HC + c0) = o;
+    cur = nxt;
   }
 }
 
@@ -840,9 +861,8 @@ __global__ void __launch_bounds__(kDecThreads)
           HeadMask<2> hm;
           hm.init(c0, at.C, ok);
           Philox rng(at.seed + (at.seed_dev ? (uint64_t)*at.seed_dev : 0ull));
-          int64_t rr;
-          o = attn_small_fwd_row<2, 10>(at, (int)ids_r[row * B + e0 + slot], lane, hm, rng, rsqrtf((float)at.C),
-                                        1.f - at.dropout_p, ok, c0, &rr);
+          const CentreHead ch = attn_centre_head<10>(at, (int)ids_r[row * B + e0 + slot], lane);
+          o = attn_small_fwd_row<2, 10>(at, ch, lane, hm, rng, rsqrtf((float)at.C), 1.f - at.dropout_p, ok, c0);
         }
         if (ok) {
           sz[(c0 + 0) * kDecVec + v] = o.x;
@@ -1252,7 +1272,7 @@ int32_t tgn_attn_core_fwd(const float* proj, const int64_t* nbr_local, const int
       case 1: launch_k(attn_core_fwd_small_kernel<1, kSmallDeg, 3>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a); break;
       case 2:
         if (max_degree <= 10 && num_centres > 8 * kNumSMs * kCoreWarps)   // occupancy only pays on multi-wave launches
-          launch_k(attn_core_fwd_small_kernel<2, 10, 4>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a);
+          launch_k(attn_core_fwd_small_kernel<2, 10, 4>, dim3(min(grid, 4 * kNumSMs)), dim3(kCoreWarps * 32), 0, s, a);
         else
           launch_k(attn_core_fwd_small_kernel<2, kSmallDeg, 3>, dim3(grid), dim3(kCoreWarps * 32), 0, s, a);
         break;

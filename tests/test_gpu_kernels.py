@@ -681,3 +681,40 @@ def test_attn_core_small_path_equals_general_path_with_dropout(ops, H, C):
     _cabi.check(L.tgn_attn_core_fwd(p(dev[0]), p(dev[1]), p(dev[2]), p(dev[3]), R, None, H, C, p(dev[4]), 0.0,
                                     99, None, K, p(out_nodrop), p(al2), 0))
     assert not torch.allclose(out_nodrop, res[0][0])
+
+
+@pytest.mark.parametrize("K,R", [(10, 150_000), (7, 40_000), (10, 500)])
+def test_ring_lookup_writes_stay_inside_their_buffers(ops, K, R):
+    """Guard bands around every output of tgn_nbr_lookup (and its workspace) on the large-launch path (count +
+    emit passes) and the single-launch path: nothing outside [0, count) / [0, R] / the declared workspace is
+    written (compute-sanitizer is not available on the pool)."""
+    import ctypes
+    from tgn_b200 import _cabi
+    L = _cabi.lib()
+    N, G = 20_000, 64
+    g = torch.Generator(device=DEV).manual_seed(R)
+    e_id = torch.randint(-1, 1_000_000, (N, K), device=DEV, generator=g)
+    nbrs = torch.randint(0, N, (N, K), device=DEV, generator=g)
+    t = torch.rand((N, K), device=DEV, generator=g)
+    roots = torch.randint(0, N, (R,), device=DEV, generator=g)
+    count = int((e_id[roots] >= 0).sum())
+    cap = R * K
+    mk = lambda n, dt, v: torch.full((n + 2 * G,), v, dtype=dt, device=DEV)
+    o_n, o_c, o_e = (mk(cap, torch.int64, -777) for _ in range(3))
+    o_t = mk(cap, torch.float32, -777.0)
+    off = mk(R + 1, torch.int32, -777)
+    cnt = mk(1, torch.int32, -777)
+    wsn = L.tgn_nbr_lookup_ws_bytes(R, K) // 8
+    ws = mk(wsn, torch.int64, -777)
+    p = lambda x: x.data_ptr() + G * x.element_size()
+    _cabi.check(L.tgn_nbr_lookup(roots.data_ptr(), R, None, K, N, nbrs.data_ptr(), e_id.data_ptr(), t.data_ptr(),
+                                 p(o_n), p(o_c), p(o_e), p(o_t), p(off), p(cnt), None, p(ws),
+                                 torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert int(cnt[G]) == count
+    for buf, n in ((o_n, cap), (o_c, cap), (o_e, cap), (o_t, cap), (off, R + 1), (cnt, 1), (ws, wsn)):
+        assert bool((buf[:G] == -777).all()) and bool((buf[G + n:] == -777).all())
+    for buf in (o_n, o_c, o_e, o_t):          # the compacted outputs end at `count`
+        assert bool((buf[G + count:G + cap] == -777).all())
+    valid = e_id[roots] >= 0
+    assert torch.equal(o_e[G:G + count], e_id[roots][valid])

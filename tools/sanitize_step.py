@@ -37,5 +37,31 @@ rts = torch.from_numpy(rng.integers(0, 4200, 500).astype(np.float32)).to(dev)
 for strat in (0, 1):
     out, off, cnt = ops.tcsr_sample(g[0], g[1], g[2], g[3], roots, rts, 10, strat, coarse=coarse)
 print("sampled", int(cnt))
+# ---- round 2: the large-launch ring lookup (count + emit passes, >= 64 tiles), odd K
+for K2, R2 in ((10, 20_000), (7, 30_000)):
+    N2 = 5_000
+    e2 = torch.randint(-1, 1000, (N2, K2), device=dev)
+    nb2 = torch.randint(0, N2, (N2, K2), device=dev)
+    t2 = torch.rand((N2, K2), device=dev)
+    r2 = torch.randint(0, N2, (R2,), device=dev)
+    o = ops.nbr_lookup_raw(r2, nb2, e2, t2, None)
+    assert int(o[5]) == int((e2[r2] >= 0).sum())
+print("large lookup ok")
+# ---- the persistent GEMM kernel (more than two waves of tiles), both precisions, a device row count
+A = torch.randn(40_000, 116, device=dev); W = torch.randn(100, 116, device=dev); C = torch.zeros(40_000, 100, device=dev)
+md = torch.tensor([39_001], dtype=torch.int32, device=dev)
+for prec in (3, 1):
+    ops.gemm_batch([ops.gemm_desc(A, W, C, m=40_000, n=100, k=116, lda=116, ldb=116, ldc=100, m_dev=md)], prec)
+print("persistent gemm", float(C[:39_001].abs().sum()) > 0)
+# ---- sharded evaluation on a dense candidate set (in-place rows), one rank
+eng2 = TGNEngine(60, De, D, K, B, device=dev, lr=1e-3, dropout=0.1, use_graph=False, log_capacity=E)
+eng2.load_state(*bench.init_state_dicts(De, D, 60, seed=1))
+s2 = rng.integers(0, 30, E); d2 = rng.integers(30, 60, E)
+eng2.set_events(torch.from_numpy(s2), torch.from_numpy(d2), ev["t"], ev["msg"], torch.from_numpy(d2))
+eng2.flush_to_eval()
+negs = torch.from_numpy(rng.integers(30, 60, (B, 20)))
+pos, gt, ge = eng2.eval_batch_dp(torch.from_numpy(s2[:B]), torch.from_numpy(d2[:B]), negs, ev["t"][:B], ev["msg"][:B], 0, 1)
+assert eng2._eval_ctx_dp(B, 20, 0, 1).dense
+print("dense eval", float(pos.sum()))
 torch.cuda.synchronize()
 print("sanitize pass done")

@@ -9,7 +9,8 @@ One step = the per-batch flow the reference's four hot-path pieces serve
     z, last_update = memory(n_id)            -> store gather + concat + time-enc + Last
                                                 aggregation (msgstore.cu), fused GRUCell: both gate
                                                 GEMMs in TMEM + gate math (gemm_tma.cu)
-    z = gnn(z, last_update, edges, t, msg)   -> projection / edge GEMMs + softmax core (step.cu)
+    z = gnn(z, last_update, edges, t, msg)   -> projection / edge GEMMs + softmax core (step.cu); in training
+                                                (batch <= 600) the softmax core runs INSIDE the decoder launch
     pos/neg logits, BCE loss                 -> fused decoder forward + loss + d_emb (step.cu)
     backward                                 -> hand-derived, same kernels; every weight
                                                 gradient is a split-K GEMM accumulating

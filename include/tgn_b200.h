@@ -287,6 +287,15 @@ int32_t tgn_msg_build_gathered(const tgn_msgstore* st, const int64_t* n_id, int3
                                const float* time_w, const float* time_b, int32_t time_dim, float* x,
                                int32_t ldx, float* h_out, float* sin_out, void* lu_out,
                                int32_t* sel_ev, float* sel_dt, void* stream);
+/* The same with the rows read in place: node n's memory row and last_update come straight out of the shard of
+ * its owner (rank n % world, local row n / world; peer_memory[r] / peer_last_update[r] = rank r's mapping of
+ * the symmetric allocations) -- tgn_part_gather_p2p + tgn_msg_build_gathered as one launch, no staging
+ * buffer.  Last aggregation. */
+int32_t tgn_msg_build_p2p(const tgn_msgstore* st, const int64_t* n_id, int32_t num, const int32_t* num_dev,
+                          const void* const* peer_memory, const void* const* peer_last_update, int32_t world,
+                          int32_t memory_dim, const float* time_w, const float* time_b, int32_t time_dim, float* x,
+                          int32_t ldx, float* h_out, float* sin_out, void* lu_out, int32_t* sel_ev, float* sel_dt,
+                          void* stream);
 int32_t tgn_memory_scatter_owned(const int64_t* n_id, int32_t num, const int32_t* num_dev,
                                  const float* new_mem, const void* new_lu, int32_t lu_is_float,
                                  const int64_t* src_rows, int32_t dim, int32_t rank, int32_t world,

@@ -221,7 +221,16 @@ __device__ __forceinline__ float rel_time<float>(float t, int64_t lu) {
   return t - (float)lu;  // float32 - int64 promotes to float32
 }
 
-template <typename T>
+// Owner-partitioned node memory (csrc/partition.cu): node n lives on rank n % world at row n / world; the
+// shards of all ranks are mapped (symmetric memory), so a row is read straight out of its owner's HBM.
+constexpr int kMsgMaxPeers = 16;
+struct MsgPeers {
+  const float* mem[kMsgMaxPeers];
+  const int64_t* lu[kMsgMaxPeers];
+  int world;      // 0: not partitioned (the dense `memory` / `last_update` tables are used)
+};
+
+template <typename T, bool kPeers>
 __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_id, DevCount num,
                                  int agg_mode, const float* __restrict__ memory,
                                  const int64_t* __restrict__ last_update, int Dm,
@@ -231,10 +240,14 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
                                  T* __restrict__ lu_out, int32_t* __restrict__ sel_ev,
                                  float* __restrict__ sel_dt, const float* __restrict__ gath_n,
                                  const float* __restrict__ gath_o,
-                                 const int64_t* __restrict__ gath_lu) {
+                                 const int64_t* __restrict__ gath_lu, MsgPeers peers) {
   pdl_wait();
   pdl_launch();
   const int lane = threadIdx.x & 31;
+  // memory row / last_update of node id: the dense table, or the owner's shard over the peer mapping
+  auto row_of = [&](int64_t id) -> const float* {
+    return kPeers ? peers.mem[id % peers.world] + (id / peers.world) * Dm : memory + id * Dm;
+  };
   const int warps_per_block = blockDim.x >> 5;
   const int S = num.get();
   const int De = st.raw_dim;
@@ -248,7 +261,7 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
     const int sc = ok ? st.s_cnt[n] : 0, dc = ok ? st.d_cnt[n] : 0;
     for (int c = W + lane; c < ldx; c += 32) xr[c] = 0.f;  // row padding (TMA-aligned stride)
     // owner-partitioned memory: rows / last_update come pre-assembled per row s (partition.cu)
-    const float* mn_src = gath_n ? gath_n + (long long)s * Dm : memory + (ok ? n : 0) * Dm;
+    const float* mn_src = gath_n ? gath_n + (long long)s * Dm : row_of(ok ? n : 0);
     if (h_out)
       for (int c = lane; c < Dm; c += 32) h_out[(long long)s * Dm + c] = ok ? mn_src[c] : 0.f;
     if (sc + dc == 0) {
@@ -260,7 +273,8 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
       }
       continue;
     }
-    const int64_t lu = gath_lu ? gath_lu[s] : last_update[n];
+    const int64_t lu = gath_lu ? gath_lu[s]
+                               : (kPeers ? peers.lu[n % peers.world][n / peers.world] : last_update[n]);
     const float* mn = mn_src;
     if (agg_mode == TGN_AGG_LAST) {
       const int es = sc > 0 ? st.s_last[n] : -1, ed = dc > 0 ? st.d_last[n] : -1;
@@ -272,7 +286,7 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
       const T te = pick_s ? ts_ : td_;
       const int64_t other = pick_s ? st.ev_dst[e] : st.ev_src[e];
       const float dt = rel_time<T>(te, lu);
-      const float* mo = gath_o ? gath_o + (long long)s * Dm : memory + other * Dm;
+      const float* mo = gath_o ? gath_o + (long long)s * Dm : row_of(other);
       const float* rw = st.ev_msg + (long long)e * De;
       for (int c = lane; c < Dm; c += 32) {
         xr[c] = mn[c];
@@ -314,7 +328,7 @@ __global__ void msg_build_kernel(tgn_msgstore st, const int64_t* __restrict__ n_
               if (c < Dm) v = mn[c];
               else if (c < 2 * Dm) {
                 const int64_t other = dir == 0 ? st.ev_dst[e] : st.ev_src[e];
-                v = memory[other * Dm + (c - Dm)];
+                v = row_of(other)[c - Dm];
               } else if (c < 2 * Dm + De) v = st.ev_msg[(long long)e * De + (c - 2 * Dm)];
               else {
                 const int cc = c - 2 * Dm - De;
@@ -449,7 +463,10 @@ static int32_t msg_build_impl(const tgn_msgstore* st, const int64_t* n_id, int32
                               const float* time_b, int32_t time_dim, float* x, int32_t ldx,
                               float* h_out, float* sin_out, void* lu_out, int32_t* sel_ev,
                               float* sel_dt, const float* gath_n, const float* gath_o,
-                              const int64_t* gath_lu, void* stream) {
+                              const int64_t* gath_lu, void* stream, const MsgPeers* peers_in = nullptr) {
+  MsgPeers peers;
+  memset(&peers, 0, sizeof(peers));
+  if (peers_in) peers = *peers_in;
   int32_t rc = check_store(st, "msg_build");
   if (rc) return rc;
   TGN_REQUIRE(num >= 0 && memory_dim >= 1 && time_dim >= 0, "msg_build: bad sizes");
@@ -462,14 +479,18 @@ static int32_t msg_build_impl(const tgn_msgstore* st, const int64_t* n_id, int32
   cudaStream_t s = (cudaStream_t)stream;
   DevCount c{num_dev, num};
   const int grid = stride_grid((long long)num * 32, 256);
-  if (st->t_is_float)
-    launch_k(msg_build_kernel<float>, dim3(grid), dim3(256), 0, s, *st, n_id, c, agg_mode, memory, last_update,
-                                                 memory_dim, time_w, time_b, time_dim, x, ldx, h_out,
-                                                 sin_out, (float*)lu_out, sel_ev, sel_dt, gath_n, gath_o, gath_lu);
-  else
-    launch_k(msg_build_kernel<int64_t>, dim3(grid), dim3(256), 0, s, *st, n_id, c, agg_mode, memory, last_update,
-                                                   memory_dim, time_w, time_b, time_dim, x, ldx,
-                                                   h_out, sin_out, (int64_t*)lu_out, sel_ev, sel_dt, gath_n, gath_o, gath_lu);
+#define TGN_MB_LAUNCH(T, PEERS)                                                                              \
+  launch_k(msg_build_kernel<T, PEERS>, dim3(grid), dim3(256), 0, s, *st, n_id, c, agg_mode, memory, last_update, \
+           memory_dim, time_w, time_b, time_dim, x, ldx, h_out, sin_out, (T*)lu_out, sel_ev, sel_dt, gath_n,     \
+           gath_o, gath_lu, peers)
+  if (peers.world > 0) {
+    if (st->t_is_float) TGN_MB_LAUNCH(float, true);
+    else TGN_MB_LAUNCH(int64_t, true);
+  } else {
+    if (st->t_is_float) TGN_MB_LAUNCH(float, false);
+    else TGN_MB_LAUNCH(int64_t, false);
+  }
+#undef TGN_MB_LAUNCH
   TGN_LAUNCH_CHECK();
   return TGN_OK;
 }
@@ -495,6 +516,27 @@ int32_t tgn_msg_build_gathered(const tgn_msgstore* st, const int64_t* n_id, int3
   return msg_build_impl(st, n_id, num, num_dev, TGN_AGG_LAST, rows_n, last_update_rows, memory_dim,
                         time_w, time_b, time_dim, x, ldx, h_out, sin_out, lu_out, sel_ev, sel_dt, rows_n,
                         rows_other, last_update_rows, stream);
+}
+
+int32_t tgn_msg_build_p2p(const tgn_msgstore* st, const int64_t* n_id, int32_t num, const int32_t* num_dev,
+                          const void* const* peer_memory, const void* const* peer_last_update, int32_t world,
+                          int32_t memory_dim, const float* time_w, const float* time_b, int32_t time_dim, float* x,
+                          int32_t ldx, float* h_out, float* sin_out, void* lu_out, int32_t* sel_ev, float* sel_dt,
+                          void* stream) {
+  TGN_REQUIRE(peer_memory && peer_last_update && world >= 1 && world <= kMsgMaxPeers,
+              "msg_build_p2p: peer tables / world (<= %d)", kMsgMaxPeers);
+  MsgPeers peers;
+  memset(&peers, 0, sizeof(peers));
+  peers.world = world;
+  for (int r = 0; r < world; ++r) {
+    peers.mem[r] = (const float*)peer_memory[r];
+    peers.lu[r] = (const int64_t*)peer_last_update[r];
+    TGN_REQUIRE(peers.mem[r] && peers.lu[r], "msg_build_p2p: peer %d has no mapping", r);
+  }
+  // (the dense table arguments are unused in this mode; rank 0's shard satisfies the NULL checks)
+  return msg_build_impl(st, n_id, num, num_dev, TGN_AGG_LAST, peers.mem[0], peers.lu[0], memory_dim, time_w, time_b,
+                        time_dim, x, ldx, h_out, sin_out, lu_out, sel_ev, sel_dt, nullptr, nullptr, nullptr, stream,
+                        &peers);
 }
 
 int32_t tgn_msg_build(const tgn_msgstore* st, const int64_t* n_id, int32_t num,

@@ -817,12 +817,19 @@ class TGNEngine:
         wo, D, L, p, Sb = self.wo, self.D, _L(), self.p, self.So_b
         st = ctypes.byref(self.store.struct())
         g_o = wo.g_rows.data_ptr() + 4 * wo.g_rows.shape[1] * D
-        check(L.tgn_part_gather_p2p(st, _p(w.own_n), Sb, _p(w.So_dev), self._peer_mem, self._peer_lu, D,
-                                    self.world, _p(wo.g_rows), g_o, _p(wo.g_lu), _stream()))
-        check(L.tgn_msg_build_gathered(st, _p(w.own_n), Sb, _p(w.So_dev), _p(wo.g_rows), g_o, _p(wo.g_lu), D,
-                                       _p(p["time_enc.lin.weight"]), _p(p["time_enc.lin.bias"]), self.Dt,
-                                       _p(wo.x), self.ldx, _p(wo.h), _p(wo.sn_m), _p(wo.lu), _p(wo.sel_ev),
-                                       _p(wo.sel_dt), _stream()))
+        if os.environ.get("TGN_PART_FUSED_GATHER", "1") == "1":
+            # the message build reads its rows in place, out of the owners' shards (no staging launch)
+            check(L.tgn_msg_build_p2p(st, _p(w.own_n), Sb, _p(w.So_dev), self._peer_mem, self._peer_lu, self.world, D,
+                                      _p(p["time_enc.lin.weight"]), _p(p["time_enc.lin.bias"]), self.Dt,
+                                      _p(wo.x), self.ldx, _p(wo.h), _p(wo.sn_m), _p(wo.lu), _p(wo.sel_ev),
+                                      _p(wo.sel_dt), _stream()))
+        else:
+            check(L.tgn_part_gather_p2p(st, _p(w.own_n), Sb, _p(w.So_dev), self._peer_mem, self._peer_lu, D,
+                                        self.world, _p(wo.g_rows), g_o, _p(wo.g_lu), _stream()))
+            check(L.tgn_msg_build_gathered(st, _p(w.own_n), Sb, _p(w.So_dev), _p(wo.g_rows), g_o, _p(wo.g_lu), D,
+                                           _p(p["time_enc.lin.weight"]), _p(p["time_enc.lin.bias"]), self.Dt,
+                                           _p(wo.x), self.ldx, _p(wo.h), _p(wo.sn_m), _p(wo.lu), _p(wo.sel_ev),
+                                           _p(wo.sel_dt), _stream()))
         self._memory_gru(wo, Sb, w.So_dev)
         check(L.tgn_part_publish(_p(wo.z), _p(wo.lu), _p(w.own_pos), Sb, _p(w.So_dev), D, self._peer_z,
                                  self._peer_rowlu, self.world, _stream()))

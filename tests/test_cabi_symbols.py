@@ -47,6 +47,27 @@ def test_argument_validation_needs_no_gpu():
                                         None, None, None, None, None, None, None, None, None))
 
 
+def test_round2_entry_points_validate_without_a_gpu():
+    """The entry points added in round 2 answer bad arguments with TGN_EINVAL before any CUDA call."""
+    lib = _cabi.lib()
+    buf = (ctypes.c_void_p * 2)(1024, 2048)
+    # tgn_peer_bcast: sizes / offsets are multiples of 16 bytes, world <= 16
+    assert lib.tgn_peer_bcast(ctypes.c_void_p(4096), 60, buf, 0, 2, None) == _cabi.TGN_EINVAL
+    assert b"16" in lib.tgn_last_error()
+    assert lib.tgn_peer_bcast(ctypes.c_void_p(4096), 64, buf, 0, 17, None) == _cabi.TGN_EINVAL
+    assert lib.tgn_peer_bcast(None, 0, None, 0, 1, None) == 0          # an empty block is a no-op
+    # tgn_dec_attn_fused: two heads, at most 10 edges per centre
+    args = [None] * 4 + [4, 4, 25] + [None, 0.0, 0, None, 10] + [None] * 3 + [8] + [None] * 16
+    assert lib.tgn_dec_attn_fused(*args) == _cabi.TGN_EINVAL and b"two heads" in lib.tgn_last_error()
+    args[5], args[11] = 2, 12
+    assert lib.tgn_dec_attn_fused(*args) == _cabi.TGN_EINVAL and b"10 edges" in lib.tgn_last_error()
+    # tgn_msg_build_p2p: needs the peer tables
+    assert lib.tgn_msg_build_p2p(None, None, 4, None, None, None, 2, 100, None, None, 100, None, 304, None, None,
+                                 None, None, None, None) == _cabi.TGN_EINVAL
+    # workspace of the ring lookup: ticket + tiles + groups of eight tiles
+    assert lib.tgn_nbr_lookup_ws_bytes(1_000_000, 10) == (1 + 4902 + 613) * 8
+
+
 def test_msgstore_struct_matches_header():
     src = open(_cabi.HEADER).read()
     body = src[src.index("typedef struct tgn_msgstore {"):src.index("} tgn_msgstore;")]
